@@ -1,0 +1,228 @@
+"""Seeded synthetic spinning-LiDAR frame pairs with the shapes of the reference datasets.
+
+There is no dataset access, so the bench and the parity tests use ray-cast scenes:
+a ground plane plus seeded random boxes (cars, walls, poles), scanned by a spinning
+sensor (K: 64 beams, N: 32 beams, A: 2x32 beams), frame t1 = same scene after ego motion
+and object motion.  The per-sample dict layout mirrors what the reference's DataLoader
+hands to ``SLIM.forward``:
+
+* ``pcl_full_no_ground_ta``  list[B] of (N_i, 4) f32   -- network input (``kabsch/main_utils.py:247-261``)
+* ``pcl_ta``: ``pcl`` (B, Nmax, 4) NaN-padded, ``pcl_is_valid`` (B, Nmax) bool,
+  ``pillar_coors`` (B, Nmax, 2) int32 padded with -1      (collate: ``torch_dataset_commons.py:380-401``)
+* ``gt.odom_ta_tb`` (B, 4, 4) f64
+
+Ground removal follows ``infer_ground_label_using_cone`` (``torch_dataset_commons.py:133-146``,
+threshold ``liso_config.yml:113-114``); ``pcl_ta`` / ``pillar_coors`` follow ``voxelize_sample``
+(``torch_dataset_commons.py:975-987``) and are computed by :func:`pillar_coors_f64_numpy`, a
+host-side helper kept bit-identical to ``voxelize_pcl`` (``datasets/nuscenes/analyse_boxes.py:6-26``).
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Tuple
+
+import numpy as np
+
+SENSOR_HEIGHT_M = 1.73
+MAX_RANGE_M = 85.0
+
+_BEAM_LAYOUT = {
+    # (number of beams, elevation max deg, elevation min deg)
+    64: (64, 2.0, -24.8),
+    32: (32, 10.67, -30.67),
+}
+
+
+def _scene(rng: np.random.Generator, half_extent: float) -> Dict[str, np.ndarray]:
+    """Random oriented boxes: centre (x,y,z), size (l,w,h), yaw, velocity (vx,vy)."""
+    boxes = []
+
+    def add(n, size_lo, size_hi, moving_frac):
+        for _ in range(n):
+            cx, cy = rng.uniform(-half_extent, half_extent, size=2)
+            l, w, h = rng.uniform(size_lo, size_hi)
+            yaw = rng.uniform(-np.pi, np.pi)
+            # keep a 5 m disc around the sensor free: distance from the origin to the footprint
+            c, s = np.cos(-yaw), np.sin(-yaw)
+            ox, oy = -(c * cx - s * cy), -(s * cx + c * cy)
+            dx, dy = max(abs(ox) - l / 2, 0.0), max(abs(oy) - w / 2, 0.0)
+            if dx * dx + dy * dy < 25.0:
+                continue
+            speed = rng.uniform(2.0, 12.0) if rng.uniform() < moving_frac else 0.0
+            boxes.append([cx, cy, -SENSOR_HEIGHT_M + h / 2, l, w, h, yaw, speed * np.cos(yaw), speed * np.sin(yaw)])
+
+    add(90, (3.5, 1.6, 1.4), (5.5, 2.1, 2.0), 0.35)  # cars
+    add(60, (8.0, 0.4, 2.5), (30.0, 1.0, 7.0), 0.0)  # walls / facades
+    add(120, (0.2, 0.2, 2.0), (0.6, 0.6, 6.0), 0.0)  # poles / trunks
+    add(80, (1.0, 1.0, 1.0), (3.5, 3.5, 4.0), 0.0)  # bushes / clutter
+    # vegetation height field (1.5 m cells over +-120 m): ground hits inside a vegetated cell
+    # return from a random height inside the canopy instead of from the ground
+    veg = rng.uniform(0.3, 3.0, size=(160, 160)) * (rng.uniform(size=(160, 160)) < 0.45)
+    return {"boxes": np.asarray(boxes, dtype=np.float64), "veg": veg}
+
+
+def _ray_dirs(beams: int, n_azimuth: int, dual: bool) -> np.ndarray:
+    nb, emax, emin = _BEAM_LAYOUT[beams]
+    elev = np.deg2rad(np.linspace(emax, emin, nb))
+    az = np.linspace(-np.pi, np.pi, n_azimuth, endpoint=False)
+    if dual:  # AV2: two stacked 32-beam sensors, second one offset by half a step
+        elev = np.concatenate([elev, elev + np.deg2rad(0.4)])
+    ce, se = np.cos(elev), np.sin(elev)
+    d = np.stack(
+        [np.outer(np.cos(az), ce), np.outer(np.sin(az), ce), np.broadcast_to(se, (n_azimuth, elev.size))], axis=-1
+    )
+    return d.reshape(-1, 3)
+
+
+def _cast(dirs: np.ndarray, n_rows: int, boxes: np.ndarray, veg: np.ndarray, veg_T: np.ndarray, rng: np.random.Generator) -> np.ndarray:
+    """Nearest hit of each ray (origin 0) with ground/vegetation and the boxes -> (N,4) f32.
+
+    ``veg_T`` maps sensor-frame xy to the (static) world frame of the vegetation field.
+    """
+    n = dirs.shape[0]
+    t_best = np.full(n, np.inf)
+    dz = dirs[:, 2]
+    down = dz < -1e-6
+    t_ground = np.where(down, -SENSOR_HEIGHT_M / np.where(down, dz, -1.0), np.inf)
+    gx = dirs[:, 0] * np.where(down, t_ground, 0.0)
+    gy = dirs[:, 1] * np.where(down, t_ground, 0.0)
+    wx = veg_T[0, 0] * gx + veg_T[0, 1] * gy + veg_T[0, 3]
+    wy = veg_T[1, 0] * gx + veg_T[1, 1] * gy + veg_T[1, 3]
+    ci = np.clip(((wx + 120.0) / 1.5).astype(np.int64), 0, veg.shape[0] - 1)
+    cj = np.clip(((wy + 120.0) / 1.5).astype(np.int64), 0, veg.shape[1] - 1)
+    hveg = veg[ci, cj] * rng.uniform(0.0, 1.0, size=n)
+    # move the return back along the ray so that it sits hveg above the ground
+    t_ground = np.where(down, (-SENSOR_HEIGHT_M + hveg) / np.where(down, dz, -1.0), np.inf)
+    t_best = np.minimum(t_best, t_ground)
+    # rays are laid out (azimuth-major, beam-minor); each box only sees a small azimuth interval
+    n_rows = int(n_rows)
+    n_az = n // n_rows
+    for b in boxes:
+        c, s = np.cos(b[6]), np.sin(b[6])
+        hl, hw = b[3] / 2, b[4] / 2
+        corners = np.array([[hl, hw], [hl, -hw], [-hl, -hw], [-hl, hw]])
+        cxy = corners @ np.array([[c, s], [-s, c]]) + b[:2]
+        ang = np.arctan2(cxy[:, 1], cxy[:, 0])
+        a0 = np.arctan2(b[1], b[0])
+        rel = np.mod(ang - a0 + np.pi, 2 * np.pi) - np.pi
+        lo = a0 + rel.min() - 0.01
+        hi = a0 + rel.max() + 0.01
+        i0 = int(np.floor((lo + np.pi) / (2 * np.pi) * n_az))
+        i1 = int(np.ceil((hi + np.pi) / (2 * np.pi) * n_az)) + 1
+        az_idx = np.arange(i0, i1) % n_az
+        ridx = (az_idx[:, None] * n_rows + np.arange(n_rows)[None, :]).reshape(-1)
+        dsub = dirs[ridx]
+        c, s = np.cos(-b[6]), np.sin(-b[6])
+        # ray in box frame
+        ox, oy, oz = -b[0], -b[1], -b[2]
+        o = np.array([c * ox - s * oy, s * ox + c * oy, oz])
+        d = np.stack([c * dsub[:, 0] - s * dsub[:, 1], s * dsub[:, 0] + c * dsub[:, 1], dsub[:, 2]], axis=-1)
+        half = b[3:6] / 2
+        with np.errstate(divide="ignore", invalid="ignore"):
+            inv = 1.0 / d
+            t1 = (-half - o) * inv
+            t2 = (half - o) * inv
+        tmin = np.nanmax(np.minimum(t1, t2), axis=-1)
+        tmax = np.nanmin(np.maximum(t1, t2), axis=-1)
+        hit = (tmax >= np.maximum(tmin, 0.0)) & (tmin > 0.5)
+        cur = t_best[ridx]
+        t_best[ridx] = np.where(hit & (tmin < cur), tmin, cur)
+    ok = np.isfinite(t_best) & (t_best < MAX_RANGE_M)
+    t = t_best[ok] + rng.normal(0.0, 0.02, size=int(ok.sum()))
+    pts = dirs[ok] * t[:, None]
+    inten = rng.uniform(0.0, 1.0, size=(pts.shape[0], 1))
+    return np.concatenate([pts, inten], axis=-1).astype(np.float32)
+
+
+def ground_mask_cone(pcl: np.ndarray, cone_z_threshold_m: float = -1.5, cone_angle_deg: float = 0.8) -> np.ndarray:
+    """``infer_ground_label_using_cone`` (``torch_dataset_commons.py:133-146``)."""
+    cone_angle = cone_angle_deg / 180.0 * np.pi
+    d_xy = np.linalg.norm(pcl[..., 0:2], axis=-1)
+    return pcl[..., 2] < cone_z_threshold_m + np.tan(cone_angle) * d_xy
+
+
+def pillar_coors_f64_numpy(pcl: np.ndarray, bev_range_m, grid_size, height_range_m=(-2.0, 1.0)):
+    """Dataset-side point->pillar map, identical arithmetic to ``voxelize_pcl`` + ``voxelize_sample``.
+
+    float32 points promoted against a float64 range array, ``astype(int32)`` truncation toward
+    zero, strict ``zmin < z < zmax`` height filter.  Returns (coors (N,2) int32, valid (N,) bool).
+    """
+    rng_m = np.append(np.asarray(bev_range_m, dtype=np.float64), 1000.0)
+    gsz = np.append(np.asarray(grid_size, dtype=np.int64), 1)
+    c = (pcl[:, :3] + 0.5 * rng_m) / rng_m
+    c = (c * gsz).astype(np.int32)
+    ok = (
+        (0 <= c[:, 0]) & (0 <= c[:, 1]) & (0 <= c[:, 2]) & (c[:, 0] < gsz[0]) & (c[:, 1] < gsz[1]) & (c[:, 2] < gsz[2])
+    )
+    ok &= (height_range_m[0] < pcl[:, 2]) & (pcl[:, 2] < height_range_m[1])
+    return c[:, :2], ok
+
+
+def _ego_motion(rng: np.random.Generator) -> np.ndarray:
+    yaw = np.deg2rad(rng.uniform(-2.0, 2.0))
+    T = np.eye(4)
+    T[:2, :2] = [[np.cos(yaw), -np.sin(yaw)], [np.sin(yaw), np.cos(yaw)]]
+    T[:2, 3] = [rng.uniform(0.6, 1.4), rng.uniform(-0.05, 0.05)]
+    return T
+
+
+def make_frame_pair(workload: Dict[str, Any], seed: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Return (full no-ground cloud t0, same t1, odom_t0_t1 4x4 f64) for one pair."""
+    rng = np.random.default_rng(seed)
+    bev = float(workload["bev_range_m"][0])
+    beams = workload["beams"]
+    dual = workload.get("dual", False)
+    scene = _scene(rng, bev / 2 + 5.0)
+    n_target = int(workload["n_points"])
+    rows = _BEAM_LAYOUT[beams][0] * (2 if dual else 1)
+
+    def frame(boxes, n_az, noise_rng, veg_T=np.eye(4)):
+        pts = _cast(_ray_dirs(beams, n_az, dual), rows, boxes, scene["veg"], veg_T, noise_rng)
+        return pts[~ground_mask_cone(pts)]
+
+    # calibrate azimuth resolution so the ground-free cloud has about n_target points
+    n_az = max(64, int(2.5 * n_target / rows))
+    probe = frame(scene["boxes"], n_az // 8, np.random.default_rng(seed + 7))
+    keep_per_az = max(probe.shape[0], 1) / (n_az // 8)
+    n_az = max(64, int(round(n_target / keep_per_az)))
+    pc0 = frame(scene["boxes"], n_az, rng)
+
+    odom = _ego_motion(rng)  # pose of sensor at t1 expressed in t0
+    boxes1 = scene["boxes"].copy()
+    dt = 0.1
+    boxes1[:, 0] += boxes1[:, 7] * dt
+    boxes1[:, 1] += boxes1[:, 8] * dt
+    inv = np.linalg.inv(odom)
+    ctr = np.concatenate([boxes1[:, :3], np.ones((boxes1.shape[0], 1))], axis=-1) @ inv.T
+    boxes1[:, :3] = ctr[:, :3]
+    boxes1[:, 6] -= np.arctan2(odom[1, 0], odom[0, 0])
+    pc1 = frame(boxes1, n_az, rng, odom)
+    return pc0, pc1, odom
+
+
+def make_sample_dicts(workload: Dict[str, Any], seeds: List[int], as_torch: bool = True):
+    """Batch of pairs in the reference's collated layout -> (sample_data_t0, sample_data_t1)."""
+    import torch
+
+    bev, grid = workload["bev_range_m"], workload["img_grid_size"]
+    per_t: List[Dict[str, list]] = [dict(full=[], pcl=[], coors=[], odom=[]) for _ in range(2)]
+    for s in seeds:
+        pc0, pc1, odom = make_frame_pair(workload, s)
+        for t, (pc, od) in enumerate(((pc0, odom), (pc1, np.linalg.inv(odom)))):
+            coors, ok = pillar_coors_f64_numpy(pc, bev, grid)
+            per_t[t]["full"].append(torch.from_numpy(pc))
+            per_t[t]["pcl"].append(torch.from_numpy(pc[ok]))
+            per_t[t]["coors"].append(torch.from_numpy(coors[ok]))
+            per_t[t]["odom"].append(torch.from_numpy(od))
+    out = []
+    for t in range(2):
+        pcl = torch.nn.utils.rnn.pad_sequence(per_t[t]["pcl"], batch_first=True, padding_value=float("nan"))
+        coors = torch.nn.utils.rnn.pad_sequence(per_t[t]["coors"], batch_first=True, padding_value=-1)
+        valid = torch.logical_not(torch.isnan(pcl).sum(-1))
+        out.append(
+            {
+                "pcl_full_no_ground_ta": per_t[t]["full"],
+                "pcl_ta": {"pcl": pcl, "pcl_is_valid": valid, "pillar_coors": coors},
+                "gt": {"odom_ta_tb": torch.stack(per_t[t]["odom"], 0)},
+            }
+        )
+    return out[0], out[1]
