@@ -1,0 +1,151 @@
+/*
+ * slimb200 -- C ABI of the B200-native (sm_100a) SLIM scene-flow hot path.
+ *
+ * Drop-in boundary for baurst/liso (paths relative to the reference tree):
+ *   stage 1  liso/networks/pcl_to_feature_grid/pcl_to_feature_grid.py:56-107
+ *            (mmcv.ops.Voxelization -> PillarFeatureNet -> PointPillarsScatter x2)
+ *   stage 2  liso/slim/model/raft_code/corr.py:6-56 (CorrBlock: all-pairs volume, pyramid, lookup)
+ *   dataset  liso/datasets/nuscenes/analyse_boxes.py:6-26 (point -> pillar map used by HeadDecoder)
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every device buffer (inputs, outputs, workspace) is owned by
+ *     the caller; the library never allocates or frees device memory and keeps no pointer after
+ *     return.  Host arrays (marked "host") are read before the call returns.
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work (no device sync) and are
+ *     CUDA-graph capturable.
+ *   - return value: 0 success; negative SLIMB200_E_*; positive = cudaError_t of a failed launch.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef SLIMB200_H_
+#define SLIMB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLIMB200_VERSION 100
+
+enum {
+  SLIMB200_OK = 0,
+  SLIMB200_E_INVALID = -1,      /* bad argument (null pointer, negative size, ...) */
+  SLIMB200_E_UNSUPPORTED = -2,  /* shape / dtype outside what the kernels implement */
+  SLIMB200_E_WORKSPACE = -3,    /* workspace too small */
+  SLIMB200_E_ALIGNMENT = -4,    /* pointer or pitch not aligned as required */
+  SLIMB200_E_DRIVER = -5        /* CUDA driver entry point (tensor map encode) unavailable */
+};
+
+#define SLIMB200_MAX_BATCH 64
+#define SLIMB200_MAX_LEVELS 4
+
+/* ------------------------------------------------------------------------------------------
+ * Stage 1: pillar encoder.  Replaces PointsPillarFeatureNetWrapper.extract_pts_feat
+ * (pcl_to_feature_grid.py:86-102): hard voxelisation (mmcv-full==1.7.1 hard_voxelize_forward,
+ * semantics of mmdet3d/core/voxel/voxel_generator.py:137-208, deterministic point-index order),
+ * PillarFeatureNet.forward (mmdet3d/models/voxel_encoders/pillar_encoder.py:93-159), PFNLayer
+ * (voxel_encoders/utils.py:146-182) and both PointPillarsScatter calls
+ * (middle_encoders/pillar_scatter.py:62-102).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  /* fp32 casts of point_cloud_range[:3] and voxel_size, exactly what mmcv hands its kernels */
+  float range_min[3];
+  float voxel_size[3];
+  int32_t grid[3];        /* round((max-min)/voxel): x, y, z cell counts; grid[2] must be 1 */
+  int32_t max_points;     /* 20   (pcl_to_feature_grid.py:25) */
+  int32_t max_voxels;     /* 40000 (pcl_to_feature_grid.py:27) */
+  /* PillarFeatureNet constants (pillar_encoder.py:86-92), fp32 casts of the python floats */
+  float vx, vy, vz;
+  float x_offset, y_offset, z_offset;
+  int32_t c_in;           /* 3 or 4 point channels */
+  int32_t c_out;          /* PFN units, 1..64 (64 // channel_reduction_factor) */
+  int32_t bn_training;    /* 0: running stats; 1: batch statistics (+ running-stat update) */
+  float bn_eps;           /* 1e-3 */
+  float bn_momentum;      /* 0.01 */
+} slimb200_pillar_params;
+
+size_t slimb200_pillar_workspace_bytes(int32_t batch, int64_t total_points,
+                                       const slimb200_pillar_params* p);
+
+/*
+ * points[b]            device (n_points[b], c_in) f32 row-major, 16-byte aligned when c_in == 4
+ * linear_weight        device (c_out, c_in + 6) f32     pfn_layers[0].linear.weight
+ * bn_weight..bn_var    device (c_out) f32               pfn_layers[0].norm.{weight,bias,running_mean,running_var}
+ *                      (running_mean / running_var are updated in place when bn_training)
+ * canvas               device (batch, c_out, grid[0], grid[1]) f32; row = x index, col = y index
+ * occupancy            device (batch, 1, grid[0], grid[1]) f32
+ * optional outputs (may be NULL):
+ *   pillar_counts      device int32[batch + 1]: exclusive prefix of kept pillars per sample
+ *   coors_out          device int32 (>= sum kept pillars, 4): (b, z=0, x index, y index) rows in
+ *                      first-appearance order per sample (== voxelize() of the reference, :56-84)
+ *   num_points_out     device int32 (>= sum kept pillars)
+ *   voxels_out         device f32 (>= sum kept pillars, max_points, c_in), zero padded
+ *   pt2pillar_out      device int32 (total_points): row in coors_out of every stored point, else -1
+ */
+int slimb200_pillar_encode(const float* const* points /*host[batch]*/,
+                           const int32_t* n_points /*host[batch]*/, int32_t batch,
+                           const slimb200_pillar_params* p, const float* linear_weight,
+                           const float* bn_weight, const float* bn_bias, float* bn_running_mean,
+                           float* bn_running_var, float* canvas, float* occupancy,
+                           int32_t* pillar_counts, int32_t* coors_out, int32_t* num_points_out,
+                           float* voxels_out, int32_t* pt2pillar_out, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
+/* Dataset-side point -> pillar map (voxelize_pcl + voxelize_sample, analyse_boxes.py:6-26,
+ * torch_dataset_commons.py:975-987): coors = int32_trunc(((p + R/2) / R) * G) in float64, valid =
+ * in range && zmin < z < zmax.  pts (n, c_in) f32; coors (n, 2) int32; valid (n) uint8. */
+int slimb200_pillar_coors_f64(const float* pts, int64_t n, int32_t c_in, double range_x,
+                              double range_y, int32_t grid_x, int32_t grid_y, float z_min,
+                              float z_max, int32_t* coors, uint8_t* valid, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage 2: all-pairs correlation pyramid + lookup.  Replaces CorrBlock.__init__ / CorrBlock.corr
+ * (corr.py:7-21,48-56) and CorrBlock.__call__ + bilinear_sampler (corr.py:23-46,
+ * raft_code/utils.py:15-29).
+ *
+ * Pyramid storage: one row per source pixel, all levels side by side:
+ *   pyramid[b][i][level_offset[l] + r * w_l + c],  row pitch `pitch` elements (multiple of 64),
+ *   h_0 = h, w_0 = w, h_{l+1} = h_l / 2 (floor), level_offset[l] = sum_{k<l} h_k * w_k.
+ * Level l as the reference exposes it (corr_pyramid[l], shape (B*h*w, 1, h_l, w_l)) is the strided
+ * view base + level_offset[l] with strides (pitch, -, w_l, 1).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t batch, dim, h, w, levels;
+  int32_t level_h[SLIMB200_MAX_LEVELS];
+  int32_t level_w[SLIMB200_MAX_LEVELS];
+  int32_t level_offset[SLIMB200_MAX_LEVELS];
+  int32_t n_cols;   /* sum h_l * w_l */
+  int32_t pitch;    /* elements per pyramid row */
+} slimb200_corr_layout;
+
+enum { SLIMB200_DTYPE_F32 = 0, SLIMB200_DTYPE_BF16 = 1 };
+
+/* fills `out` for (batch, dim, h, w, levels); returns 0 or a negative error */
+int slimb200_corr_layout_init(int32_t batch, int32_t dim, int32_t h, int32_t w, int32_t levels,
+                              slimb200_corr_layout* out);
+size_t slimb200_corr_workspace_bytes(const slimb200_corr_layout* L);
+size_t slimb200_corr_pyramid_bytes(const slimb200_corr_layout* L, int32_t store_dtype);
+
+/* fmap1, fmap2: device (batch, dim, h, w) f32 contiguous (dim == 128).
+ * pyramid: device bf16, slimb200_corr_pyramid_bytes() bytes, 128-byte aligned.
+ * Computes pyramid[b][i][j] = bf16( sum_d f1[b,d,i] * pool_l(f2)[b,d,j] / sqrt(dim) ) with bf16
+ * operands and fp32 accumulation on the tcgen05 tensor cores (pooling folded into the operand:
+ * avg_pool(corr) == corr(avg_pool(f2)) by linearity). */
+int slimb200_corr_build(const float* fmap1, const float* fmap2, const slimb200_corr_layout* L,
+                        int32_t store_dtype, void* pyramid, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+/* coords: device (batch, 2, h, w) f32, channel 0 = x (column), 1 = y (row).
+ * out:    device (batch, levels * (2r+1)^2, h, w) f32 contiguous, channel k = l*(2r+1)^2 + i*(2r+1) + j
+ *         sampled at (x / 2^l + i - r, y / 2^l + j - r), bilinear, zeros outside, align_corners. */
+int slimb200_corr_lookup(const void* pyramid, int32_t pyramid_dtype, const slimb200_corr_layout* L,
+                         const float* coords, int32_t radius, float* out, void* stream);
+
+const char* slimb200_strerror(int code);
+int slimb200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLIMB200_H_ */

@@ -1,0 +1,123 @@
+"""ctypes binding of ``libslimb200.so`` (the C ABI declared in ``include/slimb200.h``).
+
+The library is the product path.  There is no fallback: if the shared object is missing, or a
+call is made without a CUDA device, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libslimb200.so")
+
+MAX_BATCH = 64
+MAX_LEVELS = 4
+DTYPE_F32, DTYPE_BF16 = 0, 1
+
+
+class PillarParams(C.Structure):
+    _fields_ = [
+        ("range_min", C.c_float * 3),
+        ("voxel_size", C.c_float * 3),
+        ("grid", C.c_int32 * 3),
+        ("max_points", C.c_int32),
+        ("max_voxels", C.c_int32),
+        ("vx", C.c_float),
+        ("vy", C.c_float),
+        ("vz", C.c_float),
+        ("x_offset", C.c_float),
+        ("y_offset", C.c_float),
+        ("z_offset", C.c_float),
+        ("c_in", C.c_int32),
+        ("c_out", C.c_int32),
+        ("bn_training", C.c_int32),
+        ("bn_eps", C.c_float),
+        ("bn_momentum", C.c_float),
+    ]
+
+
+class CorrLayout(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32),
+        ("dim", C.c_int32),
+        ("h", C.c_int32),
+        ("w", C.c_int32),
+        ("levels", C.c_int32),
+        ("level_h", C.c_int32 * MAX_LEVELS),
+        ("level_w", C.c_int32 * MAX_LEVELS),
+        ("level_offset", C.c_int32 * MAX_LEVELS),
+        ("n_cols", C.c_int32),
+        ("pitch", C.c_int32),
+    ]
+
+
+# every symbol include/slimb200.h declares: (restype, argtypes)
+SYMBOLS = {
+    "slimb200_pillar_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int64, C.POINTER(PillarParams)]),
+    "slimb200_pillar_encode": (
+        C.c_int,
+        [C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32, C.POINTER(PillarParams)]
+        + [C.c_void_p] * 12 + [C.c_void_p, C.c_size_t, C.c_void_p],
+    ),
+    "slimb200_pillar_coors_f64": (
+        C.c_int,
+        [C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_float, C.c_float,
+         C.c_void_p, C.c_void_p, C.c_void_p],
+    ),
+    "slimb200_corr_layout_init": (C.c_int, [C.c_int32] * 5 + [C.POINTER(CorrLayout)]),
+    "slimb200_corr_workspace_bytes": (C.c_size_t, [C.POINTER(CorrLayout)]),
+    "slimb200_corr_pyramid_bytes": (C.c_size_t, [C.POINTER(CorrLayout), C.c_int32]),
+    "slimb200_corr_build": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.POINTER(CorrLayout), C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p],
+    ),
+    "slimb200_corr_lookup": (
+        C.c_int,
+        [C.c_void_p, C.c_int32, C.POINTER(CorrLayout), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p],
+    ),
+    "slimb200_strerror": (C.c_char_p, [C.c_int]),
+    "slimb200_version": (C.c_int, []),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libslimb200.so is missing (%s). Build it with `python -m liso_b200.build`; "
+            "the SLIM hot path has no CPU or PyTorch fallback." % LIB_PATH
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().slimb200_strerror(rc)
+        raise RuntimeError("%s (code %d)" % (msg.decode() if msg else "slimb200 error", rc))
+
+
+def current_stream_ptr():
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "slimb200 kernels run on CUDA (sm_100a) only; got a %s tensor. There is no CPU fallback." % t.device
+            )

@@ -1,0 +1,499 @@
+// Stage 2a of the SLIM hot path on B200: all-pairs BEV correlation volume + pyramid.
+//
+// Replaces CorrBlock.corr and CorrBlock.__init__ (liso/slim/model/raft_code/corr.py:7-21,48-56):
+//   corr[b,i,j] = sum_d f1[b,d,i] * f2[b,d,j] / sqrt(D), followed by 3x avg_pool2d(2,2).
+//
+// B200 design
+//   k_feat_pack          NCHW fp32 feature maps -> K-major bf16 operands.  The B operand is
+//                        [f2 | pool1(f2) | pool2(f2) | pool3(f2)] (floor 2x2 means, iterated in
+//                        fp32), so the whole pyramid is ONE GEMM: avg_pool(corr) == corr(avg_pool(f2))
+//                        by linearity; no pooling pass ever reads the volume back.
+//   k_corr_gemm_tcgen05  persistent, warp-specialised 128x128x128 tiles:
+//                          warp 0   TMA producer (cp.async.bulk.tensor, 128B swizzle, 4-stage ring)
+//                          warp 1   tcgen05.mma issuer (one elected lane), fp32 accumulators in TMEM,
+//                                   4 accumulator buffers (512 columns) so the epilogue of tile t
+//                                   overlaps the MMAs of tiles t+1..t+3
+//                          warps 2-5 epilogue: tcgen05.ld -> * 1/sqrt(D) -> bf16 -> swizzled smem ->
+//                                   TMA store (double-buffered staging)
+//                        K = D = 128 only, so the kernel is bound by the bf16 store of the volume
+//                        (algorithmic bytes = Nf * Ncols * 2 per sample per direction), not by MMA.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_N = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int DIM = 128;     // feature dimension of the SLIM fnet (raft_mod.py:48)
+constexpr int K_BLOCKS = DIM / BLOCK_K;
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int ACC_STAGES = 4;
+constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;  // 512
+constexpr int OUT_STAGES = 2;
+constexpr int GEMM_THREADS = 192;
+constexpr int EPI_THREADS = 128;
+
+constexpr uint32_t A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+constexpr uint32_t B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;  // 16 KB
+constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr uint32_t OUT_HALF_BYTES = BLOCK_M * 64 * 2;  // 128 rows x 128 B
+constexpr uint32_t OUT_STAGE_BYTES = 2 * OUT_HALF_BYTES;
+constexpr uint32_t SMEM_DATA_BYTES = STAGES * STAGE_BYTES + OUT_STAGES * OUT_STAGE_BYTES;  // 192 KB
+constexpr uint32_t SMEM_BYTES = SMEM_DATA_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+// ---------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, K-major operand, 128-byte swizzle (cute::UMMA::SmemDescriptor):
+//   [0,14) start address >> 4, [16,30) leading byte offset >> 4 (ignored for swizzled K-major, 1),
+//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B between 8-row groups),
+//   [46,48) version = 1 (Blackwell), [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (1 << 4), A = B = bf16 (1 << 7, 1 << 10),
+// both K-major (bits 15, 16 = 0), N >> 3 at [17,23), M >> 4 at [24,29).
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+                           ((uint32_t)(BLOCK_M >> 4) << 24);
+
+struct GemmShape {
+  int batch, m_tiles, n_tiles, total_tiles;
+  float scale;
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+k_corr_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_c, const GemmShape shape) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_out = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t bar_base = smem_base + SMEM_DATA_BYTES;
+  // barrier layout (8 bytes each): full[STAGES], empty[STAGES], tmem_full[ACC], tmem_empty[ACC], tmem ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + ACC_STAGES + s); };
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < ACC_STAGES; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), EPI_THREADS / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_smem), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+
+  const int tiles_per_b = shape.m_tiles * shape.n_tiles;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < shape.total_tiles; t += gridDim.x) {
+        const int b = t / tiles_per_b;
+        const int r = t - b * tiles_per_b;
+        const int m = r / shape.n_tiles, n = r - m * shape.n_tiles;
+        for (int kb = 0; kb < K_BLOCKS; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          tma_load_3d(&map_a, full_bar(stage), sa, kb * BLOCK_K, m * BLOCK_M, b);
+          tma_load_3d(&map_b, full_bar(stage), sa + A_STAGE_BYTES, kb * BLOCK_K, n * BLOCK_N, b);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < shape.total_tiles; t += gridDim.x, ++it) {
+      const int acc = it % ACC_STAGES;
+      const uint32_t acc_phase = (uint32_t)(it / ACC_STAGES) & 1u;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+      for (int kb = 0; kb < K_BLOCKS; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint64_t adesc = make_smem_desc_sw128(sa);
+          const uint64_t bdesc = make_smem_desc_sw128(sa + A_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance the start address by k * 16 elements * 2 B = 32 B (>> 4 = 2) inside the swizzle row
+            umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
+          }
+          tcgen05_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+          if (kb == K_BLOCKS - 1) tcgen05_commit(tfull_bar(acc));
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ================================ epilogue ====================================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;          // accumulator row == TMEM lane
+    const bool store_thread = (threadIdx.x == 64);
+    int it = 0;
+    for (int t = blockIdx.x; t < shape.total_tiles; t += gridDim.x, ++it) {
+      const int b = t / tiles_per_b;
+      const int r = t - b * tiles_per_b;
+      const int m = r / shape.n_tiles, n = r - m * shape.n_tiles;
+      const int acc = it % ACC_STAGES;
+      const uint32_t acc_phase = (uint32_t)(it / ACC_STAGES) & 1u;
+      const uint32_t out_buf = smem_out + (uint32_t)(it % OUT_STAGES) * OUT_STAGE_BYTES;
+      // staging buffer (it % 2) was handed to TMA two tiles ago: wait until it has been read
+      if (store_thread) tma_store_wait_read<OUT_STAGES - 1>();
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+#pragma unroll
+      for (int j = 0; j < BLOCK_N / 32; ++j) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + (uint32_t)(j * 32), v);
+        tmem_ld_wait();
+        const uint32_t half = out_buf + (uint32_t)(j >> 1) * OUT_HALF_BYTES + (uint32_t)row * 128u;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float lo = __uint_as_float(v[c * 8 + 2 * e]) * shape.scale;
+            const float hi = __uint_as_float(v[c * 8 + 2 * e + 1]) * shape.scale;
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk[e]) : "f"(hi), "f"(lo));
+          }
+          const uint32_t chunk = (uint32_t)((j & 1) * 4 + c);
+          const uint32_t dst = half + ((chunk ^ ((uint32_t)row & 7u)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+                       "r"(pk[3])
+                       : "memory");
+        }
+      }
+      // accumulator buffer is drained: hand it back to the MMA warp
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      // make the smem writes visible to the async proxy, then one thread issues the TMA stores
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+      if (store_thread) {
+        tma_store_3d(&map_c, out_buf, n * BLOCK_N, m * BLOCK_M, b);
+        tma_store_3d(&map_c, out_buf + OUT_HALF_BYTES, n * BLOCK_N + 64, m * BLOCK_M, b);
+        tma_store_commit();
+      }
+    }
+    if (store_thread) tma_store_wait_all();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------- operand pack
+template <int L>
+__device__ __forceinline__ float pooled(const float* __restrict__ img, int w, int r, int c) {
+  if constexpr (L == 0) {
+    return __ldg(img + (size_t)r * w + c);
+  } else {
+    // F.avg_pool2d(k=2, s=2): sum in window order (0,0),(0,1),(1,0),(1,1), then / 4  (corr.py:20)
+    float s = pooled<L - 1>(img, w, 2 * r, 2 * c);
+    s += pooled<L - 1>(img, w, 2 * r, 2 * c + 1);
+    s += pooled<L - 1>(img, w, 2 * r + 1, 2 * c);
+    s += pooled<L - 1>(img, w, 2 * r + 1, 2 * c + 1);
+    return s * 0.25f;
+  }
+}
+
+constexpr int PACK_ROWS = 32;
+constexpr int PACK_PITCH = DIM + 8;
+
+// grid.x: row groups of A (ceil(Nf/32)) followed by row groups of B_ext (ceil(Ncols/32)); grid.y: batch
+__global__ void __launch_bounds__(256) k_feat_pack(const float* __restrict__ fmap1, const float* __restrict__ fmap2,
+                                                   const slimb200_corr_layout L, __nv_bfloat16* __restrict__ A,
+                                                   __nv_bfloat16* __restrict__ Bx) {
+  __shared__ __align__(16) __nv_bfloat16 s[PACK_ROWS][PACK_PITCH];
+  const int b = blockIdx.y;
+  const int nf = L.h * L.w;
+  const int groups_a = (nf + PACK_ROWS - 1) / PACK_ROWS;
+  const bool is_a = (int)blockIdx.x < groups_a;
+  const int row0 = (is_a ? blockIdx.x : blockIdx.x - groups_a) * PACK_ROWS;
+  const int n_rows = is_a ? nf : L.n_cols;
+  const int lane = lane_id(), warp = warp_id();
+  const int row = row0 + lane;
+  const float* src = (is_a ? fmap1 : fmap2) + (size_t)b * DIM * nf;
+  if (row < n_rows) {
+    int lvl = 0;
+    if (!is_a) {
+      while (lvl + 1 < L.levels && row >= L.level_offset[lvl + 1]) ++lvl;
+    }
+    const int local = row - (is_a ? 0 : L.level_offset[lvl]);
+    const int wl = is_a ? L.w : L.level_w[lvl];
+    const int r = local / wl, c = local - r * wl;
+#pragma unroll 4
+    for (int i = 0; i < DIM / 8; ++i) {
+      const int d = warp * (DIM / 8) + i;
+      const float* img = src + (size_t)d * nf;
+      float v;
+      switch (lvl) {
+        case 0: v = pooled<0>(img, L.w, r, c); break;
+        case 1: v = pooled<1>(img, L.w, r, c); break;
+        case 2: v = pooled<2>(img, L.w, r, c); break;
+        default: v = pooled<3>(img, L.w, r, c); break;
+      }
+      s[lane][d] = __float2bfloat16_rn(v);
+    }
+  }
+  __syncthreads();
+  __nv_bfloat16* dst = (is_a ? A : Bx) + (size_t)b * n_rows * DIM;
+  for (int qd = threadIdx.x; qd < PACK_ROWS * (DIM / 8); qd += 256) {
+    const int rr = qd / (DIM / 8), ch = qd - rr * (DIM / 8);
+    if (row0 + rr < n_rows) {
+      const uint4 val = *reinterpret_cast<const uint4*>(&s[rr][ch * 8]);
+      *reinterpret_cast<uint4*>(dst + (size_t)(row0 + rr) * DIM + ch * 8) = val;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || !p)
+    return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+// 3-D bf16 tensor map: dims (inner, rows, batch), box (64, 128, 1), 128-byte swizzle
+int make_map(PFN_encodeTiled enc, CUtensorMap* map, void* base, uint64_t inner, uint64_t rows, uint64_t batch,
+             uint64_t row_pitch_elems) {
+  const cuuint64_t dims[3] = {inner, rows, batch};
+  const cuuint64_t strides[2] = {row_pitch_elems * 2, rows * row_pitch_elems * 2};
+  const cuuint32_t box[3] = {64, 128, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? SLIMB200_OK : SLIMB200_E_DRIVER;
+}
+
+}  // namespace
+
+extern "C" int slimb200_corr_layout_init(int32_t batch, int32_t dim, int32_t h, int32_t w, int32_t levels,
+                                         slimb200_corr_layout* out) {
+  if (!out || batch < 1 || h < 1 || w < 1 || levels < 1) return SLIMB200_E_INVALID;
+  if (levels > SLIMB200_MAX_LEVELS || dim != DIM) return SLIMB200_E_UNSUPPORTED;
+  slimb200_corr_layout L{};
+  L.batch = batch;
+  L.dim = dim;
+  L.h = h;
+  L.w = w;
+  L.levels = levels;
+  int hl = h, wl = w, off = 0;
+  for (int l = 0; l < levels; ++l) {
+    if (hl < 1 || wl < 1) return SLIMB200_E_UNSUPPORTED;
+    L.level_h[l] = hl;
+    L.level_w[l] = wl;
+    L.level_offset[l] = off;
+    off += hl * wl;
+    hl /= 2;
+    wl /= 2;
+  }
+  L.n_cols = off;
+  L.pitch = (off + 63) / 64 * 64;
+  *out = L;
+  return SLIMB200_OK;
+}
+
+extern "C" size_t slimb200_corr_pyramid_bytes(const slimb200_corr_layout* L, int32_t store_dtype) {
+  if (!L) return 0;
+  const size_t es = store_dtype == SLIMB200_DTYPE_BF16 ? 2 : 4;
+  return (size_t)L->batch * L->h * L->w * L->pitch * es;
+}
+
+extern "C" size_t slimb200_corr_workspace_bytes(const slimb200_corr_layout* L) {
+  if (!L) return 0;
+  WorkspaceCarver w(nullptr);
+  w.take<__nv_bfloat16>((size_t)L->batch * L->h * L->w * DIM);
+  w.take<__nv_bfloat16>((size_t)L->batch * L->n_cols * DIM);
+  return w.used();
+}
+
+extern "C" int slimb200_corr_build(const float* fmap1, const float* fmap2, const slimb200_corr_layout* L,
+                                   int32_t store_dtype, void* pyramid, void* workspace, size_t workspace_bytes,
+                                   void* stream_) {
+  if (!fmap1 || !fmap2 || !L || !pyramid || !workspace) return SLIMB200_E_INVALID;
+  if (store_dtype != SLIMB200_DTYPE_BF16 || L->dim != DIM) return SLIMB200_E_UNSUPPORTED;
+  if (workspace_bytes < slimb200_corr_workspace_bytes(L)) return SLIMB200_E_WORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(pyramid) & 127) || (reinterpret_cast<uintptr_t>(workspace) & 255))
+    return SLIMB200_E_ALIGNMENT;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int nf = L->h * L->w;
+  WorkspaceCarver w(workspace);
+  __nv_bfloat16* A = w.take<__nv_bfloat16>((size_t)L->batch * nf * DIM);
+  __nv_bfloat16* Bx = w.take<__nv_bfloat16>((size_t)L->batch * L->n_cols * DIM);
+
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return SLIMB200_E_DRIVER;
+  CUtensorMap map_a, map_b, map_c;
+  int rc;
+  if ((rc = make_map(enc, &map_a, A, DIM, nf, L->batch, DIM)) != SLIMB200_OK) return rc;
+  if ((rc = make_map(enc, &map_b, Bx, DIM, L->n_cols, L->batch, DIM)) != SLIMB200_OK) return rc;
+  if ((rc = make_map(enc, &map_c, pyramid, L->n_cols, nf, L->batch, L->pitch)) != SLIMB200_OK) return rc;
+
+  {
+    const int groups = (nf + PACK_ROWS - 1) / PACK_ROWS + (L->n_cols + PACK_ROWS - 1) / PACK_ROWS;
+    k_feat_pack<<<dim3(groups, L->batch), 256, 0, stream>>>(fmap1, fmap2, *L, A, Bx);
+    SLIMB200_LAUNCH_CHECK();
+  }
+  GemmShape shape;
+  shape.batch = L->batch;
+  shape.m_tiles = (nf + BLOCK_M - 1) / BLOCK_M;
+  shape.n_tiles = (L->n_cols + BLOCK_N - 1) / BLOCK_N;
+  shape.total_tiles = shape.batch * shape.m_tiles * shape.n_tiles;
+  shape.scale = 1.0f / sqrtf((float)L->dim);
+
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    SLIMB200_CUDA_TRY(cudaGetDevice(&dev));
+    SLIMB200_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    SLIMB200_CUDA_TRY(cudaFuncSetAttribute(k_corr_gemm_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  }
+  const int grid = shape.total_tiles < n_sm ? shape.total_tiles : n_sm;
+  k_corr_gemm_tcgen05<<<grid, GEMM_THREADS, SMEM_BYTES, stream>>>(map_a, map_b, map_c, shape);
+  SLIMB200_LAUNCH_CHECK();
+  return SLIMB200_OK;
+}

@@ -1,0 +1,133 @@
+"""B200 drop-in for ``liso/slim/model/raft_code/corr.py`` and ``raft_code/utils.py``.
+
+``CorrBlock(fmap1, fmap2, num_levels=4, radius=4)`` is constructed once per direction per
+forward (``raft_mod.py:160-165``) and called once per GRU iteration (``:196``), exactly like the
+reference class.  Construction = one operand-pack launch + one persistent tcgen05 GEMM that
+writes the whole 4-level pyramid (bf16) in a single pass; ``__call__`` = one gather launch that
+emits the ``(B, L*(2r+1)^2, h, w)`` fp32 tensor directly.
+
+Differences a caller can observe (documented in DESIGN.md):
+* ``corr_pyramid[l]`` has the reference's shape ``(B*h*w, 1, h_l, w_l)`` but is a bf16 *strided
+  view* into one packed buffer (row pitch ``layout.pitch``).
+* values carry bf16 operand + storage rounding: |err| <= 2^-7 * ||f1_i|| * ||f2_j|| / sqrt(D).
+* forward only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List
+
+import torch
+import torch.nn.functional as F
+
+from .. import _lib
+
+
+def make_layout(batch: int, dim: int, h: int, w: int, levels: int) -> _lib.CorrLayout:
+    L = _lib.CorrLayout()
+    _lib.check(_lib.load().slimb200_corr_layout_init(batch, dim, h, w, levels, C.byref(L)))
+    return L
+
+
+def _level_views(pyramid: torch.Tensor, L: _lib.CorrLayout) -> List[torch.Tensor]:
+    """Expose each level with the reference's shape (B*h*w, 1, h_l, w_l) as a strided view."""
+    nf = L.h * L.w
+    flat = pyramid.view(-1)
+    views = []
+    for l in range(L.levels):
+        hl, wl = L.level_h[l], L.level_w[l]
+        views.append(flat.as_strided((L.batch * nf, 1, hl, wl), (L.pitch, hl * wl, wl, 1), L.level_offset[l]))
+    return views
+
+
+def lookup(pyramid: torch.Tensor, L: _lib.CorrLayout, coords: torch.Tensor, radius: int) -> torch.Tensor:
+    """``slimb200_corr_lookup`` on a packed pyramid (bf16 or fp32)."""
+    _lib.require_cuda(pyramid, coords)
+    if coords.shape != (L.batch, 2, L.h, L.w):
+        raise ValueError("coords must be (B,2,h,w) = %s, got %s" % ((L.batch, 2, L.h, L.w), tuple(coords.shape)))
+    coords = coords.detach()
+    if coords.dtype != torch.float32 or not coords.is_contiguous():
+        coords = coords.float().contiguous()
+    n_ch = L.levels * (2 * radius + 1) ** 2
+    out = torch.empty((L.batch, n_ch, L.h, L.w), dtype=torch.float32, device=coords.device)
+    dt = _lib.DTYPE_BF16 if pyramid.dtype == torch.bfloat16 else _lib.DTYPE_F32
+    if pyramid.dtype not in (torch.bfloat16, torch.float32):
+        raise ValueError("pyramid dtype must be bfloat16 or float32")
+    _lib.check(_lib.load().slimb200_corr_lookup(pyramid.data_ptr(), dt, C.byref(L), coords.data_ptr(), radius,
+                                                out.data_ptr(), _lib.current_stream_ptr()))
+    return out
+
+
+def pack_pyramid_f32(levels: List[torch.Tensor], L: _lib.CorrLayout) -> torch.Tensor:
+    """Pack reference-shaped fp32 levels (B*h*w,1,h_l,w_l) into the library's row layout (tests)."""
+    nf = L.h * L.w
+    buf = torch.zeros((L.batch * nf, L.pitch), dtype=torch.float32, device=levels[0].device)
+    for l, lv in enumerate(levels):
+        buf[:, L.level_offset[l]:L.level_offset[l] + L.level_h[l] * L.level_w[l]] = lv.reshape(L.batch * nf, -1)
+    return buf
+
+
+class CorrBlock:
+    def __init__(self, fmap1: torch.Tensor, fmap2: torch.Tensor, num_levels: int = 4, radius: int = 4):
+        self.num_levels = num_levels
+        self.radius = radius
+        _lib.require_cuda(fmap1, fmap2)
+        if torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad):
+            raise RuntimeError("liso_b200 CorrBlock is forward-only (flow export): call it under torch.no_grad()")
+        if fmap1.shape != fmap2.shape or fmap1.dim() != 4:
+            raise ValueError("fmap1/fmap2 must both be (B, D, h, w)")
+        B, D, h, w = fmap1.shape
+        lib = _lib.load()
+        self.layout = make_layout(B, D, h, w, num_levels)
+        f1 = fmap1.detach().float().contiguous()
+        f2 = fmap2.detach().float().contiguous()
+        L = self.layout
+        self.pyramid = torch.empty((B * h * w, L.pitch), dtype=torch.bfloat16, device=f1.device)
+        ws = torch.empty(lib.slimb200_corr_workspace_bytes(C.byref(L)), dtype=torch.uint8, device=f1.device)
+        _lib.check(lib.slimb200_corr_build(f1.data_ptr(), f2.data_ptr(), C.byref(L), _lib.DTYPE_BF16,
+                                           self.pyramid.data_ptr(), ws.data_ptr(), ws.numel(),
+                                           _lib.current_stream_ptr()))
+        self.corr_pyramid = _level_views(self.pyramid, L)
+
+    def __call__(self, coords: torch.Tensor) -> torch.Tensor:
+        return lookup(self.pyramid, self.layout, coords, self.radius)
+
+    @staticmethod
+    def corr(fmap1: torch.Tensor, fmap2: torch.Tensor) -> torch.Tensor:
+        """All-pairs volume with the reference's return shape (B, h, w, 1, h, w), fp32 values."""
+        B, _, h, w = fmap1.shape
+        blk = CorrBlock(fmap1, fmap2, num_levels=1, radius=0)
+        return blk.corr_pyramid[0].float().reshape(B, h, w, 1, h, w)
+
+
+# ---------------------------------------------------------------- raft_code/utils.py (stock PyTorch)
+def bilinear_sampler(img, coords, mode="bilinear", mask=False):
+    """Pixel-coordinate wrapper around ``F.grid_sample`` (``raft_code/utils.py:15-29``)."""
+    H, W = img.shape[-2:]
+    xg, yg = coords.split([1, 1], dim=-1)
+    xg = 2 * xg / (W - 1) - 1
+    yg = 2 * yg / (H - 1) - 1
+    out = F.grid_sample(img, torch.cat([xg, yg], dim=-1), align_corners=True)
+    if mask:
+        inside = (xg > -1) & (yg > -1) & (xg < 1) & (yg < 1)
+        return out, inside.float()
+    return out
+
+
+def coords_grid(batch, ht, wd, device):
+    """channel 0 = x (column), channel 1 = y (row) (``raft_code/utils.py:32-37``, ``raft_mod.py:134-135``)."""
+    ys, xs = torch.meshgrid(torch.arange(ht, device=device), torch.arange(wd, device=device), indexing="ij")
+    return torch.stack([xs, ys], dim=0).float()[None].repeat(batch, 1, 1, 1)
+
+
+def initialize_flow(img, downscale_factor=8):
+    n, _, H, W = img.shape
+    return coords_grid(n, H // downscale_factor, W // downscale_factor, device=img.device)
+
+
+def upflow_n(flow, n=8, mode="bilinear"):
+    return n * F.interpolate(flow, size=(n * flow.shape[2], n * flow.shape[3]), mode=mode, align_corners=True)
+
+
+def uplogits_n(logits, n=8, mode="bilinear"):
+    return F.interpolate(logits, size=(n * logits.shape[2], n * logits.shape[3]), mode=mode, align_corners=True)

@@ -1,0 +1,86 @@
+"""Flow-export driver: the workload the SLIM hot path serves (reference ``liso/slim/experiment.py``).
+
+* frame pairs are independent; the reference shards them over worker processes with
+  ``sample_idx % world_size == worker_id`` (``experiment.py:330-332,351-353``) -> :func:`shard_indices`
+* per pair it keeps the last-iteration BEV ``static_flow`` (H,W,2) and ``dynamicness`` (H,W) of both
+  directions and writes them with ``np.savez_compressed`` (``experiment.py:391-399,459-471``)
+  -> :func:`export_arrays`, :func:`save_npz`
+* there is no communication in the reference; here one process drives one B200 and a single
+  collective at the end sums counters / timings (NCCL over NVLink on GPUs, gloo in CPU tests)
+  -> :func:`reduce_counters`
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, Iterable, List, Optional
+
+import numpy as np
+import torch
+
+
+def shard_indices(n_samples: int, world_size: int, worker_id: int) -> List[int]:
+    """Indices this worker owns: the reference's modulo rule (``experiment.py:330-332``)."""
+    if world_size < 1 or not (0 <= worker_id < world_size):
+        raise ValueError("bad shard spec world_size=%d worker_id=%d" % (world_size, worker_id))
+    return [i for i in range(n_samples) if i % world_size == worker_id]
+
+
+def export_arrays(preds_fw, preds_bw, threshold, batch_index: int = 0) -> Dict[str, torch.Tensor]:
+    """The tensors the reference saves for one pair (``experiment.py:391-402``), still on device."""
+    fw, bw = preds_fw[-1].modified_network_output, preds_bw[-1].modified_network_output
+    return {
+        "bev_raw_flow_t0_t1": fw.static_flow[batch_index],
+        "bev_raw_flow_t1_t0": bw.static_flow[batch_index],
+        "bev_dynamicness_t0_t1": fw.dynamicness[batch_index],
+        "bev_dynamicness_t1_t0": bw.dynamicness[batch_index],
+        "static_threshold": torch.as_tensor(threshold),
+    }
+
+
+def save_npz(target_file: str, arrays: Dict[str, torch.Tensor], bev_range_m, skip_existing: bool = False) -> bool:
+    """Write one pair like ``slim_inference_and_save_result`` (``experiment.py:459-471``)."""
+    if skip_existing and os.path.exists(target_file):
+        return False
+    out = {k: v.detach().cpu().numpy() for k, v in arrays.items()}
+    out["bev_range_m"] = np.asarray(bev_range_m)
+    os.makedirs(os.path.dirname(os.path.abspath(target_file)), exist_ok=True)
+    np.savez_compressed(target_file, **out)
+    return True
+
+
+def reduce_counters(local: Dict[str, float], device: Optional[torch.device] = None) -> Dict[str, float]:
+    """Sum per-rank counters over the default process group (no-op without one).
+
+    Keys ending in ``_max`` are reduced with MAX (timings), everything else with SUM."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return dict(local)
+    keys = sorted(local)
+    dev = device if device is not None else torch.device("cpu")
+    sums = torch.tensor([float(local[k]) for k in keys if not k.endswith("_max")], dtype=torch.float64, device=dev)
+    maxs = torch.tensor([float(local[k]) for k in keys if k.endswith("_max")], dtype=torch.float64, device=dev)
+    if sums.numel():
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    if maxs.numel():
+        dist.all_reduce(maxs, op=dist.ReduceOp.MAX)
+    out, i, j = {}, 0, 0
+    for k in keys:
+        if k.endswith("_max"):
+            out[k] = float(maxs[j])
+            j += 1
+        else:
+            out[k] = float(sums[i])
+            i += 1
+    return out
+
+
+def iterate_batches(indices: Iterable[int], batch_size: int) -> Iterable[List[int]]:
+    cur: List[int] = []
+    for i in indices:
+        cur.append(i)
+        if len(cur) == batch_size:
+            yield cur
+            cur = []
+    if cur:
+        yield cur

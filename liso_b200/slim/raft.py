@@ -1,0 +1,216 @@
+"""RAFT wiring of SLIM around the two B200 kernels stages (reference ``liso/slim/model/raft_mod.py``).
+
+Only the pillar encoder (``pp_layer``) and the correlation block are custom CUDA; the feature /
+context encoders and the ConvGRU update block stay stock PyTorch (cuDNN) as the scope asks.  Their
+module and parameter names follow the reference (``extractor.py``, ``update.py``) so that a
+reference checkpoint loads with ``strict=True`` (``experiment.py:221-223``).
+"""
+from __future__ import annotations
+
+from typing import List
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from ..networks.pcl_to_feature_grid import PointsPillarFeatureNetWrapper
+from .corr import CorrBlock, initialize_flow, uplogits_n, upflow_n
+
+
+def _make_norm(kind: str, channels: int) -> nn.Module:
+    if kind == "instance_affine":
+        return nn.InstanceNorm2d(channels, eps=1e-3, affine=True)
+    if kind == "none":
+        return nn.Sequential()
+    if kind == "instance":
+        return nn.InstanceNorm2d(channels)
+    if kind == "batch":
+        return nn.BatchNorm2d(channels)
+    if kind == "group":
+        return nn.GroupNorm(num_groups=channels // 8, num_channels=channels)
+    raise ValueError("unknown norm %r" % kind)
+
+
+class ResidualBlock(nn.Module):
+    """``extractor.py:5-68``.  The projection shortcut is created from the *stage's* input width
+    (``dummy_in_filters``), so the second block of a widening stage also gets one (and the
+    reference registers its norm twice: ``norm3`` and ``downsample.1``)."""
+
+    def __init__(self, in_filters, out_filters, dummy_in_filters, norm_fn="group", stride=1):
+        super().__init__()
+        self.conv1 = nn.Conv2d(in_filters, out_filters, kernel_size=3, padding=1, stride=stride)
+        self.conv2 = nn.Conv2d(out_filters, out_filters, kernel_size=3, padding=1)
+        self.relu = nn.ReLU(inplace=True)
+        self.norm1 = _make_norm(norm_fn, out_filters)
+        self.norm2 = _make_norm(norm_fn, out_filters)
+        self.downsample = None
+        if not (stride == 1 and dummy_in_filters == out_filters):
+            self.norm3 = _make_norm(norm_fn, out_filters)
+            self.downsample = nn.Sequential(nn.Conv2d(in_filters, out_filters, kernel_size=1, stride=stride), self.norm3)
+
+    def forward(self, x):
+        y = self.relu(self.norm1(self.conv1(x)))
+        y = self.relu(self.norm2(self.conv2(y)))
+        if self.downsample is not None:
+            x = self.downsample(x)
+        return self.relu(x + y)
+
+
+class SmallEncoder(nn.Module):
+    """``extractor.py:211-297``: 7x7/2 stem, three residual stages (32, 64/2, 96/2), 1x1 head."""
+
+    def __init__(self, output_dim=128, norm_fn="batch", dropout=0.0):
+        super().__init__()
+        self.norm_fn = norm_fn
+        self.norm1 = _make_norm(norm_fn, 32)
+        self.conv1 = nn.Conv2d(64, 32, kernel_size=7, stride=2, padding=3)
+        self.relu1 = nn.ReLU(inplace=True)
+        self.layer1 = self._stage(32, 32, 1)
+        self.layer2 = self._stage(32, 64, 2)
+        self.layer3 = self._stage(64, 96, 2)
+        self.dropout = nn.Dropout2d(p=dropout) if dropout > 0 else None
+        self.conv2 = nn.Conv2d(96, output_dim, kernel_size=1)
+
+    def _stage(self, cin, cout, stride):
+        return nn.Sequential(
+            ResidualBlock(cin, cout, dummy_in_filters=cin, norm_fn=self.norm_fn, stride=stride),
+            ResidualBlock(cout, cout, dummy_in_filters=cin, norm_fn=self.norm_fn, stride=1),
+        )
+
+    def forward(self, x):
+        x = self.relu1(self.norm1(self.conv1(x)))
+        x = self.layer3(self.layer2(self.layer1(x)))
+        x = self.conv2(x)
+        if self.training and self.dropout is not None:
+            x = self.dropout(x)
+        return x
+
+
+class FlowOrClassificationHead(nn.Module):
+    def __init__(self, input_dim=128, hidden_dim=256, out_dims=2):
+        super().__init__()
+        self.conv1 = nn.Conv2d(input_dim, hidden_dim, 3, padding=1)
+        self.conv2 = nn.Conv2d(hidden_dim, out_dims, 3, padding=1)
+        self.relu = nn.ReLU(inplace=True)
+
+    def forward(self, x):
+        return self.conv2(self.relu(self.conv1(x)))
+
+
+class ConvGRU(nn.Module):
+    def __init__(self, hidden_dim=96, input_dim=304):
+        super().__init__()
+        self.convz = nn.Conv2d(input_dim, hidden_dim, 3, padding=1)
+        self.convr = nn.Conv2d(input_dim, hidden_dim, 3, padding=1)
+        self.convq = nn.Conv2d(input_dim, hidden_dim, 3, padding=1)
+
+    def forward(self, h, x):
+        hx = torch.cat([h, x], dim=1)
+        z = torch.sigmoid(self.convz(hx))
+        r = torch.sigmoid(self.convr(hx))
+        q = torch.tanh(self.convq(torch.cat([r * h, x], dim=1)))
+        return (1 - z) * h + z * q
+
+
+class SmallMotionEncoder(nn.Module):
+    """``update.py:41-93`` for ``flow_maps_archi != 'vanilla'`` and no static-aggregation weights."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+        cc = cfg.model.corr_cfg
+        self.conv_stat_corr1 = nn.Conv2d(cc.num_levels * (2 * cc.search_radius + 1) ** 2, 96, 1, padding=0)
+        self.conv_flow1 = nn.Conv2d(2, 64, 7, padding=3)
+        self.conv_flow2 = nn.Conv2d(64, 32, 3, padding=1)
+        self.conv_class1 = nn.Conv2d(4, 64, 7, padding=3)
+        self.conv_class2 = nn.Conv2d(64, 32, 3, padding=1)
+        self.conv = nn.Conv2d(160, 80, 3, padding=1)
+
+    def forward(self, flow, corr, logits):
+        c = F.relu(self.conv_stat_corr1(corr))
+        f = F.relu(self.conv_flow2(F.relu(self.conv_flow1(flow))))
+        lg = F.relu(self.conv_class2(F.relu(self.conv_class1(logits))))
+        out = F.relu(self.conv(torch.cat([c, f, lg], dim=1)))
+        return torch.cat([out, lg, f], dim=1)
+
+
+class SmallUpdateBlock(nn.Module):
+    def __init__(self, cfg, filters=96):
+        super().__init__()
+        if cfg.model.flow_maps_archi == "vanilla" or cfg.model.predict_weight_for_static_aggregation is not False:
+            raise NotImplementedError("only the released SLIM configuration (single flow map, no aggregation weights)")
+        self.cfg = cfg
+        self.filters = filters
+        self.motion_encoder = SmallMotionEncoder(cfg)
+        self.gru = ConvGRU(hidden_dim=filters, input_dim=304)
+        self.static_flow_head = FlowOrClassificationHead(filters, 128, 2)
+        self.classification_head = FlowOrClassificationHead(filters, 128, 4)
+
+    def forward(self, net, inp, corr, flow, logits, weight_logits_for_static_aggregation=None):
+        motion = self.motion_encoder(flow, corr, logits)
+        net = self.gru(net, torch.cat([inp, motion], dim=1))
+        return net, self.static_flow_head(net), self.classification_head(net), None
+
+
+def concat2network_output(logits, static_flow, dynamic_flow):
+    """``HeadDecoder.concat2network_output`` (``head_decoder.py:36-64``): (B,H,W,8) channels-last."""
+    return torch.cat([logits, static_flow, dynamic_flow], dim=1).permute(0, 2, 3, 1)
+
+
+class RAFT(nn.Module):
+    def __init__(self, cfg, head_decoder_fw=None, head_decoder_bw=None):
+        super().__init__()
+        self.cfg = cfg
+        self.slim_cfg = cfg.SLIM
+        m = self.slim_cfg.model
+        self.head_decoder_fw = head_decoder_fw
+        self.head_decoder_bw = head_decoder_bw
+        self.iters = m.num_iters
+        rows = float(cfg.data.bev_range_m[0]) / cfg.data.img_grid_size[0] * m.u_net.final_scale
+        cols = float(cfg.data.bev_range_m[1]) / cfg.data.img_grid_size[1] * m.u_net.final_scale
+        assert rows == cols, "anisotropic BEV resolution is not supported (raft_mod.py:42-45)"
+        self.bev_rows_res_meters_per_fs_pixel = rows
+        self.bev_cols_res_meters_per_fs_pixel = cols
+        if m.corr_cfg.module != "all" or m.feature_downsampling_factor != 8:
+            raise ValueError("only the all-pairs correlation block at 1/8 resolution exists (raft_mod.py:50-58)")
+        self.pp_layer = PointsPillarFeatureNetWrapper(cfg)
+        self.hidden_dim, self.context_dim = 96, 64
+        self.fnet = SmallEncoder(output_dim=128, norm_fn=m.raft_fnet_norm, dropout=m.dropout_rate)
+        self.cnet = SmallEncoder(output_dim=self.hidden_dim + self.context_dim, norm_fn="none", dropout=m.dropout_rate)
+        self.update_block = SmallUpdateBlock(cfg=self.slim_cfg, filters=self.hidden_dim)
+
+    def forward(self, pcl_t0, pcl_t1):
+        img_t0, occ_t0 = self.pp_layer(pcl_t0)
+        img_t1, occ_t1 = self.pp_layer(pcl_t1)
+        aux = {"t0": {"bev_net_input_dbg": occ_t0}, "t1": {"bev_net_input_dbg": occ_t1}}
+        fmap_t0 = self.fnet(img_t0)
+        fmap_t1 = self.fnet(img_t1)
+        fw = self.predict_single_flow_map_and_classes(img_t0, fmap_t0, fmap_t1, self.head_decoder_fw)
+        bw = self.predict_single_flow_map_and_classes(img_t1, fmap_t1, fmap_t0, self.head_decoder_bw)
+        return fw, bw, aux
+
+    def predict_single_flow_map_and_classes(self, img_t0, fmap_t0, fmap_t1, decoder=None) -> List[torch.Tensor]:
+        m = self.slim_cfg.model
+        ds = m.feature_downsampling_factor
+        coords0 = initialize_flow(img_t0, downscale_factor=ds)
+        coords1 = initialize_flow(img_t0, downscale_factor=ds)
+        b, _, h, w = coords0.shape
+        logits = torch.zeros((b, 4, h, w), dtype=torch.float32, device=img_t0.device)
+        correlation = CorrBlock(fmap_t0, fmap_t1, num_levels=m.corr_cfg.num_levels, radius=m.corr_cfg.search_radius)
+        net, inp = torch.split(self.cnet(img_t0), [self.hidden_dim, self.context_dim], dim=1)
+        net, inp = torch.tanh(net), torch.relu(inp)
+        res = torch.tensor([self.bev_rows_res_meters_per_fs_pixel, self.bev_cols_res_meters_per_fs_pixel],
+                           device=inp.device, dtype=inp.dtype)[None, :, None, None]
+        outs = []
+        for _ in range(m.num_iters):
+            coords1 = coords1.detach()
+            logits = logits.detach()
+            corr = correlation(coords1)
+            net, dflow, dlogits, _ = self.update_block(net, inp, corr, coords1 - coords0, logits, None)
+            coords1 = coords1 + dflow
+            logits = logits + dlogits
+            # RAFT (x, y) pixel flow -> (row, col) metres (raft_mod.py:262-266)
+            flow_m = torch.flip(upflow_n(coords1 - coords0, n=ds), dims=[1]) * res
+            outs.append(concat2network_output(uplogits_n(logits, n=ds), flow_m, flow_m))
+        return outs

@@ -1,0 +1,207 @@
+"""SLIM top module around the B200 hot path (reference ``liso/slim/model/slim.py``).
+
+``SLIM(cfg, num_train_samples).forward(sample_data_t0, sample_data_t1, summaries)`` keeps the
+reference signature, sub-module names (``raft_network``, ``head_decoder_fw/bw``,
+``moving_dynamicness_threshold``) and state-dict keys.  The decoder below is the forward /
+export part of ``HeadDecoder`` (``head_decoder.py:66-496``) for the released configuration
+(``output_modification`` defaults, ``liso_config.yml:303-310``), in stock PyTorch.
+
+Two switches exist that the reference does not have; both default to the reference behaviour:
+``decode_iterations`` ("all" | "last") and ``static_aggregation`` (bool).  The flow export only
+reads ``static_flow`` / ``dynamicness`` of the last iteration (``experiment.py:391-399``), so the
+export driver sets ("last", False) and skips 11 of 12 decoder calls and every fp64 3x3 SVD.
+"""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from ..config import AttrDict
+from .raft import RAFT
+
+
+def get_network_input_pcls(cfg, sample_data, time_key: str, to_device=None) -> List[torch.Tensor]:
+    """``liso/kabsch/main_utils.py:247-261``"""
+    key = ("pcl_full_w_ground_%s" if cfg.data.use_ground_for_network else "pcl_full_no_ground_%s") % time_key
+    if to_device:
+        return [el.to(to_device, non_blocking=True) for el in sample_data[key]]
+    return sample_data[key]
+
+
+class MovingAverageThreshold(nn.Module):
+    """State + ``value()`` of ``slim_loss/movavg_cls_threshold.py`` (the update rule is training-only)."""
+
+    def __init__(self, num_train_samples: int, num_moving: int, num_still=None, resolution: int = 100000,
+                 start_value: float = 0.5, value_range=(0.0, 1.0)):
+        super().__init__()
+        assert num_still is None, "supervised SLIM training is out of scope"
+        self.value_range = (value_range[0], value_range[1] - value_range[0])
+        self.resolution = resolution
+        total = num_moving
+        assert num_train_samples > 0
+        update_weight = 1.0 / min(2.0 * total, 5_000.0 * (total / num_train_samples))
+        self.register_buffer("start_value", torch.tensor(start_value, dtype=torch.float))
+        self.register_buffer("update_weight", torch.tensor(update_weight, dtype=torch.double))
+        self.register_buffer("bias_counter", torch.zeros((), dtype=torch.double))
+        self.register_buffer("moving_average_importance", torch.zeros((resolution,), dtype=torch.float))
+
+    def value(self):
+        if self.bias_counter > 0.0:
+            mai = self.moving_average_importance
+            cum = torch.cat([torch.zeros((1,), dtype=mai.dtype, device=mai.device), torch.cumsum(mai, 0)], dim=0)
+            idx = torch.mean(torch.where(torch.min(cum) == cum)[0].to(torch.float))
+            return self.value_range[0] + idx * self.value_range[1] / self.resolution
+        return self.start_value
+
+
+def _grid_to_points(grid, coors, valid, default):
+    """``batched_grid_data_to_pointwise_data`` (``static_aggregation.py:8-31``), without mutating ``coors``."""
+    coors = torch.where(valid[..., None], coors, torch.zeros_like(coors)).long()
+    bidx = torch.arange(valid.shape[0], device=grid.device)[:, None].expand(-1, valid.shape[1])
+    out = grid[bidx, coors[..., 0], coors[..., 1]]
+    return torch.where(valid[..., None], out, torch.full_like(out, default))
+
+
+def _weighted_kabsch(cloud_t0, cloud_t1, weights):
+    """``weighted_pc_alignment.py:10-80`` (no epsilon) + ``torch_symm_ortho`` (U @ Vh, no det fix)."""
+    not_enough = (weights > 0).sum() < 3
+    weights = torch.where(not_enough, weights + 1e-7, weights)
+    cum = weights.sum(dim=-1)
+    mx = (cloud_t0 * weights[..., None]).sum(dim=0) / cum
+    my = (cloud_t1 * weights[..., None]).sum(dim=0) / cum
+    S = ((cloud_t1 - my[None]) * weights[..., None]).T @ (cloud_t0 - mx[None]) / cum
+    U, _, Vh = torch.linalg.svd(S.to(torch.double))
+    R = U @ Vh
+    t = my.to(torch.double) - R @ mx.to(torch.double)
+    T = torch.eye(4, dtype=torch.double, device=R.device)
+    T[:3, :3] = R
+    T[:3, 3] = t
+    return T, not_enough
+
+
+class HeadDecoder(nn.Module):
+    def __init__(self, cfg, name, bev_extent):
+        super().__init__()
+        self.cfg = cfg
+        self.name = name
+        self.bev_extent = bev_extent
+        om = cfg.model.output_modification
+        if not (om.disappearing_logit is False and om.static_logit == "net" and om.dynamic_logit == "net"
+                and om.ground_logit is False and om.static_flow == "net" and om.dynamic_flow == "net"):
+            raise NotImplementedError("only the released SLIM output_modification is implemented")
+
+    def concat2network_output(self, *, logits, static_flow, dynamic_flow, weight_logits_for_static_aggregation=None):
+        assert weight_logits_for_static_aggregation is None
+        return torch.cat([logits, static_flow, dynamic_flow], dim=1).permute(0, 2, 3, 1)
+
+    def forward(self, network_output, dynamicness_threshold, *, pc, pointwise_voxel_coordinates, pointwise_valid_mask,
+                filled_pillar_mask, odom=None, inv_odom=None, summaries=None, static_aggregation: bool = True, **_):
+        fs = self.cfg.model.u_net.final_scale
+        coors = torch.div(pointwise_voxel_coordinates, fs, rounding_mode="trunc")
+        filled = filled_pillar_mask[..., None]
+        o = network_output
+        static_logit, dynamic_logit = o[..., 1:2], o[..., 2:3]
+        ones = torch.ones_like(static_logit)
+        # ground "off": global min of the live logits - 100 (head_decoder.py:919-935), before masking
+        ground_logit = torch.min(torch.cat([static_logit, dynamic_logit], dim=0)) - 100.0 * ones
+        neg = -100.0 * ones
+        md = AttrDict()
+        md.disappearing_logit = neg
+        md.static_logit = torch.where(filled, static_logit, 0.0 * ones)
+        md.dynamic_logit = torch.where(filled, dynamic_logit, neg)
+        md.ground_logit = torch.where(filled, ground_logit, neg)
+        md.static_flow = torch.where(filled, o[..., 4:6], torch.zeros_like(o[..., 4:6]))
+        md.dynamic_flow = torch.where(filled, o[..., 6:8], torch.zeros_like(o[..., 6:8]))
+        md.class_logits = torch.cat([md.static_logit, md.dynamic_logit, md.ground_logit], dim=-1)
+        md.class_probs = F.softmax(md.class_logits, dim=-1)
+        md.staticness, md.dynamicness, md.groundness = (md.class_probs[..., k] for k in range(3))
+        md.is_dynamic = md.dynamicness >= dynamicness_threshold
+        md.is_static = (md.staticness >= md.groundness) & (~md.is_dynamic)
+        md.is_ground = ~(md.is_static | md.is_dynamic)
+
+        zeros1 = torch.zeros_like(md.static_flow[..., :1])
+        static3 = torch.cat([md.static_flow, zeros1], dim=-1)
+        dynamic3 = torch.cat([md.dynamic_flow, zeros1], dim=-1)
+        valid = pointwise_valid_mask
+        ret = AttrDict()
+        ret.static_flow = _grid_to_points(static3, coors, valid, 0.0)
+        ret.dynamic_flow = _grid_to_points(dynamic3, coors, valid, 0.0)
+        ret.dynamicness = _grid_to_points(md.dynamicness[..., None], coors, valid, 0.0)[..., 0]
+        ret.staticness = _grid_to_points(md.staticness[..., None], coors, valid, 0.0)[..., 0]
+        aggregated = torch.where(md.is_static[..., None], static3, dynamic3 * (1.0 - md.groundness[..., None]))
+        ret.aggregated_flow = _grid_to_points(aggregated, coors, valid, 0.0)
+        ret.dense_maps = AttrDict(aggregated_flow=aggregated, static_flow=static3)
+        ret.dynamicness_threshold = dynamicness_threshold
+        if static_aggregation:
+            weight_map = md.staticness * filled[..., 0].float()
+            pt_w = _grid_to_points(weight_map[..., None], coors, valid, 0.0)[..., 0]
+            shape = o.shape[1:3]
+            ext = np.asarray(self.bev_extent, dtype=np.float64)
+            ctr = np.stack(np.meshgrid(np.arange(shape[0]), np.arange(shape[1]), indexing="ij"), axis=-1) + 0.5
+            ctr = ctr / np.asarray(shape) * (ext[2:] - ext[:2]) + ext[:2]
+            grid_h = torch.from_numpy(
+                np.concatenate([ctr, np.zeros_like(ctr[..., :1]), np.ones_like(ctr[..., :1])], axis=-1)).to(o.device)
+            flows, Ts, neps = [], [], []
+            eye = torch.eye(4, dtype=torch.float64, device=o.device)
+            for b in range(o.shape[0]):
+                m = valid[b]
+                T, nep = _weighted_kabsch(pc[b][m][..., :3], (pc[b][..., :3] + ret.static_flow[b])[m], pt_w[b][m])
+                flows.append(torch.einsum("ij,hwj->hwi", T - eye, grid_h)[..., 0:2].float())
+                Ts.append(T)
+                neps.append(nep)
+            md.static_aggr_flow = torch.stack(flows, 0)
+            md.masked_static_aggr_flow = torch.where(filled, md.static_aggr_flow, torch.zeros_like(md.static_aggr_flow))
+            ret.static_aggr_flow = _grid_to_points(torch.cat([md.static_aggr_flow, zeros1], dim=-1), coors, valid, 0.0)
+            ret.static_aggr_trafo = torch.stack(Ts, 0)
+            ret.not_enough_points = torch.stack(neps, 0)
+        else:
+            ret.not_enough_points = torch.zeros((o.shape[0],), dtype=torch.bool, device=o.device)
+        ret.modified_network_output = md
+        return ret
+
+
+class SLIM(nn.Module):
+    def __init__(self, cfg, num_train_samples: int = 15000, decode_iterations: str = "all",
+                 static_aggregation: bool = True):
+        super().__init__()
+        self.cfg = cfg
+        self.slim_cfg = cfg.SLIM
+        half = 0.5 * np.array(cfg.data.bev_range_m)
+        bev_extent = np.concatenate([-half, half], axis=0)
+        self.head_decoder_fw = HeadDecoder(self.slim_cfg, bev_extent=bev_extent, name="head_decoder_forward")
+        self.head_decoder_bw = HeadDecoder(self.slim_cfg, bev_extent=bev_extent, name="head_decoder_backward")
+        assert self.slim_cfg.phases.train.mode == "unsupervised"
+        self.moving_dynamicness_threshold = MovingAverageThreshold(num_train_samples, num_moving=621013971)
+        self.raft_network = RAFT(cfg, self.head_decoder_fw, self.head_decoder_bw)
+        assert decode_iterations in ("all", "last")
+        self.decode_iterations = decode_iterations
+        self.static_aggregation = static_aggregation
+
+    def forward(self, sample_data_t0, sample_data_t1, summaries=None):
+        dev = next(self.parameters()).device
+        outs_fw, outs_bw, aux = self.raft_network(
+            get_network_input_pcls(self.cfg, sample_data_t0, "ta", to_device=dev),
+            get_network_input_pcls(self.cfg, sample_data_t1, "ta", to_device=dev),
+        )
+        filled = [torch.squeeze(aux[k]["bev_net_input_dbg"] > 0.5, dim=1) for k in ("t0", "t1")]
+        its = range(len(outs_fw)) if self.decode_iterations == "all" else [len(outs_fw) - 1]
+        thr = self.moving_dynamicness_threshold.value()
+        preds_fw, preds_bw = [], []
+        per_dir = ((outs_fw, sample_data_t0, filled[0], self.head_decoder_fw, preds_fw),
+                   (outs_bw, sample_data_t1, filled[1], self.head_decoder_bw, preds_bw))
+        moved: Dict[int, tuple] = {}
+        for it in its:
+            for k, (outs, sample, fl, dec, preds) in enumerate(per_dir):
+                if k not in moved:
+                    pt = sample["pcl_ta"]
+                    moved[k] = (pt["pcl"].to(dev, non_blocking=True), pt["pillar_coors"].to(dev, non_blocking=True),
+                                pt["pcl_is_valid"].to(dev, non_blocking=True))
+                pc, coors, valid = moved[k]
+                preds.append(dec(outs[it], thr, pc=pc, pointwise_voxel_coordinates=coors, pointwise_valid_mask=valid,
+                                 filled_pillar_mask=fl, static_aggregation=self.static_aggregation))
+        self.predictions_fw, self.predictions_bw = preds_fw, preds_bw
+        return preds_fw, preds_bw

@@ -1,0 +1,71 @@
+"""CPU: the C-ABI library loads without a GPU and exports every symbol include/slimb200.h declares.
+No compute call is made here."""
+import ctypes
+import os
+import re
+
+from liso_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "slimb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(slimb200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported_and_bound():
+    names = _declared_symbols()
+    assert len(names) >= 10, names
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), "missing export: " + n
+    assert sorted(_lib.SYMBOLS) == names  # the Python binding covers exactly the header
+
+
+def test_host_only_entry_points():
+    lib = _lib.load()
+    assert lib.slimb200_version() == 100
+    assert b"workspace" in lib.slimb200_strerror(-3)
+    L = _lib.CorrLayout()
+    assert lib.slimb200_corr_layout_init(2, 128, 80, 80, 4, ctypes.byref(L)) == 0
+    assert (L.n_cols, L.pitch) == (6400 + 1600 + 400 + 100, 8512)
+    assert list(L.level_offset) == [0, 6400, 8000, 8400]
+    assert lib.slimb200_corr_layout_init(1, 128, 115, 115, 4, ctypes.byref(L)) == 0
+    assert list(L.level_h) == [115, 57, 28, 14] and L.n_cols == 13225 + 3249 + 784 + 196  # floor pooling
+    assert lib.slimb200_corr_layout_init(1, 64, 80, 80, 4, ctypes.byref(L)) == -2  # D != 128 unsupported
+    assert lib.slimb200_corr_pyramid_bytes(ctypes.byref(L), _lib.DTYPE_BF16) > 0
+    p = _lib.PillarParams()
+    p.grid[0], p.grid[1], p.grid[2] = 640, 640, 1
+    p.max_points, p.max_voxels, p.c_in, p.c_out = 20, 40000, 4, 64
+    assert lib.slimb200_pillar_workspace_bytes(8, 8 * 120000, ctypes.byref(p)) > 8 * 120000 * 24
+    p.c_in = 5
+    assert lib.slimb200_pillar_workspace_bytes(8, 1000, ctypes.byref(p)) == 0
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    try:
+        _lib.load()
+    except RuntimeError as e:
+        assert "no CPU" in str(e)
+    else:
+        raise AssertionError("load() must raise when the extension is missing")
+
+
+def test_cpu_tensors_are_rejected():
+    """The product path never falls back to CPU: a CPU tensor is an error, not a slow path."""
+    import pytest
+    import torch
+
+    from liso_b200.config import make_cfg
+    from liso_b200.networks.pcl_to_feature_grid import PointsPillarFeatureNetWrapper
+    from liso_b200.slim.corr import CorrBlock
+
+    m = PointsPillarFeatureNetWrapper(make_cfg("T")).eval()
+    with pytest.raises(RuntimeError, match="no CPU fallback"), torch.no_grad():
+        m([torch.zeros(10, 4)])
+    with pytest.raises(RuntimeError, match="no CPU fallback"), torch.no_grad():
+        CorrBlock(torch.zeros(1, 128, 8, 8), torch.zeros(1, 128, 8, 8))

@@ -1,0 +1,119 @@
+"""Stage-2 parity on the B200: tcgen05 correlation pyramid + lookup kernel vs the CPU oracle.
+
+Stated tolerances
+* correlation / pyramid entries (bf16 operands, fp32 accumulate, bf16 storage):
+    |got - fp64| <= 2^-7 * ||f1_i||_2 * ||f2_j||_2 / sqrt(D)          
+* lookup on a *given* pyramid: <= 1e-5 relative to the pyramid's max magnitude (fp32 interpolation)
+"""
+import numpy as np
+import pytest
+import torch
+
+from liso_b200.slim import corr as C
+from oracle import slim_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _fmaps(B, h, w, seed, device):
+    g = torch.Generator().manual_seed(seed)
+    f1 = torch.randn(B, 128, h, w, generator=g)
+    f2 = torch.randn(B, 128, h, w, generator=g)
+    # spatial structure so pooled levels are not just noise
+    f2 = f2 + 0.5 * torch.nn.functional.avg_pool2d(f2, 3, stride=1, padding=1)
+    return f1, f2, f1.to(device), f2.to(device)
+
+
+def _bound(f1, f2_level):
+    n1 = f1.double().flatten(2).norm(dim=1)  # (B, Nf)
+    n2 = f2_level.double().flatten(2).norm(dim=1)  # (B, Nl)
+    return (2.0 ** -7) * n1[:, :, None] * n2[:, None, :] / np.sqrt(128.0)
+
+
+@pytest.mark.parametrize("B,h,w", [(1, 16, 16), (2, 32, 32), (1, 80, 80), (1, 23, 23), (2, 12, 20), (1, 115, 115)])
+def test_pyramid_within_bf16_bound(cuda, B, h, w):
+    f1, f2, d1, d2 = _fmaps(B, h, w, 0, cuda)
+    blk = C.CorrBlock(d1, d2, num_levels=4, radius=3)
+    torch.cuda.synchronize()
+    ref = O.corr_pyramid(f1, f2, 4)
+    f2_l = f2
+    for l in range(4):
+        got = blk.corr_pyramid[l].float().cpu()
+        assert got.shape == ref[l].shape, (got.shape, ref[l].shape)
+        exact = torch.einsum("bdi,bdj->bij", f1.double().flatten(2), f2_l.double().flatten(2)) / np.sqrt(128.0)
+        err = (got.double().reshape(B, h * w, -1) - exact).abs()
+        bound = _bound(f1, f2_l)
+        assert bool((err <= bound).all()), (l, float(err.max()), float((err / bound).max()))
+        # and close to the oracle's fp32 pyramid in aggregate (rms error ~ 2^-9 of the entry scale)
+        rel_rms = float((got - ref[l]).pow(2).mean().sqrt() / ref[l].pow(2).mean().sqrt())
+        assert rel_rms < 6e-3, (l, rel_rms)
+        f2_l = torch.nn.functional.avg_pool2d(f2_l, 2, stride=2)
+
+
+def test_corr_static_method_shape(cuda):
+    f1, f2, d1, d2 = _fmaps(1, 16, 24, 3, cuda)
+    vol = C.CorrBlock.corr(d1, d2)
+    ref = O.corr_volume(f1, f2)
+    assert vol.shape == ref.shape == (1, 16, 24, 1, 16, 24)
+    assert float((vol.cpu() - ref).abs().max()) < 0.25
+
+
+def _coords(B, h, w, seed, spread):
+    g = torch.Generator().manual_seed(seed)
+    c = O.coords_grid(B, h, w) + spread * torch.randn(B, 2, h, w, generator=g)
+    # exact integers, negatives and far out-of-range positions
+    c[:, :, 0, 0] = torch.tensor([3.0, 2.0])
+    c[:, :, 0, 1] = torch.tensor([-2.5, 1.25])
+    c[:, :, 1, 0] = torch.tensor([w + 9.0, h + 7.0])
+    c[:, :, 1, 1] = torch.tensor([w - 1.0, h - 1.0])
+    c[:, :, 2, 2] = torch.tensor([-40.0, -40.0])
+    return c
+
+
+@pytest.mark.parametrize("B,h,w", [(1, 16, 16), (2, 24, 40), (1, 80, 80), (1, 23, 29)])
+def test_lookup_fp32_pyramid_matches_oracle(cuda, B, h, w):
+    """T8: same pyramid in, lookup out: isolates the gather kernel (fp32 storage path)."""
+    f1, f2, _, _ = _fmaps(B, h, w, 1, cuda)
+    ref_pyr = O.corr_pyramid(f1, f2, 4)
+    L = C.make_layout(B, 128, h, w, 4)
+    packed = C.pack_pyramid_f32([p.to(cuda) for p in ref_pyr], L)
+    for spread in (0.0, 0.7, 6.0):
+        coords = _coords(B, h, w, 2, spread)
+        got = C.lookup(packed, L, coords.to(cuda), 3).cpu()
+        ref = O.corr_lookup(ref_pyr, coords, 3)
+        assert got.shape == ref.shape == (B, 196, h, w)
+        scale = float(ref_pyr[0].abs().max())
+        assert float((got - ref).abs().max()) <= 1e-5 * scale, (spread, float((got - ref).abs().max()), scale)
+
+
+@pytest.mark.parametrize("B,h,w", [(2, 32, 32), (1, 80, 80), (1, 115, 115)])
+def test_lookup_on_bf16_pyramid(cuda, B, h, w):
+    """End of stage 2: kernel lookup on the kernel's own bf16 pyramid == oracle lookup on the same values."""
+    f1, f2, d1, d2 = _fmaps(B, h, w, 4, cuda)
+    blk = C.CorrBlock(d1, d2, num_levels=4, radius=3)
+    coords = _coords(B, h, w, 5, 1.5)
+    got = blk(coords.to(cuda)).cpu()
+    same_values = [lv.float().cpu().contiguous() for lv in blk.corr_pyramid]
+    ref = O.corr_lookup(same_values, coords, 3)
+    scale = float(same_values[0].abs().max())
+    assert float((got - ref).abs().max()) <= 1e-5 * scale
+    # and against the full-precision oracle: bounded by the bf16 storage/operand rounding
+    ref32 = O.corr_lookup(O.corr_pyramid(f1, f2, 4), coords, 3)
+    assert float((got - ref32).abs().max()) <= 2.0 ** -6 * scale
+
+
+def test_window_channel_order(cuda):
+    """Q6: channel k = l*49 + i*7 + j samples (x + i - 3, y + j - 3): first window axis offsets x."""
+    B, h, w = 1, 16, 16
+    L = C.make_layout(B, 128, h, w, 1)
+    lvl = torch.zeros(h * w, 1, h, w)
+    lvl[:, 0] = torch.arange(h * w, dtype=torch.float32).view(h, w)  # value = 16*row + col for every source pixel
+    packed = C.pack_pyramid_f32([lvl.to(cuda)], L)
+    coords = torch.zeros(1, 2, h, w)
+    coords[0, 0] = 8.0  # x (column)
+    coords[0, 1] = 5.0  # y (row)
+    out = C.lookup(packed, L, coords.to(cuda), 3).cpu()
+    for i in range(7):
+        for j in range(7):
+            # (the normalise / un-normalise round trip of grid_sample is not exact: ~1e-6 relative)
+            assert abs(float(out[0, i * 7 + j, 0, 0]) - (16.0 * (5 + j - 3) + (8 + i - 3))) < 1e-3

@@ -1,0 +1,91 @@
+"""End-to-end parity on the B200: SLIM forward through the CUDA hot path vs the CPU oracle port of the
+reference forward.  Bar: final per-point flow within 1 cm average end-point error (AEE as in
+``liso/slim/utils/metrics.py:113-121``); BEV masks identical."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from liso_b200.config import WORKLOADS, make_cfg
+from liso_b200.slim.slim import SLIM
+from liso_b200.synth import make_sample_dicts
+from liso_b200.weights import synth_weights_like
+from oracle import slim_forward as SF
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _model(cfg, device, seed=0, **kw):
+    m = SLIM(cfg, **kw).eval()
+    sd = synth_weights_like(m.state_dict(), seed)
+    m.load_state_dict(sd, strict=True)
+    return m.to(device), sd
+
+
+def _aee(pred, ref, valid):
+    return float((pred - ref).norm(dim=-1)[valid].mean())
+
+
+@pytest.mark.parametrize("workload,seeds", [("T", [3, 4]), ("N", [5]), ("K", [6])])
+def test_slim_forward_flow_within_1cm(cuda, workload, seeds):
+    cfg = make_cfg(workload)
+    model, sd = _model(cfg, cuda)
+    s0, s1 = make_sample_dicts(WORKLOADS[workload], seeds)
+    with torch.no_grad():
+        pf, pb = model(s0, s1, None)
+        torch.cuda.synchronize()
+        of, ob, _ = SF.slim_forward(sd, cfg, s0, s1, decode_all_iterations=False)
+    for p, o, s in ((pf, of, s0), (pb, ob, s1)):
+        valid = s["pcl_ta"]["pcl_is_valid"]
+        aee = _aee(p[-1].static_flow.cpu(), o[-1]["pointwise_static_flow"], valid)
+        bev = float((p[-1].modified_network_output.static_flow.cpu() - o[-1]["static_flow"]).abs().max())
+        dyn = float((p[-1].modified_network_output.dynamicness.cpu() - o[-1]["dynamicness"]).abs().max())
+        mag = float(o[-1]["pointwise_static_flow"].norm(dim=-1)[valid].mean())
+        print("%s: AEE %.3e m, BEV max |d| %.3e m, dynamicness max |d| %.3e, mean |flow| %.3f m" % (workload, aee, bev, dyn, mag))
+        assert aee <= 0.01
+        assert torch.equal(p[-1].modified_network_output.static_flow.cpu() != 0, o[-1]["static_flow"] != 0)
+        assert dyn < 5e-2
+
+
+def test_decode_last_equals_decode_all(cuda):
+    """The export shortcut (decode only the last iteration, no Kabsch) returns the same exported tensors."""
+    cfg = make_cfg("T")
+    full, sd = _model(cfg, cuda)
+    fast, _ = _model(cfg, cuda, decode_iterations="last", static_aggregation=False)
+    s0, s1 = make_sample_dicts(WORKLOADS["T"], [9])
+    with torch.no_grad():
+        a_fw, a_bw = full(s0, s1, None)
+        b_fw, b_bw = fast(s0, s1, None)
+    assert len(a_fw) == 6 and len(b_fw) == 1
+    for a, b in ((a_fw, b_fw), (a_bw, b_bw)):
+        assert torch.equal(a[-1].modified_network_output.static_flow, b[-1].modified_network_output.static_flow)
+        assert torch.equal(a[-1].modified_network_output.dynamicness, b[-1].modified_network_output.dynamicness)
+        assert torch.equal(a[-1].static_flow, b[-1].static_flow)
+
+
+def test_against_committed_golden(cuda):
+    """Golden produced by the *unmodified reference* in the authoring container (oracle/gen_golden.py)."""
+    path = os.path.join(GOLDEN, "slim_forward_tiny.npz")
+    g = np.load(path)
+    cfg = make_cfg("T")
+    cfg.data.img_grid_size = tuple(int(v) for v in g["img_grid_size"])
+    cfg.data.bev_range_m = tuple(float(v) for v in g["bev_range_m"])
+    model, _ = _model(cfg, cuda, seed=int(g["weight_seed"]))
+
+    def sample(t):
+        pcl = torch.from_numpy(g["pcl_%s" % t])
+        return {"pcl_full_no_ground_ta": [torch.from_numpy(g["full_%s" % t])],
+                "pcl_ta": {"pcl": pcl[None], "pcl_is_valid": torch.ones(1, pcl.shape[0], dtype=torch.bool),
+                           "pillar_coors": torch.from_numpy(g["coors_%s" % t])[None]},
+                "gt": {"odom_ta_tb": torch.eye(4, dtype=torch.float64)[None]}}
+
+    with torch.no_grad():
+        pf, pb = model(sample("t0"), sample("t1"), None)
+    for p, d in ((pf, "fw"), (pb, "bw")):
+        ref_pt = torch.from_numpy(g["pt_static_flow_%s" % d])
+        aee = float((p[-1].static_flow[0].cpu() - ref_pt).norm(dim=-1).mean())
+        assert aee <= 0.01, aee
+        ref_bev = torch.from_numpy(g["bev_static_flow_%s" % d])
+        assert torch.equal(p[-1].modified_network_output.static_flow[0].cpu() != 0, ref_bev != 0)

@@ -1,0 +1,144 @@
+"""CPU: host-side logic around the kernels -- module wiring, state-dict contract, frame sharding and
+the world_size-2 gather (gloo)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from liso_b200.config import WORKLOADS, make_cfg
+from liso_b200.slim import export
+from liso_b200.synth import make_sample_dicts, pillar_coors_f64_numpy
+from liso_b200.weights import synth_weights_like
+from oracle import slim_forward as SF
+from oracle import slim_oracle as O
+
+REFERENCE_KEYS_HEAD = [
+    "moving_dynamicness_threshold.start_value",
+    "moving_dynamicness_threshold.update_weight",
+    "moving_dynamicness_threshold.bias_counter",
+    "moving_dynamicness_threshold.moving_average_importance",
+    "raft_network.pp_layer.pts_voxel_encoder.pfn_layers.0.norm.weight",
+    "raft_network.pp_layer.pts_voxel_encoder.pfn_layers.0.norm.bias",
+    "raft_network.pp_layer.pts_voxel_encoder.pfn_layers.0.norm.running_mean",
+    "raft_network.pp_layer.pts_voxel_encoder.pfn_layers.0.norm.running_var",
+    "raft_network.pp_layer.pts_voxel_encoder.pfn_layers.0.norm.num_batches_tracked",
+    "raft_network.pp_layer.pts_voxel_encoder.pfn_layers.0.linear.weight",
+    "raft_network.fnet.norm1.weight",
+]
+
+
+def test_state_dict_contract():
+    """Keys the reference SLIM checkpoint has (verified against the live reference
+    in test_oracle_vs_reference.py): 150 entries, 2,423,606 parameters, quirky norm3/downsample.1 aliases."""
+    from liso_b200.slim.slim import SLIM
+
+    m = SLIM(make_cfg("K"))
+    keys = list(m.state_dict().keys())
+    assert keys[: len(REFERENCE_KEYS_HEAD)] == REFERENCE_KEYS_HEAD
+    assert len(keys) == 150
+    assert sum(p.numel() for p in m.parameters()) == 2423606
+    assert "raft_network.fnet.layer2.1.downsample.1.weight" in keys and "raft_network.fnet.layer2.1.norm3.weight" in keys
+    assert "raft_network.cnet.layer2.1.downsample.0.weight" in keys and "raft_network.cnet.layer1.1.downsample.0.weight" not in keys
+    assert tuple(m.state_dict()["raft_network.update_block.gru.convz.weight"].shape) == (96, 304, 3, 3)
+
+
+def test_slim_wiring_with_oracle_stages(monkeypatch):
+    """Everything around the two CUDA stages (stock encoders, GRU loop, upsampling, decoder) equals the
+    oracle port when the two stages are replaced by their oracle counterparts."""
+    import liso_b200.slim.raft as raft_mod
+    from liso_b200.slim.slim import SLIM
+
+    cfg = make_cfg("T")
+    m = SLIM(cfg).eval()
+    sd = synth_weights_like(m.state_dict(), 0)
+    m.load_state_dict(sd, strict=True)
+
+    class OracleCorr:
+        def __init__(self, f1, f2, num_levels=4, radius=4):
+            self.pyr, self.r = O.corr_pyramid(f1, f2, num_levels), radius
+
+        def __call__(self, coords):
+            return O.corr_lookup(self.pyr, coords, self.r)
+
+    monkeypatch.setattr(raft_mod, "CorrBlock", OracleCorr)
+    pp = m.raft_network.pp_layer
+    pfn = pp.pts_voxel_encoder.pfn_layers[0]
+
+    def pp_forward(pts, img=None):
+        params = dict(linear_weight=pfn.linear.weight, bn_weight=pfn.norm.weight, bn_bias=pfn.norm.bias,
+                      running_mean=pfn.norm.running_mean, running_var=pfn.norm.running_var)
+        e = O.pillar_encoder_forward([p.numpy() for p in pts], params, cfg.data.bev_range_m, cfg.data.img_grid_size, 10.0, False)
+        return e["canvas"], e["occupancy"]
+
+    monkeypatch.setattr(pp, "forward", pp_forward)
+    s0, s1 = make_sample_dicts(WORKLOADS["T"], [3])
+    with torch.no_grad():
+        pf, pb = m(s0, s1, None)
+        of, ob, _ = SF.slim_forward(sd, cfg, s0, s1)
+    assert len(pf) == len(pb) == 6
+    for it in (0, 5):
+        for p, o in ((pf, of), (pb, ob)):
+            assert torch.equal(p[it].modified_network_output.static_flow, o[it]["static_flow"])
+            assert torch.equal(p[it].modified_network_output.dynamicness, o[it]["dynamicness"])
+            assert torch.equal(p[it].static_flow, o[it]["pointwise_static_flow"])
+            assert torch.allclose(p[it].static_aggr_trafo, o[it]["static_aggr_trafo"], atol=1e-9)
+
+
+def test_synth_pillar_coors_match_oracle_a12():
+    W = WORKLOADS["A"]
+    rng = np.random.default_rng(0)
+    pts = rng.uniform(-61, 61, size=(50000, 4)).astype(np.float32)
+    pts[:, 2] = rng.uniform(-2.5, 1.5, size=pts.shape[0])
+    c0, ok0 = pillar_coors_f64_numpy(pts, W["bev_range_m"], W["img_grid_size"])
+    c1, ok1 = O.pillar_coors_f64(pts, W["bev_range_m"], W["img_grid_size"])
+    assert np.array_equal(ok0, ok1) and np.array_equal(c0, c1)
+
+
+def test_shard_indices_cover_exactly_once():
+    """experiment.py:330-332: sample_idx % world_size == worker_id."""
+    for n in (0, 1, 7, 10000):
+        for ws in (1, 2, 4, 8):
+            seen = np.zeros(n, dtype=np.int32)
+            for r in range(ws):
+                idx = export.shard_indices(n, ws, r)
+                assert all(i % ws == r for i in idx)
+                seen[idx] += 1
+            assert (seen == 1).all()
+    with pytest.raises(ValueError):
+        export.shard_indices(10, 2, 2)
+    assert list(export.iterate_batches(range(5), 2)) == [[0, 1], [2, 3], [4]]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    idx = export.shard_indices(11, world, rank)
+    local = {"pairs": float(len(idx)), "index_sum": float(sum(idx)), "elapsed_s_max": 1.0 + rank}
+    tot = export.reduce_counters(local)
+    torch.save(tot, os.path.join(out_dir, "r%d.pt" % rank))
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gather_gloo(tmp_path):
+    """The N>1 path: shard by the modulo rule, one collective at the end; totals equal the single-process run."""
+    port = _free_port()
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    single = export.reduce_counters({"pairs": 11.0, "index_sum": float(sum(range(11))), "elapsed_s_max": 2.0})
+    for r in range(2):
+        tot = torch.load(os.path.join(str(tmp_path), "r%d.pt" % r))
+        assert tot == single

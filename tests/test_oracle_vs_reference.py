@@ -1,0 +1,75 @@
+"""CPU, authoring container only: the oracle restatement against the LIVE unmodified reference at larger
+sizes than the committed fixtures.  Skipped where /root/reference does not exist (e.g. the GPU box)."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_shims
+
+pytestmark = pytest.mark.skipif(not ref_shims.reference_available(), reason="reference tree not present")
+
+
+def test_state_dict_keys_equal_reference():
+    from liso_b200.config import make_cfg
+    from liso_b200.slim.slim import SLIM
+
+    R = ref_shims.ref_modules()
+    cfg = make_cfg("T")
+    ref = R.SLIM(cfg, num_train_samples=15000)
+    mine = SLIM(cfg)
+    assert list(ref.state_dict().keys()) == list(mine.state_dict().keys())
+    for k, v in ref.state_dict().items():
+        assert mine.state_dict()[k].shape == v.shape and mine.state_dict()[k].dtype == v.dtype, k
+    mine.load_state_dict(ref.state_dict(), strict=True)  # T10
+    ref.load_state_dict(mine.state_dict(), strict=True)
+
+
+def test_oracle_forward_equals_reference_forward():
+    from liso_b200.config import WORKLOADS, make_cfg
+    from liso_b200.synth import make_sample_dicts
+    from liso_b200.weights import synth_weights_like
+    from oracle import slim_forward as SF
+
+    R = ref_shims.ref_modules()
+    cfg = make_cfg("T")
+    ref = R.SLIM(cfg, num_train_samples=15000)
+    sd = synth_weights_like(ref.state_dict(), 1)
+    ref.load_state_dict(sd, strict=True)
+    ref.eval()
+    s0, s1 = make_sample_dicts(WORKLOADS["T"], [5, 6])
+    summ = {"writer": None, "imgs_eval": False, "metrics_eval": False, "aggregated_metrics": False}
+    with torch.no_grad():
+        pf, pb = ref(copy.deepcopy(s0), copy.deepcopy(s1), summ)
+        of, ob, _ = SF.slim_forward(sd, cfg, s0, s1)
+    for it in range(6):
+        for p, o in ((pf, of), (pb, ob)):
+            assert torch.equal(p[it].modified_network_output.static_flow, o[it]["static_flow"])
+            assert torch.equal(p[it].modified_network_output.dynamicness, o[it]["dynamicness"])
+            assert torch.equal(p[it].static_flow, o[it]["pointwise_static_flow"])
+            assert torch.allclose(p[it].modified_network_output.static_aggr_flow, o[it]["static_aggr_flow"], atol=1e-6)
+
+
+def test_oracle_pillar_encoder_equals_reference_kitti_size():
+    from liso_b200.config import WORKLOADS, make_cfg
+    from liso_b200.synth import make_frame_pair
+    from oracle import slim_oracle as O
+
+    R = ref_shims.ref_modules()
+    cfg = make_cfg("K")
+    torch.manual_seed(0)
+    ref = R.PointsPillarFeatureNetWrapper(cfg)
+    bn = ref.pts_voxel_encoder.pfn_layers[0].norm
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5), bn.bias.uniform_(-0.5, 0.5), bn.running_mean.uniform_(-0.3, 0.3), bn.running_var.uniform_(0.5, 2)
+    p0, p1, _ = make_frame_pair(WORKLOADS["K"], 1)
+    for training in (False, True):
+        params = dict(linear_weight=ref.pts_voxel_encoder.pfn_layers[0].linear.weight.detach(), bn_weight=bn.weight.detach(),
+                      bn_bias=bn.bias.detach(), running_mean=bn.running_mean.clone(), running_var=bn.running_var.clone())
+        ref.train(training)
+        with torch.no_grad():
+            canvas, occ = ref([torch.from_numpy(p0), torch.from_numpy(p1)])
+        out = O.pillar_encoder_forward([p0, p1], params, cfg.data.bev_range_m, cfg.data.img_grid_size, 10.0, training)
+        assert torch.equal(canvas, out["canvas"]) and torch.equal(occ, out["occupancy"])
+        assert torch.equal(bn.running_mean, out["running_mean"])
