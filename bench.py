@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""SLIM flow-export benchmark (BASELINE.json metric: SLIM flow pairs/sec on synthetic KITTI-sized pairs).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo: CUDA hot path on N B200s
+  python bench.py --impl reference --steps K --warmup W     # the reference's CPU path (oracle port)
+
+A step = one ``SLIM.forward`` over one batch of 8 synthetic KITTI-sized frame pairs (config
+"SLIM forward batch 8 synthetic KITTI pairs bf16 on 1xB200"), export outputs = last-iteration BEV
+static flow + dynamicness of both directions (``experiment.py:391-399``).
+
+* ``value``  pairs/s with the batch already resident in HBM when the timed region starts
+* ``e2e``    the same through the public API with HOST (pinned) inputs: H2D of the clouds and the
+             D2H read of the exported tensors are inside the timed region
+* ``roofline``  dominant hand-written kernel, duration measured live with CUDA events on the launching
+             stream (library hooks), algorithmic bytes from SURVEY.md 8(d) / DESIGN.md
+* ``cpu_baseline``  the oracle port of the reference forward on the host cores (rank 0, N=1 only)
+Multi-GPU: frame pairs are sharded by the reference's modulo rule, one NCCL reduction at the end.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "slim_flow_pairs_per_sec"
+UNIT = "pairs/s"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source="fallback")  # B200_PROFILING.md
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def build_inputs(workload, seeds):
+    from liso_b200.synth import make_sample_dicts
+
+    return make_sample_dicts(workload, seeds)
+
+
+def to_device(sample, dev):
+    return {"pcl_full_no_ground_ta": [t.to(dev) for t in sample["pcl_full_no_ground_ta"]],
+            "pcl_ta": {k: v.to(dev) for k, v in sample["pcl_ta"].items()}}
+
+
+def to_pinned(sample):
+    return {"pcl_full_no_ground_ta": [t.pin_memory() for t in sample["pcl_full_no_ground_ta"]],
+            "pcl_ta": {k: v.pin_memory() for k, v in sample["pcl_ta"].items()}}
+
+
+def sample_bytes(sample):
+    n = sum(t.numel() * t.element_size() for t in sample["pcl_full_no_ground_ta"])
+    return n + sum(v.numel() * v.element_size() for v in sample["pcl_ta"].values())
+
+
+def export_tensors(pf, pb):
+    fw, bw = pf[-1].modified_network_output, pb[-1].modified_network_output
+    return [fw.static_flow, bw.static_flow, fw.dynamicness, bw.dynamicness]
+
+
+def run_oracle_pairs(cfg, sd, s0, s1, n_runs, warmup):
+    """Time the CPU port of the reference forward (one pair per run) on all host threads."""
+    from oracle import slim_forward as SF
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    one0 = {"pcl_full_no_ground_ta": s0["pcl_full_no_ground_ta"][:1], "pcl_ta": {k: v[:1] for k, v in s0["pcl_ta"].items()}}
+    one1 = {"pcl_full_no_ground_ta": s1["pcl_full_no_ground_ta"][:1], "pcl_ta": {k: v[:1] for k, v in s1["pcl_ta"].items()}}
+    out, times = None, []
+    with torch.no_grad():
+        for i in range(warmup + n_runs):
+            t = time.perf_counter()
+            out = SF.slim_forward(sd, cfg, one0, one1, decode_all_iterations=True)  # the reference decodes all 6
+            if i >= warmup:
+                times.append(time.perf_counter() - t)
+    return out, times
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="K", choices=["K", "N", "A", "T"])
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--conv-precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--profile-one-step", action="store_true",
+                    help="bracket ONE resident step with cudaProfilerStart/Stop (for `ncu --profile-from-start off`) and exit")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    from liso_b200.config import WORKLOADS, make_cfg
+    from liso_b200.weights import synth_weights_like
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    W = WORKLOADS[args.workload]
+    cfg = make_cfg(args.workload)
+    config = {"workload": "SLIM forward batch %d synthetic %s pairs (%dk pts/frame, %dx%d BEV) bf16-corr" % (
+        args.batch, {"K": "KITTI-sized", "N": "nuScenes-sized", "A": "AV2-sized", "T": "tiny"}[args.workload],
+        W["n_points"] // 1000, W["img_grid_size"][0], W["img_grid_size"][1]),
+        "pairs_per_step_per_gpu": args.batch, "iters": 6, "directions": 2,
+        "parallelism": "frame-sharded x%d (idx %% world == rank)" % world,
+        "l2": "per-step working set (canvas %.0f MB + pyramid %.0f MB per batch) exceeds the 126 MB L2; no flush needed" % (
+            2 * args.batch * 64 * W["img_grid_size"][0] * W["img_grid_size"][1] * 4 / 1e6,
+            2 * args.batch * (W["img_grid_size"][0] // 8) ** 2 * 8512 * 2 / 1e6)}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from liso_b200.slim.slim import SLIM
+
+        sd = synth_weights_like(SLIM(cfg).state_dict(), 0)
+        s0, s1 = build_inputs(W, [1000])
+        _, times = run_oracle_pairs(cfg, sd, s0, s1, n_runs=max(1, args.steps), warmup=args.warmup)
+        v = len(times) / sum(times)
+        cores = os.cpu_count() or 1
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+                "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                 "sample": "each step = 1 pair (B=1) of the workload through the CPU port of SLIM.forward"},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ this repo (CUDA)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device: the SLIM hot path has no CPU fallback")
+    import torch.distributed as dist
+
+    from liso_b200 import _lib
+    from liso_b200.slim.slim import SLIM
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    torch.backends.cudnn.allow_tf32 = args.conv_precision == "tf32"
+    torch.backends.cuda.matmul.allow_tf32 = args.conv_precision == "tf32"
+    torch.backends.cudnn.benchmark = True
+
+    model = SLIM(cfg, decode_iterations="last", static_aggregation=False).eval()
+    sd = synth_weights_like(model.state_dict(), 0)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(dev)
+
+    # pairs of this rank: global pair indices sharded by the reference's modulo rule
+    from liso_b200.slim.export import reduce_counters, shard_indices
+
+    mine = shard_indices(args.batch * world, world, rank)
+    s0, s1 = build_inputs(W, [1000 + i for i in mine])
+    d0, d1 = to_device(s0, dev), to_device(s1, dev)
+    h0, h1 = to_pinned(s0), to_pinned(s1)
+    h2d = sample_bytes(s0) + sample_bytes(s1)
+    H, Wd = W["img_grid_size"]
+    pinned_out = [torch.empty((args.batch, H, Wd, 2), dtype=torch.float32).pin_memory() for _ in range(2)] + \
+                 [torch.empty((args.batch, H, Wd), dtype=torch.float32).pin_memory() for _ in range(2)]
+    d2h = sum(t.numel() * 4 for t in pinned_out)
+
+    def step_resident():
+        with torch.no_grad():
+            pf, pb = model(d0, d1, None)
+        return export_tensors(pf, pb)
+
+    def step_e2e():
+        with torch.no_grad():
+            pf, pb = model(h0, h1, None)
+        for dst, src in zip(pinned_out, export_tensors(pf, pb)):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, profile=False):
+        barrier()
+        if profile:
+            lib.slimb200_profile_begin()
+        l0 = lib.slimb200_launch_count(-1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = lib.slimb200_launch_count(-1) - l0
+        prof = None
+        if profile:
+            ms_k = (C.c_float * _lib.N_KERNELS)()
+            n_k = (C.c_int64 * _lib.N_KERNELS)()
+            _lib.check(lib.slimb200_profile_end(ms_k, n_k))
+            prof = {i: (float(ms_k[i]), int(n_k[i])) for i in range(_lib.N_KERNELS) if n_k[i]}
+        return ms, launches, prof
+
+    for _ in range(args.warmup):
+        step_resident()
+    if args.profile_one_step:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_res, launches, prof = timed(step_resident, args.steps, profile=True)
+    for _ in range(args.warmup):
+        step_e2e()
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    tot = reduce_counters({"pairs": float(args.batch * args.steps), "ms_res_max": ms_res, "ms_e2e_max": ms_e2e,
+                           "launches": float(launches)}, device=dev)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = tot["pairs"] / (tot["ms_res_max"] / 1e3)
+    e2e_value = tot["pairs"] / (tot["ms_e2e_max"] / 1e3)
+
+    # ---- roofline of the dominant hand-written kernel (rank 0, live CUDA-event durations) ----
+    peaks = _peaks()
+    B = args.batch
+    n_pts = [t.shape[0] for t in s0["pcl_full_no_ground_ta"]]
+    nf = (H // 8) * (Wd // 8)
+    L = _lib.CorrLayout()
+    lib.slimb200_corr_layout_init(B, 128, H // 8, Wd // 8, 4, C.byref(L))
+    alg = {
+        _lib.K_TILE_ENCODE: dict(bytes=sum(n_pts) * 16 + B * 65 * H * Wd * 4, flops=0,
+                                 what="points read + canvas (zeros incl.) + occupancy written, B frames per launch"),
+        _lib.K_CORR_GEMM: dict(bytes=B * nf * L.n_cols * 2 + B * (nf + L.n_cols) * 128 * 2, flops=2.0 * B * nf * L.n_cols * 128,
+                               what="bf16 pyramid written + bf16 operands read, B samples per launch"),
+        _lib.K_CORR_LOOKUP: dict(bytes=B * 196 * nf * 4 + B * nf * 4 * 8 * 32, flops=0,
+                                 what="fp32 lookup written + 8 tap rows x 32 B sectors per level read"),
+    }
+    kernels = []
+    for kid, (ms_k, n_k) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+        name = lib.slimb200_kernel_name(kid).decode()
+        ent = {"kernel": name, "launches_per_step": n_k / args.steps, "avg_ms": ms_k / n_k,
+               "share_of_step": ms_k / ms_res}
+        if kid in alg:
+            gbs = alg[kid]["bytes"] / (ms_k / n_k * 1e-3) / 1e9
+            ent.update({"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": gbs / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": alg[kid]["bytes"],
+                        "what": alg[kid]["what"]})
+            if alg[kid]["flops"]:
+                tf = alg[kid]["flops"] / (ms_k / n_k * 1e-3) / 1e12
+                ent["tensor"] = {"achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"]}
+        kernels.append(ent)
+    dom = next((k for k in kernels if "bound" in k), None)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if dom and os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("%s:%s:B%d" % (dom["kernel"], args.workload, B))
+    roofline = None
+    if dom:
+        roofline = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"],
+                    "unit": dom["unit"], "frac": dom["frac"], "traffic": traffic, "peak_source": peaks["source"] + " (of measured)"
+                    if peaks["source"] == "measured" else "fallback", "avg_launch_ms": dom["avg_ms"],
+                    "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"]}
+        if "tensor" in dom:
+            roofline["tensor"] = dom["tensor"]
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": tot["ms_res_max"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": tot["ms_e2e_max"] / args.steps},
+            "gpu_launches": int(tot["launches"]), "roofline": roofline, "kernels": kernels,
+            "precision": {"pillar": "f32", "correlation": "bf16 operands, f32 accumulate, bf16 storage",
+                          "stock_convs": "cudnn " + args.conv_precision}}
+
+    # ---- CPU baseline (oracle port of the reference forward), N=1 only, bounded sample ----
+    if world == 1 and not args.no_cpu_baseline:
+        (of, ob, _), times = run_oracle_pairs(cfg, sd, s0, s1, n_runs=2, warmup=1)
+        v = len(times) / sum(times)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                                "sample": "2 timed runs (1 warm-up) of 1 pair (B=1) of the same workload, fp32, all host threads"}
+        with torch.no_grad():
+            pf, pb = model(d0, d1, None)
+        valid = s0["pcl_ta"]["pcl_is_valid"][0]
+        epe = (pf[-1].static_flow[0].cpu() - of[-1]["pointwise_static_flow"][0]).norm(dim=-1)[valid]
+        line["parity"] = {"per_point_static_flow_aee_m_vs_oracle": float(epe.mean()), "max_m": float(epe.max()), "limit_m": 0.01}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

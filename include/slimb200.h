@@ -145,6 +145,31 @@ int slimb200_corr_lookup(const void* pyramid, int32_t pyramid_dtype, const slimb
 const char* slimb200_strerror(int code);
 int slimb200_version(void);
 
+/* ------------------------------------------------------------------------------------------
+ * Measurement hooks (bench.py): every kernel launch of the library is counted; between
+ * profile_begin / profile_end each launch is additionally bracketed by CUDA events on its stream.
+ * profile_end synchronises on the recorded events and returns per-kernel totals.
+ * ---------------------------------------------------------------------------------------- */
+enum {
+  SLIMB200_K_POINT_KEYS = 0,
+  SLIMB200_K_SCAN_LOCAL,
+  SLIMB200_K_SCAN_GLOBAL,
+  SLIMB200_K_RANK_SCATTER,
+  SLIMB200_K_TILE_ENCODE_STATS,
+  SLIMB200_K_BN_FINALIZE,
+  SLIMB200_K_TILE_ENCODE,
+  SLIMB200_K_FEAT_PACK,
+  SLIMB200_K_CORR_GEMM,
+  SLIMB200_K_CORR_LOOKUP,
+  SLIMB200_K_PILLAR_COORS,
+  SLIMB200_N_KERNELS
+};
+int slimb200_profile_begin(void);
+int slimb200_profile_end(float* ms_total /*host[SLIMB200_N_KERNELS]*/,
+                         int64_t* timed_launches /*host[SLIMB200_N_KERNELS]*/);
+int64_t slimb200_launch_count(int32_t kernel_id /* <0: all kernels */);
+const char* slimb200_kernel_name(int32_t kernel_id);
+
 #ifdef __cplusplus
 }
 #endif

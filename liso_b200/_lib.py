@@ -79,7 +79,13 @@ SYMBOLS = {
     ),
     "slimb200_strerror": (C.c_char_p, [C.c_int]),
     "slimb200_version": (C.c_int, []),
+    "slimb200_profile_begin": (C.c_int, []),
+    "slimb200_profile_end": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
+    "slimb200_launch_count": (C.c_int64, [C.c_int32]),
+    "slimb200_kernel_name": (C.c_char_p, [C.c_int32]),
 }
+N_KERNELS = 11
+K_TILE_ENCODE, K_FEAT_PACK, K_CORR_GEMM, K_CORR_LOOKUP = 6, 7, 8, 9
 
 _lib: Optional[C.CDLL] = None
 

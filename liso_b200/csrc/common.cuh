@@ -36,3 +36,14 @@ struct WorkspaceCarver {
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+
+// launch accounting / optional event timing (profile.cu)
+void slimb200_prof_pre(int id, cudaStream_t s);
+void slimb200_prof_post(int id, cudaStream_t s);
+#define SLIMB200_LAUNCH(id, stream, ...)  \
+  do {                                    \
+    slimb200_prof_pre((id), (stream));    \
+    __VA_ARGS__;                          \
+    slimb200_prof_post((id), (stream));   \
+    SLIMB200_LAUNCH_CHECK();              \
+  } while (0)

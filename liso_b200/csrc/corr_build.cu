@@ -475,8 +475,8 @@ extern "C" int slimb200_corr_build(const float* fmap1, const float* fmap2, const
 
   {
     const int groups = (nf + PACK_ROWS - 1) / PACK_ROWS + (L->n_cols + PACK_ROWS - 1) / PACK_ROWS;
-    k_feat_pack<<<dim3(groups, L->batch), 256, 0, stream>>>(fmap1, fmap2, *L, A, Bx);
-    SLIMB200_LAUNCH_CHECK();
+    SLIMB200_LAUNCH(SLIMB200_K_FEAT_PACK, stream,
+                    (k_feat_pack<<<dim3(groups, L->batch), 256, 0, stream>>>(fmap1, fmap2, *L, A, Bx)));
   }
   GemmShape shape;
   shape.batch = L->batch;
@@ -493,7 +493,7 @@ extern "C" int slimb200_corr_build(const float* fmap1, const float* fmap2, const
     SLIMB200_CUDA_TRY(cudaFuncSetAttribute(k_corr_gemm_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   }
   const int grid = shape.total_tiles < n_sm ? shape.total_tiles : n_sm;
-  k_corr_gemm_tcgen05<<<grid, GEMM_THREADS, SMEM_BYTES, stream>>>(map_a, map_b, map_c, shape);
-  SLIMB200_LAUNCH_CHECK();
+  SLIMB200_LAUNCH(SLIMB200_K_CORR_GEMM, stream,
+                  (k_corr_gemm_tcgen05<<<grid, GEMM_THREADS, SMEM_BYTES, stream>>>(map_a, map_b, map_c, shape)));
   return SLIMB200_OK;
 }

@@ -110,8 +110,10 @@ extern "C" int slimb200_corr_lookup(const void* pyramid, int32_t pyramid_dtype, 
                                              LK_MAX_CH * (LK_PIX + 1) * (int)sizeof(float)));
       attr_set = true;
     }
+    slimb200_prof_pre(SLIMB200_K_CORR_LOOKUP, stream);
     k_corr_lookup<__nv_bfloat16><<<grid, LK_THREADS, smem, stream>>>(static_cast<const __nv_bfloat16*>(pyramid), *L,
                                                                      coords, radius, out);
+    slimb200_prof_post(SLIMB200_K_CORR_LOOKUP, stream);
   } else if (pyramid_dtype == SLIMB200_DTYPE_F32) {
     static bool attr_set = false;
     if (!attr_set) {
@@ -119,8 +121,10 @@ extern "C" int slimb200_corr_lookup(const void* pyramid, int32_t pyramid_dtype, 
                                              LK_MAX_CH * (LK_PIX + 1) * (int)sizeof(float)));
       attr_set = true;
     }
+    slimb200_prof_pre(SLIMB200_K_CORR_LOOKUP, stream);
     k_corr_lookup<float><<<grid, LK_THREADS, smem, stream>>>(static_cast<const float*>(pyramid), *L, coords, radius,
                                                              out);
+    slimb200_prof_post(SLIMB200_K_CORR_LOOKUP, stream);
   } else {
     return SLIMB200_E_UNSUPPORTED;
   }

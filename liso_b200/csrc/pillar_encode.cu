@@ -655,26 +655,20 @@ extern "C" int slimb200_pillar_encode(const float* const* points, const int32_t*
   SLIMB200_CUDA_TRY(cudaMemsetAsync(workspace, 0, plan.zero_bytes, stream));
   if (plan.max_pts_per_sample > 0) {
     dim3 g((plan.max_pts_per_sample + PT_BLOCK - 1) / PT_BLOCK, batch);
-    k_point_keys<<<g, PT_BLOCK, 0, stream>>>(a);
-    SLIMB200_LAUNCH_CHECK();
+    SLIMB200_LAUNCH(SLIMB200_K_POINT_KEYS, stream, (k_point_keys<<<g, PT_BLOCK, 0, stream>>>(a)));
   }
-  k_scan_local<<<plan.n_cell_blocks + plan.n_pt_blocks, 256, 0, stream>>>(a, plan.n_cell_blocks);
-  SLIMB200_LAUNCH_CHECK();
-  k_scan_global<<<3, 1024, 0, stream>>>(a);
-  SLIMB200_LAUNCH_CHECK();
+  SLIMB200_LAUNCH(SLIMB200_K_SCAN_LOCAL, stream,
+                  (k_scan_local<<<plan.n_cell_blocks + plan.n_pt_blocks, 256, 0, stream>>>(a, plan.n_cell_blocks)));
+  SLIMB200_LAUNCH(SLIMB200_K_SCAN_GLOBAL, stream, (k_scan_global<<<3, 1024, 0, stream>>>(a)));
   if (plan.n_pt_blocks > 0) {
-    k_rank_scatter<<<plan.n_pt_blocks, PT_BLOCK, 0, stream>>>(a);
-    SLIMB200_LAUNCH_CHECK();
+    SLIMB200_LAUNCH(SLIMB200_K_RANK_SCATTER, stream, (k_rank_scatter<<<plan.n_pt_blocks, PT_BLOCK, 0, stream>>>(a)));
   }
   if (p->bn_training) {
     const int n_ctas = a.n_tiles < STATS_MAX_CTAS ? a.n_tiles : STATS_MAX_CTAS;
-    k_tile_encode<1><<<n_ctas, ENC_THREADS, 0, stream>>>(a);
-    SLIMB200_LAUNCH_CHECK();
-    k_bn_finalize<<<1, MAX_COUT, 0, stream>>>(a, n_ctas);
-    SLIMB200_LAUNCH_CHECK();
+    SLIMB200_LAUNCH(SLIMB200_K_TILE_ENCODE_STATS, stream, (k_tile_encode<1><<<n_ctas, ENC_THREADS, 0, stream>>>(a)));
+    SLIMB200_LAUNCH(SLIMB200_K_BN_FINALIZE, stream, (k_bn_finalize<<<1, MAX_COUT, 0, stream>>>(a, n_ctas)));
   }
-  k_tile_encode<0><<<a.n_tiles, ENC_THREADS, 0, stream>>>(a);
-  SLIMB200_LAUNCH_CHECK();
+  SLIMB200_LAUNCH(SLIMB200_K_TILE_ENCODE, stream, (k_tile_encode<0><<<a.n_tiles, ENC_THREADS, 0, stream>>>(a)));
   return SLIMB200_OK;
 }
 
@@ -686,8 +680,8 @@ extern "C" int slimb200_pillar_coors_f64(const float* pts, int64_t n, int32_t c_
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int threads = 256;
   const int64_t blocks = (n + threads - 1) / threads;
-  k_pillar_coors_f64<<<(unsigned)blocks, threads, 0, stream>>>(pts, n, c_in, range_x, range_y, grid_x, grid_y, z_min,
-                                                              z_max, coors, valid);
-  SLIMB200_LAUNCH_CHECK();
+  SLIMB200_LAUNCH(SLIMB200_K_PILLAR_COORS, stream,
+                  (k_pillar_coors_f64<<<(unsigned)blocks, threads, 0, stream>>>(pts, n, c_in, range_x, range_y, grid_x,
+                                                                               grid_y, z_min, z_max, coors, valid)));
   return SLIMB200_OK;
 }

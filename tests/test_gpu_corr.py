@@ -47,7 +47,8 @@ def test_pyramid_within_bf16_bound(cuda, B, h, w):
         # and close to the oracle's fp32 pyramid in aggregate (rms error ~ 2^-9 of the entry scale)
         rel_rms = float((got - ref[l]).pow(2).mean().sqrt() / ref[l].pow(2).mean().sqrt())
         assert rel_rms < 6e-3, (l, rel_rms)
-        f2_l = torch.nn.functional.avg_pool2d(f2_l, 2, stride=2)
+        if l < 3:
+            f2_l = torch.nn.functional.avg_pool2d(f2_l, 2, stride=2)
 
 
 def test_corr_static_method_shape(cuda):
