@@ -13,8 +13,8 @@
 //                          warp 1   tcgen05.mma issuer (one elected lane), fp32 accumulators in TMEM,
 //                                   4 accumulator buffers (512 columns) so the epilogue of tile t
 //                                   overlaps the MMAs of tiles t+1..t+3
-//                          warps 2-5 epilogue: tcgen05.ld -> * 1/sqrt(D) -> bf16 -> swizzled smem ->
-//                                   TMA store (double-buffered staging)
+//                          warps 2-9 epilogue, two groups of four alternating over the tiles:
+//                                   tcgen05.ld -> * 1/sqrt(D) -> bf16 -> swizzled smem -> TMA store
 //                        K = D = 128 only, so the kernel is bound by the bf16 store of the volume
 //                        (algorithmic bytes = Nf * Ncols * 2 per sample per direction), not by MMA.
 #include <cuda.h>
@@ -33,8 +33,9 @@ constexpr int UMMA_K = 16;
 constexpr int STAGES = 4;
 constexpr int ACC_STAGES = 4;
 constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;  // 512
-constexpr int OUT_STAGES = 2;
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_GROUPS = 2;     // two epilogue warpgroups alternate over the tiles
+constexpr int OUT_STAGES = EPI_GROUPS;  // one staging buffer per epilogue group
+constexpr int GEMM_THREADS = 64 + 128 * EPI_GROUPS;
 constexpr int EPI_THREADS = 128;
 
 constexpr uint32_t A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
@@ -251,36 +252,42 @@ k_corr_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   } else {
     // ================================ epilogue ====================================
+    // Two groups of 4 warps; group g drains the accumulator of every tile with (it % 2 == g), so the
+    // TMEM -> register -> smem -> TMA-store chain of one tile overlaps the same chain of the next.
+    const int grp = (warp - 2) >> 2;
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;          // accumulator row == TMEM lane
-    const bool store_thread = (threadIdx.x == 64);
-    int it = 0;
-    for (int t = blockIdx.x; t < shape.total_tiles; t += gridDim.x, ++it) {
+    const bool store_thread = (threadIdx.x == 64 + grp * EPI_THREADS);
+    const uint32_t out_buf = smem_out + (uint32_t)grp * OUT_STAGE_BYTES;
+    const int bar_id = 1 + grp;
+    for (int it = grp; ; it += EPI_GROUPS) {
+      const int t = blockIdx.x + it * gridDim.x;
+      if (t >= shape.total_tiles) break;
       const int b = t / tiles_per_b;
       const int r = t - b * tiles_per_b;
       const int m = r / shape.n_tiles, n = r - m * shape.n_tiles;
       const int acc = it % ACC_STAGES;
       const uint32_t acc_phase = (uint32_t)(it / ACC_STAGES) & 1u;
-      const uint32_t out_buf = smem_out + (uint32_t)(it % OUT_STAGES) * OUT_STAGE_BYTES;
-      // staging buffer (it % 2) was handed to TMA two tiles ago: wait until it has been read
-      if (store_thread) tma_store_wait_read<OUT_STAGES - 1>();
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+      // this group's staging buffer was handed to TMA one (group-)tile ago: wait until it has been read
+      if (store_thread) tma_store_wait_read<0>();
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(EPI_THREADS) : "memory");
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      uint32_t v[2][32];
+      tmem_ld_32x32b_x32(taddr, v[0]);
+      tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < BLOCK_N / 32; ++j) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(taddr + (uint32_t)(j * 32), v);
-        tmem_ld_wait();
+        if (j + 1 < BLOCK_N / 32) tmem_ld_32x32b_x32(taddr + (uint32_t)((j + 1) * 32), v[(j + 1) & 1]);  // prefetch
         const uint32_t half = out_buf + (uint32_t)(j >> 1) * OUT_HALF_BYTES + (uint32_t)row * 128u;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t pk[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float lo = __uint_as_float(v[c * 8 + 2 * e]) * shape.scale;
-            const float hi = __uint_as_float(v[c * 8 + 2 * e + 1]) * shape.scale;
+            const float lo = __uint_as_float(v[j & 1][c * 8 + 2 * e]) * shape.scale;
+            const float hi = __uint_as_float(v[j & 1][c * 8 + 2 * e + 1]) * shape.scale;
             asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk[e]) : "f"(hi), "f"(lo));
           }
           const uint32_t chunk = (uint32_t)((j & 1) * 4 + c);
@@ -289,6 +296,7 @@ k_corr_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                        "r"(pk[3])
                        : "memory");
         }
+        tmem_ld_wait();
       }
       // accumulator buffer is drained: hand it back to the MMA warp
       tcgen05_fence_before();
@@ -296,7 +304,7 @@ k_corr_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       // make the smem writes visible to the async proxy, then one thread issues the TMA stores
       fence_proxy_async_smem();
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(EPI_THREADS) : "memory");
       if (store_thread) {
         tma_store_3d(&map_c, out_buf, n * BLOCK_N, m * BLOCK_M, b);
         tma_store_3d(&map_c, out_buf + OUT_HALF_BYTES, n * BLOCK_N + 64, m * BLOCK_M, b);

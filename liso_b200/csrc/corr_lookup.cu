@@ -19,7 +19,8 @@ namespace {
 
 constexpr int LK_PIX = 32;
 constexpr int LK_THREADS = 256;
-constexpr int LK_MAX_CH = 4 * 81;  // up to 4 levels, radius <= 4
+constexpr int LK_SMEM_MAX = (256 * 33 + 32 * 4 * 2 * 9) * 4;
+constexpr int LK_MAX_CH = 256;     // one thread per output channel: levels * (2r+1)^2 <= 256
 
 template <typename T>
 __device__ __forceinline__ float ld_val(const T* p);
@@ -32,61 +33,83 @@ __device__ __forceinline__ float ld_val<__nv_bfloat16>(const __nv_bfloat16* p) {
   return __bfloat162float(__ldg(p));
 }
 
+// One thread owns one output channel k = (level, i, j) and walks the CTA's 32 pixels, so the
+// per-channel constants (level geometry, window offsets) stay in registers and the lanes of a warp
+// read neighbouring taps of the SAME pyramid row.  The pixel-space sample positions (the
+// normalise / un-normalise round trip of bilinear_sampler + grid_sample) are computed once per
+// (pixel, level, axis, offset) into shared memory instead of once per output.
 template <typename T>
-__global__ void __launch_bounds__(LK_THREADS) k_corr_lookup(const T* __restrict__ pyr, const slimb200_corr_layout L,
-                                                            const float* __restrict__ coords, int radius,
-                                                            float* __restrict__ out) {
-  extern __shared__ float s_out[];  // [n_ch][LK_PIX + 1]
+__global__ void __launch_bounds__(LK_THREADS, 4) k_corr_lookup(const T* __restrict__ pyr, const slimb200_corr_layout L,
+                                                               const float* __restrict__ coords, int radius,
+                                                               float* __restrict__ out) {
+  extern __shared__ float s_dyn[];  // [n_ch][LK_PIX + 1] results, then [LK_PIX][levels][2][win] positions
   __shared__ float s_xy[2][LK_PIX];
+  __shared__ int s_lw[SLIMB200_MAX_LEVELS], s_lh[SLIMB200_MAX_LEVELS], s_lo[SLIMB200_MAX_LEVELS];
   const int nf = L.h * L.w;
   const int b = blockIdx.y;
   const int i0 = blockIdx.x * LK_PIX;
   const int win = 2 * radius + 1, win2 = win * win;
   const int n_ch = L.levels * win2;
+  float* s_out = s_dyn;
+  float* s_pos = s_dyn + n_ch * (LK_PIX + 1);
   if (threadIdx.x < 2 * LK_PIX) {
     const int ch = threadIdx.x / LK_PIX, p = threadIdx.x % LK_PIX;
     s_xy[ch][p] = (i0 + p < nf) ? __ldg(coords + ((size_t)b * 2 + ch) * nf + i0 + p) : 0.f;
   }
+  if (threadIdx.x < SLIMB200_MAX_LEVELS) {
+    s_lw[threadIdx.x] = L.level_w[threadIdx.x];
+    s_lh[threadIdx.x] = L.level_h[threadIdx.x];
+    s_lo[threadIdx.x] = L.level_offset[threadIdx.x];
+  }
   __syncthreads();
-  for (int q = threadIdx.x; q < LK_PIX * n_ch; q += LK_THREADS) {
-    const int p = q / n_ch, k = q - p * n_ch;
-    const int i = i0 + p;
-    float val = 0.f;
-    if (i < nf) {
-      const int l = k / win2, rem = k - l * win2;
-      const int wa = rem / win, wb = rem - wa * win;
-      const float inv = 1.0f / (float)(1 << l);  // coords / 2**l, exact
-      const float xs = __fadd_rn(s_xy[0][p] * inv, (float)(wa - radius));
-      const float ys = __fadd_rn(s_xy[1][p] * inv, (float)(wb - radius));
-      const int W = L.level_w[l], H = L.level_h[l];
-      const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
-      // bilinear_sampler normalisation (utils.py:19-20) ...
-      const float xg = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, xs), wm1), 1.f);
-      const float yg = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, ys), hm1), 1.f);
-      // ... undone by grid_sample(align_corners=True): ((g + 1) / 2) * (size - 1)
-      const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(xg, 1.f), 2.f), wm1);
-      const float iy = __fmul_rn(__fdiv_rn(__fadd_rn(yg, 1.f), 2.f), hm1);
-      if (fabsf(ix) < 1e7f && fabsf(iy) < 1e7f) {
-        const float fx = floorf(ix), fy = floorf(iy);
-        const int x0 = (int)fx, y0 = (int)fy;
-        const float ex = __fsub_rn(__fadd_rn(fx, 1.f), ix), ey = __fsub_rn(__fadd_rn(fy, 1.f), iy);  // se - i
-        const float dx = __fsub_rn(ix, fx), dy = __fsub_rn(iy, fy);                                  // i - nw
-        const T* row = pyr + ((size_t)b * nf + i) * L.pitch + L.level_offset[l];
-        const bool xin0 = x0 >= 0 && x0 < W, xin1 = x0 + 1 >= 0 && x0 + 1 < W;
-        const bool yin0 = y0 >= 0 && y0 < H, yin1 = y0 + 1 >= 0 && y0 + 1 < H;
-        if (yin0 && xin0) val += ld_val(row + y0 * W + x0) * __fmul_rn(ex, ey);            // nw
-        if (yin0 && xin1) val += ld_val(row + y0 * W + x0 + 1) * __fmul_rn(dx, ey);        // ne
-        if (yin1 && xin0) val += ld_val(row + (y0 + 1) * W + x0) * __fmul_rn(ex, dy);      // sw
-        if (yin1 && xin1) val += ld_val(row + (y0 + 1) * W + x0 + 1) * __fmul_rn(dx, dy);  // se
-      }
+  // ---- sample positions: ix = (((2*xs/(W-1) - 1) + 1) / 2) * (W-1), xs = x / 2^l + (i - r) ------------
+  const int per_pix = L.levels * 2 * win;
+  for (int e = threadIdx.x; e < LK_PIX * per_pix; e += LK_THREADS) {
+    const int p = e / per_pix, rem = e - p * per_pix;
+    const int l = rem / (2 * win), rem2 = rem - l * 2 * win;
+    const int axis = rem2 / win, o = rem2 - axis * win;
+    const float inv = 1.0f / (float)(1 << l);  // coords / 2**l is exact
+    const float pos = __fadd_rn(s_xy[axis][p] * inv, (float)(o - radius));
+    const float sm1 = (float)((axis == 0 ? s_lw[l] : s_lh[l]) - 1);
+    const float g = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, pos), sm1), 1.f);            // utils.py:19-20
+    float ip = __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.f), 2.f), sm1);                    // grid_sample un-normalise
+    if (!(fabsf(ip) < 1e7f)) ip = -1e7f;                                             // NaN / inf / far away: all taps outside
+    s_pos[e] = ip;
+  }
+  __syncthreads();
+  // ---- one output channel per thread, 32 pixels ---------------------------------------------------
+  const int k = threadIdx.x;
+  if (k < n_ch) {
+    const int l = k / win2, rem = k - l * win2;
+    const int wa = rem / win, wb = rem - wa * win;
+    const int W = s_lw[l], H = s_lh[l];
+    const T* base = pyr + ((size_t)b * nf + i0) * L.pitch + s_lo[l];
+    const float* px = s_pos + (l * 2 + 0) * win + wa;
+    const float* py = s_pos + (l * 2 + 1) * win + wb;
+    const int n_pix = min(LK_PIX, nf - i0);
+#pragma unroll 4
+    for (int p = 0; p < n_pix; ++p) {
+      const float ix = px[p * per_pix], iy = py[p * per_pix];
+      const float fx = floorf(ix), fy = floorf(iy);
+      const int x0 = (int)fx, y0 = (int)fy;
+      const float ex = __fsub_rn(__fadd_rn(fx, 1.f), ix), ey = __fsub_rn(__fadd_rn(fy, 1.f), iy);  // se - i
+      const float dx = __fsub_rn(ix, fx), dy = __fsub_rn(iy, fy);                                  // i - nw
+      const bool xin0 = (unsigned)x0 < (unsigned)W, xin1 = (unsigned)(x0 + 1) < (unsigned)W;
+      const bool yin0 = (unsigned)y0 < (unsigned)H, yin1 = (unsigned)(y0 + 1) < (unsigned)H;
+      const T* row = base + (size_t)p * L.pitch + y0 * W + x0;
+      float val = 0.f;
+      if (yin0 && xin0) val += ld_val(row) * __fmul_rn(ex, ey);          // nw
+      if (yin0 && xin1) val += ld_val(row + 1) * __fmul_rn(dx, ey);      // ne
+      if (yin1 && xin0) val += ld_val(row + W) * __fmul_rn(ex, dy);      // sw
+      if (yin1 && xin1) val += ld_val(row + W + 1) * __fmul_rn(dx, dy);  // se
+      s_out[k * (LK_PIX + 1) + p] = val;
     }
-    s_out[k * (LK_PIX + 1) + p] = val;
   }
   __syncthreads();
   const int lane = lane_id(), warp = warp_id();
   if (i0 + lane < nf) {
-    for (int k = warp; k < n_ch; k += LK_THREADS / 32)
-      out[((size_t)b * n_ch + k) * nf + i0 + lane] = s_out[k * (LK_PIX + 1) + lane];
+    for (int kk = warp; kk < n_ch; kk += LK_THREADS / 32)
+      out[((size_t)b * n_ch + kk) * nf + i0 + lane] = s_out[kk * (LK_PIX + 1) + lane];
   }
 }
 
@@ -101,13 +124,14 @@ extern "C" int slimb200_corr_lookup(const void* pyramid, int32_t pyramid_dtype, 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int nf = L->h * L->w;
   const int n_ch = L->levels * (2 * radius + 1) * (2 * radius + 1);
-  const size_t smem = (size_t)n_ch * (LK_PIX + 1) * sizeof(float);
+  if (n_ch > LK_MAX_CH) return SLIMB200_E_UNSUPPORTED;
+  const size_t smem = ((size_t)n_ch * (LK_PIX + 1) + (size_t)LK_PIX * L->levels * 2 * (2 * radius + 1)) * sizeof(float);
   dim3 grid((nf + LK_PIX - 1) / LK_PIX, L->batch);
   if (pyramid_dtype == SLIMB200_DTYPE_BF16) {
     static bool attr_set = false;
     if (!attr_set) {
       SLIMB200_CUDA_TRY(cudaFuncSetAttribute(k_corr_lookup<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             LK_MAX_CH * (LK_PIX + 1) * (int)sizeof(float)));
+                                             LK_SMEM_MAX));
       attr_set = true;
     }
     slimb200_prof_pre(SLIMB200_K_CORR_LOOKUP, stream);
@@ -118,7 +142,7 @@ extern "C" int slimb200_corr_lookup(const void* pyramid, int32_t pyramid_dtype, 
     static bool attr_set = false;
     if (!attr_set) {
       SLIMB200_CUDA_TRY(cudaFuncSetAttribute(k_corr_lookup<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             LK_MAX_CH * (LK_PIX + 1) * (int)sizeof(float)));
+                                             LK_SMEM_MAX));
       attr_set = true;
     }
     slimb200_prof_pre(SLIMB200_K_CORR_LOOKUP, stream);

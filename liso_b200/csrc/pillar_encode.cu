@@ -37,6 +37,7 @@ constexpr int ENC_WARPS = ENC_THREADS / 32;
 constexpr int MAX_COUT = 64;
 constexpr int INV_BASE = 0x7fffffff;
 constexpr int STATS_MAX_CTAS = 148 * 4;
+constexpr int ENC_CTAS_PER_SM = 3;
 
 struct PillarArgs {
   const float* pts[SLIMB200_MAX_BATCH];
@@ -278,9 +279,24 @@ __device__ __forceinline__ unsigned long long bitonic_sort_warp(unsigned long lo
   return v;
 }
 
+// Rank the (<= 32) candidate points of one cell by point index without a sorting network: two
+// counting passes of n shuffles each.  Returns, for destination lane r < n, the source lane holding
+// the r-th smallest index (keys are unique).
+__device__ __forceinline__ int rank_order_small(unsigned idx, int n, int lane) {
+  int rank = 0;
+  for (int j = 0; j < n; ++j) rank += (__shfl_sync(0xffffffffu, idx, j) < idx) ? 1 : 0;
+  if (lane >= n) rank = 32;
+  int src = 0;
+  for (int j = 0; j < n; ++j)
+    if (__shfl_sync(0xffffffffu, rank, j) == lane) src = j;
+  return src;
+}
+
+constexpr int STAGE_PITCH = TILE_CELLS + 4;  // multiple of 4 floats: 128-bit reads of the stage
+
 template <int MODE>  // 0: encode + write canvas, 1: BatchNorm batch statistics only
-__global__ void __launch_bounds__(ENC_THREADS) k_tile_encode(const PillarArgs a) {
-  __shared__ float s_stage[MODE == 0 ? MAX_COUT : 1][TILE_CELLS + 1];
+__global__ void __launch_bounds__(ENC_THREADS, 3) k_tile_encode(const PillarArgs a) {
+  __shared__ __align__(16) float s_stage[MODE == 0 ? MAX_COUT : 1][STAGE_PITCH];
   __shared__ int s_cnt[TILE_CELLS], s_start[TILE_CELLS], s_ord[TILE_CELLS];
   __shared__ unsigned s_mask[TILE_R];
   __shared__ unsigned char s_list[TILE_CELLS];
@@ -291,9 +307,10 @@ __global__ void __launch_bounds__(ENC_THREADS) k_tile_encode(const PillarArgs a)
   const int G0 = p.grid[0], G1 = p.grid[1];
   const int c_out = p.c_out;
   const int max_pts = p.max_points;
+  const bool vec_ok = (G1 & 3) == 0;  // rows are 16-byte aligned: 128-bit stores
 
-  // per-lane slice of the PFN weights: channels lane and lane + 32, canonical 10 columns
-  // [xc yc zc i | dx dy dz | xc yc zc]; a 3-channel cloud has no intensity column.
+  // per-lane slice of the PFN weights (loaded once per persistent CTA): channels lane and lane + 32,
+  // canonical 10 columns [xc yc zc i | dx dy dz | xc yc zc]; a 3-channel cloud has no intensity column.
   float W[2][10], alpha[2], betap[2];
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
@@ -348,14 +365,25 @@ __global__ void __launch_bounds__(ENC_THREADS) k_tile_encode(const PillarArgs a)
         const int n_all = s_cnt[cl], st = s_start[cl];
         const int xi = tx * TILE_R + cl / TILE_C, yi = ty * TILE_C + (cl % TILE_C);
         // --- the max_points lowest point indices of the cell, ascending ------------------
-        unsigned long long key = ~0ull;
         float4 pt = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (lane < n_all) {
-          key = ((unsigned long long)(unsigned)a.sorted_idx[st + lane] << 32) | (unsigned)lane;
-          pt = a.sorted_pts[st + lane];
-        }
-        key = bitonic_sort_warp(key);
-        if (n_all > 32) {
+        int pidx = 0;
+        const int n = n_all < max_pts ? n_all : max_pts;
+        if (n_all <= 32) {
+          unsigned idx = 0xffffffffu;
+          if (lane < n_all) {
+            idx = (unsigned)a.sorted_idx[st + lane];
+            pt = a.sorted_pts[st + lane];
+          }
+          const int src = rank_order_small(idx, n_all, lane);
+          pidx = (int)__shfl_sync(0xffffffffu, idx, src);
+          pt.x = __shfl_sync(0xffffffffu, pt.x, src);
+          pt.y = __shfl_sync(0xffffffffu, pt.y, src);
+          pt.z = __shfl_sync(0xffffffffu, pt.z, src);
+          pt.w = __shfl_sync(0xffffffffu, pt.w, src);
+        } else {
+          // heavy cell: stream the candidates through a bitonic network, keep the lowest max_points
+          unsigned long long key = ((unsigned long long)(unsigned)a.sorted_idx[st + lane] << 32) | (unsigned)lane;
+          key = bitonic_sort_warp(key);
           const int keep = max_pts;  // <= 24: lanes [keep, 32) take new candidates
           for (int base = 32; base < n_all; base += 32 - keep) {
             if (lane >= keep) {
@@ -364,18 +392,8 @@ __global__ void __launch_bounds__(ENC_THREADS) k_tile_encode(const PillarArgs a)
             }
             key = bitonic_sort_warp(key);
           }
-        }
-        const int n = n_all < max_pts ? n_all : max_pts;
-        const int pos = (int)(unsigned)(key & 0xffffffffull);
-        const int pidx = (int)(unsigned)(key >> 32);
-        if (n_all <= 32) {
-          const int src = lane < n ? pos : 0;
-          pt.x = __shfl_sync(0xffffffffu, pt.x, src);
-          pt.y = __shfl_sync(0xffffffffu, pt.y, src);
-          pt.z = __shfl_sync(0xffffffffu, pt.z, src);
-          pt.w = __shfl_sync(0xffffffffu, pt.w, src);
-        } else if (lane < n) {
-          pt = a.sorted_pts[st + pos];
+          pidx = (int)(unsigned)(key >> 32);
+          if (lane < n) pt = a.sorted_pts[st + (int)(unsigned)(key & 0xffffffffull)];
         }
         const bool act = lane < n;
         // --- cluster centre: sum over the slots / num_points (pillar_encoder.py:108-113) ---
@@ -460,19 +478,48 @@ __global__ void __launch_bounds__(ENC_THREADS) k_tile_encode(const PillarArgs a)
     }
 
     if (MODE == 0) {
-      // ---- write the whole tile, zeros included: one 128-byte row segment per warp store -----
-      const int yi = ty * TILE_C + lane;
-      const bool col_ok = yi < G1;
-      for (int it = warp; it < (c_out + 1) * TILE_R; it += ENC_WARPS) {
-        const int c = it / TILE_R, r = it - c * TILE_R;
-        const int xi = tx * TILE_R + r;
-        if (xi >= G0 || !col_ok) continue;
-        const bool occ = total != 0 && ((s_mask[r] >> lane) & 1u);
-        if (c < c_out) {
-          const float v = occ ? s_stage[c][r * TILE_C + lane] : 0.f;
-          a.canvas[(((size_t)b * c_out + c) * G0 + xi) * G1 + yi] = v;
-        } else {
-          a.occupancy[((size_t)b * G0 + xi) * G1 + yi] = occ ? 1.f : 0.f;
+      // ---- write the whole tile, zeros included; every store instruction covers full 128-byte rows ----
+      const size_t plane = (size_t)G0 * G1;
+      float* const cbase = a.canvas + (size_t)b * c_out * plane;
+      float* const obase = a.occupancy + (size_t)b * plane;
+      if (vec_ok) {
+        // 8 lanes x 16 B = one row segment; a warp instruction = the 4 rows of one channel
+        const int r = (tid >> 3) & 3, j = tid & 7;
+        const int xi = tx * TILE_R + r, yi = ty * TILE_C + 4 * j;
+        const bool ok = xi < G0 && yi < G1;
+        const unsigned bits = total != 0 ? (s_mask[r] >> (4 * j)) & 15u : 0u;
+        const size_t off = (size_t)xi * G1 + yi;
+        if (ok) {
+          for (int c = tid >> 5; c < c_out; c += ENC_WARPS) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bits) {
+              v = *reinterpret_cast<const float4*>(&s_stage[c][r * TILE_C + 4 * j]);
+              v.x = (bits & 1u) ? v.x : 0.f;
+              v.y = (bits & 2u) ? v.y : 0.f;
+              v.z = (bits & 4u) ? v.z : 0.f;
+              v.w = (bits & 8u) ? v.w : 0.f;
+            }
+            *reinterpret_cast<float4*>(cbase + c * plane + off) = v;
+          }
+          if ((tid >> 5) == ENC_WARPS - 1) {
+            const float4 o = make_float4((bits & 1u) ? 1.f : 0.f, (bits & 2u) ? 1.f : 0.f, (bits & 4u) ? 1.f : 0.f,
+                                         (bits & 8u) ? 1.f : 0.f);
+            *reinterpret_cast<float4*>(obase + off) = o;
+          }
+        }
+      } else {
+        const int yi = ty * TILE_C + lane;
+        const bool col_ok = yi < G1;
+        for (int it = warp; it < (c_out + 1) * TILE_R; it += ENC_WARPS) {
+          const int c = it / TILE_R, r = it - c * TILE_R;
+          const int xi = tx * TILE_R + r;
+          if (xi >= G0 || !col_ok) continue;
+          const bool occ = total != 0 && ((s_mask[r] >> lane) & 1u);
+          if (c < c_out) {
+            cbase[c * plane + (size_t)xi * G1 + yi] = occ ? s_stage[c][r * TILE_C + lane] : 0.f;
+          } else {
+            obase[(size_t)xi * G1 + yi] = occ ? 1.f : 0.f;
+          }
         }
       }
       __syncthreads();
@@ -668,7 +715,16 @@ extern "C" int slimb200_pillar_encode(const float* const* points, const int32_t*
     SLIMB200_LAUNCH(SLIMB200_K_TILE_ENCODE_STATS, stream, (k_tile_encode<1><<<n_ctas, ENC_THREADS, 0, stream>>>(a)));
     SLIMB200_LAUNCH(SLIMB200_K_BN_FINALIZE, stream, (k_bn_finalize<<<1, MAX_COUT, 0, stream>>>(a, n_ctas)));
   }
-  SLIMB200_LAUNCH(SLIMB200_K_TILE_ENCODE, stream, (k_tile_encode<0><<<a.n_tiles, ENC_THREADS, 0, stream>>>(a)));
+  {
+    static int n_sm = 0;
+    if (n_sm == 0) {
+      int dev = 0;
+      SLIMB200_CUDA_TRY(cudaGetDevice(&dev));
+      SLIMB200_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int n_ctas = a.n_tiles < n_sm * ENC_CTAS_PER_SM ? a.n_tiles : n_sm * ENC_CTAS_PER_SM;
+    SLIMB200_LAUNCH(SLIMB200_K_TILE_ENCODE, stream, (k_tile_encode<0><<<n_ctas, ENC_THREADS, 0, stream>>>(a)));
+  }
   return SLIMB200_OK;
 }
 
