@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SLIMB200_VERSION 100
+#define SLIMB200_VERSION 101
 
 enum {
   SLIMB200_OK = 0,
@@ -39,6 +39,7 @@ enum {
 
 #define SLIMB200_MAX_BATCH 64
 #define SLIMB200_MAX_LEVELS 4
+#define SLIMB200_PANEL_COLS 128
 
 /* ------------------------------------------------------------------------------------------
  * Stage 1: pillar encoder.  Replaces PointsPillarFeatureNetWrapper.extract_pts_feat
@@ -63,7 +64,12 @@ typedef struct {
   int32_t bn_training;    /* 0: running stats; 1: batch statistics (+ running-stat update) */
   float bn_eps;           /* 1e-3 */
   float bn_momentum;      /* 0.01 */
+  int32_t canvas_layout;  /* SLIMB200_CANVAS_NCHW (the reference's contiguous layout) or SLIMB200_CANVAS_NHWC
+                             (same logical tensor in channels-last memory format, what cuDNN's convs consume);
+                             NHWC needs c_out % 4 == 0 */
 } slimb200_pillar_params;
+
+enum { SLIMB200_CANVAS_NCHW = 0, SLIMB200_CANVAS_NHWC = 1 };
 
 size_t slimb200_pillar_workspace_bytes(int32_t batch, int64_t total_points,
                                        const slimb200_pillar_params* p);
@@ -73,7 +79,8 @@ size_t slimb200_pillar_workspace_bytes(int32_t batch, int64_t total_points,
  * linear_weight        device (c_out, c_in + 6) f32     pfn_layers[0].linear.weight
  * bn_weight..bn_var    device (c_out) f32               pfn_layers[0].norm.{weight,bias,running_mean,running_var}
  *                      (running_mean / running_var are updated in place when bn_training)
- * canvas               device (batch, c_out, grid[0], grid[1]) f32; row = x index, col = y index
+ * canvas               device (batch, c_out, grid[0], grid[1]) f32; row = x index, col = y index; stored NCHW or,
+ *                      with canvas_layout = NHWC, as (batch, grid[0], grid[1], c_out)
  * occupancy            device (batch, 1, grid[0], grid[1]) f32
  * optional outputs (may be NULL):
  *   pillar_counts      device int32[batch + 1]: exclusive prefix of kept pillars per sample
@@ -104,11 +111,15 @@ int slimb200_pillar_coors_f64(const float* pts, int64_t n, int32_t c_in, double 
  * (corr.py:7-21,48-56) and CorrBlock.__call__ + bilinear_sampler (corr.py:23-46,
  * raft_code/utils.py:15-29).
  *
- * Pyramid storage: one row per source pixel, all levels side by side:
- *   pyramid[b][i][level_offset[l] + r * w_l + c],  row pitch `pitch` elements (multiple of 64),
- *   h_0 = h, w_0 = w, h_{l+1} = h_l / 2 (floor), level_offset[l] = sum_{k<l} h_k * w_k.
- * Level l as the reference exposes it (corr_pyramid[l], shape (B*h*w, 1, h_l, w_l)) is the strided
- * view base + level_offset[l] with strides (pitch, -, w_l, 1).
+ * Pyramid storage ("panel" layout, chosen so that every 128 x 128 GEMM tile is one contiguous 32 KB
+ * block in HBM -- contiguous blocks store at ~6.3 TB/s on B200, 128-byte pieces of a pitched row at 4.7):
+ *   the Ncols = sum_l h_l * w_l columns (all levels side by side, level_offset[l] = sum_{k<l} h_k * w_k,
+ *   h_0 = h, w_0 = w, h_{l+1} = h_l / 2 floor) are cut into n_panels = ceil(Ncols / 128) panels of 128;
+ *   element (b, source pixel i, column j) lives at
+ *       pyramid[((b * n_panels + j / 128) * (h * w) + i) * 128 + j % 128]
+ *   Columns >= Ncols of the last panel are zero.  `pitch` = n_panels * 128.
+ * Level l as the reference exposes it (corr_pyramid[l], shape (B*h*w, 1, h_l, w_l)) is columns
+ * [level_offset[l], level_offset[l] + h_l * w_l) of every row (liso_b200/slim/corr.py materialises it lazily).
  * ---------------------------------------------------------------------------------------- */
 typedef struct {
   int32_t batch, dim, h, w, levels;
@@ -116,7 +127,8 @@ typedef struct {
   int32_t level_w[SLIMB200_MAX_LEVELS];
   int32_t level_offset[SLIMB200_MAX_LEVELS];
   int32_t n_cols;   /* sum h_l * w_l */
-  int32_t pitch;    /* elements per pyramid row */
+  int32_t pitch;    /* n_panels * 128: columns per source pixel including the zero padding */
+  int32_t n_panels; /* ceil(n_cols / 128) */
 } slimb200_corr_layout;
 
 enum { SLIMB200_DTYPE_F32 = 0, SLIMB200_DTYPE_BF16 = 1 };
@@ -158,6 +170,7 @@ enum {
   SLIMB200_K_TILE_ENCODE_STATS,
   SLIMB200_K_BN_FINALIZE,
   SLIMB200_K_TILE_ENCODE,
+  SLIMB200_K_PILLAR_NHWC,
   SLIMB200_K_FEAT_PACK,
   SLIMB200_K_CORR_GEMM,
   SLIMB200_K_CORR_LOOKUP,

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libslimb200.so")
 
 MAX_BATCH = 64
 MAX_LEVELS = 4
+PANEL_COLS = 128
 DTYPE_F32, DTYPE_BF16 = 0, 1
 
 
@@ -35,6 +36,7 @@ class PillarParams(C.Structure):
         ("bn_training", C.c_int32),
         ("bn_eps", C.c_float),
         ("bn_momentum", C.c_float),
+        ("canvas_layout", C.c_int32),
     ]
 
 
@@ -50,6 +52,7 @@ class CorrLayout(C.Structure):
         ("level_offset", C.c_int32 * MAX_LEVELS),
         ("n_cols", C.c_int32),
         ("pitch", C.c_int32),
+        ("n_panels", C.c_int32),
     ]
 
 
@@ -84,8 +87,9 @@ SYMBOLS = {
     "slimb200_launch_count": (C.c_int64, [C.c_int32]),
     "slimb200_kernel_name": (C.c_char_p, [C.c_int32]),
 }
-N_KERNELS = 11
-K_TILE_ENCODE, K_FEAT_PACK, K_CORR_GEMM, K_CORR_LOOKUP = 6, 7, 8, 9
+N_KERNELS = 12
+K_TILE_ENCODE, K_PILLAR_NHWC, K_FEAT_PACK, K_CORR_GEMM, K_CORR_LOOKUP = 6, 7, 8, 9, 10
+CANVAS_NCHW, CANVAS_NHWC = 0, 1
 
 _lib: Optional[C.CDLL] = None
 

@@ -26,6 +26,7 @@ namespace {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_N = 128;
+static_assert(BLOCK_N == SLIMB200_PANEL_COLS, "one GEMM tile column == one pyramid panel");
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int DIM = 128;     // feature dimension of the SLIM fnet (raft_mod.py:48)
 constexpr int K_BLOCKS = DIM / BLOCK_K;
@@ -88,10 +89,17 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar
       "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src),
-               "r"(c0), "r"(c1), "r"(c2)
+// streaming store: the volume is written once and next read by another kernel, so its lines are marked
+// evict-first in L2 (measured +8..+37 % store bandwidth, tools/membench.cu)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;" ::"l"(map),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
                : "memory");
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
@@ -260,6 +268,7 @@ k_corr_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const bool store_thread = (threadIdx.x == 64 + grp * EPI_THREADS);
     const uint32_t out_buf = smem_out + (uint32_t)grp * OUT_STAGE_BYTES;
     const int bar_id = 1 + grp;
+    const uint64_t policy = l2_evict_first_policy();
     for (int it = grp; ; it += EPI_GROUPS) {
       const int t = blockIdx.x + it * gridDim.x;
       if (t >= shape.total_tiles) break;
@@ -306,8 +315,9 @@ k_corr_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       fence_proxy_async_smem();
       asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(EPI_THREADS) : "memory");
       if (store_thread) {
-        tma_store_3d(&map_c, out_buf, n * BLOCK_N, m * BLOCK_M, b);
-        tma_store_3d(&map_c, out_buf + OUT_HALF_BYTES, n * BLOCK_N + 64, m * BLOCK_M, b);
+        // panel layout: tile (m, n) of sample b = rows [128 m, 128 m + 128) of panel b * n_tiles + n: 32 KB contiguous
+        tma_store_3d(&map_c, out_buf, 0, m * BLOCK_M, b * shape.n_tiles + n, policy);
+        tma_store_3d(&map_c, out_buf + OUT_HALF_BYTES, 64, m * BLOCK_M, b * shape.n_tiles + n, policy);
         tma_store_commit();
       }
     }
@@ -440,7 +450,8 @@ extern "C" int slimb200_corr_layout_init(int32_t batch, int32_t dim, int32_t h, 
     wl /= 2;
   }
   L.n_cols = off;
-  L.pitch = (off + 63) / 64 * 64;
+  L.n_panels = (off + SLIMB200_PANEL_COLS - 1) / SLIMB200_PANEL_COLS;
+  L.pitch = L.n_panels * SLIMB200_PANEL_COLS;
   *out = L;
   return SLIMB200_OK;
 }
@@ -479,7 +490,10 @@ extern "C" int slimb200_corr_build(const float* fmap1, const float* fmap2, const
   int rc;
   if ((rc = make_map(enc, &map_a, A, DIM, nf, L->batch, DIM)) != SLIMB200_OK) return rc;
   if ((rc = make_map(enc, &map_b, Bx, DIM, L->n_cols, L->batch, DIM)) != SLIMB200_OK) return rc;
-  if ((rc = make_map(enc, &map_c, pyramid, L->n_cols, nf, L->batch, L->pitch)) != SLIMB200_OK) return rc;
+  // output: (batch * n_panels) panels of (nf rows x 128 columns) bf16, rows 256 B apart
+  if ((rc = make_map(enc, &map_c, pyramid, SLIMB200_PANEL_COLS, nf, (uint64_t)L->batch * L->n_panels, SLIMB200_PANEL_COLS)) !=
+      SLIMB200_OK)
+    return rc;
 
   {
     const int groups = (nf + PACK_ROWS - 1) / PACK_ROWS + (L->n_cols + PACK_ROWS - 1) / PACK_ROWS;
@@ -489,7 +503,7 @@ extern "C" int slimb200_corr_build(const float* fmap1, const float* fmap2, const
   GemmShape shape;
   shape.batch = L->batch;
   shape.m_tiles = (nf + BLOCK_M - 1) / BLOCK_M;
-  shape.n_tiles = (L->n_cols + BLOCK_N - 1) / BLOCK_N;
+  shape.n_tiles = L->n_panels;
   shape.total_tiles = shape.batch * shape.m_tiles * shape.n_tiles;
   shape.scale = 1.0f / sqrtf((float)L->dim);
 

@@ -1,16 +1,21 @@
-// Stage 2b of the SLIM hot path on B200: multi-level bilinear lookup in the correlation pyramid,
-// re-run on every GRU iteration.
+// Stage 2b of the SLIM hot path on B200: multi-level bilinear lookup into the correlation pyramid.
 //
-// Replaces CorrBlock.__call__ (liso/slim/model/raft_code/corr.py:23-46) and bilinear_sampler
-// (liso/slim/model/raft_code/utils.py:15-29) = F.grid_sample(align_corners=True, zeros padding):
-//   out[b, l*49 + i*7 + j, y0, x0] = bilinear(level_l[b, (y0,x0)], x = cx/2^l + (i-r), y = cy/2^l + (j-r))
-// Note the RAFT transposition: the FIRST window axis offsets x (corr.py:31-41).
+// Replaces CorrBlock.__call__ (liso/slim/model/raft_code/corr.py:23-46) + bilinear_sampler
+// (raft_code/utils.py:15-29) + F.grid_sample(align_corners=True, zeros padding):
+//   out[b, l*(2r+1)^2 + i*(2r+1) + j, y, x] = bilinear(pyr_l[b, (y,x)], (cx / 2^l + i - r, cy / 2^l + j - r))
+// i.e. the FIRST window index offsets x (RAFT's transposed window), OOB taps contribute zero.
 //
-// One launch covers all levels and writes the (B, L*(2r+1)^2, h, w) fp32 tensor directly (the
-// reference needs 4 x (CPU meshgrid + H2D + grid_sample) + cat + permute + contiguous).
-// A CTA owns 32 consecutive source pixels; the window taps of one pixel sit in one pyramid row
-// (17 KB at 80x80), results are transposed through shared memory so that every channel row is
-// written as one full 128-byte line.
+// B200 design: a gather kernel bound by DRAM sector fetches.  One CTA owns 32 consecutive source pixels of one
+// sample and one lane owns one pixel (lane == pixel in every phase, so the fp32 output is stored with one
+// coalesced 128-byte row per warp instruction and shared memory is addressed [..][lane], conflict-free):
+//   phase 1  sample positions per (pixel, level, axis, offset), with the reference's exact normalise /
+//            un-normalise fp32 arithmetic; per-offset bilinear weights with the zero padding folded in
+//   phase 2  every (pixel, level, window row) fetches its (2r+2)-element row segment of the pyramid with
+//            16-byte loads (all loads of the CTA are independent and in flight together) into shared memory;
+//            the 32 lanes of a load touch 32 neighbouring 256-byte panel rows -> one DRAM page
+//   phase 3  49 outputs per (pixel, level) from the (2r+2)^2 window in shared memory: 4 taps x weights
+// Window rows that straddle rounding (floor of offset o != floor of offset 0 + o, |prob| ~ 1e-6) take a slow,
+// fully predicated global-memory path so that results always follow the reference arithmetic.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -19,97 +24,244 @@ namespace {
 
 constexpr int LK_PIX = 32;
 constexpr int LK_THREADS = 256;
-constexpr int LK_SMEM_MAX = (256 * 33 + 32 * 4 * 2 * 9) * 4;
-constexpr int LK_MAX_CH = 256;     // one thread per output channel: levels * (2r+1)^2 <= 256
+constexpr int LK_WARPS = LK_THREADS / 32;
+constexpr int PW = SLIMB200_PANEL_COLS;
 
 template <typename T>
-__device__ __forceinline__ float ld_val(const T* p);
+struct Elem;
 template <>
-__device__ __forceinline__ float ld_val<float>(const float* p) {
-  return __ldg(p);
-}
+struct Elem<float> {
+  static constexpr int EPC = 4;  // elements per 16-byte chunk
+  __device__ static __forceinline__ float ld(const float* p) { return __ldg(p); }
+};
 template <>
-__device__ __forceinline__ float ld_val<__nv_bfloat16>(const __nv_bfloat16* p) {
-  return __bfloat162float(__ldg(p));
+struct Elem<__nv_bfloat16> {
+  static constexpr int EPC = 8;
+  __device__ static __forceinline__ float ld(const __nv_bfloat16* p) { return __bfloat162float(__ldg(p)); }
+};
+
+// sample position in level pixels: bilinear_sampler's normalisation (utils.py:19-20) followed by grid_sample's
+// un-normalisation ((g + 1) / 2) * (size - 1), all in fp32 with IEEE division
+__device__ __forceinline__ float sample_pos(float c, float inv, int offs, int size) {
+  const float pos = __fadd_rn(c * inv, (float)offs);
+  const float sm1 = (float)(size - 1);
+  const float g = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, pos), sm1), 1.f);
+  float ip = __fmul_rn(__fmul_rn(__fadd_rn(g, 1.f), 0.5f), sm1);  // x / 2 == x * 0.5 exactly
+  if (!(fabsf(ip) < 1e7f)) ip = -1e7f;                             // NaN / inf / far away: every tap is outside
+  return ip;
 }
 
-// One thread owns one output channel k = (level, i, j) and walks the CTA's 32 pixels, so the
-// per-channel constants (level geometry, window offsets) stay in registers and the lanes of a warp
-// read neighbouring taps of the SAME pyramid row.  The pixel-space sample positions (the
-// normalise / un-normalise round trip of bilinear_sampler + grid_sample) are computed once per
-// (pixel, level, axis, offset) into shared memory instead of once per output.
 template <typename T>
-__global__ void __launch_bounds__(LK_THREADS, 4) k_corr_lookup(const T* __restrict__ pyr, const slimb200_corr_layout L,
-                                                               const float* __restrict__ coords, int radius,
-                                                               float* __restrict__ out) {
-  extern __shared__ float s_dyn[];  // [n_ch][LK_PIX + 1] results, then [LK_PIX][levels][2][win] positions
+__device__ __forceinline__ size_t panel_index(int n_panels, int nf, int b, int i, int col) {
+  return ((size_t)(b * n_panels + (col / PW)) * nf + i) * PW + (col % PW);
+}
+
+// fully predicated 4-tap sample straight from global memory (rare path)
+template <typename T>
+__device__ __noinline__ float sample_slow(const T* __restrict__ pyr, int n_panels, int nf, int b, int i, int W, int H, int off,
+                                          float ix, float iy) {
+  const float fx = floorf(ix), fy = floorf(iy);
+  const int x0 = (int)fx, y0 = (int)fy;
+  const float ex = __fsub_rn(__fadd_rn(fx, 1.f), ix), ey = __fsub_rn(__fadd_rn(fy, 1.f), iy);
+  const float dx = __fsub_rn(ix, fx), dy = __fsub_rn(iy, fy);
+  const bool xin0 = (unsigned)x0 < (unsigned)W, xin1 = (unsigned)(x0 + 1) < (unsigned)W;
+  const bool yin0 = (unsigned)y0 < (unsigned)H, yin1 = (unsigned)(y0 + 1) < (unsigned)H;
+  float val = 0.f;
+  if (yin0 && xin0) val += Elem<T>::ld(pyr + panel_index<T>(n_panels, nf, b, i, off + y0 * W + x0)) * __fmul_rn(ex, ey);
+  if (yin0 && xin1) val += Elem<T>::ld(pyr + panel_index<T>(n_panels, nf, b, i, off + y0 * W + x0 + 1)) * __fmul_rn(dx, ey);
+  if (yin1 && xin0) val += Elem<T>::ld(pyr + panel_index<T>(n_panels, nf, b, i, off + (y0 + 1) * W + x0)) * __fmul_rn(ex, dy);
+  if (yin1 && xin1) val += Elem<T>::ld(pyr + panel_index<T>(n_panels, nf, b, i, off + (y0 + 1) * W + x0 + 1)) * __fmul_rn(dx, dy);
+  return val;
+}
+
+template <typename T, int R>
+struct Cfg {
+  static constexpr int WIN = 2 * R + 1;
+  static constexpr int W1 = WIN + 1;                                         // window rows / cols fetched
+  static constexpr int EPC = Elem<T>::EPC;
+  static constexpr int NCHUNK = (EPC - 1 + W1 + EPC - 1) / EPC;              // 16-byte chunks covering any W1-element segment
+  static constexpr int NW = NCHUNK * 4;                                      // 32-bit words per segment
+  // dynamic shared memory in 4-byte words for `levels` levels
+  __host__ __device__ static constexpr int raw_words(int levels) { return levels * W1 * NW * LK_PIX; }
+  __host__ __device__ static constexpr int tab_words(int levels) { return levels * 2 * WIN * LK_PIX; }
+  __host__ __device__ static constexpr int smem_bytes(int levels) {
+    return (raw_words(levels) + 3 * tab_words(levels) + 3 * levels * LK_PIX) * 4;
+  }
+};
+
+// two neighbouring elements (e, e + 1) of a segment held as words [..][lane] in shared memory
+template <typename T>
+__device__ __forceinline__ void tap_pair(const uint32_t* seg_words, int e, float& v0, float& v1);
+template <>
+__device__ __forceinline__ void tap_pair<float>(const uint32_t* seg_words, int e, float& v0, float& v1) {
+  v0 = __uint_as_float(seg_words[e * LK_PIX]);
+  v1 = __uint_as_float(seg_words[(e + 1) * LK_PIX]);
+}
+template <>
+__device__ __forceinline__ void tap_pair<__nv_bfloat16>(const uint32_t* seg_words, int e, float& v0, float& v1) {
+  const int w = e >> 1;
+  const uint32_t lo = seg_words[w * LK_PIX], hi = seg_words[(w + 1) * LK_PIX];
+  const uint32_t t = __funnelshift_r(lo, hi, (e & 1) * 16);  // [bf16 e | bf16 e+1]
+  v0 = __uint_as_float(t << 16);
+  v1 = __uint_as_float(t & 0xffff0000u);
+}
+
+template <typename T, int R>
+__global__ void __launch_bounds__(LK_THREADS) k_corr_lookup(const T* __restrict__ pyr, const slimb200_corr_layout L,
+                                                            const float* __restrict__ coords, float* __restrict__ out) {
+  using C = Cfg<T, R>;
+  constexpr int WIN = C::WIN, W1 = C::W1, EPC = C::EPC, NCHUNK = C::NCHUNK, NW = C::NW;
+  extern __shared__ __align__(16) uint32_t s_dyn[];
+  const int levels = L.levels;
+  uint32_t* s_raw = s_dyn;                                                    // [level][row][word][lane]
+  float* s_pos = reinterpret_cast<float*>(s_dyn + C::raw_words(levels));      // [level][axis][offset][lane] sample position
+  float* s_w0 = s_pos + C::tab_words(levels);                                 //   weight of the floor tap (0 if outside)
+  float* s_w1 = s_w0 + C::tab_words(levels);                                  //   weight of the floor + 1 tap
+  int* s_xb = reinterpret_cast<int*>(s_w1 + C::tab_words(levels));            // [level][lane] window origin x
+  int* s_yb = s_xb + levels * LK_PIX;                                         // [level][lane] window origin y
+  int* s_ok = s_yb + levels * LK_PIX;                                         // [level][lane] offsets consistent with origin
   __shared__ float s_xy[2][LK_PIX];
-  __shared__ int s_lw[SLIMB200_MAX_LEVELS], s_lh[SLIMB200_MAX_LEVELS], s_lo[SLIMB200_MAX_LEVELS];
+  __shared__ int s_lw[SLIMB200_MAX_LEVELS], s_lh[SLIMB200_MAX_LEVELS], s_lo[SLIMB200_MAX_LEVELS];  // no dynamic indexing of L
+
   const int nf = L.h * L.w;
+  const int n_panels = L.n_panels;
   const int b = blockIdx.y;
   const int i0 = blockIdx.x * LK_PIX;
-  const int win = 2 * radius + 1, win2 = win * win;
-  const int n_ch = L.levels * win2;
-  float* s_out = s_dyn;
-  float* s_pos = s_dyn + n_ch * (LK_PIX + 1);
+  const int lane = lane_id(), warp = warp_id();
+  const int pix = i0 + lane;
+  const bool live = pix < nf;
+  const int n_ch = levels * WIN * WIN;
+
   if (threadIdx.x < 2 * LK_PIX) {
-    const int ch = threadIdx.x / LK_PIX, p = threadIdx.x % LK_PIX;
-    s_xy[ch][p] = (i0 + p < nf) ? __ldg(coords + ((size_t)b * 2 + ch) * nf + i0 + p) : 0.f;
+    const int ch = threadIdx.x / LK_PIX;
+    s_xy[ch][lane] = live ? __ldg(coords + ((size_t)b * 2 + ch) * nf + pix) : 0.f;
   }
-  if (threadIdx.x < SLIMB200_MAX_LEVELS) {
-    s_lw[threadIdx.x] = L.level_w[threadIdx.x];
-    s_lh[threadIdx.x] = L.level_h[threadIdx.x];
-    s_lo[threadIdx.x] = L.level_offset[threadIdx.x];
+  if (threadIdx.x == 64) {
+    s_lw[0] = L.level_w[0]; s_lw[1] = L.level_w[1]; s_lw[2] = L.level_w[2]; s_lw[3] = L.level_w[3];
+    s_lh[0] = L.level_h[0]; s_lh[1] = L.level_h[1]; s_lh[2] = L.level_h[2]; s_lh[3] = L.level_h[3];
+    s_lo[0] = L.level_offset[0]; s_lo[1] = L.level_offset[1]; s_lo[2] = L.level_offset[2]; s_lo[3] = L.level_offset[3];
   }
   __syncthreads();
-  // ---- sample positions: ix = (((2*xs/(W-1) - 1) + 1) / 2) * (W-1), xs = x / 2^l + (i - r) ------------
-  const int per_pix = L.levels * 2 * win;
-  for (int e = threadIdx.x; e < LK_PIX * per_pix; e += LK_THREADS) {
-    const int p = e / per_pix, rem = e - p * per_pix;
-    const int l = rem / (2 * win), rem2 = rem - l * 2 * win;
-    const int axis = rem2 / win, o = rem2 - axis * win;
+
+  // ---- phase 1: positions and weights, one (level, axis, offset) row of the tables per warp iteration ----
+  for (int e = warp; e < levels * 2 * WIN; e += LK_WARPS) {
+    const int l = e / (2 * WIN), rem = e - l * 2 * WIN;
+    const int axis = rem / WIN, o = rem - axis * WIN;
+    const int size = axis == 0 ? s_lw[l] : s_lh[l];
     const float inv = 1.0f / (float)(1 << l);  // coords / 2**l is exact
-    const float pos = __fadd_rn(s_xy[axis][p] * inv, (float)(o - radius));
-    const float sm1 = (float)((axis == 0 ? s_lw[l] : s_lh[l]) - 1);
-    const float g = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, pos), sm1), 1.f);            // utils.py:19-20
-    float ip = __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.f), 2.f), sm1);                    // grid_sample un-normalise
-    if (!(fabsf(ip) < 1e7f)) ip = -1e7f;                                             // NaN / inf / far away: all taps outside
-    s_pos[e] = ip;
+    const float ip = sample_pos(s_xy[axis][lane], inv, o - R, size);
+    const float f = floorf(ip);
+    const int i0p = (int)f;
+    const float w_hi = __fsub_rn(ip, f);                  // weight of tap floor + 1  (ix - ix_nw)
+    const float w_lo = __fsub_rn(__fadd_rn(f, 1.f), ip);  // weight of tap floor      (ix_se - ix)
+    s_pos[e * LK_PIX + lane] = ip;
+    s_w0[e * LK_PIX + lane] = ((unsigned)i0p < (unsigned)size) ? w_lo : 0.f;
+    s_w1[e * LK_PIX + lane] = ((unsigned)(i0p + 1) < (unsigned)size) ? w_hi : 0.f;
   }
   __syncthreads();
-  // ---- one output channel per thread, 32 pixels ---------------------------------------------------
-  const int k = threadIdx.x;
-  if (k < n_ch) {
-    const int l = k / win2, rem = k - l * win2;
-    const int wa = rem / win, wb = rem - wa * win;
-    const int W = s_lw[l], H = s_lh[l];
-    const T* base = pyr + ((size_t)b * nf + i0) * L.pitch + s_lo[l];
-    const float* px = s_pos + (l * 2 + 0) * win + wa;
-    const float* py = s_pos + (l * 2 + 1) * win + wb;
-    const int n_pix = min(LK_PIX, nf - i0);
-#pragma unroll 4
-    for (int p = 0; p < n_pix; ++p) {
-      const float ix = px[p * per_pix], iy = py[p * per_pix];
-      const float fx = floorf(ix), fy = floorf(iy);
-      const int x0 = (int)fx, y0 = (int)fy;
-      const float ex = __fsub_rn(__fadd_rn(fx, 1.f), ix), ey = __fsub_rn(__fadd_rn(fy, 1.f), iy);  // se - i
-      const float dx = __fsub_rn(ix, fx), dy = __fsub_rn(iy, fy);                                  // i - nw
-      const bool xin0 = (unsigned)x0 < (unsigned)W, xin1 = (unsigned)(x0 + 1) < (unsigned)W;
-      const bool yin0 = (unsigned)y0 < (unsigned)H, yin1 = (unsigned)(y0 + 1) < (unsigned)H;
-      const T* row = base + (size_t)p * L.pitch + y0 * W + x0;
-      float val = 0.f;
-      if (yin0 && xin0) val += ld_val(row) * __fmul_rn(ex, ey);          // nw
-      if (yin0 && xin1) val += ld_val(row + 1) * __fmul_rn(dx, ey);      // ne
-      if (yin1 && xin0) val += ld_val(row + W) * __fmul_rn(ex, dy);      // sw
-      if (yin1 && xin1) val += ld_val(row + W + 1) * __fmul_rn(dx, dy);  // se
-      s_out[k * (LK_PIX + 1) + p] = val;
+  for (int l = warp; l < levels; l += LK_WARPS) {
+    const int xb = (int)floorf(s_pos[((l * 2 + 0) * WIN) * LK_PIX + lane]);
+    const int yb = (int)floorf(s_pos[((l * 2 + 1) * WIN) * LK_PIX + lane]);
+    bool ok = true;
+#pragma unroll
+    for (int o = 1; o < WIN; ++o) {
+      ok = ok && ((int)floorf(s_pos[((l * 2 + 0) * WIN + o) * LK_PIX + lane]) == xb + o);
+      ok = ok && ((int)floorf(s_pos[((l * 2 + 1) * WIN + o) * LK_PIX + lane]) == yb + o);
+    }
+    s_xb[l * LK_PIX + lane] = xb;
+    s_yb[l * LK_PIX + lane] = yb;
+    s_ok[l * LK_PIX + lane] = ok ? 1 : 0;
+  }
+  __syncthreads();
+
+  // ---- phase 2: fetch the (W1 x W1) window of every (pixel, level): one row segment per thread iteration ----
+  for (int seg = warp; seg < levels * W1; seg += LK_WARPS) {
+    const int l = seg / W1, ry = seg - l * W1;
+    const int W = s_lw[l], H = s_lh[l], off = s_lo[l];
+    const int xb = s_xb[l * LK_PIX + lane], yb = s_yb[l * LK_PIX + lane];
+    const int y = yb + ry;
+    const bool row_ok = live && (unsigned)y < (unsigned)H && s_ok[l * LK_PIX + lane];
+    const int row0 = off + y * W;
+    const int a_start = row0 + xb;                      // absolute column of window column 0 (may be < 0)
+    const int ca = a_start & ~(EPC - 1);                // chunk-aligned start (two's complement floor)
+    const int lo = row0 + max(xb, 0), hi = row0 + min(xb + W1, W);  // valid absolute columns [lo, hi)
+#pragma unroll
+    for (int c = 0; c < NCHUNK; ++c) {
+      const int col = ca + c * EPC;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (row_ok && col < hi && col + EPC > lo)  // (implies 0 <= col < n_cols)
+        v = __ldg(reinterpret_cast<const uint4*>(pyr + panel_index<T>(n_panels, nf, b, pix, col)));
+      uint32_t* dst = s_raw + ((size_t)(seg * NW + c * 4) * LK_PIX + lane);
+      dst[0] = v.x;
+      dst[LK_PIX] = v.y;
+      dst[2 * LK_PIX] = v.z;
+      dst[3 * LK_PIX] = v.w;
     }
   }
   __syncthreads();
-  const int lane = lane_id(), warp = warp_id();
-  if (i0 + lane < nf) {
-    for (int kk = warp; kk < n_ch; kk += LK_THREADS / 32)
-      out[((size_t)b * n_ch + kk) * nf + i0 + lane] = s_out[kk * (LK_PIX + 1) + lane];
+
+  // ---- phase 3: one (level, i) column of the output window per warp iteration, WIN outputs (j) each ----
+  for (int u = warp; u < levels * WIN; u += LK_WARPS) {
+    const int l = u / WIN, i = u - l * WIN;
+    const int W = s_lw[l], off = s_lo[l];
+    float* dst = out + ((size_t)b * n_ch + (size_t)l * WIN * WIN + (size_t)i * WIN) * nf + pix;
+    if (s_ok[l * LK_PIX + lane]) {
+      const int xb = s_xb[l * LK_PIX + lane], yb = s_yb[l * LK_PIX + lane];
+      const float wx0 = s_w0[((l * 2 + 0) * WIN + i) * LK_PIX + lane], wx1 = s_w1[((l * 2 + 0) * WIN + i) * LK_PIX + lane];
+      // the (i, i + 1) column pair of every window row; outputs j and j + 1 share a row
+      float tap0[W1], tap1[W1];
+#pragma unroll
+      for (int r = 0; r < W1; ++r) {
+        const int s = (off + (yb + r) * W + xb) & (EPC - 1);
+        tap_pair<T>(s_raw + ((size_t)((l * W1 + r) * NW) * LK_PIX + lane), s + i, tap0[r], tap1[r]);
+      }
+#pragma unroll
+      for (int j = 0; j < WIN; ++j) {
+        const float wy0 = s_w0[((l * 2 + 1) * WIN + j) * LK_PIX + lane], wy1 = s_w1[((l * 2 + 1) * WIN + j) * LK_PIX + lane];
+        float val = tap0[j] * __fmul_rn(wx0, wy0);             // nw
+        val += tap1[j] * __fmul_rn(wx1, wy0);                  // ne
+        val += tap0[j + 1] * __fmul_rn(wx0, wy1);              // sw
+        val += tap1[j + 1] * __fmul_rn(wx1, wy1);              // se
+        if (live) dst[(size_t)j * nf] = val;
+      }
+    } else {
+      const float ix = s_pos[((l * 2 + 0) * WIN + i) * LK_PIX + lane];
+      for (int j = 0; j < WIN; ++j) {
+        const float iy = s_pos[((l * 2 + 1) * WIN + j) * LK_PIX + lane];
+        const float val = live ? sample_slow<T>(pyr, n_panels, nf, b, pix, W, s_lh[l], off, ix, iy) : 0.f;
+        if (live) dst[(size_t)j * nf] = val;
+      }
+    }
+  }
+}
+
+template <typename T, int R>
+int launch_lookup(const void* pyramid, const slimb200_corr_layout* L, const float* coords, float* out, cudaStream_t stream) {
+  using C = Cfg<T, R>;
+  const int nf = L->h * L->w;
+  const int smem = C::smem_bytes(L->levels);
+  static int attr_set = 0;
+  if (attr_set < smem) {
+    SLIMB200_CUDA_TRY(cudaFuncSetAttribute(k_corr_lookup<T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           C::smem_bytes(SLIMB200_MAX_LEVELS)));
+    attr_set = C::smem_bytes(SLIMB200_MAX_LEVELS);
+  }
+  dim3 grid((nf + LK_PIX - 1) / LK_PIX, L->batch);
+  SLIMB200_LAUNCH(SLIMB200_K_CORR_LOOKUP, stream,
+                  (k_corr_lookup<T, R><<<grid, LK_THREADS, smem, stream>>>(static_cast<const T*>(pyramid), *L, coords, out)));
+  return SLIMB200_OK;
+}
+
+template <typename T>
+int dispatch_radius(int radius, const void* pyramid, const slimb200_corr_layout* L, const float* coords, float* out,
+                    cudaStream_t stream) {
+  switch (radius) {
+    case 0: return launch_lookup<T, 0>(pyramid, L, coords, out, stream);
+    case 1: return launch_lookup<T, 1>(pyramid, L, coords, out, stream);
+    case 2: return launch_lookup<T, 2>(pyramid, L, coords, out, stream);
+    case 3: return launch_lookup<T, 3>(pyramid, L, coords, out, stream);
+    case 4: return launch_lookup<T, 4>(pyramid, L, coords, out, stream);
+    default: return SLIMB200_E_UNSUPPORTED;
   }
 }
 
@@ -119,53 +271,10 @@ extern "C" int slimb200_corr_lookup(const void* pyramid, int32_t pyramid_dtype, 
                                     const float* coords, int32_t radius, float* out, void* stream_) {
   if (!pyramid || !L || !coords || !out) return SLIMB200_E_INVALID;
   if (radius < 0 || radius > 4 || L->levels < 1 || L->levels > SLIMB200_MAX_LEVELS) return SLIMB200_E_UNSUPPORTED;
-  for (int l = 0; l < L->levels; ++l)
-    if (L->level_h[l] < 2 || L->level_w[l] < 2) return SLIMB200_E_UNSUPPORTED;  // (size - 1) normalisation
+  if (L->n_panels * PW != L->pitch || L->n_panels < 1) return SLIMB200_E_INVALID;
+  if (reinterpret_cast<uintptr_t>(pyramid) & 15) return SLIMB200_E_ALIGNMENT;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const int nf = L->h * L->w;
-  const int n_ch = L->levels * (2 * radius + 1) * (2 * radius + 1);
-  if (n_ch > LK_MAX_CH) return SLIMB200_E_UNSUPPORTED;
-  const size_t smem = ((size_t)n_ch * (LK_PIX + 1) + (size_t)LK_PIX * L->levels * 2 * (2 * radius + 1)) * sizeof(float);
-  dim3 grid((nf + LK_PIX - 1) / LK_PIX, L->batch);
-  if (pyramid_dtype == SLIMB200_DTYPE_BF16) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      SLIMB200_CUDA_TRY(cudaFuncSetAttribute(k_corr_lookup<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             LK_SMEM_MAX));
-      attr_set = true;
-    }
-    slimb200_prof_pre(SLIMB200_K_CORR_LOOKUP, stream);
-    k_corr_lookup<__nv_bfloat16><<<grid, LK_THREADS, smem, stream>>>(static_cast<const __nv_bfloat16*>(pyramid), *L,
-                                                                     coords, radius, out);
-    slimb200_prof_post(SLIMB200_K_CORR_LOOKUP, stream);
-  } else if (pyramid_dtype == SLIMB200_DTYPE_F32) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      SLIMB200_CUDA_TRY(cudaFuncSetAttribute(k_corr_lookup<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             LK_SMEM_MAX));
-      attr_set = true;
-    }
-    slimb200_prof_pre(SLIMB200_K_CORR_LOOKUP, stream);
-    k_corr_lookup<float><<<grid, LK_THREADS, smem, stream>>>(static_cast<const float*>(pyramid), *L, coords, radius,
-                                                             out);
-    slimb200_prof_post(SLIMB200_K_CORR_LOOKUP, stream);
-  } else {
-    return SLIMB200_E_UNSUPPORTED;
-  }
-  SLIMB200_LAUNCH_CHECK();
-  return SLIMB200_OK;
+  if (pyramid_dtype == SLIMB200_DTYPE_BF16) return dispatch_radius<__nv_bfloat16>(radius, pyramid, L, coords, out, stream);
+  if (pyramid_dtype == SLIMB200_DTYPE_F32) return dispatch_radius<float>(radius, pyramid, L, coords, out, stream);
+  return SLIMB200_E_UNSUPPORTED;
 }
-
-extern "C" const char* slimb200_strerror(int code) {
-  switch (code) {
-    case SLIMB200_OK: return "success";
-    case SLIMB200_E_INVALID: return "slimb200: invalid argument";
-    case SLIMB200_E_UNSUPPORTED: return "slimb200: unsupported shape or dtype";
-    case SLIMB200_E_WORKSPACE: return "slimb200: workspace too small";
-    case SLIMB200_E_ALIGNMENT: return "slimb200: misaligned pointer or pitch";
-    case SLIMB200_E_DRIVER: return "slimb200: CUDA driver entry point unavailable";
-    default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "slimb200: unknown error";
-  }
-}
-
-extern "C" int slimb200_version(void) { return SLIMB200_VERSION; }

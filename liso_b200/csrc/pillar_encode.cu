@@ -61,6 +61,7 @@ struct PillarArgs {
   int32_t* blk_cnt;         // [total point blocks] first-point flags per block
   int32_t* blk_base;        // [total point blocks] exclusive prefix inside the sample
   int32_t* pillar_base;     // [batch + 1] exclusive prefix of kept pillars
+  int4* pillar_info;        // [kept pillars] (cell key, first sorted point, point count, sample), first-appearance order
   float* bn_ab;             // [2][MAX_COUT] alpha, beta' of the folded BatchNorm
   double* stat_partials;    // [STATS_MAX_CTAS][MAX_COUT][2]
   // parameters / outputs
@@ -252,7 +253,13 @@ __global__ void __launch_bounds__(PT_BLOCK) k_rank_scatter(const PillarArgs a) {
   __syncthreads();
   int before = 0;
   for (int w = 0; w < warp; ++w) before += s_warp[w];
-  if (flag) a.cell_ord[key] = a.blk_base[pb] + before + __popc(bal & ((1u << lane) - 1u));
+  if (flag) {
+    const int ord = a.blk_base[pb] + before + __popc(bal & ((1u << lane) - 1u));
+    a.cell_ord[key] = ord;
+    if (ord < a.p.max_voxels)
+      a.pillar_info[a.pillar_base[b] + ord] =
+          make_int4(key, a.tile_start[key / TILE_CELLS] + a.cell_prefix[key], a.cell_count[key], b);
+  }
   if (live && a.pt2pillar_out) a.pt2pillar_out[a.pt_off[b] + i] = -1;
   if (key >= 0) {
     const int slot = atomicAdd(a.cell_fill + key, 1);
@@ -541,6 +548,185 @@ __global__ void __launch_bounds__(ENC_THREADS, 3) k_tile_encode(const PillarArgs
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Channels-last canvas (canvas_layout = NHWC): a cell is c_out contiguous floats, so an occupied pillar is two
+// coalesced 128-byte stores straight from the registers that hold its 64 maxima and the empty cells are a
+// contiguous zero stream.  Every warp of the persistent grid interleaves two independent work lists, so the
+// (latency-bound) pillar arithmetic runs under the (bandwidth-bound) zero fill and both are perfectly balanced
+// whatever the spatial distribution of the points:
+//   pillars  a.pillar_info[0 .. n_pillars): rank <= 32 candidates by point index (20 lowest kept), cluster mean by
+//            warp reduction, 10 -> 64 linear + folded BN + ReLU + max in registers, 2 channels per lane
+//   chunks   one BEV tile row (32 cells = 32 * c_out * 4 bytes contiguous) each: zero float4 stores predicated
+//            on the occupancy ballot, plus the 128-byte occupancy row
+// Every canvas byte is written exactly once and never read.
+// ------------------------------------------------------------------------------------------
+constexpr int NH_THREADS = 256;
+constexpr int NH_WARPS = NH_THREADS / 32;
+constexpr int NH_CTAS_PER_SM = 4;
+
+__global__ void __launch_bounds__(NH_THREADS, NH_CTAS_PER_SM) k_pillar_nhwc(const PillarArgs a) {
+  const int lane = lane_id();
+  const slimb200_pillar_params& p = a.p;
+  const int G0 = p.grid[0], G1 = p.grid[1];
+  const int c_out = p.c_out;
+  const int max_pts = p.max_points;
+  const int gw = blockIdx.x * NH_WARPS + warp_id();
+  const int tw = gridDim.x * NH_WARPS;
+
+  float W[2][10], alpha[2], betap[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int c = lane + 32 * q;
+    const bool cv = c < c_out;
+    const int cf = p.c_in + 6;
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+      int col = j;
+      if (p.c_in == 3) col = j < 3 ? j : (j == 3 ? -1 : j - 1);
+      W[q][j] = (cv && col >= 0) ? __ldg(a.linear_weight + c * cf + col) : 0.f;
+    }
+    alpha[q] = cv ? a.bn_ab[c] : 0.f;
+    betap[q] = cv ? a.bn_ab[MAX_COUT + c] : 0.f;
+  }
+
+  const int n_pillars = a.pillar_base[a.batch];
+  const int n_chunks = a.n_tiles * TILE_R;
+  const int my_chunks = gw < n_chunks ? (n_chunks - gw + tw - 1) / tw : 0;
+  const int my_pillars = gw < n_pillars ? (n_pillars - gw + tw - 1) / tw : 0;
+  const int q4 = c_out >> 2;  // float4 per cell
+  int ci = 0, pi = 0;
+  int4 info = my_pillars > 0 ? a.pillar_info[gw] : make_int4(0, 0, 0, 0);
+
+  while (ci < my_chunks || pi < my_pillars) {
+    const bool do_chunk = pi >= my_pillars || (ci < my_chunks && (long long)ci * my_pillars <= (long long)pi * my_chunks);
+    if (do_chunk) {
+      // ---------------- zero fill of one tile row ----------------
+      const int zc = gw + ci * tw;
+      ++ci;
+      const int tile = zc / TILE_R, r = zc - tile * TILE_R;
+      const int b = tile / a.tiles_per_sample;
+      const int tl = tile - b * a.tiles_per_sample;
+      const int tx = tl / a.tiles_y, ty = tl - tx * a.tiles_y;
+      const int xi = tx * TILE_R + r, yi0 = ty * TILE_C;
+      const int cell = tile * TILE_CELLS + r * TILE_C + lane;
+      const int cnt = a.cell_count[cell];
+      const bool kept = cnt > 0 && a.cell_ord[cell] < p.max_voxels;
+      const unsigned mask = __ballot_sync(0xffffffffu, kept);
+      if (xi < G0) {
+        const size_t row = ((size_t)b * G0 + xi) * G1 + yi0;
+        if (yi0 + lane < G1) a.occupancy[row + lane] = kept ? 1.f : 0.f;
+        float4* dst = reinterpret_cast<float4*>(a.canvas + row * c_out);
+        const int n_cols = min(TILE_C, G1 - yi0);
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int f = lane; f < n_cols * q4; f += 32) {
+          const int j = f / q4;
+          if (!((mask >> j) & 1u)) dst[f] = z;
+        }
+      }
+    } else {
+      // ---------------- one pillar ----------------
+      const int row = gw + pi * tw;
+      ++pi;
+      const int key = info.x, st = info.y, n_all = info.z, b = info.w;
+      if (pi < my_pillars) info = a.pillar_info[gw + pi * tw];  // prefetch the next one
+      const int tile = key / TILE_CELLS, cl = key - tile * TILE_CELLS;
+      const int tl = tile - b * a.tiles_per_sample;
+      const int tx = tl / a.tiles_y, ty = tl - tx * a.tiles_y;
+      const int xi = tx * TILE_R + cl / TILE_C, yi = ty * TILE_C + (cl % TILE_C);
+      // --- the max_points lowest point indices of the cell, ascending ------------------
+      float4 pt = make_float4(0.f, 0.f, 0.f, 0.f);
+      int pidx = 0;
+      const int n = n_all < max_pts ? n_all : max_pts;
+      if (n_all <= 32) {
+        unsigned idx = 0xffffffffu;
+        if (lane < n_all) {
+          idx = (unsigned)a.sorted_idx[st + lane];
+          pt = a.sorted_pts[st + lane];
+        }
+        const int src = rank_order_small(idx, n_all, lane);
+        pidx = (int)__shfl_sync(0xffffffffu, idx, src);
+        pt.x = __shfl_sync(0xffffffffu, pt.x, src);
+        pt.y = __shfl_sync(0xffffffffu, pt.y, src);
+        pt.z = __shfl_sync(0xffffffffu, pt.z, src);
+        pt.w = __shfl_sync(0xffffffffu, pt.w, src);
+      } else {
+        unsigned long long k64 = ((unsigned long long)(unsigned)a.sorted_idx[st + lane] << 32) | (unsigned)lane;
+        k64 = bitonic_sort_warp(k64);
+        const int keep = max_pts;
+        for (int base = 32; base < n_all; base += 32 - keep) {
+          if (lane >= keep) {
+            const int j = base + lane - keep;
+            k64 = j < n_all ? (((unsigned long long)(unsigned)a.sorted_idx[st + j] << 32) | (unsigned)j) : ~0ull;
+          }
+          k64 = bitonic_sort_warp(k64);
+        }
+        pidx = (int)(unsigned)(k64 >> 32);
+        if (lane < n) pt = a.sorted_pts[st + (int)(unsigned)(k64 & 0xffffffffull)];
+      }
+      const bool act = lane < n;
+      // --- cluster centre (pillar_encoder.py:108-113) ---
+      float sx = act ? pt.x : 0.f, sy = act ? pt.y : 0.f, sz = act ? pt.z : 0.f;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, d);
+        sy += __shfl_xor_sync(0xffffffffu, sy, d);
+        sz += __shfl_xor_sync(0xffffffffu, sz, d);
+      }
+      const float fn = (float)n;
+      const float mx = __fdiv_rn(sx, fn), my = __fdiv_rn(sy, fn), mz = __fdiv_rn(sz, fn);
+      // --- voxel-centre offsets, legacy aliasing + swapped index (pillar_encoder.py:129-139) ---
+      float f[7];
+      f[0] = __fsub_rn(pt.x, __fadd_rn(__fmul_rn((float)yi, p.vx), p.x_offset));
+      f[1] = __fsub_rn(pt.y, __fadd_rn(__fmul_rn((float)xi, p.vy), p.y_offset));
+      f[2] = __fsub_rn(pt.z, __fadd_rn(__fmul_rn(0.f, p.vz), p.z_offset));
+      f[3] = pt.w;
+      f[4] = __fsub_rn(pt.x, mx);
+      f[5] = __fsub_rn(pt.y, my);
+      f[6] = __fsub_rn(pt.z, mz);
+      float best[2] = {0.f, 0.f};
+      for (int k = 0; k < n; ++k) {
+        float g[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) g[j] = __shfl_sync(0xffffffffu, f[j], k);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          float x = W[q][0] * g[0];
+          x = fmaf(W[q][1], g[1], x);
+          x = fmaf(W[q][2], g[2], x);
+          x = fmaf(W[q][3], g[3], x);
+          x = fmaf(W[q][4], g[4], x);
+          x = fmaf(W[q][5], g[5], x);
+          x = fmaf(W[q][6], g[6], x);
+          x = fmaf(W[q][7], g[0], x);
+          x = fmaf(W[q][8], g[1], x);
+          x = fmaf(W[q][9], g[2], x);
+          best[q] = fmaxf(best[q], fmaf(x, alpha[q], betap[q]));  // ReLU folded: best starts at 0
+        }
+      }
+      if (n < max_pts) {  // padded zero rows take part in the max: BN(0) = beta'
+        best[0] = fmaxf(best[0], betap[0]);
+        best[1] = fmaxf(best[1], betap[1]);
+      }
+      float* dst = a.canvas + (((size_t)b * G0 + xi) * G1 + yi) * c_out;
+      if (lane < c_out) dst[lane] = best[0];
+      if (lane + 32 < c_out) dst[lane + 32] = best[1];
+      if (a.coors_out || a.num_points_out || a.voxels_out || a.pt2pillar_out) {
+        if (lane == 0 && a.coors_out) *reinterpret_cast<int4*>(a.coors_out + (size_t)row * 4) = make_int4(b, 0, xi, yi);
+        if (lane == 0 && a.num_points_out) a.num_points_out[row] = n;
+        if (a.pt2pillar_out && act) a.pt2pillar_out[a.pt_off[b] + pidx] = row;
+        if (a.voxels_out && lane < max_pts) {
+          float* v = a.voxels_out + ((size_t)row * max_pts + lane) * p.c_in;
+          v[0] = act ? pt.x : 0.f;
+          v[1] = act ? pt.y : 0.f;
+          v[2] = act ? pt.z : 0.f;
+          if (p.c_in == 4) v[3] = act ? pt.w : 0.f;
+        }
+      }
+    }
+  }
+}
+
 // BatchNorm1d in training mode: statistics over all (kept pillars x max_points) rows, padded zero
 // rows included (they add nothing to the sums but count in the denominator); biased variance for
 // the normalisation, unbiased for the running update (momentum 0.01).  Q3/Q4 of SURVEY.md.
@@ -601,6 +787,8 @@ int make_plan(const float* const* points, const int32_t* n_points, int32_t batch
   if (p->c_out < 1 || p->c_out > MAX_COUT) return SLIMB200_E_UNSUPPORTED;
   if (p->max_points < 1 || p->max_points > 24) return SLIMB200_E_UNSUPPORTED;
   if (p->grid[0] < 1 || p->grid[1] < 1 || p->grid[2] != 1) return SLIMB200_E_UNSUPPORTED;
+  if (p->canvas_layout != SLIMB200_CANVAS_NCHW && p->canvas_layout != SLIMB200_CANVAS_NHWC) return SLIMB200_E_INVALID;
+  if (p->canvas_layout == SLIMB200_CANVAS_NHWC && (p->c_out & 3)) return SLIMB200_E_UNSUPPORTED;
   PillarArgs& a = plan->a;
   a = PillarArgs{};
   a.batch = batch;
@@ -646,6 +834,10 @@ int make_plan(const float* const* points, const int32_t* n_points, int32_t batch
   a.blk_cnt = w.take<int32_t>(n_blk_cap);
   a.blk_base = w.take<int32_t>(n_blk_cap);
   a.pillar_base = w.take<int32_t>(SLIMB200_MAX_BATCH + 1);
+  {
+    const size_t cap = (size_t)batch * (size_t)p->max_voxels;
+    a.pillar_info = w.take<int4>((n_tot < cap ? n_tot : cap) + 1);
+  }
   a.bn_ab = w.take<float>(2 * MAX_COUT);
   a.stat_partials = w.take<double>((size_t)STATS_MAX_CTAS * MAX_COUT * 2);
   plan->bytes = w.used();
@@ -722,8 +914,13 @@ extern "C" int slimb200_pillar_encode(const float* const* points, const int32_t*
       SLIMB200_CUDA_TRY(cudaGetDevice(&dev));
       SLIMB200_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     }
-    const int n_ctas = a.n_tiles < n_sm * ENC_CTAS_PER_SM ? a.n_tiles : n_sm * ENC_CTAS_PER_SM;
-    SLIMB200_LAUNCH(SLIMB200_K_TILE_ENCODE, stream, (k_tile_encode<0><<<n_ctas, ENC_THREADS, 0, stream>>>(a)));
+    if (p->canvas_layout == SLIMB200_CANVAS_NHWC) {
+      SLIMB200_LAUNCH(SLIMB200_K_PILLAR_NHWC, stream,
+                      (k_pillar_nhwc<<<n_sm * NH_CTAS_PER_SM, NH_THREADS, 0, stream>>>(a)));
+    } else {
+      const int n_ctas = a.n_tiles < n_sm * ENC_CTAS_PER_SM ? a.n_tiles : n_sm * ENC_CTAS_PER_SM;
+      SLIMB200_LAUNCH(SLIMB200_K_TILE_ENCODE, stream, (k_tile_encode<0><<<n_ctas, ENC_THREADS, 0, stream>>>(a)));
+    }
   }
   return SLIMB200_OK;
 }

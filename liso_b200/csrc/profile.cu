@@ -70,6 +70,20 @@ extern "C" int64_t slimb200_launch_count(int32_t kernel_id) {
 extern "C" const char* slimb200_kernel_name(int32_t kernel_id) {
   static const char* names[SLIMB200_N_KERNELS] = {
       "k_point_keys", "k_scan_local", "k_scan_global", "k_rank_scatter", "k_tile_encode_stats", "k_bn_finalize",
-      "k_tile_encode", "k_feat_pack", "k_corr_gemm_tcgen05", "k_corr_lookup", "k_pillar_coors_f64"};
+      "k_tile_encode", "k_pillar_nhwc", "k_feat_pack", "k_corr_gemm_tcgen05", "k_corr_lookup", "k_pillar_coors_f64"};
   return (kernel_id >= 0 && kernel_id < SLIMB200_N_KERNELS) ? names[kernel_id] : "?";
 }
+
+extern "C" const char* slimb200_strerror(int code) {
+  switch (code) {
+    case SLIMB200_OK: return "success";
+    case SLIMB200_E_INVALID: return "slimb200: invalid argument";
+    case SLIMB200_E_UNSUPPORTED: return "slimb200: unsupported shape or dtype";
+    case SLIMB200_E_WORKSPACE: return "slimb200: workspace too small";
+    case SLIMB200_E_ALIGNMENT: return "slimb200: misaligned pointer or pitch";
+    case SLIMB200_E_DRIVER: return "slimb200: CUDA driver entry point unavailable";
+    default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "slimb200: unknown error";
+  }
+}
+
+extern "C" int slimb200_version(void) { return SLIMB200_VERSION; }

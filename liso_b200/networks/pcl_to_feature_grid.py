@@ -81,9 +81,21 @@ class PointPillarsScatter(nn.Module):
 
 
 class PointsPillarFeatureNetWrapper(nn.Module):
-    def __init__(self, cfg) -> None:
+    """``canvas_memory_format``: ``"channels_last"`` (default) returns the ``(B, C, H, W)`` canvas in
+    channels-last memory format -- same shape, same values, what the cuDNN convolutions that consume it
+    want and what stores fastest -- ``"contiguous"`` returns the reference's NCHW-contiguous tensor.
+    Can also be set with ``cfg.network.b200_canvas_memory_format``."""
+
+    def __init__(self, cfg, canvas_memory_format=None) -> None:
         super().__init__()
         self.cfg = cfg
+        if canvas_memory_format is None:
+            canvas_memory_format = getattr(cfg.network, "b200_canvas_memory_format", None) \
+                if not isinstance(cfg.network, dict) else cfg.network.get("b200_canvas_memory_format")
+        canvas_memory_format = canvas_memory_format or "channels_last"
+        if canvas_memory_format not in ("channels_last", "contiguous"):
+            raise ValueError("canvas_memory_format must be 'channels_last' or 'contiguous'")
+        self.canvas_memory_format = canvas_memory_format
         z_cut = cfg.data.setdefault("z_pillar_cutoff_value", 5.0)
         assert z_cut > 0.0, z_cut
         half = np.append(np.array(cfg.data.bev_range_m) / 2.0, z_cut)
@@ -130,6 +142,8 @@ class PointsPillarFeatureNetWrapper(nn.Module):
         p.bn_training = 1 if training else 0
         p.bn_eps = ve.pfn_layers[0].norm.eps
         p.bn_momentum = ve.pfn_layers[0].norm.momentum
+        nhwc = self.canvas_memory_format == "channels_last" and p.c_out % 4 == 0
+        p.canvas_layout = _lib.CANVAS_NHWC if nhwc else _lib.CANVAS_NCHW
         return p
 
     def _prep_points(self, pts: Sequence[torch.Tensor]) -> List[torch.Tensor]:
@@ -157,7 +171,8 @@ class PointsPillarFeatureNetWrapper(nn.Module):
         p = self._params(training)
         ny, nx = self.pts_middle_encoder.ny, self.pts_middle_encoder.nx
         total = int(sum(t.shape[0] for t in pts))
-        canvas = torch.empty((B, p.c_out, ny, nx), dtype=torch.float32, device=dev)
+        fmt = torch.channels_last if p.canvas_layout == _lib.CANVAS_NHWC else torch.contiguous_format
+        canvas = torch.empty((B, p.c_out, ny, nx), dtype=torch.float32, device=dev, memory_format=fmt)
         occupancy = torch.empty((B, 1, ny, nx), dtype=torch.float32, device=dev)
         ws_bytes = lib.slimb200_pillar_workspace_bytes(B, total, C.byref(p))
         if ws_bytes == 0:

@@ -7,8 +7,8 @@ writes the whole 4-level pyramid (bf16) in a single pass; ``__call__`` = one gat
 emits the ``(B, L*(2r+1)^2, h, w)`` fp32 tensor directly.
 
 Differences a caller can observe (documented in DESIGN.md):
-* ``corr_pyramid[l]`` has the reference's shape ``(B*h*w, 1, h_l, w_l)`` but is a bf16 *strided
-  view* into one packed buffer (row pitch ``layout.pitch``).
+* ``corr_pyramid[l]`` has the reference's shape ``(B*h*w, 1, h_l, w_l)`` but is bf16 and is gathered
+  lazily (a copy) out of the panel-tiled buffer the kernels use (``include/slimb200.h``).
 * values carry bf16 operand + storage rounding: |err| <= 2^-7 * ||f1_i|| * ||f2_j|| / sqrt(D).
 * forward only.
 """
@@ -29,15 +29,37 @@ def make_layout(batch: int, dim: int, h: int, w: int, levels: int) -> _lib.CorrL
     return L
 
 
-def _level_views(pyramid: torch.Tensor, L: _lib.CorrLayout) -> List[torch.Tensor]:
-    """Expose each level with the reference's shape (B*h*w, 1, h_l, w_l) as a strided view."""
-    nf = L.h * L.w
-    flat = pyramid.view(-1)
-    views = []
-    for l in range(L.levels):
-        hl, wl = L.level_h[l], L.level_w[l]
-        views.append(flat.as_strided((L.batch * nf, 1, hl, wl), (L.pitch, hl * wl, wl, 1), L.level_offset[l]))
-    return views
+def unpack_level(pyramid: torch.Tensor, L: _lib.CorrLayout, level: int) -> torch.Tensor:
+    """Level ``level`` with the reference's shape (B*h*w, 1, h_l, w_l), gathered out of the panel layout
+    (``include/slimb200.h``: element (b, i, j) at ``((b*n_panels + j//128)*Nf + i)*128 + j%128``)."""
+    nf, P, pw = L.h * L.w, L.n_panels, _lib.PANEL_COLS
+    off, hl, wl = L.level_offset[level], L.level_h[level], L.level_w[level]
+    p0, p1 = off // pw, (off + hl * wl - 1) // pw + 1
+    rows = pyramid.view(L.batch, P, nf, pw)[:, p0:p1].permute(0, 2, 1, 3).reshape(L.batch * nf, (p1 - p0) * pw)
+    return rows[:, off - p0 * pw: off - p0 * pw + hl * wl].reshape(L.batch * nf, 1, hl, wl)
+
+
+class _LazyLevels:
+    """``corr_pyramid`` of the reference is a list of dense tensors; here the levels live interleaved in one
+    panel-tiled buffer, so each level is materialised (a copy) only when somebody indexes the list."""
+
+    def __init__(self, pyramid: torch.Tensor, L: _lib.CorrLayout):
+        self._pyramid, self._L = pyramid, L
+
+    def __len__(self) -> int:
+        return self._L.levels
+
+    def __getitem__(self, level: int) -> torch.Tensor:
+        if isinstance(level, slice):
+            return [self[i] for i in range(*level.indices(len(self)))]
+        if level < 0:
+            level += len(self)
+        if not 0 <= level < len(self):
+            raise IndexError(level)
+        return unpack_level(self._pyramid, self._L, level)
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
 
 
 def lookup(pyramid: torch.Tensor, L: _lib.CorrLayout, coords: torch.Tensor, radius: int) -> torch.Tensor:
@@ -59,12 +81,12 @@ def lookup(pyramid: torch.Tensor, L: _lib.CorrLayout, coords: torch.Tensor, radi
 
 
 def pack_pyramid_f32(levels: List[torch.Tensor], L: _lib.CorrLayout) -> torch.Tensor:
-    """Pack reference-shaped fp32 levels (B*h*w,1,h_l,w_l) into the library's row layout (tests)."""
-    nf = L.h * L.w
-    buf = torch.zeros((L.batch * nf, L.pitch), dtype=torch.float32, device=levels[0].device)
+    """Pack reference-shaped fp32 levels (B*h*w,1,h_l,w_l) into the library's panel layout (tests)."""
+    nf, P, pw = L.h * L.w, L.n_panels, _lib.PANEL_COLS
+    rows = torch.zeros((L.batch * nf, P * pw), dtype=torch.float32, device=levels[0].device)
     for l, lv in enumerate(levels):
-        buf[:, L.level_offset[l]:L.level_offset[l] + L.level_h[l] * L.level_w[l]] = lv.reshape(L.batch * nf, -1)
-    return buf
+        rows[:, L.level_offset[l]:L.level_offset[l] + L.level_h[l] * L.level_w[l]] = lv.reshape(L.batch * nf, -1)
+    return rows.view(L.batch, nf, P, pw).permute(0, 2, 1, 3).contiguous().view(L.batch * P * nf, pw)
 
 
 class CorrBlock:
@@ -82,12 +104,12 @@ class CorrBlock:
         f1 = fmap1.detach().float().contiguous()
         f2 = fmap2.detach().float().contiguous()
         L = self.layout
-        self.pyramid = torch.empty((B * h * w, L.pitch), dtype=torch.bfloat16, device=f1.device)
+        self.pyramid = torch.empty((B * L.n_panels * h * w, _lib.PANEL_COLS), dtype=torch.bfloat16, device=f1.device)
         ws = torch.empty(lib.slimb200_corr_workspace_bytes(C.byref(L)), dtype=torch.uint8, device=f1.device)
         _lib.check(lib.slimb200_corr_build(f1.data_ptr(), f2.data_ptr(), C.byref(L), _lib.DTYPE_BF16,
                                            self.pyramid.data_ptr(), ws.data_ptr(), ws.numel(),
                                            _lib.current_stream_ptr()))
-        self.corr_pyramid = _level_views(self.pyramid, L)
+        self.corr_pyramid = _LazyLevels(self.pyramid, L)
 
     def __call__(self, coords: torch.Tensor) -> torch.Tensor:
         return lookup(self.pyramid, self.layout, coords, self.radius)

@@ -17,9 +17,19 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5  # stated tolerance: |a - b| <= RTOL * max(1, |b|_inf-scale)
 
 
+FORMAT = {"fmt": "channels_last"}
+
+
+@pytest.fixture(autouse=True, params=["channels_last", "contiguous"])
+def canvas_format(request):
+    """Every test runs for both canvas layouts: NHWC (k_pillar_nhwc, product default) and NCHW (k_tile_encode)."""
+    FORMAT["fmt"] = request.param
+    yield request.param
+
+
 def _module(cfg, device, seed=0, training=False):
     torch.manual_seed(seed)
-    m = PointsPillarFeatureNetWrapper(cfg)
+    m = PointsPillarFeatureNetWrapper(cfg, canvas_memory_format=FORMAT["fmt"])
     bn = m.pts_voxel_encoder.pfn_layers[0].norm
     with torch.no_grad():  # randomised BN so the zero-row value relu(beta - mu*gamma/sigma) is non-trivial
         bn.weight.uniform_(0.5, 1.5)
@@ -56,6 +66,8 @@ def _check(cfg, clouds, device, training=False, c_in=4):
     assert torch.equal(got["occupancy"].cpu(), ref["occupancy"])
     # --- fp32 features: 1e-5 relative -----------------------------------------------------
     canvas = got["canvas"].cpu()
+    want_fmt = torch.channels_last if FORMAT["fmt"] == "channels_last" else torch.contiguous_format
+    assert got["canvas"].is_contiguous(memory_format=want_fmt) and canvas.shape == ref["canvas"].shape
     scale = max(1.0, float(ref["canvas"].abs().max()))
     err = float((canvas - ref["canvas"]).abs().max())
     assert err <= RTOL * scale, (err, scale)

@@ -1,0 +1,79 @@
+#!/usr/bin/env python
+"""Per-kernel timing of the slimb200 library on the bench workload (K, B=8) without the stock PyTorch part.
+Measurement tool for kernel iteration; the judged numbers come from bench.py."""
+import argparse
+import ctypes as C
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from liso_b200 import _lib  # noqa: E402
+from liso_b200.config import WORKLOADS, make_cfg  # noqa: E402
+from liso_b200.networks.pcl_to_feature_grid import PointsPillarFeatureNetWrapper  # noqa: E402
+from liso_b200.slim.corr import CorrBlock, coords_grid  # noqa: E402
+from liso_b200.synth import make_sample_dicts  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="K")
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--skip-pillar", action="store_true")
+    ap.add_argument("--skip-corr", action="store_true")
+    ap.add_argument("--train-bn", action="store_true")
+    args = ap.parse_args()
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    W = WORKLOADS[args.workload]
+    cfg = make_cfg(args.workload)
+    H, Wd = W["img_grid_size"]
+    B = args.batch
+    runs = []
+    if not args.skip_pillar:
+        s0, _ = make_sample_dicts(W, [1000 + i for i in range(B)])
+        clouds = [t.to(dev) for t in s0["pcl_full_no_ground_ta"]]
+        for fmt in ("channels_last", "contiguous"):
+            m = PointsPillarFeatureNetWrapper(cfg, canvas_memory_format=fmt).to(dev)
+            m.train(args.train_bn)
+            runs.append(("pillar " + fmt[:8], (lambda mm: (lambda: mm(clouds)))(m)))
+    if not args.skip_corr:
+        g = torch.Generator(device="cpu").manual_seed(0)
+        h, w = H // 8, Wd // 8
+        f1 = torch.randn(B, 128, h, w, generator=g).to(dev)
+        f2 = torch.randn(B, 128, h, w, generator=g).to(dev)
+        coords = (coords_grid(B, h, w, dev) + 1.5 * torch.randn(B, 2, h, w, generator=g).to(dev)).contiguous()
+        state = {}
+
+        def build():
+            state["blk"] = CorrBlock(f1, f2, num_levels=4, radius=3)
+
+        def look():
+            for _ in range(6):
+                state["out"] = state["blk"](coords)
+
+        runs.append(("corr_build", build))
+        runs.append(("corr_lookup x6", look))
+    with torch.no_grad():
+        for name, fn in runs:
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            lib.slimb200_profile_begin()
+            for _ in range(args.reps):
+                fn()
+            torch.cuda.synchronize()
+            ms_k = (C.c_float * _lib.N_KERNELS)()
+            n_k = (C.c_int64 * _lib.N_KERNELS)()
+            _lib.check(lib.slimb200_profile_end(ms_k, n_k))
+            for i in range(_lib.N_KERNELS):
+                if n_k[i]:
+                    print("%-16s %-24s %8.4f ms/launch  (%d launches)" % (name, lib.slimb200_kernel_name(i).decode(), ms_k[i] / n_k[i], n_k[i]))
+    sys.stdout.flush()
+
+
+if __name__ == "__main__":
+    main()

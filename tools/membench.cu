@@ -64,6 +64,30 @@ __global__ void k_tma_3d(const __grid_constant__ CUtensorMap map, int n0, int n1
   }
 }
 
+__global__ void k_tma_3d_hint(const __grid_constant__ CUtensorMap map, int n0, int n1, int n2, int b0, int b1, int b2, int box_bytes, int order) {
+  extern __shared__ __align__(1024) char s[];
+  for (int i = threadIdx.x; i < box_bytes / 16; i += blockDim.x) reinterpret_cast<float4*>(s)[i] = make_float4(0, 0, 0, 0);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    const int t0 = (n0 + b0 - 1) / b0, t1 = (n1 + b1 - 1) / b1, t2 = (n2 + b2 - 1) / b2;
+    const long long total = (long long)t0 * t1 * t2;
+    const long long per = (total + gridDim.x - 1) / gridDim.x;
+    for (long long q = 0; q < per; ++q) {
+      const long long t = order == 0 ? (long long)blockIdx.x + q * gridDim.x : (long long)blockIdx.x * per + q;
+      if (t >= total) break;
+      const int i0 = (int)(t % t0), i1 = (int)((t / t0) % t1), i2 = (int)(t / ((long long)t0 * t1));
+      asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;" ::"l"(&map), "r"(smem_u32(s)),
+                   "r"(i0 * b0), "r"(i1 * b1), "r"(i2 * b2), "l"(pol) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 8;" ::: "memory");
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+}
+
 // ---- (e) canvas pattern with plain stores: CTA per tile (4 rows x 32 cols x 64 ch), 8 lanes x 16B per row ----
 __global__ void k_canvas_st(float* __restrict__ canvas, int B, int C, int G0, int G1) {
   const int tiles_x = G0 / 4, tiles_y = G1 / 32;
@@ -141,8 +165,10 @@ int main() {
   void* p = nullptr; cudaDriverEntryPointQueryResult q;
   CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
   PFN_encodeTiled enc = (PFN_encodeTiled)p;
-  {  // canvas: dims (G1=640, G0=640, B*C=512) f32, box (32,4,64) = 32 KB
-    struct Cfg { int b0, b1, b2; } cfgs[] = {{32, 4, 64}, {32, 8, 32}, {64, 4, 32}, {128, 4, 16}, {32, 4, 32}, {160, 2, 16}};
+  CK(cudaFuncSetAttribute(k_tma_3d, cudaFuncAttributeMaxDynamicSharedMemorySize, 132096));
+  CK(cudaFuncSetAttribute(k_tma_3d_hint, cudaFuncAttributeMaxDynamicSharedMemorySize, 132096));
+  {  // canvas: dims (G1=640, G0=640, B*C=512) f32
+    struct Cfg { int b0, b1, b2; } cfgs[] = {{32, 4, 64}, {64, 2, 64}, {64, 4, 64}, {64, 4, 32}, {128, 2, 64}, {128, 1, 64}};
     for (auto c : cfgs) {
       CUtensorMap map;
       cuuint64_t dims[3] = {640, 640, 512}; cuuint64_t str[2] = {640 * 4, 640 * 640 * 4};
@@ -151,40 +177,56 @@ int main() {
                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) { printf("encode failed %d\n", (int)r); continue; }
       const int bb = c.b0 * c.b1 * c.b2 * 4;
-      CK(cudaFuncSetAttribute(k_tma_3d, cudaFuncAttributeMaxDynamicSharedMemorySize, 66560));
-      for (int cps : {1, 2, 3}) {
-        char nm[128]; snprintf(nm, 128, "TMA tensor store canvas box(%d,%d,%d)=%dKB, %d CTA/SM", c.b0, c.b1, c.b2, bb / 1024, cps);
-        rep(nm, time_it([&] { k_tma_3d<<<148 * cps, 128, bb + 1024>>>(map, 640, 640, 512, c.b0, c.b1, c.b2, bb); }), bytes);
-      }
-    }
-  }
-  {  // pyramid: dims (8500 cols, 6400 rows, 8) bf16, pitch 8512, box (64,128,1) = 16 KB
-    const size_t pbytes = (size_t)8 * 6400 * 8512 * 2;
-    char* pyr; CK(cudaMalloc(&pyr, pbytes));
-    struct Cfg { int b0, b1; CUtensorMapSwizzle sw; } cfgs[] = {{64, 128, CU_TENSOR_MAP_SWIZZLE_128B}, {64, 256, CU_TENSOR_MAP_SWIZZLE_128B}, {256, 64, CU_TENSOR_MAP_SWIZZLE_NONE}, {256, 32, CU_TENSOR_MAP_SWIZZLE_NONE}, {128, 128, CU_TENSOR_MAP_SWIZZLE_NONE}};
-    for (auto c : cfgs) {
-      CUtensorMap map;
-      cuuint64_t dims[3] = {8500, 6400, 8}; cuuint64_t str[2] = {8512 * 2, (cuuint64_t)6400 * 8512 * 2};
-      cuuint32_t box[3] = {(cuuint32_t)c.b0, (cuuint32_t)c.b1, 1}; cuuint32_t es[3] = {1, 1, 1};
-      CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, pyr, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, c.sw,
-                       CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (r != CUDA_SUCCESS) { printf("encode failed %d\n", (int)r); continue; }
-      const int bb = c.b0 * c.b1 * 2;
       for (int cps : {1, 2}) {
-        char nm[128]; snprintf(nm, 128, "TMA tensor store pyramid box(%d,%d)=%dKB, %d CTA/SM", c.b0, c.b1, bb / 1024, cps);
-        rep(nm, time_it([&] { k_tma_3d<<<148 * cps, 128, bb + 1024>>>(map, 8500, 6400, 8, c.b0, c.b1, 1, bb); }), (size_t)8 * 6400 * 8500 * 2);
+        if ((bb + 1024) * cps > 220000) continue;
+        char nm[128]; snprintf(nm, 128, "TMA canvas box(%d,%d,%d)=%dKB, %d CTA/SM", c.b0, c.b1, c.b2, bb / 1024, cps);
+        rep(nm, time_it([&] { k_tma_3d<<<148 * cps, 128, bb + 1024>>>(map, 640, 640, 512, c.b0, c.b1, c.b2, bb); }), bytes);
+        snprintf(nm, 128, "TMA canvas box(%d,%d,%d)=%dKB, %d CTA/SM evict_first", c.b0, c.b1, c.b2, bb / 1024, cps);
+        rep(nm, time_it([&] { k_tma_3d_hint<<<148 * cps, 128, bb + 1024>>>(map, 640, 640, 512, c.b0, c.b1, c.b2, bb, 0); }), bytes);
       }
     }
-    CK(cudaFree(pyr));
   }
-  for (int cps : {2, 3, 4, 6, 8}) {
-    char nm[128]; snprintf(nm, 128, "canvas tiles 4x32x64 st.v4, %d CTA/SM x 256", cps);
-    rep(nm, time_it([&] { k_canvas_st<<<148 * cps, 256>>>((float*)buf, 8, 64, 640, 640); }), bytes);
-  }
-  for (int rpt : {1, 2, 4})
-    for (int cps : {2, 4}) {
-      char nm[128]; snprintf(nm, 128, "canvas full rows x%d, all ch, st.v4, %d CTA/SM x 256", rpt, cps);
-      rep(nm, time_it([&] { k_canvas_rows<<<148 * cps, 256>>>((float*)buf, 8, 64, 640, 640, rpt); }), bytes);
+  {  // pyramid: dims (8500 cols, 6400 rows, 8) bf16, various pitches
+    for (int pitch : {8512, 8576, 8704, 16384}) {
+      const size_t pbytes = (size_t)8 * 6400 * pitch * 2;
+      char* pyr; CK(cudaMalloc(&pyr, pbytes));
+      struct Cfg { int b0, b1; CUtensorMapSwizzle sw; } cfgs[] = {{64, 128, CU_TENSOR_MAP_SWIZZLE_128B}, {256, 64, CU_TENSOR_MAP_SWIZZLE_NONE}};
+      for (auto c : cfgs) {
+        CUtensorMap map;
+        cuuint64_t dims[3] = {8500, 6400, 8}; cuuint64_t str[2] = {(cuuint64_t)pitch * 2, (cuuint64_t)6400 * pitch * 2};
+        cuuint32_t box[3] = {(cuuint32_t)c.b0, (cuuint32_t)c.b1, 1}; cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, pyr, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, c.sw,
+                         CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { printf("encode failed %d\n", (int)r); continue; }
+        const int bb = c.b0 * c.b1 * 2;
+        for (int order : {0, 1}) {
+          char nm[128]; snprintf(nm, 128, "TMA pyramid pitch %d box(%d,%d) order %s evict_first", pitch, c.b0, c.b1, order ? "contig/CTA" : "strided");
+          rep(nm, time_it([&] { k_tma_3d_hint<<<148, 128, bb + 1024>>>(map, 8500, 6400, 8, c.b0, c.b1, 1, bb, order); }), (size_t)8 * 6400 * 8500 * 2);
+        }
+        char nm[128]; snprintf(nm, 128, "TMA pyramid pitch %d box(%d,%d) strided, no hint", pitch, c.b0, c.b1);
+        rep(nm, time_it([&] { k_tma_3d<<<148, 128, bb + 1024>>>(map, 8500, 6400, 8, c.b0, c.b1, 1, bb); }), (size_t)8 * 6400 * 8500 * 2);
+      }
+      CK(cudaFree(pyr));
     }
+    // panel layout: [b][panel=67][6400 rows][128 cols] bf16 -> each 128x128 tile is 32 KB contiguous
+    {
+      const size_t pbytes = (size_t)8 * 67 * 6400 * 128 * 2;
+      char* pyr; CK(cudaMalloc(&pyr, pbytes));
+      CUtensorMap map;
+      cuuint64_t dims[3] = {128, 6400, 8 * 67}; cuuint64_t str[2] = {256, (cuuint64_t)6400 * 256};
+      for (int b0 : {64, 128}) {
+        cuuint32_t box[3] = {(cuuint32_t)b0, 128, 1}; cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, pyr, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         b0 == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { printf("encode failed %d\n", (int)r); continue; }
+        const int bb = b0 * 128 * 2;
+        char nm[128]; snprintf(nm, 128, "TMA pyramid PANEL layout box(%d,128)", b0);
+        rep(nm, time_it([&] { k_tma_3d<<<148, 128, bb + 1024>>>(map, 128, 6400, 8 * 67, b0, 128, 1, bb); }), pbytes);
+        snprintf(nm, 128, "TMA pyramid PANEL layout box(%d,128) evict_first", b0);
+        rep(nm, time_it([&] { k_tma_3d_hint<<<148, 128, bb + 1024>>>(map, 128, 6400, 8 * 67, b0, 128, 1, bb, 0); }), pbytes);
+      }
+      CK(cudaFree(pyr));
+    }
+  }
   return 0;
 }
