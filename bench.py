@@ -139,6 +139,8 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--conv-precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--memory-format", default="channels_last", choices=["channels_last", "contiguous"],
+                    help="memory format of the canvas our encoder emits and of the stock convs that consume it")
     ap.add_argument("--profile-one-step", action="store_true",
                     help="bracket ONE resident step with cudaProfilerStart/Stop (for `ncu --profile-from-start off`) and exit")
     args = ap.parse_args()
@@ -199,10 +201,13 @@ def main():
     torch.backends.cuda.matmul.allow_tf32 = args.conv_precision == "tf32"
     torch.backends.cudnn.benchmark = True
 
+    cfg.network["b200_canvas_memory_format"] = args.memory_format
     model = SLIM(cfg, decode_iterations="last", static_aggregation=False).eval()
     sd = synth_weights_like(model.state_dict(), 0)
     model.load_state_dict(sd, strict=True)
     model = model.to(dev)
+    if args.memory_format == "channels_last":
+        model = model.to(memory_format=torch.channels_last)
 
     # pairs of this rank: global pair indices sharded by the reference's modulo rule
     from liso_b200.slim.export import reduce_counters, shard_indices
@@ -291,7 +296,9 @@ def main():
     lib.slimb200_corr_layout_init(B, 128, H // 8, Wd // 8, 4, C.byref(L))
     alg = {
         _lib.K_TILE_ENCODE: dict(bytes=sum(n_pts) * 16 + B * 65 * H * Wd * 4, flops=0,
-                                 what="points read + canvas (zeros incl.) + occupancy written, B frames per launch"),
+                                 what="points read + canvas NCHW (zeros incl.) + occupancy written, B frames per launch"),
+        _lib.K_PILLAR_NHWC: dict(bytes=sum(n_pts) * 16 + B * 65 * H * Wd * 4, flops=0,
+                                 what="points read + canvas channels-last (zeros incl.) + occupancy written, B frames per launch"),
         _lib.K_CORR_GEMM: dict(bytes=B * nf * L.n_cols * 2 + B * (nf + L.n_cols) * 128 * 2, flops=2.0 * B * nf * L.n_cols * 128,
                                what="bf16 pyramid written + bf16 operands read, B samples per launch"),
         _lib.K_CORR_LOOKUP: dict(bytes=B * 196 * nf * 4 + B * nf * 4 * 8 * 32, flops=0,
@@ -331,6 +338,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": tot["ms_e2e_max"] / args.steps},
             "gpu_launches": int(tot["launches"]), "roofline": roofline, "kernels": kernels,
+            "memory_format": args.memory_format,
             "precision": {"pillar": "f32", "correlation": "bf16 operands, f32 accumulate, bf16 storage",
                           "stock_convs": "cudnn " + args.conv_precision}}
 

@@ -8,15 +8,20 @@
 //                        [f2 | pool1(f2) | pool2(f2) | pool3(f2)] (floor 2x2 means, iterated in
 //                        fp32), so the whole pyramid is ONE GEMM: avg_pool(corr) == corr(avg_pool(f2))
 //                        by linearity; no pooling pass ever reads the volume back.
-//   k_corr_gemm_tcgen05  persistent, warp-specialised 128x128x128 tiles:
-//                          warp 0   TMA producer (cp.async.bulk.tensor, 128B swizzle, 4-stage ring)
+//   k_corr_gemm_tcgen05  persistent, warp-specialised; a CTA keeps a PAIR of 128-row A tiles (64 KB, full
+//                        K = 128) resident in shared memory and streams 128-column B tiles past them:
+//                          warp 0   TMA producer (cp.async.bulk.tensor, 128B swizzle): A pair per unit,
+//                                   3-deep ring of B tiles
 //                          warp 1   tcgen05.mma issuer (one elected lane), fp32 accumulators in TMEM,
-//                                   4 accumulator buffers (512 columns) so the epilogue of tile t
-//                                   overlaps the MMAs of tiles t+1..t+3
-//                          warps 2-9 epilogue, two groups of four alternating over the tiles:
-//                                   tcgen05.ld -> * 1/sqrt(D) -> bf16 -> swizzled smem -> TMA store
+//                                   4 x 128 columns = two accumulators per resident A tile, so the epilogue
+//                                   of one B tile overlaps the MMAs of the next
+//                          warps 2-9 epilogue, group g drains the tiles of resident A tile g:
+//                                   tcgen05.ld -> * 1/sqrt(D) -> bf16 -> swizzled smem -> TMA store of one
+//                                   contiguous 32 KB block of the panel-tiled pyramid, L2 evict-first
 //                        K = D = 128 only, so the kernel is bound by the bf16 store of the volume
-//                        (algorithmic bytes = Nf * Ncols * 2 per sample per direction), not by MMA.
+//                        (algorithmic bytes = Nf * Ncols * 2 per sample per direction), not by MMA:
+//                        the design minimises everything that competes with the store stream (operand
+//                        re-reads cut 4x by the resident pair, contiguous blocks instead of pitched rows).
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -31,21 +36,23 @@ constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int DIM = 128;     // feature dimension of the SLIM fnet (raft_mod.py:48)
 constexpr int K_BLOCKS = DIM / BLOCK_K;
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
-constexpr int ACC_STAGES = 4;
+constexpr int M_PER_CTA = 2;      // two 128-row tiles of A stay resident in shared memory (a "pair")
+constexpr int B_STAGES = 3;       // ring of B tiles (128 columns x full K)
+constexpr int ACC_STAGES = 4;     // 4 x 128 TMEM columns: two accumulators per resident A tile
 constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;  // 512
-constexpr int EPI_GROUPS = 2;     // two epilogue warpgroups alternate over the tiles
-constexpr int OUT_STAGES = EPI_GROUPS;  // one staging buffer per epilogue group
+constexpr int EPI_GROUPS = M_PER_CTA;            // epilogue group g drains the tiles of resident A tile g
 constexpr int GEMM_THREADS = 64 + 128 * EPI_GROUPS;
 constexpr int EPI_THREADS = 128;
 
-constexpr uint32_t A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
-constexpr uint32_t B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;  // 16 KB
-constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr uint32_t OUT_HALF_BYTES = BLOCK_M * 64 * 2;  // 128 rows x 128 B
-constexpr uint32_t OUT_STAGE_BYTES = 2 * OUT_HALF_BYTES;
-constexpr uint32_t SMEM_DATA_BYTES = STAGES * STAGE_BYTES + OUT_STAGES * OUT_STAGE_BYTES;  // 192 KB
+constexpr uint32_t KBLK_BYTES = BLOCK_M * BLOCK_K * 2;          // 16 KB: 128 rows x 64 k, 128B-swizzled
+constexpr uint32_t TILE_OP_BYTES = K_BLOCKS * KBLK_BYTES;       // 32 KB: one 128-row operand tile, full K
+constexpr uint32_t A_BYTES = M_PER_CTA * TILE_OP_BYTES;         // 64 KB resident
+constexpr uint32_t B_BYTES = B_STAGES * TILE_OP_BYTES;          // 96 KB ring
+constexpr uint32_t OUT_HALF_BYTES = BLOCK_M * 64 * 2;           // 128 rows x 128 B
+constexpr uint32_t OUT_STAGE_BYTES = 2 * OUT_HALF_BYTES;        // 32 KB
+constexpr uint32_t SMEM_DATA_BYTES = A_BYTES + B_BYTES + EPI_GROUPS * OUT_STAGE_BYTES;  // 224 KB
 constexpr uint32_t SMEM_BYTES = SMEM_DATA_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
 
 // ---------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -155,23 +162,30 @@ constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOC
                            ((uint32_t)(BLOCK_M >> 4) << 24);
 
 struct GemmShape {
-  int batch, m_tiles, n_tiles, total_tiles;
+  int batch, m_tiles, m_pairs, n_tiles, total_items;  // item = (sample, pair of m tiles, n tile)
   float scale;
 };
 
+// Persistent CTA c owns the contiguous item range [c * Q / G, (c + 1) * Q / G) of the (sample, m pair)-major,
+// n-minor order, so the 256 A rows of a pair are loaded once and stay in shared memory while the B tiles
+// stream through: 16 KB of operand traffic per 32 KB output tile instead of 64 KB.
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_corr_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_c, const GemmShape shape) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t smem_out = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_base + A_BYTES;
+  const uint32_t smem_out = smem_b + B_BYTES;
   const uint32_t bar_base = smem_base + SMEM_DATA_BYTES;
-  // barrier layout (8 bytes each): full[STAGES], empty[STAGES], tmem_full[ACC], tmem_empty[ACC], tmem ptr
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + ACC_STAGES + s); };
-  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES);
+  // barriers (8 bytes each): b_full[B_STAGES], b_empty[B_STAGES], a_full, a_empty, tmem_full[ACC], tmem_empty[ACC]
+  auto bfull_bar = [&](int s) { return bar_base + 8u * s; };
+  auto bempty_bar = [&](int s) { return bar_base + 8u * (B_STAGES + s); };
+  const uint32_t afull_bar = bar_base + 8u * (2 * B_STAGES);
+  const uint32_t aempty_bar = bar_base + 8u * (2 * B_STAGES + 1);
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * B_STAGES + 2 + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * B_STAGES + 2 + ACC_STAGES + s); };
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * B_STAGES + 2 + 2 * ACC_STAGES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -180,10 +194,12 @@ k_corr_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+    for (int s = 0; s < B_STAGES; ++s) {
+      mbar_init(bfull_bar(s), 1);
+      mbar_init(bempty_bar(s), 1);
     }
+    mbar_init(afull_bar, 1);
+    mbar_init(aempty_bar, 1);
     for (int s = 0; s < ACC_STAGES; ++s) {
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), EPI_THREADS / 32);
@@ -201,88 +217,112 @@ k_corr_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
-  const int tiles_per_b = shape.m_tiles * shape.n_tiles;
+  const int q0 = (int)((long long)blockIdx.x * shape.total_items / gridDim.x);
+  const int q1 = (int)((long long)(blockIdx.x + 1) * shape.total_items / gridDim.x);
 
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (elect_one()) {
       int stage = 0;
-      uint32_t phase = 0;
-      for (int t = blockIdx.x; t < shape.total_tiles; t += gridDim.x) {
-        const int b = t / tiles_per_b;
-        const int r = t - b * tiles_per_b;
-        const int m = r / shape.n_tiles, n = r - m * shape.n_tiles;
-        for (int kb = 0; kb < K_BLOCKS; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-          const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          tma_load_3d(&map_a, full_bar(stage), sa, kb * BLOCK_K, m * BLOCK_M, b);
-          tma_load_3d(&map_b, full_bar(stage), sa + A_STAGE_BYTES, kb * BLOCK_K, n * BLOCK_N, b);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1u;
-          }
+      uint32_t phase = 0, a_phase = 0;
+      int cur_unit = -1;
+      for (int q = q0; q < q1; ++q) {
+        const int unit = q / shape.n_tiles, n = q - unit * shape.n_tiles;
+        const int b = unit / shape.m_pairs, pair = unit - b * shape.m_pairs;
+        if (unit != cur_unit) {
+          cur_unit = unit;
+          mbar_wait(aempty_bar, a_phase ^ 1u);  // every MMA that read the previous pair has retired
+          mbar_expect_tx(afull_bar, A_BYTES);
+#pragma unroll
+          for (int m = 0; m < M_PER_CTA; ++m)
+#pragma unroll
+            for (int kb = 0; kb < K_BLOCKS; ++kb)
+              tma_load_3d(&map_a, afull_bar, smem_a + (uint32_t)(m * K_BLOCKS + kb) * KBLK_BYTES, kb * BLOCK_K,
+                          (pair * M_PER_CTA + m) * BLOCK_M, b);
+          a_phase ^= 1u;
+        }
+        mbar_wait(bempty_bar(stage), phase ^ 1u);
+        mbar_expect_tx(bfull_bar(stage), TILE_OP_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < K_BLOCKS; ++kb)
+          tma_load_3d(&map_b, bfull_bar(stage), smem_b + (uint32_t)stage * TILE_OP_BYTES + (uint32_t)kb * KBLK_BYTES,
+                      kb * BLOCK_K, n * BLOCK_N, b);
+        if (++stage == B_STAGES) {
+          stage = 0;
+          phase ^= 1u;
         }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
     int stage = 0;
-    uint32_t phase = 0;
-    int it = 0;
-    for (int t = blockIdx.x; t < shape.total_tiles; t += gridDim.x, ++it) {
-      const int acc = it % ACC_STAGES;
-      const uint32_t acc_phase = (uint32_t)(it / ACC_STAGES) & 1u;
-      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-      tcgen05_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
-      for (int kb = 0; kb < K_BLOCKS; ++kb) {
-        mbar_wait(full_bar(stage), phase);
+    uint32_t phase = 0, a_phase = 0;
+    int cur_unit = -1;
+    int it = 0;  // accumulator tiles issued so far
+    for (int q = q0; q < q1; ++q) {
+      const int unit = q / shape.n_tiles;
+      if (unit != cur_unit) {
+        cur_unit = unit;
+        mbar_wait(afull_bar, a_phase);
+        a_phase ^= 1u;
+      }
+      mbar_wait(bfull_bar(stage), phase);
+      const bool last_of_unit = (q + 1 == q1) || ((q + 1) / shape.n_tiles != unit);
+#pragma unroll
+      for (int m = 0; m < M_PER_CTA; ++m, ++it) {
+        const int acc = it % ACC_STAGES;
+        const uint32_t acc_phase = (uint32_t)(it / ACC_STAGES) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tcgen05_fence_after();
         if (elect_one()) {
-          const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          const uint64_t adesc = make_smem_desc_sw128(sa);
-          const uint64_t bdesc = make_smem_desc_sw128(sa + A_STAGE_BYTES);
+          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // advance the start address by k * 16 elements * 2 B = 32 B (>> 4 = 2) inside the swizzle row
-            umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
+          for (int kb = 0; kb < K_BLOCKS; ++kb) {
+            const uint64_t adesc = make_smem_desc_sw128(smem_a + (uint32_t)(m * K_BLOCKS + kb) * KBLK_BYTES);
+            const uint64_t bdesc = make_smem_desc_sw128(smem_b + (uint32_t)stage * TILE_OP_BYTES + (uint32_t)kb * KBLK_BYTES);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              // advance the start address by k * 16 elements * 2 B = 32 B (>> 4 = 2) inside the swizzle row
+              umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
+            }
           }
-          tcgen05_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
-          if (kb == K_BLOCKS - 1) tcgen05_commit(tfull_bar(acc));
+          tcgen05_commit(tfull_bar(acc));
+          if (m == M_PER_CTA - 1) {
+            tcgen05_commit(bempty_bar(stage));          // frees the B slot when these MMAs retire
+            if (last_of_unit) tcgen05_commit(aempty_bar);  // ... and the resident A pair
+          }
         }
         __syncwarp();
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1u;
-        }
+      }
+      if (++stage == B_STAGES) {
+        stage = 0;
+        phase ^= 1u;
       }
     }
   } else {
     // ================================ epilogue ====================================
-    // Two groups of 4 warps; group g drains the accumulator of every tile with (it % 2 == g), so the
-    // TMEM -> register -> smem -> TMA-store chain of one tile overlaps the same chain of the next.
+    // Group g (4 warps) drains the accumulators of resident A tile g: TMEM -> registers -> * 1/sqrt(D) -> bf16 ->
+    // 128B-swizzled smem -> TMA store of one contiguous 32 KB panel block.
     const int grp = (warp - 2) >> 2;
-    const int q = warp & 3;                 // TMEM lane quarter this warp may read
-    const int row = q * 32 + lane;          // accumulator row == TMEM lane
+    const int qd = warp & 3;                // TMEM lane quarter this warp may read
+    const int row = qd * 32 + lane;         // accumulator row == TMEM lane
     const bool store_thread = (threadIdx.x == 64 + grp * EPI_THREADS);
     const uint32_t out_buf = smem_out + (uint32_t)grp * OUT_STAGE_BYTES;
     const int bar_id = 1 + grp;
     const uint64_t policy = l2_evict_first_policy();
-    for (int it = grp; ; it += EPI_GROUPS) {
-      const int t = blockIdx.x + it * gridDim.x;
-      if (t >= shape.total_tiles) break;
-      const int b = t / tiles_per_b;
-      const int r = t - b * tiles_per_b;
-      const int m = r / shape.n_tiles, n = r - m * shape.n_tiles;
+    int it = grp;
+    for (int q = q0; q < q1; ++q, it += M_PER_CTA) {
+      const int unit = q / shape.n_tiles, n = q - unit * shape.n_tiles;
+      const int b = unit / shape.m_pairs, pair = unit - b * shape.m_pairs;
+      const int m = pair * M_PER_CTA + grp;
       const int acc = it % ACC_STAGES;
       const uint32_t acc_phase = (uint32_t)(it / ACC_STAGES) & 1u;
-      // this group's staging buffer was handed to TMA one (group-)tile ago: wait until it has been read
+      // this group's staging buffer was handed to TMA one tile ago: wait until it has been read
       if (store_thread) tma_store_wait_read<0>();
       asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(EPI_THREADS) : "memory");
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * BLOCK_N);
       uint32_t v[2][32];
       tmem_ld_32x32b_x32(taddr, v[0]);
       tmem_ld_wait();
@@ -314,7 +354,7 @@ k_corr_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       // make the smem writes visible to the async proxy, then one thread issues the TMA stores
       fence_proxy_async_smem();
       asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(EPI_THREADS) : "memory");
-      if (store_thread) {
+      if (store_thread && m < shape.m_tiles) {
         // panel layout: tile (m, n) of sample b = rows [128 m, 128 m + 128) of panel b * n_tiles + n: 32 KB contiguous
         tma_store_3d(&map_c, out_buf, 0, m * BLOCK_M, b * shape.n_tiles + n, policy);
         tma_store_3d(&map_c, out_buf + OUT_HALF_BYTES, 64, m * BLOCK_M, b * shape.n_tiles + n, policy);
@@ -504,7 +544,8 @@ extern "C" int slimb200_corr_build(const float* fmap1, const float* fmap2, const
   shape.batch = L->batch;
   shape.m_tiles = (nf + BLOCK_M - 1) / BLOCK_M;
   shape.n_tiles = L->n_panels;
-  shape.total_tiles = shape.batch * shape.m_tiles * shape.n_tiles;
+  shape.m_pairs = (shape.m_tiles + M_PER_CTA - 1) / M_PER_CTA;
+  shape.total_items = shape.batch * shape.m_pairs * shape.n_tiles;
   shape.scale = 1.0f / sqrtf((float)L->dim);
 
   static int n_sm = 0;
@@ -514,7 +555,7 @@ extern "C" int slimb200_corr_build(const float* fmap1, const float* fmap2, const
     SLIMB200_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     SLIMB200_CUDA_TRY(cudaFuncSetAttribute(k_corr_gemm_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   }
-  const int grid = shape.total_tiles < n_sm ? shape.total_tiles : n_sm;
+  const int grid = shape.total_items < n_sm ? shape.total_items : n_sm;
   SLIMB200_LAUNCH(SLIMB200_K_CORR_GEMM, stream,
                   (k_corr_gemm_tcgen05<<<grid, GEMM_THREADS, SMEM_BYTES, stream>>>(map_a, map_b, map_c, shape)));
   return SLIMB200_OK;
