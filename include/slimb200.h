@@ -139,14 +139,16 @@ int slimb200_corr_layout_init(int32_t batch, int32_t dim, int32_t h, int32_t w, 
 size_t slimb200_corr_workspace_bytes(const slimb200_corr_layout* L);
 size_t slimb200_corr_pyramid_bytes(const slimb200_corr_layout* L, int32_t store_dtype);
 
-/* fmap1, fmap2: device (batch, dim, h, w) f32 contiguous (dim == 128).
+/* fmap1, fmap2: device (batch, dim, h, w) f32 (dim == 128), 16-byte aligned; fmap_layout says how they are stored:
+ *   SLIMB200_CANVAS_NCHW contiguous, or SLIMB200_CANVAS_NHWC = channels-last (batch, h, w, dim), which is what a
+ *   channels-last fnet emits and needs no transposition.
  * pyramid: device bf16, slimb200_corr_pyramid_bytes() bytes, 128-byte aligned.
  * Computes pyramid[b][i][j] = bf16( sum_d f1[b,d,i] * pool_l(f2)[b,d,j] / sqrt(dim) ) with bf16
  * operands and fp32 accumulation on the tcgen05 tensor cores (pooling folded into the operand:
  * avg_pool(corr) == corr(avg_pool(f2)) by linearity). */
-int slimb200_corr_build(const float* fmap1, const float* fmap2, const slimb200_corr_layout* L,
-                        int32_t store_dtype, void* pyramid, void* workspace, size_t workspace_bytes,
-                        void* stream);
+int slimb200_corr_build(const float* fmap1, const float* fmap2, int32_t fmap_layout,
+                        const slimb200_corr_layout* L, int32_t store_dtype, void* pyramid, void* workspace,
+                        size_t workspace_bytes, void* stream);
 
 /* coords: device (batch, 2, h, w) f32, channel 0 = x (column), 1 = y (row).
  * out:    device (batch, levels * (2r+1)^2, h, w) f32 contiguous, channel k = l*(2r+1)^2 + i*(2r+1) + j
@@ -171,6 +173,7 @@ enum {
   SLIMB200_K_BN_FINALIZE,
   SLIMB200_K_TILE_ENCODE,
   SLIMB200_K_PILLAR_NHWC,
+  SLIMB200_K_FEAT_TRANSPOSE,
   SLIMB200_K_FEAT_PACK,
   SLIMB200_K_CORR_GEMM,
   SLIMB200_K_CORR_LOOKUP,

@@ -74,7 +74,8 @@ SYMBOLS = {
     "slimb200_corr_pyramid_bytes": (C.c_size_t, [C.POINTER(CorrLayout), C.c_int32]),
     "slimb200_corr_build": (
         C.c_int,
-        [C.c_void_p, C.c_void_p, C.POINTER(CorrLayout), C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p],
+        [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(CorrLayout), C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t,
+         C.c_void_p],
     ),
     "slimb200_corr_lookup": (
         C.c_int,
@@ -87,8 +88,8 @@ SYMBOLS = {
     "slimb200_launch_count": (C.c_int64, [C.c_int32]),
     "slimb200_kernel_name": (C.c_char_p, [C.c_int32]),
 }
-N_KERNELS = 12
-K_TILE_ENCODE, K_PILLAR_NHWC, K_FEAT_PACK, K_CORR_GEMM, K_CORR_LOOKUP = 6, 7, 8, 9, 10
+N_KERNELS = 13
+K_TILE_ENCODE, K_PILLAR_NHWC, K_FEAT_TRANSPOSE, K_FEAT_PACK, K_CORR_GEMM, K_CORR_LOOKUP = 6, 7, 8, 9, 10, 11
 CANVAS_NCHW, CANVAS_NHWC = 0, 1
 
 _lib: Optional[C.CDLL] = None

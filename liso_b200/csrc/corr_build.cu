@@ -373,67 +373,102 @@ k_corr_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 }
 
 // ---------------------------------------------------------------------------- operand pack
+// Feature maps arrive pixel-major (NHWC, what the channels-last fnet emits: 512 contiguous bytes per pixel) or
+// NCHW (transposed to pixel-major scratch first).  One warp produces one K-major bf16 operand row: lane d/4
+// holds 4 dims, so every load is a coalesced 512-byte row and every store a coalesced 256-byte row.
+// Pooled rows of the B operand evaluate F.avg_pool2d(k=2, s=2) iterated in fp32 (corr.py:20): window order
+// (0,0),(0,1),(1,0),(1,1), then * 0.25, recursively.  Rows are scheduled heaviest first (level 3 = 64 loads).
 template <int L>
-__device__ __forceinline__ float pooled(const float* __restrict__ img, int w, int r, int c) {
+__device__ __forceinline__ float4 pooled4(const float4* __restrict__ img, int w, int r, int c) {
   if constexpr (L == 0) {
-    return __ldg(img + (size_t)r * w + c);
+    return __ldg(img + ((size_t)r * w + c) * (DIM / 4));
   } else {
-    // F.avg_pool2d(k=2, s=2): sum in window order (0,0),(0,1),(1,0),(1,1), then / 4  (corr.py:20)
-    float s = pooled<L - 1>(img, w, 2 * r, 2 * c);
-    s += pooled<L - 1>(img, w, 2 * r, 2 * c + 1);
-    s += pooled<L - 1>(img, w, 2 * r + 1, 2 * c);
-    s += pooled<L - 1>(img, w, 2 * r + 1, 2 * c + 1);
-    return s * 0.25f;
+    float4 s = pooled4<L - 1>(img, w, 2 * r, 2 * c);
+    float4 t = pooled4<L - 1>(img, w, 2 * r, 2 * c + 1);
+    s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    t = pooled4<L - 1>(img, w, 2 * r + 1, 2 * c);
+    s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    t = pooled4<L - 1>(img, w, 2 * r + 1, 2 * c + 1);
+    s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    s.x *= 0.25f; s.y *= 0.25f; s.z *= 0.25f; s.w *= 0.25f;
+    return s;
   }
 }
 
-constexpr int PACK_ROWS = 32;
-constexpr int PACK_PITCH = DIM + 8;
+constexpr int PACK_WARPS = 8;
 
-// grid.x: row groups of A (ceil(Nf/32)) followed by row groups of B_ext (ceil(Ncols/32)); grid.y: batch
-__global__ void __launch_bounds__(256) k_feat_pack(const float* __restrict__ fmap1, const float* __restrict__ fmap2,
-                                                   const slimb200_corr_layout L, __nv_bfloat16* __restrict__ A,
-                                                   __nv_bfloat16* __restrict__ Bx) {
-  __shared__ __align__(16) __nv_bfloat16 s[PACK_ROWS][PACK_PITCH];
-  const int b = blockIdx.y;
+// f1, f2: (batch, nf, 128) fp32 pixel-major.  Row order per sample: B rows of level L-1 .. 0, then the A rows.
+__global__ void __launch_bounds__(PACK_WARPS * 32) k_feat_pack(const float* __restrict__ f1, const float* __restrict__ f2,
+                                                               const slimb200_corr_layout L, __nv_bfloat16* __restrict__ A,
+                                                               __nv_bfloat16* __restrict__ Bx) {
   const int nf = L.h * L.w;
-  const int groups_a = (nf + PACK_ROWS - 1) / PACK_ROWS;
-  const bool is_a = (int)blockIdx.x < groups_a;
-  const int row0 = (is_a ? blockIdx.x : blockIdx.x - groups_a) * PACK_ROWS;
-  const int n_rows = is_a ? nf : L.n_cols;
-  const int lane = lane_id(), warp = warp_id();
-  const int row = row0 + lane;
-  const float* src = (is_a ? fmap1 : fmap2) + (size_t)b * DIM * nf;
-  if (row < n_rows) {
-    int lvl = 0;
-    if (!is_a) {
-      while (lvl + 1 < L.levels && row >= L.level_offset[lvl + 1]) ++lvl;
-    }
-    const int local = row - (is_a ? 0 : L.level_offset[lvl]);
-    const int wl = is_a ? L.w : L.level_w[lvl];
-    const int r = local / wl, c = local - r * wl;
-#pragma unroll 4
-    for (int i = 0; i < DIM / 8; ++i) {
-      const int d = warp * (DIM / 8) + i;
-      const float* img = src + (size_t)d * nf;
-      float v;
-      switch (lvl) {
-        case 0: v = pooled<0>(img, L.w, r, c); break;
-        case 1: v = pooled<1>(img, L.w, r, c); break;
-        case 2: v = pooled<2>(img, L.w, r, c); break;
-        default: v = pooled<3>(img, L.w, r, c); break;
+  const int rows_per_sample = L.n_cols + nf;
+  const long long gw = (long long)blockIdx.x * PACK_WARPS + (threadIdx.x >> 5);
+  if (gw >= (long long)rows_per_sample * L.batch) return;
+  // samples interleaved (gw % batch) so that all samples finish their heavy rows first
+  const int b = (int)(gw % L.batch);
+  int row = (int)(gw / L.batch);
+  const int lane = threadIdx.x & 31;
+  float4 v;
+  __nv_bfloat16* dst;
+  if (row < L.n_cols) {
+    // heaviest first: walk the levels from the coarsest (static indices: L stays in the constant bank)
+    int lvl = 0, wl = L.level_w[0], off = 0;
+    bool found = false;
+#pragma unroll
+    for (int l = SLIMB200_MAX_LEVELS - 1; l >= 1; --l) {
+      if (l < L.levels && !found) {
+        const int n = L.level_h[l] * L.level_w[l];
+        if (row < n) {
+          lvl = l;
+          wl = L.level_w[l];
+          off = L.level_offset[l];
+          found = true;
+        } else {
+          row -= n;
+        }
       }
-      s[lane][d] = __float2bfloat16_rn(v);
     }
+    const int r = row / wl, c = row - r * wl;
+    const float4* img = reinterpret_cast<const float4*>(f2 + (size_t)b * nf * DIM) + lane;
+    switch (lvl) {
+      case 0: v = pooled4<0>(img, L.w, r, c); break;
+      case 1: v = pooled4<1>(img, L.w, r, c); break;
+      case 2: v = pooled4<2>(img, L.w, r, c); break;
+      default: v = pooled4<3>(img, L.w, r, c); break;
+    }
+    dst = Bx + ((size_t)b * L.n_cols + off + row) * DIM;
+  } else {
+    row -= L.n_cols;
+    v = __ldg(reinterpret_cast<const float4*>(f1 + ((size_t)b * nf + row) * DIM) + lane);
+    dst = A + ((size_t)b * nf + row) * DIM;
+  }
+  __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&lo);
+  pk.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(dst + lane * 4) = pk;
+}
+
+// (batch, 128, nf) fp32 -> (batch, nf, 128) fp32, 32 x 32 tiles through shared memory; blockIdx.z = b * 2 + which map
+__global__ void __launch_bounds__(256) k_nchw_to_pixel_major(const float* __restrict__ f1, const float* __restrict__ f2, int nf,
+                                                             float* __restrict__ o1, float* __restrict__ o2) {
+  __shared__ float tile[32][33];
+  const int which = blockIdx.z & 1, b = blockIdx.z >> 1;
+  const float* src = (which ? f2 : f1) + (size_t)b * DIM * nf;
+  float* dst = (which ? o2 : o1) + (size_t)b * DIM * nf;
+  const int p0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int d = d0 + ty + 8 * k, pix = p0 + tx;
+    tile[ty + 8 * k][tx] = pix < nf ? __ldg(src + (size_t)d * nf + pix) : 0.f;
   }
   __syncthreads();
-  __nv_bfloat16* dst = (is_a ? A : Bx) + (size_t)b * n_rows * DIM;
-  for (int qd = threadIdx.x; qd < PACK_ROWS * (DIM / 8); qd += 256) {
-    const int rr = qd / (DIM / 8), ch = qd - rr * (DIM / 8);
-    if (row0 + rr < n_rows) {
-      const uint4 val = *reinterpret_cast<const uint4*>(&s[rr][ch * 8]);
-      *reinterpret_cast<uint4*>(dst + (size_t)(row0 + rr) * DIM + ch * 8) = val;
-    }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int pix = p0 + ty + 8 * k;
+    if (pix < nf) dst[(size_t)pix * DIM + d0 + tx] = tile[tx][ty + 8 * k];
   }
 }
 
@@ -507,13 +542,17 @@ extern "C" size_t slimb200_corr_workspace_bytes(const slimb200_corr_layout* L) {
   WorkspaceCarver w(nullptr);
   w.take<__nv_bfloat16>((size_t)L->batch * L->h * L->w * DIM);
   w.take<__nv_bfloat16>((size_t)L->batch * L->n_cols * DIM);
+  w.take<float>((size_t)L->batch * L->h * L->w * DIM);  // pixel-major scratch, used for NCHW inputs only
+  w.take<float>((size_t)L->batch * L->h * L->w * DIM);
   return w.used();
 }
 
-extern "C" int slimb200_corr_build(const float* fmap1, const float* fmap2, const slimb200_corr_layout* L,
-                                   int32_t store_dtype, void* pyramid, void* workspace, size_t workspace_bytes,
-                                   void* stream_) {
+extern "C" int slimb200_corr_build(const float* fmap1, const float* fmap2, int32_t fmap_layout,
+                                   const slimb200_corr_layout* L, int32_t store_dtype, void* pyramid, void* workspace,
+                                   size_t workspace_bytes, void* stream_) {
   if (!fmap1 || !fmap2 || !L || !pyramid || !workspace) return SLIMB200_E_INVALID;
+  if (fmap_layout != SLIMB200_CANVAS_NCHW && fmap_layout != SLIMB200_CANVAS_NHWC) return SLIMB200_E_INVALID;
+  if ((reinterpret_cast<uintptr_t>(fmap1) & 15) || (reinterpret_cast<uintptr_t>(fmap2) & 15)) return SLIMB200_E_ALIGNMENT;
   if (store_dtype != SLIMB200_DTYPE_BF16 || L->dim != DIM) return SLIMB200_E_UNSUPPORTED;
   if (workspace_bytes < slimb200_corr_workspace_bytes(L)) return SLIMB200_E_WORKSPACE;
   if ((reinterpret_cast<uintptr_t>(pyramid) & 127) || (reinterpret_cast<uintptr_t>(workspace) & 255))
@@ -523,6 +562,8 @@ extern "C" int slimb200_corr_build(const float* fmap1, const float* fmap2, const
   WorkspaceCarver w(workspace);
   __nv_bfloat16* A = w.take<__nv_bfloat16>((size_t)L->batch * nf * DIM);
   __nv_bfloat16* Bx = w.take<__nv_bfloat16>((size_t)L->batch * L->n_cols * DIM);
+  float* s1 = w.take<float>((size_t)L->batch * nf * DIM);
+  float* s2 = w.take<float>((size_t)L->batch * nf * DIM);
 
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return SLIMB200_E_DRIVER;
@@ -535,10 +576,16 @@ extern "C" int slimb200_corr_build(const float* fmap1, const float* fmap2, const
       SLIMB200_OK)
     return rc;
 
+  if (fmap_layout == SLIMB200_CANVAS_NCHW) {
+    dim3 g((nf + 31) / 32, DIM / 32, L->batch * 2);
+    SLIMB200_LAUNCH(SLIMB200_K_FEAT_TRANSPOSE, stream, (k_nchw_to_pixel_major<<<g, 256, 0, stream>>>(fmap1, fmap2, nf, s1, s2)));
+    fmap1 = s1;
+    fmap2 = s2;
+  }
   {
-    const int groups = (nf + PACK_ROWS - 1) / PACK_ROWS + (L->n_cols + PACK_ROWS - 1) / PACK_ROWS;
-    SLIMB200_LAUNCH(SLIMB200_K_FEAT_PACK, stream,
-                    (k_feat_pack<<<dim3(groups, L->batch), 256, 0, stream>>>(fmap1, fmap2, *L, A, Bx)));
+    const long long rows = (long long)(L->n_cols + nf) * L->batch;
+    const unsigned blocks = (unsigned)((rows + PACK_WARPS - 1) / PACK_WARPS);
+    SLIMB200_LAUNCH(SLIMB200_K_FEAT_PACK, stream, (k_feat_pack<<<blocks, PACK_WARPS * 32, 0, stream>>>(fmap1, fmap2, *L, A, Bx)));
   }
   GemmShape shape;
   shape.batch = L->batch;

@@ -101,12 +101,17 @@ class CorrBlock:
         B, D, h, w = fmap1.shape
         lib = _lib.load()
         self.layout = make_layout(B, D, h, w, num_levels)
-        f1 = fmap1.detach().float().contiguous()
-        f2 = fmap2.detach().float().contiguous()
+        f1, f2 = fmap1.detach().float(), fmap2.detach().float()
+        # feed the kernel whatever layout the feature encoder produced: channels-last needs no transposition
+        nhwc = f1.is_contiguous(memory_format=torch.channels_last) and f2.is_contiguous(memory_format=torch.channels_last) \
+            and not (f1.is_contiguous() and f2.is_contiguous())
+        if not nhwc:
+            f1, f2 = f1.contiguous(), f2.contiguous()
+        layout_flag = _lib.CANVAS_NHWC if nhwc else _lib.CANVAS_NCHW
         L = self.layout
         self.pyramid = torch.empty((B * L.n_panels * h * w, _lib.PANEL_COLS), dtype=torch.bfloat16, device=f1.device)
         ws = torch.empty(lib.slimb200_corr_workspace_bytes(C.byref(L)), dtype=torch.uint8, device=f1.device)
-        _lib.check(lib.slimb200_corr_build(f1.data_ptr(), f2.data_ptr(), C.byref(L), _lib.DTYPE_BF16,
+        _lib.check(lib.slimb200_corr_build(f1.data_ptr(), f2.data_ptr(), layout_flag, C.byref(L), _lib.DTYPE_BF16,
                                            self.pyramid.data_ptr(), ws.data_ptr(), ws.numel(),
                                            _lib.current_stream_ptr()))
         self.corr_pyramid = _LazyLevels(self.pyramid, L)

@@ -30,9 +30,12 @@ def _bound(f1, f2_level):
     return (2.0 ** -7) * n1[:, :, None] * n2[:, None, :] / np.sqrt(128.0)
 
 
+@pytest.mark.parametrize("fmt", ["contiguous", "channels_last"])
 @pytest.mark.parametrize("B,h,w", [(1, 16, 16), (2, 32, 32), (1, 80, 80), (1, 23, 23), (2, 12, 20), (1, 115, 115)])
-def test_pyramid_within_bf16_bound(cuda, B, h, w):
+def test_pyramid_within_bf16_bound(cuda, B, h, w, fmt):
     f1, f2, d1, d2 = _fmaps(B, h, w, 0, cuda)
+    if fmt == "channels_last":  # what a channels-last fnet hands over: no transposition kernel on this path
+        d1, d2 = d1.contiguous(memory_format=torch.channels_last), d2.contiguous(memory_format=torch.channels_last)
     blk = C.CorrBlock(d1, d2, num_levels=4, radius=3)
     torch.cuda.synchronize()
     ref = O.corr_pyramid(f1, f2, 4)

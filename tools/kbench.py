@@ -48,14 +48,20 @@ def main():
         coords = (coords_grid(B, h, w, dev) + 1.5 * torch.randn(B, 2, h, w, generator=g).to(dev)).contiguous()
         state = {}
 
+        f1c, f2c = f1.contiguous(memory_format=torch.channels_last), f2.contiguous(memory_format=torch.channels_last)
+
         def build():
+            state["blk"] = CorrBlock(f1c, f2c, num_levels=4, radius=3)
+
+        def build_nchw():
             state["blk"] = CorrBlock(f1, f2, num_levels=4, radius=3)
 
         def look():
             for _ in range(6):
                 state["out"] = state["blk"](coords)
 
-        runs.append(("corr_build", build))
+        runs.append(("corr_build nchw", build_nchw))
+        runs.append(("corr_build nhwc", build))
         runs.append(("corr_lookup x6", look))
     with torch.no_grad():
         for name, fn in runs:
