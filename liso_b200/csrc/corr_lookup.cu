@@ -18,6 +18,8 @@
 // fully predicated global-memory path so that results always follow the reference arithmetic.
 #include <cuda_bf16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -235,6 +237,259 @@ __global__ void __launch_bounds__(LK_THREADS) k_corr_lookup(const T* __restrict_
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Specialisation for the SLIM configuration (radius 3: 7 x 7 window, 8 x 8 fetched): same phases as the generic
+// kernel, but the fetched row segments are re-aligned to window column 0 while they are staged, so phase 3 works
+// on registers with compile-time offsets, and the interpolation is separable (8 x 7 horizontal + 7 x 7 vertical
+// blends per level instead of 49 x 4 taps).  Warp w serves level w / 2; its half w % 2 fetches window rows
+// 4 (w % 2) .. +3 in phase 2 and produces window columns i in {0..3} or {4..6} in phase 3.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct V3 {
+  static constexpr int R = 3, WIN = 7, W1 = 8;
+  static constexpr int EPC = Elem<T>::EPC;
+  static constexpr int NCHUNK = Cfg<T, 3>::NCHUNK;       // 2 (bf16) / 3 (fp32) 16-byte chunks per row segment
+  static constexpr int WPR = W1 * (int)sizeof(T) / 4;    // 32-bit words per aligned window row: 4 / 8
+  __host__ __device__ static constexpr int win_words(int levels) { return levels * W1 * WPR * LK_PIX; }
+  __host__ __device__ static constexpr int tab_words(int levels) { return levels * 2 * WIN * LK_PIX; }
+  __host__ __device__ static constexpr int smem_bytes(int levels) {
+    return (win_words(levels) + 3 * tab_words(levels) + 3 * levels * LK_PIX) * 4;
+  }
+};
+
+// window element c (0..7) of an aligned row held in registers
+template <typename T, int C>
+__device__ __forceinline__ float win_elem(const uint32_t* w);
+template <>
+__device__ __forceinline__ float win_elem<float, 0>(const uint32_t* w) { return __uint_as_float(w[0]); }
+#define SLIMB200_WIN_ELEM_F32(C) \
+  template <>                    \
+  __device__ __forceinline__ float win_elem<float, C>(const uint32_t* w) { return __uint_as_float(w[C]); }
+SLIMB200_WIN_ELEM_F32(1) SLIMB200_WIN_ELEM_F32(2) SLIMB200_WIN_ELEM_F32(3) SLIMB200_WIN_ELEM_F32(4)
+SLIMB200_WIN_ELEM_F32(5) SLIMB200_WIN_ELEM_F32(6) SLIMB200_WIN_ELEM_F32(7)
+#define SLIMB200_WIN_ELEM_BF16(C)                                                          \
+  template <>                                                                              \
+  __device__ __forceinline__ float win_elem<__nv_bfloat16, C>(const uint32_t* w) {         \
+    return __uint_as_float((C & 1) ? (w[C >> 1] & 0xffff0000u) : (w[C >> 1] << 16));       \
+  }
+SLIMB200_WIN_ELEM_BF16(0) SLIMB200_WIN_ELEM_BF16(1) SLIMB200_WIN_ELEM_BF16(2) SLIMB200_WIN_ELEM_BF16(3)
+SLIMB200_WIN_ELEM_BF16(4) SLIMB200_WIN_ELEM_BF16(5) SLIMB200_WIN_ELEM_BF16(6) SLIMB200_WIN_ELEM_BF16(7)
+
+// shift `s` elements out of the NCHUNK * 4 loaded words so that window column 0 lands in word 0
+template <typename T>
+__device__ __forceinline__ void realign(const uint32_t* ld, int s, uint32_t* out);
+template <>
+__device__ __forceinline__ void realign<float>(const uint32_t* ld, int s, uint32_t* out) {  // 12 words in, s in 0..3, 8 out
+  uint32_t t[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) t[k] = (s & 2) ? ld[k + 2] : ld[k];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) out[k] = (s & 1) ? t[k + 1] : t[k];
+}
+template <>
+__device__ __forceinline__ void realign<__nv_bfloat16>(const uint32_t* ld, int s, uint32_t* out) {  // 8 words in, s in 0..7, 4 out
+  const int ws = s >> 1;
+  uint32_t t[7], x[5];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) t[k] = (ws & 1) ? ld[k + 1] : ld[k];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) x[k] = (ws & 2) ? t[k + 2] : t[k];
+  const int sh = (s & 1) * 16;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) out[k] = __funnelshift_r(x[k], x[k + 1], sh);
+}
+
+template <typename T, int I0, int I1>
+__device__ __forceinline__ void v3_columns(const uint32_t (*win)[V3<T>::WPR], const float* wy0, const float* wy1,
+                                           const float* s_w0x, const float* s_w1x, int lane, float* dst, size_t nf,
+                                           bool live) {
+  constexpr int WIN = 7, W1 = 8;
+  // I0..I1-1 are compile-time window columns
+  auto one = [&](auto ic) {
+    constexpr int I = decltype(ic)::value;
+    const float wx0 = s_w0x[I * LK_PIX + lane], wx1 = s_w1x[I * LK_PIX + lane];
+    float h[W1];
+#pragma unroll
+    for (int r = 0; r < W1; ++r) h[r] = fmaf(win_elem<T, I + 1>(win[r]), wx1, win_elem<T, I>(win[r]) * wx0);
+    if (live) {
+#pragma unroll
+      for (int j = 0; j < WIN; ++j) dst[((size_t)I * WIN + j) * nf] = fmaf(h[j + 1], wy1[j], h[j] * wy0[j]);
+    }
+  };
+  if constexpr (I0 == 0) {
+    one(std::integral_constant<int, 0>{});
+    one(std::integral_constant<int, 1>{});
+    one(std::integral_constant<int, 2>{});
+    one(std::integral_constant<int, 3>{});
+  } else {
+    one(std::integral_constant<int, 4>{});
+    one(std::integral_constant<int, 5>{});
+    one(std::integral_constant<int, 6>{});
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(LK_THREADS, 3) k_corr_lookup_r3(const T* __restrict__ pyr, const slimb200_corr_layout L,
+                                                                  const float* __restrict__ coords, float* __restrict__ out) {
+  using V = V3<T>;
+  constexpr int R = 3, WIN = 7, W1 = 8, EPC = V::EPC, NCHUNK = V::NCHUNK, WPR = V::WPR;
+  extern __shared__ __align__(16) uint32_t s_dyn[];
+  const int levels = L.levels;
+  uint32_t* s_win = s_dyn;                                                    // [level][row][word][lane], aligned rows
+  float* s_pos = reinterpret_cast<float*>(s_dyn + V::win_words(levels));      // [level][axis][offset][lane]
+  float* s_w0 = s_pos + V::tab_words(levels);
+  float* s_w1 = s_w0 + V::tab_words(levels);
+  int* s_xb = reinterpret_cast<int*>(s_w1 + V::tab_words(levels));
+  int* s_yb = s_xb + levels * LK_PIX;
+  int* s_ok = s_yb + levels * LK_PIX;
+  __shared__ float s_xy[2][LK_PIX];
+  __shared__ int s_lw[SLIMB200_MAX_LEVELS], s_lh[SLIMB200_MAX_LEVELS], s_lo[SLIMB200_MAX_LEVELS];
+
+  const int nf = L.h * L.w;
+  const int n_panels = L.n_panels;
+  const int b = blockIdx.y;
+  const int i0 = blockIdx.x * LK_PIX;
+  const int lane = lane_id(), warp = warp_id();
+  const int pix = i0 + lane;
+  const bool live = pix < nf;
+  const int n_ch = levels * WIN * WIN;
+
+  if (threadIdx.x < 2 * LK_PIX) {
+    const int ch = threadIdx.x / LK_PIX;
+    s_xy[ch][lane] = live ? __ldg(coords + ((size_t)b * 2 + ch) * nf + pix) : 0.f;
+  }
+  if (threadIdx.x == 64) {
+    s_lw[0] = L.level_w[0]; s_lw[1] = L.level_w[1]; s_lw[2] = L.level_w[2]; s_lw[3] = L.level_w[3];
+    s_lh[0] = L.level_h[0]; s_lh[1] = L.level_h[1]; s_lh[2] = L.level_h[2]; s_lh[3] = L.level_h[3];
+    s_lo[0] = L.level_offset[0]; s_lo[1] = L.level_offset[1]; s_lo[2] = L.level_offset[2]; s_lo[3] = L.level_offset[3];
+  }
+  __syncthreads();
+
+  // ---- phase 1: positions and masked weights ----
+  for (int e = warp; e < levels * 2 * WIN; e += LK_WARPS) {
+    const int l = e / (2 * WIN), rem = e - l * 2 * WIN;
+    const int axis = rem / WIN, o = rem - axis * WIN;
+    const int size = axis == 0 ? s_lw[l] : s_lh[l];
+    const float inv = 1.0f / (float)(1 << l);
+    const float ip = sample_pos(s_xy[axis][lane], inv, o - R, size);
+    const float f = floorf(ip);
+    const int i0p = (int)f;
+    const float w_hi = __fsub_rn(ip, f);
+    const float w_lo = __fsub_rn(__fadd_rn(f, 1.f), ip);
+    s_pos[e * LK_PIX + lane] = ip;
+    s_w0[e * LK_PIX + lane] = ((unsigned)i0p < (unsigned)size) ? w_lo : 0.f;
+    s_w1[e * LK_PIX + lane] = ((unsigned)(i0p + 1) < (unsigned)size) ? w_hi : 0.f;
+  }
+  __syncthreads();
+  for (int l = warp; l < levels; l += LK_WARPS) {
+    const int xb = (int)floorf(s_pos[((l * 2 + 0) * WIN) * LK_PIX + lane]);
+    const int yb = (int)floorf(s_pos[((l * 2 + 1) * WIN) * LK_PIX + lane]);
+    bool ok = true;
+#pragma unroll
+    for (int o = 1; o < WIN; ++o) {
+      ok = ok && ((int)floorf(s_pos[((l * 2 + 0) * WIN + o) * LK_PIX + lane]) == xb + o);
+      ok = ok && ((int)floorf(s_pos[((l * 2 + 1) * WIN + o) * LK_PIX + lane]) == yb + o);
+    }
+    s_xb[l * LK_PIX + lane] = xb;
+    s_yb[l * LK_PIX + lane] = yb;
+    s_ok[l * LK_PIX + lane] = ok ? 1 : 0;
+  }
+  __syncthreads();
+
+  // ---- phase 2: warp (level, half) fetches 4 window rows per pixel, re-aligned to window column 0 ----
+  for (int u = warp; u < levels * 2; u += LK_WARPS) {
+    const int l = u >> 1, half = u & 1;
+    const int W = s_lw[l], H = s_lh[l], off = s_lo[l];
+    const int xb = s_xb[l * LK_PIX + lane], yb = s_yb[l * LK_PIX + lane];
+    const bool okp = live && s_ok[l * LK_PIX + lane];
+    uint32_t ld[4][NCHUNK * 4];
+    int sft[4];
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const int y = yb + half * 4 + rr;
+      const bool row_ok = okp && (unsigned)y < (unsigned)H;
+      const int row0 = off + y * W;
+      const int a_start = row0 + xb;
+      const int ca = a_start & ~(EPC - 1);
+      sft[rr] = a_start - ca;
+      const int lo = row0 + max(xb, 0), hi = row0 + min(xb + W1, W);
+#pragma unroll
+      for (int c = 0; c < NCHUNK; ++c) {
+        const int col = ca + c * EPC;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (row_ok && col < hi && col + EPC > lo)
+          v = __ldg(reinterpret_cast<const uint4*>(pyr + panel_index<T>(n_panels, nf, b, pix, col)));
+        ld[rr][c * 4 + 0] = v.x;
+        ld[rr][c * 4 + 1] = v.y;
+        ld[rr][c * 4 + 2] = v.z;
+        ld[rr][c * 4 + 3] = v.w;
+      }
+    }
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      uint32_t al[WPR];
+      realign<T>(ld[rr], sft[rr], al);
+      uint32_t* dst = s_win + ((size_t)((l * W1 + half * 4 + rr) * WPR) * LK_PIX + lane);
+#pragma unroll
+      for (int k = 0; k < WPR; ++k) dst[k * LK_PIX] = al[k];
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 3: warp (level, half) blends window columns {0..3} / {4..6} ----
+  for (int u = warp; u < levels * 2; u += LK_WARPS) {
+    const int l = u >> 1, half = u & 1;
+    float* dst = out + ((size_t)b * n_ch + (size_t)l * WIN * WIN) * nf + pix;
+    if (s_ok[l * LK_PIX + lane]) {
+      uint32_t win[W1][WPR];
+#pragma unroll
+      for (int r = 0; r < W1; ++r)
+#pragma unroll
+        for (int k = 0; k < WPR; ++k) win[r][k] = s_win[((size_t)((l * W1 + r) * WPR + k)) * LK_PIX + lane];
+      float wy0[WIN], wy1[WIN];
+#pragma unroll
+      for (int j = 0; j < WIN; ++j) {
+        wy0[j] = s_w0[((l * 2 + 1) * WIN + j) * LK_PIX + lane];
+        wy1[j] = s_w1[((l * 2 + 1) * WIN + j) * LK_PIX + lane];
+      }
+      const float* w0x = s_w0 + ((l * 2 + 0) * WIN) * LK_PIX;
+      const float* w1x = s_w1 + ((l * 2 + 0) * WIN) * LK_PIX;
+      if (half == 0)
+        v3_columns<T, 0, 4>(win, wy0, wy1, w0x, w1x, lane, dst, (size_t)nf, live);
+      else
+        v3_columns<T, 4, 7>(win, wy0, wy1, w0x, w1x, lane, dst, (size_t)nf, live);
+    } else {
+      const int W = s_lw[l], H = s_lh[l], off = s_lo[l];
+      const int ib = half ? 4 : 0, ie = half ? WIN : 4;
+      for (int i = ib; i < ie; ++i) {
+        const float ix = s_pos[((l * 2 + 0) * WIN + i) * LK_PIX + lane];
+        for (int j = 0; j < WIN; ++j) {
+          const float iy = s_pos[((l * 2 + 1) * WIN + j) * LK_PIX + lane];
+          if (live) dst[((size_t)i * WIN + j) * nf] = sample_slow<T>(pyr, n_panels, nf, b, pix, W, H, off, ix, iy);
+        }
+      }
+    }
+  }
+}
+
+template <typename T>
+int launch_lookup_r3(const void* pyramid, const slimb200_corr_layout* L, const float* coords, float* out, cudaStream_t stream) {
+  using V = V3<T>;
+  const int nf = L->h * L->w;
+  const int smem = V::smem_bytes(L->levels);
+  static bool attr_set = false;
+  if (!attr_set) {
+    SLIMB200_CUDA_TRY(cudaFuncSetAttribute(k_corr_lookup_r3<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           V::smem_bytes(SLIMB200_MAX_LEVELS)));
+    attr_set = true;
+  }
+  dim3 grid((nf + LK_PIX - 1) / LK_PIX, L->batch);
+  SLIMB200_LAUNCH(SLIMB200_K_CORR_LOOKUP, stream,
+                  (k_corr_lookup_r3<T><<<grid, LK_THREADS, smem, stream>>>(static_cast<const T*>(pyramid), *L, coords, out)));
+  return SLIMB200_OK;
+}
+
 template <typename T, int R>
 int launch_lookup(const void* pyramid, const slimb200_corr_layout* L, const float* coords, float* out, cudaStream_t stream) {
   using C = Cfg<T, R>;
@@ -259,7 +514,7 @@ int dispatch_radius(int radius, const void* pyramid, const slimb200_corr_layout*
     case 0: return launch_lookup<T, 0>(pyramid, L, coords, out, stream);
     case 1: return launch_lookup<T, 1>(pyramid, L, coords, out, stream);
     case 2: return launch_lookup<T, 2>(pyramid, L, coords, out, stream);
-    case 3: return launch_lookup<T, 3>(pyramid, L, coords, out, stream);
+    case 3: return launch_lookup_r3<T>(pyramid, L, coords, out, stream);
     case 4: return launch_lookup<T, 4>(pyramid, L, coords, out, stream);
     default: return SLIMB200_E_UNSUPPORTED;
   }
