@@ -61,7 +61,7 @@ struct PillarArgs {
   int32_t* blk_cnt;         // [total point blocks] first-point flags per block
   int32_t* blk_base;        // [total point blocks] exclusive prefix inside the sample
   int32_t* pillar_base;     // [batch + 1] exclusive prefix of kept pillars
-  int4* pillar_info;        // [kept pillars] (cell key, first sorted point, point count, sample), first-appearance order
+  int4* pillar_info;        // [kept pillars] (cell key, first sorted point, point count, b << 24 | xi << 12 | yi), first-appearance order
   float* bn_ab;             // [2][MAX_COUT] alpha, beta' of the folded BatchNorm
   double* stat_partials;    // [STATS_MAX_CTAS][MAX_COUT][2]
   // parameters / outputs
@@ -256,9 +256,16 @@ __global__ void __launch_bounds__(PT_BLOCK) k_rank_scatter(const PillarArgs a) {
   if (flag) {
     const int ord = a.blk_base[pb] + before + __popc(bal & ((1u << lane) - 1u));
     a.cell_ord[key] = ord;
-    if (ord < a.p.max_voxels)
+    if (ord >= a.p.max_voxels) {
+      a.cell_count[key] = -a.cell_count[key];  // over the pillar cap: dropped, reads as "not kept" (count <= 0) downstream
+    } else {
+      const int tile = key / TILE_CELLS, cl = key - tile * TILE_CELLS;
+      const int tl = tile - b * a.tiles_per_sample;
+      const int tx = tl / a.tiles_y, ty = tl - tx * a.tiles_y;
+      const int xi = tx * TILE_R + cl / TILE_C, yi = ty * TILE_C + (cl % TILE_C);
       a.pillar_info[a.pillar_base[b] + ord] =
-          make_int4(key, a.tile_start[key / TILE_CELLS] + a.cell_prefix[key], a.cell_count[key], b);
+          make_int4(key, a.tile_start[tile] + a.cell_prefix[key], a.cell_count[key], (b << 24) | (xi << 12) | yi);
+    }
   }
   if (live && a.pt2pillar_out) a.pt2pillar_out[a.pt_off[b] + i] = -1;
   if (key >= 0) {
@@ -557,153 +564,235 @@ __global__ void __launch_bounds__(ENC_THREADS, 3) k_tile_encode(const PillarArgs
 // whatever the spatial distribution of the points:
 //   pillars  a.pillar_info[0 .. n_pillars): rank <= 32 candidates by point index (20 lowest kept), cluster mean by
 //            warp reduction, 10 -> 64 linear + folded BN + ReLU + max in registers, 2 channels per lane
-//   chunks   one BEV tile row (32 cells = 32 * c_out * 4 bytes contiguous) each: zero float4 stores predicated
-//            on the occupancy ballot, plus the 128-byte occupancy row
+//   chunks   32 consecutive cells of a canvas row (32 * c_out * 4 contiguous bytes) each, enumerated row-major so
+//            that consecutive warps stream consecutive pieces: the occupancy ballot of the chunk is cut into
+//            maximal runs of empty cells and every run is ONE bulk copy (cp.async.bulk / UBLKCP) from an 8 KB
+//            zero buffer in shared memory -- no store instructions, no registers; plus the 128-byte occupancy row
+// Both lists are software-pipelined (next chunk's counts, next pillar's points, the descriptor after next).
 // Every canvas byte is written exactly once and never read.
 // ------------------------------------------------------------------------------------------
 constexpr int NH_THREADS = 256;
 constexpr int NH_WARPS = NH_THREADS / 32;
-constexpr int NH_CTAS_PER_SM = 4;
+constexpr int NH_CTAS_PER_SM = 3;
+
+// 32-bit bitonic network over the first `width` (power of two) lanes; keys unique
+__device__ __forceinline__ unsigned bitonic_sort_u32(unsigned v, int width, int lane) {
+  for (int k = 2; k <= width; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const unsigned o = __shfl_xor_sync(0xffffffffu, v, j);
+      const bool take_min = ((lane & k) == 0) == ((lane & j) == 0);
+      v = take_min ? min(v, o) : max(v, o);
+    }
+  }
+  return v;
+}
+
+__device__ __forceinline__ void bulk_store_zero(void* dst, uint32_t zero_smem, int bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(zero_smem), "r"(bytes) : "memory");
+}
 
 __global__ void __launch_bounds__(NH_THREADS, NH_CTAS_PER_SM) k_pillar_nhwc(const PillarArgs a) {
-  const int lane = lane_id();
+  // per-warp staging: the (<= 24) kept points of the current pillar in slot order, then their 7 features
+  __shared__ __align__(16) float s_feat[NH_WARPS][24][8];
+  __shared__ __align__(128) float4 s_zero[TILE_C * MAX_COUT / 4];  // one chunk of zeros (8 KB), source of the bulk stores
+  const int lane = lane_id(), warp = warp_id();
+  for (int i = threadIdx.x; i < TILE_C * MAX_COUT / 4; i += NH_THREADS) s_zero[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  const uint32_t zero_smem = (uint32_t)__cvta_generic_to_shared(s_zero);
   const slimb200_pillar_params& p = a.p;
   const int G0 = p.grid[0], G1 = p.grid[1];
   const int c_out = p.c_out;
   const int max_pts = p.max_points;
-  const int gw = blockIdx.x * NH_WARPS + warp_id();
+  const int gw = blockIdx.x * NH_WARPS + warp;
   const int tw = gridDim.x * NH_WARPS;
 
-  float W[2][10], alpha[2], betap[2];
+  // Linear(10 -> 64) with the legacy aliasing folded in: input columns 7..9 repeat columns 0..2
+  // (pillar_encoder.py:129-147), so x = sum_{j<3} (W_j + W_{j+7}) g_j + sum_{3<=j<7} W_j g_j: 7 FMAs per channel.
+  float Wc[2][7], alpha[2], betap[2];
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
     const int c = lane + 32 * q;
     const bool cv = c < c_out;
     const int cf = p.c_in + 6;
+    const float* wr = a.linear_weight + c * cf;
+    const int sh = p.c_in == 3 ? 1 : 0;  // a 3-channel cloud has no intensity column
 #pragma unroll
-    for (int j = 0; j < 10; ++j) {
-      int col = j;
-      if (p.c_in == 3) col = j < 3 ? j : (j == 3 ? -1 : j - 1);
-      W[q][j] = (cv && col >= 0) ? __ldg(a.linear_weight + c * cf + col) : 0.f;
-    }
+    for (int j = 0; j < 3; ++j) Wc[q][j] = cv ? __ldg(wr + j) + __ldg(wr + 7 + j - sh) : 0.f;
+    Wc[q][3] = (cv && !sh) ? __ldg(wr + 3) : 0.f;
+#pragma unroll
+    for (int j = 4; j < 7; ++j) Wc[q][j] = cv ? __ldg(wr + j - sh) : 0.f;
     alpha[q] = cv ? a.bn_ab[c] : 0.f;
     betap[q] = cv ? a.bn_ab[MAX_COUT + c] : 0.f;
   }
 
   const int n_pillars = a.pillar_base[a.batch];
-  const int n_chunks = a.n_tiles * TILE_R;
+  const int n_chunks = a.n_tiles * TILE_R;  // = batch * rows_pad * tiles_y
   const int my_chunks = gw < n_chunks ? (n_chunks - gw + tw - 1) / tw : 0;
   const int my_pillars = gw < n_pillars ? (n_pillars - gw + tw - 1) / tw : 0;
-  const int q4 = c_out >> 2;  // float4 per cell
+  const int q4_log = 31 - __clz(c_out >> 2);  // float4 per cell = c_out / 4, a power of two
   int ci = 0, pi = 0;
+  const bool want_extra = a.coors_out || a.num_points_out || a.voxels_out || a.pt2pillar_out;
+  // software pipeline (the kernel is bound by load latency otherwise): the occupancy counts of the next chunk,
+  // the descriptor of the pillar after next and the points of the next pillar are always in flight
+  // chunks are enumerated row-major (sample, row, column tile), so consecutive warps stream consecutive 8 KB pieces
+  const int rows_pad = a.tiles_x * TILE_R;
+  const int d_ty = tw % a.tiles_y, d_rid = tw / a.tiles_y;
+  const int d_xi = d_rid % rows_pad, d_b = d_rid / rows_pad;
+  int zy = gw % a.tiles_y, zx = (gw / a.tiles_y) % rows_pad, zb = (gw / a.tiles_y) / rows_pad;
+  int cnt_next = my_chunks > 0
+                     ? a.cell_count[((zb * a.tiles_x + (zx >> 2)) * a.tiles_y + zy) * TILE_CELLS + (zx & 3) * TILE_C + lane]
+                     : 0;
   int4 info = my_pillars > 0 ? a.pillar_info[gw] : make_int4(0, 0, 0, 0);
+  int4 info_next = my_pillars > 1 ? a.pillar_info[gw + tw] : make_int4(0, 0, 0, 0);
+  unsigned idx_cur = 0xffffffffu;
+  float4 pt_cur = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (my_pillars > 0 && lane < info.z) {
+    idx_cur = (unsigned)a.sorted_idx[info.y + lane];
+    pt_cur = a.sorted_pts[info.y + lane];
+  }
 
   while (ci < my_chunks || pi < my_pillars) {
     const bool do_chunk = pi >= my_pillars || (ci < my_chunks && (long long)ci * my_pillars <= (long long)pi * my_chunks);
     if (do_chunk) {
-      // ---------------- zero fill of one tile row ----------------
-      const int zc = gw + ci * tw;
+      // ---------------- zero fill of one tile row (chunk) ----------------
       ++ci;
-      const int tile = zc / TILE_R, r = zc - tile * TILE_R;
-      const int b = tile / a.tiles_per_sample;
-      const int tl = tile - b * a.tiles_per_sample;
-      const int tx = tl / a.tiles_y, ty = tl - tx * a.tiles_y;
-      const int xi = tx * TILE_R + r, yi0 = ty * TILE_C;
-      const int cell = tile * TILE_CELLS + r * TILE_C + lane;
-      const int cnt = a.cell_count[cell];
-      const bool kept = cnt > 0 && a.cell_ord[cell] < p.max_voxels;
+      const int b = zb, xi = zx, yi0 = zy * TILE_C;
+      const int cnt = cnt_next;
+      if (ci < my_chunks) {
+        // advance (sample, row, column tile) by tw chunks without dividing, prefetch its occupancy counts
+        zy += d_ty;
+        if (zy >= a.tiles_y) { zy -= a.tiles_y; ++zx; }
+        zx += d_xi;
+        if (zx >= rows_pad) { zx -= rows_pad; ++zb; }
+        zb += d_b;
+        cnt_next = a.cell_count[((zb * a.tiles_x + (zx >> 2)) * a.tiles_y + zy) * TILE_CELLS + (zx & 3) * TILE_C + lane];
+      }
+      const bool kept = cnt > 0;  // cells over the pillar cap carry a negative count (k_rank_scatter)
       const unsigned mask = __ballot_sync(0xffffffffu, kept);
       if (xi < G0) {
         const size_t row = ((size_t)b * G0 + xi) * G1 + yi0;
         if (yi0 + lane < G1) a.occupancy[row + lane] = kept ? 1.f : 0.f;
-        float4* dst = reinterpret_cast<float4*>(a.canvas + row * c_out);
-        const int n_cols = min(TILE_C, G1 - yi0);
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int f = lane; f < n_cols * q4; f += 32) {
-          const int j = f / q4;
-          if (!((mask >> j) & 1u)) dst[f] = z;
+        if (lane == 0) {
+          // every maximal run of empty cells is one bulk copy (UBLKCP) of zeros from shared memory
+          const int n_cols = min(TILE_C, G1 - yi0);
+          unsigned empty = ~mask & (n_cols == 32 ? 0xffffffffu : ((1u << n_cols) - 1u));
+          const int cell_bytes = c_out * 4;
+          char* dst = reinterpret_cast<char*>(a.canvas + row * c_out);
+          while (empty) {
+            const int s0 = __ffs(empty) - 1;
+            const unsigned rest = ~(empty >> s0);           // first zero bit above s0 ends the run
+            const int len = rest ? __ffs(rest) - 1 : 32 - s0;
+            bulk_store_zero(dst + s0 * cell_bytes, zero_smem, len * cell_bytes);
+            empty = (len + s0 >= 32) ? 0u : (empty & ~((1u << (s0 + len)) - 1u));
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
     } else {
       // ---------------- one pillar ----------------
       const int row = gw + pi * tw;
       ++pi;
-      const int key = info.x, st = info.y, n_all = info.z, b = info.w;
-      if (pi < my_pillars) info = a.pillar_info[gw + pi * tw];  // prefetch the next one
-      const int tile = key / TILE_CELLS, cl = key - tile * TILE_CELLS;
-      const int tl = tile - b * a.tiles_per_sample;
-      const int tx = tl / a.tiles_y, ty = tl - tx * a.tiles_y;
-      const int xi = tx * TILE_R + cl / TILE_C, yi = ty * TILE_C + (cl % TILE_C);
-      // --- the max_points lowest point indices of the cell, ascending ------------------
+      const int st = info.y, n_all = info.z;
+      const int b = (unsigned)info.w >> 24, xi = (info.w >> 12) & 0xfff, yi = info.w & 0xfff;
+      const unsigned idx_mine = idx_cur;
+      const float4 mine = pt_cur;
+      // rotate the pipeline: points of the next pillar, descriptor of the one after
+      info = info_next;
+      idx_cur = 0xffffffffu;
+      if (pi < my_pillars && lane < info.z) {
+        idx_cur = (unsigned)a.sorted_idx[info.y + lane];
+        pt_cur = a.sorted_pts[info.y + lane];
+      }
+      if (pi + 1 < my_pillars) info_next = a.pillar_info[gw + (pi + 1) * tw];
+      const int n = n_all < max_pts ? n_all : max_pts;
+      // --- the max_points lowest point indices of the cell in ascending order -> slots 0..n-1 ---
       float4 pt = make_float4(0.f, 0.f, 0.f, 0.f);
       int pidx = 0;
-      const int n = n_all < max_pts ? n_all : max_pts;
-      if (n_all <= 32) {
-        unsigned idx = 0xffffffffu;
-        if (lane < n_all) {
-          idx = (unsigned)a.sorted_idx[st + lane];
-          pt = a.sorted_pts[st + lane];
+      if (n_all == 1) {
+        if (lane == 0) {
+          pidx = (int)idx_mine;
+          pt = mine;
         }
-        const int src = rank_order_small(idx, n_all, lane);
-        pidx = (int)__shfl_sync(0xffffffffu, idx, src);
-        pt.x = __shfl_sync(0xffffffffu, pt.x, src);
-        pt.y = __shfl_sync(0xffffffffu, pt.y, src);
-        pt.z = __shfl_sync(0xffffffffu, pt.z, src);
-        pt.w = __shfl_sync(0xffffffffu, pt.w, src);
       } else {
-        unsigned long long k64 = ((unsigned long long)(unsigned)a.sorted_idx[st + lane] << 32) | (unsigned)lane;
-        k64 = bitonic_sort_warp(k64);
-        const int keep = max_pts;
-        for (int base = 32; base < n_all; base += 32 - keep) {
-          if (lane >= keep) {
-            const int j = base + lane - keep;
-            k64 = j < n_all ? (((unsigned long long)(unsigned)a.sorted_idx[st + j] << 32) | (unsigned)j) : ~0ull;
-          }
+        if (n_all <= 32) {
+          unsigned key = lane < n_all ? ((idx_mine << 5) | (unsigned)lane) : 0xffffffffu;  // point index < 2^27
+          const int width = n_all <= 2 ? 2 : (n_all <= 4 ? 4 : (n_all <= 8 ? 8 : (n_all <= 16 ? 16 : 32)));
+          key = bitonic_sort_u32(key, width, lane);
+          const int src = key & 31u;
+          pidx = (int)(key >> 5);
+          pt.x = __shfl_sync(0xffffffffu, mine.x, src);
+          pt.y = __shfl_sync(0xffffffffu, mine.y, src);
+          pt.z = __shfl_sync(0xffffffffu, mine.z, src);
+          pt.w = __shfl_sync(0xffffffffu, mine.w, src);
+        } else {
+          // heavy cell: stream the candidates through a bitonic network, keep the lowest max_points
+          unsigned long long k64 = ((unsigned long long)idx_mine << 32) | (unsigned)lane;
           k64 = bitonic_sort_warp(k64);
+          const int keep = max_pts;  // <= 24: lanes [keep, 32) take new candidates
+          for (int base = 32; base < n_all; base += 32 - keep) {
+            if (lane >= keep) {
+              const int j = base + lane - keep;
+              k64 = j < n_all ? (((unsigned long long)(unsigned)a.sorted_idx[st + j] << 32) | (unsigned)j) : ~0ull;
+            }
+            k64 = bitonic_sort_warp(k64);
+          }
+          pidx = (int)(unsigned)(k64 >> 32);
+          if (lane < n) pt = a.sorted_pts[st + (int)(unsigned)(k64 & 0xffffffffull)];
         }
-        pidx = (int)(unsigned)(k64 >> 32);
-        if (lane < n) pt = a.sorted_pts[st + (int)(unsigned)(k64 & 0xffffffffull)];
       }
       const bool act = lane < n;
-      // --- cluster centre (pillar_encoder.py:108-113) ---
+      // --- cluster centre: sum over the slots / num_points (pillar_encoder.py:108-113) ---
       float sx = act ? pt.x : 0.f, sy = act ? pt.y : 0.f, sz = act ? pt.z : 0.f;
+      if (n_all > 1) {
 #pragma unroll
-      for (int d = 16; d > 0; d >>= 1) {
-        sx += __shfl_xor_sync(0xffffffffu, sx, d);
-        sy += __shfl_xor_sync(0xffffffffu, sy, d);
-        sz += __shfl_xor_sync(0xffffffffu, sz, d);
+        for (int d = 16; d > 0; d >>= 1) {
+          sx += __shfl_xor_sync(0xffffffffu, sx, d);
+          sy += __shfl_xor_sync(0xffffffffu, sy, d);
+          sz += __shfl_xor_sync(0xffffffffu, sz, d);
+        }
+      } else {
+        sx = __shfl_sync(0xffffffffu, sx, 0);
+        sy = __shfl_sync(0xffffffffu, sy, 0);
+        sz = __shfl_sync(0xffffffffu, sz, 0);
       }
       const float fn = (float)n;
       const float mx = __fdiv_rn(sx, fn), my = __fdiv_rn(sy, fn), mz = __fdiv_rn(sz, fn);
-      // --- voxel-centre offsets, legacy aliasing + swapped index (pillar_encoder.py:129-139) ---
-      float f[7];
-      f[0] = __fsub_rn(pt.x, __fadd_rn(__fmul_rn((float)yi, p.vx), p.x_offset));
-      f[1] = __fsub_rn(pt.y, __fadd_rn(__fmul_rn((float)xi, p.vy), p.y_offset));
-      f[2] = __fsub_rn(pt.z, __fadd_rn(__fmul_rn(0.f, p.vz), p.z_offset));
-      f[3] = pt.w;
-      f[4] = __fsub_rn(pt.x, mx);
-      f[5] = __fsub_rn(pt.y, my);
-      f[6] = __fsub_rn(pt.z, mz);
+      // --- voxel-centre offsets, legacy aliasing + swapped index (pillar_encoder.py:129-139):
+      //     x uses coors[:,3] (= y index), y uses coors[:,2] (= x index), z index is 0
+      if (lane < n) {
+        float4 fa, fb;
+        fa.x = __fsub_rn(pt.x, __fadd_rn(__fmul_rn((float)yi, p.vx), p.x_offset));
+        fa.y = __fsub_rn(pt.y, __fadd_rn(__fmul_rn((float)xi, p.vy), p.y_offset));
+        fa.z = __fsub_rn(pt.z, __fadd_rn(__fmul_rn(0.f, p.vz), p.z_offset));
+        fa.w = pt.w;
+        fb.x = __fsub_rn(pt.x, mx);
+        fb.y = __fsub_rn(pt.y, my);
+        fb.z = __fsub_rn(pt.z, mz);
+        fb.w = 0.f;
+        *reinterpret_cast<float4*>(&s_feat[warp][lane][0]) = fa;
+        *reinterpret_cast<float4*>(&s_feat[warp][lane][4]) = fb;
+      }
+      __syncwarp();
+      // --- Linear + BN + ReLU + max over the slots, 2 channels per lane; features broadcast from smem ---
       float best[2] = {0.f, 0.f};
+#pragma unroll 2
       for (int k = 0; k < n; ++k) {
-        float g[7];
-#pragma unroll
-        for (int j = 0; j < 7; ++j) g[j] = __shfl_sync(0xffffffffu, f[j], k);
+        const float4 ga = *reinterpret_cast<const float4*>(&s_feat[warp][k][0]);
+        const float4 gb = *reinterpret_cast<const float4*>(&s_feat[warp][k][4]);
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          float x = W[q][0] * g[0];
-          x = fmaf(W[q][1], g[1], x);
-          x = fmaf(W[q][2], g[2], x);
-          x = fmaf(W[q][3], g[3], x);
-          x = fmaf(W[q][4], g[4], x);
-          x = fmaf(W[q][5], g[5], x);
-          x = fmaf(W[q][6], g[6], x);
-          x = fmaf(W[q][7], g[0], x);
-          x = fmaf(W[q][8], g[1], x);
-          x = fmaf(W[q][9], g[2], x);
+          float x = Wc[q][0] * ga.x;
+          x = fmaf(Wc[q][1], ga.y, x);
+          x = fmaf(Wc[q][2], ga.z, x);
+          x = fmaf(Wc[q][3], ga.w, x);
+          x = fmaf(Wc[q][4], gb.x, x);
+          x = fmaf(Wc[q][5], gb.y, x);
+          x = fmaf(Wc[q][6], gb.z, x);
           best[q] = fmaxf(best[q], fmaf(x, alpha[q], betap[q]));  // ReLU folded: best starts at 0
         }
       }
+      __syncwarp();  // s_feat is rewritten by the next pillar
       if (n < max_pts) {  // padded zero rows take part in the max: BN(0) = beta'
         best[0] = fmaxf(best[0], betap[0]);
         best[1] = fmaxf(best[1], betap[1]);
@@ -711,7 +800,7 @@ __global__ void __launch_bounds__(NH_THREADS, NH_CTAS_PER_SM) k_pillar_nhwc(cons
       float* dst = a.canvas + (((size_t)b * G0 + xi) * G1 + yi) * c_out;
       if (lane < c_out) dst[lane] = best[0];
       if (lane + 32 < c_out) dst[lane + 32] = best[1];
-      if (a.coors_out || a.num_points_out || a.voxels_out || a.pt2pillar_out) {
+      if (want_extra) {
         if (lane == 0 && a.coors_out) *reinterpret_cast<int4*>(a.coors_out + (size_t)row * 4) = make_int4(b, 0, xi, yi);
         if (lane == 0 && a.num_points_out) a.num_points_out[row] = n;
         if (a.pt2pillar_out && act) a.pt2pillar_out[a.pt_off[b] + pidx] = row;
@@ -725,6 +814,9 @@ __global__ void __launch_bounds__(NH_THREADS, NH_CTAS_PER_SM) k_pillar_nhwc(cons
       }
     }
   }
+  // the zero buffer must stay allocated until every bulk copy has read it
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  __syncthreads();
 }
 
 // BatchNorm1d in training mode: statistics over all (kept pillars x max_points) rows, padded zero
@@ -788,7 +880,10 @@ int make_plan(const float* const* points, const int32_t* n_points, int32_t batch
   if (p->max_points < 1 || p->max_points > 24) return SLIMB200_E_UNSUPPORTED;
   if (p->grid[0] < 1 || p->grid[1] < 1 || p->grid[2] != 1) return SLIMB200_E_UNSUPPORTED;
   if (p->canvas_layout != SLIMB200_CANVAS_NCHW && p->canvas_layout != SLIMB200_CANVAS_NHWC) return SLIMB200_E_INVALID;
-  if (p->canvas_layout == SLIMB200_CANVAS_NHWC && (p->c_out & 3)) return SLIMB200_E_UNSUPPORTED;
+  // channels-last cells are written as a power-of-two number of float4; grid indices are packed in 12 bits
+  if (p->canvas_layout == SLIMB200_CANVAS_NHWC &&
+      ((p->c_out & 3) || ((p->c_out >> 2) & ((p->c_out >> 2) - 1)) || p->grid[0] > 4096 || p->grid[1] > 4096 || batch > 128))
+    return SLIMB200_E_UNSUPPORTED;
   PillarArgs& a = plan->a;
   a = PillarArgs{};
   a.batch = batch;

@@ -142,7 +142,7 @@ class PointsPillarFeatureNetWrapper(nn.Module):
         p.bn_training = 1 if training else 0
         p.bn_eps = ve.pfn_layers[0].norm.eps
         p.bn_momentum = ve.pfn_layers[0].norm.momentum
-        nhwc = self.canvas_memory_format == "channels_last" and p.c_out % 4 == 0
+        nhwc = self.canvas_memory_format == "channels_last" and p.c_out in (4, 8, 16, 32, 64)
         p.canvas_layout = _lib.CANVAS_NHWC if nhwc else _lib.CANVAS_NCHW
         return p
 
