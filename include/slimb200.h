@@ -152,9 +152,11 @@ int slimb200_corr_build(const float* fmap1, const float* fmap2, int32_t fmap_lay
 
 /* coords: device (batch, 2, h, w) f32, channel 0 = x (column), 1 = y (row).
  * out:    device (batch, levels * (2r+1)^2, h, w) f32 contiguous, channel k = l*(2r+1)^2 + i*(2r+1) + j
- *         sampled at (x / 2^l + i - r, y / 2^l + j - r), bilinear, zeros outside, align_corners. */
+ *         sampled at (x / 2^l + i - r, y / 2^l + j - r), bilinear, zeros outside, align_corners.
+ *         out_layout = SLIMB200_CANVAS_NCHW, or SLIMB200_CANVAS_NHWC for the same tensor in channels-last
+ *         memory format (batch, h, w, channels) -- radius 3 only -- which the 1x1 conv consuming it prefers. */
 int slimb200_corr_lookup(const void* pyramid, int32_t pyramid_dtype, const slimb200_corr_layout* L,
-                         const float* coords, int32_t radius, float* out, void* stream);
+                         const float* coords, int32_t radius, float* out, int32_t out_layout, void* stream);
 
 const char* slimb200_strerror(int code);
 int slimb200_version(void);

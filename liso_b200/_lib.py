@@ -79,7 +79,7 @@ SYMBOLS = {
     ),
     "slimb200_corr_lookup": (
         C.c_int,
-        [C.c_void_p, C.c_int32, C.POINTER(CorrLayout), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p],
+        [C.c_void_p, C.c_int32, C.POINTER(CorrLayout), C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p],
     ),
     "slimb200_strerror": (C.c_char_p, [C.c_int]),
     "slimb200_version": (C.c_int, []),

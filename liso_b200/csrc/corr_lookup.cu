@@ -253,8 +253,8 @@ struct V3 {
   static constexpr int WPR = W1 * (int)sizeof(T) / 4;    // 32-bit words per aligned window row: 4 / 8
   __host__ __device__ static constexpr int win_words(int levels) { return levels * W1 * WPR * LK_PIX; }
   __host__ __device__ static constexpr int tab_words(int levels) { return levels * 2 * WIN * LK_PIX; }
-  __host__ __device__ static constexpr int smem_bytes(int levels) {
-    return (win_words(levels) + 3 * tab_words(levels) + 3 * levels * LK_PIX) * 4;
+  __host__ __device__ static constexpr int smem_bytes(int levels, bool nhwc) {
+    return (win_words(levels) + 3 * tab_words(levels) + 3 * levels * LK_PIX + (nhwc ? LK_PIX * (levels * WIN * WIN + 1) : 0)) * 4;
   }
 };
 
@@ -302,7 +302,7 @@ __device__ __forceinline__ void realign<__nv_bfloat16>(const uint32_t* ld, int s
 
 template <typename T, int I0, int I1>
 __device__ __forceinline__ void v3_columns(const uint32_t (*win)[V3<T>::WPR], const float* wy0, const float* wy1,
-                                           const float* s_w0x, const float* s_w1x, int lane, float* dst, size_t nf,
+                                           const float* s_w0x, const float* s_w1x, int lane, float* dst, size_t kstride,
                                            bool live) {
   constexpr int WIN = 7, W1 = 8;
   // I0..I1-1 are compile-time window columns
@@ -314,7 +314,7 @@ __device__ __forceinline__ void v3_columns(const uint32_t (*win)[V3<T>::WPR], co
     for (int r = 0; r < W1; ++r) h[r] = fmaf(win_elem<T, I + 1>(win[r]), wx1, win_elem<T, I>(win[r]) * wx0);
     if (live) {
 #pragma unroll
-      for (int j = 0; j < WIN; ++j) dst[((size_t)I * WIN + j) * nf] = fmaf(h[j + 1], wy1[j], h[j] * wy0[j]);
+      for (int j = 0; j < WIN; ++j) dst[((size_t)I * WIN + j) * kstride] = fmaf(h[j + 1], wy1[j], h[j] * wy0[j]);
     }
   };
   if constexpr (I0 == 0) {
@@ -329,7 +329,9 @@ __device__ __forceinline__ void v3_columns(const uint32_t (*win)[V3<T>::WPR], co
   }
 }
 
-template <typename T>
+// NHWC: the output is channels-last (batch, h, w, channels): the CTA's 32 pixels x 196 channels form one contiguous
+// block, staged through shared memory and written with fully coalesced rows.
+template <typename T, bool NHWC>
 __global__ void __launch_bounds__(LK_THREADS, 3) k_corr_lookup_r3(const T* __restrict__ pyr, const slimb200_corr_layout L,
                                                                   const float* __restrict__ coords, float* __restrict__ out) {
   using V = V3<T>;
@@ -343,6 +345,7 @@ __global__ void __launch_bounds__(LK_THREADS, 3) k_corr_lookup_r3(const T* __res
   int* s_xb = reinterpret_cast<int*>(s_w1 + V::tab_words(levels));
   int* s_yb = s_xb + levels * LK_PIX;
   int* s_ok = s_yb + levels * LK_PIX;
+  float* s_out = reinterpret_cast<float*>(s_ok + levels * LK_PIX);            // NHWC only: [pixel][n_ch + 1]
   __shared__ float s_xy[2][LK_PIX];
   __shared__ int s_lw[SLIMB200_MAX_LEVELS], s_lh[SLIMB200_MAX_LEVELS], s_lo[SLIMB200_MAX_LEVELS];
 
@@ -354,6 +357,7 @@ __global__ void __launch_bounds__(LK_THREADS, 3) k_corr_lookup_r3(const T* __res
   const int pix = i0 + lane;
   const bool live = pix < nf;
   const int n_ch = levels * WIN * WIN;
+  const int out_pad = n_ch + 1;
 
   if (threadIdx.x < 2 * LK_PIX) {
     const int ch = threadIdx.x / LK_PIX;
@@ -440,7 +444,8 @@ __global__ void __launch_bounds__(LK_THREADS, 3) k_corr_lookup_r3(const T* __res
   // ---- phase 3: warp (level, half) blends window columns {0..3} / {4..6} ----
   for (int u = warp; u < levels * 2; u += LK_WARPS) {
     const int l = u >> 1, half = u & 1;
-    float* dst = out + ((size_t)b * n_ch + (size_t)l * WIN * WIN) * nf + pix;
+    float* dst = NHWC ? s_out + lane * out_pad + l * WIN * WIN : out + ((size_t)b * n_ch + (size_t)l * WIN * WIN) * nf + pix;
+    const size_t kstride = NHWC ? 1 : (size_t)nf;
     if (s_ok[l * LK_PIX + lane]) {
       uint32_t win[W1][WPR];
 #pragma unroll
@@ -456,9 +461,9 @@ __global__ void __launch_bounds__(LK_THREADS, 3) k_corr_lookup_r3(const T* __res
       const float* w0x = s_w0 + ((l * 2 + 0) * WIN) * LK_PIX;
       const float* w1x = s_w1 + ((l * 2 + 0) * WIN) * LK_PIX;
       if (half == 0)
-        v3_columns<T, 0, 4>(win, wy0, wy1, w0x, w1x, lane, dst, (size_t)nf, live);
+        v3_columns<T, 0, 4>(win, wy0, wy1, w0x, w1x, lane, dst, kstride, live);
       else
-        v3_columns<T, 4, 7>(win, wy0, wy1, w0x, w1x, lane, dst, (size_t)nf, live);
+        v3_columns<T, 4, 7>(win, wy0, wy1, w0x, w1x, lane, dst, kstride, live);
     } else {
       const int W = s_lw[l], H = s_lh[l], off = s_lo[l];
       const int ib = half ? 4 : 0, ie = half ? WIN : 4;
@@ -466,27 +471,34 @@ __global__ void __launch_bounds__(LK_THREADS, 3) k_corr_lookup_r3(const T* __res
         const float ix = s_pos[((l * 2 + 0) * WIN + i) * LK_PIX + lane];
         for (int j = 0; j < WIN; ++j) {
           const float iy = s_pos[((l * 2 + 1) * WIN + j) * LK_PIX + lane];
-          if (live) dst[((size_t)i * WIN + j) * nf] = sample_slow<T>(pyr, n_panels, nf, b, pix, W, H, off, ix, iy);
+          if (live) dst[((size_t)i * WIN + j) * kstride] = sample_slow<T>(pyr, n_panels, nf, b, pix, W, H, off, ix, iy);
         }
       }
     }
   }
+  if (NHWC) {
+    __syncthreads();
+    const int n_pix = min(LK_PIX, nf - i0);
+    float* blk = out + ((size_t)b * nf + i0) * n_ch;  // 32 pixels x n_ch floats, contiguous
+    for (int pp = warp; pp < n_pix; pp += LK_WARPS)
+      for (int k = lane; k < n_ch; k += 32) blk[(size_t)pp * n_ch + k] = s_out[pp * out_pad + k];
+  }
 }
 
-template <typename T>
+template <typename T, bool NHWC>
 int launch_lookup_r3(const void* pyramid, const slimb200_corr_layout* L, const float* coords, float* out, cudaStream_t stream) {
   using V = V3<T>;
   const int nf = L->h * L->w;
-  const int smem = V::smem_bytes(L->levels);
+  const int smem = V::smem_bytes(L->levels, NHWC);
   static bool attr_set = false;
   if (!attr_set) {
-    SLIMB200_CUDA_TRY(cudaFuncSetAttribute(k_corr_lookup_r3<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           V::smem_bytes(SLIMB200_MAX_LEVELS)));
+    SLIMB200_CUDA_TRY(cudaFuncSetAttribute(k_corr_lookup_r3<T, NHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           V::smem_bytes(SLIMB200_MAX_LEVELS, NHWC)));
     attr_set = true;
   }
   dim3 grid((nf + LK_PIX - 1) / LK_PIX, L->batch);
   SLIMB200_LAUNCH(SLIMB200_K_CORR_LOOKUP, stream,
-                  (k_corr_lookup_r3<T><<<grid, LK_THREADS, smem, stream>>>(static_cast<const T*>(pyramid), *L, coords, out)));
+                  (k_corr_lookup_r3<T, NHWC><<<grid, LK_THREADS, smem, stream>>>(static_cast<const T*>(pyramid), *L, coords, out)));
   return SLIMB200_OK;
 }
 
@@ -508,13 +520,17 @@ int launch_lookup(const void* pyramid, const slimb200_corr_layout* L, const floa
 }
 
 template <typename T>
-int dispatch_radius(int radius, const void* pyramid, const slimb200_corr_layout* L, const float* coords, float* out,
-                    cudaStream_t stream) {
+int dispatch_radius(int radius, int out_layout, const void* pyramid, const slimb200_corr_layout* L, const float* coords,
+                    float* out, cudaStream_t stream) {
+  if (out_layout == SLIMB200_CANVAS_NHWC) {
+    if (radius != 3) return SLIMB200_E_UNSUPPORTED;  // channels-last output exists for the SLIM configuration only
+    return launch_lookup_r3<T, true>(pyramid, L, coords, out, stream);
+  }
   switch (radius) {
     case 0: return launch_lookup<T, 0>(pyramid, L, coords, out, stream);
     case 1: return launch_lookup<T, 1>(pyramid, L, coords, out, stream);
     case 2: return launch_lookup<T, 2>(pyramid, L, coords, out, stream);
-    case 3: return launch_lookup_r3<T>(pyramid, L, coords, out, stream);
+    case 3: return launch_lookup_r3<T, false>(pyramid, L, coords, out, stream);
     case 4: return launch_lookup<T, 4>(pyramid, L, coords, out, stream);
     default: return SLIMB200_E_UNSUPPORTED;
   }
@@ -523,13 +539,14 @@ int dispatch_radius(int radius, const void* pyramid, const slimb200_corr_layout*
 }  // namespace
 
 extern "C" int slimb200_corr_lookup(const void* pyramid, int32_t pyramid_dtype, const slimb200_corr_layout* L,
-                                    const float* coords, int32_t radius, float* out, void* stream_) {
+                                    const float* coords, int32_t radius, float* out, int32_t out_layout, void* stream_) {
+  if (out_layout != SLIMB200_CANVAS_NCHW && out_layout != SLIMB200_CANVAS_NHWC) return SLIMB200_E_INVALID;
   if (!pyramid || !L || !coords || !out) return SLIMB200_E_INVALID;
   if (radius < 0 || radius > 4 || L->levels < 1 || L->levels > SLIMB200_MAX_LEVELS) return SLIMB200_E_UNSUPPORTED;
   if (L->n_panels * PW != L->pitch || L->n_panels < 1) return SLIMB200_E_INVALID;
   if (reinterpret_cast<uintptr_t>(pyramid) & 15) return SLIMB200_E_ALIGNMENT;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (pyramid_dtype == SLIMB200_DTYPE_BF16) return dispatch_radius<__nv_bfloat16>(radius, pyramid, L, coords, out, stream);
-  if (pyramid_dtype == SLIMB200_DTYPE_F32) return dispatch_radius<float>(radius, pyramid, L, coords, out, stream);
+  if (pyramid_dtype == SLIMB200_DTYPE_BF16) return dispatch_radius<__nv_bfloat16>(radius, out_layout, pyramid, L, coords, out, stream);
+  if (pyramid_dtype == SLIMB200_DTYPE_F32) return dispatch_radius<float>(radius, out_layout, pyramid, L, coords, out, stream);
   return SLIMB200_E_UNSUPPORTED;
 }

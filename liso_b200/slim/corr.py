@@ -62,8 +62,10 @@ class _LazyLevels:
         return (self[i] for i in range(len(self)))
 
 
-def lookup(pyramid: torch.Tensor, L: _lib.CorrLayout, coords: torch.Tensor, radius: int) -> torch.Tensor:
-    """``slimb200_corr_lookup`` on a packed pyramid (bf16 or fp32)."""
+def lookup(pyramid: torch.Tensor, L: _lib.CorrLayout, coords: torch.Tensor, radius: int,
+           channels_last: bool = False) -> torch.Tensor:
+    """``slimb200_corr_lookup`` on a packed pyramid (bf16 or fp32).  ``channels_last`` (radius 3 only) returns the
+    same ``(B, L*(2r+1)^2, h, w)`` tensor in channels-last memory format."""
     _lib.require_cuda(pyramid, coords)
     if coords.shape != (L.batch, 2, L.h, L.w):
         raise ValueError("coords must be (B,2,h,w) = %s, got %s" % ((L.batch, 2, L.h, L.w), tuple(coords.shape)))
@@ -71,12 +73,15 @@ def lookup(pyramid: torch.Tensor, L: _lib.CorrLayout, coords: torch.Tensor, radi
     if coords.dtype != torch.float32 or not coords.is_contiguous():
         coords = coords.float().contiguous()
     n_ch = L.levels * (2 * radius + 1) ** 2
-    out = torch.empty((L.batch, n_ch, L.h, L.w), dtype=torch.float32, device=coords.device)
+    channels_last = bool(channels_last) and radius == 3
+    out = torch.empty((L.batch, n_ch, L.h, L.w), dtype=torch.float32, device=coords.device,
+                      memory_format=torch.channels_last if channels_last else torch.contiguous_format)
     dt = _lib.DTYPE_BF16 if pyramid.dtype == torch.bfloat16 else _lib.DTYPE_F32
     if pyramid.dtype not in (torch.bfloat16, torch.float32):
         raise ValueError("pyramid dtype must be bfloat16 or float32")
     _lib.check(_lib.load().slimb200_corr_lookup(pyramid.data_ptr(), dt, C.byref(L), coords.data_ptr(), radius,
-                                                out.data_ptr(), _lib.current_stream_ptr()))
+                                                out.data_ptr(), _lib.CANVAS_NHWC if channels_last else _lib.CANVAS_NCHW,
+                                                _lib.current_stream_ptr()))
     return out
 
 
@@ -108,6 +113,7 @@ class CorrBlock:
         if not nhwc:
             f1, f2 = f1.contiguous(), f2.contiguous()
         layout_flag = _lib.CANVAS_NHWC if nhwc else _lib.CANVAS_NCHW
+        self.channels_last = nhwc  # answer lookups in the memory format the feature maps came in
         L = self.layout
         self.pyramid = torch.empty((B * L.n_panels * h * w, _lib.PANEL_COLS), dtype=torch.bfloat16, device=f1.device)
         ws = torch.empty(lib.slimb200_corr_workspace_bytes(C.byref(L)), dtype=torch.uint8, device=f1.device)
@@ -117,7 +123,7 @@ class CorrBlock:
         self.corr_pyramid = _LazyLevels(self.pyramid, L)
 
     def __call__(self, coords: torch.Tensor) -> torch.Tensor:
-        return lookup(self.pyramid, self.layout, coords, self.radius)
+        return lookup(self.pyramid, self.layout, coords, self.radius, self.channels_last)
 
     @staticmethod
     def corr(fmap1: torch.Tensor, fmap2: torch.Tensor) -> torch.Tensor:

@@ -18,6 +18,34 @@ from ..networks.pcl_to_feature_grid import PointsPillarFeatureNetWrapper
 from .corr import CorrBlock, initialize_flow, uplogits_n, upflow_n
 
 
+# Stock-op plumbing (no custom kernels): when True, Conv2d -> ReLU pairs go through cuDNN's fused
+# conv + bias + activation (``torch.cudnn_convolution_relu``) instead of conv, bias-add and clamp as three
+# launches, and affine InstanceNorm on channels-last tensors is computed with var_mean / addcmul so that the
+# tensor is not copied to NCHW and back for cuDNN's batch-norm kernel.  Same math, fp32 / TF32 as configured.
+FAST_STOCK_OPS = True
+
+
+def conv_relu(conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
+    if FAST_STOCK_OPS and x.is_cuda and x.dtype == torch.float32 and conv.padding_mode == "zeros" and not torch.is_grad_enabled():
+        return torch.cudnn_convolution_relu(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups)
+    return F.relu(conv(x))
+
+
+def norm_relu(norm: nn.Module, x: torch.Tensor) -> torch.Tensor:
+    """relu(norm(x)) for the norms `_make_norm` builds."""
+    if (FAST_STOCK_OPS and isinstance(norm, nn.InstanceNorm2d) and norm.affine and not norm.track_running_stats
+            and x.is_cuda and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last)):
+        var, mean = torch.var_mean(x, dim=(2, 3), unbiased=False, keepdim=True)
+        scale = norm.weight.view(1, -1, 1, 1) * torch.rsqrt(var + norm.eps)
+        shift = norm.bias.view(1, -1, 1, 1) - mean * scale
+        return torch.addcmul(shift, x, scale).relu_()
+    return F.relu(norm(x))
+
+
+def _is_identity(norm: nn.Module) -> bool:
+    return isinstance(norm, nn.Sequential) and len(norm) == 0
+
+
 def _make_norm(kind: str, channels: int) -> nn.Module:
     if kind == "instance_affine":
         return nn.InstanceNorm2d(channels, eps=1e-3, affine=True)
@@ -50,8 +78,11 @@ class ResidualBlock(nn.Module):
             self.downsample = nn.Sequential(nn.Conv2d(in_filters, out_filters, kernel_size=1, stride=stride), self.norm3)
 
     def forward(self, x):
-        y = self.relu(self.norm1(self.conv1(x)))
-        y = self.relu(self.norm2(self.conv2(y)))
+        if _is_identity(self.norm1):
+            y = conv_relu(self.conv2, conv_relu(self.conv1, x))
+        else:
+            y = norm_relu(self.norm1, self.conv1(x))
+            y = norm_relu(self.norm2, self.conv2(y))
         if self.downsample is not None:
             x = self.downsample(x)
         return self.relu(x + y)
@@ -79,7 +110,7 @@ class SmallEncoder(nn.Module):
         )
 
     def forward(self, x):
-        x = self.relu1(self.norm1(self.conv1(x)))
+        x = conv_relu(self.conv1, x) if _is_identity(self.norm1) else norm_relu(self.norm1, self.conv1(x))
         x = self.layer3(self.layer2(self.layer1(x)))
         x = self.conv2(x)
         if self.training and self.dropout is not None:
@@ -95,7 +126,7 @@ class FlowOrClassificationHead(nn.Module):
         self.relu = nn.ReLU(inplace=True)
 
     def forward(self, x):
-        return self.conv2(self.relu(self.conv1(x)))
+        return self.conv2(conv_relu(self.conv1, x))
 
 
 class ConvGRU(nn.Module):
@@ -128,10 +159,10 @@ class SmallMotionEncoder(nn.Module):
         self.conv = nn.Conv2d(160, 80, 3, padding=1)
 
     def forward(self, flow, corr, logits):
-        c = F.relu(self.conv_stat_corr1(corr))
-        f = F.relu(self.conv_flow2(F.relu(self.conv_flow1(flow))))
-        lg = F.relu(self.conv_class2(F.relu(self.conv_class1(logits))))
-        out = F.relu(self.conv(torch.cat([c, f, lg], dim=1)))
+        c = conv_relu(self.conv_stat_corr1, corr)
+        f = conv_relu(self.conv_flow2, conv_relu(self.conv_flow1, flow))
+        lg = conv_relu(self.conv_class2, conv_relu(self.conv_class1, logits))
+        out = conv_relu(self.conv, torch.cat([c, f, lg], dim=1))
         return torch.cat([out, lg, f], dim=1)
 
 
@@ -167,6 +198,9 @@ class RAFT(nn.Module):
         self.head_decoder_fw = head_decoder_fw
         self.head_decoder_bw = head_decoder_bw
         self.iters = m.num_iters
+        # "all": one (B,H,W,8) output per GRU iteration like the reference (raft_mod.py:216-257); "last": only the
+        # final one is up-sampled / assembled (the flow export reads nothing else, experiment.py:391-399)
+        self.output_iterations = "all"
         rows = float(cfg.data.bev_range_m[0]) / cfg.data.img_grid_size[0] * m.u_net.final_scale
         cols = float(cfg.data.bev_range_m[1]) / cfg.data.img_grid_size[1] * m.u_net.final_scale
         assert rows == cols, "anisotropic BEV resolution is not supported (raft_mod.py:42-45)"
@@ -203,13 +237,15 @@ class RAFT(nn.Module):
         res = torch.tensor([self.bev_rows_res_meters_per_fs_pixel, self.bev_cols_res_meters_per_fs_pixel],
                            device=inp.device, dtype=inp.dtype)[None, :, None, None]
         outs = []
-        for _ in range(m.num_iters):
+        for it in range(m.num_iters):
             coords1 = coords1.detach()
             logits = logits.detach()
             corr = correlation(coords1)
             net, dflow, dlogits, _ = self.update_block(net, inp, corr, coords1 - coords0, logits, None)
             coords1 = coords1 + dflow
             logits = logits + dlogits
+            if self.output_iterations == "last" and it != m.num_iters - 1:
+                continue
             # RAFT (x, y) pixel flow -> (row, col) metres (raft_mod.py:262-266)
             flow_m = torch.flip(upflow_n(coords1 - coords0, n=ds), dims=[1]) * res
             outs.append(concat2network_output(uplogits_n(logits, n=ds), flow_m, flow_m))

@@ -179,6 +179,7 @@ class SLIM(nn.Module):
         self.raft_network = RAFT(cfg, self.head_decoder_fw, self.head_decoder_bw)
         assert decode_iterations in ("all", "last")
         self.decode_iterations = decode_iterations
+        self.raft_network.output_iterations = decode_iterations
         self.static_aggregation = static_aggregation
 
     def forward(self, sample_data_t0, sample_data_t1, summaries=None):
@@ -188,7 +189,7 @@ class SLIM(nn.Module):
             get_network_input_pcls(self.cfg, sample_data_t1, "ta", to_device=dev),
         )
         filled = [torch.squeeze(aux[k]["bev_net_input_dbg"] > 0.5, dim=1) for k in ("t0", "t1")]
-        its = range(len(outs_fw)) if self.decode_iterations == "all" else [len(outs_fw) - 1]
+        its = range(len(outs_fw))  # one entry per iteration, or only the last one in "last" mode
         thr = self.moving_dynamicness_threshold.value()
         preds_fw, preds_bw = [], []
         per_dir = ((outs_fw, sample_data_t0, filled[0], self.head_decoder_fw, preds_fw),

@@ -90,13 +90,19 @@ def test_lookup_fp32_pyramid_matches_oracle(cuda, B, h, w):
         assert float((got - ref).abs().max()) <= 1e-5 * scale, (spread, float((got - ref).abs().max()), scale)
 
 
+@pytest.mark.parametrize("fmt", ["contiguous", "channels_last"])
 @pytest.mark.parametrize("B,h,w", [(2, 32, 32), (1, 80, 80), (1, 115, 115)])
-def test_lookup_on_bf16_pyramid(cuda, B, h, w):
-    """End of stage 2: kernel lookup on the kernel's own bf16 pyramid == oracle lookup on the same values."""
+def test_lookup_on_bf16_pyramid(cuda, B, h, w, fmt):
+    """End of stage 2: kernel lookup on the kernel's own bf16 pyramid == oracle lookup on the same values.
+    With channels-last feature maps the lookup is answered channels-last too (same logical tensor)."""
     f1, f2, d1, d2 = _fmaps(B, h, w, 4, cuda)
+    if fmt == "channels_last":
+        d1, d2 = d1.contiguous(memory_format=torch.channels_last), d2.contiguous(memory_format=torch.channels_last)
     blk = C.CorrBlock(d1, d2, num_levels=4, radius=3)
     coords = _coords(B, h, w, 5, 1.5)
-    got = blk(coords.to(cuda)).cpu()
+    got_dev = blk(coords.to(cuda))
+    assert got_dev.is_contiguous(memory_format=torch.channels_last if fmt == "channels_last" else torch.contiguous_format)
+    got = got_dev.cpu()
     same_values = [lv.float().cpu().contiguous() for lv in blk.corr_pyramid]
     ref = O.corr_lookup(same_values, coords, 3)
     scale = float(same_values[0].abs().max())
