@@ -35,9 +35,16 @@ def norm_relu(norm: nn.Module, x: torch.Tensor) -> torch.Tensor:
     """relu(norm(x)) for the norms `_make_norm` builds."""
     if (FAST_STOCK_OPS and isinstance(norm, nn.InstanceNorm2d) and norm.affine and not norm.track_running_stats
             and x.is_cuda and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last)):
-        var, mean = torch.var_mean(x, dim=(2, 3), unbiased=False, keepdim=True)
-        scale = norm.weight.view(1, -1, 1, 1) * torch.rsqrt(var + norm.eps)
-        shift = norm.bias.view(1, -1, 1, 1) - mean * scale
+        # statistics over (H, W) of an NHWC tensor: reduce over H with (W*C) contiguous columns (streams at HBM
+        # speed), then merge the W partial (mean, var) pairs exactly (equal counts, Chan et al.)
+        B, C, H, W = x.shape
+        var_w, mean_w = torch.var_mean(x.permute(0, 2, 3, 1).reshape(B, H, W * C), dim=1, unbiased=False)
+        mean_w, var_w = mean_w.view(B, W, C), var_w.view(B, W, C)
+        mean = mean_w.mean(dim=1)
+        var = var_w.mean(dim=1) + (mean_w - mean[:, None, :]).square().mean(dim=1)
+        scale = norm.weight[None, :] * torch.rsqrt(var + norm.eps)
+        shift = (norm.bias[None, :] - mean * scale).view(B, C, 1, 1)
+        scale = scale.view(B, C, 1, 1)
         return torch.addcmul(shift, x, scale).relu_()
     return F.relu(norm(x))
 
