@@ -138,7 +138,8 @@ def main():
     ap.add_argument("--workload", default="K", choices=["K", "N", "A", "T"])
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--conv-precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--conv-precision", default="tf32", choices=["tf32", "fp32", "bf16"],
+                    help="precision of the stock cuDNN convolutions: tf32 (default), fp32, or bf16 autocast")
     ap.add_argument("--memory-format", default="channels_last", choices=["channels_last", "contiguous"],
                     help="memory format of the canvas our encoder emits and of the stock convs that consume it")
     ap.add_argument("--profile-one-step", action="store_true",
@@ -197,8 +198,12 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
-    torch.backends.cudnn.allow_tf32 = args.conv_precision == "tf32"
-    torch.backends.cuda.matmul.allow_tf32 = args.conv_precision == "tf32"
+    torch.backends.cudnn.allow_tf32 = args.conv_precision != "fp32"
+    torch.backends.cuda.matmul.allow_tf32 = args.conv_precision != "fp32"
+    import contextlib
+
+    def amp():
+        return torch.autocast("cuda", dtype=torch.bfloat16) if args.conv_precision == "bf16" else contextlib.nullcontext()
     torch.backends.cudnn.benchmark = True
 
     cfg.network["b200_canvas_memory_format"] = args.memory_format
@@ -223,12 +228,12 @@ def main():
     d2h = sum(t.numel() * 4 for t in pinned_out)
 
     def step_resident():
-        with torch.no_grad():
+        with torch.no_grad(), amp():
             pf, pb = model(d0, d1, None)
         return export_tensors(pf, pb)
 
     def step_e2e():
-        with torch.no_grad():
+        with torch.no_grad(), amp():
             pf, pb = model(h0, h1, None)
         for dst, src in zip(pinned_out, export_tensors(pf, pb)):
             dst.copy_(src, non_blocking=True)
@@ -348,7 +353,7 @@ def main():
         v = len(times) / sum(times)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                                 "sample": "2 timed runs (1 warm-up) of 1 pair (B=1) of the same workload, fp32, all host threads"}
-        with torch.no_grad():
+        with torch.no_grad(), amp():
             pf, pb = model(d0, d1, None)
         valid = s0["pcl_ta"]["pcl_is_valid"][0]
         epe = (pf[-1].static_flow[0].cpu() - of[-1]["pointwise_static_flow"][0]).norm(dim=-1)[valid]

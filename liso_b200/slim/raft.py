@@ -25,9 +25,31 @@ from .corr import CorrBlock, initialize_flow, uplogits_n, upflow_n
 FAST_STOCK_OPS = True
 
 
+_PARAM_CAST_CACHE = {}
+
+
+def _autocast_param(t, dtype):
+    """Low-precision copy of a parameter, cached like autocast caches its weight casts (inference only)."""
+    if t is None:
+        return None
+    key = (t.data_ptr(), t._version, dtype, tuple(t.stride()))
+    hit = _PARAM_CAST_CACHE.get(key)
+    if hit is None:
+        hit = t.detach().to(dtype)
+        if t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last):
+            hit = hit.contiguous(memory_format=torch.channels_last)
+        _PARAM_CAST_CACHE[key] = hit
+    return hit
+
+
 def conv_relu(conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
-    if FAST_STOCK_OPS and x.is_cuda and x.dtype == torch.float32 and conv.padding_mode == "zeros" and not torch.is_grad_enabled():
-        return torch.cudnn_convolution_relu(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups)
+    if FAST_STOCK_OPS and x.is_cuda and conv.padding_mode == "zeros" and not torch.is_grad_enabled():
+        w, b = conv.weight, conv.bias
+        if torch.is_autocast_enabled():  # the fused op is not on autocast's cast list
+            dt = torch.get_autocast_dtype("cuda")
+            x, w, b = x.to(dt), _autocast_param(w, dt), _autocast_param(b, dt)
+        if x.dtype == w.dtype:
+            return torch.cudnn_convolution_relu(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
     return F.relu(conv(x))
 
 
