@@ -158,6 +158,45 @@ int slimb200_corr_build(const float* fmap1, const float* fmap2, int32_t fmap_lay
 int slimb200_corr_lookup(const void* pyramid, int32_t pyramid_dtype, const slimb200_corr_layout* L,
                          const float* coords, int32_t radius, float* out, int32_t out_layout, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * output decoder.  Replaces HeadDecoder.forward (liso/slim/model/head_decoder.py:410-496,
+ * 517-717) for the released output_modification, batched_grid_data_to_pointwise_data and
+ * compute_batched_bev_static_aggregated_flow (slim_loss/static_aggregation.py:8-110), weighted_pc_alignment
+ * (slim_loss/weighted_pc_alignment.py:10-80, no epsilon) and symmetric_orthogonalization
+ * (torch_symm_ortho/__init__.py:68-69: U @ Vh, no determinant fix).  No host synchronisation.
+ *
+ * bev (batch, H, W, 20) f32, one packed row per cell (the reference's tensors are channel slices of it):
+ *    0      disappearing_logit (-100)            1:4    class_logits = static | dynamic | ground logit (masked)
+ *    4:7    class_probs = staticness | dynamicness | groundness
+ *    7:10   static flow (x, y, 0), masked         10:13  dynamic flow (x, y, 0), masked
+ *    13:16  aggregated flow                        16:18  static_aggr_flow      18:20  masked_static_aggr_flow
+ * bev_classes (batch, H, W, 3) u8: is_dynamic | is_static | is_ground
+ * points (batch, n_points, 14) f32: 0:3 static flow, 3:6 dynamic flow, 6 dynamicness, 7 staticness,
+ *    8:11 aggregated flow, 11:14 static_aggr_flow (x, y, 0); all zero for invalid points
+ * trafo (batch, 4, 4) f64 row-major, not_enough (batch) u8: only with static_aggregation
+ * ---------------------------------------------------------------------------------------- */
+#define SLIMB200_DECODE_BEV_CHANNELS 20
+#define SLIMB200_DECODE_POINT_CHANNELS 14
+typedef struct {
+  int32_t batch, H, W;
+  int32_t n_points;            /* padded points per sample */
+  int32_t pc_stride;           /* floats per point in `pc` (>= 3) */
+  int32_t final_scale;         /* pillar coordinate divisor (u_net.final_scale, 1) */
+  int32_t static_aggregation;  /* 0: skip the weighted Kabsch part (channels 16:20 / 11:14 are zero) */
+  int32_t reserved;
+  double ext_min_x, ext_min_y, ext_max_x, ext_max_y; /* bev_extent (head_decoder.py:498-514) */
+} slimb200_decode_params;
+
+size_t slimb200_head_decode_workspace_bytes(const slimb200_decode_params* p);
+
+/* net_out (batch, H, W, 8) f32 contiguous: logits 0:4 (1 = static, 2 = dynamic), static flow 4:6, dynamic flow 6:8
+ * filled (batch, H, W) u8; pc (batch, n_points, pc_stride) f32; coors (batch, n_points, 2) i32; valid (batch, n_points) u8
+ * dyn_threshold: DEVICE pointer to one float (MovingAverageThreshold.value(), no host read) */
+int slimb200_head_decode(const float* net_out, const uint8_t* filled, const float* pc, const int32_t* coors,
+                         const uint8_t* valid, const float* dyn_threshold, const slimb200_decode_params* p,
+                         float* bev, uint8_t* bev_classes, float* points, double* trafo, uint8_t* not_enough,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
 const char* slimb200_strerror(int code);
 int slimb200_version(void);
 
@@ -180,6 +219,11 @@ enum {
   SLIMB200_K_CORR_GEMM,
   SLIMB200_K_CORR_LOOKUP,
   SLIMB200_K_PILLAR_COORS,
+  SLIMB200_K_DECODE_MIN,
+  SLIMB200_K_DECODE_BEV,
+  SLIMB200_K_DECODE_POINTS,
+  SLIMB200_K_KABSCH,
+  SLIMB200_K_DECODE_AGGR,
   SLIMB200_N_KERNELS
 };
 int slimb200_profile_begin(void);

@@ -56,6 +56,16 @@ class CorrLayout(C.Structure):
     ]
 
 
+class DecodeParams(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("n_points", C.c_int32), ("pc_stride", C.c_int32),
+        ("final_scale", C.c_int32), ("static_aggregation", C.c_int32), ("reserved", C.c_int32),
+        ("ext_min_x", C.c_double), ("ext_min_y", C.c_double), ("ext_max_x", C.c_double), ("ext_max_y", C.c_double),
+    ]
+
+
+DECODE_BEV_CHANNELS, DECODE_POINT_CHANNELS = 20, 14
+
 # every symbol include/slimb200.h declares: (restype, argtypes)
 SYMBOLS = {
     "slimb200_pillar_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int64, C.POINTER(PillarParams)]),
@@ -81,6 +91,11 @@ SYMBOLS = {
         C.c_int,
         [C.c_void_p, C.c_int32, C.POINTER(CorrLayout), C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p],
     ),
+    "slimb200_head_decode_workspace_bytes": (C.c_size_t, [C.POINTER(DecodeParams)]),
+    "slimb200_head_decode": (
+        C.c_int,
+        [C.c_void_p] * 6 + [C.POINTER(DecodeParams)] + [C.c_void_p] * 5 + [C.c_void_p, C.c_size_t, C.c_void_p],
+    ),
     "slimb200_strerror": (C.c_char_p, [C.c_int]),
     "slimb200_version": (C.c_int, []),
     "slimb200_profile_begin": (C.c_int, []),
@@ -88,7 +103,7 @@ SYMBOLS = {
     "slimb200_launch_count": (C.c_int64, [C.c_int32]),
     "slimb200_kernel_name": (C.c_char_p, [C.c_int32]),
 }
-N_KERNELS = 13
+N_KERNELS = 18
 K_TILE_ENCODE, K_PILLAR_NHWC, K_FEAT_TRANSPOSE, K_FEAT_PACK, K_CORR_GEMM, K_CORR_LOOKUP = 6, 7, 8, 9, 10, 11
 CANVAS_NCHW, CANVAS_NHWC = 0, 1
 

@@ -1,0 +1,372 @@
+// SURVEY 8(f).1 -- the SLIM output decoder on B200: BEV class/flow maps, BEV -> point gather and the weighted
+// Kabsch "static aggregation", fused into five launches with no host synchronisation.
+//
+// Replaces, for the released output_modification (liso_config.yml:303-310):
+//   HeadDecoder.forward                               liso/slim/model/head_decoder.py:410-496, 517-717
+//   batched_grid_data_to_pointwise_data               liso/slim/slim_loss/static_aggregation.py:8-31
+//   compute_batched_bev_static_aggregated_flow        static_aggregation.py:34-110
+//   weighted_pc_alignment (no epsilon)                slim_loss/weighted_pc_alignment.py:10-80
+//   symmetric_orthogonalization (U @ Vh, no det fix)  liso/torch_symm_ortho/__init__.py:68-69
+// The reference runs ~60 element-wise launches per call plus, per sample, boolean-mask indexing (host sync), a
+// fp64 3x3 SVD and host-side asserts; it is called 12 times per frame pair.
+//
+//   k_decode_min      global min of the live static/dynamic logits (ground logit "off" = min - 100)
+//   k_decode_bev      one thread per BEV cell: masks, 3-way softmax, class decisions, masked flows, aggregated flow;
+//                     one packed (B,H,W,20) row per cell written with 128-bit stores
+//   k_decode_points   one thread per point: gather, weights, fp64 Kabsch moments (block partials, fixed order)
+//   k_kabsch_finalize one CTA per sample: sum the partials, 3x3 one-sided Jacobi SVD in fp64, R = U V^T, T (4x4)
+//   k_decode_aggr     (T - I) * cell centre for every cell and every point
+#include "common.cuh"
+
+namespace {
+
+constexpr int BEV_C = SLIMB200_DECODE_BEV_CHANNELS;    // 20
+constexpr int PT_C = SLIMB200_DECODE_POINT_CHANNELS;   // 14
+constexpr int N_MOM = 33;  // 1 + 3 + 3 + 9 weighted, the same 16 unweighted (for the +1e-7 case), count(w > 0)
+constexpr int PT_THREADS = 256;
+
+__device__ __forceinline__ unsigned f2key(float f) {
+  const unsigned b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__global__ void __launch_bounds__(256) k_decode_min(const float* __restrict__ net_out, size_t n_cells, unsigned* __restrict__ out_key) {
+  unsigned best = 0xffffffffu;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cells; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 lo = __ldg(reinterpret_cast<const float4*>(net_out + i * 8));  // logits 0..3
+    best = min(best, min(f2key(lo.y), f2key(lo.z)));
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, d));
+  if ((threadIdx.x & 31) == 0) atomicMin(out_key, best);
+}
+
+struct DecodeArgs {
+  const float* net_out;
+  const uint8_t* filled;
+  const float* pc;
+  const int32_t* coors;
+  const uint8_t* valid;
+  const float* thr;
+  slimb200_decode_params p;
+  float* bev;
+  uint8_t* bev_cls;
+  float* pts;
+  double* trafo;
+  uint8_t* not_enough;
+  unsigned* min_key;
+  double* partials;  // [batch][blocks_per_sample][N_MOM]
+  int blocks_per_sample;
+};
+
+__global__ void __launch_bounds__(256) k_decode_bev(const DecodeArgs a) {
+  const size_t n_cells = (size_t)a.p.batch * a.p.H * a.p.W;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cells) return;
+  const float4 lg = __ldg(reinterpret_cast<const float4*>(a.net_out + i * 8));
+  const float4 fl = __ldg(reinterpret_cast<const float4*>(a.net_out + i * 8 + 4));
+  const bool filled = a.filled[i] != 0;
+  const float ground_off = key2f(*a.min_key) - 100.0f;
+  // mask non-filled pillars (head_decoder.py:568-609)
+  const float l_st = filled ? lg.y : 0.f;
+  const float l_dy = filled ? lg.z : -100.f;
+  const float l_gr = filled ? ground_off : -100.f;
+  const float sfx = filled ? fl.x : 0.f, sfy = filled ? fl.y : 0.f;
+  const float dfx = filled ? fl.z : 0.f, dfy = filled ? fl.w : 0.f;
+  // softmax over (static, dynamic, ground)
+  const float m = fmaxf(l_st, fmaxf(l_dy, l_gr));
+  const float e0 = expf(l_st - m), e1 = expf(l_dy - m), e2 = expf(l_gr - m);
+  const float s = e0 + e1 + e2;
+  const float p_st = e0 / s, p_dy = e1 / s, p_gr = e2 / s;
+  const float thr = __ldg(a.thr);
+  const bool is_dyn = p_dy >= thr;
+  const bool is_sta = (p_st >= p_gr) && !is_dyn;
+  const bool is_gr = !(is_sta || is_dyn);
+  const float g = 1.0f - p_gr;
+  const float agx = is_sta ? sfx : dfx * g, agy = is_sta ? sfy : dfy * g, agz = is_sta ? 0.f : 0.f * g;
+  float4* o = reinterpret_cast<float4*>(a.bev + i * BEV_C);
+  o[0] = make_float4(-100.f, l_st, l_dy, l_gr);      // disappearing | class_logits (static, dynamic, ground)
+  o[1] = make_float4(p_st, p_dy, p_gr, sfx);         // class_probs | static3.x
+  o[2] = make_float4(sfy, 0.f, dfx, dfy);            // static3.yz | dynamic3.xy
+  o[3] = make_float4(0.f, agx, agy, agz);            // dynamic3.z | aggregated3
+  if (!a.p.static_aggregation) o[4] = make_float4(0.f, 0.f, 0.f, 0.f);
+  uint8_t* c = a.bev_cls + i * 3;
+  c[0] = is_dyn;
+  c[1] = is_sta;
+  c[2] = is_gr;
+}
+
+__global__ void __launch_bounds__(PT_THREADS) k_decode_points(const DecodeArgs a) {
+  __shared__ double s_part[PT_THREADS / 32][N_MOM];
+  const int b = blockIdx.y;
+  const int n = a.p.n_points;
+  const int j = blockIdx.x * PT_THREADS + threadIdx.x;
+  double mom[N_MOM];
+#pragma unroll
+  for (int k = 0; k < N_MOM; ++k) mom[k] = 0.0;
+  if (j < n) {
+    const size_t pi = (size_t)b * n + j;
+    const bool valid = a.valid[pi] != 0;
+    float out[11];
+#pragma unroll
+    for (int k = 0; k < 11; ++k) out[k] = 0.f;
+    if (valid) {
+      const int r = a.coors[pi * 2] / a.p.final_scale, c = a.coors[pi * 2 + 1] / a.p.final_scale;
+      const size_t cell = ((size_t)b * a.p.H + r) * a.p.W + c;
+      const float* row = a.bev + cell * BEV_C;
+      const float p_st = __ldg(row + 4), p_dy = __ldg(row + 5);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        out[k] = __ldg(row + 7 + k);        // static3
+        out[3 + k] = __ldg(row + 10 + k);   // dynamic3
+        out[8 + k] = __ldg(row + 13 + k);   // aggregated3
+      }
+      out[6] = p_dy;
+      out[7] = p_st;
+      if (a.p.static_aggregation) {
+        const float w = a.filled[cell] ? p_st : 0.f;  // staticness * filled (head_decoder.py -> static_aggregation.py:66-71)
+        const float* q = a.pc + pi * a.p.pc_stride;
+        const float x0 = q[0], y0 = q[1], z0 = q[2];
+        const float x1 = x0 + out[0], y1 = y0 + out[1], z1 = z0 + out[2];  // fp32 add like the reference
+        const double p0[3] = {x0, y0, z0}, p1[3] = {x1, y1, z1};
+        const double wd = (double)w;
+        mom[0] = wd;
+        mom[16] = 1.0;
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          mom[1 + u] = wd * p0[u];
+          mom[4 + u] = wd * p1[u];
+          mom[17 + u] = p0[u];
+          mom[20 + u] = p1[u];
+#pragma unroll
+          for (int v = 0; v < 3; ++v) {
+            mom[7 + u * 3 + v] = wd * p1[u] * p0[v];  // S[u][v] = sum w * y_u * x_v
+            mom[23 + u * 3 + v] = p1[u] * p0[v];
+          }
+        }
+        mom[32] = w > 0.f ? 1.0 : 0.0;
+      }
+    }
+    float* o = a.pts + pi * PT_C;
+#pragma unroll
+    for (int k = 0; k < 11; ++k) o[k] = out[k];
+    if (!a.p.static_aggregation) {
+      o[11] = 0.f;
+      o[12] = 0.f;
+      o[13] = 0.f;
+    }
+  }
+  if (!a.p.static_aggregation) return;
+  // fixed-order reduction: lanes -> warps -> block partial; blocks are summed in order by k_kabsch_finalize
+#pragma unroll
+  for (int k = 0; k < N_MOM; ++k) {
+    double v = mom[k];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < N_MOM) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < PT_THREADS / 32; ++w) v += s_part[w][threadIdx.x];
+    a.partials[((size_t)b * a.blocks_per_sample + blockIdx.x) * N_MOM + threadIdx.x] = v;
+  }
+}
+
+// One-sided Jacobi (Hestenes) SVD of a 3x3 matrix in fp64: A V = U diag(sigma); returns R = U V^T (the
+// orthogonal polar factor; symmetric_orthogonalization returns exactly U @ Vh, without determinant fix).
+__device__ void polar_uvt(const double S[3][3], double R[3][3]) {
+  double A[3][3], V[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      A[i][j] = S[i][j];
+      V[i][j] = i == j ? 1.0 : 0.0;
+    }
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        double alpha = 0, beta = 0, gamma = 0;
+        for (int i = 0; i < 3; ++i) {
+          alpha += A[i][p] * A[i][p];
+          beta += A[i][q] * A[i][q];
+          gamma += A[i][p] * A[i][q];
+        }
+        if (gamma == 0.0) continue;
+        off = fmax(off, fabs(gamma) / sqrt(fmax(alpha * beta, 1e-300)));
+        const double zeta = (beta - alpha) / (2.0 * gamma);
+        const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+        for (int i = 0; i < 3; ++i) {
+          const double ap = A[i][p], aq = A[i][q];
+          A[i][p] = c * ap - s * aq;
+          A[i][q] = s * ap + c * aq;
+          const double vp = V[i][p], vq = V[i][q];
+          V[i][p] = c * vp - s * vq;
+          V[i][q] = s * vp + c * vq;
+        }
+      }
+    if (off < 1e-15) break;
+  }
+  double U[3][3], sig[3];
+  for (int j = 0; j < 3; ++j) sig[j] = sqrt(A[0][j] * A[0][j] + A[1][j] * A[1][j] + A[2][j] * A[2][j]);
+  const double smax = fmax(sig[0], fmax(sig[1], sig[2]));
+  int n_ok = 0;
+  bool ok[3];
+  for (int j = 0; j < 3; ++j) {
+    ok[j] = sig[j] > smax * 1e-14 && sig[j] > 0.0;
+    n_ok += ok[j];
+    for (int i = 0; i < 3; ++i) U[i][j] = ok[j] ? A[i][j] / sig[j] : 0.0;
+  }
+  if (n_ok == 2) {  // rank 2: complete the basis with the cross product (the null direction is not unique anyway)
+    int z = !ok[0] ? 0 : (!ok[1] ? 1 : 2);
+    const int u = (z + 1) % 3, v = (z + 2) % 3;
+    U[0][z] = U[1][u] * U[2][v] - U[2][u] * U[1][v];
+    U[1][z] = U[2][u] * U[0][v] - U[0][u] * U[2][v];
+    U[2][z] = U[0][u] * U[1][v] - U[1][u] * U[0][v];
+  } else if (n_ok < 2) {  // rank <= 1: fall back to the identity rotation
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        U[i][j] = i == j ? 1.0 : 0.0;
+        V[i][j] = i == j ? 1.0 : 0.0;
+      }
+  }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) R[i][j] = U[i][0] * V[j][0] + U[i][1] * V[j][1] + U[i][2] * V[j][2];
+}
+
+__global__ void __launch_bounds__(64) k_kabsch_finalize(const DecodeArgs a) {
+  __shared__ double s_m[N_MOM];
+  const int b = blockIdx.x;
+  if (threadIdx.x < N_MOM) {
+    double v = 0.0;
+    const double* src = a.partials + (size_t)b * a.blocks_per_sample * N_MOM + threadIdx.x;
+    for (int k = 0; k < a.blocks_per_sample; ++k) v += src[(size_t)k * N_MOM];
+    s_m[threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const bool not_enough = s_m[32] < 3.0;  // (weights > 0).sum() < 3 -> weights += 1e-7 (weighted_pc_alignment.py:31-35)
+  const double eps = not_enough ? 1e-7 : 0.0;
+  const double cum = s_m[0] + eps * s_m[16];
+  double mx[3], my[3], S[3][3], R[3][3];
+  for (int u = 0; u < 3; ++u) {
+    mx[u] = (s_m[1 + u] + eps * s_m[17 + u]) / cum;
+    my[u] = (s_m[4 + u] + eps * s_m[20 + u]) / cum;
+  }
+  for (int u = 0; u < 3; ++u)
+    for (int v = 0; v < 3; ++v) S[u][v] = (s_m[7 + u * 3 + v] + eps * s_m[23 + u * 3 + v]) / cum - my[u] * mx[v];
+  polar_uvt(S, R);
+  double* T = a.trafo + (size_t)b * 16;
+  for (int u = 0; u < 3; ++u) {
+    for (int v = 0; v < 3; ++v) T[u * 4 + v] = R[u][v];
+    T[u * 4 + 3] = my[u] - (R[u][0] * mx[0] + R[u][1] * mx[1] + R[u][2] * mx[2]);
+  }
+  T[12] = 0.0;
+  T[13] = 0.0;
+  T[14] = 0.0;
+  T[15] = 1.0;
+  a.not_enough[b] = not_enough ? 1 : 0;
+}
+
+// static_aggr_flow of a cell: ((T - I) [xc, yc, 0, 1])[:2] in fp64, then float (static_aggregation.py:88-103);
+// cell centres as head_decoder.py:498-514: (idx + 0.5) / shape * (max - min) + min
+__device__ __forceinline__ float2 aggr_flow_of_cell(const double* __restrict__ T, const slimb200_decode_params& p, int r, int c) {
+  const double xc = ((double)r + 0.5) / (double)p.H * (p.ext_max_x - p.ext_min_x) + p.ext_min_x;
+  const double yc = ((double)c + 0.5) / (double)p.W * (p.ext_max_y - p.ext_min_y) + p.ext_min_y;
+  const double fx = (T[0] - 1.0) * xc + T[1] * yc + T[3];
+  const double fy = T[4] * xc + (T[5] - 1.0) * yc + T[7];
+  return make_float2((float)fx, (float)fy);
+}
+
+__global__ void __launch_bounds__(256) k_decode_aggr(const DecodeArgs a) {
+  const size_t n_cells = (size_t)a.p.batch * a.p.H * a.p.W;
+  const size_t n_pts = (size_t)a.p.batch * a.p.n_points;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_cells) {
+    const int c = (int)(i % a.p.W);
+    const size_t t = i / a.p.W;
+    const int r = (int)(t % a.p.H), b = (int)(t / a.p.H);
+    const float2 f = aggr_flow_of_cell(a.trafo + (size_t)b * 16, a.p, r, c);
+    const bool filled = a.filled[i] != 0;
+    *reinterpret_cast<float4*>(a.bev + i * BEV_C + 16) = make_float4(f.x, f.y, filled ? f.x : 0.f, filled ? f.y : 0.f);
+  } else if (i - n_cells < n_pts) {
+    const size_t pi = i - n_cells;
+    const int b = (int)(pi / a.p.n_points);
+    float2 f = make_float2(0.f, 0.f);
+    if (a.valid[pi]) {
+      const int r = a.coors[pi * 2] / a.p.final_scale, c = a.coors[pi * 2 + 1] / a.p.final_scale;
+      f = aggr_flow_of_cell(a.trafo + (size_t)b * 16, a.p, r, c);
+    }
+    float* o = a.pts + pi * PT_C + 11;
+    o[0] = f.x;
+    o[1] = f.y;
+    o[2] = 0.f;
+  }
+}
+
+int blocks_per_sample(const slimb200_decode_params* p) { return (p->n_points + PT_THREADS - 1) / PT_THREADS; }
+
+}  // namespace
+
+extern "C" size_t slimb200_head_decode_workspace_bytes(const slimb200_decode_params* p) {
+  if (!p || p->batch < 1 || p->n_points < 0) return 0;
+  WorkspaceCarver w(nullptr);
+  w.take<unsigned>(64);
+  w.take<double>((size_t)p->batch * (blocks_per_sample(p) + 1) * N_MOM);
+  return w.used();
+}
+
+extern "C" int slimb200_head_decode(const float* net_out, const uint8_t* filled, const float* pc, const int32_t* coors,
+                                    const uint8_t* valid, const float* dyn_threshold, const slimb200_decode_params* p,
+                                    float* bev, uint8_t* bev_classes, float* points, double* trafo, uint8_t* not_enough,
+                                    void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!net_out || !filled || !dyn_threshold || !p || !bev || !bev_classes || !workspace) return SLIMB200_E_INVALID;
+  if (p->batch < 1 || p->H < 1 || p->W < 1 || p->n_points < 0 || p->final_scale < 1) return SLIMB200_E_INVALID;
+  if (p->n_points > 0 && (!pc || !coors || !valid || !points || p->pc_stride < 3)) return SLIMB200_E_INVALID;
+  if (p->static_aggregation && (!trafo || !not_enough)) return SLIMB200_E_INVALID;
+  if (workspace_bytes < slimb200_head_decode_workspace_bytes(p)) return SLIMB200_E_WORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(net_out) & 15) || (reinterpret_cast<uintptr_t>(bev) & 15) ||
+      (reinterpret_cast<uintptr_t>(workspace) & 255))
+    return SLIMB200_E_ALIGNMENT;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DecodeArgs a{};
+  a.net_out = net_out;
+  a.filled = filled;
+  a.pc = pc;
+  a.coors = coors;
+  a.valid = valid;
+  a.thr = dyn_threshold;
+  a.p = *p;
+  a.bev = bev;
+  a.bev_cls = bev_classes;
+  a.pts = points;
+  a.trafo = trafo;
+  a.not_enough = not_enough;
+  WorkspaceCarver w(workspace);
+  a.min_key = w.take<unsigned>(64);
+  a.blocks_per_sample = blocks_per_sample(p);
+  a.partials = w.take<double>((size_t)p->batch * (a.blocks_per_sample + 1) * N_MOM);
+
+  const size_t n_cells = (size_t)p->batch * p->H * p->W;
+  SLIMB200_CUDA_TRY(cudaMemsetAsync(a.min_key, 0xff, sizeof(unsigned), stream));
+  {
+    const unsigned blocks = (unsigned)((n_cells + 255) / 256 < 148 * 8 ? (n_cells + 255) / 256 : 148 * 8);
+    SLIMB200_LAUNCH(SLIMB200_K_DECODE_MIN, stream, (k_decode_min<<<blocks, 256, 0, stream>>>(net_out, n_cells, a.min_key)));
+  }
+  SLIMB200_LAUNCH(SLIMB200_K_DECODE_BEV, stream, (k_decode_bev<<<(unsigned)((n_cells + 255) / 256), 256, 0, stream>>>(a)));
+  if (p->n_points > 0) {
+    dim3 g(a.blocks_per_sample, p->batch);
+    SLIMB200_LAUNCH(SLIMB200_K_DECODE_POINTS, stream, (k_decode_points<<<g, PT_THREADS, 0, stream>>>(a)));
+  }
+  if (p->static_aggregation) {
+    SLIMB200_LAUNCH(SLIMB200_K_KABSCH, stream, (k_kabsch_finalize<<<p->batch, 64, 0, stream>>>(a)));
+    const size_t total = n_cells + (size_t)p->batch * p->n_points;
+    SLIMB200_LAUNCH(SLIMB200_K_DECODE_AGGR, stream, (k_decode_aggr<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a)));
+  }
+  return SLIMB200_OK;
+}

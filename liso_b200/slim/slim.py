@@ -100,6 +100,79 @@ class HeadDecoder(nn.Module):
 
     def forward(self, network_output, dynamicness_threshold, *, pc, pointwise_voxel_coordinates, pointwise_valid_mask,
                 filled_pillar_mask, odom=None, inv_odom=None, summaries=None, static_aggregation: bool = True, **_):
+        if network_output.is_cuda:
+            return self._forward_fused(network_output, dynamicness_threshold, pc, pointwise_voxel_coordinates,
+                                       pointwise_valid_mask, filled_pillar_mask, static_aggregation)
+        return self._forward_torch(network_output, dynamicness_threshold, pc=pc,
+                                   pointwise_voxel_coordinates=pointwise_voxel_coordinates,
+                                   pointwise_valid_mask=pointwise_valid_mask, filled_pillar_mask=filled_pillar_mask,
+                                   static_aggregation=static_aggregation)
+
+    def _forward_fused(self, o, thr, pc, coors, valid, filled, static_aggregation):
+        """One call into ``slimb200_head_decode``: five launches, no host sync; the tensors of the
+        reference's result are channel slices of two packed buffers."""
+        import ctypes as C
+
+        from .. import _lib
+
+        lib = _lib.load()
+        dev = o.device
+        B, H, W, ch = o.shape
+        assert ch == 8, o.shape
+        o = o.float().contiguous()
+        N = int(valid.shape[1])
+        p = _lib.DecodeParams()
+        p.batch, p.H, p.W, p.n_points = B, H, W, N
+        pc = pc.float().contiguous()
+        p.pc_stride = int(pc.shape[-1])
+        p.final_scale = int(self.cfg.model.u_net.final_scale)
+        p.static_aggregation = 1 if static_aggregation else 0
+        ext = [float(v) for v in self.bev_extent]
+        p.ext_min_x, p.ext_min_y, p.ext_max_x, p.ext_max_y = ext
+        coors = coors.to(torch.int32).contiguous()
+        valid_u8 = valid.contiguous().view(torch.uint8)
+        filled_u8 = filled.contiguous().view(torch.uint8)
+        thr_t = torch.as_tensor(thr, dtype=torch.float32, device=dev).reshape(1)
+        bev = torch.empty((B, H, W, _lib.DECODE_BEV_CHANNELS), dtype=torch.float32, device=dev)
+        cls = torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev)
+        pts = torch.empty((B, N, _lib.DECODE_POINT_CHANNELS), dtype=torch.float32, device=dev)
+        trafo = torch.empty((B, 4, 4), dtype=torch.float64, device=dev)
+        nep = torch.zeros((B,), dtype=torch.uint8, device=dev)
+        ws_bytes = lib.slimb200_head_decode_workspace_bytes(C.byref(p))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.slimb200_head_decode(
+            o.data_ptr(), filled_u8.data_ptr(), pc.data_ptr(), coors.data_ptr(), valid_u8.data_ptr(), thr_t.data_ptr(),
+            C.byref(p), bev.data_ptr(), cls.data_ptr(), pts.data_ptr(), trafo.data_ptr(), nep.data_ptr(),
+            ws.data_ptr(), ws.numel(), _lib.current_stream_ptr()))
+        clsb = cls.view(torch.bool)
+        md = AttrDict()
+        md.disappearing_logit = bev[..., 0:1]
+        md.static_logit, md.dynamic_logit, md.ground_logit = bev[..., 1:2], bev[..., 2:3], bev[..., 3:4]
+        md.class_logits = bev[..., 1:4]
+        md.class_probs = bev[..., 4:7]
+        md.staticness, md.dynamicness, md.groundness = bev[..., 4], bev[..., 5], bev[..., 6]
+        md.static_flow, md.dynamic_flow = bev[..., 7:9], bev[..., 10:12]
+        md.is_dynamic, md.is_static, md.is_ground = clsb[..., 0], clsb[..., 1], clsb[..., 2]
+        ret = AttrDict()
+        ret.static_flow, ret.dynamic_flow = pts[..., 0:3], pts[..., 3:6]
+        ret.dynamicness, ret.staticness = pts[..., 6], pts[..., 7]
+        ret.aggregated_flow = pts[..., 8:11]
+        ret.dense_maps = AttrDict(aggregated_flow=bev[..., 13:16], static_flow=bev[..., 7:10])
+        ret.dynamicness_threshold = thr
+        if static_aggregation:
+            md.static_aggr_flow = bev[..., 16:18]
+            md.masked_static_aggr_flow = bev[..., 18:20]
+            ret.static_aggr_flow = pts[..., 11:14]
+            ret.static_aggr_trafo = trafo
+            ret.not_enough_points = nep.view(torch.bool)
+        else:
+            ret.not_enough_points = torch.zeros((B,), dtype=torch.bool, device=dev)
+        ret.modified_network_output = md
+        return ret
+
+    def _forward_torch(self, network_output, dynamicness_threshold, *, pc, pointwise_voxel_coordinates, pointwise_valid_mask,
+                       filled_pillar_mask, static_aggregation: bool = True):
+        """Stock-PyTorch restatement (CPU tensors, host-logic tests)."""
         fs = self.cfg.model.u_net.final_scale
         coors = torch.div(pointwise_voxel_coordinates, fs, rounding_mode="trunc")
         filled = filled_pillar_mask[..., None]
