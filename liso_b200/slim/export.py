@@ -84,3 +84,97 @@ def iterate_batches(indices: Iterable[int], batch_size: int) -> Iterable[List[in
             cur = []
     if cur:
         yield cur
+
+
+class ExportPipeline:
+    """Double-buffered export loop for one GPU: the host->device upload of batch i+1 and the device->host download
+    of batch i-1 run on a copy stream while batch i is computed on the caller's stream.  (The reference uploads,
+    computes and ``.cpu().numpy()``s each sample strictly in sequence, ``experiment.py:363-402``.)
+
+    ``batches``: iterable of ``(sample_data_t0, sample_data_t1)`` with tensors in *pinned* host memory.
+    ``consume(index, arrays)``: called with the exported tensors of a batch as pinned host tensors once they have
+    arrived (they are reused two batches later: copy or write them out inside the callback).
+    """
+
+    KEYS = ("pcl_full_no_ground_ta", "pcl_ta")
+
+    def __init__(self, model, device, amp_ctx=None):
+        self.model, self.device = model, device
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.amp_ctx = amp_ctx
+        self._out_bufs = [None, None]
+
+    def _upload(self, sample):
+        out = {}
+        for k, v in sample.items():
+            if isinstance(v, dict):
+                out[k] = {kk: vv.to(self.device, non_blocking=True) for kk, vv in v.items()}
+            elif isinstance(v, (list, tuple)):
+                out[k] = [t.to(self.device, non_blocking=True) for t in v]
+            else:
+                out[k] = v.to(self.device, non_blocking=True)
+        return out
+
+    def run(self, batches, consume=None):
+        import contextlib
+
+        cur = torch.cuda.current_stream(self.device)
+        it = iter(batches)
+        pending = None  # (index, device tensors, event) waiting for download
+        downloads = []  # (index, host tensors, event)
+        nxt = next(it, None)
+        staged = None
+        if nxt is not None:
+            with torch.cuda.stream(self.copy_stream):
+                staged = (self._upload(nxt[0]), self._upload(nxt[1]))
+                up_evt = torch.cuda.Event()
+                up_evt.record(self.copy_stream)
+        idx = 0
+        n_done = 0
+        while staged is not None:
+            cur.wait_event(up_evt)
+            d0, d1 = staged
+            for d in (d0, d1):  # the uploaded tensors are consumed on the compute stream
+                for v in d.values():
+                    for t in (v.values() if isinstance(v, dict) else (v if isinstance(v, (list, tuple)) else [v])):
+                        t.record_stream(cur)
+            ctx = self.amp_ctx() if self.amp_ctx else contextlib.nullcontext()
+            with torch.no_grad(), ctx:
+                pf, pb = self.model(d0, d1, None)
+            fw, bw = pf[-1].modified_network_output, pb[-1].modified_network_output
+            outs = [fw.static_flow, bw.static_flow, fw.dynamicness, bw.dynamicness]
+            done = torch.cuda.Event()
+            done.record(cur)
+            # stage the next batch and download this one on the copy stream, behind the compute of this batch
+            nxt = next(it, None)
+            with torch.cuda.stream(self.copy_stream):
+                if nxt is not None:
+                    staged = (self._upload(nxt[0]), self._upload(nxt[1]))
+                    up_evt = torch.cuda.Event()
+                    up_evt.record(self.copy_stream)
+                else:
+                    staged = None
+                self.copy_stream.wait_event(done)
+                slot = idx % 2
+                if self._out_bufs[slot] is None or any(b.shape != o.shape for b, o in zip(self._out_bufs[slot], outs)):
+                    self._out_bufs[slot] = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
+                for dst, src in zip(self._out_bufs[slot], outs):
+                    src.record_stream(self.copy_stream)
+                    dst.copy_(src, non_blocking=True)
+                dl_evt = torch.cuda.Event()
+                dl_evt.record(self.copy_stream)
+            downloads.append((idx, self._out_bufs[slot], dl_evt))
+            # hand over the batch downloaded one iteration ago (its pinned buffers are reused next iteration)
+            while len(downloads) > 1:
+                j, host, evt = downloads.pop(0)
+                evt.synchronize()
+                if consume is not None:
+                    consume(j, host)
+                n_done += 1
+            idx += 1
+        for j, host, evt in downloads:
+            evt.synchronize()
+            if consume is not None:
+                consume(j, host)
+            n_done += 1
+        return n_done
