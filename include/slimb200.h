@@ -192,10 +192,21 @@ size_t slimb200_head_decode_workspace_bytes(const slimb200_decode_params* p);
 /* net_out (batch, H, W, 8) f32 contiguous: logits 0:4 (1 = static, 2 = dynamic), static flow 4:6, dynamic flow 6:8
  * filled (batch, H, W) u8; pc (batch, n_points, pc_stride) f32; coors (batch, n_points, 2) i32; valid (batch, n_points) u8
  * dyn_threshold: DEVICE pointer to one float (MovingAverageThreshold.value(), no host read) */
-int slimb200_head_decode(const float* net_out, const uint8_t* filled, const float* pc, const int32_t* coors,
+int slimb200_head_decode(const float* net_out, const uint32_t* logit_min_key /* from slimb200_raft_output, or NULL */,
+                         const uint8_t* filled, const float* pc, const int32_t* coors,
                          const uint8_t* valid, const float* dyn_threshold, const slimb200_decode_params* p,
                          float* bev, uint8_t* bev_classes, float* points, double* trafo, uint8_t* not_enough,
                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* SURVEY 8(f).2 glue, once per GRU iteration (raft_mod.py:216-257): upflow_n / uplogits_n (bilinear, align_corners,
+ * raft_code/utils.py:50-60), flip (x, y) -> (row, col) and * metres per pixel (raft_mod.py:262-266), and
+ * HeadDecoder.concat2network_output (head_decoder.py:36-64) in one pass.
+ * flow (batch, 2, h, w) f32 = coords1 - coords0, logits (batch, 4, h, w) f32, both NCHW contiguous;
+ * net_out (batch, n*h, n*w, 8) f32 = [logits 0:4 | static flow (row, col) | dynamic flow (row, col)];
+ * logit_min_key (optional, one device word): order-preserving encoding of min(logits[:, 1:3]) over the whole batch,
+ * to be handed to slimb200_head_decode. */
+int slimb200_raft_output(const float* flow, const float* logits, int32_t batch, int32_t h, int32_t w, int32_t n,
+                         float res_rows, float res_cols, float* net_out, uint32_t* logit_min_key, void* stream);
 
 const char* slimb200_strerror(int code);
 int slimb200_version(void);
@@ -224,6 +235,7 @@ enum {
   SLIMB200_K_DECODE_POINTS,
   SLIMB200_K_KABSCH,
   SLIMB200_K_DECODE_AGGR,
+  SLIMB200_K_RAFT_OUTPUT,
   SLIMB200_N_KERNELS
 };
 int slimb200_profile_begin(void);

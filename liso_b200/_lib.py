@@ -94,7 +94,12 @@ SYMBOLS = {
     "slimb200_head_decode_workspace_bytes": (C.c_size_t, [C.POINTER(DecodeParams)]),
     "slimb200_head_decode": (
         C.c_int,
-        [C.c_void_p] * 6 + [C.POINTER(DecodeParams)] + [C.c_void_p] * 5 + [C.c_void_p, C.c_size_t, C.c_void_p],
+        [C.c_void_p] * 7 + [C.POINTER(DecodeParams)] + [C.c_void_p] * 5 + [C.c_void_p, C.c_size_t, C.c_void_p],
+    ),
+    "slimb200_raft_output": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
+         C.c_void_p],
     ),
     "slimb200_strerror": (C.c_char_p, [C.c_int]),
     "slimb200_version": (C.c_int, []),
@@ -103,9 +108,9 @@ SYMBOLS = {
     "slimb200_launch_count": (C.c_int64, [C.c_int32]),
     "slimb200_kernel_name": (C.c_char_p, [C.c_int32]),
 }
-N_KERNELS = 18
+N_KERNELS = 19
 K_TILE_ENCODE, K_PILLAR_NHWC, K_FEAT_TRANSPOSE, K_FEAT_PACK, K_CORR_GEMM, K_CORR_LOOKUP = 6, 7, 8, 9, 10, 11
-K_DECODE_BEV, K_DECODE_POINTS, K_DECODE_AGGR = 14, 15, 17
+K_DECODE_BEV, K_DECODE_POINTS, K_DECODE_AGGR, K_RAFT_OUTPUT = 14, 15, 17, 18
 CANVAS_NCHW, CANVAS_NHWC = 0, 1
 
 _lib: Optional[C.CDLL] = None

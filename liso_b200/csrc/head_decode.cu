@@ -44,6 +44,52 @@ __global__ void __launch_bounds__(256) k_decode_min(const float* __restrict__ ne
   if ((threadIdx.x & 31) == 0) atomicMin(out_key, best);
 }
 
+// ------------------------------------------------------------------------------------------
+// SURVEY 8(f).2 glue: RAFT.predict_single_flow_map_and_classes, raft_mod.py:216-257 -- per GRU iteration
+//   upflow_n / uplogits_n   (raft_code/utils.py:50-60: F.interpolate bilinear, align_corners=True, flow * n)
+//   change_flow_convention_from_raft2usfl (raft_mod.py:262-266: flip (x, y) -> (row, col), * metres per pixel)
+//   HeadDecoder.concat2network_output (head_decoder.py:36-64: cat [logits, static, dynamic] -> (B, H, W, 8))
+// as ONE pass that writes the (B, H, W, 8) network output (32 contiguous bytes per pixel) and, on the way, takes
+// the global min of the static / dynamic logits that the decoder needs (k_decode_min disappears).
+// Interpolation follows ATen's upsample_bilinear2d: src = dst * (in - 1) / (out - 1), taps (i, i + (i < in - 1)).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_raft_output(const float* __restrict__ flow, const float* __restrict__ logits, int batch,
+                                                     int h, int w, int n, float res_rows, float res_cols,
+                                                     float* __restrict__ net_out, unsigned* __restrict__ min_key) {
+  const int H = h * n, W = w * n;
+  const size_t total = (size_t)batch * H * W;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned best = 0xffffffffu;
+  if (i < total) {
+    const int x = (int)(i % W);
+    const size_t t = i / W;
+    const int y = (int)(t % H), b = (int)(t / H);
+    const float rh = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, rw = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
+    const float hr = rh * (float)y, wr = rw * (float)x;
+    const int h1 = (int)hr, w1 = (int)wr;
+    const int hp = h1 < h - 1 ? 1 : 0, wp = w1 < w - 1 ? 1 : 0;
+    const float hl1 = hr - (float)h1, hl0 = 1.f - hl1;
+    const float wl1 = wr - (float)w1, wl0 = 1.f - wl1;
+    const size_t plane = (size_t)h * w;
+    const size_t o00 = (size_t)h1 * w + w1, o01 = o00 + wp, o10 = o00 + (size_t)hp * w, o11 = o10 + wp;
+    auto interp = [&](const float* img) {
+      return hl0 * (wl0 * __ldg(img + o00) + wl1 * __ldg(img + o01)) + hl1 * (wl0 * __ldg(img + o10) + wl1 * __ldg(img + o11));
+    };
+    const float* lg = logits + (size_t)b * 4 * plane;
+    const float* fl = flow + (size_t)b * 2 * plane;
+    const float l0 = interp(lg), l1 = interp(lg + plane), l2 = interp(lg + 2 * plane), l3 = interp(lg + 3 * plane);
+    const float fx = __fmul_rn((float)n, interp(fl)), fy = __fmul_rn((float)n, interp(fl + plane));  // upflow_n
+    const float f_row = __fmul_rn(fy, res_rows), f_col = __fmul_rn(fx, res_cols);                    // flip, then * res
+    float4* o = reinterpret_cast<float4*>(net_out + i * 8);
+    o[0] = make_float4(l0, l1, l2, l3);
+    o[1] = make_float4(f_row, f_col, f_row, f_col);
+    best = min(f2key(l1), f2key(l2));
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, d));
+  if ((threadIdx.x & 31) == 0 && min_key) atomicMin(min_key, best);
+}
+
 struct DecodeArgs {
   const float* net_out;
   const uint8_t* filled;
@@ -63,40 +109,55 @@ struct DecodeArgs {
 };
 
 __global__ void __launch_bounds__(256) k_decode_bev(const DecodeArgs a) {
+  // a CTA's 256 cells form one contiguous 20 KB block of the packed output: stage the rows in shared memory
+  // (80-byte pitch: the 128-bit stores of a quarter-warp hit 32 distinct banks) and write them back linearly
+  __shared__ __align__(16) float s_row[256 * BEV_C];
+  __shared__ __align__(4) uint8_t s_cls[256 * 3];
   const size_t n_cells = (size_t)a.p.batch * a.p.H * a.p.W;
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_cells) return;
-  const float4 lg = __ldg(reinterpret_cast<const float4*>(a.net_out + i * 8));
-  const float4 fl = __ldg(reinterpret_cast<const float4*>(a.net_out + i * 8 + 4));
-  const bool filled = a.filled[i] != 0;
-  const float ground_off = key2f(*a.min_key) - 100.0f;
-  // mask non-filled pillars (head_decoder.py:568-609)
-  const float l_st = filled ? lg.y : 0.f;
-  const float l_dy = filled ? lg.z : -100.f;
-  const float l_gr = filled ? ground_off : -100.f;
-  const float sfx = filled ? fl.x : 0.f, sfy = filled ? fl.y : 0.f;
-  const float dfx = filled ? fl.z : 0.f, dfy = filled ? fl.w : 0.f;
-  // softmax over (static, dynamic, ground)
-  const float m = fmaxf(l_st, fmaxf(l_dy, l_gr));
-  const float e0 = expf(l_st - m), e1 = expf(l_dy - m), e2 = expf(l_gr - m);
-  const float s = e0 + e1 + e2;
-  const float p_st = e0 / s, p_dy = e1 / s, p_gr = e2 / s;
-  const float thr = __ldg(a.thr);
-  const bool is_dyn = p_dy >= thr;
-  const bool is_sta = (p_st >= p_gr) && !is_dyn;
-  const bool is_gr = !(is_sta || is_dyn);
-  const float g = 1.0f - p_gr;
-  const float agx = is_sta ? sfx : dfx * g, agy = is_sta ? sfy : dfy * g, agz = is_sta ? 0.f : 0.f * g;
-  float4* o = reinterpret_cast<float4*>(a.bev + i * BEV_C);
-  o[0] = make_float4(-100.f, l_st, l_dy, l_gr);      // disappearing | class_logits (static, dynamic, ground)
-  o[1] = make_float4(p_st, p_dy, p_gr, sfx);         // class_probs | static3.x
-  o[2] = make_float4(sfy, 0.f, dfx, dfy);            // static3.yz | dynamic3.xy
-  o[3] = make_float4(0.f, agx, agy, agz);            // dynamic3.z | aggregated3
-  if (!a.p.static_aggregation) o[4] = make_float4(0.f, 0.f, 0.f, 0.f);
-  uint8_t* c = a.bev_cls + i * 3;
-  c[0] = is_dyn;
-  c[1] = is_sta;
-  c[2] = is_gr;
+  const size_t base = (size_t)blockIdx.x * 256;
+  const size_t i = base + threadIdx.x;
+  if (i < n_cells) {
+    const float4 lg = __ldg(reinterpret_cast<const float4*>(a.net_out + i * 8));
+    const float4 fl = __ldg(reinterpret_cast<const float4*>(a.net_out + i * 8 + 4));
+    const bool filled = a.filled[i] != 0;
+    const float ground_off = key2f(*a.min_key) - 100.0f;
+    // mask non-filled pillars (head_decoder.py:568-609)
+    const float l_st = filled ? lg.y : 0.f;
+    const float l_dy = filled ? lg.z : -100.f;
+    const float l_gr = filled ? ground_off : -100.f;
+    const float sfx = filled ? fl.x : 0.f, sfy = filled ? fl.y : 0.f;
+    const float dfx = filled ? fl.z : 0.f, dfy = filled ? fl.w : 0.f;
+    // softmax over (static, dynamic, ground)
+    const float m = fmaxf(l_st, fmaxf(l_dy, l_gr));
+    const float e0 = expf(l_st - m), e1 = expf(l_dy - m), e2 = expf(l_gr - m);
+    const float s = e0 + e1 + e2;
+    const float p_st = e0 / s, p_dy = e1 / s, p_gr = e2 / s;
+    const float thr = __ldg(a.thr);
+    const bool is_dyn = p_dy >= thr;
+    const bool is_sta = (p_st >= p_gr) && !is_dyn;
+    const bool is_gr = !(is_sta || is_dyn);
+    const float g = 1.0f - p_gr;
+    const float agx = is_sta ? sfx : dfx * g, agy = is_sta ? sfy : dfy * g, agz = is_sta ? 0.f : 0.f * g;
+    float4* o = reinterpret_cast<float4*>(s_row + threadIdx.x * BEV_C);
+    o[0] = make_float4(-100.f, l_st, l_dy, l_gr);      // disappearing | class_logits (static, dynamic, ground)
+    o[1] = make_float4(p_st, p_dy, p_gr, sfx);         // class_probs | static3.x
+    o[2] = make_float4(sfy, 0.f, dfx, dfy);            // static3.yz | dynamic3.xy
+    o[3] = make_float4(0.f, agx, agy, agz);            // dynamic3.z | aggregated3
+    o[4] = make_float4(0.f, 0.f, 0.f, 0.f);            // static_aggr_flow: k_decode_aggr fills it in
+    s_cls[threadIdx.x * 3 + 0] = is_dyn;
+    s_cls[threadIdx.x * 3 + 1] = is_sta;
+    s_cls[threadIdx.x * 3 + 2] = is_gr;
+  }
+  __syncthreads();
+  const int n_here = (int)min((size_t)256, n_cells - base);
+  float4* dst = reinterpret_cast<float4*>(a.bev + base * BEV_C);
+  const float4* src = reinterpret_cast<const float4*>(s_row);
+  for (int k = threadIdx.x; k < n_here * (BEV_C / 4); k += 256) dst[k] = src[k];
+  if (n_here == 256) {
+    if (threadIdx.x < 192) reinterpret_cast<uint32_t*>(a.bev_cls + base * 3)[threadIdx.x] = reinterpret_cast<const uint32_t*>(s_cls)[threadIdx.x];
+  } else {
+    for (int k = threadIdx.x; k < n_here * 3; k += 256) a.bev_cls[base * 3 + k] = s_cls[k];
+  }
 }
 
 __global__ void __launch_bounds__(PT_THREADS) k_decode_points(const DecodeArgs a) {
@@ -321,8 +382,22 @@ extern "C" size_t slimb200_head_decode_workspace_bytes(const slimb200_decode_par
   return w.used();
 }
 
-extern "C" int slimb200_head_decode(const float* net_out, const uint8_t* filled, const float* pc, const int32_t* coors,
-                                    const uint8_t* valid, const float* dyn_threshold, const slimb200_decode_params* p,
+extern "C" int slimb200_raft_output(const float* flow, const float* logits, int32_t batch, int32_t h, int32_t w, int32_t n,
+                                    float res_rows, float res_cols, float* net_out, uint32_t* min_key, void* stream_) {
+  if (!flow || !logits || !net_out || batch < 1 || h < 1 || w < 1 || n < 1) return SLIMB200_E_INVALID;
+  if (reinterpret_cast<uintptr_t>(net_out) & 15) return SLIMB200_E_ALIGNMENT;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (min_key) SLIMB200_CUDA_TRY(cudaMemsetAsync(min_key, 0xff, sizeof(uint32_t), stream));
+  const size_t total = (size_t)batch * h * n * w * n;
+  SLIMB200_LAUNCH(SLIMB200_K_RAFT_OUTPUT, stream,
+                  (k_raft_output<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(flow, logits, batch, h, w, n, res_rows, res_cols,
+                                                                                     net_out, min_key)));
+  return SLIMB200_OK;
+}
+
+extern "C" int slimb200_head_decode(const float* net_out, const uint32_t* logit_min_key, const uint8_t* filled, const float* pc,
+                                    const int32_t* coors, const uint8_t* valid, const float* dyn_threshold,
+                                    const slimb200_decode_params* p,
                                     float* bev, uint8_t* bev_classes, float* points, double* trafo, uint8_t* not_enough,
                                     void* workspace, size_t workspace_bytes, void* stream_) {
   if (!net_out || !filled || !dyn_threshold || !p || !bev || !bev_classes || !workspace) return SLIMB200_E_INVALID;
@@ -353,8 +428,10 @@ extern "C" int slimb200_head_decode(const float* net_out, const uint8_t* filled,
   a.partials = w.take<double>((size_t)p->batch * (a.blocks_per_sample + 1) * N_MOM);
 
   const size_t n_cells = (size_t)p->batch * p->H * p->W;
-  SLIMB200_CUDA_TRY(cudaMemsetAsync(a.min_key, 0xff, sizeof(unsigned), stream));
-  {
+  if (logit_min_key) {
+    a.min_key = const_cast<unsigned*>(logit_min_key);  // already taken by slimb200_raft_output
+  } else {
+    SLIMB200_CUDA_TRY(cudaMemsetAsync(a.min_key, 0xff, sizeof(unsigned), stream));
     const unsigned blocks = (unsigned)((n_cells + 255) / 256 < 148 * 8 ? (n_cells + 255) / 256 : 148 * 8);
     SLIMB200_LAUNCH(SLIMB200_K_DECODE_MIN, stream, (k_decode_min<<<blocks, 256, 0, stream>>>(net_out, n_cells, a.min_key)));
   }

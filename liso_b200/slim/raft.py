@@ -213,6 +213,23 @@ class SmallUpdateBlock(nn.Module):
         return net, self.static_flow_head(net), self.classification_head(net), None
 
 
+def raft_output_fused(flow, logits, n, res_rows, res_cols):
+    """upflow_n + uplogits_n + flip / scale + concat2network_output in one kernel (``slimb200_raft_output``,
+    SURVEY 8f.2); the returned (B, H, W, 8) tensor carries the logit minimum the decoder needs."""
+    from .. import _lib
+
+    lib = _lib.load()
+    B, _, h, w = flow.shape
+    flow = flow.detach().float().contiguous()
+    logits = logits.detach().float().contiguous()
+    out = torch.empty((B, h * n, w * n, 8), dtype=torch.float32, device=flow.device)
+    min_key = torch.empty((1,), dtype=torch.int32, device=flow.device)
+    _lib.check(lib.slimb200_raft_output(flow.data_ptr(), logits.data_ptr(), B, h, w, n, float(res_rows), float(res_cols),
+                                        out.data_ptr(), min_key.data_ptr(), _lib.current_stream_ptr()))
+    out._slimb200_min_key = min_key
+    return out
+
+
 def concat2network_output(logits, static_flow, dynamic_flow):
     """``HeadDecoder.concat2network_output`` (``head_decoder.py:36-64``): (B,H,W,8) channels-last."""
     return torch.cat([logits, static_flow, dynamic_flow], dim=1).permute(0, 2, 3, 1)
@@ -274,6 +291,10 @@ class RAFT(nn.Module):
             coords1 = coords1 + dflow
             logits = logits + dlogits
             if self.output_iterations == "last" and it != m.num_iters - 1:
+                continue
+            if FAST_STOCK_OPS and coords1.is_cuda:
+                outs.append(raft_output_fused(coords1 - coords0, logits, ds, self.bev_rows_res_meters_per_fs_pixel,
+                                              self.bev_cols_res_meters_per_fs_pixel))
                 continue
             # RAFT (x, y) pixel flow -> (row, col) metres (raft_mod.py:262-266)
             flow_m = torch.flip(upflow_n(coords1 - coords0, n=ds), dims=[1]) * res

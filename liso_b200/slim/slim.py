@@ -119,7 +119,8 @@ class HeadDecoder(nn.Module):
         dev = o.device
         B, H, W, ch = o.shape
         assert ch == 8, o.shape
-        o = o.float().contiguous()
+        if o.dtype != torch.float32 or not o.is_contiguous():
+            o = o.float().contiguous()
         N = int(valid.shape[1])
         p = _lib.DecodeParams()
         p.batch, p.H, p.W, p.n_points = B, H, W, N
@@ -140,8 +141,9 @@ class HeadDecoder(nn.Module):
         nep = torch.zeros((B,), dtype=torch.uint8, device=dev)
         ws_bytes = lib.slimb200_head_decode_workspace_bytes(C.byref(p))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        min_key = getattr(o, "_slimb200_min_key", None)  # set by RAFT's fused output kernel: spares a pass over `o`
         _lib.check(lib.slimb200_head_decode(
-            o.data_ptr(), filled_u8.data_ptr(), pc.data_ptr(), coors.data_ptr(), valid_u8.data_ptr(), thr_t.data_ptr(),
+            o.data_ptr(), min_key.data_ptr() if min_key is not None else None, filled_u8.data_ptr(), pc.data_ptr(), coors.data_ptr(), valid_u8.data_ptr(), thr_t.data_ptr(),
             C.byref(p), bev.data_ptr(), cls.data_ptr(), pts.data_ptr(), trafo.data_ptr(), nep.data_ptr(),
             ws.data_ptr(), ws.numel(), _lib.current_stream_ptr()))
         clsb = cls.view(torch.bool)

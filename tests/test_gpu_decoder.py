@@ -103,3 +103,29 @@ def test_not_enough_points_branch(cuda):
                   pointwise_valid_mask=valid.to(cuda), filled_pillar_mask=filled.to(cuda), static_aggregation=True)
     assert bool(got.not_enough_points.all()) and bool(ref["not_enough_points"].all())
     assert float((got.static_aggr_trafo.cpu() - ref["static_aggr_trafo"]).abs().max()) <= 2e-4
+
+
+@pytest.mark.parametrize("B,h,w,n", [(1, 8, 8, 8), (2, 32, 32, 8), (1, 80, 80, 8), (1, 23, 17, 4)])
+def test_raft_output_kernel_matches_stock_ops(cuda, B, h, w, n):
+    """SURVEY 8f.2 glue: upflow_n + uplogits_n + flip/scale + concat2network_output (raft_mod.py:216-266) in one kernel
+    vs the stock PyTorch ops; <= 1e-5 relative (interpolation arithmetic may contract differently), min exact."""
+    from liso_b200.slim import raft as R
+    from liso_b200.slim.corr import uplogits_n, upflow_n
+
+    g = torch.Generator().manual_seed(B * 100 + h)
+    flow = (3.0 * torch.randn(B, 2, h, w, generator=g)).to(cuda)
+    logits = (2.0 * torch.randn(B, 4, h, w, generator=g)).to(cuda)
+    rr, rc = 0.875, 0.875
+    res = torch.tensor([rr, rc], device=cuda)[None, :, None, None]
+    flow_m = torch.flip(upflow_n(flow, n=n), dims=[1]) * res
+    ref = R.concat2network_output(uplogits_n(logits, n=n), flow_m, flow_m)
+    got = R.raft_output_fused(flow, logits, n, rr, rc)
+    torch.cuda.synchronize()
+    assert got.shape == ref.shape == (B, h * n, w * n, 8)
+    scale = float(ref.abs().max())
+    assert float((got - ref).abs().max()) <= 1e-5 * scale
+    # the carried minimum == min of the static / dynamic logits the kernel itself wrote
+    key = int(got._slimb200_min_key.item()) & 0xffffffff
+    bits = (key & 0x7fffffff) if key & 0x80000000 else (~key & 0xffffffff)
+    val = np.frombuffer(np.uint32(bits).tobytes(), dtype=np.float32)[0]
+    assert val == float(got[..., 1:3].min())
