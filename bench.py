@@ -360,7 +360,7 @@ def main():
         _lib.K_CORR_GEMM: dict(bytes=B * nf * L.n_cols * 2 + B * (nf + L.n_cols) * 128 * 2, flops=2.0 * B * nf * L.n_cols * 128,
                                what="bf16 pyramid written + bf16 operands read, B samples per launch"),
         _lib.K_DECODE_BEV: dict(bytes=B * H * Wd * (8 * 4 + 1 + 16 * 4 + 3), flops=0,
-                                what="net output + filled mask read, packed BEV row (16 of 20 floats) + class bytes written"),
+                                what="net output + filled mask read, packed 16-float BEV row + class bytes written"),
         _lib.K_DECODE_AGGR: dict(bytes=B * H * Wd * (1 + 16) + B * n_pad * (9 + 12), flops=0,
                                  what="static-aggregated flow written per cell (4 floats) and per point (3 floats)"),
         _lib.K_CORR_LOOKUP: dict(bytes=B * 196 * nf * 4 + B * nf * 4 * 8 * 32, flops=0,

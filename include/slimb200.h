@@ -165,24 +165,25 @@ int slimb200_corr_lookup(const void* pyramid, int32_t pyramid_dtype, const slimb
  * (slim_loss/weighted_pc_alignment.py:10-80, no epsilon) and symmetric_orthogonalization
  * (torch_symm_ortho/__init__.py:68-69: U @ Vh, no determinant fix).  No host synchronisation.
  *
- * bev (batch, H, W, 20) f32, one packed row per cell (the reference's tensors are channel slices of it):
+ * bev (batch, H, W, 16) f32, one packed 64-byte row per cell (the reference's tensors are channel slices of it):
  *    0      disappearing_logit (-100)            1:4    class_logits = static | dynamic | ground logit (masked)
  *    4:7    class_probs = staticness | dynamicness | groundness
  *    7:10   static flow (x, y, 0), masked         10:13  dynamic flow (x, y, 0), masked
- *    13:16  aggregated flow                        16:18  static_aggr_flow      18:20  masked_static_aggr_flow
+ *    13:16  aggregated flow
+ * bev_aggr (batch, H, W, 4) f32, only with static_aggregation: 0:2 static_aggr_flow, 2:4 masked_static_aggr_flow
  * bev_classes (batch, H, W, 3) u8: is_dynamic | is_static | is_ground
  * points (batch, n_points, 14) f32: 0:3 static flow, 3:6 dynamic flow, 6 dynamicness, 7 staticness,
  *    8:11 aggregated flow, 11:14 static_aggr_flow (x, y, 0); all zero for invalid points
  * trafo (batch, 4, 4) f64 row-major, not_enough (batch) u8: only with static_aggregation
  * ---------------------------------------------------------------------------------------- */
-#define SLIMB200_DECODE_BEV_CHANNELS 20
+#define SLIMB200_DECODE_BEV_CHANNELS 16
 #define SLIMB200_DECODE_POINT_CHANNELS 14
 typedef struct {
   int32_t batch, H, W;
   int32_t n_points;            /* padded points per sample */
   int32_t pc_stride;           /* floats per point in `pc` (>= 3) */
   int32_t final_scale;         /* pillar coordinate divisor (u_net.final_scale, 1) */
-  int32_t static_aggregation;  /* 0: skip the weighted Kabsch part (channels 16:20 / 11:14 are zero) */
+  int32_t static_aggregation;  /* 0: skip the weighted Kabsch part (bev_aggr untouched, point channels 11:14 zero) */
   int32_t reserved;
   double ext_min_x, ext_min_y, ext_max_x, ext_max_y; /* bev_extent (head_decoder.py:498-514) */
 } slimb200_decode_params;
@@ -195,8 +196,8 @@ size_t slimb200_head_decode_workspace_bytes(const slimb200_decode_params* p);
 int slimb200_head_decode(const float* net_out, const uint32_t* logit_min_key /* from slimb200_raft_output, or NULL */,
                          const uint8_t* filled, const float* pc, const int32_t* coors,
                          const uint8_t* valid, const float* dyn_threshold, const slimb200_decode_params* p,
-                         float* bev, uint8_t* bev_classes, float* points, double* trafo, uint8_t* not_enough,
-                         void* workspace, size_t workspace_bytes, void* stream);
+                         float* bev, float* bev_aggr, uint8_t* bev_classes, float* points, double* trafo,
+                         uint8_t* not_enough, void* workspace, size_t workspace_bytes, void* stream);
 
 /* SURVEY 8(f).2 glue, once per GRU iteration (raft_mod.py:216-257): upflow_n / uplogits_n (bilinear, align_corners,
  * raft_code/utils.py:50-60), flip (x, y) -> (row, col) and * metres per pixel (raft_mod.py:262-266), and

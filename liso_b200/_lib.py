@@ -64,7 +64,7 @@ class DecodeParams(C.Structure):
     ]
 
 
-DECODE_BEV_CHANNELS, DECODE_POINT_CHANNELS = 20, 14
+DECODE_BEV_CHANNELS, DECODE_POINT_CHANNELS = 16, 14
 
 # every symbol include/slimb200.h declares: (restype, argtypes)
 SYMBOLS = {
@@ -94,7 +94,7 @@ SYMBOLS = {
     "slimb200_head_decode_workspace_bytes": (C.c_size_t, [C.POINTER(DecodeParams)]),
     "slimb200_head_decode": (
         C.c_int,
-        [C.c_void_p] * 7 + [C.POINTER(DecodeParams)] + [C.c_void_p] * 5 + [C.c_void_p, C.c_size_t, C.c_void_p],
+        [C.c_void_p] * 7 + [C.POINTER(DecodeParams)] + [C.c_void_p] * 6 + [C.c_void_p, C.c_size_t, C.c_void_p],
     ),
     "slimb200_raft_output": (
         C.c_int,

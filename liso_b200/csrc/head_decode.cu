@@ -12,7 +12,7 @@
 //
 //   k_decode_min      global min of the live static/dynamic logits (ground logit "off" = min - 100)
 //   k_decode_bev      one thread per BEV cell: masks, 3-way softmax, class decisions, masked flows, aggregated flow;
-//                     one packed (B,H,W,20) row per cell written with 128-bit stores
+//                     one packed (B,H,W,16) row per cell, staged in smem and written back linearly
 //   k_decode_points   one thread per point: gather, weights, fp64 Kabsch moments (block partials, fixed order)
 //   k_kabsch_finalize one CTA per sample: sum the partials, 3x3 one-sided Jacobi SVD in fp64, R = U V^T, T (4x4)
 //   k_decode_aggr     (T - I) * cell centre for every cell and every point
@@ -24,6 +24,7 @@ constexpr int BEV_C = SLIMB200_DECODE_BEV_CHANNELS;    // 20
 constexpr int PT_C = SLIMB200_DECODE_POINT_CHANNELS;   // 14
 constexpr int N_MOM = 33;  // 1 + 3 + 3 + 9 weighted, the same 16 unweighted (for the +1e-7 case), count(w > 0)
 constexpr int PT_THREADS = 256;
+constexpr int PT_PER_THREAD = 8;  // points per thread before the (expensive, fp64) block reduction
 
 __device__ __forceinline__ unsigned f2key(float f) {
   const unsigned b = __float_as_uint(f);
@@ -33,15 +34,27 @@ __device__ __forceinline__ float key2f(unsigned k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
+// Same-address atomics serialise in L2 (~1 per 2 clocks): reduce per CTA and only touch the global word when this
+// CTA can still lower it (the running minimum settles after a handful of CTAs).
+__device__ __forceinline__ void block_min_to_global(unsigned best, unsigned* __restrict__ key) {
+  __shared__ unsigned s_min[8];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, d));
+  if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0 && key) {
+    for (int k = 1; k < (int)(blockDim.x >> 5); ++k) best = min(best, s_min[k]);
+    if (best < *reinterpret_cast<volatile unsigned*>(key)) atomicMin(key, best);
+  }
+}
+
 __global__ void __launch_bounds__(256) k_decode_min(const float* __restrict__ net_out, size_t n_cells, unsigned* __restrict__ out_key) {
   unsigned best = 0xffffffffu;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cells; i += (size_t)gridDim.x * blockDim.x) {
     const float4 lo = __ldg(reinterpret_cast<const float4*>(net_out + i * 8));  // logits 0..3
     best = min(best, min(f2key(lo.y), f2key(lo.z)));
   }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, d));
-  if ((threadIdx.x & 31) == 0) atomicMin(out_key, best);
+  block_min_to_global(best, out_key);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -57,13 +70,11 @@ __global__ void __launch_bounds__(256) k_raft_output(const float* __restrict__ f
                                                      int h, int w, int n, float res_rows, float res_cols,
                                                      float* __restrict__ net_out, unsigned* __restrict__ min_key) {
   const int H = h * n, W = w * n;
-  const size_t total = (size_t)batch * H * W;
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y % H, b = blockIdx.y / H;  // warp-uniform
   unsigned best = 0xffffffffu;
-  if (i < total) {
-    const int x = (int)(i % W);
-    const size_t t = i / W;
-    const int y = (int)(t % H), b = (int)(t / H);
+  float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+  if (x < W) {
     const float rh = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, rw = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
     const float hr = rh * (float)y, wr = rw * (float)x;
     const int h1 = (int)hr, w1 = (int)wr;
@@ -80,14 +91,29 @@ __global__ void __launch_bounds__(256) k_raft_output(const float* __restrict__ f
     const float l0 = interp(lg), l1 = interp(lg + plane), l2 = interp(lg + 2 * plane), l3 = interp(lg + 3 * plane);
     const float fx = __fmul_rn((float)n, interp(fl)), fy = __fmul_rn((float)n, interp(fl + plane));  // upflow_n
     const float f_row = __fmul_rn(fy, res_rows), f_col = __fmul_rn(fx, res_cols);                    // flip, then * res
-    float4* o = reinterpret_cast<float4*>(net_out + i * 8);
-    o[0] = make_float4(l0, l1, l2, l3);
-    o[1] = make_float4(f_row, f_col, f_row, f_col);
+    v0 = make_float4(l0, l1, l2, l3);
+    v1 = make_float4(f_row, f_col, f_row, f_col);
     best = min(f2key(l1), f2key(l2));
   }
+  // a warp owns 32 consecutive pixels = 1 KB of output: exchange so that each store instruction writes 512
+  // contiguous bytes (lane l stores float4 number l resp. 32 + l of the warp's 64)
+  {
+    const int lane = threadIdx.x & 31;
+    const int x0 = x - lane;  // first pixel of the warp (W is a multiple of 32 or the tail is handled per lane)
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, d));
-  if ((threadIdx.x & 31) == 0 && min_key) atomicMin(min_key, best);
+    for (int half = 0; half < 2; ++half) {
+      const int src = half * 16 + (lane >> 1);
+      const bool second = lane & 1;
+      float4 t0, t1;
+      t0.x = __shfl_sync(0xffffffffu, v0.x, src); t0.y = __shfl_sync(0xffffffffu, v0.y, src);
+      t0.z = __shfl_sync(0xffffffffu, v0.z, src); t0.w = __shfl_sync(0xffffffffu, v0.w, src);
+      t1.x = __shfl_sync(0xffffffffu, v1.x, src); t1.y = __shfl_sync(0xffffffffu, v1.y, src);
+      t1.z = __shfl_sync(0xffffffffu, v1.z, src); t1.w = __shfl_sync(0xffffffffu, v1.w, src);
+      const float4 t = second ? t1 : t0;
+      if (x0 + src < W) reinterpret_cast<float4*>(net_out + (((size_t)b * H + y) * W + x0) * 8)[half * 32 + lane] = t;
+    }
+  }
+  block_min_to_global(best, min_key);
 }
 
 struct DecodeArgs {
@@ -99,6 +125,7 @@ struct DecodeArgs {
   const float* thr;
   slimb200_decode_params p;
   float* bev;
+  float* bev_aggr;
   uint8_t* bev_cls;
   float* pts;
   double* trafo;
@@ -110,8 +137,9 @@ struct DecodeArgs {
 
 __global__ void __launch_bounds__(256) k_decode_bev(const DecodeArgs a) {
   // a CTA's 256 cells form one contiguous 20 KB block of the packed output: stage the rows in shared memory
-  // (80-byte pitch: the 128-bit stores of a quarter-warp hit 32 distinct banks) and write them back linearly
-  __shared__ __align__(16) float s_row[256 * BEV_C];
+  // (80-byte smem pitch: the 128-bit stores of a quarter-warp hit 32 distinct banks) and write them back linearly
+  constexpr int S_PITCH = BEV_C + 4;
+  __shared__ __align__(16) float s_row[256 * S_PITCH];
   __shared__ __align__(4) uint8_t s_cls[256 * 3];
   const size_t n_cells = (size_t)a.p.batch * a.p.H * a.p.W;
   const size_t base = (size_t)blockIdx.x * 256;
@@ -138,12 +166,11 @@ __global__ void __launch_bounds__(256) k_decode_bev(const DecodeArgs a) {
     const bool is_gr = !(is_sta || is_dyn);
     const float g = 1.0f - p_gr;
     const float agx = is_sta ? sfx : dfx * g, agy = is_sta ? sfy : dfy * g, agz = is_sta ? 0.f : 0.f * g;
-    float4* o = reinterpret_cast<float4*>(s_row + threadIdx.x * BEV_C);
+    float4* o = reinterpret_cast<float4*>(s_row + threadIdx.x * S_PITCH);
     o[0] = make_float4(-100.f, l_st, l_dy, l_gr);      // disappearing | class_logits (static, dynamic, ground)
     o[1] = make_float4(p_st, p_dy, p_gr, sfx);         // class_probs | static3.x
     o[2] = make_float4(sfy, 0.f, dfx, dfy);            // static3.yz | dynamic3.xy
     o[3] = make_float4(0.f, agx, agy, agz);            // dynamic3.z | aggregated3
-    o[4] = make_float4(0.f, 0.f, 0.f, 0.f);            // static_aggr_flow: k_decode_aggr fills it in
     s_cls[threadIdx.x * 3 + 0] = is_dyn;
     s_cls[threadIdx.x * 3 + 1] = is_sta;
     s_cls[threadIdx.x * 3 + 2] = is_gr;
@@ -152,7 +179,8 @@ __global__ void __launch_bounds__(256) k_decode_bev(const DecodeArgs a) {
   const int n_here = (int)min((size_t)256, n_cells - base);
   float4* dst = reinterpret_cast<float4*>(a.bev + base * BEV_C);
   const float4* src = reinterpret_cast<const float4*>(s_row);
-  for (int k = threadIdx.x; k < n_here * (BEV_C / 4); k += 256) dst[k] = src[k];
+  for (int k = threadIdx.x; k < n_here * (BEV_C / 4); k += 256) dst[k] = src[(k >> 2) * (S_PITCH / 4) + (k & 3)];
+  static_assert(BEV_C == 16, "row copy assumes 4 float4 per cell");
   if (n_here == 256) {
     if (threadIdx.x < 192) reinterpret_cast<uint32_t*>(a.bev_cls + base * 3)[threadIdx.x] = reinterpret_cast<const uint32_t*>(s_cls)[threadIdx.x];
   } else {
@@ -164,11 +192,12 @@ __global__ void __launch_bounds__(PT_THREADS) k_decode_points(const DecodeArgs a
   __shared__ double s_part[PT_THREADS / 32][N_MOM];
   const int b = blockIdx.y;
   const int n = a.p.n_points;
-  const int j = blockIdx.x * PT_THREADS + threadIdx.x;
   double mom[N_MOM];
 #pragma unroll
   for (int k = 0; k < N_MOM; ++k) mom[k] = 0.0;
-  if (j < n) {
+  for (int it = 0; it < PT_PER_THREAD; ++it) {
+    const int j = (blockIdx.x * PT_PER_THREAD + it) * PT_THREADS + threadIdx.x;
+    if (j >= n) break;
     const size_t pi = (size_t)b * n + j;
     const bool valid = a.valid[pi] != 0;
     float out[11];
@@ -178,37 +207,37 @@ __global__ void __launch_bounds__(PT_THREADS) k_decode_points(const DecodeArgs a
       const int r = a.coors[pi * 2] / a.p.final_scale, c = a.coors[pi * 2 + 1] / a.p.final_scale;
       const size_t cell = ((size_t)b * a.p.H + r) * a.p.W + c;
       const float* row = a.bev + cell * BEV_C;
-      const float p_st = __ldg(row + 4), p_dy = __ldg(row + 5);
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        out[k] = __ldg(row + 7 + k);        // static3
-        out[3 + k] = __ldg(row + 10 + k);   // dynamic3
-        out[8 + k] = __ldg(row + 13 + k);   // aggregated3
-      }
+      const float4 q1 = __ldg(reinterpret_cast<const float4*>(row + 4));    // staticness dynamicness groundness static.x
+      const float4 q2 = __ldg(reinterpret_cast<const float4*>(row + 8));    // static.y static.z dynamic.x dynamic.y
+      const float4 q3 = __ldg(reinterpret_cast<const float4*>(row + 12));   // dynamic.z aggregated.xyz
+      const float p_st = q1.x, p_dy = q1.y;
+      out[0] = q1.w; out[1] = q2.x; out[2] = q2.y;      // static3
+      out[3] = q2.z; out[4] = q2.w; out[5] = q3.x;      // dynamic3
       out[6] = p_dy;
       out[7] = p_st;
+      out[8] = q3.y; out[9] = q3.z; out[10] = q3.w;     // aggregated3
       if (a.p.static_aggregation) {
-        const float w = a.filled[cell] ? p_st : 0.f;  // staticness * filled (head_decoder.py -> static_aggregation.py:66-71)
+        const float w = a.filled[cell] ? p_st : 0.f;  // staticness * filled (static_aggregation.py:66-71)
         const float* q = a.pc + pi * a.p.pc_stride;
         const float x0 = q[0], y0 = q[1], z0 = q[2];
         const float x1 = x0 + out[0], y1 = y0 + out[1], z1 = z0 + out[2];  // fp32 add like the reference
         const double p0[3] = {x0, y0, z0}, p1[3] = {x1, y1, z1};
         const double wd = (double)w;
-        mom[0] = wd;
-        mom[16] = 1.0;
+        mom[0] += wd;
+        mom[16] += 1.0;
 #pragma unroll
         for (int u = 0; u < 3; ++u) {
-          mom[1 + u] = wd * p0[u];
-          mom[4 + u] = wd * p1[u];
-          mom[17 + u] = p0[u];
-          mom[20 + u] = p1[u];
+          mom[1 + u] += wd * p0[u];
+          mom[4 + u] += wd * p1[u];
+          mom[17 + u] += p0[u];
+          mom[20 + u] += p1[u];
 #pragma unroll
           for (int v = 0; v < 3; ++v) {
-            mom[7 + u * 3 + v] = wd * p1[u] * p0[v];  // S[u][v] = sum w * y_u * x_v
-            mom[23 + u * 3 + v] = p1[u] * p0[v];
+            mom[7 + u * 3 + v] += wd * p1[u] * p0[v];  // S[u][v] = sum w * y_u * x_v
+            mom[23 + u * 3 + v] += p1[u] * p0[v];
           }
         }
-        mom[32] = w > 0.f ? 1.0 : 0.0;
+        mom[32] += w > 0.f ? 1.0 : 0.0;
       }
     }
     float* o = a.pts + pi * PT_C;
@@ -337,27 +366,31 @@ __global__ void __launch_bounds__(64) k_kabsch_finalize(const DecodeArgs a) {
 // static_aggr_flow of a cell: ((T - I) [xc, yc, 0, 1])[:2] in fp64, then float (static_aggregation.py:88-103);
 // cell centres as head_decoder.py:498-514: (idx + 0.5) / shape * (max - min) + min
 __device__ __forceinline__ float2 aggr_flow_of_cell(const double* __restrict__ T, const slimb200_decode_params& p, int r, int c) {
-  const double xc = ((double)r + 0.5) / (double)p.H * (p.ext_max_x - p.ext_min_x) + p.ext_min_x;
-  const double yc = ((double)c + 0.5) / (double)p.W * (p.ext_max_y - p.ext_min_y) + p.ext_min_y;
+  // (the reference divides by the shape; multiplying by the fp64 reciprocal differs by <= 1 ulp of fp64, invisible
+  // after the cast to float)
+  const double xc = ((double)r + 0.5) * (1.0 / (double)p.H) * (p.ext_max_x - p.ext_min_x) + p.ext_min_x;
+  const double yc = ((double)c + 0.5) * (1.0 / (double)p.W) * (p.ext_max_y - p.ext_min_y) + p.ext_min_y;
   const double fx = (T[0] - 1.0) * xc + T[1] * yc + T[3];
   const double fy = T[4] * xc + (T[5] - 1.0) * yc + T[7];
   return make_float2((float)fx, (float)fy);
 }
 
-__global__ void __launch_bounds__(256) k_decode_aggr(const DecodeArgs a) {
-  const size_t n_cells = (size_t)a.p.batch * a.p.H * a.p.W;
-  const size_t n_pts = (size_t)a.p.batch * a.p.n_points;
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_cells) {
-    const int c = (int)(i % a.p.W);
-    const size_t t = i / a.p.W;
-    const int r = (int)(t % a.p.H), b = (int)(t / a.p.H);
+// grid.y < batch * H: one BEV row per blockIdx.y; the remaining blockIdx.y values cover the points
+__global__ void __launch_bounds__(256) k_decode_aggr(const DecodeArgs a, int point_rows) {
+  const int rows = a.p.batch * a.p.H;
+  if ((int)blockIdx.y < rows) {
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= a.p.W) return;
+    const int r = blockIdx.y % a.p.H, b = blockIdx.y / a.p.H;
+    const size_t i = (size_t)blockIdx.y * a.p.W + c;
     const float2 f = aggr_flow_of_cell(a.trafo + (size_t)b * 16, a.p, r, c);
     const bool filled = a.filled[i] != 0;
-    *reinterpret_cast<float4*>(a.bev + i * BEV_C + 16) = make_float4(f.x, f.y, filled ? f.x : 0.f, filled ? f.y : 0.f);
-  } else if (i - n_cells < n_pts) {
-    const size_t pi = i - n_cells;
-    const int b = (int)(pi / a.p.n_points);
+    reinterpret_cast<float4*>(a.bev_aggr)[i] = make_float4(f.x, f.y, filled ? f.x : 0.f, filled ? f.y : 0.f);
+  } else {
+    const size_t n_pts = (size_t)a.p.batch * a.p.n_points;
+    const size_t pi = ((size_t)(blockIdx.y - rows) * gridDim.x + blockIdx.x) * 256 + threadIdx.x;
+    if (pi >= n_pts) return;
+    const int b = (int)(pi / (size_t)a.p.n_points);
     float2 f = make_float2(0.f, 0.f);
     if (a.valid[pi]) {
       const int r = a.coors[pi * 2] / a.p.final_scale, c = a.coors[pi * 2 + 1] / a.p.final_scale;
@@ -370,7 +403,9 @@ __global__ void __launch_bounds__(256) k_decode_aggr(const DecodeArgs a) {
   }
 }
 
-int blocks_per_sample(const slimb200_decode_params* p) { return (p->n_points + PT_THREADS - 1) / PT_THREADS; }
+int blocks_per_sample(const slimb200_decode_params* p) {
+  return (p->n_points + PT_THREADS * PT_PER_THREAD - 1) / (PT_THREADS * PT_PER_THREAD);
+}
 
 }  // namespace
 
@@ -388,22 +423,23 @@ extern "C" int slimb200_raft_output(const float* flow, const float* logits, int3
   if (reinterpret_cast<uintptr_t>(net_out) & 15) return SLIMB200_E_ALIGNMENT;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (min_key) SLIMB200_CUDA_TRY(cudaMemsetAsync(min_key, 0xff, sizeof(uint32_t), stream));
-  const size_t total = (size_t)batch * h * n * w * n;
+  if ((long long)batch * h * n > 0x7fffffffLL) return SLIMB200_E_UNSUPPORTED;
+  dim3 grid((w * n + 255) / 256, batch * h * n);
   SLIMB200_LAUNCH(SLIMB200_K_RAFT_OUTPUT, stream,
-                  (k_raft_output<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(flow, logits, batch, h, w, n, res_rows, res_cols,
-                                                                                     net_out, min_key)));
+                  (k_raft_output<<<grid, 256, 0, stream>>>(flow, logits, batch, h, w, n, res_rows, res_cols, net_out, min_key)));
   return SLIMB200_OK;
 }
 
 extern "C" int slimb200_head_decode(const float* net_out, const uint32_t* logit_min_key, const uint8_t* filled, const float* pc,
                                     const int32_t* coors, const uint8_t* valid, const float* dyn_threshold,
                                     const slimb200_decode_params* p,
-                                    float* bev, uint8_t* bev_classes, float* points, double* trafo, uint8_t* not_enough,
-                                    void* workspace, size_t workspace_bytes, void* stream_) {
+                                    float* bev, float* bev_aggr, uint8_t* bev_classes, float* points, double* trafo,
+                                    uint8_t* not_enough, void* workspace, size_t workspace_bytes, void* stream_) {
   if (!net_out || !filled || !dyn_threshold || !p || !bev || !bev_classes || !workspace) return SLIMB200_E_INVALID;
   if (p->batch < 1 || p->H < 1 || p->W < 1 || p->n_points < 0 || p->final_scale < 1) return SLIMB200_E_INVALID;
   if (p->n_points > 0 && (!pc || !coors || !valid || !points || p->pc_stride < 3)) return SLIMB200_E_INVALID;
-  if (p->static_aggregation && (!trafo || !not_enough)) return SLIMB200_E_INVALID;
+  if (p->static_aggregation && (!trafo || !not_enough || !bev_aggr)) return SLIMB200_E_INVALID;
+  if (reinterpret_cast<uintptr_t>(bev_aggr) & 15) return SLIMB200_E_ALIGNMENT;
   if (workspace_bytes < slimb200_head_decode_workspace_bytes(p)) return SLIMB200_E_WORKSPACE;
   if ((reinterpret_cast<uintptr_t>(net_out) & 15) || (reinterpret_cast<uintptr_t>(bev) & 15) ||
       (reinterpret_cast<uintptr_t>(workspace) & 255))
@@ -418,6 +454,7 @@ extern "C" int slimb200_head_decode(const float* net_out, const uint32_t* logit_
   a.thr = dyn_threshold;
   a.p = *p;
   a.bev = bev;
+  a.bev_aggr = bev_aggr;
   a.bev_cls = bev_classes;
   a.pts = points;
   a.trafo = trafo;
@@ -442,8 +479,11 @@ extern "C" int slimb200_head_decode(const float* net_out, const uint32_t* logit_
   }
   if (p->static_aggregation) {
     SLIMB200_LAUNCH(SLIMB200_K_KABSCH, stream, (k_kabsch_finalize<<<p->batch, 64, 0, stream>>>(a)));
-    const size_t total = n_cells + (size_t)p->batch * p->n_points;
-    SLIMB200_LAUNCH(SLIMB200_K_DECODE_AGGR, stream, (k_decode_aggr<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a)));
+    const unsigned gx = (unsigned)((p->W + 255) / 256);
+    const size_t n_pts = (size_t)p->batch * p->n_points;
+    const int point_rows = (int)((n_pts + (size_t)gx * 256 - 1) / ((size_t)gx * 256));
+    dim3 g(gx, (unsigned)(p->batch * p->H + point_rows));
+    SLIMB200_LAUNCH(SLIMB200_K_DECODE_AGGR, stream, (k_decode_aggr<<<g, 256, 0, stream>>>(a, point_rows)));
   }
   return SLIMB200_OK;
 }

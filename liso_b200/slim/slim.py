@@ -135,6 +135,7 @@ class HeadDecoder(nn.Module):
         filled_u8 = filled.contiguous().view(torch.uint8)
         thr_t = torch.as_tensor(thr, dtype=torch.float32, device=dev).reshape(1)
         bev = torch.empty((B, H, W, _lib.DECODE_BEV_CHANNELS), dtype=torch.float32, device=dev)
+        aggr = torch.empty((B, H, W, 4), dtype=torch.float32, device=dev) if static_aggregation else None
         cls = torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev)
         pts = torch.empty((B, N, _lib.DECODE_POINT_CHANNELS), dtype=torch.float32, device=dev)
         trafo = torch.empty((B, 4, 4), dtype=torch.float64, device=dev)
@@ -144,7 +145,8 @@ class HeadDecoder(nn.Module):
         min_key = getattr(o, "_slimb200_min_key", None)  # set by RAFT's fused output kernel: spares a pass over `o`
         _lib.check(lib.slimb200_head_decode(
             o.data_ptr(), min_key.data_ptr() if min_key is not None else None, filled_u8.data_ptr(), pc.data_ptr(), coors.data_ptr(), valid_u8.data_ptr(), thr_t.data_ptr(),
-            C.byref(p), bev.data_ptr(), cls.data_ptr(), pts.data_ptr(), trafo.data_ptr(), nep.data_ptr(),
+            C.byref(p), bev.data_ptr(), aggr.data_ptr() if aggr is not None else None, cls.data_ptr(), pts.data_ptr(),
+            trafo.data_ptr(), nep.data_ptr(),
             ws.data_ptr(), ws.numel(), _lib.current_stream_ptr()))
         clsb = cls.view(torch.bool)
         md = AttrDict()
@@ -162,8 +164,8 @@ class HeadDecoder(nn.Module):
         ret.dense_maps = AttrDict(aggregated_flow=bev[..., 13:16], static_flow=bev[..., 7:10])
         ret.dynamicness_threshold = thr
         if static_aggregation:
-            md.static_aggr_flow = bev[..., 16:18]
-            md.masked_static_aggr_flow = bev[..., 18:20]
+            md.static_aggr_flow = aggr[..., 0:2]
+            md.masked_static_aggr_flow = aggr[..., 2:4]
             ret.static_aggr_flow = pts[..., 11:14]
             ret.static_aggr_trafo = trafo
             ret.not_enough_points = nep.view(torch.bool)
