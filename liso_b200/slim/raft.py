@@ -42,6 +42,18 @@ def _autocast_param(t, dtype):
     return hit
 
 
+def _cat_params(ts):
+    """dim-0 concatenation of parameters, cached (inference only; keyed by storage + version)."""
+    key = tuple((t.data_ptr(), t._version) for t in ts)
+    hit = _PARAM_CAST_CACHE.get(key)
+    if hit is None:
+        hit = torch.cat([t.detach() for t in ts], dim=0)
+        if hit.dim() == 4 and ts[0].is_contiguous(memory_format=torch.channels_last) and not ts[0].is_contiguous():
+            hit = hit.contiguous(memory_format=torch.channels_last)
+        _PARAM_CAST_CACHE[key] = hit
+    return hit
+
+
 def conv_relu(conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
     if FAST_STOCK_OPS and x.is_cuda and conv.padding_mode == "zeros" and not torch.is_grad_enabled():
         w, b = conv.weight, conv.bias
@@ -167,8 +179,14 @@ class ConvGRU(nn.Module):
 
     def forward(self, h, x):
         hx = torch.cat([h, x], dim=1)
-        z = torch.sigmoid(self.convz(hx))
-        r = torch.sigmoid(self.convr(hx))
+        if FAST_STOCK_OPS and hx.is_cuda and not torch.is_grad_enabled():
+            # the update and reset gates read the same input: one 192-channel convolution instead of two
+            w = _cat_params((self.convz.weight, self.convr.weight))
+            b = _cat_params((self.convz.bias, self.convr.bias))
+            z, r = torch.sigmoid(F.conv2d(hx, w, b, padding=1)).split(self.convz.out_channels, dim=1)
+        else:
+            z = torch.sigmoid(self.convz(hx))
+            r = torch.sigmoid(self.convr(hx))
         q = torch.tanh(self.convq(torch.cat([r * h, x], dim=1)))
         return (1 - z) * h + z * q
 
