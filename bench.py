@@ -161,6 +161,9 @@ def main():
                          "decoded, with the weighted-Kabsch static aggregation (12 decodes per pair); "
                          "last: the export shortcut -- only the final iteration is decoded, no aggregation "
                          "(identical exported tensors); the other mode is reported beside the headline as `other_mode`")
+    ap.add_argument("--write-npz", default=None, metavar="DIR",
+                    help="also time the export loop WITH the per-pair .npz files written by AsyncNpzWriter (SURVEY 8f.3); "
+                         "reported as `export_with_writer`, never as the headline")
     ap.add_argument("--memory-format", default="channels_last", choices=["channels_last", "contiguous"],
                     help="memory format of the canvas our encoder emits and of the stock convs that consume it")
     ap.add_argument("--profile-one-step", action="store_true",
@@ -334,6 +337,28 @@ def main():
     ms_other_e2e /= max(3, args.steps // 2)
     set_mode(args.decode)
 
+    writer_line = None
+    if args.write_npz and rank == 0:
+        import shutil
+
+        from liso_b200.slim.export import AsyncNpzWriter
+
+        out_dir = os.path.join(args.write_npz, "rank%d" % rank)
+        shutil.rmtree(out_dir, ignore_errors=True)
+        thr_host = float(model.moving_dynamicness_threshold.value())
+        n_batches = max(3, args.steps)
+        t0 = time.perf_counter()
+        wr = AsyncNpzWriter(out_dir, W["bev_range_m"])
+        pipeline.run(((h0, h1) for _ in range(n_batches)),
+                     lambda j, host: wr.submit_batch(["%06d_%d" % (j, b) for b in range(args.batch)], host, thr_host))
+        n_files = wr.close()
+        dt = time.perf_counter() - t0
+        mb = sum(os.path.getsize(os.path.join(out_dir, f)) for f in os.listdir(out_dir)) / 1e6
+        writer_line = {"value": n_files / dt, "unit": UNIT, "files": n_files, "compressed_mb_per_pair": mb / max(1, n_files),
+                       "writer_threads": wr.pool._max_workers, "what": "ExportPipeline + AsyncNpzWriter (np.savez_compressed, "
+                       "reference schema), wall clock incl. the final flush"}
+        shutil.rmtree(out_dir, ignore_errors=True)
+
     tot = reduce_counters({"pairs": float(args.batch * args.steps), "ms_res_max": ms_res, "ms_e2e_max": ms_e2e,
                            "launches": float(launches), "ms_other_max": ms_other, "ms_other_e2e_max": ms_other_e2e},
                           device=dev)
@@ -418,6 +443,8 @@ def main():
         valid = s0["pcl_ta"]["pcl_is_valid"][0]
         epe = (pf[-1].static_flow[0].cpu() - of[-1]["pointwise_static_flow"][0]).norm(dim=-1)[valid]
         line["parity"] = {"per_point_static_flow_aee_m_vs_oracle": float(epe.mean()), "max_m": float(epe.max()), "limit_m": 0.01}
+    if writer_line:
+        line["export_with_writer"] = writer_line
     out.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -48,6 +48,75 @@ def save_npz(target_file: str, arrays: Dict[str, torch.Tensor], bev_range_m, ski
     return True
 
 
+class AsyncNpzWriter:
+    """the reference writes one ``np.savez_compressed`` file per pair on the thread that drives the
+    GPU (``experiment.py:459-471``); at hundreds of pairs/s zlib would be the bottleneck, so the files are written
+    by a pool of worker threads (zlib releases the GIL) while the GPU computes the next batches.  Same schema:
+    ``static_threshold``, ``bev_raw_flow_{t0_t1,t1_t0}`` (H,W,2) f32, ``bev_dynamicness_{t0_t1,t1_t0}`` (H,W) f32,
+    ``bev_range_m`` -- what ``torch_dataset_commons.py:619-675`` reads back.
+
+    ``submit`` copies the arrays it is given (the caller's pinned buffers are reused) and returns immediately;
+    at most ``max_pending`` files are in flight (back-pressure instead of unbounded memory)."""
+
+    KEYS = ("bev_raw_flow_t0_t1", "bev_raw_flow_t1_t0", "bev_dynamicness_t0_t1", "bev_dynamicness_t1_t0")
+
+    def __init__(self, target_dir: str, bev_range_m, workers: Optional[int] = None, max_pending: int = 64,
+                 skip_existing: bool = False, compressed: bool = True):
+        from concurrent.futures import ThreadPoolExecutor
+
+        self.target_dir = target_dir
+        self.bev_range_m = np.asarray(bev_range_m)
+        self.skip_existing = skip_existing
+        self.compressed = compressed
+        self.max_pending = max_pending
+        self.pool = ThreadPoolExecutor(max_workers=workers or max(1, (os.cpu_count() or 2) - 1))
+        self.pending: List = []
+        self.written = 0
+        os.makedirs(target_dir, exist_ok=True)
+
+    def target_file(self, sample_id: str) -> str:
+        return os.path.join(self.target_dir, sample_id + ".npz")  # sample ids may contain sub-folders (waymo)
+
+    def _write(self, path: str, arrays: Dict[str, np.ndarray]) -> str:
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        tmp = path + ".tmp.npz"
+        (np.savez_compressed if self.compressed else np.savez)(tmp, **arrays)
+        os.replace(tmp, path)  # never leave a truncated file behind
+        return path
+
+    def submit(self, sample_id: str, flow_fw, flow_bw, dyn_fw, dyn_bw, static_threshold) -> bool:
+        """Arrays of ONE pair (numpy or CPU tensors).  Returns False when the file exists and is skipped."""
+        path = self.target_file(sample_id)
+        if self.skip_existing and os.path.exists(path):
+            return False
+        arrays = {"static_threshold": np.array(float(static_threshold), dtype=np.float32)}
+        for k, v in zip(self.KEYS, (flow_fw, flow_bw, dyn_fw, dyn_bw)):
+            arrays[k] = np.array(v.numpy() if torch.is_tensor(v) else v, dtype=np.float32, copy=True)
+        arrays["bev_range_m"] = self.bev_range_m
+        while len(self.pending) >= self.max_pending:
+            self.pending.pop(0).result()
+            self.written += 1
+        self.pending.append(self.pool.submit(self._write, path, arrays))
+        return True
+
+    def submit_batch(self, sample_ids, host_tensors, static_threshold) -> int:
+        """``host_tensors`` as handed to ``ExportPipeline``'s consume callback: batched
+        [flow_fw (B,H,W,2), flow_bw, dyn_fw (B,H,W), dyn_bw]."""
+        n = 0
+        for b, sid in enumerate(sample_ids):
+            n += bool(self.submit(sid, host_tensors[0][b], host_tensors[1][b], host_tensors[2][b], host_tensors[3][b],
+                                  static_threshold))
+        return n
+
+    def close(self) -> int:
+        for f in self.pending:
+            f.result()
+            self.written += 1
+        self.pending = []
+        self.pool.shutdown(wait=True)
+        return self.written
+
+
 def reduce_counters(local: Dict[str, float], device: Optional[torch.device] = None) -> Dict[str, float]:
     """Sum per-rank counters over the default process group (no-op without one).
 

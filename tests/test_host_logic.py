@@ -142,3 +142,35 @@ def test_world_size_2_gather_gloo(tmp_path):
     for r in range(2):
         tot = torch.load(os.path.join(str(tmp_path), "r%d.pt" % r))
         assert tot == single
+
+
+def test_async_npz_writer_schema_matches_reference_consumer(tmp_path):
+    """files written off the critical path have the reference's schema (experiment.py:391-402,459-471) and
+    can be consumed like torch_dataset_commons.py:619-675 does (np.load, bev_range_m, bev_raw_flow_* [H,W,2])."""
+    from liso_b200.slim.export import AsyncNpzWriter
+
+    rng = np.random.default_rng(0)
+    H, W, B = 32, 24, 3
+    host = [torch.from_numpy(rng.normal(size=(B, H, W, 2)).astype(np.float32)),
+            torch.from_numpy(rng.normal(size=(B, H, W, 2)).astype(np.float32)),
+            torch.from_numpy(rng.uniform(size=(B, H, W)).astype(np.float32)),
+            torch.from_numpy(rng.uniform(size=(B, H, W)).astype(np.float32))]
+    keep = [t.clone() for t in host]
+    w = AsyncNpzWriter(str(tmp_path), bev_range_m=(70.0, 70.0), workers=2, max_pending=2)
+    ids = ["seq_a/000001", "seq_a/000002", "000003"]
+    assert w.submit_batch(ids, host, torch.tensor(0.5)) == 3
+    for t in host:  # the caller reuses its (pinned) buffers right away
+        t.zero_()
+    assert w.close() == 3
+    for b, sid in enumerate(ids):
+        f = np.load(tmp_path / (sid + ".npz"), allow_pickle=True)
+        assert set(f.files) == {"static_threshold", "bev_raw_flow_t0_t1", "bev_raw_flow_t1_t0", "bev_dynamicness_t0_t1",
+                                "bev_dynamicness_t1_t0", "bev_range_m"}
+        assert f["bev_raw_flow_t0_t1"].shape == (H, W, 2) and f["bev_raw_flow_t0_t1"].dtype == np.float32
+        assert f["bev_dynamicness_t1_t0"].shape == (H, W)
+        assert np.array_equal(f["bev_raw_flow_t0_t1"], keep[0][b].numpy()) and np.array_equal(f["bev_dynamicness_t1_t0"], keep[3][b].numpy())
+        assert float(f["static_threshold"]) == 0.5 and f["static_threshold"].shape == ()
+        grid_size = np.append(f["bev_raw_flow_t0_t1"].shape[:2], np.array(1))  # what the consumer derives
+        assert tuple(grid_size) == (H, W, 1) and np.allclose(f["bev_range_m"], (70.0, 70.0))
+    w2 = AsyncNpzWriter(str(tmp_path), bev_range_m=(70.0, 70.0), workers=1, skip_existing=True)
+    assert w2.submit_batch(ids, keep, 0.5) == 0 and w2.close() == 0
