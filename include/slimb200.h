@@ -64,6 +64,12 @@ typedef struct {
   int32_t bn_training;    /* 0: running stats; 1: batch statistics (+ running-stat update) */
   float bn_eps;           /* 1e-3 */
   float bn_momentum;      /* 0.01 */
+  int32_t ground_filter;  /* 1: drop ground points with the cone rule below before voxelising, i.e. take the RAW scan
+                             ("pcl_full_w_ground") and behave as if "pcl_full_no_ground" had been passed
+                             (torch_dataset_commons.py:133-146, 1164-1184); point order and hence pillar order are the
+                             same as for the compacted cloud */
+  float ground_cone_z;    /* cone_z_threshold__m = data.ground_height_map.ground_threshold (liso_config.yml:113-114) */
+  float ground_cone_tan;  /* tan(cone_angle__deg = 0.8 deg) as float32 */
   int32_t canvas_layout;  /* SLIMB200_CANVAS_NCHW (the reference's contiguous layout) or SLIMB200_CANVAS_NHWC
                              (same logical tensor in channels-last memory format, what cuDNN's convs consume);
                              NHWC needs c_out % 4 == 0 */
@@ -105,6 +111,30 @@ int slimb200_pillar_encode(const float* const* points /*host[batch]*/,
 int slimb200_pillar_coors_f64(const float* pts, int64_t n, int32_t c_in, double range_x,
                               double range_y, int32_t grid_x, int32_t grid_y, float z_min,
                               float z_max, int32_t* coors, uint8_t* valid, void* stream);
+
+/* dataset-side pre-processing on the GPU (raw scan in, decoder inputs out).  Replaces
+ * infer_ground_label_using_cone + remove_ground_points_from_sample + voxelize_sample/voxelize_pcl + pillarize_bev
+ * (torch_dataset_commons.py:133-146, 975-987, 1140-1184; analyse_boxes.py:6-26) and the NaN / -1 / mask padding of
+ * the collate function (torch_dataset_commons.py:380-401).
+ *   scans[b]          device (n_points[b], c_in) f32 raw scan      ground_labels[b] optional device u8 (n_points[b])
+ *   pcl_ta            device (batch, cap, c_in) f32: the non-ground, in-range points in scan order, then NaN
+ *   pillar_coors      device (batch, cap, 2) i32 (then -1)          valid   device (batch, cap) u8
+ *   counts            device (batch) i32: kept points per sample (stays on the device; nothing is synchronised) */
+typedef struct {
+  float cone_z_threshold; /* ground rule, evaluated in float32: z < cone_z_threshold + cone_tan * sqrt(x^2 + y^2) */
+  float cone_tan;
+  double range_x, range_y; /* a12: bev_range_m */
+  int32_t grid_x, grid_y;  /* img_grid_size */
+  float z_min, z_max;      /* pillar_height_range_m, strict */
+  int32_t c_in;
+  int32_t reserved;
+} slimb200_preprocess_params;
+
+size_t slimb200_preprocess_workspace_bytes(int32_t batch, int32_t cap, const slimb200_preprocess_params* p);
+int slimb200_preprocess_points(const float* const* scans /*host[batch]*/, const uint8_t* const* ground_labels /*host[batch] or NULL*/,
+                               const int32_t* n_points /*host[batch]*/, int32_t batch, int32_t cap,
+                               const slimb200_preprocess_params* p, float* pcl_ta, int32_t* pillar_coors, uint8_t* valid,
+                               int32_t* counts, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Stage 2: all-pairs correlation pyramid + lookup.  Replaces CorrBlock.__init__ / CorrBlock.corr
@@ -237,6 +267,10 @@ enum {
   SLIMB200_K_KABSCH,
   SLIMB200_K_DECODE_AGGR,
   SLIMB200_K_RAFT_OUTPUT,
+  SLIMB200_K_PRE_COUNT,
+  SLIMB200_K_PRE_SCAN,
+  SLIMB200_K_PRE_SCATTER,
+  SLIMB200_K_PRE_PAD,
   SLIMB200_N_KERNELS
 };
 int slimb200_profile_begin(void);

@@ -36,6 +36,9 @@ class PillarParams(C.Structure):
         ("bn_training", C.c_int32),
         ("bn_eps", C.c_float),
         ("bn_momentum", C.c_float),
+        ("ground_filter", C.c_int32),
+        ("ground_cone_z", C.c_float),
+        ("ground_cone_tan", C.c_float),
         ("canvas_layout", C.c_int32),
     ]
 
@@ -53,6 +56,14 @@ class CorrLayout(C.Structure):
         ("n_cols", C.c_int32),
         ("pitch", C.c_int32),
         ("n_panels", C.c_int32),
+    ]
+
+
+class PreprocessParams(C.Structure):
+    _fields_ = [
+        ("cone_z_threshold", C.c_float), ("cone_tan", C.c_float), ("range_x", C.c_double), ("range_y", C.c_double),
+        ("grid_x", C.c_int32), ("grid_y", C.c_int32), ("z_min", C.c_float), ("z_max", C.c_float), ("c_in", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -91,6 +102,12 @@ SYMBOLS = {
         C.c_int,
         [C.c_void_p, C.c_int32, C.POINTER(CorrLayout), C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p],
     ),
+    "slimb200_preprocess_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.POINTER(PreprocessParams)]),
+    "slimb200_preprocess_points": (
+        C.c_int,
+        [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.POINTER(PreprocessParams)]
+        + [C.c_void_p] * 4 + [C.c_void_p, C.c_size_t, C.c_void_p],
+    ),
     "slimb200_head_decode_workspace_bytes": (C.c_size_t, [C.POINTER(DecodeParams)]),
     "slimb200_head_decode": (
         C.c_int,
@@ -108,7 +125,7 @@ SYMBOLS = {
     "slimb200_launch_count": (C.c_int64, [C.c_int32]),
     "slimb200_kernel_name": (C.c_char_p, [C.c_int32]),
 }
-N_KERNELS = 19
+N_KERNELS = 23
 K_TILE_ENCODE, K_PILLAR_NHWC, K_FEAT_TRANSPOSE, K_FEAT_PACK, K_CORR_GEMM, K_CORR_LOOKUP = 6, 7, 8, 9, 10, 11
 K_DECODE_BEV, K_DECODE_POINTS, K_DECODE_AGGR, K_RAFT_OUTPUT = 14, 15, 17, 18
 CANVAS_NCHW, CANVAS_NHWC = 0, 1

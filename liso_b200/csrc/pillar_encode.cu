@@ -114,7 +114,12 @@ __global__ void __launch_bounds__(PT_BLOCK) k_point_keys(const PillarArgs a) {
   if (i >= a.n_pts[b]) return;
   const float4 pt = load_point(a.pts[b], i, a.p.c_in);
   int xi, yi;
-  const bool ok = pillar_cell(a.p, pt.x, pt.y, pt.z, xi, yi);
+  bool ok = pillar_cell(a.p, pt.x, pt.y, pt.z, xi, yi);
+  if (a.p.ground_filter) {
+    // raw scan in: drop what the reference's dataset drops (cone rule in float32, torch_dataset_commons.py:133-146)
+    const float d = sqrtf(__fadd_rn(__fmul_rn(pt.x, pt.x), __fmul_rn(pt.y, pt.y)));
+    ok = ok && !(pt.z < __fadd_rn(a.p.ground_cone_z, __fmul_rn(a.p.ground_cone_tan, d)));
+  }
   int key = -1;
   if (ok) {
     const int tile = (b * a.tiles_x + xi / TILE_R) * a.tiles_y + yi / TILE_C;

@@ -96,6 +96,12 @@ class PointsPillarFeatureNetWrapper(nn.Module):
         if canvas_memory_format not in ("channels_last", "contiguous"):
             raise ValueError("canvas_memory_format must be 'channels_last' or 'contiguous'")
         self.canvas_memory_format = canvas_memory_format
+        # ground rule applied inside the encoder when it is handed RAW scans (forward(..., raw_scan=True)):
+        # cone_z_threshold__m = data.ground_height_map.ground_threshold, cone angle 0.8 deg
+        # (torch_dataset_commons.py:133-146, 1171-1174)
+        ghm = cfg.data.get("ground_height_map", None) if hasattr(cfg.data, "get") else getattr(cfg.data, "ground_height_map", None)
+        self.ground_cone_z = float(ghm["ground_threshold"]) if ghm is not None and "ground_threshold" in ghm else -1.5
+        self.ground_cone_deg = 0.8
         z_cut = cfg.data.setdefault("z_pillar_cutoff_value", 5.0)
         assert z_cut > 0.0, z_cut
         half = np.append(np.array(cfg.data.bev_range_m) / 2.0, z_cut)
@@ -124,7 +130,7 @@ class PointsPillarFeatureNetWrapper(nn.Module):
             grid, cfg.data.img_grid_size)
 
     # ------------------------------------------------------------------ C-ABI plumbing
-    def _params(self, training: bool) -> _lib.PillarParams:
+    def _params(self, training: bool, raw_scan: bool = False) -> _lib.PillarParams:
         vl, ve = self.pts_voxel_layer, self.pts_voxel_encoder
         p = _lib.PillarParams()
         rg = np.asarray(vl.point_cloud_range, dtype=np.float32)
@@ -142,6 +148,9 @@ class PointsPillarFeatureNetWrapper(nn.Module):
         p.bn_training = 1 if training else 0
         p.bn_eps = ve.pfn_layers[0].norm.eps
         p.bn_momentum = ve.pfn_layers[0].norm.momentum
+        p.ground_filter = 1 if raw_scan else 0
+        p.ground_cone_z = float(np.float32(self.ground_cone_z))
+        p.ground_cone_tan = float(np.float32(np.tan(self.ground_cone_deg / 180.0 * np.pi)))
         nhwc = self.canvas_memory_format == "channels_last" and p.c_out in (4, 8, 16, 32, 64)
         p.canvas_layout = _lib.CANVAS_NHWC if nhwc else _lib.CANVAS_NCHW
         return p
@@ -158,7 +167,7 @@ class PointsPillarFeatureNetWrapper(nn.Module):
             out.append(t)
         return out
 
-    def _encode(self, pts: Sequence[torch.Tensor], want_voxels: bool):
+    def _encode(self, pts: Sequence[torch.Tensor], want_voxels: bool, raw_scan: bool = False):
         assert isinstance(pts, (list, tuple)), type(pts)
         lib = _lib.load()
         pfn = self.pts_voxel_encoder.pfn_layers[0]
@@ -168,7 +177,7 @@ class PointsPillarFeatureNetWrapper(nn.Module):
             raise ValueError("batch size must be in [1, %d]" % _lib.MAX_BATCH)
         dev = pts[0].device
         training = self.training
-        p = self._params(training)
+        p = self._params(training, raw_scan)
         ny, nx = self.pts_middle_encoder.ny, self.pts_middle_encoder.nx
         total = int(sum(t.shape[0] for t in pts))
         fmt = torch.channels_last if p.canvas_layout == _lib.CANVAS_NHWC else torch.contiguous_format
@@ -228,14 +237,16 @@ class PointsPillarFeatureNetWrapper(nn.Module):
         return dict(voxels=ex["voxels"][:n], num_points=ex["num_points"][:n], coors=ex["coors"][:n],
                     pt2pillar=ex["pt2pillar"], pillar_counts=ex["pillar_counts"], canvas=canvas, occupancy=occ)
 
-    def extract_pts_feat(self, pts) -> Tuple[torch.Tensor, torch.Tensor]:
+    def extract_pts_feat(self, pts, raw_scan: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
         if torch.is_grad_enabled() and any(q.requires_grad for q in self.parameters()):
             raise RuntimeError(
                 "liso_b200 pillar encoder is forward-only (flow export): call it under torch.no_grad() "
                 "or freeze its parameters; autograd through the fused kernel is not provided")
         with torch.no_grad():
-            canvas, occupancy, _ = self._encode(pts, want_voxels=False)
+            canvas, occupancy, _ = self._encode(pts, want_voxels=False, raw_scan=raw_scan)
         return canvas, occupancy
 
-    def forward(self, pcl_t0, img_t0=None):
-        return self.extract_pts_feat(pcl_t0)
+    def forward(self, pcl_t0, img_t0=None, raw_scan: bool = False):
+        """``raw_scan=True``: ``pcl_t0`` are raw scans (with ground); the ground points are dropped inside the kernel
+        with the dataset's cone rule, which gives the same canvas as passing ``pcl_full_no_ground``."""
+        return self.extract_pts_feat(pcl_t0, raw_scan=raw_scan)

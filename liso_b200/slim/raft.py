@@ -278,9 +278,12 @@ class RAFT(nn.Module):
         self.cnet = SmallEncoder(output_dim=self.hidden_dim + self.context_dim, norm_fn="none", dropout=m.dropout_rate)
         self.update_block = SmallUpdateBlock(cfg=self.slim_cfg, filters=self.hidden_dim)
 
-    def forward(self, pcl_t0, pcl_t1):
-        img_t0, occ_t0 = self.pp_layer(pcl_t0)
-        img_t1, occ_t1 = self.pp_layer(pcl_t1)
+    def forward(self, pcl_t0, pcl_t1, raw_scans: bool = False):
+        """``raw_scans``: the clouds are raw scans with ground (``liso_b200.datasets.preprocess_scans``); the encoder
+        applies the dataset's ground rule itself."""
+        kw = {"raw_scan": True} if raw_scans else {}  # (the reference signature is forward(pcl, img=None))
+        img_t0, occ_t0 = self.pp_layer(pcl_t0, **kw)
+        img_t1, occ_t1 = self.pp_layer(pcl_t1, **kw)
         aux = {"t0": {"bev_net_input_dbg": occ_t0}, "t1": {"bev_net_input_dbg": occ_t1}}
         fmap_t0 = self.fnet(img_t0)
         fmap_t1 = self.fnet(img_t1)

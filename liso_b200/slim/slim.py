@@ -25,8 +25,11 @@ from .raft import RAFT
 
 
 def get_network_input_pcls(cfg, sample_data, time_key: str, to_device=None) -> List[torch.Tensor]:
-    """``liso/kabsch/main_utils.py:247-261``"""
+    """``liso/kabsch/main_utils.py:247-261`` (+ raw scans from ``liso_b200.datasets.preprocess_scans``: the pillar
+    encoder removes the ground in-kernel, so the raw cloud stands in for ``pcl_full_no_ground``)."""
     key = ("pcl_full_w_ground_%s" if cfg.data.use_ground_for_network else "pcl_full_no_ground_%s") % time_key
+    if key not in sample_data and sample_data.get("raw_scan", False):
+        key = "pcl_full_w_ground_%s" % time_key
     if to_device:
         return [el.to(to_device, non_blocking=True) for el in sample_data[key]]
     return sample_data[key]
@@ -261,9 +264,12 @@ class SLIM(nn.Module):
 
     def forward(self, sample_data_t0, sample_data_t1, summaries=None):
         dev = next(self.parameters()).device
+        raw = bool(sample_data_t0.get("raw_scan", False)) and not self.cfg.data.use_ground_for_network
+        assert raw == (bool(sample_data_t1.get("raw_scan", False)) and not self.cfg.data.use_ground_for_network)
         outs_fw, outs_bw, aux = self.raft_network(
             get_network_input_pcls(self.cfg, sample_data_t0, "ta", to_device=dev),
             get_network_input_pcls(self.cfg, sample_data_t1, "ta", to_device=dev),
+            raw_scans=raw,
         )
         filled = [torch.squeeze(aux[k]["bev_net_input_dbg"] > 0.5, dim=1) for k in ("t0", "t1")]
         its = range(len(outs_fw))  # one entry per iteration, or only the last one in "last" mode

@@ -50,6 +50,34 @@ def pillar_geometry(bev_range_m: Sequence[float], img_grid_size: Sequence[int], 
 
 
 # ----------------------------------------------------------------------------------
+# f.4: dataset-side pre-processing      torch_dataset_commons.py:133-146, 975-987, 1061-1184
+# ----------------------------------------------------------------------------------
+def ground_label_cone_f32(pcl: np.ndarray, cone_z_threshold_m: float = -1.5, cone_angle_deg: float = 0.8) -> np.ndarray:
+    """``infer_ground_label_using_cone`` (``torch_dataset_commons.py:133-146``) as the reference environment
+    evaluates it: float32 cloud, and -- NumPy < 2 value-based casting -- the float64 scalars ``tan(angle)`` and the
+    threshold are cast to float32, so every operation rounds to float32 (written out explicitly here because
+    NumPy >= 2 would promote to float64)."""
+    x, y, z = (pcl[..., k].astype(np.float32) for k in range(3))
+    d_xy = np.sqrt((x * x + y * y).astype(np.float32)).astype(np.float32)
+    tan32 = np.float32(np.tan(cone_angle_deg / 180.0 * np.pi))
+    thr = (np.float32(cone_z_threshold_m) + (tan32 * d_xy).astype(np.float32)).astype(np.float32)
+    return z < thr
+
+
+def preprocess_scan(pcl: np.ndarray, bev_range_m, img_grid_size, ground_label=None, cone_z_threshold_m: float = -1.5,
+                    height_range_m=(-2.0, 1.0)):
+    """One frame of ``pillarize_points_remove_ground_add_bev_ghm_occupancy`` (``torch_dataset_commons.py:1061-1106``):
+    returns (pcl_full_no_ground, pcl_ta, pillar_coors) -- ground = label | cone rule (``:1164-1184``), pcl_ta = in-range
+    (``voxelize_sample`` ``:975-987``) non-ground points in scan order."""
+    ground = ground_label_cone_f32(pcl, cone_z_threshold_m)
+    if ground_label is not None:
+        ground = ground | ground_label.astype(bool)
+    coors, in_range = pillar_coors_f64(pcl, bev_range_m, img_grid_size, height_range_m)
+    keep = in_range & ~ground
+    return pcl[~ground], pcl[keep], coors[keep]
+
+
+# ----------------------------------------------------------------------------------
 # a2: hard voxelisation                  mmdet3d/core/voxel/voxel_generator.py:76-208
 # ----------------------------------------------------------------------------------
 def hard_voxelize_loop(points, voxel_size, coors_range, max_points=MAX_POINTS_PER_PILLAR, max_voxels=MAX_PILLARS):
