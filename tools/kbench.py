@@ -40,6 +40,12 @@ def main():
             m = PointsPillarFeatureNetWrapper(cfg, canvas_memory_format=fmt).to(dev)
             m.train(args.train_bn)
             runs.append(("pillar " + fmt[:8], (lambda mm: (lambda: mm(clouds)))(m)))
+    if not args.skip_pillar:
+        from liso_b200.datasets import preprocess_scans
+
+        raw = [torch.cat([c, c[: c.shape[0] // 3] * torch.tensor([1.0, 1.0, 0.0, 1.0], device=dev)
+                          + torch.tensor([0.0, 0.0, -1.73, 0.0], device=dev)]) for c in clouds]
+        runs.append(("preprocess raw", lambda: preprocess_scans(raw, cfg)))
     if not args.skip_corr:
         g = torch.Generator(device="cpu").manual_seed(0)
         h, w = H // 8, Wd // 8
