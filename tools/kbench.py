@@ -69,6 +69,13 @@ def main():
         runs.append(("corr_build nchw", build_nchw))
         runs.append(("corr_build nhwc", build))
         runs.append(("corr_lookup x6", look))
+        grid = coords_grid(B, h, w, dev).contiguous()
+
+        def look_int():
+            for _ in range(6):
+                state["out"] = state["blk"](grid)
+
+        runs.append(("corr_lookup integer coords", look_int))
     with torch.no_grad():
         for name, fn in runs:
             for _ in range(3):
