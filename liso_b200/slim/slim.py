@@ -53,6 +53,15 @@ class MovingAverageThreshold(nn.Module):
         self.register_buffer("moving_average_importance", torch.zeros((resolution,), dtype=torch.float))
 
     def value(self):
+        """Device scalar.  The reference branches on ``bias_counter > 0`` (a host sync in the middle of every forward);
+        the buffers only change in training, so the result is cached per buffer version."""
+        key = (self.bias_counter._version, self.moving_average_importance._version, self.start_value._version,
+               self.bias_counter.data_ptr(), self.start_value.device)
+        if getattr(self, "_value_cache", (None, None))[0] != key:
+            self._value_cache = (key, self._value())
+        return self._value_cache[1]
+
+    def _value(self):
         if self.bias_counter > 0.0:
             mai = self.moving_average_importance
             cum = torch.cat([torch.zeros((1,), dtype=mai.dtype, device=mai.device), torch.cumsum(mai, 0)], dim=0)

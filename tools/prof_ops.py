@@ -18,7 +18,7 @@ cfg.network["b200_canvas_memory_format"] = fmt
 torch.backends.cudnn.allow_tf32 = True
 torch.backends.cuda.matmul.allow_tf32 = True
 torch.backends.cudnn.benchmark = True
-model = SLIM(cfg, decode_iterations="last", static_aggregation=False).eval()
+model = SLIM(cfg, decode_iterations=(sys.argv[2] if len(sys.argv) > 2 else "all"), static_aggregation=(len(sys.argv) <= 2 or sys.argv[2] == "all")).eval()
 model.load_state_dict(synth_weights_like(model.state_dict(), 0))
 model = model.to(dev)
 if fmt == "channels_last":
