@@ -170,3 +170,17 @@ def require_cuda(*tensors) -> None:
             raise RuntimeError(
                 "slimb200 kernels run on CUDA (sm_100a) only; got a %s tensor. There is no CPU fallback." % t.device
             )
+
+
+# kernels of this library that ran as part of CUDA-graph replays (the library's own counter only sees the capture)
+_graph_replayed_launches = 0
+
+
+def note_graph_replay(n_kernels: int) -> None:
+    global _graph_replayed_launches
+    _graph_replayed_launches += int(n_kernels)
+
+
+def total_launch_count() -> int:
+    """Launches of slimb200 kernels so far: direct launches + kernels inside replayed CUDA graphs."""
+    return int(load().slimb200_launch_count(-1)) + _graph_replayed_launches

@@ -98,6 +98,13 @@ class CorrBlock:
     def __init__(self, fmap1: torch.Tensor, fmap2: torch.Tensor, num_levels: int = 4, radius: int = 4):
         self.num_levels = num_levels
         self.radius = radius
+        self.pyramid = None
+        self._ws = None
+        self.rebuild(fmap1, fmap2)
+
+    def rebuild(self, fmap1: torch.Tensor, fmap2: torch.Tensor) -> "CorrBlock":
+        """(Re)compute the pyramid for a new pair of feature maps INTO the buffers this block already owns (same
+        shapes), so that a captured CUDA graph of the lookups keeps pointing at valid data."""
         _lib.require_cuda(fmap1, fmap2)
         if torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad):
             raise RuntimeError("liso_b200 CorrBlock is forward-only (flow export): call it under torch.no_grad()")
@@ -105,7 +112,7 @@ class CorrBlock:
             raise ValueError("fmap1/fmap2 must both be (B, D, h, w)")
         B, D, h, w = fmap1.shape
         lib = _lib.load()
-        self.layout = make_layout(B, D, h, w, num_levels)
+        L = make_layout(B, D, h, w, self.num_levels)
         f1, f2 = fmap1.detach().float(), fmap2.detach().float()
         # feed the kernel whatever layout the feature encoder produced: channels-last needs no transposition
         nhwc = f1.is_contiguous(memory_format=torch.channels_last) and f2.is_contiguous(memory_format=torch.channels_last) \
@@ -113,14 +120,19 @@ class CorrBlock:
         if not nhwc:
             f1, f2 = f1.contiguous(), f2.contiguous()
         layout_flag = _lib.CANVAS_NHWC if nhwc else _lib.CANVAS_NCHW
-        self.channels_last = nhwc  # answer lookups in the memory format the feature maps came in
-        L = self.layout
-        self.pyramid = torch.empty((B * L.n_panels * h * w, _lib.PANEL_COLS), dtype=torch.bfloat16, device=f1.device)
-        ws = torch.empty(lib.slimb200_corr_workspace_bytes(C.byref(L)), dtype=torch.uint8, device=f1.device)
+        shape = (B * L.n_panels * h * w, _lib.PANEL_COLS)
+        if self.pyramid is None:
+            self.pyramid = torch.empty(shape, dtype=torch.bfloat16, device=f1.device)
+            self._ws = torch.empty(lib.slimb200_corr_workspace_bytes(C.byref(L)), dtype=torch.uint8, device=f1.device)
+            self.channels_last = nhwc  # answer lookups in the memory format the feature maps came in
+        elif tuple(self.pyramid.shape) != shape or self.pyramid.device != f1.device or self.channels_last != nhwc:
+            raise ValueError("CorrBlock.rebuild needs feature maps of the shape / layout the block was built for")
+        self.layout = L
         _lib.check(lib.slimb200_corr_build(f1.data_ptr(), f2.data_ptr(), layout_flag, C.byref(L), _lib.DTYPE_BF16,
-                                           self.pyramid.data_ptr(), ws.data_ptr(), ws.numel(),
+                                           self.pyramid.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
                                            _lib.current_stream_ptr()))
         self.corr_pyramid = _LazyLevels(self.pyramid, L)
+        return self
 
     def __call__(self, coords: torch.Tensor) -> torch.Tensor:
         return lookup(self.pyramid, self.layout, coords, self.radius, self.channels_last)

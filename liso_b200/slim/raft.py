@@ -15,7 +15,13 @@ import torch.nn.functional as F
 from torch import nn
 
 from ..networks.pcl_to_feature_grid import PointsPillarFeatureNetWrapper
-from .corr import CorrBlock, initialize_flow, uplogits_n, upflow_n
+from .corr import CorrBlock, coords_grid, initialize_flow, uplogits_n, upflow_n
+
+
+def _lib_mod():
+    from .. import _lib
+
+    return _lib
 
 
 # Stock-op plumbing (no custom kernels): when True, Conv2d -> ReLU pairs go through cuDNN's fused
@@ -265,6 +271,10 @@ class RAFT(nn.Module):
         # "all": one (B,H,W,8) output per GRU iteration like the reference (raft_mod.py:216-257); "last": only the
         # final one is up-sampled / assembled (the flow export reads nothing else, experiment.py:391-399)
         self.output_iterations = "all"
+        # capture the GRU refinement loop in a CUDA graph (inference on CUDA only; falls back to eager launches of the
+        # same kernels when switched off)
+        self.use_cuda_graph = True
+        self._graphs = {}
         rows = float(cfg.data.bev_range_m[0]) / cfg.data.img_grid_size[0] * m.u_net.final_scale
         cols = float(cfg.data.bev_range_m[1]) / cfg.data.img_grid_size[1] * m.u_net.final_scale
         assert rows == cols, "anisotropic BEV resolution is not supported (raft_mod.py:42-45)"
@@ -287,22 +297,19 @@ class RAFT(nn.Module):
         aux = {"t0": {"bev_net_input_dbg": occ_t0}, "t1": {"bev_net_input_dbg": occ_t1}}
         fmap_t0 = self.fnet(img_t0)
         fmap_t1 = self.fnet(img_t1)
-        fw = self.predict_single_flow_map_and_classes(img_t0, fmap_t0, fmap_t1, self.head_decoder_fw)
-        bw = self.predict_single_flow_map_and_classes(img_t1, fmap_t1, fmap_t0, self.head_decoder_bw)
+        fw = self.predict_single_flow_map_and_classes(img_t0, fmap_t0, fmap_t1, self.head_decoder_fw, slot=0)
+        bw = self.predict_single_flow_map_and_classes(img_t1, fmap_t1, fmap_t0, self.head_decoder_bw, slot=1)
         return fw, bw, aux
 
-    def predict_single_flow_map_and_classes(self, img_t0, fmap_t0, fmap_t1, decoder=None) -> List[torch.Tensor]:
+    def _gru_loop(self, correlation, net, inp, img_hw, batch, device) -> List[torch.Tensor]:
+        """The refinement loop of ``raft_mod.py:188-257``: lookup -> update block -> coordinate / logit update, and the
+        per-iteration network output.  Pure function of (pyramid, net, inp): this is what gets captured in a CUDA graph."""
         m = self.slim_cfg.model
         ds = m.feature_downsampling_factor
-        coords0 = initialize_flow(img_t0, downscale_factor=ds)
-        coords1 = initialize_flow(img_t0, downscale_factor=ds)
-        b, _, h, w = coords0.shape
-        logits = torch.zeros((b, 4, h, w), dtype=torch.float32, device=img_t0.device)
-        correlation = CorrBlock(fmap_t0, fmap_t1, num_levels=m.corr_cfg.num_levels, radius=m.corr_cfg.search_radius)
-        net, inp = torch.split(self.cnet(img_t0), [self.hidden_dim, self.context_dim], dim=1)
-        net, inp = torch.tanh(net), torch.relu(inp)
-        res = torch.tensor([self.bev_rows_res_meters_per_fs_pixel, self.bev_cols_res_meters_per_fs_pixel],
-                           device=inp.device, dtype=inp.dtype)[None, :, None, None]
+        h, w = img_hw[0] // ds, img_hw[1] // ds
+        coords0 = coords_grid(batch, h, w, device)
+        coords1 = coords_grid(batch, h, w, device)
+        logits = torch.zeros((batch, 4, h, w), dtype=torch.float32, device=device)
         outs = []
         for it in range(m.num_iters):
             coords1 = coords1.detach()
@@ -318,6 +325,65 @@ class RAFT(nn.Module):
                                               self.bev_cols_res_meters_per_fs_pixel))
                 continue
             # RAFT (x, y) pixel flow -> (row, col) metres (raft_mod.py:262-266)
+            res = torch.tensor([self.bev_rows_res_meters_per_fs_pixel, self.bev_cols_res_meters_per_fs_pixel],
+                               device=device, dtype=torch.float32)[None, :, None, None]
             flow_m = torch.flip(upflow_n(coords1 - coords0, n=ds), dims=[1]) * res
             outs.append(concat2network_output(uplogits_n(logits, n=ds), flow_m, flow_m))
         return outs
+
+    def predict_single_flow_map_and_classes(self, img_t0, fmap_t0, fmap_t1, decoder=None, slot: int = 0) -> List[torch.Tensor]:
+        m = self.slim_cfg.model
+        b, _, H, W = img_t0.shape
+        dev = img_t0.device
+        use_graph = (self.use_cuda_graph and FAST_STOCK_OPS and img_t0.is_cuda and not torch.is_grad_enabled()
+                     and not self.training and not torch.cuda.is_current_stream_capturing())
+        if not use_graph:
+            correlation = CorrBlock(fmap_t0, fmap_t1, num_levels=m.corr_cfg.num_levels, radius=m.corr_cfg.search_radius)
+            net, inp = torch.split(self.cnet(img_t0), [self.hidden_dim, self.context_dim], dim=1)
+            return self._gru_loop(correlation, torch.tanh(net), torch.relu(inp), (H, W), b, dev)
+
+        # ---- CUDA-graphed refinement loop: ~270 small launches per direction become one graph launch.
+        # The graph reads three static buffers (pyramid, net, inp) and owns its outputs; one graph per direction slot,
+        # so the forward outputs survive the backward replay.
+        nhwc = fmap_t0.is_contiguous(memory_format=torch.channels_last) and not fmap_t0.is_contiguous()
+        # the captured kernels hold raw pointers to the update-block weights (and to cached concatenations of them):
+        # any in-place update or re-allocation of a parameter invalidates the graph
+        wsig = tuple((p.data_ptr(), p._version) for p in self.update_block.parameters())
+        key = (b, H, W, self.output_iterations, nhwc, str(dev), torch.backends.cudnn.allow_tf32, wsig)
+        st = self._graphs.get(slot)
+        if st is not None and st["key"] != key:
+            st = None  # (the old graph and its buffers are released when the slot is overwritten)
+        net, inp = torch.split(self.cnet(img_t0), [self.hidden_dim, self.context_dim], dim=1)
+        net, inp = torch.tanh(net), torch.relu(inp)
+        if st is None:
+            st = self._capture_gru_graph(slot, key, fmap_t0, fmap_t1, net, inp, (H, W), b, dev)
+        else:
+            st["corr"].rebuild(fmap_t0, fmap_t1)
+            st["net"].copy_(net)
+            st["inp"].copy_(inp)
+        st["graph"].replay()
+        _lib_mod().note_graph_replay(st["launches"])
+        return st["outs"]
+
+    def _capture_gru_graph(self, slot, key, fmap_t0, fmap_t1, net, inp, img_hw, batch, dev):
+        m = self.slim_cfg.model
+        lib = _lib_mod()
+        corr = CorrBlock(fmap_t0, fmap_t1, num_levels=m.corr_cfg.num_levels, radius=m.corr_cfg.search_radius)
+        st = {"corr": corr, "net": net.clone(), "inp": inp.clone()}
+        # warm-up on a side stream (cuDNN autotuning, lazy kernel attributes), as torch.cuda.graphs asks
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._gru_loop(corr, st["net"], st["inp"], img_hw, batch, dev)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        n0 = lib.load().slimb200_launch_count(-1)
+        with torch.cuda.graph(graph):
+            st["outs"] = self._gru_loop(corr, st["net"], st["inp"], img_hw, batch, dev)
+        st["launches"] = int(lib.load().slimb200_launch_count(-1) - n0)  # library kernels inside one replay
+        st["graph"] = graph
+        st["key"] = key
+        self._graphs[slot] = st
+        return st
+

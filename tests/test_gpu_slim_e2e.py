@@ -89,3 +89,25 @@ def test_against_committed_golden(cuda):
         assert aee <= 0.01, aee
         ref_bev = torch.from_numpy(g["bev_static_flow_%s" % d])
         assert torch.equal(p[-1].modified_network_output.static_flow[0].cpu() != 0, ref_bev != 0)
+
+
+def test_cuda_graphed_gru_loop_equals_eager_and_tracks_weight_updates(cuda):
+    """the CUDA-graphed refinement loop replays the same kernels as the eager loop (bit-identical outputs),
+    is re-captured when a weight changes in place, and different inputs flow through the same captured graph."""
+    cfg = make_cfg("T")
+    model, sd = _model(cfg, cuda)
+    s0, s1 = make_sample_dicts(WORKLOADS["T"], [31])
+    t0, t1 = make_sample_dicts(WORKLOADS["T"], [32])
+    with torch.no_grad():
+        model.raft_network.use_cuda_graph = False
+        e_a = model(s0, s1, None)[0][-1].modified_network_output.static_flow.clone()
+        e_b = model(t0, t1, None)[0][-1].modified_network_output.static_flow.clone()
+        model.raft_network.use_cuda_graph = True
+        g_a = model(s0, s1, None)[0][-1].modified_network_output.static_flow.clone()   # capture + replay
+        g_b = model(t0, t1, None)[0][-1].modified_network_output.static_flow.clone()   # replay with new inputs
+        assert torch.equal(e_a, g_a) and torch.equal(e_b, g_b) and not torch.equal(g_a, g_b)
+        model.raft_network.update_block.static_flow_head.conv2.bias.add_(0.25)         # in-place weight update
+        g_c = model(s0, s1, None)[0][-1].modified_network_output.static_flow.clone()
+        model.raft_network.use_cuda_graph = False
+        e_c = model(s0, s1, None)[0][-1].modified_network_output.static_flow.clone()
+        assert torch.equal(g_c, e_c) and not torch.equal(g_c, g_a)
