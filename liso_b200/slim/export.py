@@ -172,16 +172,32 @@ class ExportPipeline:
         self.copy_stream = torch.cuda.Stream(device=device)
         self.amp_ctx = amp_ctx
         self._out_bufs = [None, None]
+        self._up_bufs = {}
 
-    def _upload(self, sample):
+    def _stage(self, slot: int, name: str, host: torch.Tensor) -> torch.Tensor:
+        """Copy ``host`` into a grow-only device buffer owned by (slot, name): no allocator traffic, no cross-stream
+        block reuse in steady state."""
+        key = (slot, name)
+        buf = self._up_bufs.get(key)
+        n = host.numel()
+        if buf is None or buf.numel() < n or buf.dtype != host.dtype:
+            buf = torch.empty(max(n, 1), dtype=host.dtype, device=self.device)
+            self._up_bufs[key] = buf
+        dst = buf[:n].view(host.shape)
+        dst.copy_(host, non_blocking=True)
+        return dst
+
+    def _upload(self, sample, slot: int, tag: str):
         out = {}
         for k, v in sample.items():
             if isinstance(v, dict):
-                out[k] = {kk: vv.to(self.device, non_blocking=True) for kk, vv in v.items()}
+                out[k] = {kk: self._stage(slot, "%s/%s/%s" % (tag, k, kk), vv) for kk, vv in v.items()}
             elif isinstance(v, (list, tuple)):
-                out[k] = [t.to(self.device, non_blocking=True) for t in v]
+                out[k] = [self._stage(slot, "%s/%s/%d" % (tag, k, i), t) for i, t in enumerate(v)]
+            elif torch.is_tensor(v):
+                out[k] = self._stage(slot, "%s/%s" % (tag, k), v)
             else:
-                out[k] = v.to(self.device, non_blocking=True)
+                out[k] = v
         return out
 
     def run(self, batches, consume=None):
@@ -189,13 +205,14 @@ class ExportPipeline:
 
         cur = torch.cuda.current_stream(self.device)
         it = iter(batches)
-        pending = None  # (index, device tensors, event) waiting for download
         downloads = []  # (index, host tensors, event)
+        done_evt = [None, None]  # compute-finished event of the batch that last used upload slot 0 / 1
         nxt = next(it, None)
         staged = None
         if nxt is not None:
+            self.copy_stream.wait_stream(cur)
             with torch.cuda.stream(self.copy_stream):
-                staged = (self._upload(nxt[0]), self._upload(nxt[1]))
+                staged = (self._upload(nxt[0], 0, "t0"), self._upload(nxt[1], 0, "t1"))
                 up_evt = torch.cuda.Event()
                 up_evt.record(self.copy_stream)
         idx = 0
@@ -203,10 +220,6 @@ class ExportPipeline:
         while staged is not None:
             cur.wait_event(up_evt)
             d0, d1 = staged
-            for d in (d0, d1):  # the uploaded tensors are consumed on the compute stream
-                for v in d.values():
-                    for t in (v.values() if isinstance(v, dict) else (v if isinstance(v, (list, tuple)) else [v])):
-                        t.record_stream(cur)
             ctx = self.amp_ctx() if self.amp_ctx else contextlib.nullcontext()
             with torch.no_grad(), ctx:
                 pf, pb = self.model(d0, d1, None)
@@ -214,11 +227,15 @@ class ExportPipeline:
             outs = [fw.static_flow, bw.static_flow, fw.dynamicness, bw.dynamicness]
             done = torch.cuda.Event()
             done.record(cur)
+            done_evt[idx % 2] = done
             # stage the next batch and download this one on the copy stream, behind the compute of this batch
             nxt = next(it, None)
             with torch.cuda.stream(self.copy_stream):
                 if nxt is not None:
-                    staged = (self._upload(nxt[0]), self._upload(nxt[1]))
+                    up_slot = (idx + 1) % 2
+                    if done_evt[up_slot] is not None:  # the batch that last read this slot's buffers must be through
+                        self.copy_stream.wait_event(done_evt[up_slot])
+                    staged = (self._upload(nxt[0], up_slot, "t0"), self._upload(nxt[1], up_slot, "t1"))
                     up_evt = torch.cuda.Event()
                     up_evt.record(self.copy_stream)
                 else:

@@ -385,5 +385,6 @@ class RAFT(nn.Module):
         st["graph"] = graph
         st["key"] = key
         self._graphs[slot] = st
+        self.n_graph_captures = getattr(self, "n_graph_captures", 0) + 1
         return st
 
