@@ -271,6 +271,7 @@ enum {
   SLIMB200_K_PRE_SCAN,
   SLIMB200_K_PRE_SCATTER,
   SLIMB200_K_PRE_PAD,
+  SLIMB200_K_KABSCH_MOMENTS,
   SLIMB200_N_KERNELS
 };
 int slimb200_profile_begin(void);

@@ -13,7 +13,8 @@
 //   k_decode_min      global min of the live static/dynamic logits (ground logit "off" = min - 100)
 //   k_decode_bev      one thread per BEV cell: masks, 3-way softmax, class decisions, masked flows, aggregated flow;
 //                     one packed (B,H,W,16) row per cell, staged in smem and written back linearly
-//   k_decode_points   one thread per point: gather, weights, fp64 Kabsch moments (block partials, fixed order)
+//   k_decode_points   one thread per point: gather of the BEV values, Kabsch weight
+//   k_kabsch_moments  streaming fp64 moments (several points per thread, block partials in fixed order)
 //   k_kabsch_finalize one CTA per sample: sum the partials, 3x3 one-sided Jacobi SVD in fp64, R = U V^T, T (4x4)
 //   k_decode_aggr     (T - I) * cell centre for every cell and every point
 #include "common.cuh"
@@ -132,6 +133,7 @@ struct DecodeArgs {
   uint8_t* not_enough;
   unsigned* min_key;
   double* partials;  // [batch][blocks_per_sample][N_MOM]
+  float* pt_weight;  // [batch][n_points] Kabsch weight per point, -1 = invalid point
   int blocks_per_sample;
 };
 
@@ -188,39 +190,63 @@ __global__ void __launch_bounds__(256) k_decode_bev(const DecodeArgs a) {
   }
 }
 
+// gather: one thread per point, fully parallel; the 256 x 14 output floats of a CTA are contiguous and are written back
+// linearly from shared memory; the Kabsch weight goes to a scratch array (-1 marks invalid points)
 __global__ void __launch_bounds__(PT_THREADS) k_decode_points(const DecodeArgs a) {
-  __shared__ double s_part[PT_THREADS / 32][N_MOM];
+  __shared__ __align__(16) float s_pts[PT_THREADS * PT_C];
   const int b = blockIdx.y;
   const int n = a.p.n_points;
-  double mom[N_MOM];
+  const int j0 = blockIdx.x * PT_THREADS;
+  const int j = j0 + threadIdx.x;
+  float* so = s_pts + threadIdx.x * PT_C;
 #pragma unroll
-  for (int k = 0; k < N_MOM; ++k) mom[k] = 0.0;
-  for (int it = 0; it < PT_PER_THREAD; ++it) {
-    const int j = (blockIdx.x * PT_PER_THREAD + it) * PT_THREADS + threadIdx.x;
-    if (j >= n) break;
+  for (int k = 0; k < PT_C; ++k) so[k] = 0.f;
+  if (j < n) {
     const size_t pi = (size_t)b * n + j;
-    const bool valid = a.valid[pi] != 0;
-    float out[11];
-#pragma unroll
-    for (int k = 0; k < 11; ++k) out[k] = 0.f;
-    if (valid) {
+    float w = -1.f;
+    if (a.valid[pi] != 0) {
       const int r = a.coors[pi * 2] / a.p.final_scale, c = a.coors[pi * 2 + 1] / a.p.final_scale;
       const size_t cell = ((size_t)b * a.p.H + r) * a.p.W + c;
       const float* row = a.bev + cell * BEV_C;
       const float4 q1 = __ldg(reinterpret_cast<const float4*>(row + 4));    // staticness dynamicness groundness static.x
       const float4 q2 = __ldg(reinterpret_cast<const float4*>(row + 8));    // static.y static.z dynamic.x dynamic.y
       const float4 q3 = __ldg(reinterpret_cast<const float4*>(row + 12));   // dynamic.z aggregated.xyz
-      const float p_st = q1.x, p_dy = q1.y;
-      out[0] = q1.w; out[1] = q2.x; out[2] = q2.y;      // static3
-      out[3] = q2.z; out[4] = q2.w; out[5] = q3.x;      // dynamic3
-      out[6] = p_dy;
-      out[7] = p_st;
-      out[8] = q3.y; out[9] = q3.z; out[10] = q3.w;     // aggregated3
-      if (a.p.static_aggregation) {
-        const float w = a.filled[cell] ? p_st : 0.f;  // staticness * filled (static_aggregation.py:66-71)
+      so[0] = q1.w; so[1] = q2.x; so[2] = q2.y;      // static3
+      so[3] = q2.z; so[4] = q2.w; so[5] = q3.x;      // dynamic3
+      so[6] = q1.y;                                  // dynamicness
+      so[7] = q1.x;                                  // staticness
+      so[8] = q3.y; so[9] = q3.z; so[10] = q3.w;     // aggregated3
+      if (a.p.static_aggregation) w = a.filled[cell] ? q1.x : 0.f;  // staticness * filled (static_aggregation.py:66-71)
+    }
+    if (a.p.static_aggregation) a.pt_weight[pi] = w;
+  }
+  __syncthreads();
+  const int n_here = min(PT_THREADS, n - j0);
+  float2* dst = reinterpret_cast<float2*>(a.pts + ((size_t)b * n + j0) * PT_C);  // 56-byte rows: 8-byte aligned
+  const float2* src = reinterpret_cast<const float2*>(s_pts);
+  for (int k = threadIdx.x; k < n_here * (PT_C / 2); k += PT_THREADS) dst[k] = src[k];
+}
+
+// fp64 Kabsch moments: streaming pass over (weight, point, gathered static flow), PT_PER_THREAD points per thread,
+// fixed-order reduction lanes -> warps -> block partial; blocks are summed in order by k_kabsch_finalize
+__global__ void __launch_bounds__(PT_THREADS) k_kabsch_moments(const DecodeArgs a) {
+  __shared__ double s_part[PT_THREADS / 32][N_MOM];
+  const int b = blockIdx.y;
+  const int n = a.p.n_points;
+  double mom[N_MOM];
+#pragma unroll
+  for (int k = 0; k < N_MOM; ++k) mom[k] = 0.0;
+#pragma unroll 4
+  for (int it = 0; it < PT_PER_THREAD; ++it) {
+    const int j = (blockIdx.x * PT_PER_THREAD + it) * PT_THREADS + threadIdx.x;
+    if (j < n) {
+      const size_t pi = (size_t)b * n + j;
+      const float w = __ldg(a.pt_weight + pi);
+      if (w >= 0.f) {
         const float* q = a.pc + pi * a.p.pc_stride;
-        const float x0 = q[0], y0 = q[1], z0 = q[2];
-        const float x1 = x0 + out[0], y1 = y0 + out[1], z1 = z0 + out[2];  // fp32 add like the reference
+        const float* f = a.pts + pi * PT_C;
+        const float x0 = __ldg(q), y0 = __ldg(q + 1), z0 = __ldg(q + 2);
+        const float x1 = x0 + f[0], y1 = y0 + f[1], z1 = z0 + f[2];  // fp32 add like the reference
         const double p0[3] = {x0, y0, z0}, p1[3] = {x1, y1, z1};
         const double wd = (double)w;
         mom[0] += wd;
@@ -240,17 +266,7 @@ __global__ void __launch_bounds__(PT_THREADS) k_decode_points(const DecodeArgs a
         mom[32] += w > 0.f ? 1.0 : 0.0;
       }
     }
-    float* o = a.pts + pi * PT_C;
-#pragma unroll
-    for (int k = 0; k < 11; ++k) o[k] = out[k];
-    if (!a.p.static_aggregation) {
-      o[11] = 0.f;
-      o[12] = 0.f;
-      o[13] = 0.f;
-    }
   }
-  if (!a.p.static_aggregation) return;
-  // fixed-order reduction: lanes -> warps -> block partial; blocks are summed in order by k_kabsch_finalize
 #pragma unroll
   for (int k = 0; k < N_MOM; ++k) {
     double v = mom[k];
@@ -414,6 +430,7 @@ extern "C" size_t slimb200_head_decode_workspace_bytes(const slimb200_decode_par
   WorkspaceCarver w(nullptr);
   w.take<unsigned>(64);
   w.take<double>((size_t)p->batch * (blocks_per_sample(p) + 1) * N_MOM);
+  w.take<float>((size_t)p->batch * p->n_points + 1);
   return w.used();
 }
 
@@ -463,6 +480,7 @@ extern "C" int slimb200_head_decode(const float* net_out, const uint32_t* logit_
   a.min_key = w.take<unsigned>(64);
   a.blocks_per_sample = blocks_per_sample(p);
   a.partials = w.take<double>((size_t)p->batch * (a.blocks_per_sample + 1) * N_MOM);
+  a.pt_weight = w.take<float>((size_t)p->batch * p->n_points + 1);
 
   const size_t n_cells = (size_t)p->batch * p->H * p->W;
   if (logit_min_key) {
@@ -474,10 +492,14 @@ extern "C" int slimb200_head_decode(const float* net_out, const uint32_t* logit_
   }
   SLIMB200_LAUNCH(SLIMB200_K_DECODE_BEV, stream, (k_decode_bev<<<(unsigned)((n_cells + 255) / 256), 256, 0, stream>>>(a)));
   if (p->n_points > 0) {
-    dim3 g(a.blocks_per_sample, p->batch);
+    dim3 g((p->n_points + PT_THREADS - 1) / PT_THREADS, p->batch);
     SLIMB200_LAUNCH(SLIMB200_K_DECODE_POINTS, stream, (k_decode_points<<<g, PT_THREADS, 0, stream>>>(a)));
   }
   if (p->static_aggregation) {
+    if (p->n_points > 0) {
+      dim3 g(a.blocks_per_sample, p->batch);
+      SLIMB200_LAUNCH(SLIMB200_K_KABSCH_MOMENTS, stream, (k_kabsch_moments<<<g, PT_THREADS, 0, stream>>>(a)));
+    }
     SLIMB200_LAUNCH(SLIMB200_K_KABSCH, stream, (k_kabsch_finalize<<<p->batch, 64, 0, stream>>>(a)));
     const unsigned gx = (unsigned)((p->W + 255) / 256);
     const size_t n_pts = (size_t)p->batch * p->n_points;
