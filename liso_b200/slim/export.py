@@ -162,16 +162,19 @@ class ExportPipeline:
 
     ``batches``: iterable of ``(sample_data_t0, sample_data_t1)`` with tensors in *pinned* host memory.
     ``consume(index, arrays)``: called with the exported tensors of a batch as pinned host tensors once they have
-    arrived (they are reused two batches later: copy or write them out inside the callback).
+    arrived (they are reused ``depth`` batches later: copy or write them out inside the callback).
     """
 
     KEYS = ("pcl_full_no_ground_ta", "pcl_ta")
 
-    def __init__(self, model, device, amp_ctx=None):
+    def __init__(self, model, device, amp_ctx=None, depth: int = 3):
+        """``depth``: batches the host may run ahead of the results it has consumed (number of upload / download
+        slots); >= 2.  A deeper pipeline absorbs host-side hiccups (the launch thread is the critical resource)."""
         self.model, self.device = model, device
         self.copy_stream = torch.cuda.Stream(device=device)
         self.amp_ctx = amp_ctx
-        self._out_bufs = [None, None]
+        self.depth = max(2, int(depth))
+        self._out_bufs = [None] * self.depth
         self._up_bufs = {}
 
     def _stage(self, slot: int, name: str, host: torch.Tensor) -> torch.Tensor:
@@ -206,7 +209,8 @@ class ExportPipeline:
         cur = torch.cuda.current_stream(self.device)
         it = iter(batches)
         downloads = []  # (index, host tensors, event)
-        done_evt = [None, None]  # compute-finished event of the batch that last used upload slot 0 / 1
+        D = self.depth
+        done_evt = [None] * D  # compute-finished event of the batch that last used each upload slot
         nxt = next(it, None)
         staged = None
         if nxt is not None:
@@ -227,12 +231,12 @@ class ExportPipeline:
             outs = [fw.static_flow, bw.static_flow, fw.dynamicness, bw.dynamicness]
             done = torch.cuda.Event()
             done.record(cur)
-            done_evt[idx % 2] = done
+            done_evt[idx % D] = done
             # stage the next batch and download this one on the copy stream, behind the compute of this batch
             nxt = next(it, None)
             with torch.cuda.stream(self.copy_stream):
                 if nxt is not None:
-                    up_slot = (idx + 1) % 2
+                    up_slot = (idx + 1) % D
                     if done_evt[up_slot] is not None:  # the batch that last read this slot's buffers must be through
                         self.copy_stream.wait_event(done_evt[up_slot])
                     staged = (self._upload(nxt[0], up_slot, "t0"), self._upload(nxt[1], up_slot, "t1"))
@@ -241,7 +245,7 @@ class ExportPipeline:
                 else:
                     staged = None
                 self.copy_stream.wait_event(done)
-                slot = idx % 2
+                slot = idx % D
                 if self._out_bufs[slot] is None or any(b.shape != o.shape for b, o in zip(self._out_bufs[slot], outs)):
                     self._out_bufs[slot] = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
                 for dst, src in zip(self._out_bufs[slot], outs):
@@ -250,8 +254,8 @@ class ExportPipeline:
                 dl_evt = torch.cuda.Event()
                 dl_evt.record(self.copy_stream)
             downloads.append((idx, self._out_bufs[slot], dl_evt))
-            # hand over the batch downloaded one iteration ago (its pinned buffers are reused next iteration)
-            while len(downloads) > 1:
+            # hand over the oldest batch once `depth - 1` newer ones are in flight (its pinned buffers come up for reuse)
+            while len(downloads) > D - 1:
                 j, host, evt = downloads.pop(0)
                 evt.synchronize()
                 if consume is not None:
