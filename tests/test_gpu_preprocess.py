@@ -91,3 +91,24 @@ def test_slim_forward_from_raw_scans(cuda):
         assert torch.equal(a[-1].static_flow[:, :n], b[-1].static_flow)
         assert float(a[-1].static_flow[:, n:].abs().sum()) == 0.0
         assert float((a[-1].static_aggr_trafo - b[-1].static_aggr_trafo).abs().max()) < 1e-9
+
+
+def test_preprocess_edge_cases(cuda):
+    """Empty scan, all-ground scan, single point, NaN point: counts, padding and masks stay consistent."""
+    cfg = make_cfg("T")
+    rng = np.random.default_rng(3)
+    all_ground = np.stack([rng.uniform(-10, 10, 500), rng.uniform(-10, 10, 500), np.full(500, -1.9), rng.uniform(0, 1, 500)], -1).astype(np.float32)
+    one = np.array([[1.0, 2.0, 0.1, 0.5]], dtype=np.float32)
+    with_nan = np.array([[np.nan, 0.0, 0.0, 0.0], [3.0, -4.0, 0.2, 0.1], [1e9, 0.0, 0.0, 0.0]], dtype=np.float32)
+    scans = [np.zeros((0, 4), np.float32), all_ground, one, with_nan]
+    got = preprocess_scans([torch.from_numpy(s).to(cuda) for s in scans], cfg)
+    torch.cuda.synchronize()
+    counts = got["counts"].cpu().numpy()
+    for b, s in enumerate(scans):
+        _, ref_ta, ref_coors = O.preprocess_scan(s, cfg.data.bev_range_m, cfg.data.img_grid_size)
+        assert counts[b] == ref_ta.shape[0]
+        n = int(counts[b])
+        assert np.array_equal(got["pcl_ta"]["pcl"][b, :n].cpu().numpy(), ref_ta)
+        assert np.array_equal(got["pcl_ta"]["pillar_coors"][b, :n].cpu().numpy(), ref_coors)
+        assert int(got["pcl_ta"]["pcl_is_valid"][b].sum()) == n
+    assert list(counts) == [0, 0, 1, 1]
