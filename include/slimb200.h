@@ -239,6 +239,15 @@ int slimb200_head_decode(const float* net_out, const uint32_t* logit_min_key /* 
 int slimb200_raft_output(const float* flow, const float* logits, int32_t batch, int32_t h, int32_t w, int32_t n,
                          float res_rows, float res_cols, float* net_out, uint32_t* logit_min_key, void* stream);
 
+/* Glue for the channels-last feature encoder: affine InstanceNorm2d (eps, biased variance) + optional ReLU on an
+ * NHWC tensor -- `norm_fn = "instance_affine"` + ReLU of liso/slim/model/extractor.py:5-68,211-297 -- in three
+ * launches and two passes over the data (PyTorch: copy to NCHW, cuDNN batch-norm on (1, B*C, H, W), copy back, clamp).
+ * x, out: device (batch, height, width, channels) f32, 16-byte aligned (out may alias x); channels % 4 == 0, <= 256. */
+size_t slimb200_instnorm_workspace_bytes(int32_t batch, int32_t channels, int32_t hw);
+int slimb200_instnorm_nhwc(const float* x, const float* gamma, const float* beta, float eps, int32_t batch,
+                           int32_t height, int32_t width, int32_t channels, int32_t relu, float* out,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 const char* slimb200_strerror(int code);
 int slimb200_version(void);
 
@@ -272,6 +281,9 @@ enum {
   SLIMB200_K_PRE_SCATTER,
   SLIMB200_K_PRE_PAD,
   SLIMB200_K_KABSCH_MOMENTS,
+  SLIMB200_K_IN_STATS,
+  SLIMB200_K_IN_FINALIZE,
+  SLIMB200_K_IN_APPLY,
   SLIMB200_N_KERNELS
 };
 int slimb200_profile_begin(void);

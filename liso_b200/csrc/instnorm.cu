@@ -1,0 +1,175 @@
+// Glue kernel for the channels-last feature encoder: affine InstanceNorm2d (+ optional ReLU) on an NHWC tensor.
+//
+// Replaces `norm_fn = "instance_affine"` + ReLU of the SLIM feature extractor (liso/slim/model/extractor.py:5-68,
+// 211-297: nn.InstanceNorm2d(C, eps=1e-3, affine=True) followed by nn.ReLU), which PyTorch runs as a copy to NCHW,
+// cuDNN's batch-norm kernel on (1, B*C, H, W), a copy back and a clamp.  Three launches, two passes over the data:
+//   k_in_stats     per (sample, slab of pixels): Welford mean / M2 per channel in fp32, lanes = channel groups of 4
+//                  (every load is a coalesced float4 of a pixel's channel vector)
+//   k_in_finalize  per (sample, channel): Chan merge of the slab partials in fp64 -> scale = gamma / sqrt(var + eps),
+//                  shift = beta - mean * scale   (biased variance, like F.instance_norm)
+//   k_in_apply     out = max(x * scale + shift, 0), float4
+// The convolutions themselves stay stock cuDNN.
+#include "common.cuh"
+
+namespace {
+
+constexpr int IN_THREADS = 256;
+constexpr int IN_MAX_SLABS = 64;
+
+struct InArgs {
+  const float* x;
+  const float* gamma;
+  const float* beta;
+  float* out;
+  float* partial;   // [batch][slabs][C][3] (count, mean, M2)
+  float* scale_shift;  // [batch][C][2]
+  int batch, hw, C, slabs, relu;
+  float eps;
+};
+
+__global__ void __launch_bounds__(IN_THREADS) k_in_stats(const InArgs a) {
+  __shared__ float s_cnt[IN_THREADS][4], s_mean[IN_THREADS][4], s_m2[IN_THREADS][4];
+  const int G = a.C >> 2;               // float4 groups per pixel
+  const int P = IN_THREADS / G;         // pixels per pass
+  const int b = blockIdx.y, slab = blockIdx.x;
+  const int g = threadIdx.x % G, p = threadIdx.x / G;
+  const int per_slab = (a.hw + a.slabs - 1) / a.slabs;
+  const int lo = slab * per_slab, hi = min(a.hw, lo + per_slab);
+  float cnt = 0.f, mean[4] = {0.f, 0.f, 0.f, 0.f}, m2[4] = {0.f, 0.f, 0.f, 0.f};
+  if (p < P) {
+    const float4* src = reinterpret_cast<const float4*>(a.x + (size_t)b * a.hw * a.C) + g;
+    for (int i = lo + p; i < hi; i += P) {
+      const float4 v = __ldg(src + (size_t)i * G);
+      cnt += 1.f;
+      const float inv = 1.f / cnt;
+      const float xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float d = xs[k] - mean[k];
+        mean[k] += d * inv;
+        m2[k] = fmaf(d, xs[k] - mean[k], m2[k]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    s_cnt[threadIdx.x][k] = cnt;
+    s_mean[threadIdx.x][k] = mean[k];
+    s_m2[threadIdx.x][k] = m2[k];
+  }
+  __syncthreads();
+  // thread (g, k) merges the P pixel-lanes of its channel in fixed order (Chan et al.)
+  if (threadIdx.x < a.C) {
+    const int c = threadIdx.x, gg = c >> 2, k = c & 3;
+    double n = 0.0, mu = 0.0, M2 = 0.0;
+    for (int q = 0; q < P; ++q) {
+      const int t = q * G + gg;
+      const double nb = s_cnt[t][k];
+      if (nb == 0.0) continue;
+      const double d = (double)s_mean[t][k] - mu, nn = n + nb;
+      mu += d * nb / nn;
+      M2 += (double)s_m2[t][k] + d * d * n * nb / nn;
+      n = nn;
+    }
+    float* o = a.partial + (((size_t)b * a.slabs + slab) * a.C + c) * 3;
+    o[0] = (float)n;
+    o[1] = (float)mu;
+    o[2] = (float)M2;
+  }
+}
+
+__global__ void __launch_bounds__(IN_THREADS) k_in_finalize(const InArgs a) {
+  const int i = blockIdx.x * IN_THREADS + threadIdx.x;
+  if (i >= a.batch * a.C) return;
+  const int b = i / a.C, c = i - b * a.C;
+  double n = 0.0, mu = 0.0, M2 = 0.0;
+  for (int s = 0; s < a.slabs; ++s) {
+    const float* p = a.partial + (((size_t)b * a.slabs + s) * a.C + c) * 3;
+    const double nb = p[0];
+    if (nb == 0.0) continue;
+    const double d = (double)p[1] - mu, nn = n + nb;
+    mu += d * nb / nn;
+    M2 += (double)p[2] + d * d * n * nb / nn;
+    n = nn;
+  }
+  const double var = n > 0 ? M2 / n : 0.0;  // biased, like F.instance_norm
+  const float scale = a.gamma[c] * (float)(1.0 / sqrt(var + (double)a.eps));
+  a.scale_shift[(size_t)i * 2] = scale;
+  a.scale_shift[(size_t)i * 2 + 1] = a.beta[c] - (float)mu * scale;
+}
+
+__global__ void __launch_bounds__(IN_THREADS) k_in_apply(const InArgs a) {
+  const int G = a.C >> 2;
+  const size_t per_sample = (size_t)a.hw * G;
+  const int b = blockIdx.y;
+  const float4* src = reinterpret_cast<const float4*>(a.x) + (size_t)b * per_sample;
+  float4* dst = reinterpret_cast<float4*>(a.out) + (size_t)b * per_sample;
+  const float* ss = a.scale_shift + (size_t)b * a.C * 2;
+  for (size_t i = (size_t)blockIdx.x * IN_THREADS + threadIdx.x; i < per_sample; i += (size_t)gridDim.x * IN_THREADS) {
+    const int g = (int)(i % G);
+    const float4 v = __ldg(src + i);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(ss + g * 8));      // scale0 shift0 scale1 shift1
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(ss + g * 8 + 4));  // scale2 shift2 scale3 shift3
+    float4 o;
+    o.x = fmaf(v.x, s0.x, s0.y);
+    o.y = fmaf(v.y, s0.z, s0.w);
+    o.z = fmaf(v.z, s1.x, s1.y);
+    o.w = fmaf(v.w, s1.z, s1.w);
+    if (a.relu) {
+      o.x = fmaxf(o.x, 0.f);
+      o.y = fmaxf(o.y, 0.f);
+      o.z = fmaxf(o.z, 0.f);
+      o.w = fmaxf(o.w, 0.f);
+    }
+    dst[i] = o;
+  }
+}
+
+int slabs_for(int hw) {
+  int s = hw / 2048;
+  return s < 1 ? 1 : (s > IN_MAX_SLABS ? IN_MAX_SLABS : s);
+}
+
+}  // namespace
+
+extern "C" size_t slimb200_instnorm_workspace_bytes(int32_t batch, int32_t channels, int32_t hw) {
+  if (batch < 1 || channels < 4 || hw < 1) return 0;
+  WorkspaceCarver w(nullptr);
+  w.take<float>((size_t)batch * slabs_for(hw) * channels * 3);
+  w.take<float>((size_t)batch * channels * 2);
+  return w.used();
+}
+
+extern "C" int slimb200_instnorm_nhwc(const float* x, const float* gamma, const float* beta, float eps, int32_t batch,
+                                      int32_t height, int32_t width, int32_t channels, int32_t relu, float* out,
+                                      void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!x || !gamma || !beta || !out || !workspace || batch < 1 || height < 1 || width < 1) return SLIMB200_E_INVALID;
+  if (channels < 4 || (channels & 3) || channels > IN_THREADS) return SLIMB200_E_UNSUPPORTED;
+  const long long hw = (long long)height * width;
+  if (hw > 0x7fffffffLL) return SLIMB200_E_UNSUPPORTED;
+  if (workspace_bytes < slimb200_instnorm_workspace_bytes(batch, channels, (int)hw)) return SLIMB200_E_WORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(workspace) & 255))
+    return SLIMB200_E_ALIGNMENT;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  InArgs a{};
+  a.x = x;
+  a.gamma = gamma;
+  a.beta = beta;
+  a.out = out;
+  a.batch = batch;
+  a.hw = (int)hw;
+  a.C = channels;
+  a.slabs = slabs_for((int)hw);
+  a.relu = relu;
+  a.eps = eps;
+  WorkspaceCarver w(workspace);
+  a.partial = w.take<float>((size_t)batch * a.slabs * channels * 3);
+  a.scale_shift = w.take<float>((size_t)batch * channels * 2);
+  SLIMB200_LAUNCH(SLIMB200_K_IN_STATS, stream, (k_in_stats<<<dim3(a.slabs, batch), IN_THREADS, 0, stream>>>(a)));
+  SLIMB200_LAUNCH(SLIMB200_K_IN_FINALIZE, stream,
+                  (k_in_finalize<<<(batch * channels + IN_THREADS - 1) / IN_THREADS, IN_THREADS, 0, stream>>>(a)));
+  const size_t per_sample = (size_t)hw * (channels >> 2);
+  const unsigned gx = (unsigned)((per_sample + IN_THREADS * 4 - 1) / (IN_THREADS * 4) < 148 * 4 ? (per_sample + IN_THREADS * 4 - 1) / (IN_THREADS * 4) : 148 * 4);
+  SLIMB200_LAUNCH(SLIMB200_K_IN_APPLY, stream, (k_in_apply<<<dim3(gx, batch), IN_THREADS, 0, stream>>>(a)));
+  return SLIMB200_OK;
+}
