@@ -3,18 +3,18 @@
 // Replaces `norm_fn = "instance_affine"` + ReLU of the SLIM feature extractor (liso/slim/model/extractor.py:5-68,
 // 211-297: nn.InstanceNorm2d(C, eps=1e-3, affine=True) followed by nn.ReLU), which PyTorch runs as a copy to NCHW,
 // cuDNN's batch-norm kernel on (1, B*C, H, W), a copy back and a clamp.  Three launches, two passes over the data:
-//   k_in_stats     per (sample, slab of pixels): Welford mean / M2 per channel in fp32, lanes = channel groups of 4
-//                  (every load is a coalesced float4 of a pixel's channel vector)
+//   k_in_stats     per (sample, slab of pixels): shifted sums -> (count, mean, M2) per channel, lanes = channel groups of
+//                  4 (every load is a coalesced float4 of a pixel's channel vector), Chan merge of the lanes in fp64
 //   k_in_finalize  per (sample, channel): Chan merge of the slab partials in fp64 -> scale = gamma / sqrt(var + eps),
-//                  shift = beta - mean * scale   (biased variance, like F.instance_norm)
-//   k_in_apply     out = max(x * scale + shift, 0), float4
+//                  shift = beta - mean * scale (biased variance, like F.instance_norm)
+//   k_in_apply     out = max(x * scale + shift, 0) as float4
 // The convolutions themselves stay stock cuDNN.
 #include "common.cuh"
 
 namespace {
 
 constexpr int IN_THREADS = 256;
-constexpr int IN_MAX_SLABS = 64;
+constexpr int IN_MAX_SLABS = 128;
 
 struct InArgs {
   const float* x;
@@ -35,20 +35,32 @@ __global__ void __launch_bounds__(IN_THREADS) k_in_stats(const InArgs a) {
   const int g = threadIdx.x % G, p = threadIdx.x / G;
   const int per_slab = (a.hw + a.slabs - 1) / a.slabs;
   const int lo = slab * per_slab, hi = min(a.hw, lo + per_slab);
+  // shifted sums (shift = the lane's first sample, so the sums stay small and s2 - s1^2/n does not cancel): two FMAs
+  // per element, no division in the loop; converted to (count, mean, M2) for the Chan merges
   float cnt = 0.f, mean[4] = {0.f, 0.f, 0.f, 0.f}, m2[4] = {0.f, 0.f, 0.f, 0.f};
-  if (p < P) {
+  if (p < P && lo + p < hi) {
     const float4* src = reinterpret_cast<const float4*>(a.x + (size_t)b * a.hw * a.C) + g;
+    const float4 k4 = __ldg(src + (size_t)(lo + p) * G);
+    const float K[4] = {k4.x, k4.y, k4.z, k4.w};
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    int n = 0;
+#pragma unroll 4
     for (int i = lo + p; i < hi; i += P) {
       const float4 v = __ldg(src + (size_t)i * G);
-      cnt += 1.f;
-      const float inv = 1.f / cnt;
       const float xs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float d = xs[k] - mean[k];
-        mean[k] += d * inv;
-        m2[k] = fmaf(d, xs[k] - mean[k], m2[k]);
+        const float d = xs[k] - K[k];
+        s1[k] += d;
+        s2[k] = fmaf(d, d, s2[k]);
       }
+      ++n;
+    }
+    cnt = (float)n;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      mean[k] = K[k] + s1[k] / cnt;
+      m2[k] = fmaxf(s2[k] - s1[k] * s1[k] / cnt, 0.f);
     }
   }
 #pragma unroll
@@ -78,10 +90,8 @@ __global__ void __launch_bounds__(IN_THREADS) k_in_stats(const InArgs a) {
   }
 }
 
-__global__ void __launch_bounds__(IN_THREADS) k_in_finalize(const InArgs a) {
-  const int i = blockIdx.x * IN_THREADS + threadIdx.x;
-  if (i >= a.batch * a.C) return;
-  const int b = i / a.C, c = i - b * a.C;
+// per (sample, channel): Chan merge of the slab partials in fp64 -> (scale, shift)
+__device__ __forceinline__ float2 in_scale_shift(const InArgs& a, int b, int c) {
   double n = 0.0, mu = 0.0, M2 = 0.0;
   for (int s = 0; s < a.slabs; ++s) {
     const float* p = a.partial + (((size_t)b * a.slabs + s) * a.C + c) * 3;
@@ -94,10 +104,18 @@ __global__ void __launch_bounds__(IN_THREADS) k_in_finalize(const InArgs a) {
   }
   const double var = n > 0 ? M2 / n : 0.0;  // biased, like F.instance_norm
   const float scale = a.gamma[c] * (float)(1.0 / sqrt(var + (double)a.eps));
-  a.scale_shift[(size_t)i * 2] = scale;
-  a.scale_shift[(size_t)i * 2 + 1] = a.beta[c] - (float)mu * scale;
+  return make_float2(scale, a.beta[c] - (float)mu * scale);
 }
 
+__global__ void __launch_bounds__(IN_THREADS) k_in_finalize(const InArgs a) {
+  const int i = blockIdx.x * IN_THREADS + threadIdx.x;
+  if (i >= a.batch * a.C) return;
+  const float2 ss = in_scale_shift(a, i / a.C, i % a.C);
+  a.scale_shift[(size_t)i * 2] = ss.x;
+  a.scale_shift[(size_t)i * 2 + 1] = ss.y;
+}
+
+// out = max(x * scale + shift, 0), float4
 __global__ void __launch_bounds__(IN_THREADS) k_in_apply(const InArgs a) {
   const int G = a.C >> 2;
   const size_t per_sample = (size_t)a.hw * G;
@@ -126,7 +144,7 @@ __global__ void __launch_bounds__(IN_THREADS) k_in_apply(const InArgs a) {
 }
 
 int slabs_for(int hw) {
-  int s = hw / 2048;
+  int s = hw / 1024;
   return s < 1 ? 1 : (s > IN_MAX_SLABS ? IN_MAX_SLABS : s);
 }
 
