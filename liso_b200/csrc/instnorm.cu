@@ -90,10 +90,14 @@ __global__ void __launch_bounds__(IN_THREADS) k_in_stats(const InArgs a) {
   }
 }
 
-// per (sample, channel): Chan merge of the slab partials in fp64 -> (scale, shift)
-__device__ __forceinline__ float2 in_scale_shift(const InArgs& a, int b, int c) {
+// one warp per (sample, channel): lanes merge strided subsets of the slab partials, then a butterfly of Chan merges
+__global__ void __launch_bounds__(IN_THREADS) k_in_finalize(const InArgs a) {
+  const int i = (blockIdx.x * IN_THREADS + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= a.batch * a.C) return;
+  const int b = i / a.C, c = i - b * a.C;
   double n = 0.0, mu = 0.0, M2 = 0.0;
-  for (int s = 0; s < a.slabs; ++s) {
+  for (int s = lane; s < a.slabs; s += 32) {
     const float* p = a.partial + (((size_t)b * a.slabs + s) * a.C + c) * 3;
     const double nb = p[0];
     if (nb == 0.0) continue;
@@ -102,17 +106,26 @@ __device__ __forceinline__ float2 in_scale_shift(const InArgs& a, int b, int c) 
     M2 += (double)p[2] + d * d * n * nb / nn;
     n = nn;
   }
-  const double var = n > 0 ? M2 / n : 0.0;  // biased, like F.instance_norm
-  const float scale = a.gamma[c] * (float)(1.0 / sqrt(var + (double)a.eps));
-  return make_float2(scale, a.beta[c] - (float)mu * scale);
-}
-
-__global__ void __launch_bounds__(IN_THREADS) k_in_finalize(const InArgs a) {
-  const int i = blockIdx.x * IN_THREADS + threadIdx.x;
-  if (i >= a.batch * a.C) return;
-  const float2 ss = in_scale_shift(a, i / a.C, i % a.C);
-  a.scale_shift[(size_t)i * 2] = ss.x;
-  a.scale_shift[(size_t)i * 2 + 1] = ss.y;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const double nb = __shfl_xor_sync(0xffffffffu, n, d), mb = __shfl_xor_sync(0xffffffffu, mu, d),
+                 Mb = __shfl_xor_sync(0xffffffffu, M2, d);
+    const double nn = n + nb;
+    if (nn > 0.0) {
+      const double dl = mb - mu;
+      // symmetric form so that both partners of the exchange compute the same merged triple
+      const double mu_new = (n * mu + nb * mb) / nn;
+      M2 = M2 + Mb + dl * dl * n * nb / nn;
+      mu = mu_new;
+      n = nn;
+    }
+  }
+  if (lane == 0) {
+    const double var = n > 0 ? M2 / n : 0.0;  // biased, like F.instance_norm
+    const float scale = a.gamma[c] * (float)(1.0 / sqrt(var + (double)a.eps));
+    a.scale_shift[(size_t)i * 2] = scale;
+    a.scale_shift[(size_t)i * 2 + 1] = a.beta[c] - (float)mu * scale;
+  }
 }
 
 // out = max(x * scale + shift, 0), float4
@@ -185,7 +198,7 @@ extern "C" int slimb200_instnorm_nhwc(const float* x, const float* gamma, const 
   a.scale_shift = w.take<float>((size_t)batch * channels * 2);
   SLIMB200_LAUNCH(SLIMB200_K_IN_STATS, stream, (k_in_stats<<<dim3(a.slabs, batch), IN_THREADS, 0, stream>>>(a)));
   SLIMB200_LAUNCH(SLIMB200_K_IN_FINALIZE, stream,
-                  (k_in_finalize<<<(batch * channels + IN_THREADS - 1) / IN_THREADS, IN_THREADS, 0, stream>>>(a)));
+                  (k_in_finalize<<<(batch * channels * 32 + IN_THREADS - 1) / IN_THREADS, IN_THREADS, 0, stream>>>(a)));
   const size_t per_sample = (size_t)hw * (channels >> 2);
   const unsigned gx = (unsigned)((per_sample + IN_THREADS * 4 - 1) / (IN_THREADS * 4) < 148 * 4 ? (per_sample + IN_THREADS * 4 - 1) / (IN_THREADS * 4) : 148 * 4);
   SLIMB200_LAUNCH(SLIMB200_K_IN_APPLY, stream, (k_in_apply<<<dim3(gx, batch), IN_THREADS, 0, stream>>>(a)));

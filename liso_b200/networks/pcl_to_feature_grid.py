@@ -167,7 +167,7 @@ class PointsPillarFeatureNetWrapper(nn.Module):
             out.append(t)
         return out
 
-    def _encode(self, pts: Sequence[torch.Tensor], want_voxels: bool, raw_scan: bool = False):
+    def _encode(self, pts: Sequence[torch.Tensor], want_voxels: bool, raw_scan: bool = False, out=None):
         assert isinstance(pts, (list, tuple)), type(pts)
         lib = _lib.load()
         pfn = self.pts_voxel_encoder.pfn_layers[0]
@@ -181,8 +181,14 @@ class PointsPillarFeatureNetWrapper(nn.Module):
         ny, nx = self.pts_middle_encoder.ny, self.pts_middle_encoder.nx
         total = int(sum(t.shape[0] for t in pts))
         fmt = torch.channels_last if p.canvas_layout == _lib.CANVAS_NHWC else torch.contiguous_format
-        canvas = torch.empty((B, p.c_out, ny, nx), dtype=torch.float32, device=dev, memory_format=fmt)
-        occupancy = torch.empty((B, 1, ny, nx), dtype=torch.float32, device=dev)
+        if out is not None:  # caller-owned outputs (e.g. the static inputs of a CUDA graph)
+            canvas, occupancy = out
+            if (tuple(canvas.shape) != (B, p.c_out, ny, nx) or tuple(occupancy.shape) != (B, 1, ny, nx)
+                    or canvas.dtype != torch.float32 or not canvas.is_contiguous(memory_format=fmt)
+                    or not occupancy.is_contiguous() or canvas.device != dev):
+                raise ValueError("out= buffers do not match the canvas this call produces")
+        else:
+            canvas, occupancy = self.empty_outputs(B, dev)
         ws_bytes = lib.slimb200_pillar_workspace_bytes(B, total, C.byref(p))
         if ws_bytes == 0:
             raise RuntimeError("slimb200_pillar_workspace_bytes rejected the configuration")
@@ -218,6 +224,15 @@ class PointsPillarFeatureNetWrapper(nn.Module):
             norm.num_batches_tracked += 1
         return canvas, occupancy, extra
 
+    def empty_outputs(self, batch: int, device):
+        """Uninitialised (canvas, occupancy) with the shapes / memory format ``forward`` returns."""
+        c_out = self.pts_voxel_encoder.pfn_layers[0].units
+        nhwc = self.canvas_memory_format == "channels_last" and c_out in (4, 8, 16, 32, 64)
+        ny, nx = self.pts_middle_encoder.ny, self.pts_middle_encoder.nx
+        canvas = torch.empty((batch, c_out, ny, nx), dtype=torch.float32, device=device,
+                             memory_format=torch.channels_last if nhwc else torch.contiguous_format)
+        return canvas, torch.empty((batch, 1, ny, nx), dtype=torch.float32, device=device)
+
     # ------------------------------------------------------------------ reference interface
     @torch.no_grad()
     def voxelize(self, points):
@@ -237,16 +252,16 @@ class PointsPillarFeatureNetWrapper(nn.Module):
         return dict(voxels=ex["voxels"][:n], num_points=ex["num_points"][:n], coors=ex["coors"][:n],
                     pt2pillar=ex["pt2pillar"], pillar_counts=ex["pillar_counts"], canvas=canvas, occupancy=occ)
 
-    def extract_pts_feat(self, pts, raw_scan: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+    def extract_pts_feat(self, pts, raw_scan: bool = False, out=None) -> Tuple[torch.Tensor, torch.Tensor]:
         if torch.is_grad_enabled() and any(q.requires_grad for q in self.parameters()):
             raise RuntimeError(
                 "liso_b200 pillar encoder is forward-only (flow export): call it under torch.no_grad() "
                 "or freeze its parameters; autograd through the fused kernel is not provided")
         with torch.no_grad():
-            canvas, occupancy, _ = self._encode(pts, want_voxels=False, raw_scan=raw_scan)
+            canvas, occupancy, _ = self._encode(pts, want_voxels=False, raw_scan=raw_scan, out=out)
         return canvas, occupancy
 
-    def forward(self, pcl_t0, img_t0=None, raw_scan: bool = False):
+    def forward(self, pcl_t0, img_t0=None, raw_scan: bool = False, out=None):
         """``raw_scan=True``: ``pcl_t0`` are raw scans (with ground); the ground points are dropped inside the kernel
         with the dataset's cone rule, which gives the same canvas as passing ``pcl_full_no_ground``."""
-        return self.extract_pts_feat(pcl_t0, raw_scan=raw_scan)
+        return self.extract_pts_feat(pcl_t0, raw_scan=raw_scan, out=out)

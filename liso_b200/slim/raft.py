@@ -284,8 +284,8 @@ class RAFT(nn.Module):
         # "all": one (B,H,W,8) output per GRU iteration like the reference (raft_mod.py:216-257); "last": only the
         # final one is up-sampled / assembled (the flow export reads nothing else, experiment.py:391-399)
         self.output_iterations = "all"
-        # capture the GRU refinement loop in a CUDA graph (inference on CUDA only; falls back to eager launches of the
-        # same kernels when switched off)
+        # capture everything between the pillar encoder and the decoder in a CUDA graph (inference on CUDA only; the same
+        # kernels are launched eagerly when switched off)
         self.use_cuda_graph = True
         self._graphs = {}
         rows = float(cfg.data.bev_range_m[0]) / cfg.data.img_grid_size[0] * m.u_net.final_scale
@@ -305,14 +305,63 @@ class RAFT(nn.Module):
         """``raw_scans``: the clouds are raw scans with ground (``liso_b200.datasets.preprocess_scans``); the encoder
         applies the dataset's ground rule itself."""
         kw = {"raw_scan": True} if raw_scans else {}  # (the reference signature is forward(pcl, img=None))
-        img_t0, occ_t0 = self.pp_layer(pcl_t0, **kw)
-        img_t1, occ_t1 = self.pp_layer(pcl_t1, **kw)
-        aux = {"t0": {"bev_net_input_dbg": occ_t0}, "t1": {"bev_net_input_dbg": occ_t1}}
+        dev = pcl_t0[0].device
+        use_graph = (self.use_cuda_graph and FAST_STOCK_OPS and dev.type == "cuda" and not torch.is_grad_enabled()
+                     and not self.training and not torch.cuda.is_current_stream_capturing()
+                     and len(pcl_t0) == len(pcl_t1) and hasattr(self.pp_layer, "empty_outputs"))
+        if not use_graph:
+            img_t0, occ_t0 = self.pp_layer(pcl_t0, **kw)
+            img_t1, occ_t1 = self.pp_layer(pcl_t1, **kw)
+            fw, bw = self._net_body(img_t0, img_t1)
+            return fw, bw, {"t0": {"bev_net_input_dbg": occ_t0}, "t1": {"bev_net_input_dbg": occ_t1}}
+
+        # ---- everything between the pillar encoder and the decoder as ONE CUDA graph (SURVEY 8f.2): the encoder writes
+        # its canvases straight into the graph's static inputs; ~800 launches per step become one graph launch.
+        # The captured kernels hold raw pointers to the weights (and to cached concatenations of them): any in-place
+        # update or re-allocation of a parameter invalidates the graph.
+        B = len(pcl_t0)
+        wsig = tuple((p.data_ptr(), p._version) for mod in (self.fnet, self.cnet, self.update_block) for p in mod.parameters())
+        key = (B, self.output_iterations, self.pp_layer.canvas_memory_format, str(dev), torch.backends.cudnn.allow_tf32, wsig)
+        st = self._graphs.get("net")
+        if st is not None and st["key"] != key:
+            st = None  # (the old graph and its buffers are released when the slot is overwritten)
+        if st is None:
+            st = {"key": key, "in": [self.pp_layer.empty_outputs(B, dev) for _ in range(2)]}
+        self.pp_layer(pcl_t0, out=st["in"][0], **kw)
+        self.pp_layer(pcl_t1, out=st["in"][1], **kw)
+        if "graph" not in st:
+            self._capture_net_graph(st, dev)
+        st["graph"].replay()
+        _lib_mod().note_graph_replay(st["launches"])
+        aux = {"t0": {"bev_net_input_dbg": st["in"][0][1]}, "t1": {"bev_net_input_dbg": st["in"][1][1]}}
+        return st["outs"][0], st["outs"][1], aux
+
+    def _net_body(self, img_t0, img_t1):
+        """Feature encoders, correlation pyramids, context encoders and both refinement loops (raft_mod.py:82-257)."""
         fmap_t0 = self.fnet(img_t0)
         fmap_t1 = self.fnet(img_t1)
-        fw = self.predict_single_flow_map_and_classes(img_t0, fmap_t0, fmap_t1, self.head_decoder_fw, slot=0)
-        bw = self.predict_single_flow_map_and_classes(img_t1, fmap_t1, fmap_t0, self.head_decoder_bw, slot=1)
-        return fw, bw, aux
+        fw = self.predict_single_flow_map_and_classes(img_t0, fmap_t0, fmap_t1, self.head_decoder_fw)
+        bw = self.predict_single_flow_map_and_classes(img_t1, fmap_t1, fmap_t0, self.head_decoder_bw)
+        return fw, bw
+
+    def _capture_net_graph(self, st, dev):
+        lib = _lib_mod()
+        img_t0, img_t1 = st["in"][0][0], st["in"][1][0]
+        # warm-up on a side stream (cuDNN autotuning, lazy kernel attributes), as torch.cuda.graphs asks
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._net_body(img_t0, img_t1)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        n0 = lib.load().slimb200_launch_count(-1)
+        with torch.cuda.graph(graph):
+            st["outs"] = self._net_body(img_t0, img_t1)
+        st["launches"] = int(lib.load().slimb200_launch_count(-1) - n0)  # library kernels inside one replay
+        st["graph"] = graph
+        self._graphs["net"] = st
+        self.n_graph_captures = getattr(self, "n_graph_captures", 0) + 1
 
     def _gru_loop(self, correlation, net, inp, img_hw, batch, device) -> List[torch.Tensor]:
         """The refinement loop of ``raft_mod.py:188-257``: lookup -> update block -> coordinate / logit update, and the
@@ -344,60 +393,9 @@ class RAFT(nn.Module):
             outs.append(concat2network_output(uplogits_n(logits, n=ds), flow_m, flow_m))
         return outs
 
-    def predict_single_flow_map_and_classes(self, img_t0, fmap_t0, fmap_t1, decoder=None, slot: int = 0) -> List[torch.Tensor]:
+    def predict_single_flow_map_and_classes(self, img_t0, fmap_t0, fmap_t1, decoder=None) -> List[torch.Tensor]:
         m = self.slim_cfg.model
         b, _, H, W = img_t0.shape
-        dev = img_t0.device
-        use_graph = (self.use_cuda_graph and FAST_STOCK_OPS and img_t0.is_cuda and not torch.is_grad_enabled()
-                     and not self.training and not torch.cuda.is_current_stream_capturing())
-        if not use_graph:
-            correlation = CorrBlock(fmap_t0, fmap_t1, num_levels=m.corr_cfg.num_levels, radius=m.corr_cfg.search_radius)
-            net, inp = torch.split(self.cnet(img_t0), [self.hidden_dim, self.context_dim], dim=1)
-            return self._gru_loop(correlation, torch.tanh(net), torch.relu(inp), (H, W), b, dev)
-
-        # ---- CUDA-graphed refinement loop: ~270 small launches per direction become one graph launch.
-        # The graph reads three static buffers (pyramid, net, inp) and owns its outputs; one graph per direction slot,
-        # so the forward outputs survive the backward replay.
-        nhwc = fmap_t0.is_contiguous(memory_format=torch.channels_last) and not fmap_t0.is_contiguous()
-        # the captured kernels hold raw pointers to the update-block weights (and to cached concatenations of them):
-        # any in-place update or re-allocation of a parameter invalidates the graph
-        wsig = tuple((p.data_ptr(), p._version) for p in self.update_block.parameters())
-        key = (b, H, W, self.output_iterations, nhwc, str(dev), torch.backends.cudnn.allow_tf32, wsig)
-        st = self._graphs.get(slot)
-        if st is not None and st["key"] != key:
-            st = None  # (the old graph and its buffers are released when the slot is overwritten)
+        correlation = CorrBlock(fmap_t0, fmap_t1, num_levels=m.corr_cfg.num_levels, radius=m.corr_cfg.search_radius)
         net, inp = torch.split(self.cnet(img_t0), [self.hidden_dim, self.context_dim], dim=1)
-        net, inp = torch.tanh(net), torch.relu(inp)
-        if st is None:
-            st = self._capture_gru_graph(slot, key, fmap_t0, fmap_t1, net, inp, (H, W), b, dev)
-        else:
-            st["corr"].rebuild(fmap_t0, fmap_t1)
-            st["net"].copy_(net)
-            st["inp"].copy_(inp)
-        st["graph"].replay()
-        _lib_mod().note_graph_replay(st["launches"])
-        return st["outs"]
-
-    def _capture_gru_graph(self, slot, key, fmap_t0, fmap_t1, net, inp, img_hw, batch, dev):
-        m = self.slim_cfg.model
-        lib = _lib_mod()
-        corr = CorrBlock(fmap_t0, fmap_t1, num_levels=m.corr_cfg.num_levels, radius=m.corr_cfg.search_radius)
-        st = {"corr": corr, "net": net.clone(), "inp": inp.clone()}
-        # warm-up on a side stream (cuDNN autotuning, lazy kernel attributes), as torch.cuda.graphs asks
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            for _ in range(2):
-                self._gru_loop(corr, st["net"], st["inp"], img_hw, batch, dev)
-        torch.cuda.current_stream(dev).wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        n0 = lib.load().slimb200_launch_count(-1)
-        with torch.cuda.graph(graph):
-            st["outs"] = self._gru_loop(corr, st["net"], st["inp"], img_hw, batch, dev)
-        st["launches"] = int(lib.load().slimb200_launch_count(-1) - n0)  # library kernels inside one replay
-        st["graph"] = graph
-        st["key"] = key
-        self._graphs[slot] = st
-        self.n_graph_captures = getattr(self, "n_graph_captures", 0) + 1
-        return st
-
+        return self._gru_loop(correlation, torch.tanh(net), torch.relu(inp), (H, W), b, img_t0.device)
