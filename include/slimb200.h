@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SLIMB200_VERSION 101
+#define SLIMB200_VERSION 102
 
 enum {
   SLIMB200_OK = 0,
@@ -242,11 +242,44 @@ int slimb200_raft_output(const float* flow, const float* logits, int32_t batch, 
 /* Glue for the channels-last feature encoder: affine InstanceNorm2d (eps, biased variance) + optional ReLU on an
  * NHWC tensor -- `norm_fn = "instance_affine"` + ReLU of liso/slim/model/extractor.py:5-68,211-297 -- in three
  * launches and two passes over the data (PyTorch: copy to NCHW, cuDNN batch-norm on (1, B*C, H, W), copy back, clamp).
- * x, out: device (batch, height, width, channels) f32, 16-byte aligned (out may alias x); channels % 4 == 0, <= 256. */
+ * x, out: device (batch, height, width, channels) f32, 16-byte aligned (out may alias x); channels % 4 == 0, <= 256.
+ * relu: bit 0 = ReLU right after the normalisation; residual (optional, same shape) is added after that, and bit 1 =
+ * ReLU after the addition -- the residual join `relu(x + y)` of extractor.py:57-68 fused into the same pass. */
 size_t slimb200_instnorm_workspace_bytes(int32_t batch, int32_t channels, int32_t hw);
 int slimb200_instnorm_nhwc(const float* x, const float* gamma, const float* beta, float eps, int32_t batch,
-                           int32_t height, int32_t width, int32_t channels, int32_t relu, float* out,
-                           void* workspace, size_t workspace_bytes, void* stream);
+                           int32_t height, int32_t width, int32_t channels, int32_t relu, const float* residual,
+                           float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* SURVEY 8(f).2 glue between the stock convolutions of the ConvGRU update block (liso/slim/model/update.py:23-38,
+ * 70-93,130-150; raft_mod.py:188-212), all on channels-last fp32 tensors given as (pixels = batch*h*w, channels) rows.
+ * The two 304-channel GRU convolution inputs [h | x] and [r*h | x] are persistent caller buffers; these entry points
+ * write their channel slots directly instead of torch.cat + separate element-wise launches.  Channel counts, channel
+ * offsets and pitches are in floats and must be multiples of 4; pointers 16-byte aligned.
+ *
+ * nhwc_pack: concatenate n_src (<= 4) PACKED sources (pitch == channels) along channels and store the result at
+ *   channel offset dst_channel_offset[d] of each of the n_dst (<= 2) destinations with row pitch dst_pitch[d].
+ *   src / src_channels / dst / dst_channel_offset / dst_pitch are HOST arrays.
+ * gru_gate_zr: zr_raw (pixels, 2*hidden) = conv output WITHOUT bias of the stacked update|reset gate convolution,
+ *   bias_zr (2*hidden); z_out (pixels, hidden) = sigmoid(zr[:, :hidden] + b); rhx[:, :hidden] = sigmoid(zr[:, hidden:] + b) * hx[:, :hidden].
+ * gru_gate_out: q_raw (pixels, hidden) conv output without bias; hx[:, :hidden] <- (1 - z) * h + z * tanh(q_raw + b),
+ *   in place, and the same rows packed into h_out (pixels, hidden) for the two heads.
+ * iter_update: raw head outputs (no bias) of FlowOrClassificationHead (update.py:6-20) addressed as
+ *   base + b*C*h*w + c*channel_stride + pix*pixel_stride (NCHW: (h*w, 1); channels-last: (1, C));
+ *   coords1 (batch,2,h,w) += dflow + bias; logits (batch,n_logits,h,w) += dlogits + bias; flow = coords1 - coords_grid
+ *   (channel 0 = column, channel 1 = row: raft_code/utils.py:32-37); coords1 / flow / logits are NCHW contiguous.
+ * add_relu: out = relu(x + y) over n floats (residual join of extractor.py:57-68; out may alias x or y). */
+int slimb200_nhwc_pack(const float* const* src, const int32_t* src_channels, int32_t n_src, float* const* dst,
+                       const int32_t* dst_channel_offset, const int32_t* dst_pitch, int32_t n_dst, int64_t pixels,
+                       void* stream);
+int slimb200_gru_gate_zr(const float* zr_raw, const float* bias_zr, const float* hx, int32_t hx_pitch, float* z_out,
+                         float* rhx, int32_t rhx_pitch, int32_t hidden, int64_t pixels, void* stream);
+int slimb200_gru_gate_out(const float* q_raw, const float* bias_q, const float* z, float* hx, int32_t hx_pitch,
+                          float* h_out, int32_t hidden, int64_t pixels, void* stream);
+int slimb200_iter_update(const float* dflow_raw, int64_t dflow_channel_stride, int64_t dflow_pixel_stride,
+                         const float* bias_flow, const float* dlogits_raw, int64_t dlogits_channel_stride,
+                         int64_t dlogits_pixel_stride, const float* bias_logits, int32_t n_logits, int32_t batch,
+                         int32_t h, int32_t w, float* coords1, float* flow, float* logits, void* stream);
+int slimb200_add_relu(const float* x, const float* y, float* out, int64_t n, void* stream);
 
 const char* slimb200_strerror(int code);
 int slimb200_version(void);
@@ -284,6 +317,11 @@ enum {
   SLIMB200_K_IN_STATS,
   SLIMB200_K_IN_FINALIZE,
   SLIMB200_K_IN_APPLY,
+  SLIMB200_K_NHWC_PACK,
+  SLIMB200_K_GRU_GATE_ZR,
+  SLIMB200_K_GRU_GATE_OUT,
+  SLIMB200_K_ITER_UPDATE,
+  SLIMB200_K_ADD_RELU,
   SLIMB200_N_KERNELS
 };
 int slimb200_profile_begin(void);

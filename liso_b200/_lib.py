@@ -122,8 +122,27 @@ SYMBOLS = {
     "slimb200_instnorm_nhwc": (
         C.c_int,
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
-         C.c_void_p, C.c_size_t, C.c_void_p],
+         C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p],
     ),
+    "slimb200_nhwc_pack": (
+        C.c_int,
+        [C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int32),
+         C.POINTER(C.c_int32), C.c_int32, C.c_int64, C.c_void_p],
+    ),
+    "slimb200_gru_gate_zr": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p],
+    ),
+    "slimb200_gru_gate_out": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p],
+    ),
+    "slimb200_iter_update": (
+        C.c_int,
+        [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
+         C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+    ),
+    "slimb200_add_relu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "slimb200_strerror": (C.c_char_p, [C.c_int]),
     "slimb200_version": (C.c_int, []),
     "slimb200_profile_begin": (C.c_int, []),
@@ -131,7 +150,7 @@ SYMBOLS = {
     "slimb200_launch_count": (C.c_int64, [C.c_int32]),
     "slimb200_kernel_name": (C.c_char_p, [C.c_int32]),
 }
-N_KERNELS = 27
+N_KERNELS = 32
 K_TILE_ENCODE, K_PILLAR_NHWC, K_FEAT_TRANSPOSE, K_FEAT_PACK, K_CORR_GEMM, K_CORR_LOOKUP = 6, 7, 8, 9, 10, 11
 K_DECODE_BEV, K_DECODE_POINTS, K_DECODE_AGGR, K_RAFT_OUTPUT = 14, 15, 17, 18
 CANVAS_NCHW, CANVAS_NHWC = 0, 1

@@ -251,7 +251,10 @@ struct V3 {
   static constexpr int EPC = Elem<T>::EPC;
   static constexpr int NCHUNK = Cfg<T, 3>::NCHUNK;       // 2 (bf16) / 3 (fp32) 16-byte chunks per row segment
   static constexpr int WPR = W1 * (int)sizeof(T) / 4;    // 32-bit words per aligned window row: 4 / 8
-  __host__ __device__ static constexpr int win_words(int levels) { return levels * W1 * WPR * LK_PIX; }
+  // shared-memory window: one extra row and one extra word per row (window element 8 [and 9]) for windows whose
+  // per-offset floors are not all `origin + offset` (see the "shifted" mode in the kernel)
+  static constexpr int SROWS = W1 + 1, SWPR = WPR + 1;
+  __host__ __device__ static constexpr int win_words(int levels) { return levels * SROWS * SWPR * LK_PIX; }
   __host__ __device__ static constexpr int tab_words(int levels) { return levels * 2 * WIN * LK_PIX; }
   __host__ __device__ static constexpr int smem_bytes(int levels, bool nhwc) {
     return (win_words(levels) + 3 * tab_words(levels) + 3 * levels * LK_PIX + (nhwc ? LK_PIX * (levels * WIN * WIN + 1) : 0)) * 4;
@@ -280,24 +283,25 @@ SLIMB200_WIN_ELEM_BF16(4) SLIMB200_WIN_ELEM_BF16(5) SLIMB200_WIN_ELEM_BF16(6) SL
 template <typename T>
 __device__ __forceinline__ void realign(const uint32_t* ld, int s, uint32_t* out);
 template <>
-__device__ __forceinline__ void realign<float>(const uint32_t* ld, int s, uint32_t* out) {  // 12 words in, s in 0..3, 8 out
+__device__ __forceinline__ void realign<float>(const uint32_t* ld, int s, uint32_t* out) {  // 12 words in, s in 0..3, 9 out
   uint32_t t[10];
 #pragma unroll
   for (int k = 0; k < 10; ++k) t[k] = (s & 2) ? ld[k + 2] : ld[k];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) out[k] = (s & 1) ? t[k + 1] : t[k];
+  for (int k = 0; k < 9; ++k) out[k] = (s & 1) ? t[k + 1] : t[k];
 }
 template <>
-__device__ __forceinline__ void realign<__nv_bfloat16>(const uint32_t* ld, int s, uint32_t* out) {  // 8 words in, s in 0..7, 4 out
-  const int ws = s >> 1;
-  uint32_t t[7], x[5];
+__device__ __forceinline__ void realign<__nv_bfloat16>(const uint32_t* ld, int s, uint32_t* out) {  // 8 words in, s in 0..7, 5 out
+  const int ws = s >> 1;                                                                               // (elements 0..8 valid)
+  uint32_t t[8], x[6];
 #pragma unroll
   for (int k = 0; k < 7; ++k) t[k] = (ws & 1) ? ld[k + 1] : ld[k];
+  t[7] = (ws & 1) ? 0u : ld[7];
 #pragma unroll
-  for (int k = 0; k < 5; ++k) x[k] = (ws & 2) ? t[k + 2] : t[k];
+  for (int k = 0; k < 6; ++k) x[k] = (ws & 2) ? (k + 2 < 8 ? t[k + 2] : 0u) : t[k];
   const int sh = (s & 1) * 16;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) out[k] = __funnelshift_r(x[k], x[k + 1], sh);
+  for (int k = 0; k < 5; ++k) out[k] = __funnelshift_r(x[k], x[k + 1], sh);
 }
 
 template <typename T, int I0, int I1>
@@ -329,22 +333,68 @@ __device__ __forceinline__ void v3_columns(const uint32_t (*win)[V3<T>::WPR], co
   }
 }
 
+// one window row of one pixel: NCHUNK 16-byte loads (predicated on the valid column range), returns the shift that
+// re-aligns the row to window column 0
+template <typename T>
+__device__ __forceinline__ int v3_fetch_row(const T* __restrict__ pyr, int n_panels, int nf, int b, int pix, int off, int W, int H,
+                                            int xb, int y, int n_elems, bool okp, uint32_t* ld) {
+  constexpr int EPC = V3<T>::EPC, NCHUNK = V3<T>::NCHUNK;
+  const bool row_ok = okp && (unsigned)y < (unsigned)H;
+  const int row0 = off + y * W;
+  const int a_start = row0 + xb;
+  const int ca = a_start & ~(EPC - 1);
+  const int lo = row0 + max(xb, 0), hi = row0 + min(xb + n_elems, W);
+#pragma unroll
+  for (int c = 0; c < NCHUNK; ++c) {
+    const int col = ca + c * EPC;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (row_ok && col < hi && col + EPC > lo)
+      v = __ldg(reinterpret_cast<const uint4*>(pyr + panel_index<T>(n_panels, nf, b, pix, col)));
+    ld[c * 4 + 0] = v.x;
+    ld[c * 4 + 1] = v.y;
+    ld[c * 4 + 2] = v.z;
+    ld[c * 4 + 3] = v.w;
+  }
+  return a_start - ca;
+}
+
+// window element e (0..8) of row r from the shared-memory window (run-time indices: the "shifted" mode)
+template <typename T>
+__device__ __forceinline__ float v3_smem_elem(const uint32_t* s_win, int l, int r, int e, int lane);
+template <>
+__device__ __forceinline__ float v3_smem_elem<float>(const uint32_t* s_win, int l, int r, int e, int lane) {
+  return __uint_as_float(s_win[((size_t)((l * V3<float>::SROWS + r) * V3<float>::SWPR + e)) * LK_PIX + lane]);
+}
+template <>
+__device__ __forceinline__ float v3_smem_elem<__nv_bfloat16>(const uint32_t* s_win, int l, int r, int e, int lane) {
+  using V = V3<__nv_bfloat16>;
+  const uint32_t w = s_win[((size_t)((l * V::SROWS + r) * V::SWPR + (e >> 1))) * LK_PIX + lane];
+  return __uint_as_float((e & 1) ? (w & 0xffff0000u) : (w << 16));
+}
+
 // NHWC: the output is channels-last (batch, h, w, channels): the CTA's 32 pixels x 196 channels form one contiguous
 // block, staged through shared memory and written with fully coalesced rows.
+//
+// Window modes per (pixel, level), from the per-offset floors f_o of the sample positions (origin = min_o(f_o - o)):
+//   1 "regular"  f_o == origin + o for all 7 offsets on both axes (any non-integer position): 8 x 8 window, registers
+//   2 "shifted"  f_o - o - origin in {0, 1}: positions that sit on integers (the first GRU iteration: coords1 is the
+//                pixel grid itself) come back from the normalise / un-normalise round trip a few ulp above OR below the
+//                integer, offset by offset.  Same fetch plus window row / column 8, taps addressed per offset in smem
+//   0 "slow"     anything else: predicated 4-tap loads from global memory
 template <typename T, bool NHWC>
 __global__ void __launch_bounds__(LK_THREADS, 3) k_corr_lookup_r3(const T* __restrict__ pyr, const slimb200_corr_layout L,
                                                                   const float* __restrict__ coords, float* __restrict__ out) {
   using V = V3<T>;
-  constexpr int R = 3, WIN = 7, W1 = 8, EPC = V::EPC, NCHUNK = V::NCHUNK, WPR = V::WPR;
+  constexpr int R = 3, WIN = 7, W1 = 8, NCHUNK = V::NCHUNK, WPR = V::WPR, SROWS = V::SROWS, SWPR = V::SWPR;
   extern __shared__ __align__(16) uint32_t s_dyn[];
   const int levels = L.levels;
-  uint32_t* s_win = s_dyn;                                                    // [level][row][word][lane], aligned rows
+  uint32_t* s_win = s_dyn;                                                    // [level][row 0..8][word][lane], aligned rows
   float* s_pos = reinterpret_cast<float*>(s_dyn + V::win_words(levels));      // [level][axis][offset][lane]
   float* s_w0 = s_pos + V::tab_words(levels);
   float* s_w1 = s_w0 + V::tab_words(levels);
   int* s_xb = reinterpret_cast<int*>(s_w1 + V::tab_words(levels));
   int* s_yb = s_xb + levels * LK_PIX;
-  int* s_ok = s_yb + levels * LK_PIX;
+  int* s_ok = s_yb + levels * LK_PIX;                                         // window mode
   float* s_out = reinterpret_cast<float*>(s_ok + levels * LK_PIX);            // NHWC only: [pixel][n_ch + 1]
   __shared__ float s_xy[2][LK_PIX];
   __shared__ int s_lw[SLIMB200_MAX_LEVELS], s_lh[SLIMB200_MAX_LEVELS], s_lo[SLIMB200_MAX_LEVELS];
@@ -387,17 +437,24 @@ __global__ void __launch_bounds__(LK_THREADS, 3) k_corr_lookup_r3(const T* __res
   }
   __syncthreads();
   for (int l = warp; l < levels; l += LK_WARPS) {
-    const int xb = (int)floorf(s_pos[((l * 2 + 0) * WIN) * LK_PIX + lane]);
-    const int yb = (int)floorf(s_pos[((l * 2 + 1) * WIN) * LK_PIX + lane]);
-    bool ok = true;
+    int fx[WIN], fy[WIN];
+    int xb = 0x7fffffff, yb = 0x7fffffff;
 #pragma unroll
-    for (int o = 1; o < WIN; ++o) {
-      ok = ok && ((int)floorf(s_pos[((l * 2 + 0) * WIN + o) * LK_PIX + lane]) == xb + o);
-      ok = ok && ((int)floorf(s_pos[((l * 2 + 1) * WIN + o) * LK_PIX + lane]) == yb + o);
+    for (int o = 0; o < WIN; ++o) {
+      fx[o] = (int)floorf(s_pos[((l * 2 + 0) * WIN + o) * LK_PIX + lane]) - o;
+      fy[o] = (int)floorf(s_pos[((l * 2 + 1) * WIN + o) * LK_PIX + lane]) - o;
+      xb = min(xb, fx[o]);
+      yb = min(yb, fy[o]);
+    }
+    bool regular = true, shifted = true;
+#pragma unroll
+    for (int o = 0; o < WIN; ++o) {
+      regular = regular && fx[o] == xb && fy[o] == yb;
+      shifted = shifted && fx[o] - xb <= 1 && fy[o] - yb <= 1;
     }
     s_xb[l * LK_PIX + lane] = xb;
     s_yb[l * LK_PIX + lane] = yb;
-    s_ok[l * LK_PIX + lane] = ok ? 1 : 0;
+    s_ok[l * LK_PIX + lane] = regular ? 1 : (shifted ? 2 : 0);
   }
   __syncthreads();
 
@@ -406,37 +463,29 @@ __global__ void __launch_bounds__(LK_THREADS, 3) k_corr_lookup_r3(const T* __res
     const int l = u >> 1, half = u & 1;
     const int W = s_lw[l], H = s_lh[l], off = s_lo[l];
     const int xb = s_xb[l * LK_PIX + lane], yb = s_yb[l * LK_PIX + lane];
-    const bool okp = live && s_ok[l * LK_PIX + lane];
+    const int mode = s_ok[l * LK_PIX + lane];
+    const bool okp = live && mode != 0;
+    const int n_elems = W1 + (mode == 2 ? 1 : 0);
     uint32_t ld[4][NCHUNK * 4];
     int sft[4];
 #pragma unroll
-    for (int rr = 0; rr < 4; ++rr) {
-      const int y = yb + half * 4 + rr;
-      const bool row_ok = okp && (unsigned)y < (unsigned)H;
-      const int row0 = off + y * W;
-      const int a_start = row0 + xb;
-      const int ca = a_start & ~(EPC - 1);
-      sft[rr] = a_start - ca;
-      const int lo = row0 + max(xb, 0), hi = row0 + min(xb + W1, W);
-#pragma unroll
-      for (int c = 0; c < NCHUNK; ++c) {
-        const int col = ca + c * EPC;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (row_ok && col < hi && col + EPC > lo)
-          v = __ldg(reinterpret_cast<const uint4*>(pyr + panel_index<T>(n_panels, nf, b, pix, col)));
-        ld[rr][c * 4 + 0] = v.x;
-        ld[rr][c * 4 + 1] = v.y;
-        ld[rr][c * 4 + 2] = v.z;
-        ld[rr][c * 4 + 3] = v.w;
-      }
-    }
+    for (int rr = 0; rr < 4; ++rr)
+      sft[rr] = v3_fetch_row<T>(pyr, n_panels, nf, b, pix, off, W, H, xb, yb + half * 4 + rr, n_elems, okp, ld[rr]);
 #pragma unroll
     for (int rr = 0; rr < 4; ++rr) {
-      uint32_t al[WPR];
+      uint32_t al[SWPR];
       realign<T>(ld[rr], sft[rr], al);
-      uint32_t* dst = s_win + ((size_t)((l * W1 + half * 4 + rr) * WPR) * LK_PIX + lane);
+      uint32_t* dst = s_win + ((size_t)((l * SROWS + half * 4 + rr) * SWPR) * LK_PIX + lane);
 #pragma unroll
-      for (int k = 0; k < WPR; ++k) dst[k * LK_PIX] = al[k];
+      for (int k = 0; k < SWPR; ++k) dst[k * LK_PIX] = al[k];
+    }
+    if (half == 1 && __any_sync(0xffffffffu, mode == 2)) {  // window row 8 for the shifted windows of this warp
+      uint32_t al[SWPR];
+      const int sf = v3_fetch_row<T>(pyr, n_panels, nf, b, pix, off, W, H, xb, yb + 8, n_elems, live && mode == 2, ld[0]);
+      realign<T>(ld[0], sf, al);
+      uint32_t* dst = s_win + ((size_t)((l * SROWS + 8) * SWPR) * LK_PIX + lane);
+#pragma unroll
+      for (int k = 0; k < SWPR; ++k) dst[k * LK_PIX] = al[k];
     }
   }
   __syncthreads();
@@ -446,12 +495,16 @@ __global__ void __launch_bounds__(LK_THREADS, 3) k_corr_lookup_r3(const T* __res
     const int l = u >> 1, half = u & 1;
     float* dst = NHWC ? s_out + lane * out_pad + l * WIN * WIN : out + ((size_t)b * n_ch + (size_t)l * WIN * WIN) * nf + pix;
     const size_t kstride = NHWC ? 1 : (size_t)nf;
-    if (s_ok[l * LK_PIX + lane]) {
+    const int mode = s_ok[l * LK_PIX + lane];
+    // warp-uniform choice: as soon as one lane has a shifted window, every non-slow lane takes the smem-tap path
+    // (a regular window is a shifted one with all shifts zero), so the two paths are never both executed
+    const bool any_shifted = __any_sync(0xffffffffu, mode == 2);
+    if (mode != 0 && !any_shifted) {
       uint32_t win[W1][WPR];
 #pragma unroll
       for (int r = 0; r < W1; ++r)
 #pragma unroll
-        for (int k = 0; k < WPR; ++k) win[r][k] = s_win[((size_t)((l * W1 + r) * WPR + k)) * LK_PIX + lane];
+        for (int k = 0; k < WPR; ++k) win[r][k] = s_win[((size_t)((l * SROWS + r) * SWPR + k)) * LK_PIX + lane];
       float wy0[WIN], wy1[WIN];
 #pragma unroll
       for (int j = 0; j < WIN; ++j) {
@@ -464,6 +517,29 @@ __global__ void __launch_bounds__(LK_THREADS, 3) k_corr_lookup_r3(const T* __res
         v3_columns<T, 0, 4>(win, wy0, wy1, w0x, w1x, lane, dst, kstride, live);
       else
         v3_columns<T, 4, 7>(win, wy0, wy1, w0x, w1x, lane, dst, kstride, live);
+    } else if (mode != 0) {
+      const int xb = s_xb[l * LK_PIX + lane], yb = s_yb[l * LK_PIX + lane];
+      int ry[WIN];
+      float wy0[WIN], wy1[WIN];
+#pragma unroll
+      for (int j = 0; j < WIN; ++j) {
+        ry[j] = (int)floorf(s_pos[((l * 2 + 1) * WIN + j) * LK_PIX + lane]) - yb;  // j or j + 1
+        wy0[j] = s_w0[((l * 2 + 1) * WIN + j) * LK_PIX + lane];
+        wy1[j] = s_w1[((l * 2 + 1) * WIN + j) * LK_PIX + lane];
+      }
+      const int ib = half ? 4 : 0, ie = half ? WIN : 4;
+      for (int i = ib; i < ie; ++i) {
+        const int ex = (int)floorf(s_pos[((l * 2 + 0) * WIN + i) * LK_PIX + lane]) - xb;  // i or i + 1
+        const float wx0 = s_w0[((l * 2 + 0) * WIN + i) * LK_PIX + lane], wx1 = s_w1[((l * 2 + 0) * WIN + i) * LK_PIX + lane];
+#pragma unroll
+        for (int j = 0; j < WIN; ++j) {
+          // same association as the regular path: horizontal blends of the two rows, then the vertical blend
+          const float h0 = fmaf(v3_smem_elem<T>(s_win, l, ry[j], ex + 1, lane), wx1, v3_smem_elem<T>(s_win, l, ry[j], ex, lane) * wx0);
+          const float h1 = fmaf(v3_smem_elem<T>(s_win, l, ry[j] + 1, ex + 1, lane), wx1,
+                                v3_smem_elem<T>(s_win, l, ry[j] + 1, ex, lane) * wx0);
+          if (live) dst[((size_t)i * WIN + j) * kstride] = fmaf(h1, wy1[j], h0 * wy0[j]);
+        }
+      }
     } else {
       const int W = s_lw[l], H = s_lh[l], off = s_lo[l];
       const int ib = half ? 4 : 0, ie = half ? WIN : 4;

@@ -7,7 +7,8 @@
 //                  4 (every load is a coalesced float4 of a pixel's channel vector), Chan merge of the lanes in fp64
 //   k_in_finalize  per (sample, channel): Chan merge of the slab partials in fp64 -> scale = gamma / sqrt(var + eps),
 //                  shift = beta - mean * scale (biased variance, like F.instance_norm)
-//   k_in_apply     out = max(x * scale + shift, 0) as float4
+//   k_in_apply     out = max(x * scale + shift, 0) as float4; optionally the residual join of the block is fused in:
+//                  out = relu(residual + relu(x * scale + shift))
 // The convolutions themselves stay stock cuDNN.
 #include "common.cuh"
 
@@ -20,6 +21,7 @@ struct InArgs {
   const float* x;
   const float* gamma;
   const float* beta;
+  const float* residual;  // optional (same shape as x): added after the normalisation (+ inner ReLU)
   float* out;
   float* partial;   // [batch][slabs][C][3] (count, mean, M2)
   float* scale_shift;  // [batch][C][2]
@@ -128,13 +130,15 @@ __global__ void __launch_bounds__(IN_THREADS) k_in_finalize(const InArgs a) {
   }
 }
 
-// out = max(x * scale + shift, 0), float4
+// out = [relu_outer]([relu_inner](x * scale + shift) + residual), float4.  relu bit 0 = inner (the norm's own ReLU),
+// bit 1 = outer (the residual join relu(x + y) of extractor.py:57-68)
 __global__ void __launch_bounds__(IN_THREADS) k_in_apply(const InArgs a) {
   const int G = a.C >> 2;
   const size_t per_sample = (size_t)a.hw * G;
   const int b = blockIdx.y;
   const float4* src = reinterpret_cast<const float4*>(a.x) + (size_t)b * per_sample;
   float4* dst = reinterpret_cast<float4*>(a.out) + (size_t)b * per_sample;
+  const float4* res = a.residual ? reinterpret_cast<const float4*>(a.residual) + (size_t)b * per_sample : nullptr;
   const float* ss = a.scale_shift + (size_t)b * a.C * 2;
   for (size_t i = (size_t)blockIdx.x * IN_THREADS + threadIdx.x; i < per_sample; i += (size_t)gridDim.x * IN_THREADS) {
     const int g = (int)(i % G);
@@ -146,11 +150,24 @@ __global__ void __launch_bounds__(IN_THREADS) k_in_apply(const InArgs a) {
     o.y = fmaf(v.y, s0.z, s0.w);
     o.z = fmaf(v.z, s1.x, s1.y);
     o.w = fmaf(v.w, s1.z, s1.w);
-    if (a.relu) {
+    if (a.relu & 1) {
       o.x = fmaxf(o.x, 0.f);
       o.y = fmaxf(o.y, 0.f);
       o.z = fmaxf(o.z, 0.f);
       o.w = fmaxf(o.w, 0.f);
+    }
+    if (res) {
+      const float4 r = __ldg(res + i);
+      o.x = __fadd_rn(r.x, o.x);
+      o.y = __fadd_rn(r.y, o.y);
+      o.z = __fadd_rn(r.z, o.z);
+      o.w = __fadd_rn(r.w, o.w);
+      if (a.relu & 2) {
+        o.x = fmaxf(o.x, 0.f);
+        o.y = fmaxf(o.y, 0.f);
+        o.z = fmaxf(o.z, 0.f);
+        o.w = fmaxf(o.w, 0.f);
+      }
     }
     dst[i] = o;
   }
@@ -172,20 +189,21 @@ extern "C" size_t slimb200_instnorm_workspace_bytes(int32_t batch, int32_t chann
 }
 
 extern "C" int slimb200_instnorm_nhwc(const float* x, const float* gamma, const float* beta, float eps, int32_t batch,
-                                      int32_t height, int32_t width, int32_t channels, int32_t relu, float* out,
-                                      void* workspace, size_t workspace_bytes, void* stream_) {
+                                      int32_t height, int32_t width, int32_t channels, int32_t relu, const float* residual,
+                                      float* out, void* workspace, size_t workspace_bytes, void* stream_) {
   if (!x || !gamma || !beta || !out || !workspace || batch < 1 || height < 1 || width < 1) return SLIMB200_E_INVALID;
   if (channels < 4 || (channels & 3) || channels > IN_THREADS) return SLIMB200_E_UNSUPPORTED;
   const long long hw = (long long)height * width;
   if (hw > 0x7fffffffLL) return SLIMB200_E_UNSUPPORTED;
   if (workspace_bytes < slimb200_instnorm_workspace_bytes(batch, channels, (int)hw)) return SLIMB200_E_WORKSPACE;
-  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(workspace) & 255))
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(residual) & 15) || (reinterpret_cast<uintptr_t>(workspace) & 255))
     return SLIMB200_E_ALIGNMENT;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   InArgs a{};
   a.x = x;
   a.gamma = gamma;
   a.beta = beta;
+  a.residual = residual;
   a.out = out;
   a.batch = batch;
   a.hw = (int)hw;

@@ -1,0 +1,135 @@
+"""Python side of the SURVEY 8(f).2 glue kernels (``csrc/gru_glue.cu``): the element-wise work between the stock
+convolutions of the ConvGRU update block (``liso/slim/model/update.py:23-38,70-93,130-150``) and the refinement loop's
+coordinate / logit update (``raft_mod.py:188-212``) on channels-last fp32 CUDA tensors.
+
+Every function takes and returns ordinary ``(B, C, h, w)`` tensors in channels-last memory format; the library sees
+them as ``(B*h*w, C)`` rows.  No fallback: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Sequence, Tuple
+
+import torch
+
+from .. import _lib
+
+
+def is_nhwc(t: torch.Tensor) -> bool:
+    """Packed channels-last (B, C, h, w) fp32 CUDA tensor."""
+    return (t.dim() == 4 and t.is_cuda and t.dtype == torch.float32
+            and t.is_contiguous(memory_format=torch.channels_last))
+
+
+def as_nhwc(t: torch.Tensor) -> torch.Tensor:
+    _lib.require_cuda(t)
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if is_nhwc(t) else t.contiguous(memory_format=torch.channels_last)
+
+
+def _pixels(t: torch.Tensor) -> int:
+    return t.shape[0] * t.shape[2] * t.shape[3]
+
+
+def nhwc_pack_into(srcs: Sequence[torch.Tensor], dsts: Sequence[Tuple[torch.Tensor, int]]) -> None:
+    """Channel-concatenate ``srcs`` (<= 4) and store the result at channel offset ``off`` of every ``(dst, off)``
+    (<= 2 destinations, packed channels-last tensors with >= off + sum(C_src) channels)."""
+    srcs = [as_nhwc(s) for s in srcs]
+    B, _, h, w = srcs[0].shape
+    for s in srcs:
+        if (s.shape[0], s.shape[2], s.shape[3]) != (B, h, w):
+            raise ValueError("nhwc_pack: sources must share batch and spatial size")
+    for d, _ in dsts:
+        if not is_nhwc(d) or (d.shape[0], d.shape[2], d.shape[3]) != (B, h, w):
+            raise ValueError("nhwc_pack: destinations must be packed channels-last fp32 CUDA tensors of the sources' size")
+    n_s, n_d = len(srcs), len(dsts)
+    sp = (C.c_void_p * n_s)(*[s.data_ptr() for s in srcs])
+    sc = (C.c_int32 * n_s)(*[s.shape[1] for s in srcs])
+    dp = (C.c_void_p * n_d)(*[d.data_ptr() for d, _ in dsts])
+    do = (C.c_int32 * n_d)(*[int(o) for _, o in dsts])
+    dpitch = (C.c_int32 * n_d)(*[d.shape[1] for d, _ in dsts])
+    _lib.check(_lib.load().slimb200_nhwc_pack(sp, sc, n_s, dp, do, dpitch, n_d, B * h * w, _lib.current_stream_ptr()))
+
+
+def nhwc_cat(srcs: Sequence[torch.Tensor]) -> torch.Tensor:
+    """``torch.cat(srcs, dim=1)`` for channels-last tensors, one launch."""
+    s0 = srcs[0]
+    out = torch.empty((s0.shape[0], sum(s.shape[1] for s in srcs), s0.shape[2], s0.shape[3]), dtype=torch.float32,
+                      device=s0.device, memory_format=torch.channels_last)
+    nhwc_pack_into(srcs, [(out, 0)])
+    return out
+
+
+def gru_gate_zr(zr_raw: torch.Tensor, bias_zr: torch.Tensor, hx: torch.Tensor, rhx: torch.Tensor, hidden: int) -> torch.Tensor:
+    """``z = sigmoid(zr_raw[:, :hidden] + b)`` (returned, packed) and ``rhx[:, :hidden] = sigmoid(zr_raw[:, hidden:] + b) *
+    hx[:, :hidden]`` (``update.py:33-35``); ``zr_raw`` is the stacked update|reset convolution WITHOUT its bias."""
+    zr_raw = as_nhwc(zr_raw)
+    if not (is_nhwc(hx) and is_nhwc(rhx)) or zr_raw.shape[1] != 2 * hidden or bias_zr.numel() != 2 * hidden:
+        raise ValueError("gru_gate_zr: bad buffers")
+    z = torch.empty((zr_raw.shape[0], hidden, zr_raw.shape[2], zr_raw.shape[3]), dtype=torch.float32, device=zr_raw.device,
+                    memory_format=torch.channels_last)
+    _lib.check(_lib.load().slimb200_gru_gate_zr(zr_raw.data_ptr(), bias_zr.data_ptr(), hx.data_ptr(), hx.shape[1], z.data_ptr(),
+                                                rhx.data_ptr(), rhx.shape[1], hidden, _pixels(zr_raw), _lib.current_stream_ptr()))
+    return z
+
+
+def gru_gate_out(q_raw: torch.Tensor, bias_q: torch.Tensor, z: torch.Tensor, hx: torch.Tensor, hidden: int) -> torch.Tensor:
+    """``h' = (1 - z) * h + z * tanh(q_raw + b)`` (``update.py:35-38``) written into ``hx[:, :hidden]`` in place and
+    returned as a packed tensor for the heads."""
+    q_raw, z = as_nhwc(q_raw), as_nhwc(z)
+    if not is_nhwc(hx) or q_raw.shape[1] != hidden or z.shape != q_raw.shape or bias_q.numel() != hidden:
+        raise ValueError("gru_gate_out: bad buffers")
+    h = torch.empty_like(q_raw)
+    _lib.check(_lib.load().slimb200_gru_gate_out(q_raw.data_ptr(), bias_q.data_ptr(), z.data_ptr(), hx.data_ptr(), hx.shape[1],
+                                                 h.data_ptr(), hidden, _pixels(q_raw), _lib.current_stream_ptr()))
+    return h
+
+
+def _head_strides(t: torch.Tensor) -> Tuple[torch.Tensor, int, int]:
+    """(tensor, channel stride, pixel stride) of a (B, C, h, w) head output that is NCHW- or channels-last-contiguous."""
+    _lib.require_cuda(t)
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    if t.is_contiguous():
+        return t, t.shape[2] * t.shape[3], 1
+    if t.is_contiguous(memory_format=torch.channels_last):
+        return t, 1, t.shape[1]
+    t = t.contiguous()
+    return t, t.shape[2] * t.shape[3], 1
+
+
+def iter_update(dflow_raw: torch.Tensor, bias_flow: torch.Tensor, dlogits_raw: torch.Tensor, bias_logits: torch.Tensor,
+                coords1: torch.Tensor, flow: torch.Tensor, logits: torch.Tensor) -> None:
+    """In place (``raft_mod.py:205-212``): ``coords1 += dflow_raw + b``; ``logits += dlogits_raw + b``;
+    ``flow = coords1 - coords_grid``.  The raw tensors are the head convolutions without bias."""
+    B, _, h, w = coords1.shape
+    for t in (coords1, flow, logits):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise ValueError("iter_update: coords1 / flow / logits must be contiguous fp32 CUDA tensors")
+    if tuple(dflow_raw.shape) != (B, 2, h, w) or tuple(dlogits_raw.shape) != tuple(logits.shape) or tuple(flow.shape) != (B, 2, h, w):
+        raise ValueError("iter_update: shape mismatch")
+    df, cs_f, ps_f = _head_strides(dflow_raw)
+    dl, cs_l, ps_l = _head_strides(dlogits_raw)
+    _lib.check(_lib.load().slimb200_iter_update(df.data_ptr(), cs_f, ps_f, bias_flow.data_ptr(), dl.data_ptr(), cs_l, ps_l,
+                                                bias_logits.data_ptr(), logits.shape[1], B, h, w, coords1.data_ptr(),
+                                                flow.data_ptr(), logits.data_ptr(), _lib.current_stream_ptr()))
+
+
+def add_relu(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """``relu(x + y)`` for two fp32 CUDA tensors of the same shape and memory layout (``extractor.py:57-68``)."""
+    _lib.require_cuda(x, y)
+    if x.shape != y.shape or x.stride() != y.stride() or x.dtype != torch.float32 or y.dtype != torch.float32 \
+            or not (x.is_contiguous() or x.is_contiguous(memory_format=torch.channels_last)) or x.numel() % 4:
+        raise ValueError("add_relu: tensors must be dense fp32 with identical shape and strides, numel % 4 == 0")
+    out = torch.empty_like(x)
+    _lib.check(_lib.load().slimb200_add_relu(x.data_ptr(), y.data_ptr(), out.data_ptr(), x.numel(), _lib.current_stream_ptr()))
+    return out
+
+
+def add_relu_ok(x: torch.Tensor, y: torch.Tensor) -> bool:
+    return (x.is_cuda and y.is_cuda and x.dtype == torch.float32 and y.dtype == torch.float32 and x.shape == y.shape
+            and x.stride() == y.stride() and (x.is_contiguous() or x.is_contiguous(memory_format=torch.channels_last))
+            and x.numel() % 4 == 0 and not torch.is_grad_enabled())

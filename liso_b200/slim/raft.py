@@ -71,25 +71,29 @@ def conv_relu(conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
     return F.relu(conv(x))
 
 
-def instance_norm_nhwc(norm: nn.InstanceNorm2d, x: torch.Tensor, relu: bool) -> torch.Tensor:
+def instance_norm_nhwc(norm: nn.InstanceNorm2d, x: torch.Tensor, relu: bool, residual: torch.Tensor = None) -> torch.Tensor:
     """Affine InstanceNorm2d (+ ReLU) of a channels-last CUDA tensor in the library's glue kernel
-    (``slimb200_instnorm_nhwc``): 3 launches / 2 passes instead of copy-to-NCHW + cuDNN batch-norm + copy back + clamp."""
-    import ctypes as C
-
+    (``slimb200_instnorm_nhwc``): 3 launches / 2 passes instead of copy-to-NCHW + cuDNN batch-norm + copy back + clamp.
+    With ``residual`` the block's join is fused into the same pass: ``relu(residual + [relu](norm(x)))``."""
     lib = _lib_mod().load()
+    if not x.is_contiguous(memory_format=torch.channels_last):
+        x = x.contiguous(memory_format=torch.channels_last)
     B, Cn, H, W = x.shape
     out = torch.empty_like(x)  # preserves the channels-last strides
     ws = torch.empty(max(256, lib.slimb200_instnorm_workspace_bytes(B, Cn, H * W)), dtype=torch.uint8, device=x.device)
+    flags = (1 if relu else 0) | (2 if residual is not None else 0)
     _lib_mod().check(lib.slimb200_instnorm_nhwc(x.data_ptr(), norm.weight.data_ptr(), norm.bias.data_ptr(), float(norm.eps), B, H, W,
-                                                Cn, 1 if relu else 0, out.data_ptr(), ws.data_ptr(), ws.numel(),
-                                                _lib_mod().current_stream_ptr()))
+                                                Cn, flags, residual.data_ptr() if residual is not None else None, out.data_ptr(),
+                                                ws.data_ptr(), ws.numel(), _lib_mod().current_stream_ptr()))
     return out
 
 
-def _fused_norm_ok(norm: nn.Module, x: torch.Tensor) -> bool:
+def _fused_norm_ok(norm: nn.Module, x: torch.Tensor, channels: int = None) -> bool:
+    """``x``: the tensor to normalise, or (with ``channels``) the channels-last input of the convolution that produces it."""
+    c = x.shape[1] if channels is None else channels
     return (FAST_STOCK_OPS and isinstance(norm, nn.InstanceNorm2d) and norm.affine and not norm.track_running_stats
-            and x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled() and x.shape[1] % 4 == 0
-            and x.shape[1] <= 256 and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last))
+            and x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled() and not torch.is_autocast_enabled()
+            and c % 4 == 0 and c <= 256 and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last))
 
 
 def norm_relu(norm: nn.Module, x: torch.Tensor) -> torch.Tensor:
@@ -97,6 +101,35 @@ def norm_relu(norm: nn.Module, x: torch.Tensor) -> torch.Tensor:
     if _fused_norm_ok(norm, x):
         return instance_norm_nhwc(norm, x, relu=True)
     return F.relu(norm(x))
+
+
+def conv_norm(conv: nn.Conv2d, norm: nn.Module, x: torch.Tensor, relu: bool, residual: torch.Tensor = None) -> torch.Tensor:
+    """[relu](norm(conv(x))), or with ``residual`` the whole tail of a residual block relu(residual + [relu](norm(conv(x))))
+    (``extractor.py:57-68``).  In front of an InstanceNorm the convolution's bias is a per-channel constant that the
+    normalisation subtracts again, so on the fused path the bias add (a full pass over the tensor) is skipped: equal
+    in exact arithmetic, ~1 ulp different in fp32."""
+    if _fused_norm_ok(norm, x, conv.out_channels):
+        y = F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+        if residual is None or (residual.shape == y.shape and residual.stride() == y.stride() and residual.dtype == y.dtype
+                                and residual.is_cuda):
+            return instance_norm_nhwc(norm, y, relu=relu, residual=residual)
+        return add_relu(residual, instance_norm_nhwc(norm, y, relu=relu))
+    y = norm(conv(x))
+    y = F.relu(y) if relu else y
+    return y if residual is None else add_relu(residual, y)
+
+
+def add_relu(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """relu(x + y): one glue launch on dense fp32 CUDA tensors of equal layout, the two stock ops otherwise."""
+    if FAST_STOCK_OPS and _glue().add_relu_ok(x, y):
+        return _glue().add_relu(x, y)
+    return F.relu(x + y)
+
+
+def _glue():
+    from . import glue
+
+    return glue
 
 
 def _is_identity(norm: nn.Module) -> bool:
@@ -137,15 +170,13 @@ class ResidualBlock(nn.Module):
     def forward(self, x):
         if _is_identity(self.norm1):
             y = conv_relu(self.conv2, conv_relu(self.conv1, x))
-        else:
-            y = norm_relu(self.norm1, self.conv1(x))
-            y = norm_relu(self.norm2, self.conv2(y))
-        if self.downsample is not None:
-            if _fused_norm_ok(self.downsample[1], x):
-                x = instance_norm_nhwc(self.downsample[1], self.downsample[0](x), relu=False)
-            else:
+            if self.downsample is not None:
                 x = self.downsample(x)
-        return self.relu(x + y)
+            return add_relu(x, y)
+        y = conv_norm(self.conv1, self.norm1, x, relu=True)
+        if self.downsample is not None:
+            x = conv_norm(self.downsample[0], self.downsample[1], x, relu=False)
+        return conv_norm(self.conv2, self.norm2, y, relu=True, residual=x)  # relu(x + relu(norm2(conv2(y))))
 
 
 class SmallEncoder(nn.Module):
@@ -170,7 +201,7 @@ class SmallEncoder(nn.Module):
         )
 
     def forward(self, x):
-        x = conv_relu(self.conv1, x) if _is_identity(self.norm1) else norm_relu(self.norm1, self.conv1(x))
+        x = conv_relu(self.conv1, x) if _is_identity(self.norm1) else conv_norm(self.conv1, self.norm1, x, relu=True)
         x = self.layer3(self.layer2(self.layer1(x)))
         x = self.conv2(x)
         if self.training and self.dropout is not None:
@@ -287,6 +318,8 @@ class RAFT(nn.Module):
         # capture everything between the pillar encoder and the decoder in a CUDA graph (inference on CUDA only; the same
         # kernels are launched eagerly when switched off)
         self.use_cuda_graph = True
+        # glue-kernel version of the update block's element-wise work (channels-last fp32 inference only)
+        self.fused_update_block = True
         self._graphs = {}
         rows = float(cfg.data.bev_range_m[0]) / cfg.data.img_grid_size[0] * m.u_net.final_scale
         cols = float(cfg.data.bev_range_m[1]) / cfg.data.img_grid_size[1] * m.u_net.final_scale
@@ -321,7 +354,8 @@ class RAFT(nn.Module):
         # update or re-allocation of a parameter invalidates the graph.
         B = len(pcl_t0)
         wsig = tuple((p.data_ptr(), p._version) for mod in (self.fnet, self.cnet, self.update_block) for p in mod.parameters())
-        key = (B, self.output_iterations, self.pp_layer.canvas_memory_format, str(dev), torch.backends.cudnn.allow_tf32, wsig)
+        key = (B, self.output_iterations, self.pp_layer.canvas_memory_format, str(dev), torch.backends.cudnn.allow_tf32,
+               self.fused_update_block, FAST_STOCK_OPS, wsig)
         st = self._graphs.get("net")
         if st is not None and st["key"] != key:
             st = None  # (the old graph and its buffers are released when the slot is overwritten)
@@ -369,6 +403,8 @@ class RAFT(nn.Module):
         m = self.slim_cfg.model
         ds = m.feature_downsampling_factor
         h, w = img_hw[0] // ds, img_hw[1] // ds
+        if self._fused_update_ok(correlation, net, inp):
+            return self._gru_loop_fused(correlation, net, inp, h, w, batch, device)
         coords0 = coords_grid(batch, h, w, device)
         coords1 = coords_grid(batch, h, w, device)
         logits = torch.zeros((batch, 4, h, w), dtype=torch.float32, device=device)
@@ -391,6 +427,59 @@ class RAFT(nn.Module):
                                device=device, dtype=torch.float32)[None, :, None, None]
             flow_m = torch.flip(upflow_n(coords1 - coords0, n=ds), dims=[1]) * res
             outs.append(concat2network_output(uplogits_n(logits, n=ds), flow_m, flow_m))
+        return outs
+
+    def _fused_update_ok(self, correlation, net, inp) -> bool:
+        """The glue-kernel version of the loop needs the channels-last fp32 inference setting of the export."""
+        return (FAST_STOCK_OPS and self.fused_update_block and not torch.is_grad_enabled() and not torch.is_autocast_enabled()
+                and net.is_cuda and net.dtype == torch.float32 and inp.dtype == torch.float32
+                and getattr(correlation, "channels_last", False)
+                and isinstance(self.update_block, SmallUpdateBlock) and self.update_block.gru.convz.padding_mode == "zeros"
+                and net.shape[1] % 4 == 0 and inp.shape[1] % 4 == 0)
+
+    def _gru_loop_fused(self, correlation, net, inp, h, w, batch, device) -> List[torch.Tensor]:
+        """Same loop as `_gru_loop` (raft_mod.py:188-257, update.py:23-38,70-93,130-150) with the element-wise work
+        between the stock convolutions in the library's glue kernels: the two 304-channel GRU inputs
+        [h | inp | motion] and [r*h | inp | motion] are persistent channels-last buffers whose slots the producers
+        write directly (no torch.cat), the gates are two launches, and the coordinate / logit update is one."""
+        g = _glue()
+        m = self.slim_cfg.model
+        ds = m.feature_downsampling_factor
+        ub = self.update_block
+        me, gru = ub.motion_encoder, ub.gru
+        Ch, Cx = net.shape[1], inp.shape[1]
+        n_in = gru.convz.in_channels
+        hx = torch.empty((batch, n_in, h, w), dtype=torch.float32, device=device, memory_format=torch.channels_last)
+        rhx = torch.empty_like(hx)
+        hx[:, :Ch].copy_(net)
+        hx[:, Ch:Ch + Cx].copy_(inp)
+        rhx[:, Ch:Ch + Cx].copy_(inp)
+        w_zr = _cat_params((gru.convz.weight, gru.convr.weight))
+        b_zr = _cat_params((gru.convz.bias, gru.convr.bias))
+        fh, lh = ub.static_flow_head, ub.classification_head
+        coords1 = coords_grid(batch, h, w, device).contiguous()
+        flow = torch.zeros((batch, 2, h, w), dtype=torch.float32, device=device)
+        logits = torch.zeros((batch, lh.conv2.out_channels, h, w), dtype=torch.float32, device=device)
+
+        def raw(conv, x):  # the convolution without its bias (the consumer adds it)
+            return F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+
+        outs = []
+        for it in range(m.num_iters):
+            corr = correlation(coords1)
+            c = conv_relu(me.conv_stat_corr1, corr)
+            f = conv_relu(me.conv_flow2, conv_relu(me.conv_flow1, flow))
+            lg = conv_relu(me.conv_class2, conv_relu(me.conv_class1, logits))
+            out = conv_relu(me.conv, g.nhwc_cat([c, f, lg]))
+            g.nhwc_pack_into([out, lg, f], [(hx, Ch + Cx), (rhx, Ch + Cx)])  # x = [inp | out | logits | flow]
+            z = g.gru_gate_zr(F.conv2d(hx, w_zr, None, gru.convz.stride, gru.convz.padding), b_zr, hx, rhx, Ch)
+            net = g.gru_gate_out(raw(gru.convq, rhx), gru.convq.bias, z, hx, Ch)
+            g.iter_update(raw(fh.conv2, conv_relu(fh.conv1, net)), fh.conv2.bias, raw(lh.conv2, conv_relu(lh.conv1, net)),
+                          lh.conv2.bias, coords1, flow, logits)
+            if self.output_iterations == "last" and it != m.num_iters - 1:
+                continue
+            outs.append(raft_output_fused(flow, logits, ds, self.bev_rows_res_meters_per_fs_pixel,
+                                          self.bev_cols_res_meters_per_fs_pixel))
         return outs
 
     def predict_single_flow_map_and_classes(self, img_t0, fmap_t0, fmap_t1, decoder=None) -> List[torch.Tensor]:

@@ -1,0 +1,16 @@
+#!/bin/bash
+# iteration check: new/changed parity tests first (all failures shown), then the rest, then a bench line without the CPU arm
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_glue.py tests/test_gpu_corr.py -q -m gpu --timeout=300 > gpurun_out/pytest_new.log 2>&1; echo "pytest new exit $?" > gpurun_out/summary.txt
+timeout 900 python -m pytest tests -q -m gpu --timeout=600 --deselect tests/test_gpu_glue.py --deselect tests/test_gpu_corr.py > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rest exit $?" >> gpurun_out/summary.txt
+timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?" >> gpurun_out/summary.txt
+grep -E "^(FAILED|ERROR)|passed|failed|Error|assert" gpurun_out/pytest_new.log | head -40
+tail -n 3 gpurun_out/pytest_gpu.log; cat gpurun_out/summary.txt; tail -n 5 gpurun_out/bench.err
+python - <<'PY'
+import json
+try:
+    d=json.load(open('gpurun_out/bench.json'))
+    print('value',d['value'],'e2e',d['e2e']['value'],'ms/step',d['ms_per_step'],'other',d.get('other_mode'),'parity',d.get('parity'))
+    for k in d['kernels']: print(k['kernel'], round(k['avg_ms'],4), k['launches_per_step'], round(k.get('frac',0),3))
+except Exception as e: print('bench parse failed', e)
+PY

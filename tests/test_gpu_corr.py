@@ -99,17 +99,23 @@ def test_lookup_on_bf16_pyramid(cuda, B, h, w, fmt):
     if fmt == "channels_last":
         d1, d2 = d1.contiguous(memory_format=torch.channels_last), d2.contiguous(memory_format=torch.channels_last)
     blk = C.CorrBlock(d1, d2, num_levels=4, radius=3)
-    coords = _coords(B, h, w, 5, 1.5)
-    got_dev = blk(coords.to(cuda))
-    assert got_dev.is_contiguous(memory_format=torch.channels_last if fmt == "channels_last" else torch.contiguous_format)
-    got = got_dev.cpu()
     same_values = [lv.float().cpu().contiguous() for lv in blk.corr_pyramid]
-    ref = O.corr_lookup(same_values, coords, 3)
     scale = float(same_values[0].abs().max())
-    assert float((got - ref).abs().max()) <= 1e-5 * scale
-    # and against the full-precision oracle: bounded by the bf16 storage/operand rounding
-    ref32 = O.corr_lookup(O.corr_pyramid(f1, f2, 4), coords, 3)
-    assert float((got - ref32).abs().max()) <= 2.0 ** -6 * scale
+    ref_pyr32 = O.corr_pyramid(f1, f2, 4)
+    # spread 0: the pixel grid itself (what the first GRU iteration asks for) -- every position sits on an integer and
+    # the per-offset floors scatter around it ("shifted" windows of the kernel); 0.5: half-integers at level 0
+    for spread, seed in ((1.5, 5), (0.0, 6), (0.5, 7)):
+        coords = _coords(B, h, w, seed, spread if spread != 0.5 else 0.0)
+        if spread == 0.5:
+            coords = coords + 0.5
+        got_dev = blk(coords.to(cuda))
+        assert got_dev.is_contiguous(memory_format=torch.channels_last if fmt == "channels_last" else torch.contiguous_format)
+        got = got_dev.cpu()
+        ref = O.corr_lookup(same_values, coords, 3)
+        assert float((got - ref).abs().max()) <= 1e-5 * scale, (spread, float((got - ref).abs().max()), scale)
+        # and against the full-precision oracle: bounded by the bf16 storage/operand rounding
+        ref32 = O.corr_lookup(ref_pyr32, coords, 3)
+        assert float((got - ref32).abs().max()) <= 2.0 ** -6 * scale
 
 
 def test_window_channel_order(cuda):

@@ -1,0 +1,134 @@
+"""SURVEY 8(f).2 glue kernels (``csrc/gru_glue.cu``, the residual mode of ``slimb200_instnorm_nhwc``) against the stock
+PyTorch ops they replace (``liso/slim/model/update.py:23-38,70-93,130-150``, ``raft_mod.py:188-212``,
+``extractor.py:57-68``).  The kernels round like the PyTorch expressions, so the comparisons are (nearly) exact."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from liso_b200.config import WORKLOADS, make_cfg
+from liso_b200.slim import glue as G
+from liso_b200.slim import raft as R
+from liso_b200.slim.corr import coords_grid
+from liso_b200.slim.slim import SLIM
+from liso_b200.synth import make_sample_dicts
+from liso_b200.weights import synth_weights_like
+
+pytestmark = pytest.mark.gpu
+
+
+def _nhwc(B, C, h, w, seed, device):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(B, C, h, w, generator=g).to(device).contiguous(memory_format=torch.channels_last)
+
+
+@pytest.mark.parametrize("B,h,w", [(1, 5, 7), (2, 16, 24), (8, 80, 80)])
+def test_nhwc_pack_equals_cat(cuda, B, h, w):
+    c, f, lg, o = (_nhwc(B, C, h, w, 10 + C, cuda) for C in (96, 32, 36, 80))
+    got = G.nhwc_cat([c, f, lg])
+    assert got.is_contiguous(memory_format=torch.channels_last) and torch.equal(got, torch.cat([c, f, lg], dim=1))
+    assert torch.equal(G.nhwc_cat([c]), c) and torch.equal(G.nhwc_cat([c, f, lg, o]), torch.cat([c, f, lg, o], dim=1))
+    # slot writes into two wider buffers; everything outside the slot stays untouched
+    hx = _nhwc(B, 304, h, w, 1, cuda)
+    rhx = _nhwc(B, 312, h, w, 2, cuda)
+    hx0, rhx0 = hx.clone(), rhx.clone()
+    G.nhwc_pack_into([o, lg, f], [(hx, 156), (rhx, 160)])
+    cat = torch.cat([o, lg, f], dim=1)
+    assert torch.equal(hx[:, 156:], cat) and torch.equal(hx[:, :156], hx0[:, :156])
+    assert torch.equal(rhx[:, 160:308], cat) and torch.equal(rhx[:, :160], rhx0[:, :160]) and torch.equal(rhx[:, 308:], rhx0[:, 308:])
+    with pytest.raises(RuntimeError):
+        G.nhwc_pack_into([o, lg, f], [(hx, 160)])  # does not fit
+    with pytest.raises(RuntimeError):
+        G.nhwc_cat([c.cpu()])
+
+
+@pytest.mark.parametrize("B,h,w", [(1, 5, 7), (8, 80, 80)])
+def test_gru_gates_equal_stock_expressions(cuda, B, h, w):
+    Ch = 96
+    hx = _nhwc(B, 304, h, w, 3, cuda)
+    rhx = _nhwc(B, 304, h, w, 4, cuda)
+    zr = _nhwc(B, 2 * Ch, h, w, 5, cuda) * 3.0
+    q = _nhwc(B, Ch, h, w, 6, cuda) * 2.0
+    bzr = torch.randn(2 * Ch, device=cuda)
+    bq = torch.randn(Ch, device=cuda)
+    hprev = hx[:, :Ch].clone()
+    x_part = rhx[:, Ch:].clone()
+    # update.py:33-35 with the bias added the way F.conv2d does (a separate fp32 add)
+    zr_ref = torch.sigmoid(zr + bzr[None, :, None, None])
+    z_ref, r_ref = zr_ref[:, :Ch], zr_ref[:, Ch:]
+    z = G.gru_gate_zr(zr, bzr, hx, rhx, Ch)
+    assert torch.allclose(z, z_ref, rtol=0, atol=2e-7)
+    assert torch.allclose(rhx[:, :Ch], r_ref * hprev, rtol=1e-6, atol=1e-7)
+    assert torch.equal(rhx[:, Ch:], x_part) and torch.equal(hx[:, :Ch], hprev)
+    h_ref = (1 - z) * hprev + z * torch.tanh(q + bq[None, :, None, None])
+    hnew = G.gru_gate_out(q, bq, z, hx, Ch)
+    assert hnew.is_contiguous(memory_format=torch.channels_last)
+    assert torch.allclose(hnew, h_ref, rtol=1e-6, atol=3e-7)
+    assert torch.equal(hx[:, :Ch], hnew)
+
+
+@pytest.mark.parametrize("fmt", ["contiguous", "channels_last"])
+@pytest.mark.parametrize("B,h,w", [(1, 5, 7), (8, 80, 80)])
+def test_iter_update_equals_stock_ops(cuda, B, h, w, fmt):
+    g = torch.Generator().manual_seed(7)
+    mf = torch.channels_last if fmt == "channels_last" else torch.contiguous_format
+    df = torch.randn(B, 2, h, w, generator=g).to(cuda).contiguous(memory_format=mf)
+    dl = torch.randn(B, 4, h, w, generator=g).to(cuda).contiguous(memory_format=mf)
+    bf, bl = torch.randn(2, device=cuda), torch.randn(4, device=cuda)
+    coords0 = coords_grid(B, h, w, cuda)
+    coords1 = (coords0 + torch.randn(B, 2, h, w, generator=g).to(cuda)).contiguous()
+    logits = torch.randn(B, 4, h, w, generator=g).to(cuda)
+    flow = torch.full((B, 2, h, w), float("nan"), device=cuda)
+    c_ref = coords1 + (df + bf[None, :, None, None])
+    l_ref = logits + (dl + bl[None, :, None, None])
+    G.iter_update(df, bf, dl, bl, coords1, flow, logits)
+    assert torch.equal(coords1, c_ref) and torch.equal(logits, l_ref) and torch.equal(flow, c_ref - coords0)
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 32, 40, 56), (3, 96, 17, 23), (8, 32, 320, 320)])
+def test_residual_joins(cuda, B, C, H, W):
+    x, y = _nhwc(B, C, H, W, 8, cuda), _nhwc(B, C, H, W, 9, cuda)
+    assert torch.equal(R.add_relu(x, y), F.relu(x + y))
+    assert torch.equal(R.add_relu(x.contiguous(), y.contiguous()), F.relu(x + y).contiguous())
+    norm = torch.nn.InstanceNorm2d(C, eps=1e-3, affine=True).to(cuda)
+    with torch.no_grad():
+        norm.weight.uniform_(0.5, 1.5)
+        norm.bias.uniform_(-0.5, 0.5)
+        for relu in (True, False):
+            plain = R.instance_norm_nhwc(norm, y, relu)
+            fused = R.instance_norm_nhwc(norm, y, relu, residual=x)
+            assert fused.is_contiguous(memory_format=torch.channels_last)
+            assert torch.equal(fused, F.relu(x + plain))
+
+
+def _slim(cfg, device):
+    m = SLIM(cfg).eval()
+    m.load_state_dict(synth_weights_like(m.state_dict(), 0), strict=True)
+    return m.to(device).to(memory_format=torch.channels_last)
+
+
+def test_fused_update_block_equals_stock_loop(cuda):
+    """Whole forward with the glue kernels (fused update block, fused residual joins) vs the same network on stock
+    element-wise ops (metres / logits of the (B, H, W, 8) network output)."""
+    cfg = make_cfg("T")
+    model = _slim(cfg, cuda)
+    s0, s1 = make_sample_dicts(WORKLOADS["T"], [41, 42])
+    net = model.raft_network
+    net.use_cuda_graph = False
+    p0 = [p.to(cuda) for p in s0["pcl_full_no_ground_ta"]]
+    p1 = [p.to(cuda) for p in s1["pcl_full_no_ground_ta"]]
+    with torch.no_grad():
+        fused = [o.clone() for o in net(p0, p1)[0]]
+        net.fused_update_block = False
+        stock_loop = [o.clone() for o in net(p0, p1)[0]]
+        R.FAST_STOCK_OPS = False
+        try:
+            stock = [o.clone() for o in net(p0, p1)[0]]
+        finally:
+            R.FAST_STOCK_OPS = True
+            net.fused_update_block = True
+    assert len(fused) == len(stock_loop) == len(stock) == 6
+    for a, b, c in zip(fused, stock_loop, stock):
+        assert a.shape == b.shape == c.shape
+        # same convolutions, same element-wise rounding: the glue kernels reproduce the stock loop
+        assert float((a - b).abs().max()) <= 1e-4, float((a - b).abs().max())
+        assert float((a - c).abs().max()) <= 5e-3, float((a - c).abs().max())
