@@ -256,29 +256,34 @@ int slimb200_instnorm_nhwc(const float* x, const float* gamma, const float* beta
  * write their channel slots directly instead of torch.cat + separate element-wise launches.  Channel counts, channel
  * offsets and pitches are in floats and must be multiples of 4; pointers 16-byte aligned.
  *
- * nhwc_pack: concatenate n_src (<= 4) PACKED sources (pitch == channels) along channels and store the result at
- *   channel offset dst_channel_offset[d] of each of the n_dst (<= 2) destinations with row pitch dst_pitch[d].
- *   src / src_channels / dst / dst_channel_offset / dst_pitch are HOST arrays.
+ * nhwc_pack: concatenate n_src (<= 4) sources along channels and store the result at channel offset
+ *   dst_channel_offset[d] of each of the n_dst (<= 2) destinations with row pitch dst_pitch[d].  A source is src_channels[s]
+ *   channels starting at src[s] in rows of pitch src_pitch[s] (NULL: packed, pitch == channels; a channel slice of a wider
+ *   tensor has the pointer advanced to its first channel).  src / src_channels / src_pitch / dst / dst_channel_offset /
+ *   dst_pitch are HOST arrays.
  * gru_gate_zr: zr_raw (pixels, 2*hidden) = conv output WITHOUT bias of the stacked update|reset gate convolution,
  *   bias_zr (2*hidden); z_out (pixels, hidden) = sigmoid(zr[:, :hidden] + b); rhx[:, :hidden] = sigmoid(zr[:, hidden:] + b) * hx[:, :hidden].
  * gru_gate_out: q_raw (pixels, hidden) conv output without bias; hx[:, :hidden] <- (1 - z) * h + z * tanh(q_raw + b),
  *   in place, and the same rows packed into h_out (pixels, hidden) for the two heads.
  * iter_update: raw head outputs (no bias) of FlowOrClassificationHead (update.py:6-20) addressed as
- *   base + b*C*h*w + c*channel_stride + pix*pixel_stride (NCHW: (h*w, 1); channels-last: (1, C));
+ *   base + b*batch_stride + c*channel_stride + pix*pixel_stride (NCHW: (C*h*w, h*w, 1); channels-last: (C*h*w, 1, C);
+ *   channel slices of one stacked head output work too);
  *   coords1 (batch,2,h,w) += dflow + bias; logits (batch,n_logits,h,w) += dlogits + bias; flow = coords1 - coords_grid
- *   (channel 0 = column, channel 1 = row: raft_code/utils.py:32-37); coords1 / flow / logits are NCHW contiguous.
+ *   (channel 0 = column, channel 1 = row: raft_code/utils.py:32-37); coords1 / flow / logits are NCHW contiguous;
+ *   stacked (optional) receives the NCHW concatenation [flow | logits] (batch, 2 + n_logits, h, w).
  * add_relu: out = relu(x + y) over n floats (residual join of extractor.py:57-68; out may alias x or y). */
-int slimb200_nhwc_pack(const float* const* src, const int32_t* src_channels, int32_t n_src, float* const* dst,
-                       const int32_t* dst_channel_offset, const int32_t* dst_pitch, int32_t n_dst, int64_t pixels,
-                       void* stream);
+int slimb200_nhwc_pack(const float* const* src, const int32_t* src_channels, const int32_t* src_pitch, int32_t n_src,
+                       float* const* dst, const int32_t* dst_channel_offset, const int32_t* dst_pitch, int32_t n_dst,
+                       int64_t pixels, void* stream);
 int slimb200_gru_gate_zr(const float* zr_raw, const float* bias_zr, const float* hx, int32_t hx_pitch, float* z_out,
                          float* rhx, int32_t rhx_pitch, int32_t hidden, int64_t pixels, void* stream);
 int slimb200_gru_gate_out(const float* q_raw, const float* bias_q, const float* z, float* hx, int32_t hx_pitch,
                           float* h_out, int32_t hidden, int64_t pixels, void* stream);
-int slimb200_iter_update(const float* dflow_raw, int64_t dflow_channel_stride, int64_t dflow_pixel_stride,
-                         const float* bias_flow, const float* dlogits_raw, int64_t dlogits_channel_stride,
-                         int64_t dlogits_pixel_stride, const float* bias_logits, int32_t n_logits, int32_t batch,
-                         int32_t h, int32_t w, float* coords1, float* flow, float* logits, void* stream);
+int slimb200_iter_update(const float* dflow_raw, int64_t dflow_batch_stride, int64_t dflow_channel_stride,
+                         int64_t dflow_pixel_stride, const float* bias_flow, const float* dlogits_raw,
+                         int64_t dlogits_batch_stride, int64_t dlogits_channel_stride, int64_t dlogits_pixel_stride,
+                         const float* bias_logits, int32_t n_logits, int32_t batch, int32_t h, int32_t w, float* coords1,
+                         float* flow, float* logits, float* stacked, void* stream);
 int slimb200_add_relu(const float* x, const float* y, float* out, int64_t n, void* stream);
 
 const char* slimb200_strerror(int code);

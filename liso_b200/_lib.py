@@ -126,8 +126,8 @@ SYMBOLS = {
     ),
     "slimb200_nhwc_pack": (
         C.c_int,
-        [C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int32),
-         C.POINTER(C.c_int32), C.c_int32, C.c_int64, C.c_void_p],
+        [C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p),
+         C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.c_int64, C.c_void_p],
     ),
     "slimb200_gru_gate_zr": (
         C.c_int,
@@ -139,8 +139,8 @@ SYMBOLS = {
     ),
     "slimb200_iter_update": (
         C.c_int,
-        [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
-         C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+        [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
+         C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     ),
     "slimb200_add_relu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "slimb200_strerror": (C.c_char_p, [C.c_int]),

@@ -33,7 +33,8 @@ inline unsigned grid_for(size_t items, int per_thread = 1) {
 
 struct PackArgs {
   const float4* src[4];
-  int src_g[4];      // float4 groups per pixel of each source (packed: pitch == channels)
+  int src_g[4];      // float4 groups per pixel of each source
+  int src_pitch_g[4];  // row pitch of each source in float4 groups (== src_g for a packed tensor, larger for a channel slice)
   int n_src, total_g;
   float4* dst[2];
   int dst_off_g[2], dst_pitch_g[2];
@@ -46,7 +47,7 @@ __global__ void __launch_bounds__(GL_THREADS) k_nhwc_pack(const PackArgs a) {
   for (size_t i = (size_t)blockIdx.x * GL_THREADS + threadIdx.x; i < total; i += (size_t)gridDim.x * GL_THREADS) {
     const size_t p = i / a.total_g;
     const int gg = (int)(i - p * a.total_g);
-    int g = gg, sg = a.src_g[0];
+    int g = gg, sg = a.src_g[0], spitch = a.src_pitch_g[0];
     const float4* sp = a.src[0];
 #pragma unroll
     for (int s = 1; s < 4; ++s) {
@@ -54,9 +55,10 @@ __global__ void __launch_bounds__(GL_THREADS) k_nhwc_pack(const PackArgs a) {
         g -= sg;
         sp = a.src[s];
         sg = a.src_g[s];
+        spitch = a.src_pitch_g[s];
       }
     }
-    const float4 v = __ldg(sp + p * sg + g);
+    const float4 v = __ldg(sp + p * spitch + g);
     a.dst[0][p * a.dst_pitch_g[0] + a.dst_off_g[0] + gg] = v;
     if (a.n_dst > 1) a.dst[1][p * a.dst_pitch_g[1] + a.dst_off_g[1] + gg] = v;
   }
@@ -120,15 +122,16 @@ __global__ void __launch_bounds__(GL_THREADS) k_gru_gate_out(const float* __rest
 }
 
 struct IterArgs {
-  const float* dflow;    // (batch, 2, h, w) raw head output, element (b, c, pix) at b * 2 * hw + c * cs_f + pix * ps_f
-  const float* dlogits;  // (batch, nl, h, w) likewise with cs_l / ps_l
+  const float* dflow;    // (batch, 2, h, w) raw head output, element (b, c, pix) at b * bs_f + c * cs_f + pix * ps_f
+  const float* dlogits;  // (batch, nl, h, w) likewise with bs_l / cs_l / ps_l
   const float* bias_f;
   const float* bias_l;
   float* coords1;  // (batch, 2, h, w) planar
   float* flow;     // (batch, 2, h, w) planar
   float* logits;   // (batch, nl, h, w) planar
+  float* stacked;  // optional (batch, 2 + nl, h, w) planar copy [flow | logits]
   int batch, h, w, nl;
-  long long cs_f, ps_f, cs_l, ps_l;
+  long long bs_f, cs_f, ps_f, bs_l, cs_l, ps_l;
 };
 
 __global__ void __launch_bounds__(GL_THREADS) k_iter_update(const IterArgs a) {
@@ -139,16 +142,20 @@ __global__ void __launch_bounds__(GL_THREADS) k_iter_update(const IterArgs a) {
     const int row = pix / a.w, col = pix - row * a.w;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-      const float d = __fadd_rn(__ldg(a.dflow + (size_t)b * 2 * hw + c * a.cs_f + pix * a.ps_f), __ldg(a.bias_f + c));
+      const float d = __fadd_rn(__ldg(a.dflow + b * a.bs_f + c * a.cs_f + pix * a.ps_f), __ldg(a.bias_f + c));
       float* cp = a.coords1 + ((size_t)b * 2 + c) * hw + pix;
       const float nc = __fadd_rn(*cp, d);
       *cp = nc;
-      a.flow[((size_t)b * 2 + c) * hw + pix] = __fsub_rn(nc, (float)(c == 0 ? col : row));  // coords0: ch0 = x, ch1 = y
+      const float fl = __fsub_rn(nc, (float)(c == 0 ? col : row));  // coords0: ch0 = x, ch1 = y
+      a.flow[((size_t)b * 2 + c) * hw + pix] = fl;
+      if (a.stacked) a.stacked[((size_t)b * (2 + a.nl) + c) * hw + pix] = fl;
     }
     for (int c = 0; c < a.nl; ++c) {
-      const float d = __fadd_rn(__ldg(a.dlogits + (size_t)b * a.nl * hw + c * a.cs_l + pix * a.ps_l), __ldg(a.bias_l + c));
+      const float d = __fadd_rn(__ldg(a.dlogits + b * a.bs_l + c * a.cs_l + pix * a.ps_l), __ldg(a.bias_l + c));
       float* lp = a.logits + ((size_t)b * a.nl + c) * hw + pix;
-      *lp = __fadd_rn(*lp, d);
+      const float nv = __fadd_rn(*lp, d);
+      *lp = nv;
+      if (a.stacked) a.stacked[((size_t)b * (2 + a.nl) + 2 + c) * hw + pix] = nv;
     }
   }
 }
@@ -171,7 +178,7 @@ inline bool mis16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) 
 }  // namespace
 
 extern "C" int slimb200_nhwc_pack(const float* const* src /*host[n_src]*/, const int32_t* src_channels /*host[n_src]*/,
-                                  int32_t n_src, float* const* dst /*host[n_dst]*/, const int32_t* dst_channel_offset,
+                                  const int32_t* src_pitch /*host[n_src] or NULL = packed*/, int32_t n_src, float* const* dst /*host[n_dst]*/, const int32_t* dst_channel_offset,
                                   const int32_t* dst_pitch, int32_t n_dst, int64_t pixels, void* stream_) {
   if (!src || !src_channels || !dst || !dst_channel_offset || !dst_pitch || pixels < 0) return SLIMB200_E_INVALID;
   if (n_src < 1 || n_src > 4 || n_dst < 1 || n_dst > 2) return SLIMB200_E_UNSUPPORTED;
@@ -182,6 +189,7 @@ extern "C" int slimb200_nhwc_pack(const float* const* src /*host[n_src]*/, const
   for (int i = 0; i < 4; ++i) {
     a.src[i] = nullptr;
     a.src_g[i] = 0;
+    a.src_pitch_g[i] = 0;
   }
   int total = 0;
   for (int i = 0; i < n_src; ++i) {
@@ -190,6 +198,10 @@ extern "C" int slimb200_nhwc_pack(const float* const* src /*host[n_src]*/, const
     if (mis16(src[i])) return SLIMB200_E_ALIGNMENT;
     a.src[i] = reinterpret_cast<const float4*>(src[i]);
     a.src_g[i] = src_channels[i] >> 2;
+    const int pitch = src_pitch ? src_pitch[i] : src_channels[i];
+    if (pitch < src_channels[i]) return SLIMB200_E_INVALID;
+    if (pitch & 3) return SLIMB200_E_UNSUPPORTED;
+    a.src_pitch_g[i] = pitch >> 2;
     total += src_channels[i];
   }
   a.total_g = total >> 2;
@@ -235,10 +247,11 @@ extern "C" int slimb200_gru_gate_out(const float* q_raw, const float* bias_q, co
   return SLIMB200_OK;
 }
 
-extern "C" int slimb200_iter_update(const float* dflow_raw, int64_t dflow_channel_stride, int64_t dflow_pixel_stride,
-                                    const float* bias_flow, const float* dlogits_raw, int64_t dlogits_channel_stride,
-                                    int64_t dlogits_pixel_stride, const float* bias_logits, int32_t n_logits, int32_t batch,
-                                    int32_t h, int32_t w, float* coords1, float* flow, float* logits, void* stream_) {
+extern "C" int slimb200_iter_update(const float* dflow_raw, int64_t dflow_batch_stride, int64_t dflow_channel_stride,
+                                    int64_t dflow_pixel_stride, const float* bias_flow, const float* dlogits_raw,
+                                    int64_t dlogits_batch_stride, int64_t dlogits_channel_stride, int64_t dlogits_pixel_stride,
+                                    const float* bias_logits, int32_t n_logits, int32_t batch, int32_t h, int32_t w,
+                                    float* coords1, float* flow, float* logits, float* stacked, void* stream_) {
   if (!dflow_raw || !bias_flow || !dlogits_raw || !bias_logits || !coords1 || !flow || !logits) return SLIMB200_E_INVALID;
   if (batch < 1 || h < 1 || w < 1 || n_logits < 1 || n_logits > 16) return SLIMB200_E_INVALID;
   IterArgs a{};
@@ -249,6 +262,9 @@ extern "C" int slimb200_iter_update(const float* dflow_raw, int64_t dflow_channe
   a.coords1 = coords1;
   a.flow = flow;
   a.logits = logits;
+  a.stacked = stacked;
+  a.bs_f = dflow_batch_stride;
+  a.bs_l = dlogits_batch_stride;
   a.batch = batch;
   a.h = h;
   a.w = w;

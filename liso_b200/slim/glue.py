@@ -33,10 +33,29 @@ def _pixels(t: torch.Tensor) -> int:
     return t.shape[0] * t.shape[2] * t.shape[3]
 
 
+def _nhwc_source(t: torch.Tensor) -> Tuple[torch.Tensor, int]:
+    """(tensor, row pitch in floats) of a source: a packed channels-last tensor or a channel slice ``u[:, a:b]`` of one
+    (channel offset and width multiples of 4); anything else is copied to a packed channels-last tensor first."""
+    _lib.require_cuda(t)
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    if is_nhwc(t):
+        return t, t.shape[1]
+    B, Cn, h, w = t.shape
+    pitch = t.stride(3)
+    if (t.dim() == 4 and t.stride(1) == 1 and pitch >= Cn and pitch % 4 == 0 and t.stride(2) == w * pitch
+            and t.stride(0) == h * w * pitch and t.data_ptr() % 16 == 0):
+        return t, pitch
+    return t.contiguous(memory_format=torch.channels_last), Cn
+
+
 def nhwc_pack_into(srcs: Sequence[torch.Tensor], dsts: Sequence[Tuple[torch.Tensor, int]]) -> None:
-    """Channel-concatenate ``srcs`` (<= 4) and store the result at channel offset ``off`` of every ``(dst, off)``
-    (<= 2 destinations, packed channels-last tensors with >= off + sum(C_src) channels)."""
-    srcs = [as_nhwc(s) for s in srcs]
+    """Channel-concatenate ``srcs`` (<= 4; packed channels-last tensors or channel slices of such) and store the result at
+    channel offset ``off`` of every ``(dst, off)`` (<= 2 destinations, packed channels-last tensors with
+    >= off + sum(C_src) channels)."""
+    pairs = [_nhwc_source(s) for s in srcs]
+    srcs = [p[0] for p in pairs]
     B, _, h, w = srcs[0].shape
     for s in srcs:
         if (s.shape[0], s.shape[2], s.shape[3]) != (B, h, w):
@@ -47,10 +66,11 @@ def nhwc_pack_into(srcs: Sequence[torch.Tensor], dsts: Sequence[Tuple[torch.Tens
     n_s, n_d = len(srcs), len(dsts)
     sp = (C.c_void_p * n_s)(*[s.data_ptr() for s in srcs])
     sc = (C.c_int32 * n_s)(*[s.shape[1] for s in srcs])
+    spitch = (C.c_int32 * n_s)(*[p[1] for p in pairs])
     dp = (C.c_void_p * n_d)(*[d.data_ptr() for d, _ in dsts])
     do = (C.c_int32 * n_d)(*[int(o) for _, o in dsts])
     dpitch = (C.c_int32 * n_d)(*[d.shape[1] for d, _ in dsts])
-    _lib.check(_lib.load().slimb200_nhwc_pack(sp, sc, n_s, dp, do, dpitch, n_d, B * h * w, _lib.current_stream_ptr()))
+    _lib.check(_lib.load().slimb200_nhwc_pack(sp, sc, spitch, n_s, dp, do, dpitch, n_d, B * h * w, _lib.current_stream_ptr()))
 
 
 def nhwc_cat(srcs: Sequence[torch.Tensor]) -> torch.Tensor:
@@ -87,35 +107,39 @@ def gru_gate_out(q_raw: torch.Tensor, bias_q: torch.Tensor, z: torch.Tensor, hx:
     return h
 
 
-def _head_strides(t: torch.Tensor) -> Tuple[torch.Tensor, int, int]:
-    """(tensor, channel stride, pixel stride) of a (B, C, h, w) head output that is NCHW- or channels-last-contiguous."""
+def _head_strides(t: torch.Tensor) -> Tuple[torch.Tensor, int, int, int]:
+    """(tensor, batch stride, channel stride, pixel stride) of a (B, C, h, w) head output: NCHW- or channels-last-dense,
+    or a channel slice of such a tensor (the two heads evaluated as one stacked convolution)."""
     _lib.require_cuda(t)
     t = t.detach()
     if t.dtype != torch.float32:
         t = t.float()
-    if t.is_contiguous():
-        return t, t.shape[2] * t.shape[3], 1
-    if t.is_contiguous(memory_format=torch.channels_last):
-        return t, 1, t.shape[1]
+    _, _, h, w = t.shape
+    if t.stride(3) * w == t.stride(2) and (h == 1 or t.stride(2) > 0):  # pixels are evenly spaced: pix * stride(3)
+        return t, t.stride(0), t.stride(1), t.stride(3)
     t = t.contiguous()
-    return t, t.shape[2] * t.shape[3], 1
+    return t, t.stride(0), t.stride(1), 1
 
 
 def iter_update(dflow_raw: torch.Tensor, bias_flow: torch.Tensor, dlogits_raw: torch.Tensor, bias_logits: torch.Tensor,
-                coords1: torch.Tensor, flow: torch.Tensor, logits: torch.Tensor) -> None:
+                coords1: torch.Tensor, flow: torch.Tensor, logits: torch.Tensor, stacked: torch.Tensor = None) -> None:
     """In place (``raft_mod.py:205-212``): ``coords1 += dflow_raw + b``; ``logits += dlogits_raw + b``;
-    ``flow = coords1 - coords_grid``.  The raw tensors are the head convolutions without bias."""
+    ``flow = coords1 - coords_grid``; optionally ``stacked = cat[flow, logits]``.  The raw tensors are the head
+    convolutions without bias."""
     B, _, h, w = coords1.shape
-    for t in (coords1, flow, logits):
+    for t in (coords1, flow, logits) + ((stacked,) if stacked is not None else ()):
         if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
-            raise ValueError("iter_update: coords1 / flow / logits must be contiguous fp32 CUDA tensors")
+            raise ValueError("iter_update: coords1 / flow / logits / stacked must be contiguous fp32 CUDA tensors")
     if tuple(dflow_raw.shape) != (B, 2, h, w) or tuple(dlogits_raw.shape) != tuple(logits.shape) or tuple(flow.shape) != (B, 2, h, w):
         raise ValueError("iter_update: shape mismatch")
-    df, cs_f, ps_f = _head_strides(dflow_raw)
-    dl, cs_l, ps_l = _head_strides(dlogits_raw)
-    _lib.check(_lib.load().slimb200_iter_update(df.data_ptr(), cs_f, ps_f, bias_flow.data_ptr(), dl.data_ptr(), cs_l, ps_l,
-                                                bias_logits.data_ptr(), logits.shape[1], B, h, w, coords1.data_ptr(),
-                                                flow.data_ptr(), logits.data_ptr(), _lib.current_stream_ptr()))
+    if stacked is not None and tuple(stacked.shape) != (B, 2 + logits.shape[1], h, w):
+        raise ValueError("iter_update: stacked must be (B, 2 + n_logits, h, w)")
+    df, bs_f, cs_f, ps_f = _head_strides(dflow_raw)
+    dl, bs_l, cs_l, ps_l = _head_strides(dlogits_raw)
+    _lib.check(_lib.load().slimb200_iter_update(df.data_ptr(), bs_f, cs_f, ps_f, bias_flow.data_ptr(), dl.data_ptr(), bs_l, cs_l,
+                                                ps_l, bias_logits.data_ptr(), logits.shape[1], B, h, w, coords1.data_ptr(),
+                                                flow.data_ptr(), logits.data_ptr(),
+                                                stacked.data_ptr() if stacked is not None else None, _lib.current_stream_ptr()))
 
 
 def add_relu(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:

@@ -60,15 +60,42 @@ def _cat_params(ts):
     return hit
 
 
-def conv_relu(conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
+def conv_relu(conv: nn.Conv2d, x: torch.Tensor, weight: torch.Tensor = None, bias: torch.Tensor = None) -> torch.Tensor:
+    """relu(conv(x)); ``weight`` / ``bias`` override the module's own (stacked parallel convolutions, same geometry)."""
+    w, b = (conv.weight, conv.bias) if weight is None else (weight, bias)
     if FAST_STOCK_OPS and x.is_cuda and conv.padding_mode == "zeros" and not torch.is_grad_enabled():
-        w, b = conv.weight, conv.bias
         if torch.is_autocast_enabled():  # the fused op is not on autocast's cast list
             dt = torch.get_autocast_dtype("cuda")
             x, w, b = x.to(dt), _autocast_param(w, dt), _autocast_param(b, dt)
         if x.dtype == w.dtype:
             return torch.cudnn_convolution_relu(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
-    return F.relu(conv(x))
+    return F.relu(F.conv2d(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups))
+
+
+def _same_geometry(a: nn.Conv2d, b: nn.Conv2d) -> bool:
+    return (a.kernel_size == b.kernel_size and a.stride == b.stride and a.padding == b.padding and a.dilation == b.dilation
+            and a.groups == b.groups == 1 and a.padding_mode == b.padding_mode == "zeros")
+
+
+def _stacked_params(a: nn.Conv2d, b: nn.Conv2d, shared_input: bool):
+    """Weight / bias of ONE convolution that evaluates the parallel convolutions ``a`` and ``b`` (same geometry): outputs
+    stacked [a | b]; with ``shared_input`` both read the same tensor, otherwise the input is the channel concatenation
+    [in_a | in_b] and the weight is block-diagonal (the zero blocks add exact zeros).  Cached like `_cat_params`."""
+    key = ("stacked", shared_input) + tuple((t.data_ptr(), t._version) for t in (a.weight, a.bias, b.weight, b.bias))
+    hit = _PARAM_CAST_CACHE.get(key)
+    if hit is None:
+        wa, wb = a.weight.detach(), b.weight.detach()
+        if shared_input:
+            w = torch.cat([wa, wb], dim=0)
+        else:
+            w = wa.new_zeros((wa.shape[0] + wb.shape[0], wa.shape[1] + wb.shape[1]) + tuple(wa.shape[2:]))
+            w[:wa.shape[0], :wa.shape[1]] = wa
+            w[wa.shape[0]:, wa.shape[1]:] = wb
+        if wa.is_contiguous(memory_format=torch.channels_last) and not wa.is_contiguous():
+            w = w.contiguous(memory_format=torch.channels_last)
+        hit = (w, torch.cat([a.bias.detach(), b.bias.detach()], dim=0))
+        _PARAM_CAST_CACHE[key] = hit
+    return hit
 
 
 def instance_norm_nhwc(norm: nn.InstanceNorm2d, x: torch.Tensor, relu: bool, residual: torch.Tensor = None) -> torch.Tensor:
@@ -320,6 +347,9 @@ class RAFT(nn.Module):
         self.use_cuda_graph = True
         # glue-kernel version of the update block's element-wise work (channels-last fp32 inference only)
         self.fused_update_block = True
+        # ... and its pairs of parallel convolutions (flow / logits branches of the motion encoder, the two heads) stacked
+        # into one cuDNN launch each
+        self.merge_parallel_convs = True
         self._graphs = {}
         rows = float(cfg.data.bev_range_m[0]) / cfg.data.img_grid_size[0] * m.u_net.final_scale
         cols = float(cfg.data.bev_range_m[1]) / cfg.data.img_grid_size[1] * m.u_net.final_scale
@@ -355,7 +385,7 @@ class RAFT(nn.Module):
         B = len(pcl_t0)
         wsig = tuple((p.data_ptr(), p._version) for mod in (self.fnet, self.cnet, self.update_block) for p in mod.parameters())
         key = (B, self.output_iterations, self.pp_layer.canvas_memory_format, str(dev), torch.backends.cudnn.allow_tf32,
-               self.fused_update_block, FAST_STOCK_OPS, wsig)
+               self.fused_update_block, self.merge_parallel_convs, FAST_STOCK_OPS, wsig)
         st = self._graphs.get("net")
         if st is not None and st["key"] != key:
             st = None  # (the old graph and its buffers are released when the slot is overwritten)
@@ -464,18 +494,41 @@ class RAFT(nn.Module):
         def raw(conv, x):  # the convolution without its bias (the consumer adds it)
             return F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
 
+        # parallel convolutions evaluated as one launch each (stock cuDNN, like the stacked update | reset gates):
+        # [conv_flow1 | conv_class1] on [flow | logits], [conv_flow2 | conv_class2] block-diagonal, both heads' conv1 on
+        # the shared hidden state, both heads' conv2 block-diagonal
+        merge = (self.merge_parallel_convs and _same_geometry(me.conv_flow1, me.conv_class1)
+                 and _same_geometry(me.conv_flow2, me.conv_class2) and _same_geometry(fh.conv1, lh.conv1)
+                 and _same_geometry(fh.conv2, lh.conv2) and me.conv_flow2.out_channels % 4 == 0
+                 and me.conv_class2.out_channels % 4 == 0)
+        if merge:
+            w_m1, b_m1 = _stacked_params(me.conv_flow1, me.conv_class1, shared_input=False)
+            w_m2, b_m2 = _stacked_params(me.conv_flow2, me.conv_class2, shared_input=False)
+            w_h1, b_h1 = _stacked_params(fh.conv1, lh.conv1, shared_input=True)
+            w_h2, _ = _stacked_params(fh.conv2, lh.conv2, shared_input=False)
+            stacked = torch.zeros((batch, 2 + logits.shape[1], h, w), dtype=torch.float32, device=device)  # [flow | logits]
+            n_f = me.conv_flow2.out_channels
         outs = []
         for it in range(m.num_iters):
             corr = correlation(coords1)
             c = conv_relu(me.conv_stat_corr1, corr)
-            f = conv_relu(me.conv_flow2, conv_relu(me.conv_flow1, flow))
-            lg = conv_relu(me.conv_class2, conv_relu(me.conv_class1, logits))
-            out = conv_relu(me.conv, g.nhwc_cat([c, f, lg]))
+            if merge:
+                flg = conv_relu(me.conv_flow2, conv_relu(me.conv_flow1, stacked, w_m1, b_m1), w_m2, b_m2)  # [flow | logits] features
+                f, lg = flg[:, :n_f], flg[:, n_f:]
+                out = conv_relu(me.conv, g.nhwc_cat([c, flg]))
+            else:
+                f = conv_relu(me.conv_flow2, conv_relu(me.conv_flow1, flow))
+                lg = conv_relu(me.conv_class2, conv_relu(me.conv_class1, logits))
+                out = conv_relu(me.conv, g.nhwc_cat([c, f, lg]))
             g.nhwc_pack_into([out, lg, f], [(hx, Ch + Cx), (rhx, Ch + Cx)])  # x = [inp | out | logits | flow]
             z = g.gru_gate_zr(F.conv2d(hx, w_zr, None, gru.convz.stride, gru.convz.padding), b_zr, hx, rhx, Ch)
             net = g.gru_gate_out(raw(gru.convq, rhx), gru.convq.bias, z, hx, Ch)
-            g.iter_update(raw(fh.conv2, conv_relu(fh.conv1, net)), fh.conv2.bias, raw(lh.conv2, conv_relu(lh.conv1, net)),
-                          lh.conv2.bias, coords1, flow, logits)
+            if merge:
+                d = F.conv2d(conv_relu(fh.conv1, net, w_h1, b_h1), w_h2, None, fh.conv2.stride, fh.conv2.padding)
+                g.iter_update(d[:, :2], fh.conv2.bias, d[:, 2:], lh.conv2.bias, coords1, flow, logits, stacked)
+            else:
+                g.iter_update(raw(fh.conv2, conv_relu(fh.conv1, net)), fh.conv2.bias, raw(lh.conv2, conv_relu(lh.conv1, net)),
+                              lh.conv2.bias, coords1, flow, logits)
             if self.output_iterations == "last" and it != m.num_iters - 1:
                 continue
             outs.append(raft_output_fused(flow, logits, ds, self.bev_rows_res_meters_per_fs_pixel,

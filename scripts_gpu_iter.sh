@@ -3,9 +3,10 @@
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_glue.py tests/test_gpu_corr.py -q -m gpu --timeout=300 > gpurun_out/pytest_new.log 2>&1; echo "pytest new exit $?" > gpurun_out/summary.txt
 timeout 900 python -m pytest tests -q -m gpu --timeout=600 --deselect tests/test_gpu_glue.py --deselect tests/test_gpu_corr.py > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rest exit $?" >> gpurun_out/summary.txt
+timeout 300 python tools/kbench.py --skip-pillar > gpurun_out/kbench.txt 2>&1; echo "kbench exit $?" >> gpurun_out/summary.txt
 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?" >> gpurun_out/summary.txt
 grep -E "^(FAILED|ERROR)|passed|failed|Error|assert" gpurun_out/pytest_new.log | head -40
-tail -n 3 gpurun_out/pytest_gpu.log; cat gpurun_out/summary.txt; tail -n 5 gpurun_out/bench.err
+grep lookup gpurun_out/kbench.txt; tail -n 3 gpurun_out/pytest_gpu.log; cat gpurun_out/summary.txt; tail -n 5 gpurun_out/bench.err
 python - <<'PY'
 import json
 try:

@@ -35,6 +35,10 @@ def test_nhwc_pack_equals_cat(cuda, B, h, w):
     cat = torch.cat([o, lg, f], dim=1)
     assert torch.equal(hx[:, 156:], cat) and torch.equal(hx[:, :156], hx0[:, :156])
     assert torch.equal(rhx[:, 160:308], cat) and torch.equal(rhx[:, :160], rhx0[:, :160]) and torch.equal(rhx[:, 308:], rhx0[:, 308:])
+    # channel slices of a wider channels-last tensor as sources (the stacked flow | logits branch of the motion encoder)
+    wide = _nhwc(B, 64, h, w, 3, cuda)
+    G.nhwc_pack_into([o, wide[:, 32:], wide[:, :32]], [(hx, 160)])
+    assert torch.equal(hx[:, 160:], torch.cat([o, wide[:, 32:], wide[:, :32]], dim=1)) and torch.equal(hx[:, :156], hx0[:, :156])
     with pytest.raises(RuntimeError):
         G.nhwc_pack_into([o, lg, f], [(hx, 160)])  # does not fit
     with pytest.raises(RuntimeError):
@@ -82,6 +86,14 @@ def test_iter_update_equals_stock_ops(cuda, B, h, w, fmt):
     l_ref = logits + (dl + bl[None, :, None, None])
     G.iter_update(df, bf, dl, bl, coords1, flow, logits)
     assert torch.equal(coords1, c_ref) and torch.equal(logits, l_ref) and torch.equal(flow, c_ref - coords0)
+    # both head outputs as channel slices of ONE stacked tensor, plus the stacked [flow | logits] copy
+    d6 = torch.cat([df, dl], dim=1).contiguous(memory_format=mf)
+    stacked = torch.full((B, 6, h, w), float("nan"), device=cuda)
+    c2_ref = c_ref + (df + bf[None, :, None, None])
+    l2_ref = l_ref + (dl + bl[None, :, None, None])
+    G.iter_update(d6[:, :2], bf, d6[:, 2:], bl, coords1, flow, logits, stacked)
+    assert torch.equal(coords1, c2_ref) and torch.equal(logits, l2_ref) and torch.equal(flow, c2_ref - coords0)
+    assert torch.equal(stacked, torch.cat([flow, logits], dim=1))
 
 
 @pytest.mark.parametrize("B,C,H,W", [(2, 32, 40, 56), (3, 96, 17, 23), (8, 32, 320, 320)])
@@ -118,6 +130,9 @@ def test_fused_update_block_equals_stock_loop(cuda):
     p1 = [p.to(cuda) for p in s1["pcl_full_no_ground_ta"]]
     with torch.no_grad():
         fused = [o.clone() for o in net(p0, p1)[0]]
+        net.merge_parallel_convs = False
+        unmerged = [o.clone() for o in net(p0, p1)[0]]
+        net.merge_parallel_convs = True
         net.fused_update_block = False
         stock_loop = [o.clone() for o in net(p0, p1)[0]]
         R.FAST_STOCK_OPS = False
@@ -127,8 +142,10 @@ def test_fused_update_block_equals_stock_loop(cuda):
             R.FAST_STOCK_OPS = True
             net.fused_update_block = True
     assert len(fused) == len(stock_loop) == len(stock) == 6
-    for a, b, c in zip(fused, stock_loop, stock):
-        assert a.shape == b.shape == c.shape
+    for a, u, b, c in zip(fused, unmerged, stock_loop, stock):
+        assert a.shape == b.shape == c.shape == u.shape
+        # stacked parallel convolutions: same products, possibly another summation order inside cuDNN
+        assert float((a - u).abs().max()) <= 2e-4, float((a - u).abs().max())
         # same convolutions, same element-wise rounding: the glue kernels reproduce the stock loop
-        assert float((a - b).abs().max()) <= 1e-4, float((a - b).abs().max())
+        assert float((u - b).abs().max()) <= 1e-4, float((u - b).abs().max())
         assert float((a - c).abs().max()) <= 5e-3, float((a - c).abs().max())
