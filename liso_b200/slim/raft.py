@@ -350,6 +350,9 @@ class RAFT(nn.Module):
         # ... and its pairs of parallel convolutions (flow / logits branches of the motion encoder, the two heads) stacked
         # into one cuDNN launch each
         self.merge_parallel_convs = True
+        # forward and backward direction as two parallel branches of the CUDA graph
+        self.concurrent_directions = True
+        self._streams = {}
         self._graphs = {}
         rows = float(cfg.data.bev_range_m[0]) / cfg.data.img_grid_size[0] * m.u_net.final_scale
         cols = float(cfg.data.bev_range_m[1]) / cfg.data.img_grid_size[1] * m.u_net.final_scale
@@ -385,7 +388,7 @@ class RAFT(nn.Module):
         B = len(pcl_t0)
         wsig = tuple((p.data_ptr(), p._version) for mod in (self.fnet, self.cnet, self.update_block) for p in mod.parameters())
         key = (B, self.output_iterations, self.pp_layer.canvas_memory_format, str(dev), torch.backends.cudnn.allow_tf32,
-               self.fused_update_block, self.merge_parallel_convs, FAST_STOCK_OPS, wsig)
+               self.fused_update_block, self.merge_parallel_convs, self.concurrent_directions, FAST_STOCK_OPS, wsig)
         st = self._graphs.get("net")
         if st is not None and st["key"] != key:
             st = None  # (the old graph and its buffers are released when the slot is overwritten)
@@ -404,9 +407,28 @@ class RAFT(nn.Module):
         """Feature encoders, correlation pyramids, context encoders and both refinement loops (raft_mod.py:82-257)."""
         fmap_t0 = self.fnet(img_t0)
         fmap_t1 = self.fnet(img_t1)
+        if self.concurrent_directions and img_t0.is_cuda and torch.cuda.is_current_stream_capturing():
+            # the forward and the backward direction (context encoder, pyramid, refinement loop) share nothing but the
+            # read-only feature maps and weights: inside the CUDA graph they are two parallel branches, so the many
+            # short kernels of one loop fill the gaps of the other.  Fork / join with stream waits (captured as graph
+            # dependencies); every tensor a branch allocates stays on its own stream, the shared inputs outlive the join.
+            main = torch.cuda.current_stream(img_t0.device)
+            side = self._branch_stream(img_t0.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                bw = self.predict_single_flow_map_and_classes(img_t1, fmap_t1, fmap_t0, self.head_decoder_bw)
+            fw = self.predict_single_flow_map_and_classes(img_t0, fmap_t0, fmap_t1, self.head_decoder_fw)
+            main.wait_stream(side)
+            return fw, bw
         fw = self.predict_single_flow_map_and_classes(img_t0, fmap_t0, fmap_t1, self.head_decoder_fw)
         bw = self.predict_single_flow_map_and_classes(img_t1, fmap_t1, fmap_t0, self.head_decoder_bw)
         return fw, bw
+
+    def _branch_stream(self, device):
+        st = self._streams.get(str(device))
+        if st is None:
+            st = self._streams[str(device)] = torch.cuda.Stream(device=device)
+        return st
 
     def _capture_net_graph(self, st, dev):
         lib = _lib_mod()

@@ -91,6 +91,16 @@ def main():
             for i in range(_lib.N_KERNELS):
                 if n_k[i]:
                     print("%-16s %-24s %8.4f ms/launch  (%d launches)" % (name, lib.slimb200_kernel_name(i).decode(), ms_k[i] / n_k[i], n_k[i]))
+            # the same calls back to back behind a spin kernel (queue full before the GPU starts), two events only:
+            # stream time per call without per-launch event brackets
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda._sleep(int(30e-3 * 1.9e9))
+            e0.record()
+            for _ in range(args.reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            print("%-16s %-24s %8.4f ms/call back-to-back (2 events, %d calls)" % (name, "(stream time)", e0.elapsed_time(e1) / args.reps, args.reps))
     sys.stdout.flush()
 
 
