@@ -348,8 +348,8 @@ __device__ __forceinline__ int v3_fetch_row(const T* __restrict__ pyr, int n_pan
   for (int c = 0; c < NCHUNK; ++c) {
     const int col = ca + c * EPC;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (row_ok && col < hi && col + EPC > lo)
-      v = __ldg(reinterpret_cast<const uint4*>(pyr + panel_index<T>(n_panels, nf, b, pix, col)));
+    if (row_ok && col < hi && col + EPC > lo)  // read once per lookup, 878 MB per 8 samples: streaming (evict-first) loads
+      v = __ldcs(reinterpret_cast<const uint4*>(pyr + panel_index<T>(n_panels, nf, b, pix, col)));
     ld[c * 4 + 0] = v.x;
     ld[c * 4 + 1] = v.y;
     ld[c * 4 + 2] = v.z;

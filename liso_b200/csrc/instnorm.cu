@@ -3,10 +3,11 @@
 // Replaces `norm_fn = "instance_affine"` + ReLU of the SLIM feature extractor (liso/slim/model/extractor.py:5-68,
 // 211-297: nn.InstanceNorm2d(C, eps=1e-3, affine=True) followed by nn.ReLU), which PyTorch runs as a copy to NCHW,
 // cuDNN's batch-norm kernel on (1, B*C, H, W), a copy back and a clamp.  Three launches, two passes over the data:
-//   k_in_stats     per (sample, slab of pixels): shifted sums -> (count, mean, M2) per channel, lanes = channel groups of
-//                  4 (every load is a coalesced float4 of a pixel's channel vector), Chan merge of the lanes in fp64
-//   k_in_finalize  per (sample, channel): Chan merge of the slab partials in fp64 -> scale = gamma / sqrt(var + eps),
-//                  shift = beta - mean * scale (biased variance, like F.instance_norm)
+//   k_in_stats     per (sample, slab of pixels): shifted sums (shift = the slab's first pixel) per channel, lanes = channel
+//                  groups of 4 (every load is a coalesced float4 of a pixel's channel vector), lanes added in fp64 ->
+//                  (count, mean, M2) per slab; about one wave of CTAs whatever the tensor size
+//   k_in_finalize  per (sample, channel): exact pooling of the slab partials in fp64 (no division per partial) ->
+//                  scale = gamma / sqrt(var + eps), shift = beta - mean * scale (biased variance, like F.instance_norm)
 //   k_in_apply     out = max(x * scale + shift, 0) as float4; optionally the residual join of the block is fused in:
 //                  out = relu(residual + relu(x * scale + shift))
 // The convolutions themselves stay stock cuDNN.
@@ -15,7 +16,7 @@
 namespace {
 
 constexpr int IN_THREADS = 256;
-constexpr int IN_MAX_SLABS = 128;
+constexpr int IN_MAX_SLABS = 512;
 
 struct InArgs {
   const float* x;
@@ -29,24 +30,56 @@ struct InArgs {
   float eps;
 };
 
-__global__ void __launch_bounds__(IN_THREADS) k_in_stats(const InArgs a) {
-  __shared__ float s_cnt[IN_THREADS][4], s_mean[IN_THREADS][4], s_m2[IN_THREADS][4];
+// One warp merges the slab partials of one (sample, channel): exact pooled mean and M2 in fp64 without a division per
+// partial -- N = sum n_s, mean = sum n_s mean_s / N, M2 = sum [M2_s + n_s (mean_s - mean)^2] -- lanes take strided
+// subsets, plain butterfly sums; biased variance like F.instance_norm.
+__device__ __forceinline__ void in_finalize_channel(const InArgs& a, int b, int c, int lane) {
+  const float* base = a.partial + ((size_t)b * a.slabs * a.C + c) * 3;
+  const size_t stride = (size_t)a.C * 3;
+  double n = 0.0, sm = 0.0;
+  for (int s = lane; s < a.slabs; s += 32) {
+    const double nb = (double)__ldcg(base + s * stride), mb = (double)__ldcg(base + s * stride + 1);
+    n += nb;
+    sm = fma(nb, mb, sm);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    n += __shfl_xor_sync(0xffffffffu, n, d);
+    sm += __shfl_xor_sync(0xffffffffu, sm, d);
+  }
+  const double mu = n > 0.0 ? sm / n : 0.0;
+  double M2 = 0.0;
+  for (int s = lane; s < a.slabs; s += 32) {
+    const double nb = (double)__ldcg(base + s * stride), dl = (double)__ldcg(base + s * stride + 1) - mu;
+    M2 += (double)__ldcg(base + s * stride + 2) + nb * dl * dl;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) M2 += __shfl_xor_sync(0xffffffffu, M2, d);
+  if (lane == 0) {
+    const double var = n > 0.0 ? M2 / n : 0.0;
+    const float scale = a.gamma[c] * (float)(1.0 / sqrt(var + (double)a.eps));
+    a.scale_shift[((size_t)b * a.C + c) * 2] = scale;
+    a.scale_shift[((size_t)b * a.C + c) * 2 + 1] = a.beta[c] - (float)mu * scale;
+  }
+}
+
+__global__ void __launch_bounds__(IN_THREADS, 6) k_in_stats(const InArgs a) {
+  __shared__ float s_s1[IN_THREADS][4], s_s2[IN_THREADS][4];
   const int G = a.C >> 2;               // float4 groups per pixel
   const int P = IN_THREADS / G;         // pixels per pass
   const int b = blockIdx.y, slab = blockIdx.x;
   const int g = threadIdx.x % G, p = threadIdx.x / G;
   const int per_slab = (a.hw + a.slabs - 1) / a.slabs;
   const int lo = slab * per_slab, hi = min(a.hw, lo + per_slab);
-  // shifted sums (shift = the lane's first sample, so the sums stay small and s2 - s1^2/n does not cancel): two FMAs
-  // per element, no division in the loop; converted to (count, mean, M2) for the Chan merges
-  float cnt = 0.f, mean[4] = {0.f, 0.f, 0.f, 0.f}, m2[4] = {0.f, 0.f, 0.f, 0.f};
-  if (p < P && lo + p < hi) {
+  // shifted sums: the shift of a channel is its value at the slab's first pixel (shared by all pixel-lanes, so their
+  // sums simply add); the sums stay small and s2 - s1^2/n does not cancel.  Two FMAs per element, 8 loads in flight.
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  float K[4] = {0.f, 0.f, 0.f, 0.f};
+  if (lo < hi && p < P) {
     const float4* src = reinterpret_cast<const float4*>(a.x + (size_t)b * a.hw * a.C) + g;
-    const float4 k4 = __ldg(src + (size_t)(lo + p) * G);
-    const float K[4] = {k4.x, k4.y, k4.z, k4.w};
-    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-    int n = 0;
-#pragma unroll 4
+    const float4 k4 = __ldg(src + (size_t)lo * G);
+    K[0] = k4.x; K[1] = k4.y; K[2] = k4.z; K[3] = k4.w;
+#pragma unroll 8
     for (int i = lo + p; i < hi; i += P) {
       const float4 v = __ldg(src + (size_t)i * G);
       const float xs[4] = {v.x, v.y, v.z, v.w};
@@ -56,78 +89,42 @@ __global__ void __launch_bounds__(IN_THREADS) k_in_stats(const InArgs a) {
         s1[k] += d;
         s2[k] = fmaf(d, d, s2[k]);
       }
-      ++n;
-    }
-    cnt = (float)n;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      mean[k] = K[k] + s1[k] / cnt;
-      m2[k] = fmaxf(s2[k] - s1[k] * s1[k] / cnt, 0.f);
     }
   }
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    s_cnt[threadIdx.x][k] = cnt;
-    s_mean[threadIdx.x][k] = mean[k];
-    s_m2[threadIdx.x][k] = m2[k];
+    s_s1[threadIdx.x][k] = s1[k];
+    s_s2[threadIdx.x][k] = s2[k];
   }
   __syncthreads();
-  // thread (g, k) merges the P pixel-lanes of its channel in fixed order (Chan et al.)
+  // thread (g, k) adds the P pixel-lanes of its channel in fixed order (fp64) and converts to (count, mean, M2)
   if (threadIdx.x < a.C) {
     const int c = threadIdx.x, gg = c >> 2, k = c & 3;
-    double n = 0.0, mu = 0.0, M2 = 0.0;
+    double S1 = 0.0, S2 = 0.0;
     for (int q = 0; q < P; ++q) {
-      const int t = q * G + gg;
-      const double nb = s_cnt[t][k];
-      if (nb == 0.0) continue;
-      const double d = (double)s_mean[t][k] - mu, nn = n + nb;
-      mu += d * nb / nn;
-      M2 += (double)s_m2[t][k] + d * d * n * nb / nn;
-      n = nn;
+      S1 += (double)s_s1[q * G + gg][k];
+      S2 += (double)s_s2[q * G + gg][k];
     }
+    const int n = max(hi - lo, 0);
     float* o = a.partial + (((size_t)b * a.slabs + slab) * a.C + c) * 3;
+    double mean = 0.0, M2 = 0.0;
+    if (n > 0) {
+      // the thread that loaded channel c's shift is (p = 0, g = gg): same value in every lane of the group
+      const double Kc = (double)__ldg(a.x + ((size_t)b * a.hw + lo) * a.C + c);
+      mean = Kc + S1 / n;
+      M2 = fmax(S2 - S1 * S1 / n, 0.0);
+    }
     o[0] = (float)n;
-    o[1] = (float)mu;
+    o[1] = (float)mean;
     o[2] = (float)M2;
   }
 }
 
-// one warp per (sample, channel): lanes merge strided subsets of the slab partials, then a butterfly of Chan merges
+// one warp per (sample, channel)
 __global__ void __launch_bounds__(IN_THREADS) k_in_finalize(const InArgs a) {
   const int i = (blockIdx.x * IN_THREADS + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
   if (i >= a.batch * a.C) return;
-  const int b = i / a.C, c = i - b * a.C;
-  double n = 0.0, mu = 0.0, M2 = 0.0;
-  for (int s = lane; s < a.slabs; s += 32) {
-    const float* p = a.partial + (((size_t)b * a.slabs + s) * a.C + c) * 3;
-    const double nb = p[0];
-    if (nb == 0.0) continue;
-    const double d = (double)p[1] - mu, nn = n + nb;
-    mu += d * nb / nn;
-    M2 += (double)p[2] + d * d * n * nb / nn;
-    n = nn;
-  }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    const double nb = __shfl_xor_sync(0xffffffffu, n, d), mb = __shfl_xor_sync(0xffffffffu, mu, d),
-                 Mb = __shfl_xor_sync(0xffffffffu, M2, d);
-    const double nn = n + nb;
-    if (nn > 0.0) {
-      const double dl = mb - mu;
-      // symmetric form so that both partners of the exchange compute the same merged triple
-      const double mu_new = (n * mu + nb * mb) / nn;
-      M2 = M2 + Mb + dl * dl * n * nb / nn;
-      mu = mu_new;
-      n = nn;
-    }
-  }
-  if (lane == 0) {
-    const double var = n > 0 ? M2 / n : 0.0;  // biased, like F.instance_norm
-    const float scale = a.gamma[c] * (float)(1.0 / sqrt(var + (double)a.eps));
-    a.scale_shift[(size_t)i * 2] = scale;
-    a.scale_shift[(size_t)i * 2 + 1] = a.beta[c] - (float)mu * scale;
-  }
+  in_finalize_channel(a, i / a.C, i % a.C, threadIdx.x & 31);
 }
 
 // out = [relu_outer]([relu_inner](x * scale + shift) + residual), float4.  relu bit 0 = inner (the norm's own ReLU),
@@ -173,8 +170,10 @@ __global__ void __launch_bounds__(IN_THREADS) k_in_apply(const InArgs a) {
   }
 }
 
-int slabs_for(int hw) {
-  int s = hw / 1024;
+// slabs per sample: one full wave of CTAs (148 SMs x 6 resident) over the batch, at least 32 pixels per slab
+int slabs_for(int batch, int hw) {
+  int s = (148 * 6) / batch;
+  if (s > hw / 32) s = hw / 32;
   return s < 1 ? 1 : (s > IN_MAX_SLABS ? IN_MAX_SLABS : s);
 }
 
@@ -183,7 +182,7 @@ int slabs_for(int hw) {
 extern "C" size_t slimb200_instnorm_workspace_bytes(int32_t batch, int32_t channels, int32_t hw) {
   if (batch < 1 || channels < 4 || hw < 1) return 0;
   WorkspaceCarver w(nullptr);
-  w.take<float>((size_t)batch * slabs_for(hw) * channels * 3);
+  w.take<float>((size_t)batch * slabs_for(batch, hw) * channels * 3);
   w.take<float>((size_t)batch * channels * 2);
   return w.used();
 }
@@ -208,7 +207,7 @@ extern "C" int slimb200_instnorm_nhwc(const float* x, const float* gamma, const 
   a.batch = batch;
   a.hw = (int)hw;
   a.C = channels;
-  a.slabs = slabs_for((int)hw);
+  a.slabs = slabs_for(batch, (int)hw);
   a.relu = relu;
   a.eps = eps;
   WorkspaceCarver w(workspace);

@@ -98,15 +98,17 @@ def _stacked_params(a: nn.Conv2d, b: nn.Conv2d, shared_input: bool):
     return hit
 
 
-def instance_norm_nhwc(norm: nn.InstanceNorm2d, x: torch.Tensor, relu: bool, residual: torch.Tensor = None) -> torch.Tensor:
+def instance_norm_nhwc(norm: nn.InstanceNorm2d, x: torch.Tensor, relu: bool, residual: torch.Tensor = None,
+                       inplace: bool = False) -> torch.Tensor:
     """Affine InstanceNorm2d (+ ReLU) of a channels-last CUDA tensor in the library's glue kernel
     (``slimb200_instnorm_nhwc``): 3 launches / 2 passes instead of copy-to-NCHW + cuDNN batch-norm + copy back + clamp.
-    With ``residual`` the block's join is fused into the same pass: ``relu(residual + [relu](norm(x)))``."""
+    With ``residual`` the block's join is fused into the same pass: ``relu(residual + [relu](norm(x)))``.
+    ``inplace`` overwrites ``x`` (a convolution output nobody else reads): half the L2 footprint of the apply pass."""
     lib = _lib_mod().load()
     if not x.is_contiguous(memory_format=torch.channels_last):
         x = x.contiguous(memory_format=torch.channels_last)
     B, Cn, H, W = x.shape
-    out = torch.empty_like(x)  # preserves the channels-last strides
+    out = x if inplace else torch.empty_like(x)  # (empty_like preserves the channels-last strides)
     ws = torch.empty(max(256, lib.slimb200_instnorm_workspace_bytes(B, Cn, H * W)), dtype=torch.uint8, device=x.device)
     flags = (1 if relu else 0) | (2 if residual is not None else 0)
     _lib_mod().check(lib.slimb200_instnorm_nhwc(x.data_ptr(), norm.weight.data_ptr(), norm.bias.data_ptr(), float(norm.eps), B, H, W,
@@ -139,8 +141,8 @@ def conv_norm(conv: nn.Conv2d, norm: nn.Module, x: torch.Tensor, relu: bool, res
         y = F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
         if residual is None or (residual.shape == y.shape and residual.stride() == y.stride() and residual.dtype == y.dtype
                                 and residual.is_cuda):
-            return instance_norm_nhwc(norm, y, relu=relu, residual=residual)
-        return add_relu(residual, instance_norm_nhwc(norm, y, relu=relu))
+            return instance_norm_nhwc(norm, y, relu=relu, residual=residual, inplace=True)
+        return add_relu(residual, instance_norm_nhwc(norm, y, relu=relu, inplace=True))
     y = norm(conv(x))
     y = F.relu(y) if relu else y
     return y if residual is None else add_relu(residual, y)

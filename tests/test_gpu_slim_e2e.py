@@ -28,7 +28,7 @@ def _aee(pred, ref, valid):
     return float((pred - ref).norm(dim=-1)[valid].mean())
 
 
-@pytest.mark.parametrize("workload,seeds", [("T", [3, 4]), ("N", [5]), ("K", [6])])
+@pytest.mark.parametrize("workload,seeds", [("T", [3, 4]), ("N", [5]), ("K", [6]), ("A", [7])])
 def test_slim_forward_flow_within_1cm(cuda, workload, seeds):
     cfg = make_cfg(workload)
     model, sd = _model(cfg, cuda)
