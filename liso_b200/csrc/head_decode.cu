@@ -67,40 +67,66 @@ __global__ void __launch_bounds__(256) k_decode_min(const float* __restrict__ ne
 // the global min of the static / dynamic logits that the decoder needs (k_decode_min disappears).
 // Interpolation follows ATen's upsample_bilinear2d: src = dst * (in - 1) / (out - 1), taps (i, i + (i < in - 1)).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_raft_output(const float* __restrict__ flow, const float* __restrict__ logits, int batch,
-                                                     int h, int w, int n, float res_rows, float res_cols,
-                                                     float* __restrict__ net_out, unsigned* __restrict__ min_key) {
+constexpr int RO_THREADS = 128;
+
+__device__ __forceinline__ float sel3(float a, float b, float c, int i) { return i == 0 ? a : (i == 1 ? b : c); }
+
+// One thread = one output column x and RO_ROWS <= n consecutive output rows: the rows share the column taps / weights
+// and, since (RO_ROWS - 1) * (h - 1) / (H - 1) < 1, touch at most 3 source rows, so (n = 8) the 6 maps cost 36 loads
+// per 8 output cells instead of 192 and the horizontal blends are shared.  Same association as ATen:
+// hl0 * (wl0 * a + wl1 * b) + hl1 * (wl0 * c + wl1 * d).
+template <int RO_ROWS>
+__global__ void __launch_bounds__(RO_THREADS) k_raft_output(const float* __restrict__ flow, const float* __restrict__ logits,
+                                                            int batch, int h, int w, int n, float res_rows, float res_cols,
+                                                            float* __restrict__ net_out, unsigned* __restrict__ min_key) {
   const int H = h * n, W = w * n;
+  const int groups = (H + RO_ROWS - 1) / RO_ROWS;
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y % H, b = blockIdx.y / H;  // warp-uniform
+  const int y0 = (blockIdx.y % groups) * RO_ROWS, b = blockIdx.y / groups;  // warp-uniform
+  const int lane = threadIdx.x & 31;
+  const int x0 = x - lane;  // first pixel of the warp
   unsigned best = 0xffffffffu;
-  float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+  const float rh = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, rw = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
+  const int hb = (int)(rh * (float)y0);  // first source row of the group
+  float t[6][3];                         // horizontally blended source rows hb, hb + 1, hb + 2 of the 6 maps
   if (x < W) {
-    const float rh = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, rw = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
-    const float hr = rh * (float)y, wr = rw * (float)x;
-    const int h1 = (int)hr, w1 = (int)wr;
-    const int hp = h1 < h - 1 ? 1 : 0, wp = w1 < w - 1 ? 1 : 0;
-    const float hl1 = hr - (float)h1, hl0 = 1.f - hl1;
+    const float wr = rw * (float)x;
+    const int w1 = (int)wr;
+    const int wp = w1 < w - 1 ? 1 : 0;
     const float wl1 = wr - (float)w1, wl0 = 1.f - wl1;
     const size_t plane = (size_t)h * w;
-    const size_t o00 = (size_t)h1 * w + w1, o01 = o00 + wp, o10 = o00 + (size_t)hp * w, o11 = o10 + wp;
-    auto interp = [&](const float* img) {
-      return hl0 * (wl0 * __ldg(img + o00) + wl1 * __ldg(img + o01)) + hl1 * (wl0 * __ldg(img + o10) + wl1 * __ldg(img + o11));
-    };
-    const float* lg = logits + (size_t)b * 4 * plane;
-    const float* fl = flow + (size_t)b * 2 * plane;
-    const float l0 = interp(lg), l1 = interp(lg + plane), l2 = interp(lg + 2 * plane), l3 = interp(lg + 3 * plane);
-    const float fx = __fmul_rn((float)n, interp(fl)), fy = __fmul_rn((float)n, interp(fl + plane));  // upflow_n
-    const float f_row = __fmul_rn(fy, res_rows), f_col = __fmul_rn(fx, res_cols);                    // flip, then * res
-    v0 = make_float4(l0, l1, l2, l3);
-    v1 = make_float4(f_row, f_col, f_row, f_col);
-    best = min(f2key(l1), f2key(l2));
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      const float* img = c < 4 ? logits + ((size_t)b * 4 + c) * plane : flow + ((size_t)b * 2 + (c - 4)) * plane;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int hr = min(hb + r, h - 1);
+        t[c][r] = wl0 * __ldg(img + (size_t)hr * w + w1) + wl1 * __ldg(img + (size_t)hr * w + w1 + wp);
+      }
+    }
   }
-  // a warp owns 32 consecutive pixels = 1 KB of output: exchange so that each store instruction writes 512
-  // contiguous bytes (lane l stores float4 number l resp. 32 + l of the warp's 64)
-  {
-    const int lane = threadIdx.x & 31;
-    const int x0 = x - lane;  // first pixel of the warp (W is a multiple of 32 or the tail is handled per lane)
+#pragma unroll
+  for (int dy = 0; dy < RO_ROWS; ++dy) {
+    const int y = y0 + dy;
+    if (y >= H) break;  // warp-uniform
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+    if (x < W) {
+      const float hr = rh * (float)y;
+      const int h1 = (int)hr;
+      const int hp = h1 < h - 1 ? 1 : 0;
+      const float hl1 = hr - (float)h1, hl0 = 1.f - hl1;
+      const int i0 = h1 - hb, i1 = i0 + hp;  // 0..2
+      float o[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) o[c] = hl0 * sel3(t[c][0], t[c][1], t[c][2], i0) + hl1 * sel3(t[c][0], t[c][1], t[c][2], i1);
+      const float fx = __fmul_rn((float)n, o[4]), fy = __fmul_rn((float)n, o[5]);              // upflow_n
+      const float f_row = __fmul_rn(fy, res_rows), f_col = __fmul_rn(fx, res_cols);            // flip, then * res
+      v0 = make_float4(o[0], o[1], o[2], o[3]);
+      v1 = make_float4(f_row, f_col, f_row, f_col);
+      best = min(best, min(f2key(o[1]), f2key(o[2])));
+    }
+    // a warp owns 32 consecutive pixels = 1 KB of output: exchange so that each store instruction writes 512
+    // contiguous bytes (lane l stores float4 number l resp. 32 + l of the warp's 64)
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       const int src = half * 16 + (lane >> 1);
@@ -110,8 +136,8 @@ __global__ void __launch_bounds__(256) k_raft_output(const float* __restrict__ f
       t0.z = __shfl_sync(0xffffffffu, v0.z, src); t0.w = __shfl_sync(0xffffffffu, v0.w, src);
       t1.x = __shfl_sync(0xffffffffu, v1.x, src); t1.y = __shfl_sync(0xffffffffu, v1.y, src);
       t1.z = __shfl_sync(0xffffffffu, v1.z, src); t1.w = __shfl_sync(0xffffffffu, v1.w, src);
-      const float4 t = second ? t1 : t0;
-      if (x0 + src < W) reinterpret_cast<float4*>(net_out + (((size_t)b * H + y) * W + x0) * 8)[half * 32 + lane] = t;
+      const float4 tv = second ? t1 : t0;
+      if (x0 + src < W) reinterpret_cast<float4*>(net_out + (((size_t)b * H + y) * W + x0) * 8)[half * 32 + lane] = tv;
     }
   }
   block_min_to_global(best, min_key);
@@ -441,9 +467,22 @@ extern "C" int slimb200_raft_output(const float* flow, const float* logits, int3
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (min_key) SLIMB200_CUDA_TRY(cudaMemsetAsync(min_key, 0xff, sizeof(uint32_t), stream));
   if ((long long)batch * h * n > 0x7fffffffLL) return SLIMB200_E_UNSUPPORTED;
-  dim3 grid((w * n + 255) / 256, batch * h * n);
-  SLIMB200_LAUNCH(SLIMB200_K_RAFT_OUTPUT, stream,
-                  (k_raft_output<<<grid, 256, 0, stream>>>(flow, logits, batch, h, w, n, res_rows, res_cols, net_out, min_key)));
+  const int rows = n >= 8 ? 8 : (n >= 4 ? 4 : (n >= 2 ? 2 : 1));  // rows per thread, <= n
+  dim3 grid((w * n + RO_THREADS - 1) / RO_THREADS, batch * ((h * n + rows - 1) / rows));
+#define SLIMB200_RO_LAUNCH(R)                                                                                        \
+  SLIMB200_LAUNCH(SLIMB200_K_RAFT_OUTPUT, stream,                                                                    \
+                  (k_raft_output<R><<<grid, RO_THREADS, 0, stream>>>(flow, logits, batch, h, w, n, res_rows, res_cols, \
+                                                                      net_out, min_key)))
+  if (rows == 8) {
+    SLIMB200_RO_LAUNCH(8);
+  } else if (rows == 4) {
+    SLIMB200_RO_LAUNCH(4);
+  } else if (rows == 2) {
+    SLIMB200_RO_LAUNCH(2);
+  } else {
+    SLIMB200_RO_LAUNCH(1);
+  }
+#undef SLIMB200_RO_LAUNCH
   return SLIMB200_OK;
 }
 

@@ -228,7 +228,9 @@ class ExportPipeline:
             with torch.no_grad(), ctx:
                 pf, pb = self.model(d0, d1, None)
             fw, bw = pf[-1].modified_network_output, pb[-1].modified_network_output
-            outs = [fw.static_flow, bw.static_flow, fw.dynamicness, bw.dynamicness]
+            # packed copies: the predictions may be views of the CUDA graph's static outputs, which the next forward
+            # overwrites while this batch is still being downloaded
+            outs = [t.contiguous() for t in (fw.static_flow, bw.static_flow, fw.dynamicness, bw.dynamicness)]
             done = torch.cuda.Event()
             done.record(cur)
             done_evt[idx % D] = done

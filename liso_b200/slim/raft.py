@@ -354,6 +354,13 @@ class RAFT(nn.Module):
         self.merge_parallel_convs = True
         # forward and backward direction as two parallel branches of the CUDA graph
         self.concurrent_directions = True
+        # consumer of the per-iteration network outputs, e.g. SLIM's output decoder: called as
+        # output_sink(direction, iteration, net_out, occupancy) right behind the kernel that wrote `net_out`.  While the
+        # CUDA graph is captured it runs on a forked stream, i.e. the decodes become side branches of the graph that
+        # overlap the following GRU iterations; output_sink_begin() announces a new pass (eager call or capture).
+        self.output_sink = None
+        self.output_sink_begin = None
+        self.graph_extra_key = None  # whatever else the captured graph depends on (the sink's static buffers)
         self._streams = {}
         self._graphs = {}
         rows = float(cfg.data.bev_range_m[0]) / cfg.data.img_grid_size[0] * m.u_net.final_scale
@@ -374,13 +381,10 @@ class RAFT(nn.Module):
         applies the dataset's ground rule itself."""
         kw = {"raw_scan": True} if raw_scans else {}  # (the reference signature is forward(pcl, img=None))
         dev = pcl_t0[0].device
-        use_graph = (self.use_cuda_graph and FAST_STOCK_OPS and dev.type == "cuda" and not torch.is_grad_enabled()
-                     and not self.training and not torch.cuda.is_current_stream_capturing()
-                     and len(pcl_t0) == len(pcl_t1) and hasattr(self.pp_layer, "empty_outputs"))
-        if not use_graph:
+        if not self.will_use_graph(pcl_t0, pcl_t1):
             img_t0, occ_t0 = self.pp_layer(pcl_t0, **kw)
             img_t1, occ_t1 = self.pp_layer(pcl_t1, **kw)
-            fw, bw = self._net_body(img_t0, img_t1)
+            fw, bw = self._net_body(img_t0, img_t1, (occ_t0, occ_t1))
             return fw, bw, {"t0": {"bev_net_input_dbg": occ_t0}, "t1": {"bev_net_input_dbg": occ_t1}}
 
         # ---- everything between the pillar encoder and the decoder as ONE CUDA graph (SURVEY 8f.2): the encoder writes
@@ -390,7 +394,8 @@ class RAFT(nn.Module):
         B = len(pcl_t0)
         wsig = tuple((p.data_ptr(), p._version) for mod in (self.fnet, self.cnet, self.update_block) for p in mod.parameters())
         key = (B, self.output_iterations, self.pp_layer.canvas_memory_format, str(dev), torch.backends.cudnn.allow_tf32,
-               self.fused_update_block, self.merge_parallel_convs, self.concurrent_directions, FAST_STOCK_OPS, wsig)
+               self.fused_update_block, self.merge_parallel_convs, self.concurrent_directions, FAST_STOCK_OPS,
+               self.output_sink is not None, self.graph_extra_key, wsig)
         st = self._graphs.get("net")
         if st is not None and st["key"] != key:
             st = None  # (the old graph and its buffers are released when the slot is overwritten)
@@ -405,8 +410,17 @@ class RAFT(nn.Module):
         aux = {"t0": {"bev_net_input_dbg": st["in"][0][1]}, "t1": {"bev_net_input_dbg": st["in"][1][1]}}
         return st["outs"][0], st["outs"][1], aux
 
-    def _net_body(self, img_t0, img_t1):
+    def will_use_graph(self, pcl_t0, pcl_t1) -> bool:
+        dev = pcl_t0[0].device
+        return (self.use_cuda_graph and FAST_STOCK_OPS and dev.type == "cuda" and not torch.is_grad_enabled()
+                and not self.training and not torch.cuda.is_current_stream_capturing()
+                and len(pcl_t0) == len(pcl_t1) and hasattr(self.pp_layer, "empty_outputs"))
+
+    def _net_body(self, img_t0, img_t1, occupancies=(None, None)):
         """Feature encoders, correlation pyramids, context encoders and both refinement loops (raft_mod.py:82-257)."""
+        self._occupancies = occupancies
+        if self.output_sink_begin is not None:
+            self.output_sink_begin()
         fmap_t0 = self.fnet(img_t0)
         fmap_t1 = self.fnet(img_t1)
         if self.concurrent_directions and img_t0.is_cuda and torch.cuda.is_current_stream_capturing():
@@ -418,47 +432,70 @@ class RAFT(nn.Module):
             side = self._branch_stream(img_t0.device)
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                bw = self.predict_single_flow_map_and_classes(img_t1, fmap_t1, fmap_t0, self.head_decoder_bw)
-            fw = self.predict_single_flow_map_and_classes(img_t0, fmap_t0, fmap_t1, self.head_decoder_fw)
+                bw = self.predict_single_flow_map_and_classes(img_t1, fmap_t1, fmap_t0, self.head_decoder_bw, direction=1)
+            fw = self.predict_single_flow_map_and_classes(img_t0, fmap_t0, fmap_t1, self.head_decoder_fw, direction=0)
             main.wait_stream(side)
             return fw, bw
-        fw = self.predict_single_flow_map_and_classes(img_t0, fmap_t0, fmap_t1, self.head_decoder_fw)
-        bw = self.predict_single_flow_map_and_classes(img_t1, fmap_t1, fmap_t0, self.head_decoder_bw)
+        fw = self.predict_single_flow_map_and_classes(img_t0, fmap_t0, fmap_t1, self.head_decoder_fw, direction=0)
+        bw = self.predict_single_flow_map_and_classes(img_t1, fmap_t1, fmap_t0, self.head_decoder_bw, direction=1)
         return fw, bw
 
-    def _branch_stream(self, device):
-        st = self._streams.get(str(device))
+    def _branch_stream(self, device, name="bw", priority=-1):
+        """Streams of the graph's branches.  The two refinement loops are captured on high-priority streams, the sink
+        (decoder) branches on default-priority ones: the node priorities are captured with the graph, so the decoders'
+        large grids fill the SMs only where the latency-bound loops leave them idle."""
+        st = self._streams.get((str(device), name))
         if st is None:
-            st = self._streams[str(device)] = torch.cuda.Stream(device=device)
+            st = self._streams[(str(device), name)] = torch.cuda.Stream(device=device, priority=priority)
         return st
+
+    def _emit(self, direction, it, out):
+        """Hand a finished network output to the sink: inline in eager mode, on a forked stream (= a side branch of the
+        graph, joined by `_join_sink` at the end of the loop) while capturing."""
+        if self.output_sink is None:
+            return
+        occ = self._occupancies[direction]
+        if out.is_cuda and torch.cuda.is_current_stream_capturing():
+            cur = torch.cuda.current_stream(out.device)
+            ds = self._branch_stream(out.device, "sink%d" % direction, priority=0)
+            ds.wait_stream(cur)
+            with torch.cuda.stream(ds):
+                self.output_sink(direction, it, out, occ)
+        else:
+            self.output_sink(direction, it, out, occ)
+
+    def _join_sink(self, direction, device):
+        if self.output_sink is not None and device.type == "cuda" and torch.cuda.is_current_stream_capturing():
+            torch.cuda.current_stream(device).wait_stream(self._branch_stream(device, "sink%d" % direction, priority=0))
 
     def _capture_net_graph(self, st, dev):
         lib = _lib_mod()
         img_t0, img_t1 = st["in"][0][0], st["in"][1][0]
+        occ = (st["in"][0][1], st["in"][1][1])
         # warm-up on a side stream (cuDNN autotuning, lazy kernel attributes), as torch.cuda.graphs asks
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(2):
-                self._net_body(img_t0, img_t1)
+                self._net_body(img_t0, img_t1, occ)
         torch.cuda.current_stream(dev).wait_stream(side)
         graph = torch.cuda.CUDAGraph()
         n0 = lib.load().slimb200_launch_count(-1)
-        with torch.cuda.graph(graph):
-            st["outs"] = self._net_body(img_t0, img_t1)
+        with torch.cuda.graph(graph, stream=self._branch_stream(dev, "fw")):
+            st["outs"] = self._net_body(img_t0, img_t1, occ)
         st["launches"] = int(lib.load().slimb200_launch_count(-1) - n0)  # library kernels inside one replay
         st["graph"] = graph
         self._graphs["net"] = st
         self.n_graph_captures = getattr(self, "n_graph_captures", 0) + 1
 
-    def _gru_loop(self, correlation, net, inp, img_hw, batch, device) -> List[torch.Tensor]:
+    def _gru_loop(self, correlation, net, inp, img_hw, batch, device, direction=0) -> List[torch.Tensor]:
         """The refinement loop of ``raft_mod.py:188-257``: lookup -> update block -> coordinate / logit update, and the
         per-iteration network output.  Pure function of (pyramid, net, inp): this is what gets captured in a CUDA graph."""
         m = self.slim_cfg.model
         ds = m.feature_downsampling_factor
         h, w = img_hw[0] // ds, img_hw[1] // ds
         if self._fused_update_ok(correlation, net, inp):
-            return self._gru_loop_fused(correlation, net, inp, h, w, batch, device)
+            return self._gru_loop_fused(correlation, net, inp, h, w, batch, device, direction)
         coords0 = coords_grid(batch, h, w, device)
         coords1 = coords_grid(batch, h, w, device)
         logits = torch.zeros((batch, 4, h, w), dtype=torch.float32, device=device)
@@ -475,12 +512,15 @@ class RAFT(nn.Module):
             if FAST_STOCK_OPS and coords1.is_cuda:
                 outs.append(raft_output_fused(coords1 - coords0, logits, ds, self.bev_rows_res_meters_per_fs_pixel,
                                               self.bev_cols_res_meters_per_fs_pixel))
+                self._emit(direction, it, outs[-1])
                 continue
             # RAFT (x, y) pixel flow -> (row, col) metres (raft_mod.py:262-266)
             res = torch.tensor([self.bev_rows_res_meters_per_fs_pixel, self.bev_cols_res_meters_per_fs_pixel],
                                device=device, dtype=torch.float32)[None, :, None, None]
             flow_m = torch.flip(upflow_n(coords1 - coords0, n=ds), dims=[1]) * res
             outs.append(concat2network_output(uplogits_n(logits, n=ds), flow_m, flow_m))
+            self._emit(direction, it, outs[-1])
+        self._join_sink(direction, device)
         return outs
 
     def _fused_update_ok(self, correlation, net, inp) -> bool:
@@ -491,7 +531,7 @@ class RAFT(nn.Module):
                 and isinstance(self.update_block, SmallUpdateBlock) and self.update_block.gru.convz.padding_mode == "zeros"
                 and net.shape[1] % 4 == 0 and inp.shape[1] % 4 == 0)
 
-    def _gru_loop_fused(self, correlation, net, inp, h, w, batch, device) -> List[torch.Tensor]:
+    def _gru_loop_fused(self, correlation, net, inp, h, w, batch, device, direction=0) -> List[torch.Tensor]:
         """Same loop as `_gru_loop` (raft_mod.py:188-257, update.py:23-38,70-93,130-150) with the element-wise work
         between the stock convolutions in the library's glue kernels: the two 304-channel GRU inputs
         [h | inp | motion] and [r*h | inp | motion] are persistent channels-last buffers whose slots the producers
@@ -557,11 +597,13 @@ class RAFT(nn.Module):
                 continue
             outs.append(raft_output_fused(flow, logits, ds, self.bev_rows_res_meters_per_fs_pixel,
                                           self.bev_cols_res_meters_per_fs_pixel))
+            self._emit(direction, it, outs[-1])
+        self._join_sink(direction, device)
         return outs
 
-    def predict_single_flow_map_and_classes(self, img_t0, fmap_t0, fmap_t1, decoder=None) -> List[torch.Tensor]:
+    def predict_single_flow_map_and_classes(self, img_t0, fmap_t0, fmap_t1, decoder=None, direction=0) -> List[torch.Tensor]:
         m = self.slim_cfg.model
         b, _, H, W = img_t0.shape
         correlation = CorrBlock(fmap_t0, fmap_t1, num_levels=m.corr_cfg.num_levels, radius=m.corr_cfg.search_radius)
         net, inp = torch.split(self.cnet(img_t0), [self.hidden_dim, self.context_dim], dim=1)
-        return self._gru_loop(correlation, torch.tanh(net), torch.relu(inp), (H, W), b, img_t0.device)
+        return self._gru_loop(correlation, torch.tanh(net), torch.relu(inp), (H, W), b, img_t0.device, direction)

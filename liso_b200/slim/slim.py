@@ -270,19 +270,98 @@ class SLIM(nn.Module):
         self.decode_iterations = decode_iterations
         self.raft_network.output_iterations = decode_iterations
         self.static_aggregation = static_aggregation
+        # decode each network output as soon as it exists (a side branch of the CUDA graph) instead of after the network
+        self.decode_as_sink = True
+        self._dec_static, self._dec_ctx, self._dec_n, self._sink_preds = {}, {}, {}, {}
+
+    # ---- output decoding as a sink of the network (SURVEY 8f.1 + 8f.2) ------------------------------------------
+    # The reference decodes every iteration's network output after the network has run (slim.py:77-148).  Here the
+    # decoder is handed to RAFT as `output_sink`: each (B, H, W, 8) output is decoded right behind the kernel that wrote
+    # it -- inline in eager mode, and as a SIDE BRANCH of the CUDA graph when the network is graph-captured, where the
+    # HBM-bound decode kernels overlap the latency-bound GRU iterations that follow.  In graph mode the decoder's inputs
+    # (points, pillar coordinates, validity, threshold) live in grow-only static buffers that are refreshed before every
+    # replay, and the returned predictions are views of the graph's static outputs: valid until the next forward.
+    POINT_CAPACITY_STEP = 8192
+
+    def _sink_begin(self):
+        self._sink_preds = {}
+
+    def _sink(self, direction, it, net_out, occupancy):
+        pc, coors, valid, thr = self._dec_ctx[direction]
+        dec = self.head_decoder_fw if direction == 0 else self.head_decoder_bw
+        filled = torch.squeeze(occupancy > 0.5, dim=1)
+        self._sink_preds[(direction, it)] = dec(net_out, thr, pc=pc, pointwise_voxel_coordinates=coors,
+                                                pointwise_valid_mask=valid, filled_pillar_mask=filled,
+                                                static_aggregation=self.static_aggregation)
+
+    def _stage_decode_inputs(self, samples, dev, thr, static: bool):
+        """Decoder inputs per direction; `static`: copies into grow-only buffers the captured graph points at (padding
+        rows are invalid points).  Returns the graph key part that changes when a buffer is re-allocated."""
+        self._dec_ctx, self._dec_n = {}, {}
+        keys = []
+        for k, sample in enumerate(samples):
+            pt = sample["pcl_ta"]
+            pcl, coors, valid = pt["pcl"], pt["pillar_coors"], pt["pcl_is_valid"]
+            B, N = int(valid.shape[0]), int(valid.shape[1])
+            self._dec_n[k] = N
+            if not static:
+                self._dec_ctx[k] = (pcl.to(dev, non_blocking=True), coors.to(dev, non_blocking=True),
+                                    valid.to(dev, non_blocking=True), thr)
+                continue
+            C = int(pcl.shape[-1])
+            st = self._dec_static.get(k)
+            if st is None or st["pc"].shape[0] != B or st["pc"].shape[2] != C or st["pc"].shape[1] < N or st["pc"].device != dev:
+                step = self.POINT_CAPACITY_STEP
+                cap = max((N + step - 1) // step * step, step, 0 if st is None else int(st["pc"].shape[1]))
+                st = {"pc": torch.full((B, cap, C), float("nan"), dtype=torch.float32, device=dev),
+                      "coors": torch.full((B, cap, 2), -1, dtype=torch.int32, device=dev),
+                      "valid": torch.zeros((B, cap), dtype=torch.bool, device=dev),
+                      "thr": torch.zeros((1,), dtype=torch.float32, device=dev)}
+                self._dec_static[k] = st
+            st["pc"][:, :N].copy_(pcl, non_blocking=True)
+            st["coors"][:, :N].copy_(coors, non_blocking=True)
+            st["valid"][:, :N].copy_(valid, non_blocking=True)
+            if N < st["valid"].shape[1]:
+                st["valid"][:, N:].zero_()
+            st["thr"].copy_(torch.as_tensor(thr, dtype=torch.float32).reshape(1), non_blocking=True)
+            self._dec_ctx[k] = (st["pc"], st["coors"], st["valid"], st["thr"])
+            keys += [st["pc"].data_ptr(), st["coors"].data_ptr(), st["valid"].data_ptr(), st["thr"].data_ptr(),
+                     int(st["pc"].shape[1])]
+        return tuple(keys)
+
+    _POINTWISE = ("static_flow", "dynamic_flow", "dynamicness", "staticness", "aggregated_flow", "static_aggr_flow")
+
+    def _present(self, ret, n_points: int, thr):
+        """The prediction with its point-wise tensors cut to the real number of points (graph mode pads to capacity)."""
+        out = AttrDict(ret)
+        for name in self._POINTWISE:
+            if name in ret and ret[name].shape[1] != n_points:
+                out[name] = ret[name][:, :n_points]
+        out.dynamicness_threshold = thr
+        return out
 
     def forward(self, sample_data_t0, sample_data_t1, summaries=None):
         dev = next(self.parameters()).device
         raw = bool(sample_data_t0.get("raw_scan", False)) and not self.cfg.data.use_ground_for_network
         assert raw == (bool(sample_data_t1.get("raw_scan", False)) and not self.cfg.data.use_ground_for_network)
-        outs_fw, outs_bw, aux = self.raft_network(
-            get_network_input_pcls(self.cfg, sample_data_t0, "ta", to_device=dev),
-            get_network_input_pcls(self.cfg, sample_data_t1, "ta", to_device=dev),
-            raw_scans=raw,
-        )
+        net = self.raft_network
+        pcl_t0 = get_network_input_pcls(self.cfg, sample_data_t0, "ta", to_device=dev)
+        pcl_t1 = get_network_input_pcls(self.cfg, sample_data_t1, "ta", to_device=dev)
+        thr = self.moving_dynamicness_threshold.value()
+        if self.decode_as_sink and dev.type == "cuda":
+            static = net.will_use_graph(pcl_t0, pcl_t1)
+            key = self._stage_decode_inputs((sample_data_t0, sample_data_t1), dev, thr, static)
+            net.output_sink, net.output_sink_begin = self._sink, self._sink_begin
+            net.graph_extra_key = (key, self.static_aggregation) if static else None
+            net(pcl_t0, pcl_t1, raw_scans=raw)
+            preds_fw, preds_bw = ([self._present(self._sink_preds[(k, it)], self._dec_n[k], thr)
+                                   for it in sorted(i for (kk, i) in self._sink_preds if kk == k)] for k in (0, 1))
+            self.predictions_fw, self.predictions_bw = preds_fw, preds_bw
+            return preds_fw, preds_bw
+        net.output_sink = net.output_sink_begin = net.graph_extra_key = None
+        outs_fw, outs_bw, aux = net(pcl_t0, pcl_t1, raw_scans=raw)
         filled = [torch.squeeze(aux[k]["bev_net_input_dbg"] > 0.5, dim=1) for k in ("t0", "t1")]
         its = range(len(outs_fw))  # one entry per iteration, or only the last one in "last" mode
-        thr = self.moving_dynamicness_threshold.value()
         preds_fw, preds_bw = [], []
         per_dir = ((outs_fw, sample_data_t0, filled[0], self.head_decoder_fw, preds_fw),
                    (outs_bw, sample_data_t1, filled[1], self.head_decoder_bw, preds_bw))
