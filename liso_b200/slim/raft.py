@@ -31,7 +31,14 @@ def _lib_mod():
 FAST_STOCK_OPS = True
 
 
-_PARAM_CAST_CACHE = {}
+_PARAM_CAST_CACHE = {}  # derived copies of parameters, keyed by storage + version (inference only)
+
+
+def _cache_put(key, value):
+    if len(_PARAM_CAST_CACHE) > 256:  # entries of overwritten parameter versions are never hit again
+        _PARAM_CAST_CACHE.clear()
+    _PARAM_CAST_CACHE[key] = value
+    return value
 
 
 def _autocast_param(t, dtype):
@@ -44,7 +51,7 @@ def _autocast_param(t, dtype):
         hit = t.detach().to(dtype)
         if t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last):
             hit = hit.contiguous(memory_format=torch.channels_last)
-        _PARAM_CAST_CACHE[key] = hit
+        _cache_put(key, hit)
     return hit
 
 
@@ -56,7 +63,7 @@ def _cat_params(ts):
         hit = torch.cat([t.detach() for t in ts], dim=0)
         if hit.dim() == 4 and ts[0].is_contiguous(memory_format=torch.channels_last) and not ts[0].is_contiguous():
             hit = hit.contiguous(memory_format=torch.channels_last)
-        _PARAM_CAST_CACHE[key] = hit
+        _cache_put(key, hit)
     return hit
 
 
@@ -93,8 +100,7 @@ def _stacked_params(a: nn.Conv2d, b: nn.Conv2d, shared_input: bool):
             w[wa.shape[0]:, wa.shape[1]:] = wb
         if wa.is_contiguous(memory_format=torch.channels_last) and not wa.is_contiguous():
             w = w.contiguous(memory_format=torch.channels_last)
-        hit = (w, torch.cat([a.bias.detach(), b.bias.detach()], dim=0))
-        _PARAM_CAST_CACHE[key] = hit
+        hit = _cache_put(key, (w, torch.cat([a.bias.detach(), b.bias.detach()], dim=0)))
     return hit
 
 
@@ -485,6 +491,7 @@ class RAFT(nn.Module):
             st["outs"] = self._net_body(img_t0, img_t1, occ)
         st["launches"] = int(lib.load().slimb200_launch_count(-1) - n0)  # library kernels inside one replay
         st["graph"] = graph
+        st["keepalive"] = list(_PARAM_CAST_CACHE.values())  # derived weights the captured kernels point at
         self._graphs["net"] = st
         self.n_graph_captures = getattr(self, "n_graph_captures", 0) + 1
 

@@ -111,3 +111,43 @@ def test_cuda_graphed_gru_loop_equals_eager_and_tracks_weight_updates(cuda):
         model.raft_network.use_cuda_graph = False
         e_c = model(s0, s1, None)[0][-1].modified_network_output.static_flow.clone()
         assert torch.equal(g_c, e_c) and not torch.equal(g_c, g_a)
+
+
+def test_graphed_decoder_static_inputs_follow_the_batch(cuda):
+    """The output decoders run as side branches of the CUDA graph on static input buffers (points, pillar coordinates,
+    validity) that are refreshed before every replay: pairs with fewer / more points than the captured capacity, and a
+    switch of the decode mode, give exactly what the eager decoder gives."""
+    cfg = make_cfg("T")
+    model, _ = _model(cfg, cuda)
+    model.POINT_CAPACITY_STEP = 256  # small steps so that the second pair outgrows the captured buffers
+    pairs = [make_sample_dicts(WORKLOADS["T"], [51]), make_sample_dicts(WORKLOADS["T"], [52, 53])[0:2],
+             make_sample_dicts(WORKLOADS["T"], [54])]
+
+    def run(s0, s1):
+        pf, pb = model(s0, s1, None)
+        return [t.clone() for p in (pf[-1], pb[-1], pf[0])
+                for t in (p.static_flow, p.static_aggr_flow, p.modified_network_output.dynamicness)], len(pf)
+
+    with torch.no_grad():
+        for s0, s1 in pairs:
+            model.raft_network.use_cuda_graph = False
+            eager, n_e = run(s0, s1)
+            model.raft_network.use_cuda_graph = True
+            graphed, n_g = run(s0, s1)
+            assert n_e == n_g == 6
+            for a, b in zip(eager, graphed):
+                assert a.shape == b.shape and torch.equal(a, b)
+        assert model.raft_network.n_graph_captures >= 2  # batch size 1 -> 2 -> 1 (and grown point buffers)
+        model.decode_iterations = model.raft_network.output_iterations = "last"
+        s0, s1 = pairs[0]
+        pf, pb = model(s0, s1, None)
+        assert len(pf) == len(pb) == 1
+        assert torch.equal(pf[-1].static_flow, eager_last(model, s0, s1))
+
+
+def eager_last(model, s0, s1):
+    model.raft_network.use_cuda_graph = False
+    try:
+        return model(s0, s1, None)[0][-1].static_flow.clone()
+    finally:
+        model.raft_network.use_cuda_graph = True
