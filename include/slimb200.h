@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SLIMB200_VERSION 102
+#define SLIMB200_VERSION 103
 
 enum {
   SLIMB200_OK = 0,
@@ -141,13 +141,18 @@ int slimb200_preprocess_points(const float* const* scans /*host[batch]*/, const 
  * (corr.py:7-21,48-56) and CorrBlock.__call__ + bilinear_sampler (corr.py:23-46,
  * raft_code/utils.py:15-29).
  *
- * Pyramid storage ("panel" layout, chosen so that every 128 x 128 GEMM tile is one contiguous 32 KB
- * block in HBM -- contiguous blocks store at ~6.3 TB/s on B200, 128-byte pieces of a pitched row at 4.7):
+ * Pyramid storage ("panel" layout, chosen for the two kernels that touch it):
  *   the Ncols = sum_l h_l * w_l columns (all levels side by side, level_offset[l] = sum_{k<l} h_k * w_k,
- *   h_0 = h, w_0 = w, h_{l+1} = h_l / 2 floor) are cut into n_panels = ceil(Ncols / 128) panels of 128;
- *   element (b, source pixel i, column j) lives at
- *       pyramid[((b * n_panels + j / 128) * (h * w) + i) * 128 + j % 128]
- *   Columns >= Ncols of the last panel are zero.  `pitch` = n_panels * 128.
+ *   h_0 = h, w_0 = w, h_{l+1} = h_l / 2 floor) are cut into n_panels = ceil(Ncols / 128) panels of 128, the
+ *   h * w source pixels (rows) into m_tiles = ceil(h * w / 128) tiles of 128 (rows_padded = 128 * m_tiles).
+ *   Every 128 x 128 GEMM tile is two contiguous 16 KB half-tiles (64 columns each) -- contiguous blocks store at
+ *   ~6.3 TB/s on B200, 128-byte pieces of a pitched row at 4.7.  Inside a half-tile FOUR neighbouring source pixels
+ *   x EIGHT consecutive columns form one 64-byte unit: neighbouring pixels look up nearly the same window, so one
+ *   64-byte DRAM burst serves four lanes of the lookup (a pixel-row-major tile spends a burst per pixel and row).
+ *   Element (b, source pixel i, column j), with c = j % 128:
+ *       half-tile  t = ((b * n_panels + j / 128) * m_tiles + i / 128) * 2 + c / 64
+ *       pyramid[t * 8192 + ((i % 128) / 4) * 256 + ((c % 64) / 8) * 32 + (i % 4) * 8 + c % 8]
+ *   Columns >= Ncols of the last panel and rows >= h * w of the last tile are zero.  `pitch` = n_panels * 128.
  * Level l as the reference exposes it (corr_pyramid[l], shape (B*h*w, 1, h_l, w_l)) is columns
  * [level_offset[l], level_offset[l] + h_l * w_l) of every row (liso_b200/slim/corr.py materialises it lazily).
  * ---------------------------------------------------------------------------------------- */
@@ -159,6 +164,7 @@ typedef struct {
   int32_t n_cols;   /* sum h_l * w_l */
   int32_t pitch;    /* n_panels * 128: columns per source pixel including the zero padding */
   int32_t n_panels; /* ceil(n_cols / 128) */
+  int32_t rows_padded; /* 128 * ceil(h * w / 128): source-pixel rows per panel including the zero padding */
 } slimb200_corr_layout;
 
 enum { SLIMB200_DTYPE_F32 = 0, SLIMB200_DTYPE_BF16 = 1 };

@@ -56,6 +56,7 @@ class CorrLayout(C.Structure):
         ("n_cols", C.c_int32),
         ("pitch", C.c_int32),
         ("n_panels", C.c_int32),
+        ("rows_padded", C.c_int32),
     ]
 
 

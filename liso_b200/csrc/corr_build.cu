@@ -329,7 +329,12 @@ k_corr_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
       for (int j = 0; j < BLOCK_N / 32; ++j) {
         if (j + 1 < BLOCK_N / 32) tmem_ld_32x32b_x32(taddr + (uint32_t)((j + 1) * 32), v[(j + 1) & 1]);  // prefetch
-        const uint32_t half = out_buf + (uint32_t)(j >> 1) * OUT_HALF_BYTES + (uint32_t)row * 128u;
+        // half-tile image (include/slimb200.h): [32 groups of 4 rows][8 column blocks][4 rows][8 columns] bf16, i.e.
+        // 16-byte chunk number L = ((row / 4) * 8 + cb) * 4 + row % 4, stored with the 128-byte swizzle TMA expects
+        // (chunk L % 8 of 128-byte line L / 8 goes to position (L % 8) ^ (L / 8 % 8)): a warp's store still spreads
+        // over all 32 banks (8 distinct positions x 4 lines)
+        const uint32_t half = out_buf + (uint32_t)(j >> 1) * OUT_HALF_BYTES;
+        const uint32_t grp4 = (uint32_t)row >> 2, sub = (uint32_t)row & 3u;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t pk[4];
@@ -339,8 +344,9 @@ k_corr_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const float hi = __uint_as_float(v[j & 1][c * 8 + 2 * e + 1]) * shape.scale;
             asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk[e]) : "f"(hi), "f"(lo));
           }
-          const uint32_t chunk = (uint32_t)((j & 1) * 4 + c);
-          const uint32_t dst = half + ((chunk ^ ((uint32_t)row & 7u)) << 4);
+          const uint32_t cb = (uint32_t)((j & 1) * 4 + c);            // 8-column block inside the half
+          const uint32_t line = grp4 * 4u + (cb >> 1);                // 128-byte line of the image
+          const uint32_t dst = half + line * 128u + ((((cb & 1u) * 4u + sub) ^ (line & 7u)) << 4);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
                        "r"(pk[3])
                        : "memory");
@@ -355,9 +361,10 @@ k_corr_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       fence_proxy_async_smem();
       asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(EPI_THREADS) : "memory");
       if (store_thread && m < shape.m_tiles) {
-        // panel layout: tile (m, n) of sample b = rows [128 m, 128 m + 128) of panel b * n_tiles + n: 32 KB contiguous
-        tma_store_3d(&map_c, out_buf, 0, m * BLOCK_M, b * shape.n_tiles + n, policy);
-        tma_store_3d(&map_c, out_buf + OUT_HALF_BYTES, 64, m * BLOCK_M, b * shape.n_tiles + n, policy);
+        // panel layout: tile (m, n) of sample b = two contiguous 16 KB half-tiles
+        const int ht = ((b * shape.n_tiles + n) * shape.m_tiles + m) * 2;
+        tma_store_3d(&map_c, out_buf, 0, 0, ht, policy);
+        tma_store_3d(&map_c, out_buf + OUT_HALF_BYTES, 0, 0, ht + 1, policy);
         tma_store_commit();
       }
     }
@@ -527,6 +534,7 @@ extern "C" int slimb200_corr_layout_init(int32_t batch, int32_t dim, int32_t h, 
   L.n_cols = off;
   L.n_panels = (off + SLIMB200_PANEL_COLS - 1) / SLIMB200_PANEL_COLS;
   L.pitch = L.n_panels * SLIMB200_PANEL_COLS;
+  L.rows_padded = (h * w + BLOCK_M - 1) / BLOCK_M * BLOCK_M;
   *out = L;
   return SLIMB200_OK;
 }
@@ -534,7 +542,7 @@ extern "C" int slimb200_corr_layout_init(int32_t batch, int32_t dim, int32_t h, 
 extern "C" size_t slimb200_corr_pyramid_bytes(const slimb200_corr_layout* L, int32_t store_dtype) {
   if (!L) return 0;
   const size_t es = store_dtype == SLIMB200_DTYPE_BF16 ? 2 : 4;
-  return (size_t)L->batch * L->h * L->w * L->pitch * es;
+  return (size_t)L->batch * L->rows_padded * L->pitch * es;
 }
 
 extern "C" size_t slimb200_corr_workspace_bytes(const slimb200_corr_layout* L) {
@@ -571,9 +579,10 @@ extern "C" int slimb200_corr_build(const float* fmap1, const float* fmap2, int32
   int rc;
   if ((rc = make_map(enc, &map_a, A, DIM, nf, L->batch, DIM)) != SLIMB200_OK) return rc;
   if ((rc = make_map(enc, &map_b, Bx, DIM, L->n_cols, L->batch, DIM)) != SLIMB200_OK) return rc;
-  // output: (batch * n_panels) panels of (nf rows x 128 columns) bf16, rows 256 B apart
-  if ((rc = make_map(enc, &map_c, pyramid, SLIMB200_PANEL_COLS, nf, (uint64_t)L->batch * L->n_panels, SLIMB200_PANEL_COLS)) !=
-      SLIMB200_OK)
+  // output: batch * n_panels * m_tiles * 2 contiguous half-tiles of 128 lines x 128 bytes (include/slimb200.h)
+  const int m_tiles = (nf + BLOCK_M - 1) / BLOCK_M;
+  if (L->rows_padded != m_tiles * BLOCK_M) return SLIMB200_E_INVALID;
+  if ((rc = make_map(enc, &map_c, pyramid, 64, 128, (uint64_t)L->batch * L->n_panels * m_tiles * 2, 64)) != SLIMB200_OK)
     return rc;
 
   if (fmap_layout == SLIMB200_CANVAS_NCHW) {

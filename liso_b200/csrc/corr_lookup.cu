@@ -53,14 +53,18 @@ __device__ __forceinline__ float sample_pos(float c, float inv, int offs, int si
   return ip;
 }
 
+// element (b, source pixel i, column col) of the pyramid (include/slimb200.h): 16 KB half-tiles of 128 rows x 64
+// columns in which 4 neighbouring rows x 8 columns form one 64-byte unit.  `rows` = rows_padded of the layout.
 template <typename T>
-__device__ __forceinline__ size_t panel_index(int n_panels, int nf, int b, int i, int col) {
-  return ((size_t)(b * n_panels + (col / PW)) * nf + i) * PW + (col % PW);
+__device__ __forceinline__ size_t panel_index(int n_panels, int rows, int b, int i, int col) {
+  const int c = col % PW;
+  const size_t half_tile = ((size_t)(b * n_panels + (col / PW)) * (rows >> 7) + (i >> 7)) * 2 + (c >> 6);
+  return half_tile * 8192 + (size_t)(((i & 127) >> 2) * 256 + ((c & 63) >> 3) * 32 + (i & 3) * 8 + (c & 7));
 }
 
 // fully predicated 4-tap sample straight from global memory (rare path)
 template <typename T>
-__device__ __noinline__ float sample_slow(const T* __restrict__ pyr, int n_panels, int nf, int b, int i, int W, int H, int off,
+__device__ __noinline__ float sample_slow(const T* __restrict__ pyr, int n_panels, int rows, int b, int i, int W, int H, int off,
                                           float ix, float iy) {
   const float fx = floorf(ix), fy = floorf(iy);
   const int x0 = (int)fx, y0 = (int)fy;
@@ -69,10 +73,10 @@ __device__ __noinline__ float sample_slow(const T* __restrict__ pyr, int n_panel
   const bool xin0 = (unsigned)x0 < (unsigned)W, xin1 = (unsigned)(x0 + 1) < (unsigned)W;
   const bool yin0 = (unsigned)y0 < (unsigned)H, yin1 = (unsigned)(y0 + 1) < (unsigned)H;
   float val = 0.f;
-  if (yin0 && xin0) val += Elem<T>::ld(pyr + panel_index<T>(n_panels, nf, b, i, off + y0 * W + x0)) * __fmul_rn(ex, ey);
-  if (yin0 && xin1) val += Elem<T>::ld(pyr + panel_index<T>(n_panels, nf, b, i, off + y0 * W + x0 + 1)) * __fmul_rn(dx, ey);
-  if (yin1 && xin0) val += Elem<T>::ld(pyr + panel_index<T>(n_panels, nf, b, i, off + (y0 + 1) * W + x0)) * __fmul_rn(ex, dy);
-  if (yin1 && xin1) val += Elem<T>::ld(pyr + panel_index<T>(n_panels, nf, b, i, off + (y0 + 1) * W + x0 + 1)) * __fmul_rn(dx, dy);
+  if (yin0 && xin0) val += Elem<T>::ld(pyr + panel_index<T>(n_panels, rows, b, i, off + y0 * W + x0)) * __fmul_rn(ex, ey);
+  if (yin0 && xin1) val += Elem<T>::ld(pyr + panel_index<T>(n_panels, rows, b, i, off + y0 * W + x0 + 1)) * __fmul_rn(dx, ey);
+  if (yin1 && xin0) val += Elem<T>::ld(pyr + panel_index<T>(n_panels, rows, b, i, off + (y0 + 1) * W + x0)) * __fmul_rn(ex, dy);
+  if (yin1 && xin1) val += Elem<T>::ld(pyr + panel_index<T>(n_panels, rows, b, i, off + (y0 + 1) * W + x0 + 1)) * __fmul_rn(dx, dy);
   return val;
 }
 
@@ -126,6 +130,7 @@ __global__ void __launch_bounds__(LK_THREADS) k_corr_lookup(const T* __restrict_
   __shared__ int s_lw[SLIMB200_MAX_LEVELS], s_lh[SLIMB200_MAX_LEVELS], s_lo[SLIMB200_MAX_LEVELS];  // no dynamic indexing of L
 
   const int nf = L.h * L.w;
+  const int prow = L.rows_padded;
   const int n_panels = L.n_panels;
   const int b = blockIdx.y;
   const int i0 = blockIdx.x * LK_PIX;
@@ -192,7 +197,7 @@ __global__ void __launch_bounds__(LK_THREADS) k_corr_lookup(const T* __restrict_
       const int col = ca + c * EPC;
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
       if (row_ok && col < hi && col + EPC > lo)  // (implies 0 <= col < n_cols)
-        v = __ldg(reinterpret_cast<const uint4*>(pyr + panel_index<T>(n_panels, nf, b, pix, col)));
+        v = __ldg(reinterpret_cast<const uint4*>(pyr + panel_index<T>(n_panels, prow, b, pix, col)));
       uint32_t* dst = s_raw + ((size_t)(seg * NW + c * 4) * LK_PIX + lane);
       dst[0] = v.x;
       dst[LK_PIX] = v.y;
@@ -230,7 +235,7 @@ __global__ void __launch_bounds__(LK_THREADS) k_corr_lookup(const T* __restrict_
       const float ix = s_pos[((l * 2 + 0) * WIN + i) * LK_PIX + lane];
       for (int j = 0; j < WIN; ++j) {
         const float iy = s_pos[((l * 2 + 1) * WIN + j) * LK_PIX + lane];
-        const float val = live ? sample_slow<T>(pyr, n_panels, nf, b, pix, W, s_lh[l], off, ix, iy) : 0.f;
+        const float val = live ? sample_slow<T>(pyr, n_panels, prow, b, pix, W, s_lh[l], off, ix, iy) : 0.f;
         if (live) dst[(size_t)j * nf] = val;
       }
     }
@@ -336,7 +341,7 @@ __device__ __forceinline__ void v3_columns(const uint32_t (*win)[V3<T>::WPR], co
 // one window row of one pixel: NCHUNK 16-byte loads (predicated on the valid column range), returns the shift that
 // re-aligns the row to window column 0
 template <typename T>
-__device__ __forceinline__ int v3_fetch_row(const T* __restrict__ pyr, int n_panels, int nf, int b, int pix, int off, int W, int H,
+__device__ __forceinline__ int v3_fetch_row(const T* __restrict__ pyr, int n_panels, int rows, int b, int pix, int off, int W, int H,
                                             int xb, int y, int n_elems, bool okp, uint32_t* ld) {
   constexpr int EPC = V3<T>::EPC, NCHUNK = V3<T>::NCHUNK;
   const bool row_ok = okp && (unsigned)y < (unsigned)H;
@@ -349,7 +354,7 @@ __device__ __forceinline__ int v3_fetch_row(const T* __restrict__ pyr, int n_pan
     const int col = ca + c * EPC;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (row_ok && col < hi && col + EPC > lo)  // read once per lookup, 878 MB per 8 samples: streaming (evict-first) loads
-      v = __ldcs(reinterpret_cast<const uint4*>(pyr + panel_index<T>(n_panels, nf, b, pix, col)));
+      v = __ldcs(reinterpret_cast<const uint4*>(pyr + panel_index<T>(n_panels, rows, b, pix, col)));
     ld[c * 4 + 0] = v.x;
     ld[c * 4 + 1] = v.y;
     ld[c * 4 + 2] = v.z;
@@ -400,6 +405,7 @@ __global__ void __launch_bounds__(LK_THREADS, 3) k_corr_lookup_r3(const T* __res
   __shared__ int s_lw[SLIMB200_MAX_LEVELS], s_lh[SLIMB200_MAX_LEVELS], s_lo[SLIMB200_MAX_LEVELS];
 
   const int nf = L.h * L.w;
+  const int prow = L.rows_padded;
   const int n_panels = L.n_panels;
   const int b = blockIdx.y;
   const int i0 = blockIdx.x * LK_PIX;
@@ -470,7 +476,7 @@ __global__ void __launch_bounds__(LK_THREADS, 3) k_corr_lookup_r3(const T* __res
     int sft[4];
 #pragma unroll
     for (int rr = 0; rr < 4; ++rr)
-      sft[rr] = v3_fetch_row<T>(pyr, n_panels, nf, b, pix, off, W, H, xb, yb + half * 4 + rr, n_elems, okp, ld[rr]);
+      sft[rr] = v3_fetch_row<T>(pyr, n_panels, prow, b, pix, off, W, H, xb, yb + half * 4 + rr, n_elems, okp, ld[rr]);
 #pragma unroll
     for (int rr = 0; rr < 4; ++rr) {
       uint32_t al[SWPR];
@@ -481,7 +487,7 @@ __global__ void __launch_bounds__(LK_THREADS, 3) k_corr_lookup_r3(const T* __res
     }
     if (half == 1 && __any_sync(0xffffffffu, mode == 2)) {  // window row 8 for the shifted windows of this warp
       uint32_t al[SWPR];
-      const int sf = v3_fetch_row<T>(pyr, n_panels, nf, b, pix, off, W, H, xb, yb + 8, n_elems, live && mode == 2, ld[0]);
+      const int sf = v3_fetch_row<T>(pyr, n_panels, prow, b, pix, off, W, H, xb, yb + 8, n_elems, live && mode == 2, ld[0]);
       realign<T>(ld[0], sf, al);
       uint32_t* dst = s_win + ((size_t)((l * SROWS + 8) * SWPR) * LK_PIX + lane);
 #pragma unroll
@@ -547,7 +553,7 @@ __global__ void __launch_bounds__(LK_THREADS, 3) k_corr_lookup_r3(const T* __res
         const float ix = s_pos[((l * 2 + 0) * WIN + i) * LK_PIX + lane];
         for (int j = 0; j < WIN; ++j) {
           const float iy = s_pos[((l * 2 + 1) * WIN + j) * LK_PIX + lane];
-          if (live) dst[((size_t)i * WIN + j) * kstride] = sample_slow<T>(pyr, n_panels, nf, b, pix, W, H, off, ix, iy);
+          if (live) dst[((size_t)i * WIN + j) * kstride] = sample_slow<T>(pyr, n_panels, prow, b, pix, W, H, off, ix, iy);
         }
       }
     }
@@ -620,6 +626,7 @@ extern "C" int slimb200_corr_lookup(const void* pyramid, int32_t pyramid_dtype, 
   if (!pyramid || !L || !coords || !out) return SLIMB200_E_INVALID;
   if (radius < 0 || radius > 4 || L->levels < 1 || L->levels > SLIMB200_MAX_LEVELS) return SLIMB200_E_UNSUPPORTED;
   if (L->n_panels * PW != L->pitch || L->n_panels < 1) return SLIMB200_E_INVALID;
+  if (L->rows_padded < L->h * L->w || (L->rows_padded & 127)) return SLIMB200_E_INVALID;
   if (reinterpret_cast<uintptr_t>(pyramid) & 15) return SLIMB200_E_ALIGNMENT;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (pyramid_dtype == SLIMB200_DTYPE_BF16) return dispatch_radius<__nv_bfloat16>(radius, out_layout, pyramid, L, coords, out, stream);

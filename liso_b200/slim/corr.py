@@ -8,7 +8,8 @@ emits the ``(B, L*(2r+1)^2, h, w)`` fp32 tensor directly.
 
 Differences a caller can observe (documented in DESIGN.md):
 * ``corr_pyramid[l]`` has the reference's shape ``(B*h*w, 1, h_l, w_l)`` but is bf16 and is gathered
-  lazily (a copy) out of the panel-tiled buffer the kernels use (``include/slimb200.h``).
+  lazily (a copy) out of the tiled buffer the kernels use (``include/slimb200.h``: 16 KB half-tiles, 4 source pixels
+  x 8 columns per 64-byte unit).
 * values carry bf16 operand + storage rounding: |err| <= 2^-7 * ||f1_i|| * ||f2_j|| / sqrt(D).
 * forward only.
 """
@@ -29,14 +30,23 @@ def make_layout(batch: int, dim: int, h: int, w: int, levels: int) -> _lib.CorrL
     return L
 
 
+def _tile_view(pyramid: torch.Tensor, L: _lib.CorrLayout) -> torch.Tensor:
+    """The packed pyramid as (b, panel, m, half, g, cb, p, e): half-tiles of 128 rows x 64 columns in which 4 neighbouring
+    source pixels (p) x 8 consecutive columns (e) form one unit (``include/slimb200.h``)."""
+    return pyramid.view(L.batch, L.n_panels, L.rows_padded // 128, 2, 32, 8, 4, 8)
+
+
+def unpack_rows(pyramid: torch.Tensor, L: _lib.CorrLayout) -> torch.Tensor:
+    """(B, h*w, n_panels*128) row-major copy of the packed pyramid: row = source pixel, column = pyramid column."""
+    t = _tile_view(pyramid, L).permute(0, 2, 4, 6, 1, 3, 5, 7)  # (b, m, g, p, panel, half, cb, e)
+    return t.reshape(L.batch, L.rows_padded, L.n_panels * _lib.PANEL_COLS)[:, :L.h * L.w]
+
+
 def unpack_level(pyramid: torch.Tensor, L: _lib.CorrLayout, level: int) -> torch.Tensor:
-    """Level ``level`` with the reference's shape (B*h*w, 1, h_l, w_l), gathered out of the panel layout
-    (``include/slimb200.h``: element (b, i, j) at ``((b*n_panels + j//128)*Nf + i)*128 + j%128``)."""
-    nf, P, pw = L.h * L.w, L.n_panels, _lib.PANEL_COLS
+    """Level ``level`` with the reference's shape (B*h*w, 1, h_l, w_l), gathered out of the panel layout."""
+    nf = L.h * L.w
     off, hl, wl = L.level_offset[level], L.level_h[level], L.level_w[level]
-    p0, p1 = off // pw, (off + hl * wl - 1) // pw + 1
-    rows = pyramid.view(L.batch, P, nf, pw)[:, p0:p1].permute(0, 2, 1, 3).reshape(L.batch * nf, (p1 - p0) * pw)
-    return rows[:, off - p0 * pw: off - p0 * pw + hl * wl].reshape(L.batch * nf, 1, hl, wl)
+    return unpack_rows(pyramid, L)[:, :, off:off + hl * wl].reshape(L.batch * nf, 1, hl, wl)
 
 
 class _LazyLevels:
@@ -88,10 +98,11 @@ def lookup(pyramid: torch.Tensor, L: _lib.CorrLayout, coords: torch.Tensor, radi
 def pack_pyramid_f32(levels: List[torch.Tensor], L: _lib.CorrLayout) -> torch.Tensor:
     """Pack reference-shaped fp32 levels (B*h*w,1,h_l,w_l) into the library's panel layout (tests)."""
     nf, P, pw = L.h * L.w, L.n_panels, _lib.PANEL_COLS
-    rows = torch.zeros((L.batch * nf, P * pw), dtype=torch.float32, device=levels[0].device)
+    rows = torch.zeros((L.batch, L.rows_padded, P * pw), dtype=torch.float32, device=levels[0].device)
     for l, lv in enumerate(levels):
-        rows[:, L.level_offset[l]:L.level_offset[l] + L.level_h[l] * L.level_w[l]] = lv.reshape(L.batch * nf, -1)
-    return rows.view(L.batch, nf, P, pw).permute(0, 2, 1, 3).contiguous().view(L.batch * P * nf, pw)
+        rows[:, :nf, L.level_offset[l]:L.level_offset[l] + L.level_h[l] * L.level_w[l]] = lv.reshape(L.batch, nf, -1)
+    t = rows.view(L.batch, L.rows_padded // 128, 32, 4, P, 2, 8, 8)  # (b, m, g, p, panel, half, cb, e)
+    return t.permute(0, 4, 1, 5, 2, 6, 3, 7).contiguous().view(-1, pw)  # (b, panel, m, half, g, cb, p, e)
 
 
 class CorrBlock:
@@ -120,7 +131,7 @@ class CorrBlock:
         if not nhwc:
             f1, f2 = f1.contiguous(), f2.contiguous()
         layout_flag = _lib.CANVAS_NHWC if nhwc else _lib.CANVAS_NCHW
-        shape = (B * L.n_panels * h * w, _lib.PANEL_COLS)
+        shape = (B * L.n_panels * L.rows_padded, _lib.PANEL_COLS)
         if self.pyramid is None:
             self.pyramid = torch.empty(shape, dtype=torch.bfloat16, device=f1.device)
             self._ws = torch.empty(lib.slimb200_corr_workspace_bytes(C.byref(L)), dtype=torch.uint8, device=f1.device)

@@ -26,14 +26,15 @@ def test_header_symbols_are_exported_and_bound():
 
 def test_host_only_entry_points():
     lib = _lib.load()
-    assert lib.slimb200_version() >= 101
+    assert lib.slimb200_version() >= 103
     assert b"workspace" in lib.slimb200_strerror(-3)
     L = _lib.CorrLayout()
     assert lib.slimb200_corr_layout_init(2, 128, 80, 80, 4, ctypes.byref(L)) == 0
-    assert (L.n_cols, L.n_panels, L.pitch) == (6400 + 1600 + 400 + 100, 67, 67 * 128)
+    assert (L.n_cols, L.n_panels, L.pitch, L.rows_padded) == (6400 + 1600 + 400 + 100, 67, 67 * 128, 6400)
     assert list(L.level_offset) == [0, 6400, 8000, 8400]
     assert lib.slimb200_corr_layout_init(1, 128, 115, 115, 4, ctypes.byref(L)) == 0
     assert list(L.level_h) == [115, 57, 28, 14] and L.n_cols == 13225 + 3249 + 784 + 196  # floor pooling
+    assert L.rows_padded == 104 * 128  # 13225 source pixels in 128-row tiles
     assert lib.slimb200_corr_layout_init(1, 64, 80, 80, 4, ctypes.byref(L)) == -2  # D != 128 unsupported
     assert lib.slimb200_corr_pyramid_bytes(ctypes.byref(L), _lib.DTYPE_BF16) > 0
     p = _lib.PillarParams()
