@@ -410,6 +410,17 @@ def main():
         _lib.K_CORR_LOOKUP: dict(bytes=B * 196 * nf * 4 + B * nf * 4 * 8 * 32, flops=0,
                                  what="fp32 lookup written + 8 tap rows x 32 B sectors per level read"),
     }
+    # InstanceNorm glue of the two feature-encoder runs (B frames each): 17 normalised tensors per run -- 5 of 32 ch at
+    # H/2 (stem + layer1), 6 of 64 ch at H/4, 6 of 96 ch at H/8; two per stage also read a residual.  Average per launch.
+    if prof.get(_lib.K_IN_APPLY, (0, 0))[1] == 34 * prof_steps:
+        sizes = [(32 * (H // 2) * (Wd // 2), 5), (64 * (H // 4) * (Wd // 4), 6), (96 * (H // 8) * (Wd // 8), 6)]
+        elems = sum(e * n for e, n in sizes)
+        res_elems = sum(e * 2 for e, _ in sizes)
+        alg[_lib.K_IN_STATS] = dict(bytes=B * 4 * elems // 17, flops=0,
+                                    what="normalised tensor read once (average over the 17 tensors of an encoder run)")
+        alg[_lib.K_IN_APPLY] = dict(bytes=B * 4 * (2 * elems + res_elems) // 17, flops=0,
+                                    what="tensor read + written in place, residual read where the block joins "
+                                         "(average over the 17 tensors of an encoder run)")
     kernels = []
     for kid, (ms_k, n_k) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
         name = lib.slimb200_kernel_name(kid).decode()

@@ -154,6 +154,7 @@ SYMBOLS = {
 N_KERNELS = 32
 K_TILE_ENCODE, K_PILLAR_NHWC, K_FEAT_TRANSPOSE, K_FEAT_PACK, K_CORR_GEMM, K_CORR_LOOKUP = 6, 7, 8, 9, 10, 11
 K_DECODE_BEV, K_DECODE_POINTS, K_DECODE_AGGR, K_RAFT_OUTPUT = 14, 15, 17, 18
+K_IN_STATS, K_IN_FINALIZE, K_IN_APPLY = 24, 25, 26
 CANVAS_NCHW, CANVAS_NHWC = 0, 1
 
 _lib: Optional[C.CDLL] = None

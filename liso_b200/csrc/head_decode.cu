@@ -417,20 +417,27 @@ __device__ __forceinline__ float2 aggr_flow_of_cell(const double* __restrict__ T
   return make_float2((float)fx, (float)fy);
 }
 
-// grid.y < batch * H: one BEV row per blockIdx.y; the remaining blockIdx.y values cover the points
-__global__ void __launch_bounds__(256) k_decode_aggr(const DecodeArgs a, int point_rows) {
-  const int rows = a.p.batch * a.p.H;
-  if ((int)blockIdx.y < rows) {
-    const int c = blockIdx.x * 256 + threadIdx.x;
+// blockIdx.y < row_groups: AGGR_ROWS consecutive BEV rows of one sample per CTA, thread = column (a few fat CTAs instead
+// of one tiny CTA per row: the kernel is a 52 MB streaming write); the remaining blockIdx.y values cover the points
+constexpr int AGGR_THREADS = 128, AGGR_ROWS = 16;
+
+__global__ void __launch_bounds__(AGGR_THREADS) k_decode_aggr(const DecodeArgs a, int row_groups) {
+  if ((int)blockIdx.y < row_groups) {
+    const int c = blockIdx.x * AGGR_THREADS + threadIdx.x;
     if (c >= a.p.W) return;
-    const int r = blockIdx.y % a.p.H, b = blockIdx.y / a.p.H;
-    const size_t i = (size_t)blockIdx.y * a.p.W + c;
-    const float2 f = aggr_flow_of_cell(a.trafo + (size_t)b * 16, a.p, r, c);
-    const bool filled = a.filled[i] != 0;
-    reinterpret_cast<float4*>(a.bev_aggr)[i] = make_float4(f.x, f.y, filled ? f.x : 0.f, filled ? f.y : 0.f);
+    const int groups_per_sample = (a.p.H + AGGR_ROWS - 1) / AGGR_ROWS;
+    const int b = blockIdx.y / groups_per_sample, r0 = (blockIdx.y - b * groups_per_sample) * AGGR_ROWS;
+    const double* T = a.trafo + (size_t)b * 16;
+#pragma unroll 4
+    for (int r = r0; r < min(r0 + AGGR_ROWS, a.p.H); ++r) {
+      const size_t i = ((size_t)b * a.p.H + r) * a.p.W + c;
+      const float2 f = aggr_flow_of_cell(T, a.p, r, c);
+      const bool filled = a.filled[i] != 0;
+      reinterpret_cast<float4*>(a.bev_aggr)[i] = make_float4(f.x, f.y, filled ? f.x : 0.f, filled ? f.y : 0.f);
+    }
   } else {
     const size_t n_pts = (size_t)a.p.batch * a.p.n_points;
-    const size_t pi = ((size_t)(blockIdx.y - rows) * gridDim.x + blockIdx.x) * 256 + threadIdx.x;
+    const size_t pi = ((size_t)(blockIdx.y - row_groups) * gridDim.x + blockIdx.x) * AGGR_THREADS + threadIdx.x;
     if (pi >= n_pts) return;
     const int b = (int)(pi / (size_t)a.p.n_points);
     float2 f = make_float2(0.f, 0.f);
@@ -540,11 +547,12 @@ extern "C" int slimb200_head_decode(const float* net_out, const uint32_t* logit_
       SLIMB200_LAUNCH(SLIMB200_K_KABSCH_MOMENTS, stream, (k_kabsch_moments<<<g, PT_THREADS, 0, stream>>>(a)));
     }
     SLIMB200_LAUNCH(SLIMB200_K_KABSCH, stream, (k_kabsch_finalize<<<p->batch, 64, 0, stream>>>(a)));
-    const unsigned gx = (unsigned)((p->W + 255) / 256);
+    const unsigned gx = (unsigned)((p->W + AGGR_THREADS - 1) / AGGR_THREADS);
     const size_t n_pts = (size_t)p->batch * p->n_points;
-    const int point_rows = (int)((n_pts + (size_t)gx * 256 - 1) / ((size_t)gx * 256));
-    dim3 g(gx, (unsigned)(p->batch * p->H + point_rows));
-    SLIMB200_LAUNCH(SLIMB200_K_DECODE_AGGR, stream, (k_decode_aggr<<<g, 256, 0, stream>>>(a, point_rows)));
+    const int point_rows = (int)((n_pts + (size_t)gx * AGGR_THREADS - 1) / ((size_t)gx * AGGR_THREADS));
+    const int row_groups = p->batch * ((p->H + AGGR_ROWS - 1) / AGGR_ROWS);
+    dim3 g(gx, (unsigned)(row_groups + point_rows));
+    SLIMB200_LAUNCH(SLIMB200_K_DECODE_AGGR, stream, (k_decode_aggr<<<g, AGGR_THREADS, 0, stream>>>(a, row_groups)));
   }
   return SLIMB200_OK;
 }

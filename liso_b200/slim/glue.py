@@ -8,7 +8,7 @@ them as ``(B*h*w, C)`` rows.  No fallback: CPU tensors raise.
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Sequence, Tuple
+from typing import Sequence, Tuple
 
 import torch
 

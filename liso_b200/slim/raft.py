@@ -131,13 +131,6 @@ def _fused_norm_ok(norm: nn.Module, x: torch.Tensor, channels: int = None) -> bo
             and c % 4 == 0 and c <= 256 and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last))
 
 
-def norm_relu(norm: nn.Module, x: torch.Tensor) -> torch.Tensor:
-    """relu(norm(x)) for the norms `_make_norm` builds."""
-    if _fused_norm_ok(norm, x):
-        return instance_norm_nhwc(norm, x, relu=True)
-    return F.relu(norm(x))
-
-
 def conv_norm(conv: nn.Conv2d, norm: nn.Module, x: torch.Tensor, relu: bool, residual: torch.Tensor = None) -> torch.Tensor:
     """[relu](norm(conv(x))), or with ``residual`` the whole tail of a residual block relu(residual + [relu](norm(conv(x))))
     (``extractor.py:57-68``).  In front of an InstanceNorm the convolution's bias is a per-channel constant that the
