@@ -290,6 +290,14 @@ int slimb200_iter_update(const float* dflow_raw, int64_t dflow_batch_stride, int
                          int64_t dlogits_batch_stride, int64_t dlogits_channel_stride, int64_t dlogits_pixel_stride,
                          const float* bias_logits, int32_t n_logits, int32_t batch, int32_t h, int32_t w, float* coords1,
                          float* flow, float* logits, float* stacked, void* stream);
+/* Same update with the k x k output convolution of both heads (stride 1, zero padding k/2) evaluated as ONE 1x1
+ * convolution to k*k "taps" plus the sum of the taps over the window, done here: taps (batch, h, w, k*k*(2 + n_logits))
+ * f32 channels-last, channel = (ky*k + kx)*(2 + n_logits) + c with c = [dflow 0:2 | dlogits], i.e. the 1x1 weight is
+ * W1[(ky*k + kx)*(2 + n_logits) + c][cin] = Wconv[c][cin][ky][kx]; raw[p] = sum_(ky,kx) taps[p + (ky - k/2, kx - k/2)][ky*k + kx]
+ * in fp32, taps outside the map skipped.  (cuDNN's 3x3 convolution to 6 channels takes as long as the one to 256.) */
+int slimb200_iter_update_taps(const float* taps, int32_t ksize, const float* bias_flow, const float* bias_logits,
+                              int32_t n_logits, int32_t batch, int32_t h, int32_t w, float* coords1, float* flow,
+                              float* logits, float* stacked, void* stream);
 int slimb200_add_relu(const float* x, const float* y, float* out, int64_t n, void* stream);
 
 const char* slimb200_strerror(int code);

@@ -143,6 +143,11 @@ SYMBOLS = {
         [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
          C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     ),
+    "slimb200_iter_update_taps": (
+        C.c_int,
+        [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+         C.c_void_p, C.c_void_p, C.c_void_p],
+    ),
     "slimb200_add_relu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "slimb200_strerror": (C.c_char_p, [C.c_int]),
     "slimb200_version": (C.c_int, []),

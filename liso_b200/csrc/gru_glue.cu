@@ -130,6 +130,8 @@ struct IterArgs {
   float* flow;     // (batch, 2, h, w) planar
   float* logits;   // (batch, nl, h, w) planar
   float* stacked;  // optional (batch, 2 + nl, h, w) planar copy [flow | logits]
+  const float* taps;  // alternative source of the raw head outputs (see slimb200_iter_update_taps), else NULL
+  int ksize;
   int batch, h, w, nl;
   long long bs_f, cs_f, ps_f, bs_l, cs_l, ps_l;
 };
@@ -140,9 +142,35 @@ __global__ void __launch_bounds__(GL_THREADS) k_iter_update(const IterArgs a) {
   for (long long i = (long long)blockIdx.x * GL_THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * GL_THREADS) {
     const int b = (int)(i / hw), pix = (int)(i - (long long)b * hw);
     const int row = pix / a.w, col = pix - row * a.w;
+    float raw[2 + 16];
+    if (a.taps) {
+      // the k x k output convolution of both heads as ONE 1x1 convolution to (k*k taps) x (2 + nl) channels + this sum
+      // of the taps over the window (zero padding): out[p] = sum_t taps[p + offset(t)][t]
+      const int nc = 2 + a.nl, pad = a.ksize >> 1;
+#pragma unroll
+      for (int c = 0; c < 2 + 16; ++c) raw[c] = 0.f;
+      for (int ky = 0; ky < a.ksize; ++ky) {
+        const int r = row + ky - pad;
+        if ((unsigned)r >= (unsigned)a.h) continue;
+        for (int kx = 0; kx < a.ksize; ++kx) {
+          const int cc = col + kx - pad;
+          if ((unsigned)cc >= (unsigned)a.w) continue;
+          const float* src = a.taps + (((size_t)b * hw + (size_t)r * a.w + cc) * (a.ksize * a.ksize) + (ky * a.ksize + kx)) * nc;
+#pragma unroll
+          for (int c = 0; c < 2 + 16; ++c)
+            if (c < nc) raw[c] = __fadd_rn(raw[c], __ldg(src + c));
+        }
+      }
+    } else {
+      raw[0] = __ldg(a.dflow + b * a.bs_f + pix * a.ps_f);
+      raw[1] = __ldg(a.dflow + b * a.bs_f + a.cs_f + pix * a.ps_f);
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        if (c < a.nl) raw[2 + c] = __ldg(a.dlogits + b * a.bs_l + c * a.cs_l + pix * a.ps_l);
+    }
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-      const float d = __fadd_rn(__ldg(a.dflow + b * a.bs_f + c * a.cs_f + pix * a.ps_f), __ldg(a.bias_f + c));
+      const float d = __fadd_rn(raw[c], __ldg(a.bias_f + c));
       float* cp = a.coords1 + ((size_t)b * 2 + c) * hw + pix;
       const float nc = __fadd_rn(*cp, d);
       *cp = nc;
@@ -150,8 +178,10 @@ __global__ void __launch_bounds__(GL_THREADS) k_iter_update(const IterArgs a) {
       a.flow[((size_t)b * 2 + c) * hw + pix] = fl;
       if (a.stacked) a.stacked[((size_t)b * (2 + a.nl) + c) * hw + pix] = fl;
     }
-    for (int c = 0; c < a.nl; ++c) {
-      const float d = __fadd_rn(__ldg(a.dlogits + b * a.bs_l + c * a.cs_l + pix * a.ps_l), __ldg(a.bias_l + c));
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      if (c >= a.nl) break;
+      const float d = __fadd_rn(raw[2 + c], __ldg(a.bias_l + c));
       float* lp = a.logits + ((size_t)b * a.nl + c) * hw + pix;
       const float nv = __fadd_rn(*lp, d);
       *lp = nv;
@@ -273,6 +303,30 @@ extern "C" int slimb200_iter_update(const float* dflow_raw, int64_t dflow_batch_
   a.ps_f = dflow_pixel_stride;
   a.cs_l = dlogits_channel_stride;
   a.ps_l = dlogits_pixel_stride;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SLIMB200_LAUNCH(SLIMB200_K_ITER_UPDATE, stream,
+                  (k_iter_update<<<grid_for((size_t)batch * h * w), GL_THREADS, 0, stream>>>(a)));
+  return SLIMB200_OK;
+}
+
+extern "C" int slimb200_iter_update_taps(const float* taps, int32_t ksize, const float* bias_flow, const float* bias_logits,
+                                         int32_t n_logits, int32_t batch, int32_t h, int32_t w, float* coords1, float* flow,
+                                         float* logits, float* stacked, void* stream_) {
+  if (!taps || !bias_flow || !bias_logits || !coords1 || !flow || !logits) return SLIMB200_E_INVALID;
+  if (batch < 1 || h < 1 || w < 1 || n_logits < 1 || n_logits > 16 || ksize < 1 || !(ksize & 1) || ksize > 7) return SLIMB200_E_INVALID;
+  IterArgs a{};
+  a.taps = taps;
+  a.ksize = ksize;
+  a.bias_f = bias_flow;
+  a.bias_l = bias_logits;
+  a.coords1 = coords1;
+  a.flow = flow;
+  a.logits = logits;
+  a.stacked = stacked;
+  a.batch = batch;
+  a.h = h;
+  a.w = w;
+  a.nl = n_logits;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SLIMB200_LAUNCH(SLIMB200_K_ITER_UPDATE, stream,
                   (k_iter_update<<<grid_for((size_t)batch * h * w), GL_THREADS, 0, stream>>>(a)));

@@ -142,6 +142,24 @@ def iter_update(dflow_raw: torch.Tensor, bias_flow: torch.Tensor, dlogits_raw: t
                                                 stacked.data_ptr() if stacked is not None else None, _lib.current_stream_ptr()))
 
 
+def iter_update_taps(taps: torch.Tensor, ksize: int, bias_flow: torch.Tensor, bias_logits: torch.Tensor, coords1: torch.Tensor,
+                     flow: torch.Tensor, logits: torch.Tensor, stacked: torch.Tensor = None) -> None:
+    """`iter_update` with the heads' k x k output convolution given as the 1x1 "tap" tensor (B, k*k*(2 + n_logits), h, w),
+    channel = tap * (2 + n_logits) + c: the window sum of the taps is taken inside the kernel."""
+    B, _, h, w = coords1.shape
+    for t in (coords1, flow, logits) + ((stacked,) if stacked is not None else ()):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise ValueError("iter_update_taps: coords1 / flow / logits / stacked must be contiguous fp32 CUDA tensors")
+    nl = logits.shape[1]
+    taps = as_nhwc(taps)
+    if tuple(taps.shape) != (B, ksize * ksize * (2 + nl), h, w) or tuple(flow.shape) != (B, 2, h, w):
+        raise ValueError("iter_update_taps: shape mismatch")
+    _lib.check(_lib.load().slimb200_iter_update_taps(taps.data_ptr(), ksize, bias_flow.data_ptr(), bias_logits.data_ptr(), nl, B,
+                                                     h, w, coords1.data_ptr(), flow.data_ptr(), logits.data_ptr(),
+                                                     stacked.data_ptr() if stacked is not None else None,
+                                                     _lib.current_stream_ptr()))
+
+
 def add_relu(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     """``relu(x + y)`` for two fp32 CUDA tensors of the same shape and memory layout (``extractor.py:57-68``)."""
     _lib.require_cuda(x, y)

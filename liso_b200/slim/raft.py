@@ -351,6 +351,7 @@ class RAFT(nn.Module):
         # ... and its pairs of parallel convolutions (flow / logits branches of the motion encoder, the two heads) stacked
         # into one cuDNN launch each
         self.merge_parallel_convs = True
+        self.tap_heads = True  # ... and the heads' 3x3 output convolution as a 1x1 convolution to taps + window sum
         # forward and backward direction as two parallel branches of the CUDA graph
         self.concurrent_directions = True
         # consumer of the per-iteration network outputs, e.g. SLIM's output decoder: called as
@@ -393,7 +394,7 @@ class RAFT(nn.Module):
         B = len(pcl_t0)
         wsig = tuple((p.data_ptr(), p._version) for mod in (self.fnet, self.cnet, self.update_block) for p in mod.parameters())
         key = (B, self.output_iterations, self.pp_layer.canvas_memory_format, str(dev), torch.backends.cudnn.allow_tf32,
-               self.fused_update_block, self.merge_parallel_convs, self.concurrent_directions, FAST_STOCK_OPS,
+               self.fused_update_block, self.merge_parallel_convs, self.tap_heads, self.concurrent_directions, FAST_STOCK_OPS,
                self.output_sink is not None, self.graph_extra_key, wsig)
         st = self._graphs.get("net")
         if st is not None and st["key"] != key:
@@ -572,6 +573,16 @@ class RAFT(nn.Module):
             w_h2, _ = _stacked_params(fh.conv2, lh.conv2, shared_input=False)
             stacked = torch.zeros((batch, 2 + logits.shape[1], h, w), dtype=torch.float32, device=device)  # [flow | logits]
             n_f = me.conv_flow2.out_channels
+            # the k x k output convolution of the heads (6 channels: as slow in cuDNN as one to 256) as a 1x1 convolution
+            # to k*k taps x 6 channels; the window sum of the taps is part of the update kernel
+            k = fh.conv2.kernel_size[0]
+            w_taps = None
+            if (self.tap_heads and fh.conv2.kernel_size == (k, k) and fh.conv2.stride == (1, 1) and fh.conv2.dilation == (1, 1)
+                    and fh.conv2.padding == (k // 2, k // 2) and k % 2 == 1 and k <= 7):
+                key = ("taps", w_h2.data_ptr(), fh.conv2.weight._version, lh.conv2.weight._version)
+                w_taps = _PARAM_CAST_CACHE.get(key)
+                if w_taps is None:  # W1[(ky*k + kx)*6 + c][cin] = W[c][cin][ky][kx]
+                    w_taps = _cache_put(key, w_h2.permute(2, 3, 0, 1).reshape(k * k * w_h2.shape[0], w_h2.shape[1], 1, 1).contiguous())
         outs = []
         for it in range(m.num_iters):
             corr = correlation(coords1)
@@ -587,7 +598,10 @@ class RAFT(nn.Module):
             g.nhwc_pack_into([out, lg, f], [(hx, Ch + Cx), (rhx, Ch + Cx)])  # x = [inp | out | logits | flow]
             z = g.gru_gate_zr(F.conv2d(hx, w_zr, None, gru.convz.stride, gru.convz.padding), b_zr, hx, rhx, Ch)
             net = g.gru_gate_out(raw(gru.convq, rhx), gru.convq.bias, z, hx, Ch)
-            if merge:
+            if merge and w_taps is not None:
+                g.iter_update_taps(F.conv2d(conv_relu(fh.conv1, net, w_h1, b_h1), w_taps), k, fh.conv2.bias, lh.conv2.bias,
+                                   coords1, flow, logits, stacked)
+            elif merge:
                 d = F.conv2d(conv_relu(fh.conv1, net, w_h1, b_h1), w_h2, None, fh.conv2.stride, fh.conv2.padding)
                 g.iter_update(d[:, :2], fh.conv2.bias, d[:, 2:], lh.conv2.bias, coords1, flow, logits, stacked)
             else:

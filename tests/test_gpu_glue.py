@@ -94,6 +94,16 @@ def test_iter_update_equals_stock_ops(cuda, B, h, w, fmt):
     G.iter_update(d6[:, :2], bf, d6[:, 2:], bl, coords1, flow, logits, stacked)
     assert torch.equal(coords1, c2_ref) and torch.equal(logits, l2_ref) and torch.equal(flow, c2_ref - coords0)
     assert torch.equal(stacked, torch.cat([flow, logits], dim=1))
+    # the heads' 3x3 output convolution given as 1x1 "taps": window sum inside the kernel == F.conv2d (summation order aside)
+    x = torch.randn(B, 32, h, w, generator=g).to(cuda)
+    w6 = (0.1 * torch.randn(6, 32, 3, 3, generator=g)).to(cuda)
+    ref6 = F.conv2d(x, w6, None, padding=1)
+    taps = F.conv2d(x, w6.permute(2, 3, 0, 1).reshape(54, 32, 1, 1).contiguous()).contiguous(memory_format=mf)
+    c3_ref = coords1 + (ref6[:, :2] + bf[None, :, None, None])
+    l3_ref = logits + (ref6[:, 2:] + bl[None, :, None, None])
+    G.iter_update_taps(taps, 3, bf, bl, coords1, flow, logits, stacked)
+    assert torch.allclose(coords1, c3_ref, rtol=0, atol=2e-5) and torch.allclose(logits, l3_ref, rtol=0, atol=2e-5)
+    assert torch.equal(flow, coords1 - coords0) and torch.equal(stacked, torch.cat([flow, logits], dim=1))
 
 
 @pytest.mark.parametrize("B,C,H,W", [(2, 32, 40, 56), (3, 96, 17, 23), (8, 32, 320, 320)])
@@ -130,9 +140,11 @@ def test_fused_update_block_equals_stock_loop(cuda):
     p1 = [p.to(cuda) for p in s1["pcl_full_no_ground_ta"]]
     with torch.no_grad():
         fused = [o.clone() for o in net(p0, p1)[0]]
+        net.tap_heads = False
+        untapped = [o.clone() for o in net(p0, p1)[0]]
         net.merge_parallel_convs = False
         unmerged = [o.clone() for o in net(p0, p1)[0]]
-        net.merge_parallel_convs = True
+        net.merge_parallel_convs = net.tap_heads = True
         net.fused_update_block = False
         stock_loop = [o.clone() for o in net(p0, p1)[0]]
         R.FAST_STOCK_OPS = False
@@ -142,6 +154,8 @@ def test_fused_update_block_equals_stock_loop(cuda):
             R.FAST_STOCK_OPS = True
             net.fused_update_block = True
     assert len(fused) == len(stock_loop) == len(stock) == 6
+    for a, t in zip(fused, untapped):  # 1x1 taps + window sum vs the 3x3 convolution: another summation order
+        assert float((a - t).abs().max()) <= 2e-4, float((a - t).abs().max())
     for a, u, b, c in zip(fused, unmerged, stock_loop, stock):
         assert a.shape == b.shape == c.shape == u.shape
         # stacked parallel convolutions: same products, possibly another summation order inside cuDNN
