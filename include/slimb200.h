@@ -276,7 +276,8 @@ int slimb200_instnorm_nhwc(const float* x, const float* gamma, const float* beta
  *   channel slices of one stacked head output work too);
  *   coords1 (batch,2,h,w) += dflow + bias; logits (batch,n_logits,h,w) += dlogits + bias; flow = coords1 - coords_grid
  *   (channel 0 = column, channel 1 = row: raft_code/utils.py:32-37); coords1 / flow / logits are NCHW contiguous;
- *   stacked (optional) receives the NCHW concatenation [flow | logits] (batch, 2 + n_logits, h, w).
+ *   stacked (optional) receives the NCHW concatenation [flow | logits] in the first 2 + n_logits channels of a
+ *   (batch, stacked_channels, h, w) buffer; further (padding) channels are left untouched.
  * add_relu: out = relu(x + y) over n floats (residual join of extractor.py:57-68; out may alias x or y). */
 int slimb200_nhwc_pack(const float* const* src, const int32_t* src_channels, const int32_t* src_pitch, int32_t n_src,
                        float* const* dst, const int32_t* dst_channel_offset, const int32_t* dst_pitch, int32_t n_dst,
@@ -289,7 +290,7 @@ int slimb200_iter_update(const float* dflow_raw, int64_t dflow_batch_stride, int
                          int64_t dflow_pixel_stride, const float* bias_flow, const float* dlogits_raw,
                          int64_t dlogits_batch_stride, int64_t dlogits_channel_stride, int64_t dlogits_pixel_stride,
                          const float* bias_logits, int32_t n_logits, int32_t batch, int32_t h, int32_t w, float* coords1,
-                         float* flow, float* logits, float* stacked, void* stream);
+                         float* flow, float* logits, float* stacked, int32_t stacked_channels, void* stream);
 /* Same update with the k x k output convolution of both heads (stride 1, zero padding k/2) evaluated as ONE 1x1
  * convolution to k*k "taps" plus the sum of the taps over the window, done here: taps (batch, h, w, k*k*(2 + n_logits))
  * f32 channels-last, channel = (ky*k + kx)*(2 + n_logits) + c with c = [dflow 0:2 | dlogits], i.e. the 1x1 weight is
@@ -297,7 +298,7 @@ int slimb200_iter_update(const float* dflow_raw, int64_t dflow_batch_stride, int
  * in fp32, taps outside the map skipped.  (cuDNN's 3x3 convolution to 6 channels takes as long as the one to 256.) */
 int slimb200_iter_update_taps(const float* taps, int32_t ksize, const float* bias_flow, const float* bias_logits,
                               int32_t n_logits, int32_t batch, int32_t h, int32_t w, float* coords1, float* flow,
-                              float* logits, float* stacked, void* stream);
+                              float* logits, float* stacked, int32_t stacked_channels, void* stream);
 int slimb200_add_relu(const float* x, const float* y, float* out, int64_t n, void* stream);
 
 const char* slimb200_strerror(int code);

@@ -141,12 +141,12 @@ SYMBOLS = {
     "slimb200_iter_update": (
         C.c_int,
         [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
-         C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+         C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p],
     ),
     "slimb200_iter_update_taps": (
         C.c_int,
         [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
-         C.c_void_p, C.c_void_p, C.c_void_p],
+         C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p],
     ),
     "slimb200_add_relu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "slimb200_strerror": (C.c_char_p, [C.c_int]),

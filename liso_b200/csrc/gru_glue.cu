@@ -129,7 +129,8 @@ struct IterArgs {
   float* coords1;  // (batch, 2, h, w) planar
   float* flow;     // (batch, 2, h, w) planar
   float* logits;   // (batch, nl, h, w) planar
-  float* stacked;  // optional (batch, 2 + nl, h, w) planar copy [flow | logits]
+  float* stacked;  // optional (batch, stacked_ch >= 2 + nl, h, w) planar copy [flow | logits | untouched padding channels]
+  int stacked_ch;
   const float* taps;  // alternative source of the raw head outputs (see slimb200_iter_update_taps), else NULL
   int ksize;
   int batch, h, w, nl;
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(GL_THREADS) k_iter_update(const IterArgs a) {
       *cp = nc;
       const float fl = __fsub_rn(nc, (float)(c == 0 ? col : row));  // coords0: ch0 = x, ch1 = y
       a.flow[((size_t)b * 2 + c) * hw + pix] = fl;
-      if (a.stacked) a.stacked[((size_t)b * (2 + a.nl) + c) * hw + pix] = fl;
+      if (a.stacked) a.stacked[((size_t)b * a.stacked_ch + c) * hw + pix] = fl;
     }
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(GL_THREADS) k_iter_update(const IterArgs a) {
       float* lp = a.logits + ((size_t)b * a.nl + c) * hw + pix;
       const float nv = __fadd_rn(*lp, d);
       *lp = nv;
-      if (a.stacked) a.stacked[((size_t)b * (2 + a.nl) + 2 + c) * hw + pix] = nv;
+      if (a.stacked) a.stacked[((size_t)b * a.stacked_ch + 2 + c) * hw + pix] = nv;
     }
   }
 }
@@ -281,8 +282,10 @@ extern "C" int slimb200_iter_update(const float* dflow_raw, int64_t dflow_batch_
                                     int64_t dflow_pixel_stride, const float* bias_flow, const float* dlogits_raw,
                                     int64_t dlogits_batch_stride, int64_t dlogits_channel_stride, int64_t dlogits_pixel_stride,
                                     const float* bias_logits, int32_t n_logits, int32_t batch, int32_t h, int32_t w,
-                                    float* coords1, float* flow, float* logits, float* stacked, void* stream_) {
+                                    float* coords1, float* flow, float* logits, float* stacked, int32_t stacked_channels,
+                                    void* stream_) {
   if (!dflow_raw || !bias_flow || !dlogits_raw || !bias_logits || !coords1 || !flow || !logits) return SLIMB200_E_INVALID;
+  if (stacked && stacked_channels < 2 + n_logits) return SLIMB200_E_INVALID;
   if (batch < 1 || h < 1 || w < 1 || n_logits < 1 || n_logits > 16) return SLIMB200_E_INVALID;
   IterArgs a{};
   a.dflow = dflow_raw;
@@ -293,6 +296,7 @@ extern "C" int slimb200_iter_update(const float* dflow_raw, int64_t dflow_batch_
   a.flow = flow;
   a.logits = logits;
   a.stacked = stacked;
+  a.stacked_ch = stacked_channels;
   a.bs_f = dflow_batch_stride;
   a.bs_l = dlogits_batch_stride;
   a.batch = batch;
@@ -311,8 +315,9 @@ extern "C" int slimb200_iter_update(const float* dflow_raw, int64_t dflow_batch_
 
 extern "C" int slimb200_iter_update_taps(const float* taps, int32_t ksize, const float* bias_flow, const float* bias_logits,
                                          int32_t n_logits, int32_t batch, int32_t h, int32_t w, float* coords1, float* flow,
-                                         float* logits, float* stacked, void* stream_) {
+                                         float* logits, float* stacked, int32_t stacked_channels, void* stream_) {
   if (!taps || !bias_flow || !bias_logits || !coords1 || !flow || !logits) return SLIMB200_E_INVALID;
+  if (stacked && stacked_channels < 2 + n_logits) return SLIMB200_E_INVALID;
   if (batch < 1 || h < 1 || w < 1 || n_logits < 1 || n_logits > 16 || ksize < 1 || !(ksize & 1) || ksize > 7) return SLIMB200_E_INVALID;
   IterArgs a{};
   a.taps = taps;
@@ -323,6 +328,7 @@ extern "C" int slimb200_iter_update_taps(const float* taps, int32_t ksize, const
   a.flow = flow;
   a.logits = logits;
   a.stacked = stacked;
+  a.stacked_ch = stacked_channels;
   a.batch = batch;
   a.h = h;
   a.w = w;

@@ -132,14 +132,15 @@ def iter_update(dflow_raw: torch.Tensor, bias_flow: torch.Tensor, dlogits_raw: t
             raise ValueError("iter_update: coords1 / flow / logits / stacked must be contiguous fp32 CUDA tensors")
     if tuple(dflow_raw.shape) != (B, 2, h, w) or tuple(dlogits_raw.shape) != tuple(logits.shape) or tuple(flow.shape) != (B, 2, h, w):
         raise ValueError("iter_update: shape mismatch")
-    if stacked is not None and tuple(stacked.shape) != (B, 2 + logits.shape[1], h, w):
-        raise ValueError("iter_update: stacked must be (B, 2 + n_logits, h, w)")
+    if stacked is not None and (stacked.shape[1] < 2 + logits.shape[1] or (stacked.shape[0], stacked.shape[2], stacked.shape[3]) != (B, h, w)):
+        raise ValueError("iter_update: stacked must be (B, >= 2 + n_logits, h, w)")
     df, bs_f, cs_f, ps_f = _head_strides(dflow_raw)
     dl, bs_l, cs_l, ps_l = _head_strides(dlogits_raw)
     _lib.check(_lib.load().slimb200_iter_update(df.data_ptr(), bs_f, cs_f, ps_f, bias_flow.data_ptr(), dl.data_ptr(), bs_l, cs_l,
                                                 ps_l, bias_logits.data_ptr(), logits.shape[1], B, h, w, coords1.data_ptr(),
                                                 flow.data_ptr(), logits.data_ptr(),
-                                                stacked.data_ptr() if stacked is not None else None, _lib.current_stream_ptr()))
+                                                stacked.data_ptr() if stacked is not None else None,
+                                                stacked.shape[1] if stacked is not None else 0, _lib.current_stream_ptr()))
 
 
 def iter_update_taps(taps: torch.Tensor, ksize: int, bias_flow: torch.Tensor, bias_logits: torch.Tensor, coords1: torch.Tensor,
@@ -152,12 +153,13 @@ def iter_update_taps(taps: torch.Tensor, ksize: int, bias_flow: torch.Tensor, bi
             raise ValueError("iter_update_taps: coords1 / flow / logits / stacked must be contiguous fp32 CUDA tensors")
     nl = logits.shape[1]
     taps = as_nhwc(taps)
-    if tuple(taps.shape) != (B, ksize * ksize * (2 + nl), h, w) or tuple(flow.shape) != (B, 2, h, w):
+    if tuple(taps.shape) != (B, ksize * ksize * (2 + nl), h, w) or tuple(flow.shape) != (B, 2, h, w) or (
+            stacked is not None and (stacked.shape[1] < 2 + nl or (stacked.shape[0], stacked.shape[2], stacked.shape[3]) != (B, h, w))):
         raise ValueError("iter_update_taps: shape mismatch")
     _lib.check(_lib.load().slimb200_iter_update_taps(taps.data_ptr(), ksize, bias_flow.data_ptr(), bias_logits.data_ptr(), nl, B,
                                                      h, w, coords1.data_ptr(), flow.data_ptr(), logits.data_ptr(),
                                                      stacked.data_ptr() if stacked is not None else None,
-                                                     _lib.current_stream_ptr()))
+                                                     stacked.shape[1] if stacked is not None else 0, _lib.current_stream_ptr()))
 
 
 def add_relu(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:

@@ -84,20 +84,21 @@ def _same_geometry(a: nn.Conv2d, b: nn.Conv2d) -> bool:
             and a.groups == b.groups == 1 and a.padding_mode == b.padding_mode == "zeros")
 
 
-def _stacked_params(a: nn.Conv2d, b: nn.Conv2d, shared_input: bool):
+def _stacked_params(a: nn.Conv2d, b: nn.Conv2d, shared_input: bool, pad_in_to: int = 0):
     """Weight / bias of ONE convolution that evaluates the parallel convolutions ``a`` and ``b`` (same geometry): outputs
     stacked [a | b]; with ``shared_input`` both read the same tensor, otherwise the input is the channel concatenation
-    [in_a | in_b] and the weight is block-diagonal (the zero blocks add exact zeros).  Cached like `_cat_params`."""
-    key = ("stacked", shared_input) + tuple((t.data_ptr(), t._version) for t in (a.weight, a.bias, b.weight, b.bias))
+    [in_a | in_b] (zero-padded to ``pad_in_to`` channels) and the weight is block-diagonal (the zero blocks add exact
+    zeros).  Cached like `_cat_params`."""
+    key = ("stacked", shared_input, pad_in_to) + tuple((t.data_ptr(), t._version) for t in (a.weight, a.bias, b.weight, b.bias))
     hit = _PARAM_CAST_CACHE.get(key)
     if hit is None:
         wa, wb = a.weight.detach(), b.weight.detach()
         if shared_input:
             w = torch.cat([wa, wb], dim=0)
         else:
-            w = wa.new_zeros((wa.shape[0] + wb.shape[0], wa.shape[1] + wb.shape[1]) + tuple(wa.shape[2:]))
+            w = wa.new_zeros((wa.shape[0] + wb.shape[0], max(wa.shape[1] + wb.shape[1], pad_in_to)) + tuple(wa.shape[2:]))
             w[:wa.shape[0], :wa.shape[1]] = wa
-            w[wa.shape[0]:, wa.shape[1]:] = wb
+            w[wa.shape[0]:, wa.shape[1]:wa.shape[1] + wb.shape[1]] = wb
         if wa.is_contiguous(memory_format=torch.channels_last) and not wa.is_contiguous():
             w = w.contiguous(memory_format=torch.channels_last)
         hit = _cache_put(key, (w, torch.cat([a.bias.detach(), b.bias.detach()], dim=0)))
@@ -567,11 +568,13 @@ class RAFT(nn.Module):
                  and _same_geometry(fh.conv2, lh.conv2) and me.conv_flow2.out_channels % 4 == 0
                  and me.conv_class2.out_channels % 4 == 0)
         if merge:
-            w_m1, b_m1 = _stacked_params(me.conv_flow1, me.conv_class1, shared_input=False)
+            # ([flow | logits] is padded from 6 to 8 channels: a tensor-core friendly width whatever cuDNN's autotuner sees)
+            n_st = (2 + logits.shape[1] + 7) // 8 * 8
+            w_m1, b_m1 = _stacked_params(me.conv_flow1, me.conv_class1, shared_input=False, pad_in_to=n_st)
             w_m2, b_m2 = _stacked_params(me.conv_flow2, me.conv_class2, shared_input=False)
             w_h1, b_h1 = _stacked_params(fh.conv1, lh.conv1, shared_input=True)
             w_h2, _ = _stacked_params(fh.conv2, lh.conv2, shared_input=False)
-            stacked = torch.zeros((batch, 2 + logits.shape[1], h, w), dtype=torch.float32, device=device)  # [flow | logits]
+            stacked = torch.zeros((batch, n_st, h, w), dtype=torch.float32, device=device)  # [flow | logits | 0]
             n_f = me.conv_flow2.out_channels
             # the k x k output convolution of the heads (6 channels: as slow in cuDNN as one to 256) as a 1x1 convolution
             # to k*k taps x 6 channels; the window sum of the taps is part of the update kernel

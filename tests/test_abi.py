@@ -70,3 +70,33 @@ def test_cpu_tensors_are_rejected():
         m([torch.zeros(10, 4)])
     with pytest.raises(RuntimeError, match="no CPU fallback"), torch.no_grad():
         CorrBlock(torch.zeros(1, 128, 8, 8), torch.zeros(1, 128, 8, 8))
+
+
+def test_glue_kernels_reject_cpu_tensors_and_bad_arguments():
+    """SURVEY 8f.2 glue: same rule -- CPU tensors raise; the C entry points validate their arguments without a GPU."""
+    import pytest
+    import torch
+
+    from liso_b200.slim import glue as G
+
+    x = torch.zeros(1, 8, 4, 4).contiguous(memory_format=torch.channels_last)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        G.nhwc_cat([x, x])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        G.add_relu(x, x)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        G.gru_gate_zr(x, torch.zeros(8), x, x, 4)
+    lib = _lib.load()
+    buf = (ctypes.c_float * 64)()
+    ptr = ctypes.cast(buf, ctypes.c_void_p)
+    one = (ctypes.c_void_p * 1)(ptr)
+    # channel counts / offsets / pitches must be multiples of 4 (float4 rows); a slot must fit its destination
+    assert lib.slimb200_nhwc_pack(one, (ctypes.c_int32 * 1)(6), None, 1, one, (ctypes.c_int32 * 1)(0), (ctypes.c_int32 * 1)(8), 1, 1, None) == -2
+    assert lib.slimb200_nhwc_pack(one, (ctypes.c_int32 * 1)(8), None, 1, one, (ctypes.c_int32 * 1)(4), (ctypes.c_int32 * 1)(8), 1, 1, None) == -1
+    assert lib.slimb200_nhwc_pack(one, (ctypes.c_int32 * 1)(8), None, 5, one, (ctypes.c_int32 * 1)(0), (ctypes.c_int32 * 1)(8), 1, 1, None) == -2
+    assert lib.slimb200_gru_gate_zr(ptr, ptr, ptr, 8, ptr, ptr, 8, 6, 1, None) == -2
+    assert lib.slimb200_gru_gate_out(None, ptr, ptr, ptr, 8, ptr, 8, 1, None) == -1
+    assert lib.slimb200_add_relu(ptr, ptr, ptr, 6, None) == -2
+    assert lib.slimb200_iter_update_taps(ptr, 2, ptr, ptr, 4, 1, 4, 4, ptr, ptr, ptr, None, 0, None) == -1  # even window
+    assert lib.slimb200_add_relu(ptr, ptr, ptr, 0, None) == 0 and lib.slimb200_nhwc_pack(
+        one, (ctypes.c_int32 * 1)(8), None, 1, one, (ctypes.c_int32 * 1)(0), (ctypes.c_int32 * 1)(8), 1, 0, None) == 0  # empty: no launch

@@ -88,12 +88,12 @@ def test_iter_update_equals_stock_ops(cuda, B, h, w, fmt):
     assert torch.equal(coords1, c_ref) and torch.equal(logits, l_ref) and torch.equal(flow, c_ref - coords0)
     # both head outputs as channel slices of ONE stacked tensor, plus the stacked [flow | logits] copy
     d6 = torch.cat([df, dl], dim=1).contiguous(memory_format=mf)
-    stacked = torch.full((B, 6, h, w), float("nan"), device=cuda)
+    stacked = torch.full((B, 8, h, w), float("nan"), device=cuda)  # 2 padding channels stay untouched
     c2_ref = c_ref + (df + bf[None, :, None, None])
     l2_ref = l_ref + (dl + bl[None, :, None, None])
     G.iter_update(d6[:, :2], bf, d6[:, 2:], bl, coords1, flow, logits, stacked)
     assert torch.equal(coords1, c2_ref) and torch.equal(logits, l2_ref) and torch.equal(flow, c2_ref - coords0)
-    assert torch.equal(stacked, torch.cat([flow, logits], dim=1))
+    assert torch.equal(stacked[:, :6], torch.cat([flow, logits], dim=1)) and bool(torch.isnan(stacked[:, 6:]).all())
     # the heads' 3x3 output convolution given as 1x1 "taps": window sum inside the kernel == F.conv2d (summation order aside)
     x = torch.randn(B, 32, h, w, generator=g).to(cuda)
     w6 = (0.1 * torch.randn(6, 32, 3, 3, generator=g)).to(cuda)
@@ -103,7 +103,7 @@ def test_iter_update_equals_stock_ops(cuda, B, h, w, fmt):
     l3_ref = logits + (ref6[:, 2:] + bl[None, :, None, None])
     G.iter_update_taps(taps, 3, bf, bl, coords1, flow, logits, stacked)
     assert torch.allclose(coords1, c3_ref, rtol=0, atol=2e-5) and torch.allclose(logits, l3_ref, rtol=0, atol=2e-5)
-    assert torch.equal(flow, coords1 - coords0) and torch.equal(stacked, torch.cat([flow, logits], dim=1))
+    assert torch.equal(flow, coords1 - coords0) and torch.equal(stacked[:, :6], torch.cat([flow, logits], dim=1))
 
 
 @pytest.mark.parametrize("B,C,H,W", [(2, 32, 40, 56), (3, 96, 17, 23), (8, 32, 320, 320)])
