@@ -174,3 +174,65 @@ def test_async_npz_writer_schema_matches_reference_consumer(tmp_path):
         assert tuple(grid_size) == (H, W, 1) and np.allclose(f["bev_range_m"], (70.0, 70.0))
     w2 = AsyncNpzWriter(str(tmp_path), bev_range_m=(70.0, 70.0), workers=1, skip_existing=True)
     assert w2.submit_batch(ids, keep, 0.5) == 0 and w2.close() == 0
+
+
+def test_stacked_parallel_convolutions_equal_the_separate_ones():
+    """`raft._stacked_params`: one block-diagonal (or output-stacked) convolution == the two parallel convolutions it
+    replaces (update.py:49-66: flow / logits branches; update.py:6-20: the two heads), padding channels ignored."""
+    import torch
+    from torch import nn
+
+    from liso_b200.slim import raft as R
+
+    torch.manual_seed(0)
+    a, b = nn.Conv2d(2, 64, 7, padding=3), nn.Conv2d(4, 64, 7, padding=3)
+    w, bias = R._stacked_params(a, b, shared_input=False, pad_in_to=8)
+    assert tuple(w.shape) == (128, 8, 7, 7)
+    x = torch.randn(2, 8, 9, 11)
+    ref = torch.cat([a(x[:, :2]), b(x[:, 2:6])], dim=1)
+    got = torch.nn.functional.conv2d(x, w, bias, padding=3)  # channels 6, 7 carry garbage: zero weights
+    assert float((ref - got).abs().max()) < 1e-5
+    c, d = nn.Conv2d(96, 128, 3, padding=1), nn.Conv2d(96, 128, 3, padding=1)
+    w2, b2 = R._stacked_params(c, d, shared_input=True)
+    h = torch.randn(1, 96, 6, 5)
+    assert float((torch.cat([c(h), d(h)], 1) - torch.nn.functional.conv2d(h, w2, b2, padding=1)).abs().max()) < 1e-5
+    assert R._same_geometry(a, b) and not R._same_geometry(a, c)
+    # the heads' 3x3 output convolution as 1x1 taps + window sum (what slimb200_iter_update_taps evaluates)
+    e = nn.Conv2d(16, 6, 3, padding=1, bias=False)
+    w_taps = e.weight.detach().permute(2, 3, 0, 1).reshape(54, 16, 1, 1)
+    y = torch.randn(1, 16, 7, 8)
+    taps = torch.nn.functional.conv2d(y, w_taps).reshape(1, 3, 3, 6, 7, 8)
+    out = torch.zeros(1, 6, 7, 8)
+    padded = torch.nn.functional.pad(taps, (1, 1, 1, 1))
+    for ky in range(3):
+        for kx in range(3):
+            out += padded[:, ky, kx, :, ky:ky + 7, kx:kx + 8]
+    assert float((out - e(y)).abs().max()) < 1e-5
+
+
+def test_pyramid_layout_formula_matches_header():
+    """The 4-pixel x 8-column interleaved half-tile layout of include/slimb200.h: pack -> address formula -> unpack."""
+    import random
+
+    import torch
+
+    from liso_b200.slim import corr as Cc
+
+    random.seed(0)
+    for B, h, w in ((2, 12, 20), (1, 23, 29)):
+        L = Cc.make_layout(B, 128, h, w, 4)
+        nf = h * w
+        levels = [torch.randn(B * nf, 1, L.level_h[l], L.level_w[l]) for l in range(4)]
+        packed = Cc.pack_pyramid_f32(levels, L)
+        assert packed.numel() == B * L.n_panels * L.rows_padded * 128 and L.rows_padded % 128 == 0 and L.rows_padded >= nf
+        flat = packed.view(-1)
+        for l in range(4):
+            assert torch.equal(Cc.unpack_level(packed, L, l), levels[l])
+        for _ in range(500):
+            b, i, l = random.randrange(B), random.randrange(nf), random.randrange(4)
+            y, x = random.randrange(L.level_h[l]), random.randrange(L.level_w[l])
+            j = L.level_offset[l] + y * L.level_w[l] + x
+            c = j % 128
+            t = ((b * L.n_panels + j // 128) * (L.rows_padded // 128) + i // 128) * 2 + c // 64
+            idx = t * 8192 + ((i % 128) // 4) * 256 + ((c % 64) // 8) * 32 + (i % 4) * 8 + c % 8
+            assert flat[idx] == levels[l][b * nf + i, 0, y, x]
