@@ -273,6 +273,7 @@ class SLIM(nn.Module):
         # decode each network output as soon as it exists (a side branch of the CUDA graph) instead of after the network
         self.decode_as_sink = True
         self._dec_static, self._dec_ctx, self._dec_n, self._sink_preds = {}, {}, {}, {}
+        self._graph_preds = None  # (graph key, decoded static outputs of the captured pass)
 
     # ---- output decoding as a sink of the network (SURVEY 8f.1 + 8f.2) ------------------------------------------
     # The reference decodes every iteration's network output after the network has run (slim.py:77-148).  Here the
@@ -329,6 +330,21 @@ class SLIM(nn.Module):
                      int(st["pc"].shape[1])]
         return tuple(keys)
 
+    def _sink_results(self, net, static: bool, captures_before: int):
+        """The decoded outputs that belong to the call `net` just served.  Eager call: what the sink produced during it.
+        Graph call: the sink only runs while a graph is captured, so the results of THAT pass (the graph's static
+        outputs) are kept with the graph's key and handed out on every replay -- `_sink_preds` itself may meanwhile
+        hold the results of eager calls made in between."""
+        if not static:
+            return self._sink_preds
+        st = net._graphs.get("net")
+        if getattr(net, "n_graph_captures", 0) != captures_before:  # this call captured (again)
+            self._graph_preds = (st["key"], dict(self._sink_preds))
+        if st is None or self._graph_preds is None or self._graph_preds[0] != st["key"]:
+            raise RuntimeError("SLIM: the replayed CUDA graph has no decoded outputs on record (it was not captured "
+                               "through SLIM.forward)")
+        return self._graph_preds[1]
+
     _POINTWISE = ("static_flow", "dynamic_flow", "dynamicness", "staticness", "aggregated_flow", "static_aggr_flow")
 
     def _present(self, ret, n_points: int, thr):
@@ -353,9 +369,11 @@ class SLIM(nn.Module):
             key = self._stage_decode_inputs((sample_data_t0, sample_data_t1), dev, thr, static)
             net.output_sink, net.output_sink_begin = self._sink, self._sink_begin
             net.graph_extra_key = (key, self.static_aggregation) if static else None
+            captures_before = getattr(net, "n_graph_captures", 0)
             net(pcl_t0, pcl_t1, raw_scans=raw)
-            preds_fw, preds_bw = ([self._present(self._sink_preds[(k, it)], self._dec_n[k], thr)
-                                   for it in sorted(i for (kk, i) in self._sink_preds if kk == k)] for k in (0, 1))
+            decoded = self._sink_results(net, static, captures_before)
+            preds_fw, preds_bw = ([self._present(decoded[(k, it)], self._dec_n[k], thr)
+                                   for it in sorted(i for (kk, i) in decoded if kk == k)] for k in (0, 1))
             self.predictions_fw, self.predictions_bw = preds_fw, preds_bw
             return preds_fw, preds_bw
         net.output_sink = net.output_sink_begin = net.graph_extra_key = None

@@ -151,3 +151,23 @@ def eager_last(model, s0, s1):
         return model(s0, s1, None)[0][-1].static_flow.clone()
     finally:
         model.raft_network.use_cuda_graph = True
+
+
+def test_graph_replay_after_eager_calls_returns_the_graphs_own_results(cuda):
+    """The sink (decoder) only runs while the graph is captured; eager calls made in between must not leak their
+    results into later replays of the still valid graph."""
+    cfg = make_cfg("T")
+    model, _ = _model(cfg, cuda)
+    s0, s1 = make_sample_dicts(WORKLOADS["T"], [61])
+    t0, t1 = make_sample_dicts(WORKLOADS["T"], [62])
+    n_s, n_t = s0["pcl_ta"]["pcl_is_valid"].shape[1], t0["pcl_ta"]["pcl_is_valid"].shape[1]
+    with torch.no_grad():
+        g_s = model(s0, s1, None)[0][-1].static_flow.clone()          # capture + replay
+        model.raft_network.use_cuda_graph = False
+        e_t = model(t0, t1, None)[0][-1].static_flow.clone()          # eager call on another pair
+        model.raft_network.use_cuda_graph = True
+        g_s2 = model(s0, s1, None)[0][-1].static_flow.clone()         # replay of the graph captured above
+        g_t = model(t0, t1, None)[0][-1].static_flow.clone()
+    assert g_s.shape[1] == n_s and g_t.shape[1] == n_t and e_t.shape[1] == n_t
+    assert torch.equal(g_s2, g_s)
+    assert torch.equal(g_t, e_t)

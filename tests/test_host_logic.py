@@ -236,3 +236,29 @@ def test_pyramid_layout_formula_matches_header():
             t = ((b * L.n_panels + j // 128) * (L.rows_padded // 128) + i // 128) * 2 + c // 64
             idx = t * 8192 + ((i % 128) // 4) * 256 + ((c % 64) // 8) * 32 + (i % 4) * 8 + c % 8
             assert flat[idx] == levels[l][b * nf + i, 0, y, x]
+
+
+def test_decoded_outputs_of_a_replayed_graph_are_the_captured_ones():
+    """`SLIM._sink_results` bookkeeping (no GPU needed): eager calls between two replays of a graph overwrite the sink's
+    scratch dict, the replay must still hand out the outputs recorded when the graph was captured."""
+    import types
+
+    import pytest
+
+    from liso_b200.config import make_cfg
+    from liso_b200.slim.slim import SLIM
+
+    m = SLIM(make_cfg("T"))
+    net = types.SimpleNamespace(_graphs={}, n_graph_captures=0)
+    m._sink_preds = {(0, 5): "captured"}
+    net._graphs["net"], net.n_graph_captures = {"key": "K1"}, 1
+    assert m._sink_results(net, True, 0) == {(0, 5): "captured"}
+    m._sink_preds = {(0, 5): "eager"}
+    assert m._sink_results(net, False, 1) == {(0, 5): "eager"}
+    assert m._sink_results(net, True, 1) == {(0, 5): "captured"}       # replay, no new capture
+    m._sink_preds = {(0, 5): "captured again"}
+    net._graphs["net"], net.n_graph_captures = {"key": "K2"}, 2
+    assert m._sink_results(net, True, 1) == {(0, 5): "captured again"}
+    net._graphs["net"] = {"key": "K3"}                                   # a graph SLIM has no record of
+    with pytest.raises(RuntimeError):
+        m._sink_results(net, True, 2)
