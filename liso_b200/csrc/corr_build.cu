@@ -17,7 +17,8 @@
 //                                   of one B tile overlaps the MMAs of the next
 //                          warps 2-9 epilogue, group g drains the tiles of resident A tile g:
 //                                   tcgen05.ld -> * 1/sqrt(D) -> bf16 -> swizzled smem -> TMA store of one
-//                                   contiguous 32 KB block of the panel-tiled pyramid, L2 evict-first
+//                                   contiguous 32 KB (two 16 KB half-tiles, 4 rows x 8 columns per 64-byte
+//                                   unit: include/slimb200.h) of the tiled pyramid, L2 evict-first
 //                        K = D = 128 only, so the kernel is bound by the bf16 store of the volume
 //                        (algorithmic bytes = Nf * Ncols * 2 per sample per direction), not by MMA:
 //                        the design minimises everything that competes with the store stream (operand
@@ -302,7 +303,7 @@ k_corr_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   } else {
     // ================================ epilogue ====================================
     // Group g (4 warps) drains the accumulators of resident A tile g: TMEM -> registers -> * 1/sqrt(D) -> bf16 ->
-    // 128B-swizzled smem -> TMA store of one contiguous 32 KB panel block.
+    // 128B-swizzled smem image of the two half-tiles -> two contiguous 16 KB TMA stores.
     const int grp = (warp - 2) >> 2;
     const int qd = warp & 3;                // TMEM lane quarter this warp may read
     const int row = qd * 32 + lane;         // accumulator row == TMEM lane

@@ -12,7 +12,8 @@
 //            un-normalise fp32 arithmetic; per-offset bilinear weights with the zero padding folded in
 //   phase 2  every (pixel, level, window row) fetches its (2r+2)-element row segment of the pyramid with
 //            16-byte loads (all loads of the CTA are independent and in flight together) into shared memory;
-//            the 32 lanes of a load touch 32 neighbouring 256-byte panel rows -> one DRAM page
+//            in the pyramid layout (include/slimb200.h) 4 neighbouring pixels x 8 columns share a 64-byte unit, so the
+//            lanes 4k..4k+3 of a load are served by the same DRAM burst
 //   phase 3  49 outputs per (pixel, level) from the (2r+2)^2 window in shared memory: 4 taps x weights
 // Window rows that straddle rounding (floor of offset o != floor of offset 0 + o, |prob| ~ 1e-6) take a slow,
 // fully predicated global-memory path so that results always follow the reference arithmetic.
