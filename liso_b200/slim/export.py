@@ -270,3 +270,78 @@ class ExportPipeline:
                 consume(j, host)
             n_done += 1
         return n_done
+
+
+def collate_pairs(pairs):
+    """Batch un-batched pairs the way the reference's collate function does (``torch_dataset_commons.py:380-401``): the
+    network clouds stay a list; ``pcl_ta`` is padded to the longest cloud with NaN points, ``-1`` pillar coordinates
+    and a validity mask.  ``pairs``: list of ``(sample_t0, sample_t1)`` with ``pcl_full_no_ground_ta`` (N, C) and
+    ``pcl_ta = {"pcl" (N', C), "pillar_coors" (N', 2)}`` per sample (host tensors)."""
+    from torch.nn.utils.rnn import pad_sequence
+
+    out = []
+    for t in range(2):
+        samples = [p[t] for p in pairs]
+        pcl = pad_sequence([s["pcl_ta"]["pcl"] for s in samples], batch_first=True, padding_value=float("nan"))
+        coors = pad_sequence([s["pcl_ta"]["pillar_coors"] for s in samples], batch_first=True, padding_value=-1)
+        batch = {"pcl_full_no_ground_ta": [s["pcl_full_no_ground_ta"] for s in samples],
+                 "pcl_ta": {"pcl": pcl, "pillar_coors": coors, "pcl_is_valid": torch.logical_not(torch.isnan(pcl).sum(-1) > 0)}}
+        if all("raw_scan" in s for s in samples):
+            batch["raw_scan"] = samples[0]["raw_scan"]
+        out.append(batch)
+    return out[0], out[1]
+
+
+def _pin(sample):
+    def pin(t):
+        return t.pin_memory() if torch.cuda.is_available() and not t.is_pinned() else t
+
+    return {k: ([pin(t) for t in v] if isinstance(v, (list, tuple)) else {kk: pin(vv) for kk, vv in v.items()}
+                if isinstance(v, dict) else (pin(v) if torch.is_tensor(v) else v)) for k, v in sample.items()}
+
+
+def run_flow_export(model, dataset, target_dir: str, bev_range_m, *, world_size: int = 1, worker_id: int = 0,
+                    batch_size: int = 8, device=None, skip_existing: bool = False, writer_workers: Optional[int] = None,
+                    pipeline_factory=None) -> Dict[str, float]:
+    """The flow export of ``liso/slim/experiment.py:225-361,363-471`` for the t0 -> t1 pairs of one worker: this rank's
+    share of the pairs (modulo rule), batched, through the double-buffered :class:`ExportPipeline`, written by
+    :class:`AsyncNpzWriter` in the reference's ``.npz`` schema under ``target_dir/<sample_id>.npz``; one collective at
+    the end sums the counters over the ranks.
+
+    ``dataset``: ``len()`` and ``dataset[i] -> (sample_id, sample_t0, sample_t1)`` with un-batched host tensors (see
+    :func:`collate_pairs`).  Returns ``{"pairs", "files", "skipped", "elapsed_s_max"}`` over all ranks."""
+    import time
+
+    writer = AsyncNpzWriter(target_dir, bev_range_m, workers=writer_workers, skip_existing=skip_existing)
+    mine = shard_indices(len(dataset), world_size, worker_id)
+    ids_of_batch: List[List[str]] = []
+    skipped = 0
+
+    def batches():
+        nonlocal skipped
+        for chunk in iterate_batches(mine, batch_size):
+            items = [dataset[i] for i in chunk]
+            if skip_existing:  # (experiment.py:380-382: an existing target file skips the forward as well)
+                keep = [it for it in items if not os.path.exists(writer.target_file(it[0]))]
+                skipped += len(items) - len(keep)
+                items = keep
+            if not items:
+                continue
+            ids_of_batch.append([it[0] for it in items])
+            d0, d1 = collate_pairs([(it[1], it[2]) for it in items])
+            yield _pin(d0), _pin(d1)
+
+    thr = float(model.moving_dynamicness_threshold.value())
+    counts = {"pairs": 0, "files": 0}
+
+    def consume(j, host):
+        counts["pairs"] += len(ids_of_batch[j])
+        counts["files"] += writer.submit_batch(ids_of_batch[j], host, thr)
+
+    pipeline = (pipeline_factory or ExportPipeline)(model, device)
+    t0 = time.perf_counter()
+    pipeline.run(batches(), consume)
+    writer.close()
+    local = {"pairs": float(counts["pairs"]), "files": float(counts["files"]), "skipped": float(skipped),
+             "elapsed_s_max": time.perf_counter() - t0}
+    return reduce_counters(local, device if device is not None and torch.device(device).type == "cuda" else None)

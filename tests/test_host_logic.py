@@ -262,3 +262,58 @@ def test_decoded_outputs_of_a_replayed_graph_are_the_captured_ones():
     net._graphs["net"] = {"key": "K3"}                                   # a graph SLIM has no record of
     with pytest.raises(RuntimeError):
         m._sink_results(net, True, 2)
+
+
+def test_run_flow_export_shards_batches_and_writes_reference_schema(tmp_path):
+    """`run_flow_export` (experiment.py:225-361): modulo sharding, collate padding, one .npz per pair in the reference's
+    schema, skip_existing -- with a stand-in pipeline that produces the exported tensors on the CPU."""
+    import numpy as np
+    import torch
+
+    from liso_b200.slim import export
+
+    H = W = 4
+
+    class FakeThreshold:
+        def value(self):
+            return torch.tensor(0.25)
+
+    class FakeModel:
+        moving_dynamicness_threshold = FakeThreshold()
+
+    class FakePipeline:  # same contract as ExportPipeline.run: consume(index, [flow_fw, flow_bw, dyn_fw, dyn_bw])
+        def __init__(self, model, device):
+            self.seen = []
+
+        def run(self, batches, consume):
+            n = 0
+            for j, (d0, d1) in enumerate(batches):
+                n += 1
+                B = len(d0["pcl_full_no_ground_ta"])
+                assert d0["pcl_ta"]["pcl"].shape[0] == B and d0["pcl_ta"]["pcl_is_valid"].dtype == torch.bool
+                # padding rows: NaN points, -1 coordinates, invalid
+                inval = ~d0["pcl_ta"]["pcl_is_valid"]
+                assert bool(torch.isnan(d0["pcl_ta"]["pcl"][inval]).all()) and bool((d0["pcl_ta"]["pillar_coors"][inval] == -1).all())
+                n0 = torch.tensor([float(t.shape[0]) for t in d0["pcl_full_no_ground_ta"]])
+                flow = n0[:, None, None, None].expand(B, H, W, 2).contiguous()
+                consume(j, [flow, -flow, flow[..., 0].contiguous(), flow[..., 1].contiguous()])
+            return n
+
+    def sample(n):
+        return {"pcl_full_no_ground_ta": torch.zeros(n + 3, 4),
+                "pcl_ta": {"pcl": torch.ones(n, 4), "pillar_coors": torch.zeros(n, 2, dtype=torch.int32)}}
+
+    dataset = [("seq/%03d" % i, sample(5 + i), sample(7 + i)) for i in range(7)]
+    out = export.run_flow_export(FakeModel(), dataset, str(tmp_path), (70.0, 70.0), world_size=2, worker_id=1, batch_size=2,
+                                 pipeline_factory=FakePipeline, writer_workers=2)
+    assert out["pairs"] == 3 and out["files"] == 3 and out["skipped"] == 0  # indices 1, 3, 5
+    files = sorted(p.name for p in (tmp_path / "seq").iterdir())
+    assert files == ["001.npz", "003.npz", "005.npz"]
+    z = np.load(tmp_path / "seq" / "003.npz")
+    assert set(z.files) == {"static_threshold", "bev_raw_flow_t0_t1", "bev_raw_flow_t1_t0", "bev_dynamicness_t0_t1",
+                            "bev_dynamicness_t1_t0", "bev_range_m"}
+    assert z["bev_raw_flow_t0_t1"].shape == (H, W, 2) and float(z["bev_raw_flow_t0_t1"][0, 0, 0]) == 5 + 3 + 3
+    assert float(z["static_threshold"]) == 0.25 and tuple(z["bev_range_m"]) == (70.0, 70.0)
+    again = export.run_flow_export(FakeModel(), dataset, str(tmp_path), (70.0, 70.0), world_size=2, worker_id=1, batch_size=2,
+                                   pipeline_factory=FakePipeline, skip_existing=True)
+    assert again["pairs"] == 0 and again["skipped"] == 3
