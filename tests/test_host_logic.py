@@ -317,3 +317,59 @@ def test_run_flow_export_shards_batches_and_writes_reference_schema(tmp_path):
     again = export.run_flow_export(FakeModel(), dataset, str(tmp_path), (70.0, 70.0), world_size=2, worker_id=1, batch_size=2,
                                    pipeline_factory=FakePipeline, skip_existing=True)
     assert again["pairs"] == 0 and again["skipped"] == 3
+
+
+class _CpuThreshold:
+    def value(self):
+        return torch.tensor(0.5)
+
+
+class _CpuModel:
+    moving_dynamicness_threshold = _CpuThreshold()
+
+
+class _CpuPipeline:
+    """Stand-in for ExportPipeline (same `run(batches, consume)` contract) that fabricates the exported tensors."""
+
+    def __init__(self, model, device):
+        pass
+
+    def run(self, batches, consume):
+        n = 0
+        for j, (d0, _d1) in enumerate(batches):
+            B = len(d0["pcl_full_no_ground_ta"])
+            flow = torch.zeros(B, 2, 2, 2)
+            consume(j, [flow, flow, flow[..., 0].contiguous(), flow[..., 0].contiguous()])
+            n += 1
+        return n
+
+
+def _export_dataset(n):
+    def sample(k):
+        return {"pcl_full_no_ground_ta": torch.zeros(k + 2, 4),
+                "pcl_ta": {"pcl": torch.ones(k, 4), "pillar_coors": torch.zeros(k, 2, dtype=torch.int32)}}
+
+    return [("p%02d" % i, sample(3 + i), sample(4 + i)) for i in range(n)]
+
+
+def _gloo_export_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    tot = export.run_flow_export(_CpuModel(), _export_dataset(9), os.path.join(out_dir, "npz"), (70.0, 70.0), world_size=world,
+                                 worker_id=rank, batch_size=2, pipeline_factory=_CpuPipeline, writer_workers=1)
+    torch.save(tot, os.path.join(out_dir, "t%d.pt" % rank))
+    dist.destroy_process_group()
+
+
+def test_world_size_2_flow_export_gloo(tmp_path):
+    """Two workers export disjoint shares of the pairs (modulo rule) into one directory; the reduced counters equal the
+    whole job on every rank and every pair has exactly one file."""
+    port = _free_port()
+    mp.spawn(_gloo_export_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        tot = torch.load(os.path.join(str(tmp_path), "t%d.pt" % r))
+        assert tot["pairs"] == 9.0 and tot["files"] == 9.0 and tot["skipped"] == 0.0 and tot["elapsed_s_max"] > 0.0
+    assert sorted(os.listdir(os.path.join(str(tmp_path), "npz"))) == ["p%02d.npz" % i for i in range(9)]
