@@ -471,10 +471,10 @@ def main():
 
     # ---- CPU baseline (oracle port of the reference forward), N=1 only, bounded sample ----
     if world == 1 and not args.no_cpu_baseline:
-        (of, ob, _), times = run_oracle_pairs(cfg, sd, s0, s1, n_runs=2, warmup=1)
+        (of, ob, _), times = run_oracle_pairs(cfg, sd, s0, s1, n_runs=3, warmup=1)
         v = len(times) / sum(times)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                                "sample": "2 timed runs (1 warm-up) of 1 pair (B=1) of the same workload, fp32, all host threads"}
+                                "sample": "3 timed runs (1 warm-up) of 1 pair (B=1) of the same workload, fp32, all host threads"}
         with torch.no_grad(), amp():
             pf, pb = model(d0, d1, None)
         valid = s0["pcl_ta"]["pcl_is_valid"][0]
