@@ -114,8 +114,9 @@ def export_tensors(pf, pb):
     return [fw.static_flow, bw.static_flow, fw.dynamicness, bw.dynamicness]
 
 
-def run_oracle_pairs(cfg, sd, s0, s1, n_runs, warmup):
-    """Time the CPU port of the reference forward (one pair per run) on all host threads."""
+def run_oracle_pairs(cfg, sd, s0, s1, n_runs, warmup, min_seconds=0.0, max_runs=None):
+    """Time the CPU port of the reference forward (one pair per run) on all host threads: at least `n_runs` timed runs,
+    continued until `min_seconds` of timed work have been collected (at most `max_runs`)."""
     from oracle import slim_forward as SF
 
     torch.set_num_threads(os.cpu_count() or 1)
@@ -123,11 +124,13 @@ def run_oracle_pairs(cfg, sd, s0, s1, n_runs, warmup):
     one1 = {"pcl_full_no_ground_ta": s1["pcl_full_no_ground_ta"][:1], "pcl_ta": {k: v[:1] for k, v in s1["pcl_ta"].items()}}
     out, times = None, []
     with torch.no_grad():
-        for i in range(warmup + n_runs):
+        i = 0
+        while i < warmup + n_runs or (sum(times) < min_seconds and len(times) < (max_runs or n_runs)):
             t = time.perf_counter()
             out = SF.slim_forward(sd, cfg, one0, one1, decode_all_iterations=True)  # the reference decodes all 6
             if i >= warmup:
                 times.append(time.perf_counter() - t)
+            i += 1
     return out, times
 
 
@@ -471,10 +474,11 @@ def main():
 
     # ---- CPU baseline (oracle port of the reference forward), N=1 only, bounded sample ----
     if world == 1 and not args.no_cpu_baseline:
-        (of, ob, _), times = run_oracle_pairs(cfg, sd, s0, s1, n_runs=3, warmup=1)
+        (of, ob, _), times = run_oracle_pairs(cfg, sd, s0, s1, n_runs=3, warmup=1, min_seconds=10.0, max_runs=24)
         v = len(times) / sum(times)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                                "sample": "3 timed runs (1 warm-up) of 1 pair (B=1) of the same workload, fp32, all host threads"}
+                                "sample": "%d timed runs (1 warm-up, %.1f s of CPU work) of 1 pair (B=1) of the same workload, fp32, all host "
+                                          "threads" % (len(times), sum(times))}
         with torch.no_grad(), amp():
             pf, pb = model(d0, d1, None)
         valid = s0["pcl_ta"]["pcl_is_valid"][0]
