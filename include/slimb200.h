@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SLIMB200_VERSION 103
+#define SLIMB200_VERSION 200
 
 enum {
   SLIMB200_OK = 0,
@@ -194,6 +194,24 @@ int slimb200_corr_build(const float* fmap1, const float* fmap2, int32_t fmap_lay
 int slimb200_corr_lookup(const void* pyramid, int32_t pyramid_dtype, const slimb200_corr_layout* L,
                          const float* coords, int32_t radius, float* out, int32_t out_layout, void* stream);
 
+/* the lookup FUSED with the 1x1 convolution that consumes it, SmallMotionEncoder.conv_stat_corr1 (+ ReLU)
+ * (liso/slim/model/update.py:49,71), so that the (batch, levels*49, h, w) lookup tensor never reaches HBM:
+ *   out[b, y, x, n] = act( bias[n] + sum_k weight[n, k] * lookup[b, k, y, x] ),  k = l*49 + i*7 + j as above.
+ * The window values and the weights are rounded to tf32 (cvt.rna), products accumulate in fp32 on the tcgen05 tensor
+ * cores -- the precision cuDNN uses for this convolution when TF32 is allowed (|err| <= 2^-10 * sum_k |w_nk| |v_k|).
+ * bf16 pyramid, radius 3 and 4 levels only; c_out in {32, 64, 96, 128}.
+ * weight: device (c_out, levels*49) f32 = conv weight (c_out, levels*49, 1, 1); bias: device (c_out) f32 or NULL.
+ * out: device, channels-last rows: pixel (b, y, x) at out + ((b*h + y)*w + x) * out_pitch, c_out floats each;
+ *      out_pitch >= c_out floats, multiple of 4 (a channel slice of a wider channels-last tensor works); 16-byte aligned.
+ * relu: 0 / 1. */
+int slimb200_corr_lookup_conv(const void* pyramid, int32_t pyramid_dtype, const slimb200_corr_layout* L,
+                              const float* coords, int32_t radius, const float* weight, const float* bias,
+                              int32_t c_out, int32_t relu, float* out, int32_t out_pitch, void* stream);
+
+/* Tuning hook (tools/kbench.py): 0 = first-generation radius-3 lookup kernel, 1 (default) = the (pixel, level)-per-thread
+ * gather of csrc/corr_lookup2.cu for bf16 pyramids.  Returns the previous value; negative values only query. */
+int slimb200_lookup_generation(int32_t generation);
+
 /* ------------------------------------------------------------------------------------------
  * output decoder.  Replaces HeadDecoder.forward (liso/slim/model/head_decoder.py:410-496,
  * 517-717) for the released output_modification, batched_grid_data_to_pointwise_data and
@@ -342,6 +360,7 @@ enum {
   SLIMB200_K_GRU_GATE_OUT,
   SLIMB200_K_ITER_UPDATE,
   SLIMB200_K_ADD_RELU,
+  SLIMB200_K_LOOKUP_CONV,
   SLIMB200_N_KERNELS
 };
 int slimb200_profile_begin(void);

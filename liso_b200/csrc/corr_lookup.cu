@@ -619,7 +619,19 @@ int dispatch_radius(int radius, int out_layout, const void* pyramid, const slimb
   }
 }
 
+int g_lookup_generation = 1;
+
 }  // namespace
+
+// csrc/corr_lookup2.cu
+int slimb200_lookup_v2_launch(const void* pyramid, const slimb200_corr_layout* L, const float* coords, float* out, int out_layout,
+                              cudaStream_t stream);
+
+extern "C" int slimb200_lookup_generation(int32_t generation) {
+  const int prev = g_lookup_generation;
+  if (generation >= 0) g_lookup_generation = generation;
+  return prev;
+}
 
 extern "C" int slimb200_corr_lookup(const void* pyramid, int32_t pyramid_dtype, const slimb200_corr_layout* L,
                                     const float* coords, int32_t radius, float* out, int32_t out_layout, void* stream_) {
@@ -630,6 +642,8 @@ extern "C" int slimb200_corr_lookup(const void* pyramid, int32_t pyramid_dtype, 
   if (L->rows_padded < L->h * L->w || (L->rows_padded & 127)) return SLIMB200_E_INVALID;
   if (reinterpret_cast<uintptr_t>(pyramid) & 15) return SLIMB200_E_ALIGNMENT;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (pyramid_dtype == SLIMB200_DTYPE_BF16 && radius == 3 && g_lookup_generation >= 1)
+    return slimb200_lookup_v2_launch(pyramid, L, coords, out, out_layout, stream);
   if (pyramid_dtype == SLIMB200_DTYPE_BF16) return dispatch_radius<__nv_bfloat16>(radius, out_layout, pyramid, L, coords, out, stream);
   if (pyramid_dtype == SLIMB200_DTYPE_F32) return dispatch_radius<float>(radius, out_layout, pyramid, L, coords, out, stream);
   return SLIMB200_E_UNSUPPORTED;

@@ -95,6 +95,47 @@ def lookup(pyramid: torch.Tensor, L: _lib.CorrLayout, coords: torch.Tensor, radi
     return out
 
 
+def lookup_conv(pyramid: torch.Tensor, L: _lib.CorrLayout, coords: torch.Tensor, radius: int, weight: torch.Tensor,
+                bias: torch.Tensor = None, relu: bool = True, out: torch.Tensor = None) -> torch.Tensor:
+    """``slimb200_corr_lookup_conv``: ``act(conv1x1(lookup(coords)))`` in one kernel -- the lookup of
+    ``corr.py:23-46`` fused with ``SmallMotionEncoder.conv_stat_corr1`` + ReLU (``update.py:49,71``); the
+    ``(B, L*49, h, w)`` lookup tensor never reaches HBM.  tf32 operands, fp32 accumulation on the tensor cores.
+
+    ``weight``: ``(C_out, L*49)`` or the conv's ``(C_out, L*49, 1, 1)``; returns ``(B, C_out, h, w)`` fp32 in
+    channels-last memory format.  ``out``: optional destination -- a channels-last tensor ``(B, >= C_out, h, w)`` whose
+    first ``C_out`` channels are written (its other channels are left untouched)."""
+    _lib.require_cuda(pyramid, coords, weight, bias, out)
+    if pyramid.dtype != torch.bfloat16:
+        raise ValueError("lookup_conv needs the bf16 pyramid")
+    if coords.shape != (L.batch, 2, L.h, L.w):
+        raise ValueError("coords must be (B,2,h,w) = %s, got %s" % ((L.batch, 2, L.h, L.w), tuple(coords.shape)))
+    coords = coords.detach()
+    if coords.dtype != torch.float32 or not coords.is_contiguous():
+        coords = coords.float().contiguous()
+    n_ch = L.levels * (2 * radius + 1) ** 2
+    c_out = int(weight.shape[0])
+    w2 = weight.detach().reshape(c_out, -1)
+    if w2.shape[1] != n_ch or w2.dtype != torch.float32:
+        raise ValueError("weight must be fp32 (C_out, %d[, 1, 1])" % n_ch)
+    if not w2.is_contiguous():
+        w2 = w2.contiguous()
+    if bias is not None and (bias.numel() != c_out or bias.dtype != torch.float32 or not bias.is_contiguous()):
+        raise ValueError("bias must be contiguous fp32 (C_out)")
+    if out is None:
+        out = torch.empty((L.batch, c_out, L.h, L.w), dtype=torch.float32, device=coords.device, memory_format=torch.channels_last)
+    elif not (out.dtype == torch.float32 and out.dim() == 4 and out.shape[0] == L.batch and out.shape[2:] == (L.h, L.w)
+              and out.shape[1] >= c_out and out.is_contiguous(memory_format=torch.channels_last)):
+        raise ValueError("out must be a channels-last fp32 (B, >= C_out, h, w) tensor")
+    _lib.check(_lib.load().slimb200_corr_lookup_conv(pyramid.data_ptr(), _lib.DTYPE_BF16, C.byref(L), coords.data_ptr(), radius,
+                                                     w2.data_ptr(), bias.data_ptr() if bias is not None else None, c_out,
+                                                     1 if relu else 0, out.data_ptr(), int(out.shape[1]), _lib.current_stream_ptr()))
+    return out
+
+
+def lookup_conv_supported(L: _lib.CorrLayout, radius: int, c_out: int) -> bool:
+    return radius == 3 and L.levels == 4 and c_out in (32, 64, 96, 128)
+
+
 def pack_pyramid_f32(levels: List[torch.Tensor], L: _lib.CorrLayout) -> torch.Tensor:
     """Pack reference-shaped fp32 levels (B*h*w,1,h_l,w_l) into the library's panel layout (tests)."""
     nf, P, pw = L.h * L.w, L.n_panels, _lib.PANEL_COLS
@@ -147,6 +188,14 @@ class CorrBlock:
 
     def __call__(self, coords: torch.Tensor) -> torch.Tensor:
         return lookup(self.pyramid, self.layout, coords, self.radius, self.channels_last)
+
+    def lookup_conv(self, coords: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor = None, relu: bool = True,
+                    out: torch.Tensor = None) -> torch.Tensor:
+        """``relu(conv1x1(self(coords)))`` without materialising the lookup tensor (see :func:`lookup_conv`)."""
+        return lookup_conv(self.pyramid, self.layout, coords, self.radius, weight, bias, relu, out)
+
+    def lookup_conv_supported(self, c_out: int) -> bool:
+        return self.pyramid.dtype == torch.bfloat16 and lookup_conv_supported(self.layout, self.radius, c_out)
 
     @staticmethod
     def corr(fmap1: torch.Tensor, fmap2: torch.Tensor) -> torch.Tensor:

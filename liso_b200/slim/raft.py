@@ -353,6 +353,10 @@ class RAFT(nn.Module):
         # into one cuDNN launch each
         self.merge_parallel_convs = True
         self.tap_heads = True  # ... and the heads' 3x3 output convolution as a 1x1 convolution to taps + window sum
+        # the lookup fused with the 1x1 convolution that consumes it (conv_stat_corr1 + ReLU, update.py:49,71) in one
+        # tcgen05 kernel with tf32 operands: True = whenever TF32 convolutions are allowed (cuDNN's precision for that
+        # layer then), "always" = also with fp32 convolutions, False = lookup kernel + stock convolution
+        self.fuse_lookup_conv = True
         # forward and backward direction as two parallel branches of the CUDA graph
         self.concurrent_directions = True
         # consumer of the per-iteration network outputs, e.g. SLIM's output decoder: called as
@@ -396,6 +400,7 @@ class RAFT(nn.Module):
         wsig = tuple((p.data_ptr(), p._version) for mod in (self.fnet, self.cnet, self.update_block) for p in mod.parameters())
         key = (B, self.output_iterations, self.pp_layer.canvas_memory_format, str(dev), torch.backends.cudnn.allow_tf32,
                self.fused_update_block, self.merge_parallel_convs, self.tap_heads, self.concurrent_directions, FAST_STOCK_OPS,
+               self.fuse_lookup_conv,
                self.output_sink is not None, self.graph_extra_key, wsig)
         st = self._graphs.get("net")
         if st is not None and st["key"] != key:
@@ -586,10 +591,16 @@ class RAFT(nn.Module):
                 w_taps = _PARAM_CAST_CACHE.get(key)
                 if w_taps is None:  # W1[(ky*k + kx)*6 + c][cin] = W[c][cin][ky][kx]
                     w_taps = _cache_put(key, w_h2.permute(2, 3, 0, 1).reshape(k * k * w_h2.shape[0], w_h2.shape[1], 1, 1).contiguous())
+        c1 = me.conv_stat_corr1
+        fuse_lookup = (bool(self.fuse_lookup_conv) and (self.fuse_lookup_conv == "always" or torch.backends.cudnn.allow_tf32)
+                       and c1.kernel_size == (1, 1) and c1.stride == (1, 1) and c1.padding == (0, 0) and c1.groups == 1
+                       and c1.bias is not None and correlation.lookup_conv_supported(c1.out_channels))
         outs = []
         for it in range(m.num_iters):
-            corr = correlation(coords1)
-            c = conv_relu(me.conv_stat_corr1, corr)
+            if fuse_lookup:
+                c = correlation.lookup_conv(coords1, c1.weight, c1.bias, relu=True)
+            else:
+                c = conv_relu(c1, correlation(coords1))
             if merge:
                 flg = conv_relu(me.conv_flow2, conv_relu(me.conv_flow1, stacked, w_m1, b_m1), w_m2, b_m2)  # [flow | logits] features
                 f, lg = flg[:, :n_f], flg[:, n_f:]

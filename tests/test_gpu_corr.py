@@ -133,3 +133,107 @@ def test_window_channel_order(cuda):
         for j in range(7):
             # (the normalise / un-normalise round trip of grid_sample is not exact: ~1e-6 relative)
             assert abs(float(out[0, i * 7 + j, 0, 0]) - (16.0 * (5 + j - 3) + (8 + i - 3))) < 1e-3
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# second-generation gather (csrc/corr_lookup2.cu) and the lookup fused with the 1x1 convolution that consumes it
+# ----------------------------------------------------------------------------------------------------------------------
+def _wild_coords(B, h, w, seed, spread):
+    c = _coords(B, h, w, seed, spread)
+    c[:, :, 3, 3] = torch.tensor([1e9, -1e9])          # absurd but finite: every tap outside
+    c[:, :, 3, 4] = torch.tensor([float("inf"), 2.0])  # non-finite: the kernel's fully predicated path
+    c[:, :, 4, 3] = torch.tensor([0.0, h - 1.0])       # corners
+    c[:, :, 4, 4] = torch.tensor([w - 1.0, 0.0])
+    return c
+
+
+@pytest.mark.parametrize("fmt", ["contiguous", "channels_last"])
+@pytest.mark.parametrize("B,h,w", [(3, 16, 16), (1, 80, 80), (1, 115, 115), (2, 12, 20)])
+def test_lookup_generations_agree(cuda, B, h, w, fmt):
+    """The (pixel, level)-per-thread gather answers like the first-generation kernel (same blend association: equal up
+    to the sign of zero) on regular, integer ("shifted"), out-of-range and non-finite coordinates."""
+    from liso_b200 import _lib
+
+    f1, f2, d1, d2 = _fmaps(B, h, w, 11, cuda)
+    if fmt == "channels_last":
+        d1, d2 = d1.contiguous(memory_format=torch.channels_last), d2.contiguous(memory_format=torch.channels_last)
+    blk = C.CorrBlock(d1, d2, num_levels=4, radius=3)
+    lib = _lib.load()
+    for spread in (1.5, 0.0, 6.0):
+        coords = _wild_coords(B, h, w, 12, spread).to(cuda)
+        try:
+            lib.slimb200_lookup_generation(0)
+            old = blk(coords).cpu()
+        finally:
+            lib.slimb200_lookup_generation(1)
+        new = blk(coords)
+        assert new.is_contiguous(memory_format=torch.channels_last if fmt == "channels_last" else torch.contiguous_format)
+        new = new.cpu()
+        assert torch.isfinite(new).all()
+        assert float(new[:, :, 3, 3].abs().max()) == 0.0 and float(new[:, :, 3, 4].abs().max()) == 0.0
+        scale = float(old.abs().max())
+        assert float((new - old).abs().max()) <= 2e-6 * scale, (spread, float((new - old).abs().max()), scale)
+
+
+def _conv_ref(look, weight, bias, relu):
+    """fp64 reference of act(conv1x1(look)) and the tf32 operand bound 2^-10 * sum_k |w_nk| |v_k| per output."""
+    B, K, h, w = look.shape
+    v = look.double().permute(0, 2, 3, 1).reshape(-1, K)
+    y = v @ weight.double().t() + (bias.double() if bias is not None else 0.0)
+    bound = (2.0 ** -10) * (v.abs() @ weight.double().abs().t())
+    if relu:
+        y = y.clamp_min(0.0)
+    n = weight.shape[0]
+    return y.reshape(B, h, w, n).permute(0, 3, 1, 2), bound.reshape(B, h, w, n).permute(0, 3, 1, 2)
+
+
+@pytest.mark.parametrize("B,h,w,n_out", [(3, 16, 16, 96), (1, 80, 80, 96), (1, 115, 115, 96), (2, 24, 40, 32), (2, 12, 20, 128),
+                                         (1, 23, 29, 64)])
+def test_lookup_conv_fused_matches_oracle(cuda, B, h, w, n_out):
+    """slimb200_corr_lookup_conv == relu(conv_stat_corr1(CorrBlock(...)(coords))) of the oracle
+    (corr.py:23-46 + update.py:49,71) within the tf32 operand bound: the window values and the weights are rounded to
+    tf32 (rel. 2^-11 each), products accumulate in fp32:
+        |got - fp64| <= 2^-10 * sum_k |w_nk| |v_k|  +  1e-5 * scale * sum_k |w_nk|  (the lookup's own fp32 interpolation)"""
+    f1, f2, d1, d2 = _fmaps(B, h, w, 21, cuda)
+    d1, d2 = d1.contiguous(memory_format=torch.channels_last), d2.contiguous(memory_format=torch.channels_last)
+    blk = C.CorrBlock(d1, d2, num_levels=4, radius=3)
+    assert blk.lookup_conv_supported(n_out)
+    same_values = [lv.float().cpu().contiguous() for lv in blk.corr_pyramid]
+    scale = float(same_values[0].abs().max())
+    g = torch.Generator().manual_seed(22)
+    weight = torch.randn(n_out, 196, 1, 1, generator=g) / 14.0
+    bias = torch.randn(n_out, generator=g)
+    wd, bd = weight.to(cuda), bias.to(cuda)
+    for spread, relu in ((1.5, True), (0.0, True), (6.0, False)):
+        coords = _wild_coords(B, h, w, 23, spread)
+        got_dev = blk.lookup_conv(coords.to(cuda), wd, bd, relu=relu)
+        assert got_dev.shape == (B, n_out, h, w) and got_dev.is_contiguous(memory_format=torch.channels_last)
+        got = got_dev.cpu()
+        look = O.corr_lookup(same_values, coords, 3)
+        ref, bound = _conv_ref(look, weight.reshape(n_out, 196), bias, relu)
+        tol = bound + 1e-5 * scale * float(weight.abs().sum(dim=1).max()) + 1e-6
+        err = (got.double() - ref).abs()
+        assert bool((err <= tol).all()), (spread, float(err.max()), float((err / tol).max()))
+        # aggregate accuracy: rms error two orders below the bound's scale (tf32 rounding is unbiased)
+        assert float(err.pow(2).mean().sqrt()) < 2.0 ** -11 * float(ref.abs().max()) + 1e-6
+        # and against the library's own unfused path (lookup kernel -> fp32 conv)
+        unf = torch.nn.functional.conv2d(blk(coords.to(cuda)), wd, bd)
+        unf = torch.relu(unf) if relu else unf
+        assert float((got_dev - unf).abs().max()) <= float(tol.max())
+
+
+def test_lookup_conv_writes_channel_slice(cuda):
+    """`out` may be a wider channels-last tensor: only its first C_out channels are written (no torch.cat afterwards)."""
+    B, h, w, n_out = 2, 24, 40, 96
+    _, _, d1, d2 = _fmaps(B, h, w, 31, cuda)
+    blk = C.CorrBlock(d1.contiguous(memory_format=torch.channels_last), d2.contiguous(memory_format=torch.channels_last), 4, 3)
+    g = torch.Generator().manual_seed(32)
+    wd = (torch.randn(n_out, 196, generator=g) / 14.0).to(cuda)
+    coords = _coords(B, h, w, 33, 1.5).to(cuda)
+    ref = blk.lookup_conv(coords, wd, None, relu=False)
+    wide = torch.full((B, 160, h, w), 7.0, device=cuda).contiguous(memory_format=torch.channels_last)
+    ret = blk.lookup_conv(coords, wd, None, relu=False, out=wide)
+    assert ret.data_ptr() == wide.data_ptr()
+    assert torch.equal(wide[:, :n_out], ref) and bool((wide[:, n_out:] == 7.0).all())
+    with pytest.raises(RuntimeError):
+        blk.lookup_conv(coords, torch.zeros(48, 196, device=cuda), None)  # C_out must be a multiple of 32

@@ -76,6 +76,35 @@ def main():
                 state["out"] = state["blk"](grid)
 
         runs.append(("corr_lookup integer coords", look_int))
+
+        # generations / layouts of the lookup, the fused lookup + 1x1 convolution and what it replaces
+        import torch.nn.functional as F
+
+        blk_l = CorrBlock(f1c, f2c, num_levels=4, radius=3)
+        blk_c = CorrBlock(f1, f2, num_levels=4, radius=3)
+        wconv = (torch.randn(96, 196, 1, 1, generator=g) / 14.0).to(dev).contiguous(memory_format=torch.channels_last)
+        bconv = torch.randn(96, generator=g).to(dev)
+        torch.backends.cudnn.allow_tf32 = True
+        torch.backends.cudnn.benchmark = True
+
+        def gen(n, fn):
+            def run():
+                lib.slimb200_lookup_generation(n)
+                try:
+                    for _ in range(6):
+                        state["out"] = fn()
+                finally:
+                    lib.slimb200_lookup_generation(1)
+            return run
+
+        runs.append(("lookup gen0 nhwc x6", gen(0, lambda: blk_l(coords))))
+        runs.append(("lookup gen1 nhwc x6", gen(1, lambda: blk_l(coords))))
+        runs.append(("lookup gen0 nchw x6", gen(0, lambda: blk_c(coords))))
+        runs.append(("lookup gen1 nchw x6", gen(1, lambda: blk_c(coords))))
+        runs.append(("lookup gen1 nchw int x6", gen(1, lambda: blk_c(grid))))
+        runs.append(("lookup+conv unfused x6", gen(1, lambda: torch.cudnn_convolution_relu(blk_l(coords), wconv, bconv, (1, 1), (0, 0), (1, 1), 1))))
+        runs.append(("lookup_conv fused x6", gen(1, lambda: blk_l.lookup_conv(coords, wconv, bconv, relu=True))))
+        runs.append(("lookup_conv fused int x6", gen(1, lambda: blk_l.lookup_conv(grid, wconv, bconv, relu=True))))
     with torch.no_grad():
         for name, fn in runs:
             for _ in range(3):
