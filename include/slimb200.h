@@ -200,13 +200,20 @@ int slimb200_corr_lookup(const void* pyramid, int32_t pyramid_dtype, const slimb
  * The window values and the weights are rounded to tf32 (cvt.rna), products accumulate in fp32 on the tcgen05 tensor
  * cores -- the precision cuDNN uses for this convolution when TF32 is allowed (|err| <= 2^-10 * sum_k |w_nk| |v_k|).
  * bf16 pyramid, radius 3 and 4 levels only; c_out in {32, 64, 96, 128}.
- * weight: device (c_out, levels*49) f32 = conv weight (c_out, levels*49, 1, 1); bias: device (c_out) f32 or NULL.
- * out: device, channels-last rows: pixel (b, y, x) at out + ((b*h + y)*w + x) * out_pitch, c_out floats each;
- *      out_pitch >= c_out floats, multiple of 4 (a channel slice of a wider channels-last tensor works); 16-byte aligned.
- * relu: 0 / 1. */
+ *
+ * corr_lookup_conv_pack: once per weight tensor -- weight: device (c_out, levels*49) f32 = conv weight
+ *   (c_out, levels*49, 1, 1); bias: device (c_out) f32 or NULL; packed: device, slimb200_corr_lookup_conv_packed_bytes(c_out)
+ *   bytes, 16-byte aligned: the tf32 B operand in its shared-memory layout (7 K blocks of c_out rows x 128 bytes,
+ *   128-byte swizzle, K slot l*56 + c, zero padded) followed by the biases.
+ * corr_lookup_conv: out: device, channels-last rows: pixel (b, y, x) at out + ((b*h + y)*w + x) * out_pitch, c_out floats
+ *   each; out_pitch >= c_out floats, multiple of 4 (a channel slice of a wider channels-last tensor works); 16-byte
+ *   aligned.  relu: 0 / 1. */
+size_t slimb200_corr_lookup_conv_packed_bytes(int32_t c_out);
+int slimb200_corr_lookup_conv_pack(const float* weight, const float* bias, int32_t levels, int32_t radius, int32_t c_out,
+                                   void* packed, void* stream);
 int slimb200_corr_lookup_conv(const void* pyramid, int32_t pyramid_dtype, const slimb200_corr_layout* L,
-                              const float* coords, int32_t radius, const float* weight, const float* bias,
-                              int32_t c_out, int32_t relu, float* out, int32_t out_pitch, void* stream);
+                              const float* coords, int32_t radius, const void* packed, int32_t c_out, int32_t relu,
+                              float* out, int32_t out_pitch, void* stream);
 
 /* Tuning hook (tools/kbench.py): 0 = first-generation radius-3 lookup kernel, 1 (default) = the (pixel, level)-per-thread
  * gather of csrc/corr_lookup2.cu for bf16 pyramids.  Returns the previous value; negative values only query. */
@@ -361,6 +368,7 @@ enum {
   SLIMB200_K_ITER_UPDATE,
   SLIMB200_K_ADD_RELU,
   SLIMB200_K_LOOKUP_CONV,
+  SLIMB200_K_LOOKUP_CONV_PACK,
   SLIMB200_N_KERNELS
 };
 int slimb200_profile_begin(void);

@@ -103,9 +103,11 @@ SYMBOLS = {
         C.c_int,
         [C.c_void_p, C.c_int32, C.POINTER(CorrLayout), C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p],
     ),
+    "slimb200_corr_lookup_conv_packed_bytes": (C.c_size_t, [C.c_int32]),
+    "slimb200_corr_lookup_conv_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "slimb200_corr_lookup_conv": (
         C.c_int,
-        [C.c_void_p, C.c_int32, C.POINTER(CorrLayout), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+        [C.c_void_p, C.c_int32, C.POINTER(CorrLayout), C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
          C.c_void_p, C.c_int32, C.c_void_p],
     ),
     "slimb200_lookup_generation": (C.c_int, [C.c_int32]),
@@ -162,7 +164,7 @@ SYMBOLS = {
     "slimb200_launch_count": (C.c_int64, [C.c_int32]),
     "slimb200_kernel_name": (C.c_char_p, [C.c_int32]),
 }
-N_KERNELS = 33
+N_KERNELS = 34
 K_TILE_ENCODE, K_PILLAR_NHWC, K_FEAT_TRANSPOSE, K_FEAT_PACK, K_CORR_GEMM, K_CORR_LOOKUP = 6, 7, 8, 9, 10, 11
 K_DECODE_BEV, K_DECODE_POINTS, K_DECODE_AGGR, K_RAFT_OUTPUT = 14, 15, 17, 18
 K_IN_STATS, K_IN_FINALIZE, K_IN_APPLY = 24, 25, 26

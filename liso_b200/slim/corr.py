@@ -16,6 +16,7 @@ Differences a caller can observe (documented in DESIGN.md):
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import List
 
 import torch
@@ -95,40 +96,71 @@ def lookup(pyramid: torch.Tensor, L: _lib.CorrLayout, coords: torch.Tensor, radi
     return out
 
 
-def lookup_conv(pyramid: torch.Tensor, L: _lib.CorrLayout, coords: torch.Tensor, radius: int, weight: torch.Tensor,
-                bias: torch.Tensor = None, relu: bool = True, out: torch.Tensor = None) -> torch.Tensor:
+class PackedLookupConv:
+    """The weights of the 1x1 convolution behind the lookup, packed for ``slimb200_corr_lookup_conv`` (tf32 B operand in
+    its shared-memory layout + biases; ``slimb200_corr_lookup_conv_pack``).  Built once per weight tensor; the owner
+    re-packs when the source parameters change (:meth:`matches`)."""
+
+    def __init__(self, weight: torch.Tensor, bias: torch.Tensor = None, levels: int = 4, radius: int = 3):
+        _lib.require_cuda(weight, bias)
+        lib = _lib.load()
+        self.c_out = int(weight.shape[0])
+        n_ch = levels * (2 * radius + 1) ** 2
+        w2 = weight.detach().reshape(self.c_out, -1)
+        if w2.shape[1] != n_ch or w2.dtype != torch.float32:
+            raise ValueError("weight must be fp32 (C_out, %d[, 1, 1])" % n_ch)
+        w2 = w2.contiguous()
+        if bias is not None:
+            if bias.numel() != self.c_out or bias.dtype != torch.float32:
+                raise ValueError("bias must be fp32 (C_out)")
+            bias = bias.detach().contiguous()
+        n_bytes = int(lib.slimb200_corr_lookup_conv_packed_bytes(self.c_out))
+        if n_bytes == 0:
+            raise RuntimeError("slimb200_corr_lookup_conv: C_out must be 32, 64, 96 or 128 (got %d)" % self.c_out)
+        self.levels, self.radius = levels, radius
+        self.packed = torch.empty(n_bytes, dtype=torch.uint8, device=weight.device)
+        _lib.check(lib.slimb200_corr_lookup_conv_pack(w2.data_ptr(), bias.data_ptr() if bias is not None else None, levels, radius,
+                                                      self.c_out, self.packed.data_ptr(), _lib.current_stream_ptr()))
+        self._src = (weakref.ref(weight), weight._version, None if bias is None else weakref.ref(bias),
+                     None if bias is None else bias._version)
+
+    def matches(self, weight: torch.Tensor, bias: torch.Tensor = None) -> bool:
+        """Packed from exactly these tensors in their current version (identity, not address)."""
+        w_ref, w_ver, b_ref, b_ver = self._src
+        if w_ref() is not weight or weight._version != w_ver or weight.device != self.packed.device:
+            return False
+        if bias is None or b_ref is None:
+            return bias is None and b_ref is None
+        return b_ref() is bias and bias._version == b_ver
+
+
+def lookup_conv(pyramid: torch.Tensor, L: _lib.CorrLayout, coords: torch.Tensor, radius: int, packed: PackedLookupConv,
+                relu: bool = True, out: torch.Tensor = None) -> torch.Tensor:
     """``slimb200_corr_lookup_conv``: ``act(conv1x1(lookup(coords)))`` in one kernel -- the lookup of
     ``corr.py:23-46`` fused with ``SmallMotionEncoder.conv_stat_corr1`` + ReLU (``update.py:49,71``); the
     ``(B, L*49, h, w)`` lookup tensor never reaches HBM.  tf32 operands, fp32 accumulation on the tensor cores.
 
-    ``weight``: ``(C_out, L*49)`` or the conv's ``(C_out, L*49, 1, 1)``; returns ``(B, C_out, h, w)`` fp32 in
-    channels-last memory format.  ``out``: optional destination -- a channels-last tensor ``(B, >= C_out, h, w)`` whose
-    first ``C_out`` channels are written (its other channels are left untouched)."""
-    _lib.require_cuda(pyramid, coords, weight, bias, out)
+    Returns ``(B, C_out, h, w)`` fp32 in channels-last memory format.  ``out``: optional destination -- a channels-last
+    tensor ``(B, >= C_out, h, w)`` whose first ``C_out`` channels are written (its other channels are left untouched)."""
+    _lib.require_cuda(pyramid, coords, out)
     if pyramid.dtype != torch.bfloat16:
         raise ValueError("lookup_conv needs the bf16 pyramid")
     if coords.shape != (L.batch, 2, L.h, L.w):
         raise ValueError("coords must be (B,2,h,w) = %s, got %s" % ((L.batch, 2, L.h, L.w), tuple(coords.shape)))
+    if packed.levels != L.levels or packed.radius != radius or packed.packed.device != pyramid.device:
+        raise ValueError("weights were packed for another lookup geometry / device")
     coords = coords.detach()
     if coords.dtype != torch.float32 or not coords.is_contiguous():
         coords = coords.float().contiguous()
-    n_ch = L.levels * (2 * radius + 1) ** 2
-    c_out = int(weight.shape[0])
-    w2 = weight.detach().reshape(c_out, -1)
-    if w2.shape[1] != n_ch or w2.dtype != torch.float32:
-        raise ValueError("weight must be fp32 (C_out, %d[, 1, 1])" % n_ch)
-    if not w2.is_contiguous():
-        w2 = w2.contiguous()
-    if bias is not None and (bias.numel() != c_out or bias.dtype != torch.float32 or not bias.is_contiguous()):
-        raise ValueError("bias must be contiguous fp32 (C_out)")
+    c_out = packed.c_out
     if out is None:
         out = torch.empty((L.batch, c_out, L.h, L.w), dtype=torch.float32, device=coords.device, memory_format=torch.channels_last)
     elif not (out.dtype == torch.float32 and out.dim() == 4 and out.shape[0] == L.batch and out.shape[2:] == (L.h, L.w)
               and out.shape[1] >= c_out and out.is_contiguous(memory_format=torch.channels_last)):
         raise ValueError("out must be a channels-last fp32 (B, >= C_out, h, w) tensor")
     _lib.check(_lib.load().slimb200_corr_lookup_conv(pyramid.data_ptr(), _lib.DTYPE_BF16, C.byref(L), coords.data_ptr(), radius,
-                                                     w2.data_ptr(), bias.data_ptr() if bias is not None else None, c_out,
-                                                     1 if relu else 0, out.data_ptr(), int(out.shape[1]), _lib.current_stream_ptr()))
+                                                     packed.packed.data_ptr(), c_out, 1 if relu else 0, out.data_ptr(),
+                                                     int(out.shape[1]), _lib.current_stream_ptr()))
     return out
 
 
@@ -189,10 +221,13 @@ class CorrBlock:
     def __call__(self, coords: torch.Tensor) -> torch.Tensor:
         return lookup(self.pyramid, self.layout, coords, self.radius, self.channels_last)
 
-    def lookup_conv(self, coords: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor = None, relu: bool = True,
+    def lookup_conv(self, coords: torch.Tensor, weight, bias: torch.Tensor = None, relu: bool = True,
                     out: torch.Tensor = None) -> torch.Tensor:
-        """``relu(conv1x1(self(coords)))`` without materialising the lookup tensor (see :func:`lookup_conv`)."""
-        return lookup_conv(self.pyramid, self.layout, coords, self.radius, weight, bias, relu, out)
+        """``act(conv1x1(self(coords)))`` without materialising the lookup tensor (see :func:`lookup_conv`).  ``weight``: a
+        :class:`PackedLookupConv` (what a caller inside a loop keeps), or the conv's weight tensor (packed on the spot)."""
+        if not isinstance(weight, PackedLookupConv):
+            weight = PackedLookupConv(weight, bias, self.num_levels, self.radius)
+        return lookup_conv(self.pyramid, self.layout, coords, self.radius, weight, relu, out)
 
     def lookup_conv_supported(self, c_out: int) -> bool:
         return self.pyramid.dtype == torch.bfloat16 and lookup_conv_supported(self.layout, self.radius, c_out)

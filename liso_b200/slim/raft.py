@@ -595,10 +595,16 @@ class RAFT(nn.Module):
         fuse_lookup = (bool(self.fuse_lookup_conv) and (self.fuse_lookup_conv == "always" or torch.backends.cudnn.allow_tf32)
                        and c1.kernel_size == (1, 1) and c1.stride == (1, 1) and c1.padding == (0, 0) and c1.groups == 1
                        and c1.bias is not None and correlation.lookup_conv_supported(c1.out_channels))
+        if fuse_lookup:  # tf32 weights in the kernel's shared-memory layout: packed once per weight version, kept on the module
+            from .corr import PackedLookupConv
+
+            packed_c1 = getattr(self, "_packed_c1", None)
+            if packed_c1 is None or not packed_c1.matches(c1.weight, c1.bias):
+                packed_c1 = self._packed_c1 = PackedLookupConv(c1.weight, c1.bias, m.corr_cfg.num_levels, m.corr_cfg.search_radius)
         outs = []
         for it in range(m.num_iters):
             if fuse_lookup:
-                c = correlation.lookup_conv(coords1, c1.weight, c1.bias, relu=True)
+                c = correlation.lookup_conv(coords1, packed_c1, relu=True)
             else:
                 c = conv_relu(c1, correlation(coords1))
             if merge:

@@ -210,6 +210,9 @@ def test_lookup_conv_fused_matches_oracle(cuda, B, h, w, n_out):
         assert got_dev.shape == (B, n_out, h, w) and got_dev.is_contiguous(memory_format=torch.channels_last)
         got = got_dev.cpu()
         look = O.corr_lookup(same_values, coords, 3)
+        # non-finite coordinates: grid_sample answers NaN, the kernels define "every tap outside" (= 0, the old kernel too)
+        assert not torch.isfinite(look[:, :, 3, 4]).all()
+        look[:, :, 3, 4] = 0.0
         ref, bound = _conv_ref(look, weight.reshape(n_out, 196), bias, relu)
         tol = bound + 1e-5 * scale * float(weight.abs().sum(dim=1).max()) + 1e-6
         err = (got.double() - ref).abs()
@@ -217,6 +220,7 @@ def test_lookup_conv_fused_matches_oracle(cuda, B, h, w, n_out):
         # aggregate accuracy: rms error two orders below the bound's scale (tf32 rounding is unbiased)
         assert float(err.pow(2).mean().sqrt()) < 2.0 ** -11 * float(ref.abs().max()) + 1e-6
         # and against the library's own unfused path (lookup kernel -> fp32 conv)
+        assert torch.isfinite(got).all()
         unf = torch.nn.functional.conv2d(blk(coords.to(cuda)), wd, bd)
         unf = torch.relu(unf) if relu else unf
         assert float((got_dev - unf).abs().max()) <= float(tol.max())
@@ -237,3 +241,8 @@ def test_lookup_conv_writes_channel_slice(cuda):
     assert torch.equal(wide[:, :n_out], ref) and bool((wide[:, n_out:] == 7.0).all())
     with pytest.raises(RuntimeError):
         blk.lookup_conv(coords, torch.zeros(48, 196, device=cuda), None)  # C_out must be a multiple of 32
+    packed = C.PackedLookupConv(wd, None, 4, 3)  # what a loop keeps: packed once, re-packed when the parameter changes
+    assert packed.matches(wd, None) and not packed.matches(wd.clone(), None)
+    assert torch.equal(blk.lookup_conv(coords, packed, relu=False), ref)
+    wd.mul_(2.0)
+    assert not packed.matches(wd, None)

@@ -103,8 +103,11 @@ def main():
         runs.append(("lookup gen1 nchw x6", gen(1, lambda: blk_c(coords))))
         runs.append(("lookup gen1 nchw int x6", gen(1, lambda: blk_c(grid))))
         runs.append(("lookup+conv unfused x6", gen(1, lambda: torch.cudnn_convolution_relu(blk_l(coords), wconv, bconv, (1, 1), (0, 0), (1, 1), 1))))
-        runs.append(("lookup_conv fused x6", gen(1, lambda: blk_l.lookup_conv(coords, wconv, bconv, relu=True))))
-        runs.append(("lookup_conv fused int x6", gen(1, lambda: blk_l.lookup_conv(grid, wconv, bconv, relu=True))))
+        from liso_b200.slim.corr import PackedLookupConv
+
+        packed = PackedLookupConv(wconv, bconv, 4, 3)
+        runs.append(("lookup_conv fused x6", gen(1, lambda: blk_l.lookup_conv(coords, packed, relu=True))))
+        runs.append(("lookup_conv fused int x6", gen(1, lambda: blk_l.lookup_conv(grid, packed, relu=True))))
     with torch.no_grad():
         for name, fn in runs:
             for _ in range(3):
