@@ -199,7 +199,7 @@ int slimb200_corr_lookup(const void* pyramid, int32_t pyramid_dtype, const slimb
  *   out[b, y, x, n] = act( bias[n] + sum_k weight[n, k] * lookup[b, k, y, x] ),  k = l*49 + i*7 + j as above.
  * The window values and the weights are rounded to tf32 (cvt.rna), products accumulate in fp32 on the tcgen05 tensor
  * cores -- the precision cuDNN uses for this convolution when TF32 is allowed (|err| <= 2^-10 * sum_k |w_nk| |v_k|).
- * bf16 pyramid, radius 3 and 4 levels only; c_out in {32, 64, 96, 128}.
+ * bf16 pyramid, radius 3 and 4 levels only; c_out in {32, 64, 96}.
  *
  * corr_lookup_conv_pack: once per weight tensor -- weight: device (c_out, levels*49) f32 = conv weight
  *   (c_out, levels*49, 1, 1); bias: device (c_out) f32 or NULL; packed: device, slimb200_corr_lookup_conv_packed_bytes(c_out)
@@ -215,8 +215,9 @@ int slimb200_corr_lookup_conv(const void* pyramid, int32_t pyramid_dtype, const 
                               const float* coords, int32_t radius, const void* packed, int32_t c_out, int32_t relu,
                               float* out, int32_t out_pitch, void* stream);
 
-/* Tuning hook (tools/kbench.py): 0 = first-generation radius-3 lookup kernel, 1 (default) = the (pixel, level)-per-thread
- * gather of csrc/corr_lookup2.cu for bf16 pyramids.  Returns the previous value; negative values only query. */
+/* Tuning hook (tools/kbench.py) for the radius-3 lookup on bf16 pyramids: 0 = first-generation kernel (lane = pixel, window
+ * staged in shared memory), 1 = one thread per (pixel, level), registers only (csrc/corr_lookup2.cu), 2 (default) = one
+ * thread per window row (csrc/corr_lookup3.cu).  Returns the previous value; negative values only query. */
 int slimb200_lookup_generation(int32_t generation);
 
 /* ------------------------------------------------------------------------------------------

@@ -619,12 +619,14 @@ int dispatch_radius(int radius, int out_layout, const void* pyramid, const slimb
   }
 }
 
-int g_lookup_generation = 1;
+int g_lookup_generation = 2;
 
 }  // namespace
 
-// csrc/corr_lookup2.cu
+// csrc/corr_lookup2.cu, csrc/corr_lookup3.cu
 int slimb200_lookup_v2_launch(const void* pyramid, const slimb200_corr_layout* L, const float* coords, float* out, int out_layout,
+                              cudaStream_t stream);
+int slimb200_lookup_v3_launch(const void* pyramid, const slimb200_corr_layout* L, const float* coords, float* out, int out_layout,
                               cudaStream_t stream);
 
 extern "C" int slimb200_lookup_generation(int32_t generation) {
@@ -642,7 +644,9 @@ extern "C" int slimb200_corr_lookup(const void* pyramid, int32_t pyramid_dtype, 
   if (L->rows_padded < L->h * L->w || (L->rows_padded & 127)) return SLIMB200_E_INVALID;
   if (reinterpret_cast<uintptr_t>(pyramid) & 15) return SLIMB200_E_ALIGNMENT;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (pyramid_dtype == SLIMB200_DTYPE_BF16 && radius == 3 && g_lookup_generation >= 1)
+  if (pyramid_dtype == SLIMB200_DTYPE_BF16 && radius == 3 && g_lookup_generation >= 2)
+    return slimb200_lookup_v3_launch(pyramid, L, coords, out, out_layout, stream);
+  if (pyramid_dtype == SLIMB200_DTYPE_BF16 && radius == 3 && g_lookup_generation == 1)
     return slimb200_lookup_v2_launch(pyramid, L, coords, out, out_layout, stream);
   if (pyramid_dtype == SLIMB200_DTYPE_BF16) return dispatch_radius<__nv_bfloat16>(radius, out_layout, pyramid, L, coords, out, stream);
   if (pyramid_dtype == SLIMB200_DTYPE_F32) return dispatch_radius<float>(radius, out_layout, pyramid, L, coords, out, stream);

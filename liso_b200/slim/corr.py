@@ -116,7 +116,7 @@ class PackedLookupConv:
             bias = bias.detach().contiguous()
         n_bytes = int(lib.slimb200_corr_lookup_conv_packed_bytes(self.c_out))
         if n_bytes == 0:
-            raise RuntimeError("slimb200_corr_lookup_conv: C_out must be 32, 64, 96 or 128 (got %d)" % self.c_out)
+            raise RuntimeError("slimb200_corr_lookup_conv: C_out must be 32, 64 or 96 (got %d)" % self.c_out)
         self.levels, self.radius = levels, radius
         self.packed = torch.empty(n_bytes, dtype=torch.uint8, device=weight.device)
         _lib.check(lib.slimb200_corr_lookup_conv_pack(w2.data_ptr(), bias.data_ptr() if bias is not None else None, levels, radius,
@@ -165,7 +165,7 @@ def lookup_conv(pyramid: torch.Tensor, L: _lib.CorrLayout, coords: torch.Tensor,
 
 
 def lookup_conv_supported(L: _lib.CorrLayout, radius: int, c_out: int) -> bool:
-    return radius == 3 and L.levels == 4 and c_out in (32, 64, 96, 128)
+    return radius == 3 and L.levels == 4 and c_out in (32, 64, 96)
 
 
 def pack_pyramid_f32(levels: List[torch.Tensor], L: _lib.CorrLayout) -> torch.Tensor:

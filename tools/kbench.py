@@ -94,7 +94,7 @@ def main():
                     for _ in range(6):
                         state["out"] = fn()
                 finally:
-                    lib.slimb200_lookup_generation(1)
+                    lib.slimb200_lookup_generation(2)
             return run
 
         runs.append(("lookup gen0 nhwc x6", gen(0, lambda: blk_l(coords))))
@@ -102,12 +102,21 @@ def main():
         runs.append(("lookup gen0 nchw x6", gen(0, lambda: blk_c(coords))))
         runs.append(("lookup gen1 nchw x6", gen(1, lambda: blk_c(coords))))
         runs.append(("lookup gen1 nchw int x6", gen(1, lambda: blk_c(grid))))
-        runs.append(("lookup+conv unfused x6", gen(1, lambda: torch.cudnn_convolution_relu(blk_l(coords), wconv, bconv, (1, 1), (0, 0), (1, 1), 1))))
+        runs.append(("lookup gen2 nhwc x6", gen(2, lambda: blk_l(coords))))
+        runs.append(("lookup gen2 nchw x6", gen(2, lambda: blk_c(coords))))
+        runs.append(("lookup gen2 nchw int x6", gen(2, lambda: blk_c(grid))))
+        # a smooth flow field (what the network asks for): neighbouring pixels look up neighbouring windows
+        smooth = (coords_grid(B, h, w, dev) + 4.0 * F.interpolate(torch.randn(B, 2, 5, 5, generator=g).to(dev), size=(h, w),
+                                                                    mode="bicubic", align_corners=True)).contiguous()
+        runs.append(("lookup gen2 nchw smooth x6", gen(2, lambda: blk_c(smooth))))
+        runs.append(("lookup gen0 nchw smooth x6", gen(0, lambda: blk_c(smooth))))
+        runs.append(("lookup+conv unfused x6", gen(2, lambda: torch.cudnn_convolution_relu(blk_l(coords), wconv, bconv, (1, 1), (0, 0), (1, 1), 1))))
         from liso_b200.slim.corr import PackedLookupConv
 
         packed = PackedLookupConv(wconv, bconv, 4, 3)
-        runs.append(("lookup_conv fused x6", gen(1, lambda: blk_l.lookup_conv(coords, packed, relu=True))))
-        runs.append(("lookup_conv fused int x6", gen(1, lambda: blk_l.lookup_conv(grid, packed, relu=True))))
+        runs.append(("lookup_conv fused x6", gen(2, lambda: blk_l.lookup_conv(coords, packed, relu=True))))
+        runs.append(("lookup_conv fused int x6", gen(2, lambda: blk_l.lookup_conv(grid, packed, relu=True))))
+        runs.append(("lookup_conv fused smooth x6", gen(2, lambda: blk_l.lookup_conv(smooth, packed, relu=True))))
     with torch.no_grad():
         for name, fn in runs:
             for _ in range(3):
