@@ -118,7 +118,7 @@ __device__ __forceinline__ float wel(const uint32_t (&w)[NW], int c) {  // windo
 }
 
 // fully predicated 4-tap sample straight from global memory (rare path)
-__device__ __noinline__ float sample_slow2(const __nv_bfloat16* __restrict__ base, int panel_stride, int W, int H, int off, float ix,
+static __device__ __noinline__ float sample_slow2(const __nv_bfloat16* __restrict__ base, int panel_stride, int W, int H, int off, float ix,
                                            float iy) {
   const float fx = floorf(ix), fy = floorf(iy);
   const int x0 = (int)fx, y0 = (int)fy;
