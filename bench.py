@@ -172,6 +172,8 @@ def main():
                          "reported as `export_with_writer`, never as the headline")
     ap.add_argument("--memory-format", default="channels_last", choices=["channels_last", "contiguous"],
                     help="memory format of the canvas our encoder emits and of the stock convs that consume it")
+    ap.add_argument("--no-fused-lookup", action="store_true",
+                    help="lookup kernel + stock 1x1 convolution instead of the fused slimb200_corr_lookup_conv (SURVEY 8f.2)")
     ap.add_argument("--profile-one-step", action="store_true",
                     help="bracket ONE resident step with cudaProfilerStart/Stop (for `ncu --profile-from-start off`) and exit")
     args = ap.parse_args()
@@ -248,6 +250,7 @@ def main():
     if args.memory_format == "channels_last":
         model = model.to(memory_format=torch.channels_last)
     model.raft_network.use_cuda_graph = not args.no_cuda_graph
+    model.raft_network.fuse_lookup_conv = not args.no_fused_lookup
 
     # pairs of this rank: global pair indices sharded by the reference's modulo rule
     from liso_b200.slim.export import reduce_counters, shard_indices

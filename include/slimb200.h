@@ -216,8 +216,8 @@ int slimb200_corr_lookup_conv(const void* pyramid, int32_t pyramid_dtype, const 
                               float* out, int32_t out_pitch, void* stream);
 
 /* Tuning hook (tools/kbench.py) for the radius-3 lookup on bf16 pyramids: 0 = first-generation kernel (lane = pixel, window
- * staged in shared memory), 1 = one thread per (pixel, level), registers only (csrc/corr_lookup2.cu), 2 (default) = one
- * thread per window row (csrc/corr_lookup3.cu).  Returns the previous value; negative values only query. */
+ * staged in shared memory), 1 (default) = one thread per (pixel, level), registers only (csrc/corr_lookup2.cu), 2 = one
+ * thread per window row (csrc/corr_lookup3.cu; the fused lookup + convolution is built on it).  Returns the previous value; negative values only query. */
 int slimb200_lookup_generation(int32_t generation);
 
 /* ------------------------------------------------------------------------------------------

@@ -619,7 +619,7 @@ int dispatch_radius(int radius, int out_layout, const void* pyramid, const slimb
   }
 }
 
-int g_lookup_generation = 2;
+int g_lookup_generation = 1;
 
 }  // namespace
 

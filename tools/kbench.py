@@ -94,7 +94,7 @@ def main():
                     for _ in range(6):
                         state["out"] = fn()
                 finally:
-                    lib.slimb200_lookup_generation(2)
+                    lib.slimb200_lookup_generation(1)
             return run
 
         runs.append(("lookup gen0 nhwc x6", gen(0, lambda: blk_l(coords))))

@@ -35,7 +35,7 @@ def main():
             if "gen0" in which:
                 lib.slimb200_lookup_generation(0)
                 blk_l(coords)
-                lib.slimb200_lookup_generation(2)
+                lib.slimb200_lookup_generation(1)
     torch.cuda.synchronize()
 
 
