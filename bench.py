@@ -251,6 +251,9 @@ def main():
         model = model.to(memory_format=torch.channels_last)
     model.raft_network.use_cuda_graph = not args.no_cuda_graph
     model.raft_network.fuse_lookup_conv = not args.no_fused_lookup
+    # the resident loop reads each step's outputs before the next forward: views of the graph's static buffers are enough
+    # (SLIM's default returns copies the caller may keep across forwards; ExportPipeline, the e2e path, sets this itself)
+    model.outputs_alias_static_buffers = True
 
     # pairs of this rank: global pair indices sharded by the reference's modulo rule
     from liso_b200.slim.export import reduce_counters, shard_indices

@@ -27,10 +27,11 @@ def preprocess_params(cfg, c_in: int = 4, cone_angle_deg: float = 0.8) -> _lib.P
     cone_z = float(ghm["ground_threshold"]) if ghm is not None and "ground_threshold" in ghm else -1.5  # liso_config.yml:113-114
     p.cone_z_threshold = float(np.float32(cone_z))
     p.cone_tan = float(np.float32(np.tan(cone_angle_deg / 180.0 * np.pi)))
-    p.range_x, p.range_y = float(cfg.data.bev_range_m[0]), float(cfg.data.bev_range_m[1])
+    # the dataset keeps bev_range_m as a float32 array (utils/bev_utils.py:42) before it is widened to float64
+    p.range_x, p.range_y = float(np.float32(cfg.data.bev_range_m[0])), float(np.float32(cfg.data.bev_range_m[1]))
     p.grid_x, p.grid_y = int(cfg.data.img_grid_size[0]), int(cfg.data.img_grid_size[1])
     hr = cfg.data.get("pillar_height_range_m", (-2.0, 1.0)) if hasattr(cfg.data, "get") else (-2.0, 1.0)
-    p.z_min, p.z_max = float(hr[0]), float(hr[1])
+    p.z_min, p.z_max = float(np.float32(hr[0])), float(np.float32(hr[1]))  # float32 array (torch_dataset_commons.py:499-501)
     p.c_in = c_in
     return p
 

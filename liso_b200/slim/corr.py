@@ -110,16 +110,17 @@ class PackedLookupConv:
         if w2.shape[1] != n_ch or w2.dtype != torch.float32:
             raise ValueError("weight must be fp32 (C_out, %d[, 1, 1])" % n_ch)
         w2 = w2.contiguous()
+        b1 = None
         if bias is not None:
             if bias.numel() != self.c_out or bias.dtype != torch.float32:
                 raise ValueError("bias must be fp32 (C_out)")
-            bias = bias.detach().contiguous()
+            b1 = bias.detach().contiguous()
         n_bytes = int(lib.slimb200_corr_lookup_conv_packed_bytes(self.c_out))
         if n_bytes == 0:
             raise RuntimeError("slimb200_corr_lookup_conv: C_out must be 32, 64 or 96 (got %d)" % self.c_out)
         self.levels, self.radius = levels, radius
         self.packed = torch.empty(n_bytes, dtype=torch.uint8, device=weight.device)
-        _lib.check(lib.slimb200_corr_lookup_conv_pack(w2.data_ptr(), bias.data_ptr() if bias is not None else None, levels, radius,
+        _lib.check(lib.slimb200_corr_lookup_conv_pack(w2.data_ptr(), b1.data_ptr() if b1 is not None else None, levels, radius,
                                                       self.c_out, self.packed.data_ptr(), _lib.current_stream_ptr()))
         self._src = (weakref.ref(weight), weight._version, None if bias is None else weakref.ref(bias),
                      None if bias is None else bias._version)

@@ -171,6 +171,8 @@ class ExportPipeline:
         """``depth``: batches the host may run ahead of the results it has consumed (number of upload / download
         slots); >= 2.  A deeper pipeline absorbs host-side hiccups (the launch thread is the critical resource)."""
         self.model, self.device = model, device
+        if hasattr(model, "outputs_alias_static_buffers"):
+            model.outputs_alias_static_buffers = True  # this loop takes its own packed copies of what it exports (see run)
         self.copy_stream = torch.cuda.Stream(device=device)
         self.amp_ctx = amp_ctx
         self.depth = max(2, int(depth))

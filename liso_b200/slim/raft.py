@@ -7,6 +7,7 @@ reference checkpoint loads with ``strict=True`` (``experiment.py:221-223``).
 """
 from __future__ import annotations
 
+import weakref
 from typing import List
 
 import numpy as np
@@ -31,40 +32,54 @@ def _lib_mod():
 FAST_STOCK_OPS = True
 
 
-_PARAM_CAST_CACHE = {}  # derived copies of parameters, keyed by storage + version (inference only)
+def _derived(owner: nn.Module, key, sources, build):
+    """A tensor derived from parameters (a cast, a concatenation, stacked or tap weights), cached ON the module that owns
+    the sources (inference only).  An entry is valid for exactly these tensor OBJECTS (weak references, not addresses: a
+    freed model's parameters may be re-allocated at the same address with the same version) in their current version and
+    storage; it dies with the module."""
+    cache = owner.__dict__.setdefault("_slimb200_derived", {})
+    sig = tuple((s._version, s.data_ptr(), s.device, tuple(s.stride())) for s in sources)
+    ent = cache.get(key)
+    if ent is not None and ent[1] == sig and len(ent[0]) == len(sources) and all(r() is s for r, s in zip(ent[0], sources)):
+        return ent[2]
+    val = build()
+    cache[key] = (tuple(weakref.ref(s) for s in sources), sig, val)
+    return val
 
 
-def _cache_put(key, value):
-    if len(_PARAM_CAST_CACHE) > 256:  # entries of overwritten parameter versions are never hit again
-        _PARAM_CAST_CACHE.clear()
-    _PARAM_CAST_CACHE[key] = value
-    return value
+def _derived_values(root: nn.Module):
+    """Every derived tensor currently cached below `root` (a captured CUDA graph points at them)."""
+    out = []
+    for mod in root.modules():
+        for ent in mod.__dict__.get("_slimb200_derived", {}).values():
+            out.append(ent[2])
+    return out
 
 
-def _autocast_param(t, dtype):
+def _autocast_param(owner: nn.Module, name: str, t, dtype):
     """Low-precision copy of a parameter, cached like autocast caches its weight casts (inference only)."""
     if t is None:
         return None
-    key = (t.data_ptr(), t._version, dtype, tuple(t.stride()))
-    hit = _PARAM_CAST_CACHE.get(key)
-    if hit is None:
+
+    def build():
         hit = t.detach().to(dtype)
         if t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last):
             hit = hit.contiguous(memory_format=torch.channels_last)
-        _cache_put(key, hit)
-    return hit
+        return hit
+
+    return _derived(owner, ("cast", name, dtype), (t,), build)
 
 
-def _cat_params(ts):
-    """dim-0 concatenation of parameters, cached (inference only; keyed by storage + version)."""
-    key = tuple((t.data_ptr(), t._version) for t in ts)
-    hit = _PARAM_CAST_CACHE.get(key)
-    if hit is None:
+def _cat_params(owner: nn.Module, name: str, ts):
+    """dim-0 concatenation of parameters, cached on `owner` (inference only)."""
+
+    def build():
         hit = torch.cat([t.detach() for t in ts], dim=0)
         if hit.dim() == 4 and ts[0].is_contiguous(memory_format=torch.channels_last) and not ts[0].is_contiguous():
             hit = hit.contiguous(memory_format=torch.channels_last)
-        _cache_put(key, hit)
-    return hit
+        return hit
+
+    return _derived(owner, ("cat", name), tuple(ts), build)
 
 
 def conv_relu(conv: nn.Conv2d, x: torch.Tensor, weight: torch.Tensor = None, bias: torch.Tensor = None) -> torch.Tensor:
@@ -73,7 +88,8 @@ def conv_relu(conv: nn.Conv2d, x: torch.Tensor, weight: torch.Tensor = None, bia
     if FAST_STOCK_OPS and x.is_cuda and conv.padding_mode == "zeros" and not torch.is_grad_enabled():
         if torch.is_autocast_enabled():  # the fused op is not on autocast's cast list
             dt = torch.get_autocast_dtype("cuda")
-            x, w, b = x.to(dt), _autocast_param(w, dt), _autocast_param(b, dt)
+            tag = "own" if weight is None else "override"
+            x, w, b = x.to(dt), _autocast_param(conv, tag + ".w", w, dt), _autocast_param(conv, tag + ".b", b, dt)
         if x.dtype == w.dtype:
             return torch.cudnn_convolution_relu(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
     return F.relu(F.conv2d(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups))
@@ -88,10 +104,9 @@ def _stacked_params(a: nn.Conv2d, b: nn.Conv2d, shared_input: bool, pad_in_to: i
     """Weight / bias of ONE convolution that evaluates the parallel convolutions ``a`` and ``b`` (same geometry): outputs
     stacked [a | b]; with ``shared_input`` both read the same tensor, otherwise the input is the channel concatenation
     [in_a | in_b] (zero-padded to ``pad_in_to`` channels) and the weight is block-diagonal (the zero blocks add exact
-    zeros).  Cached like `_cat_params`."""
-    key = ("stacked", shared_input, pad_in_to) + tuple((t.data_ptr(), t._version) for t in (a.weight, a.bias, b.weight, b.bias))
-    hit = _PARAM_CAST_CACHE.get(key)
-    if hit is None:
+    zeros).  Cached on ``a`` like `_cat_params`."""
+
+    def build():
         wa, wb = a.weight.detach(), b.weight.detach()
         if shared_input:
             w = torch.cat([wa, wb], dim=0)
@@ -101,8 +116,9 @@ def _stacked_params(a: nn.Conv2d, b: nn.Conv2d, shared_input: bool, pad_in_to: i
             w[wa.shape[0]:, wa.shape[1]:wa.shape[1] + wb.shape[1]] = wb
         if wa.is_contiguous(memory_format=torch.channels_last) and not wa.is_contiguous():
             w = w.contiguous(memory_format=torch.channels_last)
-        hit = _cache_put(key, (w, torch.cat([a.bias.detach(), b.bias.detach()], dim=0)))
-    return hit
+        return w, torch.cat([a.bias.detach(), b.bias.detach()], dim=0)
+
+    return _derived(a, ("stacked", shared_input, pad_in_to), (a.weight, a.bias, b.weight, b.bias), build)
 
 
 def instance_norm_nhwc(norm: nn.InstanceNorm2d, x: torch.Tensor, relu: bool, residual: torch.Tensor = None,
@@ -260,8 +276,8 @@ class ConvGRU(nn.Module):
         hx = torch.cat([h, x], dim=1)
         if FAST_STOCK_OPS and hx.is_cuda and not torch.is_grad_enabled():
             # the update and reset gates read the same input: one 192-channel convolution instead of two
-            w = _cat_params((self.convz.weight, self.convr.weight))
-            b = _cat_params((self.convz.bias, self.convr.bias))
+            w = _cat_params(self, "zr.weight", (self.convz.weight, self.convr.weight))
+            b = _cat_params(self, "zr.bias", (self.convz.bias, self.convr.bias))
             z, r = torch.sigmoid(F.conv2d(hx, w, b, padding=1)).split(self.convz.out_channels, dim=1)
         else:
             z = torch.sigmoid(self.convz(hx))
@@ -398,7 +414,7 @@ class RAFT(nn.Module):
         # update or re-allocation of a parameter invalidates the graph.
         B = len(pcl_t0)
         wsig = tuple((p.data_ptr(), p._version) for mod in (self.fnet, self.cnet, self.update_block) for p in mod.parameters())
-        key = (B, self.output_iterations, self.pp_layer.canvas_memory_format, str(dev), torch.backends.cudnn.allow_tf32,
+        key = (B, self.output_iterations, self.pp_layer.canvas_memory_format, str(dev), torch.backends.cudnn.allow_tf32, self.training,
                self.fused_update_block, self.merge_parallel_convs, self.tap_heads, self.concurrent_directions, FAST_STOCK_OPS,
                self.fuse_lookup_conv,
                self.output_sink is not None, self.graph_extra_key, wsig)
@@ -419,8 +435,23 @@ class RAFT(nn.Module):
     def will_use_graph(self, pcl_t0, pcl_t1) -> bool:
         dev = pcl_t0[0].device
         return (self.use_cuda_graph and FAST_STOCK_OPS and dev.type == "cuda" and not torch.is_grad_enabled()
-                and not self.training and not torch.cuda.is_current_stream_capturing()
+                and not (self.training and self._graphed_part_depends_on_training_mode())
+                and not torch.cuda.is_current_stream_capturing()
                 and len(pcl_t0) == len(pcl_t1) and hasattr(self.pp_layer, "empty_outputs"))
+
+    def _graphed_part_depends_on_training_mode(self) -> bool:
+        """The reference's flow export never calls ``model.eval()`` (``experiment.py:164-198,225-361``): it runs in train
+        mode under ``no_grad``.  The only train-mode-dependent layer of the released configuration is the pillar encoder's
+        BatchNorm1d (batch statistics + running-stat update) -- and the pillar encoder runs in front of the graph.  The
+        graph itself (encoders, pyramids, GRU loops) is mode-independent unless it holds an active Dropout or a norm with
+        running statistics."""
+        for mod in (self.fnet, self.cnet, self.update_block):
+            for sub in mod.modules():
+                if isinstance(sub, (nn.Dropout, nn.Dropout2d, nn.Dropout3d)) and sub.p > 0:
+                    return True
+                if isinstance(sub, nn.modules.batchnorm._NormBase) and sub.track_running_stats:
+                    return True
+        return False
 
     def _net_body(self, img_t0, img_t1, occupancies=(None, None)):
         """Feature encoders, correlation pyramids, context encoders and both refinement loops (raft_mod.py:82-257)."""
@@ -491,7 +522,7 @@ class RAFT(nn.Module):
             st["outs"] = self._net_body(img_t0, img_t1, occ)
         st["launches"] = int(lib.load().slimb200_launch_count(-1) - n0)  # library kernels inside one replay
         st["graph"] = graph
-        st["keepalive"] = list(_PARAM_CAST_CACHE.values())  # derived weights the captured kernels point at
+        st["keepalive"] = _derived_values(self) + [getattr(self, "_packed_c1", None)]  # derived weights the captured kernels point at
         self._graphs["net"] = st
         self.n_graph_captures = getattr(self, "n_graph_captures", 0) + 1
 
@@ -555,8 +586,8 @@ class RAFT(nn.Module):
         hx[:, :Ch].copy_(net)
         hx[:, Ch:Ch + Cx].copy_(inp)
         rhx[:, Ch:Ch + Cx].copy_(inp)
-        w_zr = _cat_params((gru.convz.weight, gru.convr.weight))
-        b_zr = _cat_params((gru.convz.bias, gru.convr.bias))
+        w_zr = _cat_params(gru, "zr.weight", (gru.convz.weight, gru.convr.weight))
+        b_zr = _cat_params(gru, "zr.bias", (gru.convz.bias, gru.convr.bias))
         fh, lh = ub.static_flow_head, ub.classification_head
         coords1 = coords_grid(batch, h, w, device).contiguous()
         flow = torch.zeros((batch, 2, h, w), dtype=torch.float32, device=device)
@@ -587,10 +618,9 @@ class RAFT(nn.Module):
             w_taps = None
             if (self.tap_heads and fh.conv2.kernel_size == (k, k) and fh.conv2.stride == (1, 1) and fh.conv2.dilation == (1, 1)
                     and fh.conv2.padding == (k // 2, k // 2) and k % 2 == 1 and k <= 7):
-                key = ("taps", w_h2.data_ptr(), fh.conv2.weight._version, lh.conv2.weight._version)
-                w_taps = _PARAM_CAST_CACHE.get(key)
-                if w_taps is None:  # W1[(ky*k + kx)*6 + c][cin] = W[c][cin][ky][kx]
-                    w_taps = _cache_put(key, w_h2.permute(2, 3, 0, 1).reshape(k * k * w_h2.shape[0], w_h2.shape[1], 1, 1).contiguous())
+                # W1[(ky*k + kx)*6 + c][cin] = W[c][cin][ky][kx]
+                w_taps = _derived(fh.conv2, ("taps",), (fh.conv2.weight, lh.conv2.weight),
+                                  lambda: w_h2.permute(2, 3, 0, 1).reshape(k * k * w_h2.shape[0], w_h2.shape[1], 1, 1).contiguous())
         c1 = me.conv_stat_corr1
         fuse_lookup = (bool(self.fuse_lookup_conv) and (self.fuse_lookup_conv == "always" or torch.backends.cudnn.allow_tf32)
                        and c1.kernel_size == (1, 1) and c1.stride == (1, 1) and c1.padding == (0, 0) and c1.groups == 1

@@ -17,7 +17,6 @@ from typing import Dict, List
 
 import numpy as np
 import torch
-import torch.nn.functional as F
 from torch import nn
 
 from ..config import AttrDict
@@ -33,6 +32,17 @@ def get_network_input_pcls(cfg, sample_data, time_key: str, to_device=None) -> L
     if to_device:
         return [el.to(to_device, non_blocking=True) for el in sample_data[key]]
     return sample_data[key]
+
+
+def _cfg_get(cfg, path, default=False):
+    """cfg.a.b.c for attribute- or item-style configs; `default` when a key is missing."""
+    cur = cfg
+    for k in path:
+        try:
+            cur = cur[k] if isinstance(cur, dict) else getattr(cur, k)
+        except (KeyError, AttributeError):
+            return default
+    return cur
 
 
 class MovingAverageThreshold(nn.Module):
@@ -70,31 +80,6 @@ class MovingAverageThreshold(nn.Module):
         return self.start_value
 
 
-def _grid_to_points(grid, coors, valid, default):
-    """``batched_grid_data_to_pointwise_data`` (``static_aggregation.py:8-31``), without mutating ``coors``."""
-    coors = torch.where(valid[..., None], coors, torch.zeros_like(coors)).long()
-    bidx = torch.arange(valid.shape[0], device=grid.device)[:, None].expand(-1, valid.shape[1])
-    out = grid[bidx, coors[..., 0], coors[..., 1]]
-    return torch.where(valid[..., None], out, torch.full_like(out, default))
-
-
-def _weighted_kabsch(cloud_t0, cloud_t1, weights):
-    """``weighted_pc_alignment.py:10-80`` (no epsilon) + ``torch_symm_ortho`` (U @ Vh, no det fix)."""
-    not_enough = (weights > 0).sum() < 3
-    weights = torch.where(not_enough, weights + 1e-7, weights)
-    cum = weights.sum(dim=-1)
-    mx = (cloud_t0 * weights[..., None]).sum(dim=0) / cum
-    my = (cloud_t1 * weights[..., None]).sum(dim=0) / cum
-    S = ((cloud_t1 - my[None]) * weights[..., None]).T @ (cloud_t0 - mx[None]) / cum
-    U, _, Vh = torch.linalg.svd(S.to(torch.double))
-    R = U @ Vh
-    t = my.to(torch.double) - R @ mx.to(torch.double)
-    T = torch.eye(4, dtype=torch.double, device=R.device)
-    T[:3, :3] = R
-    T[:3, 3] = t
-    return T, not_enough
-
-
 class HeadDecoder(nn.Module):
     def __init__(self, cfg, name, bev_extent):
         super().__init__()
@@ -105,6 +90,15 @@ class HeadDecoder(nn.Module):
         if not (om.disappearing_logit is False and om.static_logit == "net" and om.dynamic_logit == "net"
                 and om.ground_logit is False and om.static_flow == "net" and om.dynamic_flow == "net"):
             raise NotImplementedError("only the released SLIM output_modification is implemented")
+        # switches of the reference decoder that change its arithmetic (head_decoder.py:463-480, static_aggregation.py:62-68):
+        # the fused kernel implements the released setting only -- anything else must fail loudly, not decode differently
+        flags = {"model.use_static_aggr_flow_for_aggr_flow": _cfg_get(cfg, ("model", "use_static_aggr_flow_for_aggr_flow")),
+                 "model.dynamic_flow_is_non_rigid_flow": _cfg_get(cfg, ("model", "dynamic_flow_is_non_rigid_flow")),
+                 "losses.unsupervised.use_epsilon_for_weighted_pc_alignment":
+                     _cfg_get(cfg, ("losses", "unsupervised", "use_epsilon_for_weighted_pc_alignment"))}
+        for name, value in flags.items():
+            if value:
+                raise NotImplementedError("SLIM.%s = %r: only False (the released configuration) is implemented" % (name, value))
 
     def concat2network_output(self, *, logits, static_flow, dynamic_flow, weight_logits_for_static_aggregation=None):
         assert weight_logits_for_static_aggregation is None
@@ -112,13 +106,11 @@ class HeadDecoder(nn.Module):
 
     def forward(self, network_output, dynamicness_threshold, *, pc, pointwise_voxel_coordinates, pointwise_valid_mask,
                 filled_pillar_mask, odom=None, inv_odom=None, summaries=None, static_aggregation: bool = True, **_):
-        if network_output.is_cuda:
-            return self._forward_fused(network_output, dynamicness_threshold, pc, pointwise_voxel_coordinates,
-                                       pointwise_valid_mask, filled_pillar_mask, static_aggregation)
-        return self._forward_torch(network_output, dynamicness_threshold, pc=pc,
-                                   pointwise_voxel_coordinates=pointwise_voxel_coordinates,
-                                   pointwise_valid_mask=pointwise_valid_mask, filled_pillar_mask=filled_pillar_mask,
-                                   static_aggregation=static_aggregation)
+        from .. import _lib
+
+        _lib.require_cuda(network_output, pc, pointwise_voxel_coordinates, pointwise_valid_mask, filled_pillar_mask)  # no CPU path
+        return self._forward_fused(network_output, dynamicness_threshold, pc, pointwise_voxel_coordinates,
+                                   pointwise_valid_mask, filled_pillar_mask, static_aggregation)
 
     def _forward_fused(self, o, thr, pc, coors, valid, filled, static_aggregation):
         """One call into ``slimb200_head_decode``: five launches, no host sync; the tensors of the
@@ -160,6 +152,12 @@ class HeadDecoder(nn.Module):
             C.byref(p), bev.data_ptr(), aggr.data_ptr() if aggr is not None else None, cls.data_ptr(), pts.data_ptr(),
             trafo.data_ptr(), nep.data_ptr(),
             ws.data_ptr(), ws.numel(), _lib.current_stream_ptr()))
+        return self._assemble(bev, aggr, cls, pts, trafo, nep, thr, static_aggregation)
+
+    @staticmethod
+    def _assemble(bev, aggr, cls, pts, trafo, nep, thr, static_aggregation):
+        """The reference's result structure as channel slices of the kernel's packed buffers (kept in `_packed`)."""
+        dev, B = bev.device, bev.shape[0]
         clsb = cls.view(torch.bool)
         md = AttrDict()
         md.disappearing_logit = bev[..., 0:1]
@@ -184,72 +182,7 @@ class HeadDecoder(nn.Module):
         else:
             ret.not_enough_points = torch.zeros((B,), dtype=torch.bool, device=dev)
         ret.modified_network_output = md
-        return ret
-
-    def _forward_torch(self, network_output, dynamicness_threshold, *, pc, pointwise_voxel_coordinates, pointwise_valid_mask,
-                       filled_pillar_mask, static_aggregation: bool = True):
-        """Stock-PyTorch restatement (CPU tensors, host-logic tests)."""
-        fs = self.cfg.model.u_net.final_scale
-        coors = torch.div(pointwise_voxel_coordinates, fs, rounding_mode="trunc")
-        filled = filled_pillar_mask[..., None]
-        o = network_output
-        static_logit, dynamic_logit = o[..., 1:2], o[..., 2:3]
-        ones = torch.ones_like(static_logit)
-        # ground "off": global min of the live logits - 100 (head_decoder.py:919-935), before masking
-        ground_logit = torch.min(torch.cat([static_logit, dynamic_logit], dim=0)) - 100.0 * ones
-        neg = -100.0 * ones
-        md = AttrDict()
-        md.disappearing_logit = neg
-        md.static_logit = torch.where(filled, static_logit, 0.0 * ones)
-        md.dynamic_logit = torch.where(filled, dynamic_logit, neg)
-        md.ground_logit = torch.where(filled, ground_logit, neg)
-        md.static_flow = torch.where(filled, o[..., 4:6], torch.zeros_like(o[..., 4:6]))
-        md.dynamic_flow = torch.where(filled, o[..., 6:8], torch.zeros_like(o[..., 6:8]))
-        md.class_logits = torch.cat([md.static_logit, md.dynamic_logit, md.ground_logit], dim=-1)
-        md.class_probs = F.softmax(md.class_logits, dim=-1)
-        md.staticness, md.dynamicness, md.groundness = (md.class_probs[..., k] for k in range(3))
-        md.is_dynamic = md.dynamicness >= dynamicness_threshold
-        md.is_static = (md.staticness >= md.groundness) & (~md.is_dynamic)
-        md.is_ground = ~(md.is_static | md.is_dynamic)
-
-        zeros1 = torch.zeros_like(md.static_flow[..., :1])
-        static3 = torch.cat([md.static_flow, zeros1], dim=-1)
-        dynamic3 = torch.cat([md.dynamic_flow, zeros1], dim=-1)
-        valid = pointwise_valid_mask
-        ret = AttrDict()
-        ret.static_flow = _grid_to_points(static3, coors, valid, 0.0)
-        ret.dynamic_flow = _grid_to_points(dynamic3, coors, valid, 0.0)
-        ret.dynamicness = _grid_to_points(md.dynamicness[..., None], coors, valid, 0.0)[..., 0]
-        ret.staticness = _grid_to_points(md.staticness[..., None], coors, valid, 0.0)[..., 0]
-        aggregated = torch.where(md.is_static[..., None], static3, dynamic3 * (1.0 - md.groundness[..., None]))
-        ret.aggregated_flow = _grid_to_points(aggregated, coors, valid, 0.0)
-        ret.dense_maps = AttrDict(aggregated_flow=aggregated, static_flow=static3)
-        ret.dynamicness_threshold = dynamicness_threshold
-        if static_aggregation:
-            weight_map = md.staticness * filled[..., 0].float()
-            pt_w = _grid_to_points(weight_map[..., None], coors, valid, 0.0)[..., 0]
-            shape = o.shape[1:3]
-            ext = np.asarray(self.bev_extent, dtype=np.float64)
-            ctr = np.stack(np.meshgrid(np.arange(shape[0]), np.arange(shape[1]), indexing="ij"), axis=-1) + 0.5
-            ctr = ctr / np.asarray(shape) * (ext[2:] - ext[:2]) + ext[:2]
-            grid_h = torch.from_numpy(
-                np.concatenate([ctr, np.zeros_like(ctr[..., :1]), np.ones_like(ctr[..., :1])], axis=-1)).to(o.device)
-            flows, Ts, neps = [], [], []
-            eye = torch.eye(4, dtype=torch.float64, device=o.device)
-            for b in range(o.shape[0]):
-                m = valid[b]
-                T, nep = _weighted_kabsch(pc[b][m][..., :3], (pc[b][..., :3] + ret.static_flow[b])[m], pt_w[b][m])
-                flows.append(torch.einsum("ij,hwj->hwi", T - eye, grid_h)[..., 0:2].float())
-                Ts.append(T)
-                neps.append(nep)
-            md.static_aggr_flow = torch.stack(flows, 0)
-            md.masked_static_aggr_flow = torch.where(filled, md.static_aggr_flow, torch.zeros_like(md.static_aggr_flow))
-            ret.static_aggr_flow = _grid_to_points(torch.cat([md.static_aggr_flow, zeros1], dim=-1), coors, valid, 0.0)
-            ret.static_aggr_trafo = torch.stack(Ts, 0)
-            ret.not_enough_points = torch.stack(neps, 0)
-        else:
-            ret.not_enough_points = torch.zeros((o.shape[0],), dtype=torch.bool, device=o.device)
-        ret.modified_network_output = md
+        ret._packed = (bev, aggr, cls, pts, trafo, nep, static_aggregation)
         return ret
 
 
@@ -272,6 +205,12 @@ class SLIM(nn.Module):
         self.static_aggregation = static_aggregation
         # decode each network output as soon as it exists (a side branch of the CUDA graph) instead of after the network
         self.decode_as_sink = True
+        # In CUDA-graph mode the decoded outputs live in the graph's static buffers, which the NEXT forward overwrites.
+        # False (default): forward returns copies the caller may keep -- the reference's export holds the t0->t1 predictions
+        # across two further model() calls (experiment.py:386-456).  True: forward returns views of the static buffers, valid
+        # until the next forward (no copy of ~0.4 GB per decoded iteration); `ExportPipeline` works this way and takes packed
+        # copies of the four tensors it exports.
+        self.outputs_alias_static_buffers = False
         self._dec_static, self._dec_ctx, self._dec_n, self._sink_preds = {}, {}, {}, {}
         self._graph_preds = None  # (graph key, decoded static outputs of the captured pass)
 
@@ -347,8 +286,13 @@ class SLIM(nn.Module):
 
     _POINTWISE = ("static_flow", "dynamic_flow", "dynamicness", "staticness", "aggregated_flow", "static_aggr_flow")
 
-    def _present(self, ret, n_points: int, thr):
-        """The prediction with its point-wise tensors cut to the real number of points (graph mode pads to capacity)."""
+    def _present(self, ret, n_points: int, thr, copy: bool = False):
+        """The prediction with its point-wise tensors cut to the real number of points (graph mode pads to capacity);
+        `copy`: on private copies of the packed buffers instead of views of the graph's static outputs."""
+        if copy:
+            bev, aggr, cls, pts, trafo, nep, sa = ret._packed
+            ret = HeadDecoder._assemble(bev.clone(), aggr.clone() if aggr is not None else None, cls.clone(), pts.clone(),
+                                        trafo.clone(), nep.clone(), ret.dynamicness_threshold, sa)
         out = AttrDict(ret)
         for name in self._POINTWISE:
             if name in ret and ret[name].shape[1] != n_points:
@@ -372,7 +316,8 @@ class SLIM(nn.Module):
             captures_before = getattr(net, "n_graph_captures", 0)
             net(pcl_t0, pcl_t1, raw_scans=raw)
             decoded = self._sink_results(net, static, captures_before)
-            preds_fw, preds_bw = ([self._present(decoded[(k, it)], self._dec_n[k], thr)
+            copy = static and not self.outputs_alias_static_buffers
+            preds_fw, preds_bw = ([self._present(decoded[(k, it)], self._dec_n[k], thr, copy)
                                    for it in sorted(i for (kk, i) in decoded if kk == k)] for k in (0, 1))
             self.predictions_fw, self.predictions_bw = preds_fw, preds_bw
             return preds_fw, preds_bw

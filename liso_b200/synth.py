@@ -146,7 +146,8 @@ def pillar_coors_f64_numpy(pcl: np.ndarray, bev_range_m, grid_size, height_range
     float32 points promoted against a float64 range array, ``astype(int32)`` truncation toward
     zero, strict ``zmin < z < zmax`` height filter.  Returns (coors (N,2) int32, valid (N,) bool).
     """
-    rng_m = np.append(np.asarray(bev_range_m, dtype=np.float64), 1000.0)
+    rng_m = np.append(np.asarray(bev_range_m, dtype=np.float32), np.array(1000.0))  # float32 ranges widened (bev_utils.py:42)
+    height_range_m = np.asarray(height_range_m, dtype=np.float32)
     gsz = np.append(np.asarray(grid_size, dtype=np.int64), 1)
     c = (pcl[:, :3] + 0.5 * rng_m) / rng_m
     c = (c * gsz).astype(np.int32)

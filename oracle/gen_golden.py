@@ -125,13 +125,55 @@ def gen_slim_forward(R):
     np.savez_compressed(os.path.join(OUT, "slim_forward_tiny.npz"), **out)
 
 
+def preprocess_points(rng, n, bev_range, grid):
+    """Points around a (bev_range, grid) BEV: interior, exactly on cell edges and on the range limits, just outside,
+    near the height limits and near the ground cone."""
+    half = 0.5 * np.asarray(bev_range, dtype=np.float64)
+    pts = rng.uniform(-1.08, 1.08, size=(n, 4)) * np.append(half, [3.0, 1.0])
+    cell = np.asarray(bev_range, dtype=np.float64) / np.asarray(grid)
+    k = n // 8
+    pts[:k, 0] = (rng.integers(0, grid[0] + 1, size=k) * cell[0] - half[0])            # exactly on x cell edges (incl. both limits)
+    pts[k:2 * k, 1] = (rng.integers(0, grid[1] + 1, size=k) * cell[1] - half[1])
+    pts[2 * k:3 * k, 0] = -half[0] - rng.uniform(0, 1, size=k) * cell[0]                # (-cell, 0): int32 truncation lets them in
+    pts[3 * k:4 * k, 2] = rng.choice([-2.0, 1.0, -2.0000002, 0.99999994, -1.9999999], size=k)  # strict height limits
+    d = np.hypot(pts[4 * k:5 * k, 0], pts[4 * k:5 * k, 1])
+    pts[4 * k:5 * k, 2] = -1.5 + np.tan(0.8 / 180.0 * np.pi) * d + rng.choice([0.0, 1e-7, -1e-7, 1e-4, -1e-4], size=k)  # on the cone
+    return pts.astype(np.float32)
+
+
+def gen_preprocess(R):
+    """Reference dataset-side functions executed from their source (ref_shims.ref_preprocess_functions): the a12 point ->
+    pillar map (voxelize_sample / voxelize_pcl + height filter) and the cone ground rule under both NumPy promotion rules."""
+    import types
+
+    cone_new, voxelize_sample, _ = ref_shims.ref_preprocess_functions(False)
+    cone_legacy, _, _ = ref_shims.ref_preprocess_functions(True)
+    rng = np.random.default_rng(7)
+    out = {}
+    for name, bev, grid in (("k", (70.0, 70.0), (640, 640)), ("a", (120.0, 120.0), (920, 920)), ("odd", (70.4, 51.2), (176, 128))):
+        pts = preprocess_points(rng, 40000, bev, grid)
+        # LidarDataset.__init__ (torch_dataset_commons.py:487-503) / get_bev_setup_params (utils/bev_utils.py:41-43)
+        ds = types.SimpleNamespace(bev_range_m_np=np.array(bev, np.float32), img_grid_size_np=np.array(grid).astype(np.int32),
+                                   height_range_m_np=np.array((-2.0, 1.0), np.float32))
+        coors, in_range = voxelize_sample(ds, pts)
+        out.update({name + "_points": pts, name + "_bev_range_m": np.array(bev), name + "_img_grid_size": np.array(grid),
+                    name + "_coors": coors.astype(np.int32), name + "_in_range": in_range,
+                    name + "_ground_numpy2": cone_new(pts, cone_z_threshold__m=-1.5),
+                    name + "_ground_legacy": cone_legacy(pts, cone_z_threshold__m=-1.5)})
+    np.savez_compressed(os.path.join(OUT, "preprocess_ref.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     R = ref_shims.ref_modules()
+    if "--only-preprocess" in __import__("sys").argv:
+        gen_preprocess(R)
+        return
     gen_voxelize(R)
     gen_pillar_encoder(R)
     gen_corr(R)
     gen_slim_forward(R)
+    gen_preprocess(R)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
 

@@ -202,3 +202,56 @@ def ref_modules():
         SLIM=SLIM,
         voxelize_pcl=voxelize_pcl,
     )
+
+
+def ref_source_functions(rel_path: str, names, namespace=None):
+    """Execute the UNMODIFIED source text of the named functions / methods of a reference file whose module cannot be
+    imported here (``liso/datasets/torch_dataset_commons.py`` pulls in matplotlib, pykitti, nuscenes, ...).  Methods come
+    back as plain functions taking ``self`` first.  ``namespace``: the globals the code sees (default: numpy as ``np``,
+    torch)."""
+    import ast
+    import textwrap
+
+    import numpy as np
+
+    src = open(os.path.join(REF_ROOT, rel_path)).read()
+    ns = {"np": np, "torch": torch}
+    ns.update(namespace or {})
+    found = {}
+    for node in ast.walk(ast.parse(src)):
+        if isinstance(node, ast.FunctionDef) and node.name in names and node.name not in found:
+            node.decorator_list = []
+            code = textwrap.dedent("\n".join(src.split("\n")[node.lineno - 1:node.end_lineno]))
+            exec(compile(code, os.path.join(REF_ROOT, rel_path), "exec"), ns)
+            found[node.name] = ns[node.name]
+    missing = [n for n in names if n not in found]
+    if missing:
+        raise KeyError("not found in %s: %s" % (rel_path, missing))
+    return found
+
+
+def ref_preprocess_functions(legacy_numpy_promotion: bool = False):
+    """``infer_ground_label_using_cone`` (``torch_dataset_commons.py:133-146``) and ``LidarDataset.voxelize_sample``
+    (``:975-987``, calling ``voxelize_pcl``, ``datasets/nuscenes/analyse_boxes.py:6-26``) of the reference, executed from
+    their source.  ``legacy_numpy_promotion``: the reference environment (NumPy < 2, ``docker/Dockerfile.base``) casts the
+    float64 scalar ``np.tan(angle)`` to the float32 of the array it multiplies (value-based casting); NumPy >= 2 promotes
+    the product to float64.  With the flag the code sees an ``np`` whose ``tan`` already returns that float32 -- the only
+    difference between the two promotion rules in these functions -- and is otherwise untouched."""
+    install()
+    import numpy as np
+    from liso.datasets.nuscenes.analyse_boxes import voxelize_pcl
+
+    np_seen = np
+    if legacy_numpy_promotion:
+        class _LegacyNp:
+            def __getattr__(self, k):
+                return getattr(np, k)
+
+            @staticmethod
+            def tan(x):
+                return np.float32(np.tan(x))
+
+        np_seen = _LegacyNp()
+    fns = ref_source_functions("liso/datasets/torch_dataset_commons.py", ["infer_ground_label_using_cone", "voxelize_sample"],
+                               {"np": np_seen, "voxelize_pcl": voxelize_pcl})
+    return fns["infer_ground_label_using_cone"], fns["voxelize_sample"], voxelize_pcl

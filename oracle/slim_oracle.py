@@ -280,7 +280,9 @@ def pillar_encoder_forward(points: List[np.ndarray], params: Dict[str, torch.Ten
 #                                             torch_dataset_commons.py:975-987
 # ----------------------------------------------------------------------------------
 def pillar_coors_f64(pcl: np.ndarray, bev_range_m, img_grid_size, height_range_m=(-2.0, 1.0)):
-    bev = np.append(np.asarray(bev_range_m, dtype=np.float64), np.array(1000.0))
+    # (the dataset keeps bev_range_m as a float32 array, utils/bev_utils.py:42; np.append with the float64 1000.0 widens it)
+    bev = np.append(np.asarray(bev_range_m, dtype=np.float32), np.array(1000.0))
+    height_range_m = np.asarray(height_range_m, dtype=np.float32)  # torch_dataset_commons.py:499-501
     grid = np.append(np.asarray(img_grid_size), np.array(1))
     c = (pcl[:, :3] + 0.5 * bev) / bev  # fp32 + fp64 -> fp64
     c = (c * grid).astype(np.int32)  # truncation toward zero

@@ -70,6 +70,29 @@ def test_cpu_tensors_are_rejected():
         m([torch.zeros(10, 4)])
     with pytest.raises(RuntimeError, match="no CPU fallback"), torch.no_grad():
         CorrBlock(torch.zeros(1, 128, 8, 8), torch.zeros(1, 128, 8, 8))
+    # ... and so is the output decoder (the stock-PyTorch restatement lives in tests/torch_decoder.py, not in the product)
+    import numpy as np
+
+    from liso_b200.slim.slim import HeadDecoder
+
+    cfg = make_cfg("T")
+    dec = HeadDecoder(cfg.SLIM, name="t", bev_extent=np.array([-7.0, -7.0, 7.0, 7.0]))
+    with pytest.raises(RuntimeError, match="no CPU fallback"), torch.no_grad():
+        dec(torch.zeros(1, 8, 8, 8), 0.5, pc=torch.zeros(1, 4, 4), pointwise_voxel_coordinates=torch.zeros(1, 4, 2, dtype=torch.int32),
+            pointwise_valid_mask=torch.ones(1, 4, dtype=torch.bool), filled_pillar_mask=torch.ones(1, 8, 8, dtype=torch.bool))
+    assert not hasattr(HeadDecoder, "_forward_torch")
+    # switches that would change the decoder's arithmetic are refused, not ignored
+    import copy
+
+    for path in (("model", "use_static_aggr_flow_for_aggr_flow"), ("model", "dynamic_flow_is_non_rigid_flow"),
+                 ("losses", "unsupervised", "use_epsilon_for_weighted_pc_alignment")):
+        bad = copy.deepcopy(cfg.SLIM)
+        node = bad
+        for k in path[:-1]:
+            node = node[k]
+        node[path[-1]] = True
+        with pytest.raises(NotImplementedError):
+            HeadDecoder(bad, name="t", bev_extent=np.array([-7.0, -7.0, 7.0, 7.0]))
 
 
 def test_glue_kernels_reject_cpu_tensors_and_bad_arguments():

@@ -13,6 +13,7 @@ import torch
 
 from liso_b200.config import WORKLOADS, make_cfg
 from liso_b200.slim.slim import HeadDecoder
+from torch_decoder import forward_torch
 from liso_b200.synth import make_sample_dicts
 from oracle import slim_forward as SF
 
@@ -79,7 +80,7 @@ def test_fused_decoder_equals_stock_torch_decoder(cuda):
     with torch.no_grad():
         a = dec._forward_fused(net_out.to(cuda), thr, kw["pc"], kw["pointwise_voxel_coordinates"], kw["pointwise_valid_mask"],
                                kw["filled_pillar_mask"], True)
-        b = dec._forward_torch(net_out.to(cuda), thr, **kw)
+        b = forward_torch(dec, net_out.to(cuda), thr, **kw)
     for k in ("static_flow", "dynamic_flow", "dynamicness", "staticness", "aggregated_flow", "static_aggr_flow"):
         assert float((a[k] - b[k]).abs().max()) <= 2e-4, k
     ma, mb = a.modified_network_output, b.modified_network_output

@@ -112,3 +112,40 @@ def test_preprocess_edge_cases(cuda):
         assert np.array_equal(got["pcl_ta"]["pillar_coors"][b, :n].cpu().numpy(), ref_coors)
         assert int(got["pcl_ta"]["pcl_is_valid"][b].sum()) == n
     assert list(counts) == [0, 0, 1, 1]
+
+
+def test_kernels_against_reference_executed_fixture(cuda):
+    """The CUDA kernels directly against what the REFERENCE code answered (tests/golden/preprocess_ref.npz, produced by
+    oracle/gen_golden.py from the reference source): a12 pillar coordinates + range / height mask through the raw C ABI,
+    and the cone ground rule + compaction through preprocess_scans -- points exactly on cell edges, limits and the cone."""
+    import ctypes as C
+    import os
+
+    from liso_b200 import _lib
+    from liso_b200.config import AttrDict
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "preprocess_ref.npz"))
+    lib = _lib.load()
+    for name in ("k", "a", "odd"):
+        pts = g[name + "_points"]
+        bev, grid = g[name + "_bev_range_m"], g[name + "_img_grid_size"]
+        t = torch.from_numpy(pts).to(cuda)
+        coors = torch.empty((pts.shape[0], 2), dtype=torch.int32, device=cuda)
+        valid = torch.empty((pts.shape[0],), dtype=torch.uint8, device=cuda)
+        _lib.check(lib.slimb200_pillar_coors_f64(t.data_ptr(), pts.shape[0], 4, float(np.float32(bev[0])), float(np.float32(bev[1])),
+                                                 int(grid[0]), int(grid[1]), -2.0, 1.0, coors.data_ptr(), valid.data_ptr(),
+                                                 _lib.current_stream_ptr()))
+        torch.cuda.synchronize()
+        assert np.array_equal(valid.cpu().numpy().astype(bool), g[name + "_in_range"])
+        # (out-of-int32-range garbage of rejected points aside, the integers agree wherever the reference keeps the point)
+        keep = g[name + "_in_range"]
+        assert np.array_equal(coors.cpu().numpy()[keep], g[name + "_coors"][keep])
+        cfg = make_cfg("T")
+        cfg.data.bev_range_m, cfg.data.img_grid_size = (float(bev[0]), float(bev[1])), (int(grid[0]), int(grid[1]))
+        got = preprocess_scans([t], cfg)
+        torch.cuda.synchronize()
+        want = keep & ~g[name + "_ground_legacy"]
+        n = int(want.sum())
+        assert int(got["counts"][0]) == n
+        assert np.array_equal(got["pcl_ta"]["pcl"][0, :n].cpu().numpy(), pts[want])
+        assert np.array_equal(got["pcl_ta"]["pillar_coors"][0, :n].cpu().numpy(), g[name + "_coors"][want])

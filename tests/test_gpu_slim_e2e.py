@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 import torch
 
+from liso_b200 import _lib
 from liso_b200.config import WORKLOADS, make_cfg
 from liso_b200.slim.slim import SLIM
 from liso_b200.synth import make_sample_dicts
@@ -28,10 +29,15 @@ def _aee(pred, ref, valid):
     return float((pred - ref).norm(dim=-1)[valid].mean())
 
 
+@pytest.mark.parametrize("fused_lookup", [False, "always"])
 @pytest.mark.parametrize("workload,seeds", [("T", [3, 4]), ("N", [5]), ("K", [6]), ("A", [7])])
-def test_slim_forward_flow_within_1cm(cuda, workload, seeds):
+def test_slim_forward_flow_within_1cm(cuda, workload, seeds, fused_lookup):
+    """`fused_lookup`: the lookup + conv_stat_corr1 + ReLU as ONE tcgen05 kernel with tf32 operands instead of
+    the lookup kernel + the stock fp32 convolution; same 1 cm bar."""
     cfg = make_cfg(workload)
     model, sd = _model(cfg, cuda)
+    model.raft_network.fuse_lookup_conv = fused_lookup
+    n_fused = _lib.load().slimb200_launch_count(_lib.K_LOOKUP_CONV)
     s0, s1 = make_sample_dicts(WORKLOADS[workload], seeds)
     with torch.no_grad():
         pf, pb = model(s0, s1, None)
@@ -47,6 +53,89 @@ def test_slim_forward_flow_within_1cm(cuda, workload, seeds):
         assert aee <= 0.01
         assert torch.equal(p[-1].modified_network_output.static_flow.cpu() != 0, o[-1]["static_flow"] != 0)
         assert dyn < 5e-2
+    # the fused kernel really ran (12 launches: 6 iterations x 2 directions, captured once) / really did not
+    assert (_lib.load().slimb200_launch_count(_lib.K_LOOKUP_CONV) - n_fused > 0) == bool(fused_lookup)
+
+
+def test_batch_of_8_kitti_pairs_every_sample_within_1cm(cuda):
+    """The bench batch (configs[1]: 8 KITTI-sized pairs in one forward): EVERY sample of the batch against the oracle run
+    on that sample alone (eval mode: samples are independent), fused lookup on."""
+    cfg = make_cfg("K")
+    model, sd = _model(cfg, cuda, decode_iterations="last", static_aggregation=False)
+    model.raft_network.fuse_lookup_conv = "always"
+    seeds = [1000 + i for i in range(8)]
+    s0, s1 = make_sample_dicts(WORKLOADS["K"], seeds)
+    with torch.no_grad():
+        pf, pb = model(s0, s1, None)
+    torch.cuda.synchronize()
+    got = [(pf[-1].static_flow.cpu(), pf[-1].modified_network_output.static_flow.cpu()),
+           (pb[-1].static_flow.cpu(), pb[-1].modified_network_output.static_flow.cpu())]
+    for b, seed in enumerate(seeds):
+        o0, o1 = make_sample_dicts(WORKLOADS["K"], [seed])
+        with torch.no_grad():
+            of, ob, _ = SF.slim_forward(sd, cfg, o0, o1, decode_all_iterations=False)
+        for (pt, bev), o, full, one in ((got[0], of, s0, o0), (got[1], ob, s1, o1)):
+            n = int(one["pcl_ta"]["pcl_is_valid"].shape[1])
+            valid = one["pcl_ta"]["pcl_is_valid"][0]
+            assert torch.equal(full["pcl_ta"]["pcl_is_valid"][b, :n], valid) and not bool(full["pcl_ta"]["pcl_is_valid"][b, n:].any())
+            aee = _aee(pt[b, :n], o[-1]["pointwise_static_flow"][0], valid)
+            assert aee <= 0.01, (b, aee)
+            assert torch.equal(bev[b] != 0, o[-1]["static_flow"][0] != 0), b
+
+
+@pytest.mark.parametrize("workload,seeds,graph", [("T", [3, 4], True), ("T", [8], False), ("N", [5], True)])
+def test_train_mode_batchnorm_export_within_1cm(cuda, workload, seeds, graph):
+    """Q4: the reference's flow export never calls model.eval() (experiment.py:164-198,225-361), so the pillar encoder's
+    BatchNorm1d normalises with BATCH statistics (padded rows included, all samples of the batch pooled) and updates its
+    running statistics between the two frames.  Same forward here with model.train() under no_grad -- also through the
+    CUDA graph, whose part of the network does not depend on the mode -- against the oracle's bn_training path."""
+    cfg = make_cfg(workload)
+    model, sd = _model(cfg, cuda)
+    model.train()
+    model.raft_network.use_cuda_graph = graph
+    s0, s1 = make_sample_dicts(WORKLOADS[workload], seeds)
+    with torch.no_grad():
+        pf, pb = model(s0, s1, None)
+        torch.cuda.synchronize()
+        of, ob, aux = SF.slim_forward(sd, cfg, s0, s1, bn_training=True, decode_all_iterations=False)
+    assert (getattr(model.raft_network, "n_graph_captures", 0) > 0) == graph
+    for p, o, s in ((pf, of, s0), (pb, ob, s1)):
+        valid = s["pcl_ta"]["pcl_is_valid"]
+        aee = _aee(p[-1].static_flow.cpu(), o[-1]["pointwise_static_flow"], valid)
+        assert aee <= 0.01, aee
+        assert torch.equal(p[-1].modified_network_output.static_flow.cpu() != 0, o[-1]["static_flow"] != 0)
+    bn = model.raft_network.pp_layer.pts_voxel_encoder.pfn_layers[0].norm
+    # two frames = two running-stat updates (momentum 0.01, unbiased variance), like the oracle's
+    np.testing.assert_allclose(bn.running_mean.cpu().numpy(), aux["enc"][1]["running_mean"].numpy(), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(bn.running_var.cpu().numpy(), aux["enc"][1]["running_var"].numpy(), rtol=1e-4, atol=1e-6)
+    # and the eval-mode answer differs (the test would not notice a silently ignored mode otherwise)
+    ev, _ = _model(cfg, cuda)
+    with torch.no_grad():
+        ef, _ = ev(s0, s1, None)
+    assert float((ef[-1].static_flow - pf[-1].static_flow).abs().max()) > 1e-4
+
+
+def test_forward_results_survive_the_next_forward(cuda):
+    """Graph mode: by default SLIM.forward hands out copies (the reference's export keeps the t0->t1 predictions across two
+    more model() calls, experiment.py:386-456); with outputs_alias_static_buffers they are views that the next forward
+    overwrites."""
+    cfg = make_cfg("T")
+    model, _ = _model(cfg, cuda)
+    a0, a1 = make_sample_dicts(WORKLOADS["T"], [31])
+    b0, b1 = make_sample_dicts(WORKLOADS["T"], [32])
+    with torch.no_grad():
+        pf, _ = model(a0, a1, None)
+        keep_flow = pf[-1].modified_network_output.static_flow.clone()
+        keep_pts = pf[-1].static_flow.clone()
+        model(b0, b1, None)
+        assert getattr(model.raft_network, "n_graph_captures", 0) > 0
+        assert torch.equal(pf[-1].modified_network_output.static_flow, keep_flow) and torch.equal(pf[-1].static_flow, keep_pts)
+        assert torch.equal(pf[0].modified_network_output.dynamicness, pf[0].modified_network_output.class_probs[..., 1])  # views of ONE copy
+        model.outputs_alias_static_buffers = True
+        qf, _ = model(a0, a1, None)
+        assert torch.equal(qf[-1].modified_network_output.static_flow, keep_flow)
+        model(b0, b1, None)
+        assert not torch.equal(qf[-1].modified_network_output.static_flow, keep_flow)  # the documented hazard of the alias mode
 
 
 def test_decode_last_equals_decode_all(cuda):

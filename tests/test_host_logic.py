@@ -75,6 +75,14 @@ def test_slim_wiring_with_oracle_stages(monkeypatch):
         return e["canvas"], e["occupancy"]
 
     monkeypatch.setattr(pp, "forward", pp_forward)
+    # the output decoder is CUDA-only in the product too: the stock-PyTorch restatement of the tests stands in
+    from torch_decoder import forward_torch
+
+    for dec in (m.head_decoder_fw, m.head_decoder_bw):
+        monkeypatch.setattr(dec, "forward", lambda o, thr, _d=dec, **kw: forward_torch(
+            _d, o, thr, pc=kw["pc"], pointwise_voxel_coordinates=kw["pointwise_voxel_coordinates"],
+            pointwise_valid_mask=kw["pointwise_valid_mask"], filled_pillar_mask=kw["filled_pillar_mask"],
+            static_aggregation=kw.get("static_aggregation", True)))
     s0, s1 = make_sample_dicts(WORKLOADS["T"], [3])
     with torch.no_grad():
         pf, pb = m(s0, s1, None)
@@ -373,3 +381,89 @@ def test_world_size_2_flow_export_gloo(tmp_path):
         tot = torch.load(os.path.join(str(tmp_path), "t%d.pt" % r))
         assert tot["pairs"] == 9.0 and tot["files"] == 9.0 and tot["skipped"] == 0.0 and tot["elapsed_s_max"] > 0.0
     assert sorted(os.listdir(os.path.join(str(tmp_path), "npz"))) == ["p%02d.npz" % i for i in range(9)]
+
+
+def test_derived_parameter_cache_is_per_module_and_identity_checked():
+    """Derived weights (stacked update|reset gates, block-diagonal pairs, tap weights) are cached on the module that owns
+    the sources and checked by tensor IDENTITY + version: a new model whose parameters land on the addresses of a freed
+    one must never be served the old model's concatenations."""
+    import gc
+
+    from liso_b200.slim import raft as R
+
+    stale = 0
+    for seed in range(6):
+        torch.manual_seed(seed)
+        a, b = torch.nn.Conv2d(8, 4, 3, padding=1), torch.nn.Conv2d(8, 4, 3, padding=1)
+        owner = torch.nn.Module()
+        owner.a, owner.b = a, b
+        got = R._cat_params(owner, "w", (a.weight, b.weight))
+        assert torch.equal(got, torch.cat([a.weight, b.weight]).detach())
+        assert R._cat_params(owner, "w", (a.weight, b.weight)) is got                      # hit
+        w, bias = R._stacked_params(a, b, shared_input=False, pad_in_to=24)
+        assert w.shape == (8, 24, 3, 3) and torch.equal(w[:4, :8], a.weight.detach()) and torch.equal(w[4:, 8:16], b.weight.detach())
+        assert float(w[:4, 8:].abs().max()) == 0.0 and torch.equal(bias, torch.cat([a.bias, b.bias]).detach())
+        with torch.no_grad():
+            a.weight.add_(1.0)                                                              # in-place update: new version
+        again = R._cat_params(owner, "w", (a.weight, b.weight))
+        assert again is not got and torch.equal(again[:4], a.weight.detach())
+        stale += int(not torch.equal(R._stacked_params(a, b, shared_input=False, pad_in_to=24)[0][:4, :8], a.weight.detach()))
+        del a, b, owner, got, again, w, bias
+        gc.collect()
+    assert stale == 0
+    assert not hasattr(R, "_PARAM_CAST_CACHE")  # no process-global cache keyed by raw addresses
+
+
+def _rn32(fr):
+    """Fraction -> nearest float32 (ties to even), as an exactly representable python float."""
+    import math
+    from fractions import Fraction
+
+    if fr == 0:
+        return 0.0
+    sgn = -1 if fr < 0 else 1
+    a = abs(fr)
+    e = a.numerator.bit_length() - a.denominator.bit_length()
+    while Fraction(2) ** e > a:
+        e -= 1
+    while Fraction(2) ** (e + 1) <= a:
+        e += 1
+    e = max(e, -126)
+    scaled = a / (Fraction(2) ** (e - 23))
+    m = scaled.numerator // scaled.denominator
+    rem = scaled - m
+    if rem > Fraction(1, 2) or (rem == Fraction(1, 2) and (m & 1)):
+        m += 1
+    return sgn * float(Fraction(m) * Fraction(2) ** (e - 23))
+
+
+def test_lookup_division_by_precomputed_reciprocal_is_correctly_rounded():
+    """csrc/lookup_core.cuh::div_by_const -- q = a * rinv; twice q += fma(-b, q, a) * rinv with rinv = RN(1 / b) -- equals
+    the IEEE quotient RN(a / b) that bilinear_sampler's `2 * x / (W - 1)` (raft_code/utils.py:19-20) asks for.  Checked in
+    exact rational arithmetic for every divisor a level size up to 130 can produce and typical / adversarial dividends."""
+    import random
+    from fractions import Fraction
+
+    def fma32(x, y, z):
+        return _rn32(Fraction(x) * Fraction(y) + Fraction(z))
+
+    random.seed(1)
+    n = 0
+    for b in list(range(1, 130)) + [159, 199, 255, 1023, 4095]:
+        bf = float(b)
+        y = _rn32(Fraction(1) / Fraction(bf))
+        for _ in range(12):
+            kind = random.random()
+            if kind < 0.5:
+                a = np.float32(2.0 * random.uniform(-10, b + 10))
+            elif kind < 0.8:
+                a = np.float32(2.0 * (random.randint(-8, b + 8) + random.choice([0, 1e-6, -1e-6, 0.5])))
+            else:
+                a = np.float32(random.uniform(-2e7, 2e7) * random.choice([1, 1e-3, 1e-30, 1e-41]))
+            a = float(a)
+            q = _rn32(Fraction(a) * Fraction(y))
+            q = fma32(fma32(-bf, q, a), y, q)
+            q = fma32(fma32(-bf, q, a), y, q)
+            assert q == _rn32(Fraction(a) / Fraction(bf)), (a, b)
+            n += 1
+    assert n > 1500

@@ -99,3 +99,25 @@ def test_slim_forward_port_vs_reference():
         np.testing.assert_allclose(o[-1]["pointwise_static_flow"][0].numpy(), g["pt_static_flow_" + d], rtol=0, atol=2e-5)
         np.testing.assert_allclose(o[-1]["dynamicness"][0].numpy(), g["bev_dynamicness_" + d], rtol=0, atol=2e-5)
         np.testing.assert_allclose(o[-1]["static_aggr_trafo"][0].numpy(), g["static_aggr_trafo_" + d], rtol=0, atol=1e-4)
+
+
+def test_dataset_side_preprocessing_vs_reference_source():
+    """a12 + SURVEY 8f.4 pins: ``O.pillar_coors_f64`` against the reference's ``voxelize_sample`` -> ``voxelize_pcl``
+    (``torch_dataset_commons.py:975-987``, ``analyse_boxes.py:6-26``) and ``O.ground_label_cone_f32`` against
+    ``infer_ground_label_using_cone`` (``:133-146``), both executed from the reference source by ``oracle/gen_golden.py``
+    on points that sit exactly on cell edges, range limits, height limits and on the cone."""
+    g = np.load(os.path.join(GOLDEN, "preprocess_ref.npz"))
+    for name in ("k", "a", "odd"):
+        pts = g[name + "_points"]
+        coors, ok = O.pillar_coors_f64(pts, g[name + "_bev_range_m"], g[name + "_img_grid_size"])
+        assert np.array_equal(coors, g[name + "_coors"]) and coors.dtype == np.int32
+        assert np.array_equal(ok, g[name + "_in_range"])
+        assert 0.3 < ok.mean() < 0.7  # both outcomes well represented
+        ground = O.ground_label_cone_f32(pts, -1.5)
+        # the reference environment is NumPy 1.18.5 (docker/Dockerfile.base:53): float32 arithmetic throughout
+        assert np.array_equal(ground, g[name + "_ground_legacy"])
+        # NumPy >= 2 promotes the product to float64: only points within rounding of the cone may flip
+        flips = ground != g[name + "_ground_numpy2"]
+        d = np.hypot(pts[:, 0].astype(np.float64), pts[:, 1].astype(np.float64))
+        margin = np.abs(pts[:, 2].astype(np.float64) - (-1.5 + np.tan(0.8 / 180.0 * np.pi) * d))
+        assert flips.sum() > 0 and margin[flips].max() < 1e-5

@@ -73,3 +73,26 @@ def test_oracle_pillar_encoder_equals_reference_kitti_size():
         out = O.pillar_encoder_forward([p0, p1], params, cfg.data.bev_range_m, cfg.data.img_grid_size, 10.0, training)
         assert torch.equal(canvas, out["canvas"]) and torch.equal(occ, out["occupancy"])
         assert torch.equal(bn.running_mean, out["running_mean"])
+
+
+def test_dataset_side_preprocessing_live():
+    """Larger live run of the pins of test_oracle_golden.py::test_dataset_side_preprocessing_vs_reference_source."""
+    import types
+
+    from oracle import slim_oracle as O
+    from oracle.gen_golden import preprocess_points
+
+    cone_legacy, voxelize_sample, voxelize_pcl = ref_shims.ref_preprocess_functions(True)
+    rng = np.random.default_rng(11)
+    for bev, grid in (((70.0, 70.0), (640, 640)), ((120.0, 120.0), (920, 920)), ((51.2, 70.4), (128, 176))):
+        pts = preprocess_points(rng, 300000, bev, grid)
+        ds = types.SimpleNamespace(bev_range_m_np=np.array(bev, np.float32), img_grid_size_np=np.array(grid).astype(np.int32),
+                                   height_range_m_np=np.array((-2.0, 1.0), np.float32))
+        ref_c, ref_ok = voxelize_sample(ds, pts)
+        c, ok = O.pillar_coors_f64(pts, bev, grid)
+        assert np.array_equal(c, ref_c) and np.array_equal(ok, ref_ok)
+        # torch tensors take the other branch of voxelize_pcl (analyse_boxes.py:10-13): same integers
+        tc, tok = voxelize_pcl(torch.from_numpy(pts), torch.from_numpy(np.append(ds.bev_range_m_np, np.array(1000.0))),
+                               torch.from_numpy(np.append(ds.img_grid_size_np, np.array(1))))
+        assert np.array_equal(tc.numpy()[:, :2], c)
+        assert np.array_equal(O.ground_label_cone_f32(pts, -1.5), cone_legacy(pts, cone_z_threshold__m=-1.5))
