@@ -44,9 +44,9 @@ def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
-                    source="measured")
-    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source="fallback")  # B200_PROFILING.md
+        return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops_burst=float(d["bf16_tflops"]),
+                    bf16_tflops_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops_burst=1590.0, bf16_tflops_sustained=1590.0, source="fallback")  # B200_PROFILING.md
 
 
 class ClockSampler:
@@ -176,9 +176,13 @@ def main():
                     help="lookup kernel + stock 1x1 convolution instead of the fused slimb200_corr_lookup_conv (SURVEY 8f.2)")
     ap.add_argument("--profile-one-step", action="store_true",
                     help="bracket ONE resident step with cudaProfilerStart/Stop (for `ncu --profile-from-start off`) and exit")
+    ap.add_argument("--no-other-workloads", action="store_true",
+                    help="skip the short same-process lines for the nuScenes- and AV2-sized workloads (configs[2], configs[3])")
     args = ap.parse_args()
-    # >= 3 by contract; 6 because cuDNN autotuning, graph capture and the allocator need a few more steps to settle
-    args.warmup = max(args.warmup, 6) if args.impl == "ours" else args.warmup
+    warmup_note = None
+    if args.impl == "ours" and args.warmup < 3:  # the timing contract asks for >= 3 warm-up steps: said on the line, not silent
+        warmup_note = "--warmup %d raised to the contract minimum of 3" % args.warmup
+        args.warmup = 3
 
     from liso_b200.config import WORKLOADS, make_cfg
     from liso_b200.weights import synth_weights_like
@@ -215,6 +219,8 @@ def main():
                 "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                 "note": "oracle port (oracle/slim_forward.py, vectorised numpy voxeliser), not the reference's numba "
+                                         "voxeliser / mmcv op: a faithful port's speed, not the reference's",
                                  "sample": "each step = 1 pair (B=1) of the workload through the CPU port of SLIM.forward"},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -224,9 +230,12 @@ def main():
     # ------------------------------------------------------------------ this repo (CUDA)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a CUDA device: the SLIM hot path has no CPU fallback")
+    import contextlib
+
     import torch.distributed as dist
 
     from liso_b200 import _lib
+    from liso_b200.slim.export import ExportPipeline, reduce_counters, shard_indices
     from liso_b200.slim.slim import SLIM
 
     torch.cuda.set_device(local_rank)
@@ -236,141 +245,236 @@ def main():
     lib = _lib.load()
     torch.backends.cudnn.allow_tf32 = args.conv_precision != "fp32"
     torch.backends.cuda.matmul.allow_tf32 = args.conv_precision != "fp32"
-    import contextlib
+    torch.backends.cudnn.benchmark = True
+    peaks = _peaks()
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    traffic_table = json.load(open(tpath)) if os.path.exists(tpath) else {}
 
     def amp():
         return torch.autocast("cuda", dtype=torch.bfloat16) if args.conv_precision == "bf16" else contextlib.nullcontext()
-    torch.backends.cudnn.benchmark = True
-
-    cfg.network["b200_canvas_memory_format"] = args.memory_format
-    model = SLIM(cfg, decode_iterations=args.decode, static_aggregation=args.decode == "all").eval()
-    sd = synth_weights_like(model.state_dict(), 0)
-    model.load_state_dict(sd, strict=True)
-    model = model.to(dev)
-    if args.memory_format == "channels_last":
-        model = model.to(memory_format=torch.channels_last)
-    model.raft_network.use_cuda_graph = not args.no_cuda_graph
-    model.raft_network.fuse_lookup_conv = not args.no_fused_lookup
-    # the resident loop reads each step's outputs before the next forward: views of the graph's static buffers are enough
-    # (SLIM's default returns copies the caller may keep across forwards; ExportPipeline, the e2e path, sets this itself)
-    model.outputs_alias_static_buffers = True
-
-    # pairs of this rank: global pair indices sharded by the reference's modulo rule
-    from liso_b200.slim.export import reduce_counters, shard_indices
-
-    mine = shard_indices(args.batch * world, world, rank)
-    s0, s1 = build_inputs(W, [1000 + i for i in mine])
-    d0, d1 = to_device(s0, dev), to_device(s1, dev)
-    h0, h1 = to_pinned(s0), to_pinned(s1)
-    h2d = sample_bytes(s0) + sample_bytes(s1)
-    H, Wd = W["img_grid_size"]
-    pinned_out = [torch.empty((args.batch, H, Wd, 2), dtype=torch.float32).pin_memory() for _ in range(2)] + \
-                 [torch.empty((args.batch, H, Wd), dtype=torch.float32).pin_memory() for _ in range(2)]
-    d2h = sum(t.numel() * 4 for t in pinned_out)
-
-    def step_resident():
-        with torch.no_grad(), amp():
-            pf, pb = model(d0, d1, None)
-        return export_tensors(pf, pb)
-
-    from liso_b200.slim.export import ExportPipeline
-
-    pipeline = ExportPipeline(model, dev, amp_ctx=amp if args.conv_precision == "bf16" else None)
-    consumed = {"bytes": 0}
-
-    def consume(_idx, host_tensors):  # the D2H result is read on the host (checksum of one element per tensor)
-        consumed["bytes"] += sum(t.numel() * t.element_size() for t in host_tensors)
-        consumed["probe"] = float(host_tensors[0].view(-1)[0])
-
-    def run_e2e(steps):
-        """`steps` batches through the public export loop: pinned host clouds in, pinned host results out; every batch's
-        H2D and D2H copies are inside the timed region (double-buffered against the compute of its neighbours)."""
-        pipeline.run(((h0, h1) for _ in range(steps)), consume)
-        torch.cuda.synchronize()
-
-    def step_e2e():
-        run_e2e(1)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, profile=False):
-        barrier()
-        if profile:
-            lib.slimb200_profile_begin()
-        l0 = _lib.total_launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        launches = _lib.total_launch_count() - l0  # direct launches + kernels inside replayed CUDA graphs
-        prof = None
-        if profile:
-            ms_k = (C.c_float * _lib.N_KERNELS)()
-            n_k = (C.c_int64 * _lib.N_KERNELS)()
-            _lib.check(lib.slimb200_profile_end(ms_k, n_k))
-            prof = {i: (float(ms_k[i]), int(n_k[i])) for i in range(_lib.N_KERNELS) if n_k[i]}
-        return ms, launches, prof
+    class Bench:
+        """One workload on this rank: model, resident + pinned inputs, the timed loops."""
 
-    # bring the clocks up before the first forward: that pass is where cuDNN's autotuner (cudnn.benchmark) times every
-    # convolution algorithm ONCE and where the CUDA graph is captured with the winners
+        def __init__(self, workload, batch, decode):
+            self.workload, self.batch, self.W = workload, batch, WORKLOADS[workload]
+            self.cfg = make_cfg(workload)
+            self.cfg.network["b200_canvas_memory_format"] = args.memory_format
+            model = SLIM(self.cfg, decode_iterations=decode, static_aggregation=decode == "all").eval()
+            self.sd = synth_weights_like(model.state_dict(), 0)
+            model.load_state_dict(self.sd, strict=True)
+            model = model.to(dev)
+            if args.memory_format == "channels_last":
+                model = model.to(memory_format=torch.channels_last)
+            model.raft_network.use_cuda_graph = not args.no_cuda_graph
+            model.raft_network.fuse_lookup_conv = not args.no_fused_lookup
+            # the resident loop reads each step's outputs before the next forward: views of the graph's static buffers are
+            # enough (SLIM's default returns copies the caller may keep across forwards; ExportPipeline sets this itself)
+            model.outputs_alias_static_buffers = True
+            self.model = model
+            mine = shard_indices(batch * world, world, rank)  # global pair indices, the reference's modulo rule
+            self.s0, self.s1 = build_inputs(self.W, [1000 + i for i in mine])
+            self.d0, self.d1 = to_device(self.s0, dev), to_device(self.s1, dev)
+            self.h0, self.h1 = to_pinned(self.s0), to_pinned(self.s1)
+            self.h2d = sample_bytes(self.s0) + sample_bytes(self.s1)
+            H, Wd = self.W["img_grid_size"]
+            self.d2h = 2 * batch * H * Wd * 2 * 4 + 2 * batch * H * Wd * 4  # 2 x flow (B,H,W,2) + 2 x dynamicness (B,H,W), fp32
+            self.pipeline = ExportPipeline(model, dev, amp_ctx=amp if args.conv_precision == "bf16" else None)
+            self.consumed = {"bytes": 0}
+
+        def set_decode(self, mode):
+            self.model.decode_iterations = mode
+            self.model.raft_network.output_iterations = mode
+            self.model.static_aggregation = mode == "all"
+
+        def step_resident(self):
+            with torch.no_grad(), amp():
+                pf, pb = self.model(self.d0, self.d1, None)
+            return export_tensors(pf, pb)
+
+        def _consume(self, _idx, host_tensors):  # the D2H result is read on the host
+            self.consumed["bytes"] += sum(t.numel() * t.element_size() for t in host_tensors)
+            self.consumed["probe"] = float(host_tensors[0].view(-1)[0])
+
+        def run_e2e(self, steps):
+            """`steps` batches through the public export loop: pinned host clouds in, pinned host results out; every batch's
+            H2D and D2H copies are inside the timed region (double-buffered against the compute of its neighbours)."""
+            self.pipeline.run(((self.h0, self.h1) for _ in range(steps)), self._consume)
+            torch.cuda.synchronize()
+
+        def prepare(self):
+            """Not a warm-up step of the contract: cuDNN's autotuner times every convolution algorithm ONCE and the CUDA
+            graph is captured with the winners (two forwards), like loading a model before serving it."""
+            for _ in range(2):
+                self.step_resident()
+            torch.cuda.synchronize()
+
+        def timed(self, fn, steps, profile=False):
+            barrier()
+            if profile:
+                lib.slimb200_profile_begin()
+            l0 = _lib.total_launch_count()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            barrier()
+            ms = e0.elapsed_time(e1)
+            launches = _lib.total_launch_count() - l0  # direct launches + kernels inside replayed CUDA graphs
+            prof = None
+            if profile:
+                ms_k = (C.c_float * _lib.N_KERNELS)()
+                n_k = (C.c_int64 * _lib.N_KERNELS)()
+                _lib.check(lib.slimb200_profile_end(ms_k, n_k))
+                prof = {i: (float(ms_k[i]), int(n_k[i])) for i in range(_lib.N_KERNELS) if n_k[i]}
+            return ms, launches, prof
+
+        def kernel_profile(self, steps):
+            """Per-kernel durations (CUDA events around every launch of the library) in a separate pass with the CUDA graph
+            switched off, so that every kernel is launched individually on the current stream.  A spin kernel in front of
+            every step lets the host enqueue ahead of the GPU: no host launch latency inside a bracket."""
+            self.model.raft_network.use_cuda_graph = False
+            self.step_resident()
+
+            def step_profiled():
+                torch.cuda._sleep(int(25e-3 * 1.9e9))
+                self.step_resident()
+
+            _, _, prof = self.timed(step_profiled, steps, profile=True)
+            self.model.raft_network.use_cuda_graph = not args.no_cuda_graph
+            return prof
+
+        def stage_rooflines(self, prof, prof_steps, ms_step):
+            """The three north-star stages (BASELINE metric: scatter HBM GB/s, correlation tensor-pipe utilisation, lookup
+            against HBM) + every other kernel with a declared bound.  achieved = algorithmic bytes (SURVEY 8d / DESIGN 4)
+            per launch / average launch duration measured live; traffic = MEAN dram read + write bytes per launch of the
+            same kernel in the committed ncu capture (profiles/ncu_traffic.json), or null."""
+            B, W = self.batch, self.W
+            H, Wd = W["img_grid_size"]
+            n_pts = [t.shape[0] for t in self.s0["pcl_full_no_ground_ta"]]
+            nf = (H // 8) * (Wd // 8)
+            n_pad = int(self.s0["pcl_ta"]["pcl"].shape[1])
+            L = _lib.CorrLayout()
+            lib.slimb200_corr_layout_init(B, 128, H // 8, Wd // 8, 4, C.byref(L))
+            enc_bytes = sum(n_pts) * 16 + B * 65 * H * Wd * 4
+            look_read = B * nf * 4 * 8 * 32
+            alg = {
+                _lib.K_TILE_ENCODE: dict(bytes=enc_bytes, what="points read + canvas NCHW (zeros incl.) + occupancy written, B frames per launch"),
+                _lib.K_PILLAR_NHWC: dict(bytes=enc_bytes, what="points read + canvas channels-last (zeros incl.) + occupancy written, B frames per launch"),
+                _lib.K_CORR_GEMM: dict(bytes=B * nf * L.n_cols * 2 + B * (nf + L.n_cols) * 128 * 2, flops=2.0 * B * nf * L.n_cols * 128,
+                                       what="bf16 pyramid written + bf16 operands read, B samples per launch"),
+                _lib.K_DECODE_BEV: dict(bytes=B * H * Wd * (8 * 4 + 1 + 16 * 4 + 3),
+                                        what="net output + filled mask read, packed 16-float BEV row + class bytes written"),
+                _lib.K_DECODE_AGGR: dict(bytes=B * H * Wd * (1 + 16) + B * n_pad * (9 + 12),
+                                         what="static-aggregated flow written per cell (4 floats) and per point (3 floats)"),
+                _lib.K_CORR_LOOKUP: dict(bytes=B * 196 * nf * 4 + look_read, what="fp32 lookup written + 8 tap rows x 32 B sectors per level read"),
+                _lib.K_LOOKUP_CONV: dict(bytes=B * 96 * nf * 4 + look_read, flops=2.0 * B * nf * 196 * 96,
+                                         what="lookup fused with conv_stat_corr1 + ReLU: 96-channel fp32 rows written + 8 tap rows x "
+                                              "32 B sectors per level read (the 196-channel lookup tensor never reaches HBM)"),
+            }
+            if prof.get(_lib.K_IN_APPLY, (0, 0))[1] == 34 * prof_steps:
+                # InstanceNorm glue of the two feature-encoder runs: 17 normalised tensors per run; average per launch
+                sizes = [(32 * (H // 2) * (Wd // 2), 5), (64 * (H // 4) * (Wd // 4), 6), (96 * (H // 8) * (Wd // 8), 6)]
+                elems = sum(e * n for e, n in sizes)
+                res_elems = sum(e * 2 for e, _ in sizes)
+                alg[_lib.K_IN_STATS] = dict(bytes=B * 4 * elems // 17, what="normalised tensor read once (average over the 17 tensors of an encoder run)")
+                alg[_lib.K_IN_APPLY] = dict(bytes=B * 4 * (2 * elems + res_elems) // 17,
+                                            what="tensor read + written in place, residual read where the block joins (average over 17 tensors)")
+
+            def entry(kid):
+                ms_k, n_k = prof[kid]
+                name = lib.slimb200_kernel_name(kid).decode()
+                ent = {"kernel": name, "launches_per_step": n_k / prof_steps, "avg_ms": ms_k / n_k,
+                       "share_of_step": (ms_k / prof_steps) / ms_step}
+                if kid in alg:
+                    gbs = alg[kid]["bytes"] / (ms_k / n_k * 1e-3) / 1e9
+                    ent.update({"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                                "algorithmic_bytes_per_launch": alg[kid]["bytes"], "what": alg[kid]["what"],
+                                "traffic": traffic_table.get("%s:%s:B%d" % (name, self.workload, B))})
+                    if alg[kid].get("flops"):
+                        tf = alg[kid]["flops"] / (ms_k / n_k * 1e-3) / 1e12
+                        # the kernel is timed bracket by bracket at boost clocks inside a sub-second region: the BURST cuBLAS
+                        # figure is the denominator; the sustained one (measured at the power-limited clock) beside it, labelled
+                        ent["tensor"] = {"achieved": tf, "unit": "TFLOP/s", "peak": peaks["bf16_tflops_burst"],
+                                         "frac": tf / peaks["bf16_tflops_burst"], "peak_sustained": peaks["bf16_tflops_sustained"],
+                                         "frac_of_sustained": tf / peaks["bf16_tflops_sustained"]}
+                return ent
+
+            kernels = [entry(k) for k, _ in sorted(prof.items(), key=lambda kv: -kv[1][0])]
+            by_id = {k: entry(k) for k in prof}
+            stages = {}
+            # stage 1 as a STAGE: the scatter kernel + its prep launches (keys, scans, rank scatter), all per batch of frames
+            enc_id = _lib.K_PILLAR_NHWC if _lib.K_PILLAR_NHWC in prof else _lib.K_TILE_ENCODE
+            if enc_id in prof:
+                prep = [k for k in (_lib.K_POINT_KEYS, _lib.K_SCAN_LOCAL, _lib.K_SCAN_GLOBAL, _lib.K_RANK_SCATTER) if k in prof]
+                calls = prof[enc_id][1]
+                t_stage = sum(prof[k][0] for k in prep + [enc_id]) / calls  # ms per encoder call (B frames)
+                gbs = enc_bytes / (t_stage * 1e-3) / 1e9
+                stages["pillar"] = {"bound": "hbm", "kernel": by_id[enc_id]["kernel"], "achieved": by_id[enc_id]["achieved"],
+                                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": by_id[enc_id]["frac"], "avg_launch_ms": by_id[enc_id]["avg_ms"],
+                                    "traffic": by_id[enc_id]["traffic"], "algorithmic_bytes_per_launch": enc_bytes,
+                                    "stage_incl_prep": {"launches": len(prep) + 1, "ms": t_stage, "achieved": gbs, "frac": gbs / peaks["hbm_gbs"],
+                                                        "kernels": [by_id[k]["kernel"] for k in prep + [enc_id]]}}
+            if _lib.K_CORR_GEMM in prof:
+                g = by_id[_lib.K_CORR_GEMM]
+                stages["corr_gemm"] = {"bound": "hbm", "kernel": g["kernel"], "achieved": g["achieved"], "peak": g["peak"], "unit": "GB/s",
+                                       "frac": g["frac"], "avg_launch_ms": g["avg_ms"], "traffic": g["traffic"],
+                                       "algorithmic_bytes_per_launch": g["algorithmic_bytes_per_launch"], "tensor": g["tensor"],
+                                       "note": "K = D = 128 only: 2 B written per 256 flop, the store stream binds before the tensor pipe"}
+            look_id = _lib.K_LOOKUP_CONV if _lib.K_LOOKUP_CONV in prof else (_lib.K_CORR_LOOKUP if _lib.K_CORR_LOOKUP in prof else None)
+            if look_id is not None:
+                g = by_id[look_id]
+                stages["lookup"] = {"bound": "hbm", "kernel": g["kernel"], "achieved": g["achieved"], "peak": g["peak"], "unit": "GB/s",
+                                    "frac": g["frac"], "avg_launch_ms": g["avg_ms"], "launches_per_step": g["launches_per_step"],
+                                    "traffic": g["traffic"], "algorithmic_bytes_per_launch": g["algorithmic_bytes_per_launch"], "what": g["what"]}
+            return kernels, stages
+
+    # bring the clocks up before the first forward (autotune + capture happen there)
     a = torch.randn(8192, 8192, device=dev, dtype=torch.bfloat16)
     for _ in range(40):
         a @ a
     torch.cuda.synchronize()
     del a
+
+    main = Bench(args.workload, args.batch, args.decode)
+    main.prepare()
     for _ in range(args.warmup):
-        step_resident()
+        main.step_resident()
     if args.profile_one_step:
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
-        step_resident()
+        main.step_resident()
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_res, launches, _ = timed(step_resident, args.steps)
-    # per-kernel durations (CUDA events around every launch of the library) are taken in a separate pass with the
-    # GRU-loop CUDA graph switched off, so that every kernel is launched individually on the current stream
-    model.raft_network.use_cuda_graph = False
-    step_resident()
-
-    def step_profiled():
-        # a spin kernel in front of every step lets the host enqueue ahead of the GPU, so that each bracketed launch
-        # starts right behind its start event (no host launch latency inside the bracket)
-        torch.cuda._sleep(int(25e-3 * 1.9e9))
-        step_resident()
-
-    _, _, prof = timed(step_profiled, max(3, args.steps // 2), profile=True)
+    ms_res, launches, _ = main.timed(main.step_resident, args.steps)
     prof_steps = max(3, args.steps // 2)
-    model.raft_network.use_cuda_graph = not args.no_cuda_graph
-    run_e2e(args.warmup)
-    ms_e2e, _, _ = timed(lambda: run_e2e(args.steps), 1)
+    prof = main.kernel_profile(prof_steps)
+    main.run_e2e(args.warmup)
+    ms_e2e, _, _ = main.timed(lambda: main.run_e2e(args.steps), 1)
     clocks = sampler.stop() if rank == 0 else None
 
     # the other decode mode, same run, fewer steps (reported beside the headline, never as the headline)
-    def set_mode(mode):
-        model.decode_iterations = mode
-        model.raft_network.output_iterations = mode
-        model.static_aggregation = mode == "all"
-
     other = "last" if args.decode == "all" else "all"
-    set_mode(other)
+    n_other = max(3, args.steps // 2)
+    main.set_decode(other)
     for _ in range(3):
-        step_resident()
-    ms_other, _, _ = timed(step_resident, max(3, args.steps // 2))
-    ms_other /= max(3, args.steps // 2)
-    run_e2e(2)
-    ms_other_e2e, _, _ = timed(lambda: run_e2e(max(3, args.steps // 2)), 1)
-    ms_other_e2e /= max(3, args.steps // 2)
-    set_mode(args.decode)
+        main.step_resident()
+    ms_other, _, _ = main.timed(main.step_resident, n_other)
+    ms_other /= n_other
+    main.run_e2e(2)
+    ms_other_e2e, _, _ = main.timed(lambda: main.run_e2e(n_other), 1)
+    ms_other_e2e /= n_other
+    main.set_decode(args.decode)
 
     writer_line = None
     if args.write_npz and rank == 0:
@@ -380,12 +484,12 @@ def main():
 
         out_dir = os.path.join(args.write_npz, "rank%d" % rank)
         shutil.rmtree(out_dir, ignore_errors=True)
-        thr_host = float(model.moving_dynamicness_threshold.value())
+        thr_host = float(main.model.moving_dynamicness_threshold.value())
         n_batches = max(3, args.steps)
         t0 = time.perf_counter()
-        wr = AsyncNpzWriter(out_dir, W["bev_range_m"])
-        pipeline.run(((h0, h1) for _ in range(n_batches)),
-                     lambda j, host: wr.submit_batch(["%06d_%d" % (j, b) for b in range(args.batch)], host, thr_host))
+        wr = AsyncNpzWriter(out_dir, main.W["bev_range_m"])
+        main.pipeline.run(((main.h0, main.h1) for _ in range(n_batches)),
+                          lambda j, host: wr.submit_batch(["%06d_%d" % (j, b) for b in range(args.batch)], host, thr_host))
         n_files = wr.close()
         dt = time.perf_counter() - t0
         mb = sum(os.path.getsize(os.path.join(out_dir, f)) for f in os.listdir(out_dir)) / 1e6
@@ -397,6 +501,16 @@ def main():
     tot = reduce_counters({"pairs": float(args.batch * args.steps), "ms_res_max": ms_res, "ms_e2e_max": ms_e2e,
                            "launches": float(launches), "ms_other_max": ms_other, "ms_other_e2e_max": ms_other_e2e},
                           device=dev)
+    # per-rank step times (scaling hygiene: who is the straggler)
+    per_rank = None
+    if world > 1:
+        mine_t = torch.tensor([ms_res / args.steps, ms_e2e / args.steps], dtype=torch.float64, device=dev)
+        allt = [torch.zeros_like(mine_t) for _ in range(world)]
+        dist.all_gather(allt, mine_t)
+        res_t, e2e_t = [float(t[0]) for t in allt], [float(t[1]) for t in allt]
+        per_rank = {"ms_per_step": [round(v, 4) for v in res_t], "e2e_ms_per_step": [round(v, 4) for v in e2e_t],
+                    "slowest_rank": int(np.argmax(res_t)), "slowest_rank_e2e": int(np.argmax(e2e_t)),
+                    "min_ms": min(res_t), "max_ms": max(res_t), "e2e_min_ms": min(e2e_t), "e2e_max_ms": max(e2e_t)}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -404,71 +518,37 @@ def main():
     value = tot["pairs"] / (tot["ms_res_max"] / 1e3)
     e2e_value = tot["pairs"] / (tot["ms_e2e_max"] / 1e3)
 
-    # ---- roofline of the dominant hand-written kernel (rank 0, live CUDA-event durations) ----
-    peaks = _peaks()
-    B = args.batch
-    n_pts = [t.shape[0] for t in s0["pcl_full_no_ground_ta"]]
-    nf = (H // 8) * (Wd // 8)
-    n_pad = int(s0["pcl_ta"]["pcl"].shape[1])
-    L = _lib.CorrLayout()
-    lib.slimb200_corr_layout_init(B, 128, H // 8, Wd // 8, 4, C.byref(L))
-    alg = {
-        _lib.K_TILE_ENCODE: dict(bytes=sum(n_pts) * 16 + B * 65 * H * Wd * 4, flops=0,
-                                 what="points read + canvas NCHW (zeros incl.) + occupancy written, B frames per launch"),
-        _lib.K_PILLAR_NHWC: dict(bytes=sum(n_pts) * 16 + B * 65 * H * Wd * 4, flops=0,
-                                 what="points read + canvas channels-last (zeros incl.) + occupancy written, B frames per launch"),
-        _lib.K_CORR_GEMM: dict(bytes=B * nf * L.n_cols * 2 + B * (nf + L.n_cols) * 128 * 2, flops=2.0 * B * nf * L.n_cols * 128,
-                               what="bf16 pyramid written + bf16 operands read, B samples per launch"),
-        _lib.K_DECODE_BEV: dict(bytes=B * H * Wd * (8 * 4 + 1 + 16 * 4 + 3), flops=0,
-                                what="net output + filled mask read, packed 16-float BEV row + class bytes written"),
-        _lib.K_DECODE_AGGR: dict(bytes=B * H * Wd * (1 + 16) + B * n_pad * (9 + 12), flops=0,
-                                 what="static-aggregated flow written per cell (4 floats) and per point (3 floats)"),
-        _lib.K_CORR_LOOKUP: dict(bytes=B * 196 * nf * 4 + B * nf * 4 * 8 * 32, flops=0,
-                                 what="fp32 lookup written + 8 tap rows x 32 B sectors per level read"),
-    }
-    # InstanceNorm glue of the two feature-encoder runs (B frames each): 17 normalised tensors per run -- 5 of 32 ch at
-    # H/2 (stem + layer1), 6 of 64 ch at H/4, 6 of 96 ch at H/8; two per stage also read a residual.  Average per launch.
-    if prof.get(_lib.K_IN_APPLY, (0, 0))[1] == 34 * prof_steps:
-        sizes = [(32 * (H // 2) * (Wd // 2), 5), (64 * (H // 4) * (Wd // 4), 6), (96 * (H // 8) * (Wd // 8), 6)]
-        elems = sum(e * n for e, n in sizes)
-        res_elems = sum(e * 2 for e, _ in sizes)
-        alg[_lib.K_IN_STATS] = dict(bytes=B * 4 * elems // 17, flops=0,
-                                    what="normalised tensor read once (average over the 17 tensors of an encoder run)")
-        alg[_lib.K_IN_APPLY] = dict(bytes=B * 4 * (2 * elems + res_elems) // 17, flops=0,
-                                    what="tensor read + written in place, residual read where the block joins "
-                                         "(average over the 17 tensors of an encoder run)")
-    kernels = []
-    for kid, (ms_k, n_k) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
-        name = lib.slimb200_kernel_name(kid).decode()
-        ent = {"kernel": name, "launches_per_step": n_k / prof_steps, "avg_ms": ms_k / n_k,
-               "share_of_step": (ms_k / prof_steps) / (ms_res / args.steps)}
-        if kid in alg:
-            gbs = alg[kid]["bytes"] / (ms_k / n_k * 1e-3) / 1e9
-            ent.update({"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": gbs / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": alg[kid]["bytes"],
-                        "what": alg[kid]["what"]})
-            if alg[kid]["flops"]:
-                tf = alg[kid]["flops"] / (ms_k / n_k * 1e-3) / 1e12
-                ent["tensor"] = {"achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"]}
-        kernels.append(ent)
-    dom = next((k for k in kernels if "bound" in k), None)
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if dom and os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("%s:%s:B%d" % (dom["kernel"], args.workload, B))
+    # ---- roofline: the dominant NORTH-STAR kernel (largest share of the step among pillar scatter / correlation GEMM /
+    # lookup) + all three stages (rank 0, live CUDA-event durations)
+    kernels, stages = main.stage_rooflines(prof, prof_steps, ms_res / args.steps)
     roofline = None
-    if dom:
-        roofline = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"],
-                    "unit": dom["unit"], "frac": dom["frac"], "traffic": traffic, "peak_source": peaks["source"] + " (of measured)"
-                    if peaks["source"] == "measured" else "fallback", "avg_launch_ms": dom["avg_ms"],
-                    "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"]}
+    if stages:
+        def share(st):
+            return st["avg_launch_ms"] * st.get("launches_per_step", 2)
+
+        dom_name = max(stages, key=lambda k: share(stages[k]))
+        dom = stages[dom_name]
+        roofline = {"stage": dom_name, "kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"],
+                    "unit": dom["unit"], "frac": dom["frac"], "traffic": dom["traffic"],
+                    "traffic_what": "mean dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel in the committed "
+                                    "ncu capture of one bench step (profiles/ncu_traffic.json), cold cache",
+                    "peak_source": (peaks["source"] + " (MEASURED_PEAKS.json)") if peaks["source"] == "measured" else "fallback (B200_PROFILING.md)",
+                    "avg_launch_ms": dom["avg_launch_ms"], "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
+                    "stages": stages}
         if "tensor" in dom:
             roofline["tensor"] = dom["tensor"]
 
+    if warmup_note:
+        config["warmup_note"] = warmup_note
+    config["timing"] = ("untimed preparation (2 forwards: cuDNN autotune + CUDA-graph capture), then exactly --warmup warm-up steps, "
+                        "then --steps timed steps between CUDA events")
+    config["outputs"] = "graph outputs handed out as views (outputs_alias_static_buffers=True); e2e copies the exported tensors"
+    config["lookup"] = ("lookup kernel + stock conv_stat_corr1" if args.no_fused_lookup else
+                        "lookup fused with conv_stat_corr1 + ReLU (tcgen05 tf32, slimb200_corr_lookup_conv)")
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": tot["ms_res_max"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": config, "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": main.h2d, "d2h_bytes_per_step": main.d2h,
                     "ms_per_step": tot["ms_e2e_max"] / args.steps},
             "gpu_launches": int(tot["launches"]), "roofline": roofline, "kernels": kernels,
             "other_mode": {"decode": other, "value": args.batch * world / (tot["ms_other_max"] / 1e3),
@@ -476,22 +556,58 @@ def main():
                            "ms_per_step": tot["ms_other_max"]},
             "memory_format": args.memory_format, "gru_loop": "eager launches" if args.no_cuda_graph else "CUDA graph",
             "precision": {"pillar": "f32", "correlation": "bf16 operands, f32 accumulate, bf16 storage",
+                          "lookup_conv": "tf32 operands (rna), f32 accumulate" if not args.no_fused_lookup else "stock cudnn",
                           "stock_convs": "cudnn " + args.conv_precision}}
+    if per_rank:
+        line["per_rank"] = per_rank
 
     # ---- CPU baseline (oracle port of the reference forward), N=1 only, bounded sample ----
     if world == 1 and not args.no_cpu_baseline:
-        (of, ob, _), times = run_oracle_pairs(cfg, sd, s0, s1, n_runs=3, warmup=1, min_seconds=10.0, max_runs=24)
+        (of, ob, _), times = run_oracle_pairs(main.cfg, main.sd, main.s0, main.s1, n_runs=3, warmup=1, min_seconds=10.0, max_runs=24)
         v = len(times) / sum(times)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                                "note": "oracle port (oracle/slim_forward.py, vectorised numpy voxeliser), not the reference's numba voxeliser / "
+                                        "mmcv op: a faithful port's speed, not the reference's",
                                 "sample": "%d timed runs (1 warm-up, %.1f s of CPU work) of 1 pair (B=1) of the same workload, fp32, all host "
                                           "threads" % (len(times), sum(times))}
         with torch.no_grad(), amp():
-            pf, pb = model(d0, d1, None)
-        valid = s0["pcl_ta"]["pcl_is_valid"][0]
+            pf, pb = main.model(main.d0, main.d1, None)
+        valid = main.s0["pcl_ta"]["pcl_is_valid"][0]
         epe = (pf[-1].static_flow[0].cpu() - of[-1]["pointwise_static_flow"][0]).norm(dim=-1)[valid]
         line["parity"] = {"per_point_static_flow_aee_m_vs_oracle": float(epe.mean()), "max_m": float(epe.max()), "limit_m": 0.01}
     if writer_line:
         line["export_with_writer"] = writer_line
+
+    # ---- configs[2] / configs[3]: short same-process lines for the nuScenes- and AV2-sized workloads (N=1 only) ----
+    if world == 1 and not args.no_other_workloads and args.workload == "K":
+        others = {}
+        del main
+        torch.cuda.empty_cache()
+        for wl, batch in (("N", args.batch), ("A", max(1, args.batch // 2))):
+            try:
+                ob_ = Bench(wl, batch, args.decode)
+                ob_.prepare()
+                for _ in range(3):
+                    ob_.step_resident()
+                n = max(5, args.steps // 2)
+                ms, _, _ = ob_.timed(ob_.step_resident, n)
+                pr = ob_.kernel_profile(3)
+                ob_.run_e2e(3)
+                ms_e, _, _ = ob_.timed(lambda: ob_.run_e2e(n), 1)
+                _, st = ob_.stage_rooflines(pr, 3, ms / n)
+                others[wl] = {"workload": "batch %d synthetic %s pairs (%dk pts/frame, %dx%d BEV)" % (
+                    batch, {"N": "nuScenes-sized", "A": "AV2-sized"}[wl], ob_.W["n_points"] // 1000, *ob_.W["img_grid_size"]),
+                    "value": batch * n / (ms / 1e3), "e2e": batch * n / (ms_e / 1e3), "unit": UNIT, "steps": n, "warmup": 3,
+                    "ms_per_step": ms / n,
+                    "stages": {k: {kk: v[kk] for kk in ("kernel", "achieved", "frac", "avg_launch_ms", "tensor", "stage_incl_prep") if kk in v}
+                               for k, v in st.items()}}
+                del ob_
+                torch.cuda.empty_cache()
+            except Exception as e:  # a failed side line must not take the headline down
+                others[wl] = {"error": repr(e)[:300]}
+        line["other_workloads"] = others
+        if roofline is not None:
+            roofline["other_workloads"] = {k: v.get("stages") for k, v in others.items()}
     out.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

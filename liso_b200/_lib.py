@@ -165,6 +165,7 @@ SYMBOLS = {
     "slimb200_kernel_name": (C.c_char_p, [C.c_int32]),
 }
 N_KERNELS = 34
+K_POINT_KEYS, K_SCAN_LOCAL, K_SCAN_GLOBAL, K_RANK_SCATTER = 0, 1, 2, 3
 K_TILE_ENCODE, K_PILLAR_NHWC, K_FEAT_TRANSPOSE, K_FEAT_PACK, K_CORR_GEMM, K_CORR_LOOKUP = 6, 7, 8, 9, 10, 11
 K_DECODE_BEV, K_DECODE_POINTS, K_DECODE_AGGR, K_RAFT_OUTPUT = 14, 15, 17, 18
 K_IN_STATS, K_IN_FINALIZE, K_IN_APPLY = 24, 25, 26
