@@ -14,7 +14,7 @@
 //   1. lane (p, r) computes the sample position of window offset r on BOTH axes (7 of 8 lanes; the reference's
 //      normalise / un-normalise fp32 round trip, division by the precomputed reciprocal), floors and masked weights;
 //      the window origin is the minimum over the 8 lanes of the pixel (3 butterfly shuffles per axis)
-//   2. the x weights of all 7 offsets reach every lane of the pixel through a 256-byte scratch per warp
+//   2. the x weights of all 7 offsets reach every lane of the pixel by shuffles
 //   3. the lane fetches ITS window row (two 16-byte streaming loads, lanes 4r..4r+3 share the DRAM burst), re-aligns it
 //      and forms the 7 horizontal blends h[r][i]
 //   4. the vertical blend of output row j needs h[j] and h[j + 1]: one shuffle per value from the lane 4 above
@@ -23,7 +23,8 @@
 // take the 3-tap variant (weights (w0, w1, 0) or (0, w0, w1): the zero adds an exact zero) on a 9 x 9 window; pixels
 // with non-finite / absurd coordinates take predicated 4-tap loads.
 //
-// k_lookup_conv_tf32: persistent CTAs, 1024 threads = 128 pixels x 8 rows per tile, the four levels in turn.  Lane
+// k_lookup_conv_tf32: persistent CTAs, 512 threads = 64 pixels x 8 rows, two passes per 128-pixel tile, the window loads
+// of four (pass, level) units in flight per thread while an earlier unit is blended (software pipeline).  Lane
 // (p, j) writes its 7 values (rounded to tf32) + one zero as two 16-byte chunks of row `pixel` of a K-major,
 // 128-byte-swizzled A tile in shared memory (K slot = level * 56 + j * 8 + i); the weights (N x 224 tf32, packed once
 // per weight tensor by k_lookup_conv_pack in the same slot order) arrive with one bulk copy and stay for the whole
@@ -60,51 +61,73 @@ __device__ __forceinline__ int group_min(int v) {  // over the 8 lanes (rows) of
   return v;
 }
 
-// One level of 4 pixels x 8 rows (a whole warp, every lane must call).  `s_w`: this warp's scratch, 64 floats.
+// One level of 4 pixels x 8 rows (a whole warp, every lane must call), split in two so that the window loads of several
+// (pixel, level) units can be in flight while an earlier one is blended (the fused kernel keeps four):
+//   rows_prepare  positions, floors, weights, window origin, the lane's two 16-byte loads (nothing waits for them)
+//   rows_finish   re-alignment, x weights of all offsets (shuffles), horizontal + vertical blend, sink
+struct RowState {
+  uint32_t raw[8];         // the lane's window row as loaded
+  float wx0, wx1, wy0, wy1;  // masked weights of window offset r on both axes (this lane's offset)
+  int sft;                 // element shift of window column 0 inside raw
+  int row0;                // pyramid column of window element (0, 0)
+  int dx, dy;              // floor - origin of this lane's offset: 0 regular, 1 shifted, else slow (meaningless for r == 7)
+};
+
+struct LevelGeo {
+  int W, H, off;
+  float inv, swm1, shm1, rw, rh;  // 1 / 2^level, size - 1 and the correctly rounded reciprocals
+};
+
+__device__ __forceinline__ LevelGeo level_geo(const LookupGeo& G, int level) {
+  LevelGeo g;
+  g.W = pick4(G.lw, level);
+  g.H = pick4(G.lh, level);
+  g.off = pick4(G.lo, level);
+  g.inv = 1.0f / (float)(1 << level);  // coords / 2**l is exact
+  g.swm1 = (float)(g.W - 1);
+  g.shm1 = (float)(g.H - 1);
+  g.rw = __frcp_rn(g.swm1);
+  g.rh = __frcp_rn(g.shm1);
+  return g;
+}
+
+__device__ __forceinline__ void rows_prepare(RowState& st, const __nv_bfloat16* __restrict__ base, int panel_stride, int pitch,
+                                             const LevelGeo& g, float cx, float cy) {
+  const int r = lane_id() >> 2;
+  int fx, fy;
+  one_tap(cx, g.inv, r, g.W, g.swm1, g.rw, st.wx0, st.wx1, fx);
+  one_tap(cy, g.inv, r, g.H, g.shm1, g.rh, st.wy0, st.wy1, fy);
+  if (r == ROWS - 1) fx = fy = INT_MAX;  // offsets 0..6 only
+  const int xb = group_min(fx), yb = group_min(fy);
+  st.dx = fx - xb;
+  st.dy = fy - yb;
+  // window element (0, 0); origins beyond +-2^18 (every tap outside, zero weights) are clamped so that the index stays an int
+  st.row0 = g.off + max(min(yb, 1 << 18), -(1 << 18)) * g.W + max(min(xb, 1 << 18), -(1 << 18));
+  st.sft = fetch_row(base, panel_stride, pitch, st.row0 + r * g.W, st.raw);
+}
+
 // Lane (p, j), j < 7, ends with sink.emit_row(j, o) where o[i] = out[i][j]: the value of channel i * 7 + j
 // (i offsets x, j offsets y: the reference's transposed window, corr.py:29-41).
 template <class Sink>
-__device__ __forceinline__ void lookup_rows(const __nv_bfloat16* __restrict__ base, int panel_stride, int pitch, int W, int H, int off,
-                                            float cx, float cy, float inv, bool live, float* __restrict__ s_w, Sink& sink) {
+__device__ __forceinline__ void rows_finish(const RowState& st, const __nv_bfloat16* __restrict__ base, int panel_stride, int pitch,
+                                            const LevelGeo& g, float cx, float cy, bool live, Sink& sink) {
   const int lane = lane_id();
   const int p = lane & 3, r = lane >> 2;
-  const float swm1 = (float)(W - 1), shm1 = (float)(H - 1);
-  const float rw = __frcp_rn(swm1), rh = __frcp_rn(shm1);
-  float wx0, wx1, wy0, wy1;
-  int fx, fy;
-  one_tap(cx, inv, r, W, swm1, rw, wx0, wx1, fx);
-  one_tap(cy, inv, r, H, shm1, rh, wy0, wy1, fy);
-  if (r == ROWS - 1) fx = fy = INT_MAX;  // offsets 0..6 only
-  const int xb = group_min(fx), yb = group_min(fy);
-  const int dx = fx - xb, dy = fy - yb;  // 0 (regular), 1 (shifted), else slow; meaningless for r == 7
   const bool rowlane = r < ROWS - 1;
-  const unsigned bad = __ballot_sync(FULL, live && rowlane && ((unsigned)dx > 1u || (unsigned)dy > 1u));
-  const unsigned shx = __ballot_sync(FULL, rowlane && dx == 1), shy = __ballot_sync(FULL, rowlane && dy == 1);
-  const bool pixel_slow = (bad & (0x11111111u << p)) != 0u;
-
-  // x weights of all offsets to every lane of the pixel
-  s_w[p * 16 + r] = wx0;
-  s_w[p * 16 + 8 + r] = wx1;
-  __syncwarp();
-  float ax0[8], ax1[8];
-  {
-    const float4 a = *reinterpret_cast<const float4*>(s_w + p * 16), b = *reinterpret_cast<const float4*>(s_w + p * 16 + 4);
-    const float4 c = *reinterpret_cast<const float4*>(s_w + p * 16 + 8), d = *reinterpret_cast<const float4*>(s_w + p * 16 + 12);
-    ax0[0] = a.x; ax0[1] = a.y; ax0[2] = a.z; ax0[3] = a.w; ax0[4] = b.x; ax0[5] = b.y; ax0[6] = b.z; ax0[7] = b.w;
-    ax1[0] = c.x; ax1[1] = c.y; ax1[2] = c.z; ax1[3] = c.w; ax1[4] = d.x; ax1[5] = d.y; ax1[6] = d.z; ax1[7] = d.w;
+  const unsigned bad = __ballot_sync(FULL, live && rowlane && ((unsigned)st.dx > 1u || (unsigned)st.dy > 1u));
+  const unsigned shx = __ballot_sync(FULL, rowlane && st.dx == 1), shy = __ballot_sync(FULL, rowlane && st.dy == 1);
+  // x weights of all 7 offsets: offset i lives in lane (p, i)
+  float ax0[WIN], ax1[WIN];
+#pragma unroll
+  for (int i = 0; i < WIN; ++i) {
+    ax0[i] = __shfl_sync(FULL, st.wx0, i * 4 + p);
+    ax1[i] = __shfl_sync(FULL, st.wx1, i * 4 + p);
   }
-  __syncwarp();  // (the next level overwrites the scratch)
-
-  uint32_t raw[8];
-  // window element (0, 0); origins beyond +-2^18 (every tap outside, zero weights) are clamped so that the index stays an int
-  const int row0 = off + max(min(yb, 1 << 18), -(1 << 18)) * W + max(min(xb, 1 << 18), -(1 << 18));
-  const int sft = fetch_row(base, panel_stride, pitch, row0 + r * W, raw);
   float o[WIN];
-
   if (bad == 0u && (shx | shy) == 0u) {
     // ---- regular windows: 8 x 8, two taps per axis ----
     uint32_t win[4];
-    realign<4>(raw, sft, win);
+    realign<4>(st.raw, st.sft, win);
     sink.begin();
     float h[WIN];
     float e0 = wel<4>(win, 0);
@@ -117,13 +140,13 @@ __device__ __forceinline__ void lookup_rows(const __nv_bfloat16* __restrict__ ba
 #pragma unroll
     for (int i = 0; i < WIN; ++i) {
       const float hn = __shfl_down_sync(FULL, h[i], 4);  // row r + 1 of the same pixel
-      o[i] = fmaf(hn, wy1, h[i] * wy0);
+      o[i] = fmaf(hn, st.wy1, h[i] * st.wy0);
     }
   } else {
     // ---- shifted windows: 9 x 9, three taps per axis, one weight of the three is zero ----
     uint32_t raw8[8], win[5], win8[5];
-    const int sft8 = fetch_row(base, panel_stride, pitch, row0 + 8 * W, raw8);  // window row 8 (needed by row 6 only)
-    realign<5>(raw, sft, win);
+    const int sft8 = fetch_row(base, panel_stride, pitch, st.row0 + 8 * g.W, raw8);  // window row 8 (needed by row 6 only)
+    realign<5>(st.raw, st.sft, win);
     realign<5>(raw8, sft8, win8);
     sink.begin();
     float h[WIN], h8[WIN];
@@ -134,8 +157,8 @@ __device__ __forceinline__ void lookup_rows(const __nv_bfloat16* __restrict__ ba
       h[i] = fmaf(wel<5>(win, i + 2), c, fmaf(wel<5>(win, i + 1), bq, wel<5>(win, i) * a));
       h8[i] = fmaf(wel<5>(win8, i + 2), c, fmaf(wel<5>(win8, i + 1), bq, wel<5>(win8, i) * a));
     }
-    const bool t = dy == 1;
-    const float ay = t ? 0.f : wy0, by = t ? wy0 : wy1, cyw = t ? wy1 : 0.f;
+    const bool t = st.dy == 1;
+    const float ay = t ? 0.f : st.wy0, by = t ? st.wy0 : st.wy1, cyw = t ? st.wy1 : 0.f;
 #pragma unroll
     for (int i = 0; i < WIN; ++i) {
       const float hn1 = __shfl_down_sync(FULL, h[i], 4);
@@ -143,10 +166,12 @@ __device__ __forceinline__ void lookup_rows(const __nv_bfloat16* __restrict__ ba
       if (r == ROWS - 2) hn2 = h8[i];
       o[i] = fmaf(hn2, cyw, fmaf(hn1, by, h[i] * ay));
     }
+    const bool pixel_slow = (bad & (0x11111111u << p)) != 0u;
     if (pixel_slow && live && rowlane) {  // ---- anything else ----
-      const float iy = sample_pos2(cy, inv, r - R, shm1, rh);
+      const float iy = sample_pos2(cy, g.inv, r - R, g.shm1, g.rh);
 #pragma unroll
-      for (int i = 0; i < WIN; ++i) o[i] = sample_slow2(base, panel_stride, W, H, off, sample_pos2(cx, inv, i - R, swm1, rw), iy);
+      for (int i = 0; i < WIN; ++i)
+        o[i] = sample_slow2(base, panel_stride, g.W, g.H, g.off, sample_pos2(cx, g.inv, i - R, g.swm1, g.rw), iy);
     }
   }
   if (rowlane) sink.emit_row(r, o);
@@ -175,7 +200,6 @@ template <bool NHWC>
 __global__ void __launch_bounds__(V3_THREADS, 4) k_corr_lookup_v3(const __nv_bfloat16* __restrict__ pyr, const LookupGeo G,
                                                                   const float* __restrict__ coords, float* __restrict__ out) {
   __shared__ __align__(16) float s_stage[NHWC ? V3_PIX * V3_PITCH_P : V3_NCH * V3_PITCH_C];
-  __shared__ __align__(16) float s_w[V3_THREADS / 32][64];
   const int lane = lane_id(), warp = warp_id();
   const int b = blockIdx.y;
   const int i0 = blockIdx.x * V3_PIX;
@@ -189,10 +213,11 @@ __global__ void __launch_bounds__(V3_THREADS, 4) k_corr_lookup_v3(const __nv_bfl
   const int n_ch = G.levels * WIN * WIN;
 #pragma unroll 1
   for (int level = 0; level < G.levels; ++level) {
-    const int W = pick4(G.lw, level), H = pick4(G.lh, level), off = pick4(G.lo, level);
-    const float inv = 1.0f / (float)(1 << level);  // coords / 2**l is exact
+    const LevelGeo g = level_geo(G, level);
     SinkStage<NHWC> sink{NHWC ? s_stage + pl * V3_PITCH_P + level * WIN * WIN : s_stage + level * WIN * WIN * V3_PITCH_C + pl};
-    lookup_rows(base, panel_stride, G.pitch, W, H, off, cx, cy, inv, live, s_w[warp], sink);
+    RowState st;
+    rows_prepare(st, base, panel_stride, G.pitch, g, cx, cy);
+    rows_finish(st, base, panel_stride, G.pitch, g, cx, cy, live, sink);
   }
   __syncthreads();
   const int n_pix = min(V3_PIX, G.nf - i0);
@@ -209,7 +234,9 @@ __global__ void __launch_bounds__(V3_THREADS, 4) k_corr_lookup_v3(const __nv_bfl
 
 // ------------------------------------------------------------------------------------------ fused lookup + 1x1 conv
 constexpr int F_PIX = 128;                  // pixels per tile = MMA M
-constexpr int F_THREADS = F_PIX * ROWS;     // 1024: one thread per (pixel, window row), the levels in turn
+constexpr int F_PASSES = 2;                 // a tile is gathered in two passes of 64 pixels
+constexpr int F_PASS_PIX = F_PIX / F_PASSES;
+constexpr int F_THREADS = F_PASS_PIX * ROWS;  // 512: one thread per (pixel of the pass, window row)
 constexpr int F_LEVELS = 4;
 constexpr int F_K = F_LEVELS * KPL;         // 224
 constexpr int F_KBLK = 32;                  // tf32 elements per 128-byte swizzle row
@@ -217,7 +244,6 @@ constexpr int F_KBLOCKS = F_K / F_KBLK;     // 7
 constexpr int F_UMMA_K = 8;                 // tf32: 32 bytes of K per instruction
 constexpr uint32_t F_A_KBLK_BYTES = F_PIX * 128;            // 16 KB
 constexpr uint32_t F_A_BYTES = F_KBLOCKS * F_A_KBLK_BYTES;  // 112 KB
-constexpr uint32_t F_SCRATCH_BYTES = (F_THREADS / 32) * 64 * 4;  // 8 KB: x-weight exchange, 256 bytes per warp
 constexpr int F_MAX_N = 96;
 constexpr uint32_t F_ACC_COLS = 128;        // TMEM columns per accumulator (N <= 96 fp32 columns)
 constexpr uint32_t F_TMEM_COLS = 2 * F_ACC_COLS;  // two accumulators: the MMAs of tile t overlap the epilogue of tile t - 1
@@ -226,7 +252,7 @@ constexpr uint32_t F_TMEM_COLS = 2 * F_ACC_COLS;  // two accumulators: the MMAs 
 __host__ __device__ constexpr uint32_t packed_w_bytes(int n) { return (uint32_t)F_KBLOCKS * (uint32_t)n * 128u; }
 __host__ __device__ constexpr uint32_t packed_bytes(int n) { return packed_w_bytes(n) + (uint32_t)n * 4u; }
 __host__ __device__ constexpr uint32_t fused_smem_bytes(int n) {
-  return F_A_BYTES + packed_bytes(n) + F_SCRATCH_BYTES + 64u /*barriers + tmem ptr*/ + 1024u /*align*/;
+  return F_A_BYTES + packed_bytes(n) + 64u /*barriers + tmem ptr*/ + 1024u /*align*/;
 }
 static_assert(fused_smem_bytes(F_MAX_N) <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
 
@@ -303,10 +329,34 @@ __device__ __forceinline__ void fused_epilogue(uint32_t tmem_acc, int warp, int 
   }
 }
 
-// Per tile: every warp gathers its 4 pixels level by level and writes their chunks of the A tile; ONE __syncthreads;
-// one thread issues the 28 MMAs of the tile into accumulator (tile & 1); warps 0..3 then write out the PREVIOUS tile
-// (its MMAs finished long ago) while the tensor core works, and everybody moves on to the next tile -- whose first A
-// store waits for this tile's MMAs (an mbarrier that has normally fired by then).
+// Software pipeline: a thread works on the "units" (tile, pass, level) of its CTA in order -- 2 passes of 64 pixels x 4
+// levels per 128-pixel tile -- and keeps the window loads of FOUR units in flight (one RowState per level): unit u is
+// finished (blended, written to the A tile) while the loads of units u + 1 .. u + 3 travel, then the unit that will reuse
+// its state (same level, next pass or next tile) is prepared.  The DRAM latency of the gather is therefore paid once at
+// kernel start, not once per level.  Per tile: ONE __syncthreads; one thread issues the 28 MMAs of the tile into
+// accumulator (tile & 1); warps 0..3 then write out the PREVIOUS tile (its MMAs finished long ago) while the tensor
+// core works; the first A store of the next tile waits for this tile's MMAs (an mbarrier that has normally fired).
+struct TileCtx {  // what a lane needs to know about its two pixels (one per pass) of a tile
+  float cx[F_PASSES], cy[F_PASSES];
+  uint32_t base[F_PASSES];  // element offset of the pixel's pyramid rows (fits 32 bits: make_geo checks)
+  bool live[F_PASSES];
+};
+
+__device__ __forceinline__ TileCtx load_tile_ctx(const LookupGeo& G, const float* __restrict__ coords, int tile, int prow0, int n_tiles) {
+  TileCtx c;
+  const bool tile_ok = tile < n_tiles;
+  const int b = tile_ok ? tile / G.m_tiles : 0, mt = tile_ok ? tile - b * G.m_tiles : 0;
+#pragma unroll
+  for (int q = 0; q < F_PASSES; ++q) {
+    const int pix = mt * F_PIX + q * F_PASS_PIX + prow0;
+    c.live[q] = tile_ok && pix < G.nf;
+    c.cx[q] = c.live[q] ? __ldg(coords + ((size_t)b * 2 + 0) * G.nf + pix) : 0.f;
+    c.cy[q] = c.live[q] ? __ldg(coords + ((size_t)b * 2 + 1) * G.nf + pix) : 0.f;
+    c.base[q] = (uint32_t)pixel_base(G, b, c.live[q] ? pix : 0);
+  }
+  return c;
+}
+
 __global__ void __launch_bounds__(F_THREADS, 1)
 k_lookup_conv_tf32(const __nv_bfloat16* __restrict__ pyr, const LookupGeo G, const float* __restrict__ coords,
                    const uint8_t* __restrict__ packed, float* __restrict__ out, int out_pitch, int N, int relu, int n_tiles) {
@@ -317,8 +367,7 @@ k_lookup_conv_tf32(const __nv_bfloat16* __restrict__ pyr, const LookupGeo G, con
   const uint32_t smem_w = smem_base + F_A_BYTES;
   const uint32_t w_kblk_bytes = (uint32_t)N * 128u;
   const float* const s_bias = reinterpret_cast<const float*>(gen_base + F_A_BYTES + packed_w_bytes(N));
-  float* const s_scratch = reinterpret_cast<float*>(gen_base + F_A_BYTES + packed_bytes(N));  // 16-byte aligned (N % 32 == 0)
-  const uint32_t bar0 = smem_w + packed_bytes(N) + F_SCRATCH_BYTES;
+  const uint32_t bar0 = smem_w + packed_bytes(N);  // 8-byte aligned (N % 32 == 0)
   auto mma_bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   const uint32_t w_bar = bar0 + 16u;
   const uint32_t tmem_ptr_smem = bar0 + 24u;
@@ -348,30 +397,48 @@ k_lookup_conv_tf32(const __nv_bfloat16* __restrict__ pyr, const LookupGeo G, con
   // instruction descriptor: D = f32 (1 << 4), A = B = tf32 (2 << 7, 2 << 10), K-major, N >> 3 at [17,23), M >> 4 at [24,29)
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(F_PIX >> 4) << 24);
 
-  const int prow = warp * WARP_PIX + (lane & 3);  // pixel (= A row) of the tile this lane works for
+  const int prow0 = warp * WARP_PIX + (lane & 3);  // pixel (= A row) of pass 0 this lane works for; pass q: + 64 q
   const int panel_stride = G.m_tiles * 2 * 8192;
-  const uint32_t a_row = smem_a + (uint32_t)(prow >> 3) * 1024u + (uint32_t)(prow & 7) * 128u;
-  float* const s_w = s_scratch + warp * 64;
+  const uint32_t a_row0 = smem_a + (uint32_t)(prow0 >> 3) * 1024u + (uint32_t)(prow0 & 7) * 128u;
+  const LevelGeo g0 = level_geo(G, 0), g1 = level_geo(G, 1), g2 = level_geo(G, 2), g3 = level_geo(G, 3);
+  RowState s0, s1, s2, s3;  // units in flight, one per level
+
+  int tile = blockIdx.x;
+  TileCtx cur = load_tile_ctx(G, coords, tile, prow0, n_tiles);
+  rows_prepare(s0, pyr + cur.base[0], panel_stride, G.pitch, g0, cur.cx[0], cur.cy[0]);
+  rows_prepare(s1, pyr + cur.base[0], panel_stride, G.pitch, g1, cur.cx[0], cur.cy[0]);
+  rows_prepare(s2, pyr + cur.base[0], panel_stride, G.pitch, g2, cur.cx[0], cur.cy[0]);
+  rows_prepare(s3, pyr + cur.base[0], panel_stride, G.pitch, g3, cur.cx[0], cur.cy[0]);
 
   int it = 0;  // tiles this CTA has started
   int prev_b = 0, prev_mt = 0;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+  for (; tile < n_tiles; tile += gridDim.x, ++it) {
     const int b = tile / G.m_tiles, mt = tile - b * G.m_tiles;
-    const int pix = mt * F_PIX + prow;
-    const bool live = pix < G.nf;
-    {
-      const float cx = live ? __ldg(coords + ((size_t)b * 2 + 0) * G.nf + pix) : 0.f;
-      const float cy = live ? __ldg(coords + ((size_t)b * 2 + 1) * G.nf + pix) : 0.f;
-      const __nv_bfloat16* base = pyr + pixel_base(G, b, live ? pix : 0);
-#pragma unroll 1
-      for (int level = 0; level < F_LEVELS; ++level) {
-        const int W = pick4(G.lw, level), H = pick4(G.lh, level), off = pick4(G.lo, level);
-        const float inv = 1.0f / (float)(1 << level);
-        SinkA sink{a_row, (uint32_t)(prow & 7), level * (KPL / 4), (it > 0 && level == 0) ? mma_bar((it - 1) & 1) : 0u,
-                   (uint32_t)((it - 1) >> 1) & 1u};
-        lookup_rows(base, panel_stride, G.pitch, W, H, off, cx, cy, inv, live, s_w, sink);
-      }
+    const TileCtx nxt = load_tile_ctx(G, coords, tile + gridDim.x, prow0, n_tiles);  // (consumed four units later)
+#pragma unroll
+    for (int q = 0; q < F_PASSES; ++q) {
+      // the unit that reuses a state: same level, next pass of this tile or pass 0 of the next tile (dead lanes of a CTA
+      // without a next tile fetch pixel 0 of sample 0: harmless, never finished)
+      const bool last = q == F_PASSES - 1;
+      const float ncx = last ? nxt.cx[0] : cur.cx[q + 1 < F_PASSES ? q + 1 : 0], ncy = last ? nxt.cy[0] : cur.cy[q + 1 < F_PASSES ? q + 1 : 0];
+      const __nv_bfloat16* nbase = pyr + (last ? nxt.base[0] : cur.base[q + 1 < F_PASSES ? q + 1 : 0]);
+      const __nv_bfloat16* base = pyr + cur.base[q];
+      const uint32_t a_row = a_row0 + (uint32_t)q * (F_PASS_PIX / 8) * 1024u;
+      SinkA sink{a_row, (uint32_t)(prow0 & 7), 0, (it > 0 && q == 0) ? mma_bar((it - 1) & 1) : 0u, (uint32_t)((it - 1) >> 1) & 1u};
+      rows_finish(s0, base, panel_stride, G.pitch, g0, cur.cx[q], cur.cy[q], cur.live[q], sink);
+      rows_prepare(s0, nbase, panel_stride, G.pitch, g0, ncx, ncy);
+      sink.wait_bar = 0u;
+      sink.q0 = KPL / 4;
+      rows_finish(s1, base, panel_stride, G.pitch, g1, cur.cx[q], cur.cy[q], cur.live[q], sink);
+      rows_prepare(s1, nbase, panel_stride, G.pitch, g1, ncx, ncy);
+      sink.q0 = 2 * (KPL / 4);
+      rows_finish(s2, base, panel_stride, G.pitch, g2, cur.cx[q], cur.cy[q], cur.live[q], sink);
+      rows_prepare(s2, nbase, panel_stride, G.pitch, g2, ncx, ncy);
+      sink.q0 = 3 * (KPL / 4);
+      rows_finish(s3, base, panel_stride, G.pitch, g3, cur.cx[q], cur.cy[q], cur.live[q], sink);
+      rows_prepare(s3, nbase, panel_stride, G.pitch, g3, ncx, ncy);
     }
+    cur = nxt;
     fence_proxy_async_smem();  // the A rows were written through the generic proxy, the MMA reads through the async one
     __syncthreads();
     if (warp == 0) {
@@ -462,6 +529,8 @@ extern "C" int slimb200_corr_lookup_conv(const void* pyramid, int32_t pyramid_dt
   if (pyramid_dtype != SLIMB200_DTYPE_BF16 || radius != R || L->levels != F_LEVELS) return SLIMB200_E_UNSUPPORTED;
   if (c_out < 32 || c_out > F_MAX_N || (c_out & 31)) return SLIMB200_E_UNSUPPORTED;
   if (out_pitch < c_out || (out_pitch & 3)) return SLIMB200_E_INVALID;
+  // (the kernel keeps 32-bit element offsets into the pyramid)
+  if ((unsigned long long)L->batch * L->n_panels * L->rows_padded * SLIMB200_PANEL_COLS > 0xffffffffULL) return SLIMB200_E_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(pyramid) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) ||
       (reinterpret_cast<uintptr_t>(packed) & 15))
     return SLIMB200_E_ALIGNMENT;
