@@ -204,7 +204,8 @@ int slimb200_corr_lookup(const void* pyramid, int32_t pyramid_dtype, const slimb
  * corr_lookup_conv_pack: once per weight tensor -- weight: device (c_out, levels*49) f32 = conv weight
  *   (c_out, levels*49, 1, 1); bias: device (c_out) f32 or NULL; packed: device, slimb200_corr_lookup_conv_packed_bytes(c_out)
  *   bytes, 16-byte aligned: the tf32 B operand in its shared-memory layout (7 K blocks of c_out rows x 128 bytes,
- *   128-byte swizzle, K slot l*56 + c, zero padded) followed by the biases.
+ *   128-byte swizzle, zero padded to 56 K slots per level; one image per K-slot order of the two fused kernels) followed
+ *   by the biases.
  * corr_lookup_conv: out: device, channels-last rows: pixel (b, y, x) at out + ((b*h + y)*w + x) * out_pitch, c_out floats
  *   each; out_pitch >= c_out floats, multiple of 4 (a channel slice of a wider channels-last tensor works); 16-byte
  *   aligned.  relu: 0 / 1. */
@@ -219,6 +220,9 @@ int slimb200_corr_lookup_conv(const void* pyramid, int32_t pyramid_dtype, const 
  * staged in shared memory), 1 (default) = one thread per (pixel, level), registers only (csrc/corr_lookup2.cu), 2 = one
  * thread per window row (csrc/corr_lookup3.cu; the fused lookup + convolution is built on it).  Returns the previous value; negative values only query. */
 int slimb200_lookup_generation(int32_t generation);
+/* Same for the fused lookup + convolution: 3 = row-per-thread gather, A tile in shared memory (csrc/corr_lookup3.cu);
+ * 4 (default) = (pixel, level)-per-thread gather with cp.async landing slots, A tile in tensor memory (csrc/corr_lookup4.cu). */
+int slimb200_lookup_conv_generation(int32_t generation);
 
 /* ------------------------------------------------------------------------------------------
  * output decoder.  Replaces HeadDecoder.forward (liso/slim/model/head_decoder.py:410-496,

@@ -111,6 +111,7 @@ SYMBOLS = {
          C.c_void_p, C.c_int32, C.c_void_p],
     ),
     "slimb200_lookup_generation": (C.c_int, [C.c_int32]),
+    "slimb200_lookup_conv_generation": (C.c_int, [C.c_int32]),
     "slimb200_preprocess_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.POINTER(PreprocessParams)]),
     "slimb200_preprocess_points": (
         C.c_int,

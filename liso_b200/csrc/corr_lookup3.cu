@@ -248,11 +248,13 @@ constexpr int F_MAX_N = 96;
 constexpr uint32_t F_ACC_COLS = 128;        // TMEM columns per accumulator (N <= 96 fp32 columns)
 constexpr uint32_t F_TMEM_COLS = 2 * F_ACC_COLS;  // two accumulators: the MMAs of tile t overlap the epilogue of tile t - 1
 // packed weights (slimb200_corr_lookup_conv_pack): the B operand exactly as it sits in shared memory -- 7 K blocks of
-// N rows x 128 bytes (32 tf32 values, 128-byte swizzle) -- followed by the N fp32 biases
+// N rows x 128 bytes (32 tf32 values, 128-byte swizzle) -- in the K-slot order of each fused kernel (image 0: level * 56 +
+// j * 8 + i for the row-per-thread kernel of this file, image 1: level * 56 + i * 7 + j for csrc/corr_lookup4.cu),
+// followed by the N fp32 biases
 __host__ __device__ constexpr uint32_t packed_w_bytes(int n) { return (uint32_t)F_KBLOCKS * (uint32_t)n * 128u; }
-__host__ __device__ constexpr uint32_t packed_bytes(int n) { return packed_w_bytes(n) + (uint32_t)n * 4u; }
+__host__ __device__ constexpr uint32_t packed_bytes(int n) { return 2u * packed_w_bytes(n) + (uint32_t)n * 4u; }
 __host__ __device__ constexpr uint32_t fused_smem_bytes(int n) {
-  return F_A_BYTES + packed_bytes(n) + 64u /*barriers + tmem ptr*/ + 1024u /*align*/;
+  return F_A_BYTES + packed_w_bytes(n) + (uint32_t)n * 4u + 64u /*barriers + tmem ptr*/ + 1024u /*align*/;
 }
 static_assert(fused_smem_bytes(F_MAX_N) <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
 
@@ -262,7 +264,8 @@ __device__ __forceinline__ uint32_t to_tf32(float v) {
   return r;
 }
 
-// K slot l * 56 + j * 8 + i of row n holds W[n][l * 49 + i * 7 + j] (i < 7) or 0 (i == 7), rounded to tf32
+// image 0: K slot l * 56 + j * 8 + i of row n holds W[n][l * 49 + i * 7 + j] (i < 7) or 0 (i == 7); image 1: K slot
+// l * 56 + c holds W[n][l * 49 + c] (c < 49) or 0; both rounded to tf32
 __global__ void __launch_bounds__(256) k_lookup_conv_pack(const float* __restrict__ weight, const float* __restrict__ bias, int N,
                                                           uint8_t* __restrict__ packed) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -270,12 +273,15 @@ __global__ void __launch_bounds__(256) k_lookup_conv_pack(const float* __restric
     const int n = idx / F_K, kk = idx - n * F_K;
     const int l = kk / KPL, c = kk - l * KPL;
     const int j = c >> 3, i = c & 7;
-    const float v = i < WIN ? __ldg(weight + (size_t)n * (F_LEVELS * WIN * WIN) + l * WIN * WIN + i * WIN + j) : 0.f;
+    const float* wrow = weight + (size_t)n * (F_LEVELS * WIN * WIN) + l * WIN * WIN;
+    const float v0 = i < WIN ? __ldg(wrow + i * WIN + j) : 0.f;
+    const float v1 = c < WIN * WIN ? __ldg(wrow + c) : 0.f;
     const uint32_t off = (uint32_t)(kk >> 5) * ((uint32_t)N * 128u) + (uint32_t)(n >> 3) * 1024u + (uint32_t)(n & 7) * 128u +
                          (((uint32_t)((kk & 31) >> 2) ^ (uint32_t)(n & 7)) << 4) + (uint32_t)(kk & 3) * 4u;
-    *reinterpret_cast<uint32_t*>(packed + off) = to_tf32(v);
+    *reinterpret_cast<uint32_t*>(packed + off) = to_tf32(v0);
+    *reinterpret_cast<uint32_t*>(packed + packed_w_bytes(N) + off) = to_tf32(v1);
   }
-  if (idx < N) reinterpret_cast<float*>(packed + packed_w_bytes(N))[idx] = bias ? __ldg(bias + idx) : 0.f;
+  if (idx < N) reinterpret_cast<float*>(packed + 2u * packed_w_bytes(N))[idx] = bias ? __ldg(bias + idx) : 0.f;
 }
 
 // A-operand sink: lane (p, j) owns chunks 2j, 2j + 1 of the level's 14 chunks in row `pixel` of the swizzled K-major tile
@@ -367,7 +373,7 @@ k_lookup_conv_tf32(const __nv_bfloat16* __restrict__ pyr, const LookupGeo G, con
   const uint32_t smem_w = smem_base + F_A_BYTES;
   const uint32_t w_kblk_bytes = (uint32_t)N * 128u;
   const float* const s_bias = reinterpret_cast<const float*>(gen_base + F_A_BYTES + packed_w_bytes(N));
-  const uint32_t bar0 = smem_w + packed_bytes(N);  // 8-byte aligned (N % 32 == 0)
+  const uint32_t bar0 = smem_w + packed_w_bytes(N) + (uint32_t)N * 4u;  // 8-byte aligned (N % 32 == 0)
   auto mma_bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   const uint32_t w_bar = bar0 + 16u;
   const uint32_t tmem_ptr_smem = bar0 + 24u;
@@ -379,9 +385,12 @@ k_lookup_conv_tf32(const __nv_bfloat16* __restrict__ pyr, const LookupGeo G, con
     mbar_init(w_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     // weights + biases: one bulk copy of the packed image (L2 -> shared memory), under the first tile's gather
-    mbar_expect_tx(w_bar, packed_bytes(N));
+    mbar_expect_tx(w_bar, packed_w_bytes(N) + (uint32_t)N * 4u);
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_w), "l"(packed),
-                 "r"(packed_bytes(N)), "r"(w_bar)
+                 "r"(packed_w_bytes(N)), "r"(w_bar)
+                 : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_w + packed_w_bytes(N)),
+                 "l"(packed + 2u * packed_w_bytes(N)), "r"((uint32_t)N * 4u), "r"(w_bar)
                  : "memory");
   }
   if (warp == 1) {
@@ -506,6 +515,20 @@ int slimb200_lookup_v3_launch(const void* pyramid, const slimb200_corr_layout* L
   return SLIMB200_OK;
 }
 
+// csrc/corr_lookup4.cu
+int slimb200_lookup_conv_tmem_launch(const void* pyramid, const slimb200_corr_layout* L, const float* coords, const void* packed_w,
+                                     const float* packed_bias, int c_out, int relu, float* out, int out_pitch, cudaStream_t stream);
+
+namespace {
+int g_lookup_conv_generation = 4;
+}
+
+extern "C" int slimb200_lookup_conv_generation(int32_t generation) {
+  const int prev = g_lookup_conv_generation;
+  if (generation >= 0) g_lookup_conv_generation = generation;
+  return prev;
+}
+
 extern "C" size_t slimb200_corr_lookup_conv_packed_bytes(int32_t c_out) {
   return (c_out < 32 || c_out > F_MAX_N || (c_out & 31)) ? 0 : packed_bytes(c_out);
 }
@@ -538,6 +561,12 @@ extern "C" int slimb200_corr_lookup_conv(const void* pyramid, int32_t pyramid_dt
   int rc = make_geo(L, &G);
   if (rc != SLIMB200_OK) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (g_lookup_conv_generation >= 4) {
+    const uint8_t* pk = static_cast<const uint8_t*>(packed);
+    return slimb200_lookup_conv_tmem_launch(pyramid, L, coords, pk + packed_w_bytes(c_out),
+                                            reinterpret_cast<const float*>(pk + 2u * packed_w_bytes(c_out)), c_out, relu, out, out_pitch,
+                                            stream);
+  }
   static int n_sm = 0;
   if (n_sm == 0) {
     int dev = 0;

@@ -191,9 +191,20 @@ def _conv_ref(look, weight, bias, relu):
     return y.reshape(B, h, w, n).permute(0, 3, 1, 2), bound.reshape(B, h, w, n).permute(0, 3, 1, 2)
 
 
+@pytest.fixture(params=[3, 4])
+def conv_generation(request):
+    """Both fused kernels: 3 = row-per-thread gather, A tile in shared memory; 4 = cp.async landing slots, A tile in TMEM."""
+    from liso_b200 import _lib
+
+    lib = _lib.load()
+    prev = lib.slimb200_lookup_conv_generation(request.param)
+    yield request.param
+    lib.slimb200_lookup_conv_generation(prev)
+
+
 @pytest.mark.parametrize("B,h,w,n_out", [(3, 16, 16, 96), (1, 80, 80, 96), (1, 115, 115, 96), (2, 24, 40, 32), (2, 16, 20, 64),
-                                         (1, 23, 29, 64)])
-def test_lookup_conv_fused_matches_oracle(cuda, B, h, w, n_out):
+                                         (1, 23, 29, 64), (5, 80, 80, 96)])
+def test_lookup_conv_fused_matches_oracle(cuda, conv_generation, B, h, w, n_out):
     """slimb200_corr_lookup_conv == relu(conv_stat_corr1(CorrBlock(...)(coords))) of the oracle
     (corr.py:23-46 + update.py:49,71) within the tf32 operand bound: the window values and the weights are rounded to
     tf32 (rel. 2^-11 each), products accumulate in fp32:
@@ -230,7 +241,7 @@ def test_lookup_conv_fused_matches_oracle(cuda, B, h, w, n_out):
         assert float((got_dev - unf).abs().max()) <= float(tol.max())
 
 
-def test_lookup_conv_writes_channel_slice(cuda):
+def test_lookup_conv_writes_channel_slice(cuda, conv_generation):
     """`out` may be a wider channels-last tensor: only its first C_out channels are written (no torch.cat afterwards)."""
     B, h, w, n_out = 2, 24, 40, 96
     _, _, d1, d2 = _fmaps(B, h, w, 31, cuda)

@@ -114,9 +114,20 @@ def main():
         from liso_b200.slim.corr import PackedLookupConv
 
         packed = PackedLookupConv(wconv, bconv, 4, 3)
-        runs.append(("lookup_conv fused x6", gen(2, lambda: blk_l.lookup_conv(coords, packed, relu=True))))
-        runs.append(("lookup_conv fused int x6", gen(2, lambda: blk_l.lookup_conv(grid, packed, relu=True))))
-        runs.append(("lookup_conv fused smooth x6", gen(2, lambda: blk_l.lookup_conv(smooth, packed, relu=True))))
+        def cgen(n, fn):
+            def run():
+                prev = lib.slimb200_lookup_conv_generation(n)
+                try:
+                    for _ in range(6):
+                        state["out"] = fn()
+                finally:
+                    lib.slimb200_lookup_conv_generation(prev)
+            return run
+
+        for cg in (3, 4):
+            runs.append(("fused gen%d x6" % cg, cgen(cg, lambda: blk_l.lookup_conv(coords, packed, relu=True))))
+            runs.append(("fused gen%d int x6" % cg, cgen(cg, lambda: blk_l.lookup_conv(grid, packed, relu=True))))
+            runs.append(("fused gen%d smooth x6" % cg, cgen(cg, lambda: blk_l.lookup_conv(smooth, packed, relu=True))))
     with torch.no_grad():
         for name, fn in runs:
             for _ in range(3):
