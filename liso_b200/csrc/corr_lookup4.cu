@@ -9,8 +9,9 @@
 //   * a thread owns one (pixel, level) unit per 128-pixel tile, like the second-generation gather (the cheapest in
 //     instructions: ~1500 per unit against ~3200 for the row-per-thread kernel), 512 threads = 128 pixels x 4 levels
 //   * the 16 window-row loads of a unit are cp.async copies (16 bytes, L2 -> shared memory, no register landing zone)
-//     into a private 256-byte slot per thread, issued ONE TILE AHEAD: while tile t is blended the loads of tile t + 1
-//     travel, so the DRAM latency is paid once per kernel, not once per tile
+//     into a private 256-byte slot per thread, issued ONE TILE AHEAD in two halves of 4 rows (as soon as the half slot
+//     has been read out): while tile t is blended the loads of tile t + 1 travel, so the DRAM latency is paid once per
+//     kernel, not once per tile
 //   * the 128 x 224 tf32 A tile is never in shared memory: each thread stores its 49 values (+ 7 zeros) to its own
 //     TMEM lane with tcgen05.st (lane = pixel, column = K slot level * 56 + i * 7 + j) and the MMA takes A from tensor
 //     memory (tcgen05.mma with a TMEM A operand) -- that is what frees the 112 KB the landing slots need
@@ -51,6 +52,7 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t (&v)[8]) {
   __syncwarp();  // warp-collective instruction: the lanes may come out of a divergent region (slow-path sampling)
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
@@ -223,15 +225,29 @@ k_lookup_conv_tmem(const __nv_bfloat16* __restrict__ pyr, const LookupGeo G, con
   const uint32_t my_zone = smem_zone + (uint32_t)threadIdx.x * 16u;  // chunk c of row r at + (r * 2 + c) * G_THREADS * 16
   const uint32_t my_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + G_A_COL0 + (uint32_t)(level * KPL);
 
-  // positions, weights, window origin of this thread's unit of `tile` + the 16 cp.async copies of its window rows
-  auto prepare = [&](Unit& u, int tile) {
+  // coordinates of this thread's pixel in `tile` (prefetched one tile before they are needed)
+  struct Coord {
+    float cx, cy;
+    uint32_t base;
+    bool live;
+  };
+  auto load_coord = [&](int tile) {
+    Coord c;
     const bool tile_ok = tile < n_tiles;
     const int b = tile_ok ? tile / G.m_tiles : 0, mt = tile_ok ? tile - b * G.m_tiles : 0;
     const int pix = mt * G_PIX + prow;
-    u.live = tile_ok && pix < G.nf;
-    u.cx = u.live ? __ldg(coords + ((size_t)b * 2 + 0) * G.nf + pix) : 0.f;
-    u.cy = u.live ? __ldg(coords + ((size_t)b * 2 + 1) * G.nf + pix) : 0.f;
-    u.base = (uint32_t)pixel_base(G, b, u.live ? pix : 0);
+    c.live = tile_ok && pix < G.nf;
+    c.cx = c.live ? __ldg(coords + ((size_t)b * 2 + 0) * G.nf + pix) : 0.f;
+    c.cy = c.live ? __ldg(coords + ((size_t)b * 2 + 1) * G.nf + pix) : 0.f;
+    c.base = (uint32_t)pixel_base(G, b, c.live ? pix : 0);
+    return c;
+  };
+  // positions, weights, window origin of a unit
+  auto taps = [&](Unit& u, const Coord& c) {
+    u.live = c.live;
+    u.cx = c.cx;
+    u.cy = c.cy;
+    u.base = c.base;
     int xb, yb;
     bool okx, oky;
     axis_taps_compact(u.cx, inv, W, u.wx, u.inx, xb, u.sx, okx);
@@ -239,22 +255,31 @@ k_lookup_conv_tmem(const __nv_bfloat16* __restrict__ pyr, const LookupGeo G, con
     u.mode = (okx && oky) ? ((u.sx | u.sy) ? 2 : 1) : 0;
     // origins beyond +-2^18 (every tap outside, zero weights) are clamped so that the index stays an int
     u.row0 = off + max(min(yb, 1 << 18), -(1 << 18)) * W + max(min(xb, 1 << 18), -(1 << 18));
+  };
+  // the cp.async copies of window rows 4 * half .. 4 * half + 3 (one commit group): all 8 addresses first, then the 8
+  // copies back to back -- a copy whose address register is recycled right behind it stalls the warp until the LSU has
+  // taken the copy (the first version of this kernel spent 60 % of its time there)
+  auto issue = [&](const Unit& u, int half) {
     const __nv_bfloat16* base = pyr + u.base;
+    const __nv_bfloat16* src[8];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const int ca = (u.row0 + r * W) & ~7;
+    for (int rr = 0; rr < 4; ++rr) {
+      const int ca = (u.row0 + (half * 4 + rr) * W) & ~7;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int col = min(max(ca + 8 * c, 0), G.pitch - 8);  // (whatever finite value lies outside the level meets a zero weight)
-        cp_async16(my_zone + (uint32_t)((r * 2 + c) * G_THREADS) * 16u, base + col_offset(col, panel_stride));
-      }
+      for (int c = 0; c < 2; ++c)  // (whatever finite value lies outside the level meets a zero weight)
+        src[rr * 2 + c] = base + col_offset(min(max(ca + 8 * c, 0), G.pitch - 8), panel_stride);
     }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cp_async16(my_zone + (uint32_t)((half * 8 + k) * G_THREADS) * 16u, src[k]);
     cp_async_commit();
   };
 
   Unit cur;
   int tile = blockIdx.x;
-  prepare(cur, tile);
+  taps(cur, load_coord(tile));
+  issue(cur, 0);
+  issue(cur, 1);
+  Coord ahead = load_coord(tile + gridDim.x);
   int it = 0;  // tiles this CTA has started
   int prev_b = 0, prev_mt = 0;
   for (; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -262,21 +287,26 @@ k_lookup_conv_tmem(const __nv_bfloat16* __restrict__ pyr, const LookupGeo G, con
     // ---- this tile's window: shared memory -> registers, aligned to window column 0; then the slot is free and the next
     // tile's loads start their journey under this tile's blend; then the blend -> TMEM lane of this pixel (the previous
     // tile's MMAs must have read the A columns by then) ----
-    cp_async_wait_all();
     const bool any_slow = __any_sync(FULL, cur.live && cur.mode == 0);
     const bool any_shift = __any_sync(FULL, cur.live && cur.mode == 2);
     Unit nxt;
+    taps(nxt, ahead);                                 // (nothing here touches shared memory: it overlaps the wait below)
+    ahead = load_coord(tile + 2 * gridDim.x);
     SinkT sink{my_taddr, {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}};
     if (!any_slow && !any_shift) {
       // regular windows: 8 x 8, two taps per axis
       uint32_t win[8][4];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        uint32_t raw[8];
-        load_slot_row(my_zone, r, raw);
-        realign<4>(raw, (cur.row0 + r * W) & 7, win[r]);
+      for (int half = 0; half < 2; ++half) {
+        cp_async_wait_but_one();  // this half of the current tile has landed (the newest group may still travel)
+#pragma unroll
+        for (int r = half * 4; r < half * 4 + 4; ++r) {
+          uint32_t raw[8];
+          load_slot_row(my_zone, r, raw);
+          realign<4>(raw, (cur.row0 + r * W) & 7, win[r]);
+        }
+        issue(nxt, half);  // the half slot is free: the next tile's rows start their journey under this tile's blend
       }
-      prepare(nxt, tile + gridDim.x);
       if (it > 0) mbar_wait(mma_bar((it - 1) & 1), (uint32_t)((it - 1) >> 1) & 1u);
       tcgen05_fence_after();
       float e0[8], e1[8];
@@ -301,17 +331,21 @@ k_lookup_conv_tmem(const __nv_bfloat16* __restrict__ pyr, const LookupGeo G, con
       // window row 8 comes straight from global memory
       uint32_t win[9][5];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        uint32_t raw[8];
-        load_slot_row(my_zone, r, raw);
-        realign<5>(raw, (cur.row0 + r * W) & 7, win[r]);
+      for (int half = 0; half < 2; ++half) {
+        cp_async_wait_but_one();
+#pragma unroll
+        for (int r = half * 4; r < half * 4 + 4; ++r) {
+          uint32_t raw[8];
+          load_slot_row(my_zone, r, raw);
+          realign<5>(raw, (cur.row0 + r * W) & 7, win[r]);
+        }
+        issue(nxt, half);
       }
       {
         uint32_t raw8[8];
         const int sft8 = fetch_row(pyr + cur.base, panel_stride, G.pitch, cur.row0 + 8 * W, raw8);
         realign<5>(raw8, sft8, win[8]);
       }
-      prepare(nxt, tile + gridDim.x);
       if (it > 0) mbar_wait(mma_bar((it - 1) & 1), (uint32_t)((it - 1) >> 1) & 1u);
       tcgen05_fence_after();
       const bool lane_slow = cur.live && cur.mode == 0;
