@@ -191,6 +191,10 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
+    # tuning hooks (tools/, A/B runs of bench.py): SLIMB200_LOOKUP_GEN / SLIMB200_LOOKUP_CONV_GEN pick a kernel generation
+    for env, fn in (("SLIMB200_LOOKUP_GEN", lib.slimb200_lookup_generation), ("SLIMB200_LOOKUP_CONV_GEN", lib.slimb200_lookup_conv_generation)):
+        if os.environ.get(env, "").isdigit():
+            fn(int(os.environ[env]))
     _lib = lib
     return lib
 

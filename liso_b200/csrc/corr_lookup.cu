@@ -628,6 +628,7 @@ int slimb200_lookup_v2_launch(const void* pyramid, const slimb200_corr_layout* L
                               cudaStream_t stream);
 int slimb200_lookup_v3_launch(const void* pyramid, const slimb200_corr_layout* L, const float* coords, float* out, int out_layout,
                               cudaStream_t stream);
+int slimb200_lookup_probe_launch(const void* pyramid, const slimb200_corr_layout* L, const float* coords, float* out, cudaStream_t stream);
 
 extern "C" int slimb200_lookup_generation(int32_t generation) {
   const int prev = g_lookup_generation;
@@ -644,6 +645,8 @@ extern "C" int slimb200_corr_lookup(const void* pyramid, int32_t pyramid_dtype, 
   if (L->rows_padded < L->h * L->w || (L->rows_padded & 127)) return SLIMB200_E_INVALID;
   if (reinterpret_cast<uintptr_t>(pyramid) & 15) return SLIMB200_E_ALIGNMENT;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (pyramid_dtype == SLIMB200_DTYPE_BF16 && radius == 3 && g_lookup_generation == 9)  // memory-side probe (kbench only)
+    return slimb200_lookup_probe_launch(pyramid, L, coords, out, stream);
   if (pyramid_dtype == SLIMB200_DTYPE_BF16 && radius == 3 && g_lookup_generation >= 2)
     return slimb200_lookup_v3_launch(pyramid, L, coords, out, out_layout, stream);
   if (pyramid_dtype == SLIMB200_DTYPE_BF16 && radius == 3 && g_lookup_generation == 1)

@@ -187,7 +187,50 @@ __global__ void __launch_bounds__(V2_THREADS, 2) k_corr_lookup_v2(const __nv_bfl
   }
 }
 
+// Measurement probe (tools/kbench.py, generation 9): the memory side of the lookup alone -- positions, the 16 window-row
+// loads of every (pixel, level), and one word per unit written -- no re-alignment, no blend, no 196-channel store.
+__global__ void __launch_bounds__(V2_THREADS, 2) k_lookup_probe(const __nv_bfloat16* __restrict__ pyr, const LookupGeo G,
+                                                               const float* __restrict__ coords, float* __restrict__ out) {
+  const int lane = lane_id(), warp = warp_id();
+  const int level = warp >> 1;
+  const int pix = blockIdx.x * V2_PIX + (warp & 1) * 32 + lane;
+  const int b = blockIdx.y;
+  if (level >= G.levels) return;
+  const bool live = pix < G.nf;
+  const int W = pick4(G.lw, level), H = pick4(G.lh, level), off = pick4(G.lo, level);
+  const float cx = live ? __ldg(coords + ((size_t)b * 2 + 0) * G.nf + pix) : 0.f;
+  const float cy = live ? __ldg(coords + ((size_t)b * 2 + 1) * G.nf + pix) : 0.f;
+  const float inv = 1.0f / (float)(1 << level);
+  const __nv_bfloat16* base = pyr + pixel_base(G, b, live ? pix : 0);
+  float wx0[WIN], wx1[WIN], wy0[WIN], wy1[WIN];
+  int xb, yb;
+  unsigned sx, sy;
+  bool okx, oky;
+  axis_taps(cx, inv, W, wx0, wx1, xb, sx, okx);
+  axis_taps(cy, inv, H, wy0, wy1, yb, sy, oky);
+  uint32_t acc = 0u;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    uint32_t raw[8];
+    fetch_row(base, G.m_tiles * 2 * 8192, G.pitch, off + (yb + r) * W + xb, raw);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc ^= raw[k];
+  }
+  if (live) out[((size_t)b * G.nf + pix) * 4 + level] = __uint_as_float(acc & 0x3fffffffu) + wx0[0] + wy1[6];
+}
+
 }  // namespace
+
+int slimb200_lookup_probe_launch(const void* pyramid, const slimb200_corr_layout* L, const float* coords, float* out,
+                                 cudaStream_t stream) {
+  LookupGeo G;
+  int rc = make_geo(L, &G);
+  if (rc != SLIMB200_OK) return rc;
+  dim3 grid((G.nf + V2_PIX - 1) / V2_PIX, L->batch);
+  SLIMB200_LAUNCH(SLIMB200_K_CORR_LOOKUP, stream,
+                  (k_lookup_probe<<<grid, V2_THREADS, 0, stream>>>(static_cast<const __nv_bfloat16*>(pyramid), G, coords, out)));
+  return SLIMB200_OK;
+}
 
 // radius-3 lookup on a bf16 pyramid, gather core of this file (called by slimb200_corr_lookup)
 int slimb200_lookup_v2_launch(const void* pyramid, const slimb200_corr_layout* L, const float* coords, float* out, int out_layout,

@@ -110,6 +110,9 @@ def main():
                                                                     mode="bicubic", align_corners=True)).contiguous()
         runs.append(("lookup gen2 nchw smooth x6", gen(2, lambda: blk_c(smooth))))
         runs.append(("lookup gen0 nchw smooth x6", gen(0, lambda: blk_c(smooth))))
+        runs.append(("probe (loads only) x6", gen(9, lambda: blk_c(coords))))
+        runs.append(("probe (loads only) smooth x6", gen(9, lambda: blk_c(smooth))))
+        runs.append(("probe (loads only) int x6", gen(9, lambda: blk_c(grid))))
         runs.append(("lookup+conv unfused x6", gen(2, lambda: torch.cudnn_convolution_relu(blk_l(coords), wconv, bconv, (1, 1), (0, 0), (1, 1), 1))))
         from liso_b200.slim.corr import PackedLookupConv
 
