@@ -172,8 +172,9 @@ def main():
                          "reported as `export_with_writer`, never as the headline")
     ap.add_argument("--memory-format", default="channels_last", choices=["channels_last", "contiguous"],
                     help="memory format of the canvas our encoder emits and of the stock convs that consume it")
-    ap.add_argument("--no-fused-lookup", action="store_true",
-                    help="lookup kernel + stock 1x1 convolution instead of the fused slimb200_corr_lookup_conv (SURVEY 8f.2)")
+    ap.add_argument("--fused-lookup", action="store_true",
+                    help="headline with the fused lookup + conv_stat_corr1 kernel (slimb200_corr_lookup_conv, SURVEY 8f.2) instead of "
+                         "lookup kernel + stock 1x1 convolution; the other variant is measured in the same run either way")
     ap.add_argument("--profile-one-step", action="store_true",
                     help="bracket ONE resident step with cudaProfilerStart/Stop (for `ncu --profile-from-start off`) and exit")
     ap.add_argument("--no-other-workloads", action="store_true",
@@ -272,7 +273,7 @@ def main():
             if args.memory_format == "channels_last":
                 model = model.to(memory_format=torch.channels_last)
             model.raft_network.use_cuda_graph = not args.no_cuda_graph
-            model.raft_network.fuse_lookup_conv = not args.no_fused_lookup
+            model.raft_network.fuse_lookup_conv = bool(args.fused_lookup)
             # the resident loop reads each step's outputs before the next forward: views of the graph's static buffers are
             # enough (SLIM's default returns copies the caller may keep across forwards; ExportPipeline sets this itself)
             model.outputs_alias_static_buffers = True
@@ -476,6 +477,17 @@ def main():
     ms_other_e2e /= n_other
     main.set_decode(args.decode)
 
+    # the other lookup variant (fused lookup + conv_stat_corr1 <-> lookup kernel + stock convolution), same run, fewer steps
+    main.model.raft_network.fuse_lookup_conv = not args.fused_lookup
+    main.prepare()
+    for _ in range(3):
+        main.step_resident()
+    ms_var, _, _ = main.timed(main.step_resident, n_other)
+    ms_var /= n_other
+    prof_var = main.kernel_profile(3)
+    main.model.raft_network.fuse_lookup_conv = bool(args.fused_lookup)
+    main.prepare()
+
     writer_line = None
     if args.write_npz and rank == 0:
         import shutil
@@ -499,7 +511,7 @@ def main():
         shutil.rmtree(out_dir, ignore_errors=True)
 
     tot = reduce_counters({"pairs": float(args.batch * args.steps), "ms_res_max": ms_res, "ms_e2e_max": ms_e2e,
-                           "launches": float(launches), "ms_other_max": ms_other, "ms_other_e2e_max": ms_other_e2e},
+                           "launches": float(launches), "ms_other_max": ms_other, "ms_other_e2e_max": ms_other_e2e, "ms_var_max": ms_var},
                           device=dev)
     # per-rank step times (scaling hygiene: who is the straggler)
     per_rank = None
@@ -537,14 +549,22 @@ def main():
                     "stages": stages}
         if "tensor" in dom:
             roofline["tensor"] = dom["tensor"]
+        # the other lookup variant of the same run
+        _, st_var = main.stage_rooflines(prof_var, 3, tot["ms_var_max"])
+        if "lookup" in st_var:
+            v = dict(st_var["lookup"])
+            v.update({"variant": "lookup kernel + stock conv_stat_corr1" if args.fused_lookup else
+                      "fused lookup + conv_stat_corr1 + ReLU (slimb200_corr_lookup_conv)",
+                      "pairs_per_s_with_this_variant": args.batch * world / (tot["ms_var_max"] / 1e3), "ms_per_step": tot["ms_var_max"]})
+            stages["lookup_other_variant"] = v
 
     if warmup_note:
         config["warmup_note"] = warmup_note
     config["timing"] = ("untimed preparation (2 forwards: cuDNN autotune + CUDA-graph capture), then exactly --warmup warm-up steps, "
                         "then --steps timed steps between CUDA events")
     config["outputs"] = "graph outputs handed out as views (outputs_alias_static_buffers=True); e2e copies the exported tensors"
-    config["lookup"] = ("lookup kernel + stock conv_stat_corr1" if args.no_fused_lookup else
-                        "lookup fused with conv_stat_corr1 + ReLU (tcgen05 tf32, slimb200_corr_lookup_conv)")
+    config["lookup"] = ("lookup fused with conv_stat_corr1 + ReLU (tcgen05 tf32, slimb200_corr_lookup_conv)" if args.fused_lookup else
+                        "lookup kernel + stock conv_stat_corr1")
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": tot["ms_res_max"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": config, "clocks": clocks,
@@ -556,7 +576,7 @@ def main():
                            "ms_per_step": tot["ms_other_max"]},
             "memory_format": args.memory_format, "gru_loop": "eager launches" if args.no_cuda_graph else "CUDA graph",
             "precision": {"pillar": "f32", "correlation": "bf16 operands, f32 accumulate, bf16 storage",
-                          "lookup_conv": "tf32 operands (rna), f32 accumulate" if not args.no_fused_lookup else "stock cudnn",
+                          "lookup_conv": "tf32 operands (rna), f32 accumulate" if args.fused_lookup else "stock cudnn",
                           "stock_convs": "cudnn " + args.conv_precision}}
     if per_rank:
         line["per_rank"] = per_rank

@@ -18,6 +18,8 @@
 //   * weights: N x 224 tf32 in the 128-byte-swizzled K-major layout, one bulk copy per CTA, resident (84 KB at N = 96)
 //   * two fp32 accumulators in TMEM: warps 0..3 write out tile t - 1 (+ bias, ReLU, 16-byte row stores) while the tensor
 //     core works on tile t
+//   * no CTA-wide barrier per tile: threads arrive on an mbarrier when their A columns are stored and move on; only the
+//     MMA-issuing warp waits for the 512 arrivals
 // TMEM columns: [0, 96) accumulator 0, [128, 224) accumulator 1, [256, 480) A.
 #include "lookup_core.cuh"
 #include "ptx.cuh"
@@ -188,13 +190,15 @@ k_lookup_conv_tmem(const __nv_bfloat16* __restrict__ pyr, const LookupGeo G, con
   const uint32_t bar0 = smem_zone + G_ZONE_BYTES;
   auto mma_bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   const uint32_t w_bar = bar0 + 16u;
-  const uint32_t tmem_ptr_smem = bar0 + 24u;
+  const uint32_t full_bar = bar0 + 24u;  // every thread arrives when its A columns of the tile are in tensor memory
+  const uint32_t tmem_ptr_smem = bar0 + 32u;
 
   const int lane = lane_id(), warp = warp_id();
   if (threadIdx.x == 0) {
     mbar_init(mma_bar(0), 1);
     mbar_init(mma_bar(1), 1);
     mbar_init(w_bar, 1);
+    mbar_init(full_bar, G_THREADS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     mbar_expect_tx(w_bar, g_w_bytes(N) + (uint32_t)N * 4u);
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_w), "l"(packed_w),
@@ -372,11 +376,14 @@ k_lookup_conv_tmem(const __nv_bfloat16* __restrict__ pyr, const LookupGeo G, con
         }
       }
     }
+    // No CTA-wide barrier: a thread whose A columns are stored ARRIVES and moves on to the next tile (positions, slot
+    // read-out, load issue) while slower warps finish; only warp 0, which issues the MMAs, waits for all 512 arrivals.
     tmem_st_wait();
     tcgen05_fence_before();
-    __syncthreads();
+    mbar_arrive(full_bar);
     if (warp == 0) {
       if (it == 0) mbar_wait(w_bar, 0);  // the packed weights have landed
+      mbar_wait(full_bar, (uint32_t)it & 1u);
       tcgen05_fence_after();
       if (elect_one()) {
         const uint32_t tmem_d = tmem_base + (uint32_t)(it & 1) * G_ACC_STRIDE;
@@ -398,7 +405,7 @@ k_lookup_conv_tmem(const __nv_bfloat16* __restrict__ pyr, const LookupGeo G, con
       tcgen05_fence_after();
       g_epilogue(tmem_base + (uint32_t)((it - 1) & 1) * G_ACC_STRIDE, warp, lane, s_bias, N, relu,
                  out + ((size_t)prev_b * G.nf + (size_t)prev_mt * G_PIX) * (size_t)out_pitch, out_pitch, min(G_PIX, G.nf - prev_mt * G_PIX));
-      tcgen05_fence_before();  // (ordered before the MMAs of tile it + 1 by the next __syncthreads)
+      tcgen05_fence_before();  // (ordered before the MMAs of tile it + 1 by this thread's next arrival on full_bar)
     }
     prev_b = b;
     prev_mt = mt;

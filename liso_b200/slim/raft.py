@@ -370,9 +370,12 @@ class RAFT(nn.Module):
         self.merge_parallel_convs = True
         self.tap_heads = True  # ... and the heads' 3x3 output convolution as a 1x1 convolution to taps + window sum
         # the lookup fused with the 1x1 convolution that consumes it (conv_stat_corr1 + ReLU, update.py:49,71) in one
-        # tcgen05 kernel with tf32 operands: True = whenever TF32 convolutions are allowed (cuDNN's precision for that
-        # layer then), "always" = also with fp32 convolutions, False = lookup kernel + stock convolution
-        self.fuse_lookup_conv = True
+        # tcgen05 kernel with tf32 operands (slimb200_corr_lookup_conv): True = whenever TF32 convolutions are
+        # allowed (cuDNN's precision for that layer then), "always" = also with fp32 convolutions, False (default) = lookup
+        # kernel + stock convolution.  Off by default because it does not pay yet: inside the step both variants run at the
+        # same pairs/s (the fused kernel holds an SM per CTA and cannot overlap with the other
+        # direction's kernels the way the small lookup CTAs do); bench.py measures both in every run.
+        self.fuse_lookup_conv = False
         # forward and backward direction as two parallel branches of the CUDA graph
         self.concurrent_directions = True
         # consumer of the per-iteration network outputs, e.g. SLIM's output decoder: called as

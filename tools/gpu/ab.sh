@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 for g in 3 4; do
   SLIMB200_LOOKUP_CONV_GEN=$g timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-other-workloads > gpurun_out/bench_g$g.json 2> gpurun_out/bench_g$g.err
 done
-timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-other-workloads --no-fused-lookup > gpurun_out/bench_unfused.json 2> gpurun_out/bench_unfused.err
+timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-other-workloads  > gpurun_out/bench_unfused.json 2> gpurun_out/bench_unfused.err
 python - <<'PY'
 import json
 for n in ("g3", "g4", "unfused"):

@@ -3,8 +3,8 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_slim_e2e.py tests/test_gpu_corr.py -q -m gpu --timeout=600 -x > gpurun_out/pytest_e2e.log 2>&1; echo "e2e tests exit $?" > gpurun_out/summary.txt
 tail -n 5 gpurun_out/pytest_e2e.log
-timeout 900 python bench.py --steps 20 --warmup 6 --no-cpu-baseline > gpurun_out/bench_fused.json 2> gpurun_out/bench_fused.err; echo "bench fused exit $?" >> gpurun_out/summary.txt
-timeout 900 python bench.py --steps 20 --warmup 6 --no-cpu-baseline --no-fused-lookup > gpurun_out/bench_unfused.json 2> gpurun_out/bench_unfused.err; echo "bench unfused exit $?" >> gpurun_out/summary.txt
+timeout 900 python bench.py --steps 20 --warmup 6 --no-cpu-baseline --fused-lookup > gpurun_out/bench_fused.json 2> gpurun_out/bench_fused.err; echo "bench fused exit $?" >> gpurun_out/summary.txt
+timeout 900 python bench.py --steps 20 --warmup 6 --no-cpu-baseline  > gpurun_out/bench_unfused.json 2> gpurun_out/bench_unfused.err; echo "bench unfused exit $?" >> gpurun_out/summary.txt
 python - <<'PY'
 import json
 for n in ("fused", "unfused"):
