@@ -48,6 +48,17 @@ def save_npz(target_file: str, arrays: Dict[str, torch.Tensor], bev_range_m, ski
     return True
 
 
+# directions of one exported sample: the t0 <-> t1 pair (Waymo / AV2), or the three pairs of the KITTI / nuScenes export
+# (experiment.py:386-456); saved as bev_raw_flow_<dir> (H, W, 2) and bev_dynamicness_<dir> (H, W)
+DIRECTIONS_PAIR = ("t0_t1", "t1_t0")
+DIRECTIONS_TRIPLE = ("t0_t1", "t1_t0", "t0_t2", "t2_t0", "t1_t2", "t2_t1")
+
+
+def export_keys(n_directions: int):
+    dirs = {2: DIRECTIONS_PAIR, 6: DIRECTIONS_TRIPLE}[n_directions]
+    return ["bev_raw_flow_" + d for d in dirs] + ["bev_dynamicness_" + d for d in dirs]
+
+
 class AsyncNpzWriter:
     """the reference writes one ``np.savez_compressed`` file per pair on the thread that drives the
     GPU (``experiment.py:459-471``); at hundreds of pairs/s zlib would be the bottleneck, so the files are written
@@ -84,13 +95,18 @@ class AsyncNpzWriter:
         os.replace(tmp, path)  # never leave a truncated file behind
         return path
 
-    def submit(self, sample_id: str, flow_fw, flow_bw, dyn_fw, dyn_bw, static_threshold) -> bool:
-        """Arrays of ONE pair (numpy or CPU tensors).  Returns False when the file exists and is skipped."""
+    def submit(self, sample_id: str, *args) -> bool:
+        """Arrays of ONE sample (numpy or CPU tensors): ``submit(id, flow_fw, flow_bw, dyn_fw, dyn_bw, threshold)`` for a
+        pair, or ``submit(id, flows (6), dyns (6), threshold)`` in `DIRECTIONS_TRIPLE` order for the KITTI / nuScenes
+        triple.  Returns False when the file exists and is skipped."""
         path = self.target_file(sample_id)
         if self.skip_existing and os.path.exists(path):
             return False
+        *tensors, static_threshold = args
+        if len(tensors) == 2 and isinstance(tensors[0], (list, tuple)):
+            tensors = list(tensors[0]) + list(tensors[1])
         arrays = {"static_threshold": np.array(float(static_threshold), dtype=np.float32)}
-        for k, v in zip(self.KEYS, (flow_fw, flow_bw, dyn_fw, dyn_bw)):
+        for k, v in zip(export_keys(len(tensors) // 2), tensors):
             arrays[k] = np.array(v.numpy() if torch.is_tensor(v) else v, dtype=np.float32, copy=True)
         arrays["bev_range_m"] = self.bev_range_m
         while len(self.pending) >= self.max_pending:
@@ -100,12 +116,11 @@ class AsyncNpzWriter:
         return True
 
     def submit_batch(self, sample_ids, host_tensors, static_threshold) -> int:
-        """``host_tensors`` as handed to ``ExportPipeline``'s consume callback: batched
-        [flow_fw (B,H,W,2), flow_bw, dyn_fw (B,H,W), dyn_bw]."""
+        """``host_tensors`` as handed to ``ExportPipeline``'s consume callback: batched flows (B,H,W,2) of all directions,
+        then the dynamicness maps (B,H,W) of all directions (2 + 2 tensors for a pair, 6 + 6 for a triple)."""
         n = 0
         for b, sid in enumerate(sample_ids):
-            n += bool(self.submit(sid, host_tensors[0][b], host_tensors[1][b], host_tensors[2][b], host_tensors[3][b],
-                                  static_threshold))
+            n += bool(self.submit(sid, *[t[b] for t in host_tensors], static_threshold))
         return n
 
     def close(self) -> int:
@@ -160,7 +175,8 @@ class ExportPipeline:
     of batch i-1 run on a copy stream while batch i is computed on the caller's stream.  (The reference uploads,
     computes and ``.cpu().numpy()``s each sample strictly in sequence, ``experiment.py:363-402``.)
 
-    ``batches``: iterable of ``(sample_data_t0, sample_data_t1)`` with tensors in *pinned* host memory.
+    ``batches``: iterable of ``(sample_data_t0, sample_data_t1)`` -- or ``(t0, t1, t2)`` for the KITTI / nuScenes triple,
+    run as ONE ``SLIM.forward_triple`` pass in which every frame is encoded once -- with tensors in *pinned* host memory.
     ``consume(index, arrays)``: called with the exported tensors of a batch as pinned host tensors once they have
     arrived (they are reused ``depth`` batches later: copy or write them out inside the callback).
     """
@@ -218,21 +234,24 @@ class ExportPipeline:
         if nxt is not None:
             self.copy_stream.wait_stream(cur)
             with torch.cuda.stream(self.copy_stream):
-                staged = (self._upload(nxt[0], 0, "t0"), self._upload(nxt[1], 0, "t1"))
+                staged = tuple(self._upload(s, 0, "t%d" % t) for t, s in enumerate(nxt))
                 up_evt = torch.cuda.Event()
                 up_evt.record(self.copy_stream)
         idx = 0
         n_done = 0
         while staged is not None:
             cur.wait_event(up_evt)
-            d0, d1 = staged
             ctx = self.amp_ctx() if self.amp_ctx else contextlib.nullcontext()
             with torch.no_grad(), ctx:
-                pf, pb = self.model(d0, d1, None)
-            fw, bw = pf[-1].modified_network_output, pb[-1].modified_network_output
+                if len(staged) == 3:
+                    by_dir = self.model.forward_triple(*staged)
+                    mods = [by_dir[d][-1].modified_network_output for d in DIRECTIONS_TRIPLE]
+                else:
+                    pf, pb = self.model(staged[0], staged[1], None)
+                    mods = [pf[-1].modified_network_output, pb[-1].modified_network_output]
             # packed copies: the predictions may be views of the CUDA graph's static outputs, which the next forward
             # overwrites while this batch is still being downloaded
-            outs = [t.contiguous() for t in (fw.static_flow, bw.static_flow, fw.dynamicness, bw.dynamicness)]
+            outs = [m.static_flow.contiguous() for m in mods] + [m.dynamicness.contiguous() for m in mods]
             done = torch.cuda.Event()
             done.record(cur)
             done_evt[idx % D] = done
@@ -243,7 +262,7 @@ class ExportPipeline:
                     up_slot = (idx + 1) % D
                     if done_evt[up_slot] is not None:  # the batch that last read this slot's buffers must be through
                         self.copy_stream.wait_event(done_evt[up_slot])
-                    staged = (self._upload(nxt[0], up_slot, "t0"), self._upload(nxt[1], up_slot, "t1"))
+                    staged = tuple(self._upload(s, up_slot, "t%d" % t) for t, s in enumerate(nxt))
                     up_evt = torch.cuda.Event()
                     up_evt.record(self.copy_stream)
                 else:
@@ -282,7 +301,7 @@ def collate_pairs(pairs):
     from torch.nn.utils.rnn import pad_sequence
 
     out = []
-    for t in range(2):
+    for t in range(len(pairs[0])):
         samples = [p[t] for p in pairs]
         pcl = pad_sequence([s["pcl_ta"]["pcl"] for s in samples], batch_first=True, padding_value=float("nan"))
         coors = pad_sequence([s["pcl_ta"]["pillar_coors"] for s in samples], batch_first=True, padding_value=-1)
@@ -291,7 +310,7 @@ def collate_pairs(pairs):
         if all("raw_scan" in s for s in samples):
             batch["raw_scan"] = samples[0]["raw_scan"]
         out.append(batch)
-    return out[0], out[1]
+    return tuple(out)
 
 
 def _pin(sample):
@@ -311,7 +330,10 @@ def run_flow_export(model, dataset, target_dir: str, bev_range_m, *, world_size:
     the end sums the counters over the ranks.
 
     ``dataset``: ``len()`` and ``dataset[i] -> (sample_id, sample_t0, sample_t1)`` with un-batched host tensors (see
-    :func:`collate_pairs`).  Returns ``{"pairs", "files", "skipped", "elapsed_s_max"}`` over all ranks."""
+    :func:`collate_pairs`), or ``(sample_id, t0, t1, t2)`` for the KITTI / nuScenes export: then t0 -> t1, t0 -> t2 and
+    t1 -> t2 are computed in one pass per batch (every frame encoded once) and the file holds all 12 maps
+    (``experiment.py:404-456``).  Returns ``{"pairs", "files", "skipped", "elapsed_s_max"}`` over all ranks ("pairs"
+    counts samples)."""
     import time
 
     writer = AsyncNpzWriter(target_dir, bev_range_m, workers=writer_workers, skip_existing=skip_existing)
@@ -330,8 +352,7 @@ def run_flow_export(model, dataset, target_dir: str, bev_range_m, *, world_size:
             if not items:
                 continue
             ids_of_batch.append([it[0] for it in items])
-            d0, d1 = collate_pairs([(it[1], it[2]) for it in items])
-            yield _pin(d0), _pin(d1)
+            yield tuple(_pin(d) for d in collate_pairs([tuple(it[1:]) for it in items]))
 
     thr = float(model.moving_dynamicness_threshold.value())
     counts = {"pairs": 0, "files": 0}

@@ -403,44 +403,55 @@ class RAFT(nn.Module):
     def forward(self, pcl_t0, pcl_t1, raw_scans: bool = False):
         """``raw_scans``: the clouds are raw scans with ground (``liso_b200.datasets.preprocess_scans``); the encoder
         applies the dataset's ground rule itself."""
+        outs, occs = self.forward_frames([pcl_t0, pcl_t1], [(0, 1)], raw_scans)
+        return outs[0], outs[1], {"t0": {"bev_net_input_dbg": occs[0]}, "t1": {"bev_net_input_dbg": occs[1]}}
+
+    def forward_frames(self, pcls, pairs, raw_scans: bool = False):
+        """Several frame pairs over a common set of frames in one pass: ``pcls[f]`` = the cloud batch of frame f (a list of
+        (N_i, 3|4) tensors), ``pairs`` = [(a, b), ...].  Returns (outs, occupancies): ``outs[2p]`` = the network outputs of
+        a -> b of pair p, ``outs[2p + 1]`` = b -> a (each a list over GRU iterations of (B, H, W, 8)), ``occupancies[f]``
+        per frame.  Every frame is encoded ONCE -- pillar encoder, feature encoder, context encoder -- however many pairs
+        it takes part in: the reference's KITTI / nuScenes export runs t0 -> t1, t0 -> t2 and t1 -> t2 as three model()
+        calls, i.e. twelve encoder passes for three frames (``experiment.py:386-456``)."""
         kw = {"raw_scan": True} if raw_scans else {}  # (the reference signature is forward(pcl, img=None))
-        dev = pcl_t0[0].device
-        if not self.will_use_graph(pcl_t0, pcl_t1):
-            img_t0, occ_t0 = self.pp_layer(pcl_t0, **kw)
-            img_t1, occ_t1 = self.pp_layer(pcl_t1, **kw)
-            fw, bw = self._net_body(img_t0, img_t1, (occ_t0, occ_t1))
-            return fw, bw, {"t0": {"bev_net_input_dbg": occ_t0}, "t1": {"bev_net_input_dbg": occ_t1}}
+        pairs = [(int(a), int(b)) for a, b in pairs]
+        dev = pcls[0][0].device
+        if not self.will_use_graph(*pcls):
+            enc = [self.pp_layer(p, **kw) for p in pcls]
+            outs = self._net_body_frames([e[0] for e in enc], [e[1] for e in enc], pairs)
+            return outs, [e[1] for e in enc]
 
         # ---- everything between the pillar encoder and the decoder as ONE CUDA graph (SURVEY 8f.2): the encoder writes
         # its canvases straight into the graph's static inputs; ~800 launches per step become one graph launch.
         # The captured kernels hold raw pointers to the weights (and to cached concatenations of them): any in-place
         # update or re-allocation of a parameter invalidates the graph.
-        B = len(pcl_t0)
+        B = len(pcls[0])
         wsig = tuple((p.data_ptr(), p._version) for mod in (self.fnet, self.cnet, self.update_block) for p in mod.parameters())
         key = (B, self.output_iterations, self.pp_layer.canvas_memory_format, str(dev), torch.backends.cudnn.allow_tf32, self.training,
                self.fused_update_block, self.merge_parallel_convs, self.tap_heads, self.concurrent_directions, FAST_STOCK_OPS,
                self.fuse_lookup_conv,
                self.output_sink is not None, self.graph_extra_key, wsig)
-        st = self._graphs.get("net")
+        slot = "net" if (len(pcls), pairs) == (2, [(0, 1)]) else "net:%d:%s" % (len(pcls), pairs)
+        self._last_graph_slot = slot
+        st = self._graphs.get(slot)
         if st is not None and st["key"] != key:
             st = None  # (the old graph and its buffers are released when the slot is overwritten)
         if st is None:
-            st = {"key": key, "in": [self.pp_layer.empty_outputs(B, dev) for _ in range(2)]}
-        self.pp_layer(pcl_t0, out=st["in"][0], **kw)
-        self.pp_layer(pcl_t1, out=st["in"][1], **kw)
+            st = {"key": key, "in": [self.pp_layer.empty_outputs(B, dev) for _ in pcls], "pairs": pairs, "slot": slot}
+        for f, p in enumerate(pcls):
+            self.pp_layer(p, out=st["in"][f], **kw)
         if "graph" not in st:
             self._capture_net_graph(st, dev)
         st["graph"].replay()
         _lib_mod().note_graph_replay(st["launches"])
-        aux = {"t0": {"bev_net_input_dbg": st["in"][0][1]}, "t1": {"bev_net_input_dbg": st["in"][1][1]}}
-        return st["outs"][0], st["outs"][1], aux
+        return st["outs"], [i[1] for i in st["in"]]
 
-    def will_use_graph(self, pcl_t0, pcl_t1) -> bool:
+    def will_use_graph(self, pcl_t0, pcl_t1, *more) -> bool:
         dev = pcl_t0[0].device
         return (self.use_cuda_graph and FAST_STOCK_OPS and dev.type == "cuda" and not torch.is_grad_enabled()
                 and not (self.training and self._graphed_part_depends_on_training_mode())
                 and not torch.cuda.is_current_stream_capturing()
-                and len(pcl_t0) == len(pcl_t1) and hasattr(self.pp_layer, "empty_outputs"))
+                and all(len(p) == len(pcl_t0) for p in (pcl_t1,) + more) and hasattr(self.pp_layer, "empty_outputs"))
 
     def _graphed_part_depends_on_training_mode(self) -> bool:
         """The reference's flow export never calls ``model.eval()`` (``experiment.py:164-198,225-361``): it runs in train
@@ -458,27 +469,46 @@ class RAFT(nn.Module):
 
     def _net_body(self, img_t0, img_t1, occupancies=(None, None)):
         """Feature encoders, correlation pyramids, context encoders and both refinement loops (raft_mod.py:82-257)."""
-        self._occupancies = occupancies
+        outs = self._net_body_frames([img_t0, img_t1], list(occupancies), [(0, 1)])
+        return outs[0], outs[1]
+
+    def _net_body_frames(self, imgs, occupancies, pairs):
+        """`_net_body` for several pairs over common frames: fnet and cnet run once per frame; direction 2p = a -> b of
+        pair p, 2p + 1 = b -> a."""
+        self._occupancies = [occupancies[f] for a, b in pairs for f in (a, b)]  # per direction: the SOURCE frame's occupancy
         if self.output_sink_begin is not None:
             self.output_sink_begin()
-        fmap_t0 = self.fnet(img_t0)
-        fmap_t1 = self.fnet(img_t1)
-        if self.concurrent_directions and img_t0.is_cuda and torch.cuda.is_current_stream_capturing():
-            # the forward and the backward direction (context encoder, pyramid, refinement loop) share nothing but the
-            # read-only feature maps and weights: inside the CUDA graph they are two parallel branches, so the many
-            # short kernels of one loop fill the gaps of the other.  Fork / join with stream waits (captured as graph
+        fmaps = [self.fnet(img) for img in imgs]
+        sources = sorted({f for a, b in pairs for f in (a, b)})
+        ctx = {}
+        for f in sources:  # context encoder of every frame a direction starts from (raft_mod.py:170-173)
+            net, inp = torch.split(self.cnet(imgs[f]), [self.hidden_dim, self.context_dim], dim=1)
+            ctx[f] = (torch.tanh(net), torch.relu(inp))
+        dirs = [(a, b) for a, b in pairs for a, b in ((a, b), (b, a))]
+        outs = [None] * len(dirs)
+
+        def run(k):
+            a, b = dirs[k]
+            outs[k] = self.predict_single_flow_map_and_classes(imgs[a], fmaps[a], fmaps[b], direction=k, context=ctx[a])
+
+        if self.concurrent_directions and imgs[0].is_cuda and torch.cuda.is_current_stream_capturing():
+            # the forward and the backward directions (pyramid, refinement loop) share nothing but the read-only feature
+            # maps, context tensors and weights: inside the CUDA graph they are two parallel branches, so the many short
+            # kernels of one loop fill the gaps of the other.  Fork / join with stream waits (captured as graph
             # dependencies); every tensor a branch allocates stays on its own stream, the shared inputs outlive the join.
-            main = torch.cuda.current_stream(img_t0.device)
-            side = self._branch_stream(img_t0.device)
+            main = torch.cuda.current_stream(imgs[0].device)
+            side = self._branch_stream(imgs[0].device)
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                bw = self.predict_single_flow_map_and_classes(img_t1, fmap_t1, fmap_t0, self.head_decoder_bw, direction=1)
-            fw = self.predict_single_flow_map_and_classes(img_t0, fmap_t0, fmap_t1, self.head_decoder_fw, direction=0)
+                for k in range(1, len(dirs), 2):
+                    run(k)
+            for k in range(0, len(dirs), 2):
+                run(k)
             main.wait_stream(side)
-            return fw, bw
-        fw = self.predict_single_flow_map_and_classes(img_t0, fmap_t0, fmap_t1, self.head_decoder_fw, direction=0)
-        bw = self.predict_single_flow_map_and_classes(img_t1, fmap_t1, fmap_t0, self.head_decoder_bw, direction=1)
-        return fw, bw
+            return outs
+        for k in range(len(dirs)):
+            run(k)
+        return outs
 
     def _branch_stream(self, device, name="bw", priority=-1):
         """Streams of the graph's branches.  The two refinement loops are captured on high-priority streams, the sink
@@ -510,23 +540,22 @@ class RAFT(nn.Module):
 
     def _capture_net_graph(self, st, dev):
         lib = _lib_mod()
-        img_t0, img_t1 = st["in"][0][0], st["in"][1][0]
-        occ = (st["in"][0][1], st["in"][1][1])
+        imgs, occ = [i[0] for i in st["in"]], [i[1] for i in st["in"]]
         # warm-up on a side stream (cuDNN autotuning, lazy kernel attributes), as torch.cuda.graphs asks
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(2):
-                self._net_body(img_t0, img_t1, occ)
+                self._net_body_frames(imgs, occ, st["pairs"])
         torch.cuda.current_stream(dev).wait_stream(side)
         graph = torch.cuda.CUDAGraph()
         n0 = lib.load().slimb200_launch_count(-1)
         with torch.cuda.graph(graph, stream=self._branch_stream(dev, "fw")):
-            st["outs"] = self._net_body(img_t0, img_t1, occ)
+            st["outs"] = self._net_body_frames(imgs, occ, st["pairs"])
         st["launches"] = int(lib.load().slimb200_launch_count(-1) - n0)  # library kernels inside one replay
         st["graph"] = graph
         st["keepalive"] = _derived_values(self) + [getattr(self, "_packed_c1", None)]  # derived weights the captured kernels point at
-        self._graphs["net"] = st
+        self._graphs[st["slot"]] = st
         self.n_graph_captures = getattr(self, "n_graph_captures", 0) + 1
 
     def _gru_loop(self, correlation, net, inp, img_hw, batch, device, direction=0) -> List[torch.Tensor]:
@@ -668,9 +697,12 @@ class RAFT(nn.Module):
         self._join_sink(direction, device)
         return outs
 
-    def predict_single_flow_map_and_classes(self, img_t0, fmap_t0, fmap_t1, decoder=None, direction=0) -> List[torch.Tensor]:
+    def predict_single_flow_map_and_classes(self, img_t0, fmap_t0, fmap_t1, decoder=None, direction=0, context=None) -> List[torch.Tensor]:
+        """``context``: (tanh(net), relu(inp)) of ``cnet(img_t0)`` when the caller has already run the context encoder."""
         m = self.slim_cfg.model
         b, _, H, W = img_t0.shape
         correlation = CorrBlock(fmap_t0, fmap_t1, num_levels=m.corr_cfg.num_levels, radius=m.corr_cfg.search_radius)
-        net, inp = torch.split(self.cnet(img_t0), [self.hidden_dim, self.context_dim], dim=1)
-        return self._gru_loop(correlation, torch.tanh(net), torch.relu(inp), (H, W), b, img_t0.device, direction)
+        if context is None:
+            net, inp = torch.split(self.cnet(img_t0), [self.hidden_dim, self.context_dim], dim=1)
+            context = (torch.tanh(net), torch.relu(inp))
+        return self._gru_loop(correlation, context[0], context[1], (H, W), b, img_t0.device, direction)

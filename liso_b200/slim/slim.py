@@ -228,7 +228,7 @@ class SLIM(nn.Module):
 
     def _sink(self, direction, it, net_out, occupancy):
         pc, coors, valid, thr = self._dec_ctx[direction]
-        dec = self.head_decoder_fw if direction == 0 else self.head_decoder_bw
+        dec = self.head_decoder_fw if direction % 2 == 0 else self.head_decoder_bw
         filled = torch.squeeze(occupancy > 0.5, dim=1)
         self._sink_preds[(direction, it)] = dec(net_out, thr, pc=pc, pointwise_voxel_coordinates=coors,
                                                 pointwise_valid_mask=valid, filled_pillar_mask=filled,
@@ -276,13 +276,17 @@ class SLIM(nn.Module):
         hold the results of eager calls made in between."""
         if not static:
             return self._sink_preds
-        st = net._graphs.get("net")
+        st = net._graphs.get(getattr(net, "_last_graph_slot", "net"))
         if getattr(net, "n_graph_captures", 0) != captures_before:  # this call captured (again)
             self._graph_preds = (st["key"], dict(self._sink_preds))
-        if st is None or self._graph_preds is None or self._graph_preds[0] != st["key"]:
+            if not hasattr(self, "_graph_preds_by_slot"):
+                self._graph_preds_by_slot = {}
+            self._graph_preds_by_slot[getattr(net, "_last_graph_slot", "net")] = self._graph_preds
+        rec = self._graph_preds_by_slot.get(getattr(net, "_last_graph_slot", "net")) if hasattr(self, "_graph_preds_by_slot") else self._graph_preds
+        if st is None or rec is None or rec[0] != st["key"]:
             raise RuntimeError("SLIM: the replayed CUDA graph has no decoded outputs on record (it was not captured "
                                "through SLIM.forward)")
-        return self._graph_preds[1]
+        return rec[1]
 
     _POINTWISE = ("static_flow", "dynamic_flow", "dynamicness", "staticness", "aggregated_flow", "static_aggr_flow")
 
@@ -301,42 +305,60 @@ class SLIM(nn.Module):
         return out
 
     def forward(self, sample_data_t0, sample_data_t1, summaries=None):
+        preds = self.forward_frames([sample_data_t0, sample_data_t1], [(0, 1)])
+        self.predictions_fw, self.predictions_bw = preds[0], preds[1]
+        return preds[0], preds[1]
+
+    TRIPLE_PAIRS = ((0, 1), (0, 2), (1, 2))  # t0 -> t1, t0 -> t2, t1 -> t2 (experiment.py:386-456)
+
+    def forward_triple(self, sample_data_t0, sample_data_t1, sample_data_t2):
+        """The three model() calls the reference's KITTI / nuScenes export makes per sample (``experiment.py:386-456``) as ONE
+        pass in which every frame is encoded once.  Returns {"t0_t1": preds, "t1_t0": ..., "t0_t2", "t2_t0", "t1_t2",
+        "t2_t1"} -- each what ``forward`` returns for that direction (a list over decoded iterations)."""
+        preds = self.forward_frames([sample_data_t0, sample_data_t1, sample_data_t2], self.TRIPLE_PAIRS)
+        out = {}
+        for p, (a, b) in enumerate(self.TRIPLE_PAIRS):
+            out["t%d_t%d" % (a, b)] = preds[2 * p]
+            out["t%d_t%d" % (b, a)] = preds[2 * p + 1]
+        return out
+
+    def forward_frames(self, samples, pairs):
+        """``samples[f]``: the sample dictionary of frame f, ``pairs``: [(a, b), ...].  Returns the decoded predictions per
+        direction: [a -> b of pair 0, b -> a of pair 0, a -> b of pair 1, ...]; a direction is decoded with the points,
+        pillar coordinates and occupancy of its SOURCE frame, like ``slim.py:77-148``."""
         dev = next(self.parameters()).device
-        raw = bool(sample_data_t0.get("raw_scan", False)) and not self.cfg.data.use_ground_for_network
-        assert raw == (bool(sample_data_t1.get("raw_scan", False)) and not self.cfg.data.use_ground_for_network)
+        raw = bool(samples[0].get("raw_scan", False)) and not self.cfg.data.use_ground_for_network
+        assert all((bool(s.get("raw_scan", False)) and not self.cfg.data.use_ground_for_network) == raw for s in samples)
         net = self.raft_network
-        pcl_t0 = get_network_input_pcls(self.cfg, sample_data_t0, "ta", to_device=dev)
-        pcl_t1 = get_network_input_pcls(self.cfg, sample_data_t1, "ta", to_device=dev)
+        pcls = [get_network_input_pcls(self.cfg, s, "ta", to_device=dev) for s in samples]
         thr = self.moving_dynamicness_threshold.value()
+        sources = [samples[f] for a, b in pairs for f in (a, b)]  # per direction
+        n_dirs = len(sources)
         if self.decode_as_sink and dev.type == "cuda":
-            static = net.will_use_graph(pcl_t0, pcl_t1)
-            key = self._stage_decode_inputs((sample_data_t0, sample_data_t1), dev, thr, static)
+            static = net.will_use_graph(*pcls)
+            key = self._stage_decode_inputs(sources, dev, thr, static)
             net.output_sink, net.output_sink_begin = self._sink, self._sink_begin
             net.graph_extra_key = (key, self.static_aggregation) if static else None
             captures_before = getattr(net, "n_graph_captures", 0)
-            net(pcl_t0, pcl_t1, raw_scans=raw)
+            net.forward_frames(pcls, pairs, raw_scans=raw)
             decoded = self._sink_results(net, static, captures_before)
             copy = static and not self.outputs_alias_static_buffers
-            preds_fw, preds_bw = ([self._present(decoded[(k, it)], self._dec_n[k], thr, copy)
-                                   for it in sorted(i for (kk, i) in decoded if kk == k)] for k in (0, 1))
-            self.predictions_fw, self.predictions_bw = preds_fw, preds_bw
-            return preds_fw, preds_bw
+            return [[self._present(decoded[(k, it)], self._dec_n[k], thr, copy)
+                     for it in sorted(i for (kk, i) in decoded if kk == k)] for k in range(n_dirs)]
         net.output_sink = net.output_sink_begin = net.graph_extra_key = None
-        outs_fw, outs_bw, aux = net(pcl_t0, pcl_t1, raw_scans=raw)
-        filled = [torch.squeeze(aux[k]["bev_net_input_dbg"] > 0.5, dim=1) for k in ("t0", "t1")]
-        its = range(len(outs_fw))  # one entry per iteration, or only the last one in "last" mode
-        preds_fw, preds_bw = [], []
-        per_dir = ((outs_fw, sample_data_t0, filled[0], self.head_decoder_fw, preds_fw),
-                   (outs_bw, sample_data_t1, filled[1], self.head_decoder_bw, preds_bw))
+        outs, occs = net.forward_frames(pcls, pairs, raw_scans=raw)
+        frame_of = [f for a, b in pairs for f in (a, b)]
+        preds = [[] for _ in range(n_dirs)]
         moved: Dict[int, tuple] = {}
-        for it in its:
-            for k, (outs, sample, fl, dec, preds) in enumerate(per_dir):
-                if k not in moved:
-                    pt = sample["pcl_ta"]
-                    moved[k] = (pt["pcl"].to(dev, non_blocking=True), pt["pillar_coors"].to(dev, non_blocking=True),
-                                pt["pcl_is_valid"].to(dev, non_blocking=True))
-                pc, coors, valid = moved[k]
-                preds.append(dec(outs[it], thr, pc=pc, pointwise_voxel_coordinates=coors, pointwise_valid_mask=valid,
-                                 filled_pillar_mask=fl, static_aggregation=self.static_aggregation))
-        self.predictions_fw, self.predictions_bw = preds_fw, preds_bw
-        return preds_fw, preds_bw
+        for k in range(n_dirs):
+            f = frame_of[k]
+            if f not in moved:
+                pt = samples[f]["pcl_ta"]
+                moved[f] = (pt["pcl"].to(dev, non_blocking=True), pt["pillar_coors"].to(dev, non_blocking=True),
+                            pt["pcl_is_valid"].to(dev, non_blocking=True), torch.squeeze(occs[f] > 0.5, dim=1))
+            pc, coors, valid, filled = moved[f]
+            dec = self.head_decoder_fw if k % 2 == 0 else self.head_decoder_bw
+            for o in outs[k]:  # one entry per iteration, or only the last one in "last" mode
+                preds[k].append(dec(o, thr, pc=pc, pointwise_voxel_coordinates=coors, pointwise_valid_mask=valid,
+                                    filled_pillar_mask=filled, static_aggregation=self.static_aggregation))
+        return preds

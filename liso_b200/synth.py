@@ -166,8 +166,9 @@ def _ego_motion(rng: np.random.Generator) -> np.ndarray:
     return T
 
 
-def make_frame_pair(workload: Dict[str, Any], seed: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
-    """Return (full no-ground cloud t0, same t1, odom_t0_t1 4x4 f64) for one pair."""
+def make_frame_pair(workload: Dict[str, Any], seed: int, n_frames: int = 2):
+    """Return (full no-ground cloud t0, same t1, odom_t0_t1 4x4 f64) for one pair; with ``n_frames=3`` (t0, t1, t2,
+    odom_t0_t1, odom_t0_t2) -- the first two frames are the pair's."""
     rng = np.random.default_rng(seed)
     bev = float(workload["bev_range_m"][0])
     beams = workload["beams"]
@@ -197,7 +198,20 @@ def make_frame_pair(workload: Dict[str, Any], seed: int) -> Tuple[np.ndarray, np
     boxes1[:, :3] = ctr[:, :3]
     boxes1[:, 6] -= np.arctan2(odom[1, 0], odom[0, 0])
     pc1 = frame(boxes1, n_az, rng, odom)
-    return pc0, pc1, odom
+    if n_frames == 2:
+        return pc0, pc1, odom
+    # a third frame (the KITTI / nuScenes export also runs t0 -> t2 and t1 -> t2): one more ego-motion / object step
+    step = _ego_motion(rng)
+    odom2 = odom @ step  # pose of the sensor at t2 expressed in t0
+    boxes2 = scene["boxes"].copy()
+    boxes2[:, 0] += boxes2[:, 7] * 2 * dt
+    boxes2[:, 1] += boxes2[:, 8] * 2 * dt
+    inv2 = np.linalg.inv(odom2)
+    ctr2 = np.concatenate([boxes2[:, :3], np.ones((boxes2.shape[0], 1))], axis=-1) @ inv2.T
+    boxes2[:, :3] = ctr2[:, :3]
+    boxes2[:, 6] -= np.arctan2(odom2[1, 0], odom2[0, 0])
+    pc2 = frame(boxes2, n_az, rng, odom2)
+    return pc0, pc1, pc2, odom, odom2
 
 
 def make_sample_dicts(workload: Dict[str, Any], seeds: List[int], as_torch: bool = True):
@@ -227,3 +241,53 @@ def make_sample_dicts(workload: Dict[str, Any], seeds: List[int], as_torch: bool
             }
         )
     return out[0], out[1]
+
+
+def _sample_of(pc: np.ndarray, bev, grid) -> Dict[str, Any]:
+    """Un-batched sample dictionary of one frame (what ``liso_b200.slim.export.collate_pairs`` batches)."""
+    import torch
+
+    coors, ok = pillar_coors_f64_numpy(pc, bev, grid)
+    return {"pcl_full_no_ground_ta": torch.from_numpy(pc),
+            "pcl_ta": {"pcl": torch.from_numpy(pc[ok]), "pillar_coors": torch.from_numpy(coors[ok])}}
+
+
+class SyntheticExportDataset:
+    """Flow-export workload (BASELINE configs[4]): ``n_samples`` distinct samples of ``frames`` (2: t0, t1 | 3: t0, t1, t2)
+    synthetic LiDAR frames each.  The ray caster makes a sample in ~2 s of CPU time, so the samples are drawn from a pool
+    of ``pool`` cast scenes and made distinct by a per-sample yaw rotation + shift of the whole scene (every frame of a
+    sample gets the same rigid motion: the relative motion between the frames -- what the network estimates -- is kept,
+    every pillar map changes).  ``dataset[i] -> (sample_id, sample_t0, sample_t1[, sample_t2])`` with un-batched host
+    tensors, deterministic in ``i``."""
+
+    def __init__(self, workload: Dict[str, Any], n_samples: int, frames: int = 2, pool: int = 16, seed0: int = 5000):
+        assert frames in (2, 3)
+        self.workload, self.n, self.frames, self.pool, self.seed0 = workload, int(n_samples), frames, max(1, int(pool)), seed0
+        self._cache: Dict[int, tuple] = {}
+
+    def __len__(self) -> int:
+        return self.n
+
+    def _scene_frames(self, k: int):
+        if k not in self._cache:
+            out = make_frame_pair(self.workload, self.seed0 + k, n_frames=self.frames)
+            self._cache[k] = tuple(out[:self.frames])
+        return self._cache[k]
+
+    def __getitem__(self, i: int):
+        if not 0 <= i < self.n:
+            raise IndexError(i)
+        frames = self._scene_frames(i % self.pool)
+        rng = np.random.default_rng(self.seed0 * 7919 + i)
+        variant = i // self.pool
+        yaw = 0.0 if variant == 0 else rng.uniform(-np.pi, np.pi)
+        shift = np.zeros(2) if variant == 0 else rng.uniform(-1.5, 1.5, size=2)
+        c, s_ = np.float32(np.cos(yaw)), np.float32(np.sin(yaw))
+        bev, grid = self.workload["bev_range_m"], self.workload["img_grid_size"]
+        samples = []
+        for pc in frames:
+            q = pc.copy()
+            q[:, 0] = c * pc[:, 0] - s_ * pc[:, 1] + np.float32(shift[0])
+            q[:, 1] = s_ * pc[:, 0] + c * pc[:, 1] + np.float32(shift[1])
+            samples.append(_sample_of(q, bev, grid))
+        return ("%06d" % i,) + tuple(samples)

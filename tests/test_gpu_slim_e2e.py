@@ -260,3 +260,36 @@ def test_graph_replay_after_eager_calls_returns_the_graphs_own_results(cuda):
     assert g_s.shape[1] == n_s and g_t.shape[1] == n_t and e_t.shape[1] == n_t
     assert torch.equal(g_s2, g_s)
     assert torch.equal(g_t, e_t)
+
+
+def test_triple_export_pass_equals_three_forwards(cuda, tmp_path):
+    """SURVEY 8f.3 / experiment.py:386-456: SLIM.forward_triple (every frame encoded once, six directions in one graph)
+    returns what three independent SLIM.forward calls return -- t0 -> t1, t0 -> t2, t1 -> t2 -- bit for bit in the
+    exported maps; and run_flow_export writes them as the reference's 12-array file."""
+    from liso_b200.slim import export
+    from liso_b200.synth import SyntheticExportDataset
+
+    cfg = make_cfg("T")
+    model, _ = _model(cfg, cuda, decode_iterations="last", static_aggregation=False)
+    ds = SyntheticExportDataset(WORKLOADS["T"], 5, frames=3, pool=3)
+    items = [ds[i] for i in range(2)]
+    batch = export.collate_pairs([it[1:] for it in items])
+    with torch.no_grad():
+        tri = model.forward_triple(*batch)
+        tri = {k: (v[-1].modified_network_output.static_flow.clone(), v[-1].modified_network_output.dynamicness.clone(),
+                   v[-1].static_flow.clone()) for k, v in tri.items()}
+        enc_before = _lib.load().slimb200_launch_count(_lib.K_PILLAR_NHWC)
+        model.forward_triple(*batch)
+        assert _lib.load().slimb200_launch_count(_lib.K_PILLAR_NHWC) - enc_before == 3  # three frames, three encoder passes
+        for a, b in ((0, 1), (0, 2), (1, 2)):
+            pf, pb = model(batch[a], batch[b], None)
+            for key, p in (("t%d_t%d" % (a, b), pf), ("t%d_t%d" % (b, a), pb)):
+                assert torch.equal(tri[key][0], p[-1].modified_network_output.static_flow), key
+                assert torch.equal(tri[key][1], p[-1].modified_network_output.dynamicness), key
+                assert torch.equal(tri[key][2], p[-1].static_flow), key
+    out = export.run_flow_export(model, ds, str(tmp_path), cfg.data.bev_range_m, batch_size=2, device=cuda, writer_workers=2)
+    assert out["pairs"] == 5 and out["files"] == 5
+    z = np.load(os.path.join(str(tmp_path), "000001.npz"))
+    assert len(z.files) == 14
+    assert np.array_equal(z["bev_raw_flow_t2_t0"], tri["t2_t0"][0][1].cpu().numpy())
+    assert np.array_equal(z["bev_dynamicness_t1_t2"], tri["t1_t2"][1][1].cpu().numpy())

@@ -467,3 +467,66 @@ def test_lookup_division_by_precomputed_reciprocal_is_correctly_rounded():
             assert q == _rn32(Fraction(a) / Fraction(bf)), (a, b)
             n += 1
     assert n > 1500
+
+
+# (pinned against the reference source by tests/test_oracle_vs_reference.py::test_export_schema_keys_match_reference_source)
+from tests_keys import REFERENCE_TRIPLE_KEYS  # noqa: E402
+
+
+def test_triple_export_writes_the_twelve_maps_of_the_reference(tmp_path):
+    """KITTI / nuScenes export: (t0, t1, t2) samples -> one file with t0<->t1, t0<->t2, t1<->t2 (experiment.py:404-456),
+    consumable like torch_dataset_commons.py:619-675 (np.load -> bev_raw_flow_* (H, W, 2), bev_dynamicness_* (H, W))."""
+    H, W = 6, 5
+    seen = []
+
+    class FakePipeline:
+        def __init__(self, model, device):
+            pass
+
+        def run(self, batches, consume):
+            n = 0
+            for j, batch in enumerate(batches):
+                assert len(batch) == 3  # collated t0, t1, t2
+                B = len(batch[0]["pcl_full_no_ground_ta"])
+                seen.append(B)
+                n_pts = [torch.tensor([float(t.shape[0]) for t in s["pcl_full_no_ground_ta"]]) for s in batch]
+                flows, dyns = [], []
+                for k, d in enumerate(export.DIRECTIONS_TRIPLE):  # value = 100 * direction + points of the source frame
+                    src = n_pts[int(d[1])]
+                    f = (100.0 * k + src)[:, None, None, None].expand(B, H, W, 2).contiguous()
+                    flows.append(f)
+                    dyns.append(f[..., 0].contiguous() + 0.5)
+                consume(j, flows + dyns)
+                n += 1
+            return n
+
+    def sample(n):
+        return {"pcl_full_no_ground_ta": torch.zeros(n, 4),
+                "pcl_ta": {"pcl": torch.ones(n - 1, 4), "pillar_coors": torch.zeros(n - 1, 2, dtype=torch.int32)}}
+
+    dataset = [("%03d" % i, sample(10 + i), sample(20 + i), sample(30 + i)) for i in range(5)]
+    out = export.run_flow_export(_CpuModel(), dataset, str(tmp_path), (70.0, 70.0), batch_size=2, pipeline_factory=FakePipeline,
+                                 writer_workers=2)
+    assert out["pairs"] == 5 and out["files"] == 5 and seen == [2, 2, 1]
+    z = np.load(tmp_path / "003.npz")
+    assert set(z.files) == REFERENCE_TRIPLE_KEYS
+    for k, d in enumerate(export.DIRECTIONS_TRIPLE):
+        src = {"0": 13, "1": 23, "2": 33}[d[1]]
+        assert z["bev_raw_flow_" + d].shape == (H, W, 2) and z["bev_raw_flow_" + d].dtype == np.float32
+        assert float(z["bev_raw_flow_" + d][0, 0, 0]) == 100.0 * k + src
+        assert z["bev_dynamicness_" + d].shape == (H, W) and float(z["bev_dynamicness_" + d][1, 1]) == 100.0 * k + src + 0.5
+    assert export.export_keys(2) == ["bev_raw_flow_t0_t1", "bev_raw_flow_t1_t0", "bev_dynamicness_t0_t1", "bev_dynamicness_t1_t0"]
+
+
+def test_synthetic_export_dataset_is_deterministic_and_distinct():
+    from liso_b200.synth import SyntheticExportDataset
+
+    ds = SyntheticExportDataset(WORKLOADS["T"], 9, frames=3, pool=2)
+    a, b, c = ds[1], ds[3], SyntheticExportDataset(WORKLOADS["T"], 9, frames=3, pool=2)[3]
+    assert len(a) == 4 and a[0] == "000001" and b[0] == "000003"
+    assert torch.equal(b[1]["pcl_full_no_ground_ta"], c[1]["pcl_full_no_ground_ta"])                      # deterministic in i
+    assert b[1]["pcl_full_no_ground_ta"].shape == a[1]["pcl_full_no_ground_ta"].shape                    # same cast scene ...
+    assert not torch.equal(b[1]["pcl_full_no_ground_ta"], a[1]["pcl_full_no_ground_ta"])                # ... rotated + shifted
+    assert not torch.equal(b[1]["pcl_ta"]["pillar_coors"][:50], a[1]["pcl_ta"]["pillar_coors"][:50])
+    d0, d1, d2 = export.collate_pairs([ds[0][1:], ds[1][1:]])
+    assert d2["pcl_ta"]["pcl"].shape[0] == 2 and d2["pcl_ta"]["pcl_is_valid"].dtype == torch.bool

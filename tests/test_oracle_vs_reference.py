@@ -96,3 +96,21 @@ def test_dataset_side_preprocessing_live():
                                torch.from_numpy(np.append(ds.img_grid_size_np, np.array(1))))
         assert np.array_equal(tc.numpy()[:, :2], c)
         assert np.array_equal(O.ground_label_cone_f32(pts, -1.5), cone_legacy(pts, cone_z_threshold__m=-1.5))
+
+
+def test_export_schema_keys_match_reference_source():
+    """The arrays the reference export writes per sample, read off its source (experiment.py:391-456,459-471): every
+    `preds["..."]` / `save_stuff[...]` key + bev_range_m == what AsyncNpzWriter writes for a triple, and the pair subset."""
+    import os
+    import re
+
+    from liso_b200.slim import export
+    from tests_keys import REFERENCE_TRIPLE_KEYS
+
+    src = open(os.path.join(ref_shims.REF_ROOT, "liso/slim/experiment.py")).read()
+    body = src[src.index("def slim_inference_and_save_result"):src.index("def run(", src.index("def slim_inference_and_save_result"))]
+    keys = set(re.findall(r'preds\["([a-z0-9_]+)"\]', body)) | set(re.findall(r'save_stuff_cpu\["([a-z0-9_]+)"\]', body))
+    keys |= set(re.findall(r'"(static_threshold)":', body))
+    assert keys == REFERENCE_TRIPLE_KEYS
+    assert set(export.export_keys(6)) | {"static_threshold", "bev_range_m"} == keys
+    assert set(export.export_keys(2)) < keys
