@@ -167,9 +167,13 @@ def main():
                          "last: the export shortcut -- only the final iteration is decoded, no aggregation "
                          "(identical exported tensors); the other mode is reported beside the headline as `other_mode`")
     ap.add_argument("--no-cuda-graph", action="store_true", help="launch the GRU refinement loop eagerly instead of as a CUDA graph")
-    ap.add_argument("--write-npz", default=None, metavar="DIR",
-                    help="also time the export loop WITH the per-pair .npz files written by AsyncNpzWriter (SURVEY 8f.3); "
-                         "reported as `export_with_writer`, never as the headline")
+    ap.add_argument("--export-pairs", type=int, default=10000,
+                    help="BASELINE configs[4]: flow export of this many DISTINCT synthetic pairs in total, frame-sharded over the ranks, "
+                         "through run_flow_export with the .npz files written (reported as `export`); the KITTI / nuScenes triple "
+                         "export runs on a third as many samples; 0 = skip")
+    ap.add_argument("--export-pool", type=int, default=8, help="ray-cast scenes the export samples are derived from")
+    ap.add_argument("--export-zlib-pairs", type=int, default=240, help="pairs for the host-zlib writer contrast line (N=1 only; 0 = skip)")
+    ap.add_argument("--export-dir", default=None, help="where the export writes (default: a temporary directory under /dev/shm)")
     ap.add_argument("--memory-format", default="channels_last", choices=["channels_last", "contiguous"],
                     help="memory format of the canvas our encoder emits and of the stock convs that consume it")
     ap.add_argument("--fused-lookup", action="store_true",
@@ -285,7 +289,10 @@ def main():
             self.h2d = sample_bytes(self.s0) + sample_bytes(self.s1)
             H, Wd = self.W["img_grid_size"]
             self.d2h = 2 * batch * H * Wd * 2 * 4 + 2 * batch * H * Wd * 4  # 2 x flow (B,H,W,2) + 2 x dynamicness (B,H,W), fp32
-            self.pipeline = ExportPipeline(model, dev, amp_ctx=amp if args.conv_precision == "bf16" else None)
+            # e2e: the export loop with the maps deflated on the device (what run_flow_export(compress_on_gpu=True)
+            # runs); `pipeline_raw` downloads the uncompressed fp32 maps instead (round-1 behaviour, reported beside it)
+            self.pipeline = ExportPipeline(model, dev, amp_ctx=amp if args.conv_precision == "bf16" else None, compress=True)
+            self.pipeline_raw = ExportPipeline(model, dev, amp_ctx=amp if args.conv_precision == "bf16" else None)
             self.consumed = {"bytes": 0}
 
         def set_decode(self, mode):
@@ -298,14 +305,18 @@ def main():
                 pf, pb = self.model(self.d0, self.d1, None)
             return export_tensors(pf, pb)
 
-        def _consume(self, _idx, host_tensors):  # the D2H result is read on the host
-            self.consumed["bytes"] += sum(t.numel() * t.element_size() for t in host_tensors)
-            self.consumed["probe"] = float(host_tensors[0].view(-1)[0])
+        def _consume(self, _idx, host):  # the D2H result is read on the host
+            if hasattr(host, "member"):  # EncodedBatch: member table + the DEFLATE streams of all exported maps
+                self.consumed["bytes"] += host.total_bytes + host.table.nbytes
+                self.consumed["probe"] = float(host.data[host.total_bytes - 1]) + float(host.table[0, 2])
+                return
+            self.consumed["bytes"] += sum(t.numel() * t.element_size() for t in host)
+            self.consumed["probe"] = float(host[0].view(-1)[0])
 
-        def run_e2e(self, steps):
+        def run_e2e(self, steps, raw=False):
             """`steps` batches through the public export loop: pinned host clouds in, pinned host results out; every batch's
             H2D and D2H copies are inside the timed region (double-buffered against the compute of its neighbours)."""
-            self.pipeline.run(((self.h0, self.h1) for _ in range(steps)), self._consume)
+            (self.pipeline_raw if raw else self.pipeline).run(((self.h0, self.h1) for _ in range(steps)), self._consume)
             torch.cuda.synchronize()
 
         def prepare(self):
@@ -461,8 +472,14 @@ def main():
     prof_steps = max(3, args.steps // 2)
     prof = main.kernel_profile(prof_steps)
     main.run_e2e(args.warmup)
+    main.consumed["bytes"] = 0
     ms_e2e, _, _ = main.timed(lambda: main.run_e2e(args.steps), 1)
+    d2h_e2e = main.consumed["bytes"] / args.steps  # measured: member table + compressed streams actually downloaded
     clocks = sampler.stop() if rank == 0 else None
+    n_raw = max(3, args.steps // 2)
+    main.run_e2e(2, raw=True)
+    ms_e2e_raw, _, _ = main.timed(lambda: main.run_e2e(n_raw, raw=True), 1)
+    ms_e2e_raw /= n_raw
 
     # the other decode mode, same run, fewer steps (reported beside the headline, never as the headline)
     other = "last" if args.decode == "all" else "all"
@@ -488,30 +505,62 @@ def main():
     main.model.raft_network.fuse_lookup_conv = bool(args.fused_lookup)
     main.prepare()
 
-    writer_line = None
-    if args.write_npz and rank == 0:
+    # ---- the flow export itself (BASELINE configs[4]): DISTINCT synthetic samples, sharded over the ranks by the
+    # reference's modulo rule, through run_flow_export = loader thread -> ExportPipeline (raw scans prepared on the device,
+    # maps deflated on the device) -> zip framing + file write on worker threads.  Wall clock incl. the final flush, max over ranks.
+    export_line = None
+    if args.export_pairs > 0:
         import shutil
+        import tempfile
 
-        from liso_b200.slim.export import AsyncNpzWriter
+        from liso_b200.slim.export import run_flow_export
+        from liso_b200.synth import SyntheticExportDataset
 
-        out_dir = os.path.join(args.write_npz, "rank%d" % rank)
-        shutil.rmtree(out_dir, ignore_errors=True)
-        thr_host = float(main.model.moving_dynamicness_threshold.value())
-        n_batches = max(3, args.steps)
-        t0 = time.perf_counter()
-        wr = AsyncNpzWriter(out_dir, main.W["bev_range_m"])
-        main.pipeline.run(((main.h0, main.h1) for _ in range(n_batches)),
-                          lambda j, host: wr.submit_batch(["%06d_%d" % (j, b) for b in range(args.batch)], host, thr_host))
-        n_files = wr.close()
-        dt = time.perf_counter() - t0
-        mb = sum(os.path.getsize(os.path.join(out_dir, f)) for f in os.listdir(out_dir)) / 1e6
-        writer_line = {"value": n_files / dt, "unit": UNIT, "files": n_files, "compressed_mb_per_pair": mb / max(1, n_files),
-                       "writer_threads": wr.pool._max_workers, "what": "ExportPipeline + AsyncNpzWriter (np.savez_compressed, "
-                       "reference schema), wall clock incl. the final flush"}
-        shutil.rmtree(out_dir, ignore_errors=True)
+        base = args.export_dir or tempfile.mkdtemp(prefix="slimb200_export_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        main.set_decode("last")  # the export reads the last iteration only (experiment.py:391-399); identical exported tensors
+        main.model.outputs_alias_static_buffers = True
+        n_cpu = os.cpu_count() or 1
+        loaders = max(2, min(6, n_cpu // max(1, world) - 2))
+        writers = max(2, min(8, n_cpu // max(1, world) - 1))
+        export_line = {"what": "run_flow_export over distinct synthetic KITTI-sized samples (pool of ray-cast scenes, per-sample rigid motion), "
+                               "raw scans in (ground rule, pillar map, compaction on the device), .npz files out (maps deflated on the device, "
+                               "framed + written by %d worker threads, %d loader threads); files are unlinked after the write to bound "
+                               "disk use; wall clock incl. final flush, max over ranks" % (writers, loaders),
+                       "target": base, "decode": "last iteration only (what the export reads)"}
+        for kind, frames, n_total in (("pairs", 2, args.export_pairs), ("triples", 3, max(world * args.batch, args.export_pairs // 3))):
+            ds = SyntheticExportDataset(main.W, n_total, frames=frames, pool=args.export_pool, raw=True).prepare(workers=min(8, max(1, n_cpu // world)))
+            tgt = os.path.join(base, "%s_rank%d" % (kind, rank))
+            # untimed: graph capture for this frame structure + cuDNN autotune, on the first batch of this rank's share
+            warm = SyntheticExportDataset(main.W, world * args.batch, frames=frames, pool=args.export_pool, raw=True)
+            warm._cache = ds._cache
+            run_flow_export(main.model, warm, tgt + "_warm", main.W["bev_range_m"], world_size=world, worker_id=rank, batch_size=args.batch,
+                            device=dev, writer_workers=writers, compress_on_gpu=True, loader_workers=loaders, unlink_after_write=True)
+            barrier()
+            res = run_flow_export(main.model, ds, tgt, main.W["bev_range_m"], world_size=world, worker_id=rank, batch_size=args.batch,
+                                  device=dev, writer_workers=writers, compress_on_gpu=True, loader_workers=loaders, unlink_after_write=True)
+            per_sample_pairs = 1 if frames == 2 else 3
+            export_line[kind] = {"samples": int(res["pairs"]), "files": int(res["files"]), "elapsed_s": res["elapsed_s_max"],
+                                 "samples_per_s": res["pairs"] / res["elapsed_s_max"],
+                                 "pairs_per_s": per_sample_pairs * res["pairs"] / res["elapsed_s_max"],
+                                 "file_mb_per_sample": res["file_bytes"] / max(1.0, res["files"]) / 1e6,
+                                 "d2h_mb_per_sample": res["d2h_bytes"] / max(1.0, res["pairs"]) / 1e6,
+                                 "arrays_per_file": 6 if frames == 2 else 14}
+            del ds, warm
+        export_line["triple_vs_three_pair_calls"] = export_line["triples"]["pairs_per_s"] / export_line["pairs"]["pairs_per_s"]
+        if world == 1 and args.export_zlib_pairs > 0:  # the round-1 writer for contrast: raw fp32 maps downloaded, zlib on host threads
+            ds = SyntheticExportDataset(main.W, args.export_zlib_pairs, frames=2, pool=args.export_pool, raw=True)
+            res = run_flow_export(main.model, ds, os.path.join(base, "zlib"), main.W["bev_range_m"], batch_size=args.batch, device=dev,
+                                  compress_on_gpu=False, loader_workers=loaders, unlink_after_write=True)
+            export_line["pairs_host_zlib_writer"] = {"samples": int(res["pairs"]), "pairs_per_s": res["pairs"] / res["elapsed_s_max"],
+                                                     "file_mb_per_sample": res["file_bytes"] / max(1.0, res["files"]) / 1e6,
+                                                     "writer_threads": max(1, n_cpu - 1),
+                                                     "what": "np.savez_compressed on host threads (AsyncNpzWriter), raw maps downloaded"}
+        shutil.rmtree(base, ignore_errors=True)
+        main.set_decode(args.decode)
 
     tot = reduce_counters({"pairs": float(args.batch * args.steps), "ms_res_max": ms_res, "ms_e2e_max": ms_e2e,
-                           "launches": float(launches), "ms_other_max": ms_other, "ms_other_e2e_max": ms_other_e2e, "ms_var_max": ms_var},
+                           "launches": float(launches), "ms_other_max": ms_other, "ms_other_e2e_max": ms_other_e2e, "ms_var_max": ms_var,
+                           "ms_e2e_raw_max": ms_e2e_raw, "d2h_e2e": float(d2h_e2e)},
                           device=dev)
     # per-rank step times (scaling hygiene: who is the straggler)
     per_rank = None
@@ -568,8 +617,13 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": tot["ms_res_max"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": config, "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": main.h2d, "d2h_bytes_per_step": main.d2h,
-                    "ms_per_step": tot["ms_e2e_max"] / args.steps},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": main.h2d, "d2h_bytes_per_step": int(tot["d2h_e2e"] / world),
+                    "ms_per_step": tot["ms_e2e_max"] / args.steps,
+                    "result": "the exported maps of every pair (last-iteration BEV static flow + dynamicness, both directions) as DEFLATE "
+                              "streams + CRC remainders, ready to be framed as the reference's .npz members (deflated on the device; "
+                              "bytes counted from what was downloaded)",
+                    "uncompressed_d2h": {"value": args.batch * world / (tot["ms_e2e_raw_max"] / 1e3), "unit": UNIT,
+                                         "d2h_bytes_per_step": main.d2h, "what": "same loop downloading the raw fp32 maps (round 1)"}},
             "gpu_launches": int(tot["launches"]), "roofline": roofline, "kernels": kernels,
             "other_mode": {"decode": other, "value": args.batch * world / (tot["ms_other_max"] / 1e3),
                            "e2e": args.batch * world / (tot["ms_other_e2e_max"] / 1e3), "unit": UNIT,
@@ -595,8 +649,8 @@ def main():
         valid = main.s0["pcl_ta"]["pcl_is_valid"][0]
         epe = (pf[-1].static_flow[0].cpu() - of[-1]["pointwise_static_flow"][0]).norm(dim=-1)[valid]
         line["parity"] = {"per_point_static_flow_aee_m_vs_oracle": float(epe.mean()), "max_m": float(epe.max()), "limit_m": 0.01}
-    if writer_line:
-        line["export_with_writer"] = writer_line
+    if export_line:
+        line["export"] = export_line
 
     # ---- configs[2] / configs[3]: short same-process lines for the nuScenes- and AV2-sized workloads (N=1 only) ----
     if world == 1 and not args.no_other_workloads and args.workload == "K":

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SLIMB200_VERSION 200
+#define SLIMB200_VERSION 210
 
 enum {
   SLIMB200_OK = 0,
@@ -331,6 +331,46 @@ int slimb200_iter_update_taps(const float* taps, int32_t ksize, const float* bia
                               float* logits, float* stacked, int32_t stacked_channels, void* stream);
 int slimb200_add_relu(const float* x, const float* y, float* out, int64_t n, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Export writer.  Replaces the zlib pass of np.savez_compressed in
+ * slim_inference_and_save_result (liso/slim/experiment.py:459-471): every saved fp32 map becomes a raw
+ * DEFLATE stream (RFC 1951, fixed Huffman code, zero-word runs as distance-1 matches) plus the CRC-32
+ * remainder of its bytes, computed on the device; the host frames the streams as zip members
+ * (liso_b200/slim/npz_stream.py) that np.load reads like the reference's files
+ * (torch_dataset_commons.py:614-616).
+ *
+ * A member = one array of one sample: n_words 4-byte words, word k at
+ * src[(k / words_per_cell) * cell_stride + k % words_per_cell] (a channel slice of a packed
+ * channels-last buffer, or cell_stride == words_per_cell for a contiguous array).
+ *   plan    host only: fills first_chunk of every member; sizes of the workspace and of the largest
+ *           possible output (members are cut into SLIMB200_DEFLATE_CHUNK_BYTES chunks).
+ *   init    fills the caller-owned device table (SLIMB200_DEFLATE_TABLE_BYTES) the CRC needs; once per device.
+ *   encode  members_dev: the planned member array copied to the device.  out: the streams of all
+ *           members back to back.  member_out: (n_members + 1) x 4 uint32 on the device:
+ *           row i = {offset into out, bytes, crc remainder R, chunks}; row n_members = {total bytes,
+ *           overflow flag (out_capacity too small: out is incomplete), 0, 0}.
+ *           crc32(prefix | member bytes) = crc32(prefix | zeros of the member's length) ^ R.
+ *           Each stream is complete (last block has BFINAL); a stored block holding the .npy header may
+ *           be put in front of it.
+ * ---------------------------------------------------------------------------------------- */
+#define SLIMB200_DEFLATE_CHUNK_BYTES 8192
+#define SLIMB200_DEFLATE_SLOT_BYTES 9232
+#define SLIMB200_DEFLATE_MAX_CHUNKS 8192 /* per member: 64 MB */
+#define SLIMB200_DEFLATE_TABLE_BYTES ((256 + 2049 + 8192) * 4)
+typedef struct {
+  const void* src;        /* device, 4-byte aligned */
+  int32_t words_per_cell; /* >= 1 */
+  int32_t cell_stride;    /* in words, >= words_per_cell */
+  uint32_t n_words;       /* > 0 */
+  uint32_t first_chunk;   /* filled by slimb200_deflate_plan */
+} slimb200_deflate_member;
+int slimb200_deflate_plan(slimb200_deflate_member* members /*host[n_members]*/, int32_t n_members, int64_t* total_chunks,
+                          size_t* workspace_bytes, size_t* out_bound);
+int slimb200_deflate_init(void* tables, void* stream);
+int slimb200_deflate_encode(const slimb200_deflate_member* members_dev, int32_t n_members, int64_t total_chunks,
+                            const void* tables, void* workspace, size_t workspace_bytes, void* out, size_t out_capacity,
+                            uint32_t* member_out, void* stream);
+
 const char* slimb200_strerror(int code);
 int slimb200_version(void);
 
@@ -374,6 +414,10 @@ enum {
   SLIMB200_K_ADD_RELU,
   SLIMB200_K_LOOKUP_CONV,
   SLIMB200_K_LOOKUP_CONV_PACK,
+  SLIMB200_K_DEFLATE_TABLES,
+  SLIMB200_K_DEFLATE_CHUNKS,
+  SLIMB200_K_DEFLATE_SCAN,
+  SLIMB200_K_DEFLATE_GATHER,
   SLIMB200_N_KERNELS
 };
 int slimb200_profile_begin(void);

@@ -78,6 +78,14 @@ class DecodeParams(C.Structure):
 
 DECODE_BEV_CHANNELS, DECODE_POINT_CHANNELS = 16, 14
 
+
+class DeflateMember(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("words_per_cell", C.c_int32), ("cell_stride", C.c_int32), ("n_words", C.c_uint32),
+                ("first_chunk", C.c_uint32)]
+
+
+DEFLATE_CHUNK_BYTES, DEFLATE_TABLE_BYTES = 8192, (256 + 2049 + 8192) * 4
+
 # every symbol include/slimb200.h declares: (restype, argtypes)
 SYMBOLS = {
     "slimb200_pillar_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int64, C.POINTER(PillarParams)]),
@@ -158,6 +166,12 @@ SYMBOLS = {
          C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p],
     ),
     "slimb200_add_relu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "slimb200_deflate_plan": (C.c_int, [C.POINTER(DeflateMember), C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "slimb200_deflate_init": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "slimb200_deflate_encode": (
+        C.c_int,
+        [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p],
+    ),
     "slimb200_strerror": (C.c_char_p, [C.c_int]),
     "slimb200_version": (C.c_int, []),
     "slimb200_profile_begin": (C.c_int, []),
@@ -165,12 +179,13 @@ SYMBOLS = {
     "slimb200_launch_count": (C.c_int64, [C.c_int32]),
     "slimb200_kernel_name": (C.c_char_p, [C.c_int32]),
 }
-N_KERNELS = 34
+N_KERNELS = 38
 K_POINT_KEYS, K_SCAN_LOCAL, K_SCAN_GLOBAL, K_RANK_SCATTER = 0, 1, 2, 3
 K_TILE_ENCODE, K_PILLAR_NHWC, K_FEAT_TRANSPOSE, K_FEAT_PACK, K_CORR_GEMM, K_CORR_LOOKUP = 6, 7, 8, 9, 10, 11
 K_DECODE_BEV, K_DECODE_POINTS, K_DECODE_AGGR, K_RAFT_OUTPUT = 14, 15, 17, 18
 K_IN_STATS, K_IN_FINALIZE, K_IN_APPLY = 24, 25, 26
 K_LOOKUP_CONV = 32
+K_DEFLATE_CHUNKS, K_DEFLATE_SCAN, K_DEFLATE_GATHER = 35, 36, 37
 CANVAS_NCHW, CANVAS_NHWC = 0, 1
 
 _lib: Optional[C.CDLL] = None

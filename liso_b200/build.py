@@ -11,7 +11,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libslimb200.so")
-SOURCES = ["pillar_encode.cu", "corr_build.cu", "corr_lookup.cu", "corr_lookup2.cu", "corr_lookup3.cu", "corr_lookup4.cu", "head_decode.cu", "preprocess.cu", "instnorm.cu", "gru_glue.cu", "profile.cu"]
+SOURCES = ["pillar_encode.cu", "corr_build.cu", "corr_lookup.cu", "corr_lookup2.cu", "corr_lookup3.cu", "corr_lookup4.cu", "head_decode.cu", "preprocess.cu", "instnorm.cu", "gru_glue.cu", "npz_deflate.cu", "profile.cu"]
 
 
 def _nvcc() -> str:

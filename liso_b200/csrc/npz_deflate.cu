@@ -1,0 +1,425 @@
+// Export writer on the GPU.  The reference saves the BEV maps of every sample with np.savez_compressed
+// (liso/slim/experiment.py:459-471): zlib, on the CPU thread that also drives the GPU.  Here every saved array becomes a
+// raw DEFLATE stream (RFC 1951) + the CRC-32 of its bytes ON THE DEVICE; only the compressed bytes cross PCIe and the
+// host merely frames them as zip members (liso_b200/slim/npz_stream.py), so that np.load (torch_dataset_commons.py:
+// 614-616) reads the files unchanged.
+//
+// The maps are fp32 with exact zeros wherever the pillar is empty (head_decoder.py:567-609): runs of zero WORDS become
+// <literal 0><match distance 1, length <= 258>... and every other word four literals, all in the FIXED Huffman code
+// (RFC 1951 3.2.6), so that the bit length of every token is known without a histogram pass.
+//   * a member (one array of one sample) is cut into chunks of 8 KB; one CTA encodes one chunk as ONE non-final fixed
+//     block followed by an empty stored block, which byte-aligns the stream (the zlib "sync flush" marker; the last
+//     chunk's stored block carries BFINAL).  Chunks are therefore byte strings that concatenate.
+//   * thread = 4 consecutive words.  Runs are found with a block-wide prefix max (last non-zero word before me) and
+//     suffix min (first non-zero word after me); the tokens of a run are a function of the byte offset from its start,
+//     so every thread emits exactly the tokens that START inside its 16 bytes -- no token crosses a thread boundary
+//     decision.  Pass 1 counts bits, a block scan turns them into bit positions, pass 2 ORs the codes into shared memory.
+//   * CRC-32: pure remainders are linear, R(A|B) = R(A) x^(8|B|) + R(B), and R(zero words) = 0.  A thread with non-zero
+//     words folds them with the byte table, multiplies by x^(bits behind it in the chunk) (table), the CTA XORs, one
+//     thread multiplies by x^(bits behind the chunk in the member) and XORs into the member's accumulator.  The host
+//     adds the constant crc32(npy header | zeros) of the member's shape: crc(header | data) = that ^ R(data).
+//   * k_deflate_scan turns chunk sizes into offsets, k_deflate_gather packs the chunks into the output stream.
+#include "common.cuh"
+
+namespace {
+constexpr int CHUNK_BYTES = SLIMB200_DEFLATE_CHUNK_BYTES;
+constexpr int CHUNK_WORDS = CHUNK_BYTES / 4;
+constexpr int THREADS = CHUNK_WORDS / 4;  // 512: one uint4 of input per thread
+constexpr int WARPS = THREADS / 32;
+constexpr int SLOT_BYTES = SLIMB200_DEFLATE_SLOT_BYTES;
+constexpr int SLOT_WORDS = SLOT_BYTES / 4;
+constexpr uint32_t POLY = 0xEDB88320u;
+constexpr int TAB_T = 0;                          // byte table, 256 entries
+constexpr int TAB_XPW = 256;                      // x^(32 j), j = 0 .. CHUNK_WORDS
+constexpr int TAB_XPC = TAB_XPW + CHUNK_WORDS + 1;  // x^(8 CHUNK_BYTES j), j = 0 .. MAX_CHUNKS - 1
+constexpr int TAB_WORDS = TAB_XPC + SLIMB200_DEFLATE_MAX_CHUNKS;
+static_assert(TAB_WORDS * 4 == SLIMB200_DEFLATE_TABLE_BYTES, "table size");
+// worst case of a chunk: 3 header bits + 9 bits per byte + end-of-block 7 + stored header 3 + padding 7 + LEN/NLEN 32
+static_assert((3 + CHUNK_BYTES * 9 + 7 + 3 + 7 + 32 + 7) / 8 + 8 <= SLOT_BYTES, "slot too small");
+
+// GF(2)[x] / P in the reflected representation zlib uses (bit 31 = x^0): a * b mod P
+__host__ __device__ __forceinline__ uint32_t gf_mul(uint32_t a, uint32_t b) {
+  uint32_t p = 0;
+#pragma unroll 4
+  for (int i = 0; i < 32; ++i) {
+    if (a & (0x80000000u >> i)) p ^= b;
+    b = (b >> 1) ^ ((b & 1u) ? POLY : 0u);
+  }
+  return p;
+}
+__host__ __device__ inline uint32_t gf_xpow(uint64_t n) {  // x^n mod P
+  uint32_t p = 0x80000000u, sq = 0x40000000u;
+  while (n) {
+    if (n & 1) p = gf_mul(sq, p);
+    sq = gf_mul(sq, sq);
+    n >>= 1;
+  }
+  return p;
+}
+
+__global__ void k_deflate_tables(uint32_t* __restrict__ tab) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= TAB_WORDS) return;
+  if (i < TAB_XPW) {
+    uint32_t c = (uint32_t)i;
+    for (int k = 0; k < 8; ++k) c = (c & 1u) ? POLY ^ (c >> 1) : c >> 1;
+    tab[i] = c;
+  } else if (i < TAB_XPC) {
+    tab[i] = gf_xpow(32ull * (uint64_t)(i - TAB_XPW));
+  } else {
+    tab[i] = gf_xpow(8ull * CHUNK_BYTES * (uint64_t)(i - TAB_XPC));
+  }
+}
+
+// ---- fixed Huffman code, bit-reversed for LSB-first packing ---------------------------------------------------------
+struct Code {
+  uint32_t bits;
+  int n;
+};
+__device__ __forceinline__ Code lit_code(uint32_t v) {  // literal byte
+  if (v < 144u) return {__brev(0x30u + v) >> 24, 8};
+  return {__brev(0x190u + (v - 144u)) >> 23, 9};
+}
+__device__ __forceinline__ Code match_code(int len) {  // <length, distance 1>: length code + extra bits + 5 zero bits
+  uint32_t sym, extra = 0;
+  int ne = 0;
+  if (len == 258) {
+    sym = 285;
+  } else if (len <= 10) {
+    sym = 254 + len;
+  } else {
+    const uint32_t l = (uint32_t)len - 3u;
+    ne = 29 - __clz(l);  // floor(log2 l) - 2
+    sym = 257 + 4 * ne + (l >> ne);
+    extra = l & ((1u << ne) - 1u);
+  }
+  Code c;
+  if (sym < 280u) {
+    c.bits = __brev(sym - 256u) >> 25;
+    c.n = 7;
+  } else {
+    c.bits = __brev(0xC0u + (sym - 280u)) >> 24;
+    c.n = 8;
+  }
+  c.bits |= extra << c.n;
+  c.n += ne + 5;  // distance symbol 0 = five zero bits, no extra bits
+  return c;
+}
+
+struct BitCounter {
+  uint32_t n = 0;
+  __device__ __forceinline__ void put(Code c) { n += c.n; }
+};
+struct BitWriter {  // ORs codes into the shared chunk image starting at bit `pos`
+  uint32_t* buf;
+  uint64_t acc = 0;
+  int nb, w;
+  __device__ __forceinline__ BitWriter(uint32_t* b, uint32_t pos) : buf(b), nb(pos & 31), w(pos >> 5) {}
+  __device__ __forceinline__ void put(Code c) {
+    acc |= (uint64_t)c.bits << nb;
+    nb += c.n;
+    if (nb >= 32) {
+      atomicOr(&buf[w++], (uint32_t)acc);
+      acc >>= 32;
+      nb -= 32;
+    }
+  }
+  __device__ __forceinline__ void flush() {
+    if (nb > 0 && (uint32_t)acc) atomicOr(&buf[w], (uint32_t)acc);
+  }
+};
+
+// tokens of the zero run of `run_bytes` bytes that START inside [lo, hi) (byte offsets from the run's start, hi - lo <= 16):
+// offset 0: literal 0; offsets 1 + 258 k: matches of 258; then the remainder as one match (>= 3) or one / two literals
+template <class Sink>
+__device__ __forceinline__ void run_tokens(Sink& s, int run_bytes, int lo, int hi) {
+  if (lo == 0) s.put(lit_code(0));
+  const int m = run_bytes - 1, nfull = m / 258, r = m - nfull * 258;
+  const int k0 = lo <= 1 ? 0 : (lo + 256) / 258;
+  if (k0 < nfull && 1 + 258 * k0 < hi) s.put(match_code(258));
+  const int q = 1 + 258 * nfull;
+  if (r >= 3) {
+    if (q >= lo && q < hi) s.put(match_code(r));
+  } else {
+    for (int j = 0; j < r; ++j)
+      if (q + j >= lo && q + j < hi) s.put(lit_code(0));
+  }
+}
+
+// the tokens that start inside this thread's words [i0, i0 + nv); zb / za = zero words right before / behind them
+template <class Sink>
+__device__ __forceinline__ void thread_tokens(Sink& s, const uint32_t (&w)[4], int i0, int nv, int zb, int za) {
+  int i = 0;
+  while (i < nv) {
+    if (w[i]) {
+      const uint32_t v = w[i];
+      s.put(lit_code(v & 255u));
+      s.put(lit_code((v >> 8) & 255u));
+      s.put(lit_code((v >> 16) & 255u));
+      s.put(lit_code(v >> 24));
+      ++i;
+    } else {
+      const int a = i;
+      while (i < nv && w[i] == 0) ++i;
+      const int before = a == 0 ? zb : 0, behind = i == nv ? za : 0;
+      run_tokens(s, 4 * (before + (i - a) + behind), 4 * before, 4 * (before + (i - a)));
+    }
+  }
+  (void)i0;
+}
+
+__global__ void __launch_bounds__(THREADS)
+k_deflate_chunks(const slimb200_deflate_member* __restrict__ members, int n_members, const uint32_t* __restrict__ tab,
+                 uint32_t* __restrict__ scratch, uint32_t* __restrict__ chunk_bytes, uint32_t* __restrict__ member_out) {
+  __shared__ uint32_t buf[SLOT_WORDS];
+  __shared__ uint32_t T[256];
+  __shared__ int s_last[WARPS], s_first[WARPS];
+  __shared__ uint32_t s_bits[WARPS], s_crc[WARPS];
+  __shared__ int s_member;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint32_t chunk = blockIdx.x;
+  if (tid == 0) {  // the member this chunk belongs to: last one with first_chunk <= chunk
+    int lo = 0, hi = n_members - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (members[mid].first_chunk <= chunk) lo = mid; else hi = mid - 1;
+    }
+    s_member = lo;
+  }
+  for (int i = tid; i < SLOT_WORDS; i += THREADS) buf[i] = 0;
+  if (tid < 256) T[tid] = tab[TAB_T + tid];
+  __syncthreads();
+  const int mi = s_member;
+  const slimb200_deflate_member m = members[mi];
+  const uint32_t c = chunk - m.first_chunk, n_chunks = (m.n_words + CHUNK_WORDS - 1) / CHUNK_WORDS;
+  const uint32_t w0 = c * CHUNK_WORDS;
+  const int nw = (int)min((uint32_t)CHUNK_WORDS, m.n_words - w0);
+  const int i0 = 4 * tid, nv = max(0, min(4, nw - i0));
+
+  // ---- this thread's 4 words
+  uint32_t w[4] = {0u, 0u, 0u, 0u};
+  const uint32_t* src = static_cast<const uint32_t*>(m.src);
+  if (nv > 0) {
+    const uint32_t g = w0 + i0;
+    if (m.cell_stride == m.words_per_cell && nv == 4 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + g));
+      w[0] = v.x, w[1] = v.y, w[2] = v.z, w[3] = v.w;
+    } else {
+      const uint32_t wpc = (uint32_t)m.words_per_cell;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (k < nv) {
+          const uint32_t cell = (g + k) / wpc, within = (g + k) - cell * wpc;
+          w[k] = __ldg(src + (size_t)cell * (size_t)m.cell_stride + within);
+        }
+    }
+  }
+
+  // ---- zero words right before / behind my words: prefix max of the last non-zero word, suffix min of the first one
+  int last = -1, first = nw;
+  uint32_t crc = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (k < nv && w[k]) {
+      last = i0 + k;
+      if (first == nw) first = i0 + k;
+    }
+  int pl = last, sf = first;  // inclusive scans inside the warp
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int a = __shfl_up_sync(0xffffffffu, pl, d), b = __shfl_down_sync(0xffffffffu, sf, d);
+    if (lane >= d) pl = max(pl, a);
+    if (lane + d < 32) sf = min(sf, b);
+  }
+  if (lane == 31) s_last[wid] = pl;
+  if (lane == 0) s_first[wid] = sf;
+  int ex_l = __shfl_up_sync(0xffffffffu, pl, 1), ex_f = __shfl_down_sync(0xffffffffu, sf, 1);
+  if (lane == 0) ex_l = -1;
+  if (lane == 31) ex_f = nw;
+  __syncthreads();
+  for (int k = 0; k < wid; ++k) ex_l = max(ex_l, s_last[k]);
+  for (int k = wid + 1; k < WARPS; ++k) ex_f = min(ex_f, s_first[k]);
+  const int zb = i0 - 1 - ex_l, za = ex_f - (i0 + nv);
+
+  // ---- pass 1: bits of my tokens -> bit position
+  BitCounter cnt;
+  if (nv > 0) thread_tokens(cnt, w, i0, nv, zb, za);
+  uint32_t inc = cnt.n;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t a = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += a;
+  }
+  if (lane == 31) s_bits[wid] = inc;
+
+  // ---- CRC remainder of my words, moved to the end of the chunk
+  if (last >= 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k < nv) {
+        crc ^= w[k];
+        crc = T[crc & 255u] ^ (crc >> 8);
+        crc = T[crc & 255u] ^ (crc >> 8);
+        crc = T[crc & 255u] ^ (crc >> 8);
+        crc = T[crc & 255u] ^ (crc >> 8);
+      }
+    if (crc) crc = gf_mul(__ldg(tab + TAB_XPW + (nw - (i0 + nv))), crc);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) crc ^= __shfl_xor_sync(0xffffffffu, crc, d);
+  if (lane == 0) s_crc[wid] = crc;
+  __syncthreads();
+  uint32_t pos = 3 + inc - cnt.n, total = 3;
+  for (int k = 0; k < WARPS; ++k) {
+    if (k < wid) pos += s_bits[k];
+    total += s_bits[k];
+  }
+
+  // ---- pass 2: write the codes
+  if (cnt.n) {
+    BitWriter bw(buf, pos);
+    thread_tokens(bw, w, i0, nv, zb, za);
+    bw.flush();
+  }
+  // block header (BFINAL 0, BTYPE 01 -> bits 0,1,0), end-of-block (7 zero bits), stored-block header (BFINAL of the member's
+  // last chunk, BTYPE 00), zero padding to the byte boundary, LEN = 0x0000, NLEN = 0xFFFF
+  const uint32_t nbytes = (total + 10 + 7) >> 3;
+  if (tid == 0) {
+    atomicOr(&buf[0], 2u);
+    if (c == n_chunks - 1) atomicOr(&buf[(total + 7) >> 5], 1u << ((total + 7) & 31));
+    atomicOr(&buf[(nbytes + 2) >> 2], 0xFFu << (8 * ((nbytes + 2) & 3)));
+    atomicOr(&buf[(nbytes + 3) >> 2], 0xFFu << (8 * ((nbytes + 3) & 3)));
+    chunk_bytes[chunk] = nbytes + 4;
+    uint32_t r = 0;
+    for (int k = 0; k < WARPS; ++k) r ^= s_crc[k];
+    if (r) {
+      if (c != n_chunks - 1) {  // bits behind this chunk: (n_chunks - 2 - c) full chunks + the member's last chunk
+        const uint32_t last_words = m.n_words - (n_chunks - 1) * CHUNK_WORDS;
+        r = gf_mul(__ldg(tab + TAB_XPC + (n_chunks - 2 - c)), r);
+        r = gf_mul(__ldg(tab + TAB_XPW + last_words), r);
+      }
+      atomicXor(&member_out[4 * mi + 2], r);
+    }
+  }
+  __syncthreads();
+  uint32_t* dst = scratch + (size_t)chunk * SLOT_WORDS;
+  const int nwords_out = (int)((nbytes + 4 + 3) >> 2) + 1;  // (+1: the gather's funnel shift reads one word ahead)
+  for (int i = tid; i < nwords_out && i < SLOT_WORDS; i += THREADS) dst[i] = buf[i];
+}
+
+// chunk sizes -> chunk offsets, member {offset, bytes, (crc), chunks}, total; one CTA
+__global__ void __launch_bounds__(1024)
+k_deflate_scan(const slimb200_deflate_member* __restrict__ members, int n_members, const uint32_t* __restrict__ chunk_bytes,
+               uint32_t total_chunks, uint32_t* __restrict__ chunk_off, uint32_t* __restrict__ member_out) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_total;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint32_t per = (total_chunks + 1023u) / 1024u;
+  const uint32_t b = min(total_chunks, (uint32_t)tid * per), e = min(total_chunks, b + per);
+  uint32_t sum = 0;
+  for (uint32_t i = b; i < e; ++i) sum += chunk_bytes[i];
+  uint32_t inc = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t a = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += a;
+  }
+  if (lane == 31) s_warp[wid] = inc;
+  __syncthreads();
+  uint32_t off = inc - sum;
+  for (int k = 0; k < wid; ++k) off += s_warp[k];
+  if (tid == 1023) s_total = off + sum;
+  for (uint32_t i = b; i < e; ++i) {
+    chunk_off[i] = off;
+    off += chunk_bytes[i];
+  }
+  __syncthreads();
+  const uint32_t total = s_total;
+  for (int mi = tid; mi < n_members; mi += 1024) {
+    const uint32_t f = members[mi].first_chunk;
+    const uint32_t nxt = mi + 1 < n_members ? chunk_off[members[mi + 1].first_chunk] : total;
+    member_out[4 * mi + 0] = chunk_off[f];
+    member_out[4 * mi + 1] = nxt - chunk_off[f];
+    member_out[4 * mi + 3] = (members[mi].n_words + CHUNK_WORDS - 1) / CHUNK_WORDS;
+  }
+  if (tid == 0) member_out[4 * n_members + 0] = total;
+}
+
+// pack the chunks: aligned 4-byte stores, source words funnel-shifted to the destination's alignment
+__global__ void __launch_bounds__(256)
+k_deflate_gather(const uint32_t* __restrict__ scratch, const uint32_t* __restrict__ chunk_bytes, const uint32_t* __restrict__ chunk_off,
+                 uint8_t* __restrict__ out, size_t out_capacity, uint32_t* __restrict__ overflow) {
+  const uint32_t chunk = blockIdx.x, n = chunk_bytes[chunk], off = chunk_off[chunk];
+  if ((size_t)off + n > out_capacity) {
+    if (threadIdx.x == 0) *overflow = 1u;
+    return;
+  }
+  const uint32_t* src = scratch + (size_t)chunk * SLOT_WORDS;
+  const uint8_t* srcb = reinterpret_cast<const uint8_t*>(src);
+  uint8_t* dst = out + off;
+  const uint32_t head = min(n, (uint32_t)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3));
+  const uint32_t nwords = (n - head) >> 2, tail0 = head + 4 * nwords;
+  if (threadIdx.x < head) dst[threadIdx.x] = srcb[threadIdx.x];
+  if (threadIdx.x >= 32 && threadIdx.x - 32 < n - tail0) dst[tail0 + threadIdx.x - 32] = srcb[tail0 + threadIdx.x - 32];
+  uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
+  const uint32_t sh = 8 * head;  // dst word j = source bytes head + 4j .. head + 4j + 3
+  for (uint32_t j = threadIdx.x; j < nwords; j += 256) dw[j] = __funnelshift_r(src[j], src[j + 1], sh);
+}
+}  // namespace
+
+extern "C" int slimb200_deflate_plan(slimb200_deflate_member* members, int32_t n_members, int64_t* total_chunks,
+                                     size_t* workspace_bytes, size_t* out_bound) {
+  if (!members || n_members < 1 || !total_chunks || !workspace_bytes || !out_bound) return SLIMB200_E_INVALID;
+  uint64_t chunks = 0;
+  for (int i = 0; i < n_members; ++i) {
+    slimb200_deflate_member& m = members[i];
+    if (!m.src || m.n_words == 0 || m.words_per_cell < 1 || m.cell_stride < m.words_per_cell) return SLIMB200_E_INVALID;
+    if ((reinterpret_cast<uintptr_t>(m.src) & 3) != 0) return SLIMB200_E_ALIGNMENT;
+    const uint64_t n = ((uint64_t)m.n_words + CHUNK_WORDS - 1) / CHUNK_WORDS;
+    if (n > SLIMB200_DEFLATE_MAX_CHUNKS) return SLIMB200_E_UNSUPPORTED;
+    m.first_chunk = (uint32_t)chunks;
+    chunks += n;
+  }
+  if (chunks * (uint64_t)SLOT_BYTES > 0xFFFFFFFFull) return SLIMB200_E_UNSUPPORTED;  // 32-bit stream offsets
+  *total_chunks = (int64_t)chunks;
+  WorkspaceCarver ws(nullptr);
+  ws.take<uint32_t>(chunks * SLOT_WORDS + 1);
+  ws.take<uint32_t>(chunks);
+  ws.take<uint32_t>(chunks);
+  *workspace_bytes = ws.used();
+  *out_bound = slimb200_align_up(chunks * (size_t)(SLOT_BYTES - 8), 256);
+  return SLIMB200_OK;
+}
+
+extern "C" int slimb200_deflate_init(void* tables, void* stream) {
+  if (!tables) return SLIMB200_E_INVALID;
+  if ((reinterpret_cast<uintptr_t>(tables) & 3) != 0) return SLIMB200_E_ALIGNMENT;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  SLIMB200_LAUNCH(SLIMB200_K_DEFLATE_TABLES, s,
+                  (k_deflate_tables<<<(TAB_WORDS + 255) / 256, 256, 0, s>>>(static_cast<uint32_t*>(tables))));
+  return SLIMB200_OK;
+}
+
+extern "C" int slimb200_deflate_encode(const slimb200_deflate_member* members_dev, int32_t n_members, int64_t total_chunks,
+                                       const void* tables, void* workspace, size_t workspace_bytes, void* out,
+                                       size_t out_capacity, uint32_t* member_out, void* stream) {
+  if (!members_dev || n_members < 1 || total_chunks < n_members || !tables || !workspace || !out || !member_out)
+    return SLIMB200_E_INVALID;
+  if (total_chunks * (int64_t)SLOT_BYTES > 0xFFFFFFFFll) return SLIMB200_E_UNSUPPORTED;
+  WorkspaceCarver ws(workspace);
+  uint32_t* scratch = ws.take<uint32_t>((size_t)total_chunks * SLOT_WORDS + 1);
+  uint32_t* chunk_bytes = ws.take<uint32_t>((size_t)total_chunks);
+  uint32_t* chunk_off = ws.take<uint32_t>((size_t)total_chunks);
+  if (ws.used() > workspace_bytes) return SLIMB200_E_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  SLIMB200_CUDA_TRY(cudaMemsetAsync(member_out, 0, sizeof(uint32_t) * 4 * ((size_t)n_members + 1), s));
+  SLIMB200_LAUNCH(SLIMB200_K_DEFLATE_CHUNKS, s,
+                  (k_deflate_chunks<<<(unsigned)total_chunks, THREADS, 0, s>>>(members_dev, n_members, static_cast<const uint32_t*>(tables),
+                                                                               scratch, chunk_bytes, member_out)));
+  SLIMB200_LAUNCH(SLIMB200_K_DEFLATE_SCAN, s,
+                  (k_deflate_scan<<<1, 1024, 0, s>>>(members_dev, n_members, chunk_bytes, (uint32_t)total_chunks, chunk_off, member_out)));
+  SLIMB200_LAUNCH(SLIMB200_K_DEFLATE_GATHER, s,
+                  (k_deflate_gather<<<(unsigned)total_chunks, 256, 0, s>>>(scratch, chunk_bytes, chunk_off, static_cast<uint8_t*>(out),
+                                                                           out_capacity, member_out + 4 * (size_t)n_members + 1)));
+  return SLIMB200_OK;
+}

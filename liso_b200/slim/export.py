@@ -72,13 +72,15 @@ class AsyncNpzWriter:
     KEYS = ("bev_raw_flow_t0_t1", "bev_raw_flow_t1_t0", "bev_dynamicness_t0_t1", "bev_dynamicness_t1_t0")
 
     def __init__(self, target_dir: str, bev_range_m, workers: Optional[int] = None, max_pending: int = 64,
-                 skip_existing: bool = False, compressed: bool = True):
+                 skip_existing: bool = False, compressed: bool = True, unlink_after_write: bool = False):
         from concurrent.futures import ThreadPoolExecutor
 
         self.target_dir = target_dir
         self.bev_range_m = np.asarray(bev_range_m)
         self.skip_existing = skip_existing
         self.compressed = compressed
+        self.unlink_after_write = unlink_after_write  # benchmarks: bound the disk use (the write itself still happens)
+        self.bytes_written = 0
         self.max_pending = max_pending
         self.pool = ThreadPoolExecutor(max_workers=workers or max(1, (os.cpu_count() or 2) - 1))
         self.pending: List = []
@@ -93,6 +95,12 @@ class AsyncNpzWriter:
         tmp = path + ".tmp.npz"
         (np.savez_compressed if self.compressed else np.savez)(tmp, **arrays)
         os.replace(tmp, path)  # never leave a truncated file behind
+        return self._written(path)
+
+    def _written(self, path: str) -> str:
+        self.bytes_written += os.path.getsize(path)  # (racy += across workers is fine for a statistic)
+        if self.unlink_after_write:
+            os.unlink(path)
         return path
 
     def submit(self, sample_id: str, *args) -> bool:
@@ -117,11 +125,44 @@ class AsyncNpzWriter:
 
     def submit_batch(self, sample_ids, host_tensors, static_threshold) -> int:
         """``host_tensors`` as handed to ``ExportPipeline``'s consume callback: batched flows (B,H,W,2) of all directions,
-        then the dynamicness maps (B,H,W) of all directions (2 + 2 tensors for a pair, 6 + 6 for a triple)."""
+        then the dynamicness maps (B,H,W) of all directions (2 + 2 tensors for a pair, 6 + 6 for a triple) -- or, from a
+        pipeline with ``compress=True``, the :class:`~liso_b200.slim.npz_stream.EncodedBatch` of the same maps."""
         n = 0
+        if hasattr(host_tensors, "member"):
+            for b, sid in enumerate(sample_ids):
+                n += bool(self.submit_encoded(sid, host_tensors, b, static_threshold))
+            return n
         for b, sid in enumerate(sample_ids):
             n += bool(self.submit(sid, *[t[b] for t in host_tensors], static_threshold))
         return n
+
+    def _write_blob(self, path: str, members) -> str:
+        from .npz_stream import build_npz
+
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        tmp = path + ".tmp.npz"
+        with open(tmp, "wb") as f:
+            f.write(build_npz(members))
+        os.replace(tmp, path)
+        return self._written(path)
+
+    def submit_encoded(self, sample_id: str, encoded, b: int, static_threshold) -> bool:
+        """Sample ``b`` of a batch whose maps the GPU has already deflated (``DeflateEncoder``): the worker thread only
+        frames the streams as zip members -- no zlib pass over the maps (``experiment.py:459-471`` spends its time there)."""
+        path = self.target_file(sample_id)
+        if self.skip_existing and os.path.exists(path):
+            return False
+        keys = export_keys(len(encoded.shapes) // 2)
+        members = [("static_threshold", np.array(float(static_threshold), dtype=np.float32))]
+        for v, k in enumerate(keys):
+            shape, stream, r = encoded.member(v, b)  # (copies the bytes out of the pinned download buffer)
+            members.append((k, shape, np.float32, stream, r))
+        members.append(("bev_range_m", self.bev_range_m))
+        while len(self.pending) >= self.max_pending:
+            self.pending.pop(0).result()
+            self.written += 1
+        self.pending.append(self.pool.submit(self._write_blob, path, members))
+        return True
 
     def close(self) -> int:
         for f in self.pending:
@@ -183,10 +224,16 @@ class ExportPipeline:
 
     KEYS = ("pcl_full_no_ground_ta", "pcl_ta")
 
-    def __init__(self, model, device, amp_ctx=None, depth: int = 3):
+    def __init__(self, model, device, amp_ctx=None, depth: int = 3, compress: bool = False):
         """``depth``: batches the host may run ahead of the results it has consumed (number of upload / download
-        slots); >= 2.  A deeper pipeline absorbs host-side hiccups (the launch thread is the critical resource)."""
+        slots); >= 2.  A deeper pipeline absorbs host-side hiccups (the launch thread is the critical resource).
+        ``compress``: the exported maps are DEFLATE-compressed on the GPU right behind the forward pass (SURVEY 8f.3,
+        ``npz_stream.DeflateEncoder``) and only the compressed streams are downloaded; ``consume`` then receives an
+        ``EncodedBatch`` (views in the order flows of all directions, dynamicness of all directions)."""
         self.model, self.device = model, device
+        self.compress = bool(compress)
+        self.encoder = None
+        self.downloaded_bytes = 0
         if hasattr(model, "outputs_alias_static_buffers"):
             model.outputs_alias_static_buffers = True  # this loop takes its own packed copies of what it exports (see run)
         self.copy_stream = torch.cuda.Stream(device=device)
@@ -243,15 +290,30 @@ class ExportPipeline:
             cur.wait_event(up_evt)
             ctx = self.amp_ctx() if self.amp_ctx else contextlib.nullcontext()
             with torch.no_grad(), ctx:
+                if any("pcl_ta" not in s for s in staged):  # raw scans: decoder inputs prepared on the device (8f.4)
+                    from ..datasets import preprocess_scans
+
+                    staged = tuple(s if "pcl_ta" in s else preprocess_scans(s["pcl_full_w_ground_ta"], self.model.cfg) for s in staged)
                 if len(staged) == 3:
                     by_dir = self.model.forward_triple(*staged)
                     mods = [by_dir[d][-1].modified_network_output for d in DIRECTIONS_TRIPLE]
                 else:
                     pf, pb = self.model(staged[0], staged[1], None)
                     mods = [pf[-1].modified_network_output, pb[-1].modified_network_output]
-            # packed copies: the predictions may be views of the CUDA graph's static outputs, which the next forward
-            # overwrites while this batch is still being downloaded
-            outs = [m.static_flow.contiguous() for m in mods] + [m.dynamicness.contiguous() for m in mods]
+            if self.compress:
+                # the encoder reads the (strided) maps where the decoder left them, in stream order before the next forward
+                # overwrites the graph's static outputs; the member table follows on the same stream (a few hundred bytes)
+                if self.encoder is None:
+                    from .npz_stream import DeflateEncoder
+
+                    self.encoder = DeflateEncoder(self.device, slots=D)
+                self.encoder.encode([m.static_flow for m in mods] + [m.dynamicness for m in mods], slot=idx % D)
+                self.encoder.start_download(idx % D)
+                outs = None
+            else:
+                # packed copies: the predictions may be views of the CUDA graph's static outputs, which the next forward
+                # overwrites while this batch is still being downloaded
+                outs = [m.static_flow.contiguous() for m in mods] + [m.dynamicness.contiguous() for m in mods]
             done = torch.cuda.Event()
             done.record(cur)
             done_evt[idx % D] = done
@@ -267,42 +329,63 @@ class ExportPipeline:
                     up_evt.record(self.copy_stream)
                 else:
                     staged = None
-                self.copy_stream.wait_event(done)
                 slot = idx % D
-                if self._out_bufs[slot] is None or any(b.shape != o.shape for b, o in zip(self._out_bufs[slot], outs)):
-                    self._out_bufs[slot] = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
-                for dst, src in zip(self._out_bufs[slot], outs):
-                    src.record_stream(self.copy_stream)
-                    dst.copy_(src, non_blocking=True)
-                dl_evt = torch.cuda.Event()
-                dl_evt.record(self.copy_stream)
-            downloads.append((idx, self._out_bufs[slot], dl_evt))
+                if not self.compress:
+                    self.copy_stream.wait_event(done)
+                    if self._out_bufs[slot] is None or any(b.shape != o.shape for b, o in zip(self._out_bufs[slot], outs)):
+                        self._out_bufs[slot] = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
+                    for dst, src in zip(self._out_bufs[slot], outs):
+                        src.record_stream(self.copy_stream)
+                        dst.copy_(src, non_blocking=True)
+                    dl_evt = torch.cuda.Event()
+                    dl_evt.record(self.copy_stream)
+            if self.compress:
+                # the previous batch has left the GPU by now (or is about to): its sizes are known -> download exactly its
+                # compressed bytes on the copy stream, under the compute of the batch just enqueued
+                if downloads and not downloads[-1][2]["begun"]:
+                    self._begin(downloads[-1])
+                downloads.append((idx, slot, {"begun": False}))
+            else:
+                downloads.append((idx, self._out_bufs[slot], dl_evt))
             # hand over the oldest batch once `depth - 1` newer ones are in flight (its pinned buffers come up for reuse)
             while len(downloads) > D - 1:
-                j, host, evt = downloads.pop(0)
-                evt.synchronize()
-                if consume is not None:
-                    consume(j, host)
-                n_done += 1
+                n_done += self._hand_over(downloads.pop(0), consume)
             idx += 1
-        for j, host, evt in downloads:
-            evt.synchronize()
-            if consume is not None:
-                consume(j, host)
-            n_done += 1
+        for d in downloads:
+            n_done += self._hand_over(d, consume)
         return n_done
+
+    def _begin(self, d):
+        self.downloaded_bytes += self.encoder.fetch_begin(d[1], self.copy_stream)
+        d[2]["begun"] = True
+
+    def _hand_over(self, d, consume) -> int:
+        if self.compress:
+            if not d[2]["begun"]:
+                self._begin(d)
+            host = self.encoder.fetch_end(d[1])
+        else:
+            d[2].synchronize()
+            host = d[1]
+        if consume is not None:
+            consume(d[0], host)
+        return 1
 
 
 def collate_pairs(pairs):
     """Batch un-batched pairs the way the reference's collate function does (``torch_dataset_commons.py:380-401``): the
     network clouds stay a list; ``pcl_ta`` is padded to the longest cloud with NaN points, ``-1`` pillar coordinates
-    and a validity mask.  ``pairs``: list of ``(sample_t0, sample_t1)`` with ``pcl_full_no_ground_ta`` (N, C) and
+    and a validity mask.  Samples that are raw scans only (``{"pcl_full_w_ground_ta", "raw_scan": True}``) are passed on
+    as a list of scans.  ``pairs``: list of ``(sample_t0, sample_t1)`` with ``pcl_full_no_ground_ta`` (N, C) and
     ``pcl_ta = {"pcl" (N', C), "pillar_coors" (N', 2)}`` per sample (host tensors)."""
     from torch.nn.utils.rnn import pad_sequence
 
     out = []
     for t in range(len(pairs[0])):
         samples = [p[t] for p in pairs]
+        if "pcl_ta" not in samples[0]:  # raw scans: the device prepares the decoder inputs (ExportPipeline, SURVEY 8f.4)
+            out.append({"pcl_full_w_ground_ta": [s["pcl_full_w_ground_ta"] for s in samples], "raw_scan": True})
+            continue
         pcl = pad_sequence([s["pcl_ta"]["pcl"] for s in samples], batch_first=True, padding_value=float("nan"))
         coors = pad_sequence([s["pcl_ta"]["pillar_coors"] for s in samples], batch_first=True, padding_value=-1)
         batch = {"pcl_full_no_ground_ta": [s["pcl_full_no_ground_ta"] for s in samples],
@@ -311,6 +394,33 @@ def collate_pairs(pairs):
             batch["raw_scan"] = samples[0]["raw_scan"]
         out.append(batch)
     return tuple(out)
+
+
+def _prefetched(it, depth: int):
+    """Run the iterator ``it`` on a background thread, ``depth`` items ahead (the dataset access, collation and pinning of
+    the next batches then overlap the launch thread, like the workers of the reference's DataLoader)."""
+    import queue
+    import threading
+
+    q: "queue.Queue" = queue.Queue(maxsize=depth)
+    end = object()
+
+    def work():
+        try:
+            for item in it:
+                q.put(item)
+            q.put(end)
+        except BaseException as e:  # hand the error to the consumer instead of dying silently
+            q.put(e)
+
+    threading.Thread(target=work, daemon=True).start()
+    while True:
+        item = q.get()
+        if item is end:
+            return
+        if isinstance(item, BaseException):
+            raise item
+        yield item
 
 
 def _pin(sample):
@@ -323,7 +433,8 @@ def _pin(sample):
 
 def run_flow_export(model, dataset, target_dir: str, bev_range_m, *, world_size: int = 1, worker_id: int = 0,
                     batch_size: int = 8, device=None, skip_existing: bool = False, writer_workers: Optional[int] = None,
-                    pipeline_factory=None) -> Dict[str, float]:
+                    pipeline_factory=None, compress_on_gpu: bool = False, loader_workers: int = 0,
+                    unlink_after_write: bool = False) -> Dict[str, float]:
     """The flow export of ``liso/slim/experiment.py:225-361,363-471`` for the t0 -> t1 pairs of one worker: this rank's
     share of the pairs (modulo rule), batched, through the double-buffered :class:`ExportPipeline`, written by
     :class:`AsyncNpzWriter` in the reference's ``.npz`` schema under ``target_dir/<sample_id>.npz``; one collective at
@@ -332,19 +443,28 @@ def run_flow_export(model, dataset, target_dir: str, bev_range_m, *, world_size:
     ``dataset``: ``len()`` and ``dataset[i] -> (sample_id, sample_t0, sample_t1)`` with un-batched host tensors (see
     :func:`collate_pairs`), or ``(sample_id, t0, t1, t2)`` for the KITTI / nuScenes export: then t0 -> t1, t0 -> t2 and
     t1 -> t2 are computed in one pass per batch (every frame encoded once) and the file holds all 12 maps
-    (``experiment.py:404-456``).  Returns ``{"pairs", "files", "skipped", "elapsed_s_max"}`` over all ranks ("pairs"
+    (``experiment.py:404-456``).  ``compress_on_gpu``: the maps are deflated on the device and the writer threads only frame
+    zip members (same files for ``np.load``).  ``loader_workers``: > 0 moves dataset access, collation and
+    pinning to a background thread (> 1: with that many threads fetching samples), like DataLoader workers.  Returns ``{"pairs", "files", "skipped", "elapsed_s_max"}`` over all ranks ("pairs"
     counts samples)."""
     import time
 
-    writer = AsyncNpzWriter(target_dir, bev_range_m, workers=writer_workers, skip_existing=skip_existing)
+    writer = AsyncNpzWriter(target_dir, bev_range_m, workers=writer_workers, skip_existing=skip_existing,
+                            unlink_after_write=unlink_after_write)
     mine = shard_indices(len(dataset), world_size, worker_id)
     ids_of_batch: List[List[str]] = []
     skipped = 0
 
+    fetch_pool = None
+    if loader_workers > 1:
+        from concurrent.futures import ThreadPoolExecutor
+
+        fetch_pool = ThreadPoolExecutor(loader_workers)
+
     def batches():
         nonlocal skipped
         for chunk in iterate_batches(mine, batch_size):
-            items = [dataset[i] for i in chunk]
+            items = list(fetch_pool.map(dataset.__getitem__, chunk)) if fetch_pool else [dataset[i] for i in chunk]
             if skip_existing:  # (experiment.py:380-382: an existing target file skips the forward as well)
                 keep = [it for it in items if not os.path.exists(writer.target_file(it[0]))]
                 skipped += len(items) - len(keep)
@@ -361,10 +481,13 @@ def run_flow_export(model, dataset, target_dir: str, bev_range_m, *, world_size:
         counts["pairs"] += len(ids_of_batch[j])
         counts["files"] += writer.submit_batch(ids_of_batch[j], host, thr)
 
-    pipeline = (pipeline_factory or ExportPipeline)(model, device)
+    pipeline = (pipeline_factory(model, device) if pipeline_factory else ExportPipeline(model, device, compress=compress_on_gpu))
     t0 = time.perf_counter()
-    pipeline.run(batches(), consume)
+    pipeline.run(_prefetched(batches(), 3) if loader_workers > 0 else batches(), consume)
     writer.close()
+    if fetch_pool:
+        fetch_pool.shutdown()
     local = {"pairs": float(counts["pairs"]), "files": float(counts["files"]), "skipped": float(skipped),
+             "file_bytes": float(writer.bytes_written), "d2h_bytes": float(getattr(pipeline, "downloaded_bytes", 0)),
              "elapsed_s_max": time.perf_counter() - t0}
     return reduce_counters(local, device if device is not None and torch.device(device).type == "cuda" else None)

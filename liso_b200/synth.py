@@ -258,12 +258,31 @@ class SyntheticExportDataset:
     of ``pool`` cast scenes and made distinct by a per-sample yaw rotation + shift of the whole scene (every frame of a
     sample gets the same rigid motion: the relative motion between the frames -- what the network estimates -- is kept,
     every pillar map changes).  ``dataset[i] -> (sample_id, sample_t0, sample_t1[, sample_t2])`` with un-batched host
-    tensors, deterministic in ``i``."""
+    tensors, deterministic in ``i``.
 
-    def __init__(self, workload: Dict[str, Any], n_samples: int, frames: int = 2, pool: int = 16, seed0: int = 5000):
+    ``raw=True``: the samples are RAW scans only (``{"pcl_full_w_ground_ta", "raw_scan": True}``): ground rule, height
+    filter, pillar coordinates and compaction are left to the device (``liso_b200.datasets.preprocess_scans``, SURVEY
+    8f.4), as ``ExportPipeline`` does for such samples -- the host then only moves bytes."""
+
+    def __init__(self, workload: Dict[str, Any], n_samples: int, frames: int = 2, pool: int = 16, seed0: int = 5000,
+                 raw: bool = False):
         assert frames in (2, 3)
         self.workload, self.n, self.frames, self.pool, self.seed0 = workload, int(n_samples), frames, max(1, int(pool)), seed0
+        self.raw = bool(raw)
         self._cache: Dict[int, tuple] = {}
+
+    def prepare(self, workers: int = 1):
+        """Cast the pool's scenes now (optionally on several threads) instead of lazily inside the export loop."""
+        ks = [k for k in range(min(self.pool, self.n)) if k not in self._cache]
+        if workers > 1 and len(ks) > 1:
+            from concurrent.futures import ThreadPoolExecutor
+
+            with ThreadPoolExecutor(workers) as ex:
+                list(ex.map(self._scene_frames, ks))
+        else:
+            for k in ks:
+                self._scene_frames(k)
+        return self
 
     def __len__(self) -> int:
         return self.n
@@ -289,5 +308,10 @@ class SyntheticExportDataset:
             q = pc.copy()
             q[:, 0] = c * pc[:, 0] - s_ * pc[:, 1] + np.float32(shift[0])
             q[:, 1] = s_ * pc[:, 0] + c * pc[:, 1] + np.float32(shift[1])
+            if self.raw:
+                import torch
+
+                samples.append({"pcl_full_w_ground_ta": torch.from_numpy(q), "raw_scan": True})
+                continue
             samples.append(_sample_of(q, bev, grid))
         return ("%06d" % i,) + tuple(samples)

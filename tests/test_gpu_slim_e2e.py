@@ -293,3 +293,53 @@ def test_triple_export_pass_equals_three_forwards(cuda, tmp_path):
     assert len(z.files) == 14
     assert np.array_equal(z["bev_raw_flow_t2_t0"], tri["t2_t0"][0][1].cpu().numpy())
     assert np.array_equal(z["bev_dynamicness_t1_t2"], tri["t1_t2"][1][1].cpu().numpy())
+
+
+def test_gpu_compressed_export_writes_the_same_files(cuda, tmp_path):
+    """run_flow_export(compress_on_gpu=True) -- maps deflated on the device, zip members framed on the host --
+    writes files np.load reads exactly like the np.savez_compressed ones (pair and triple schema), several batches deep so
+    that every download slot is reused."""
+    from liso_b200.slim import export
+    from liso_b200.synth import SyntheticExportDataset
+
+    cfg = make_cfg("T")
+    model, _ = _model(cfg, cuda, decode_iterations="last", static_aggregation=False)
+    for frames, n_keys in ((2, 6), (3, 14)):
+        ds = SyntheticExportDataset(WORKLOADS["T"], 9, frames=frames, pool=3)
+        d_ref, d_gpu = os.path.join(str(tmp_path), "ref%d" % frames), os.path.join(str(tmp_path), "gpu%d" % frames)
+        a = export.run_flow_export(model, ds, d_ref, cfg.data.bev_range_m, batch_size=2, device=cuda, writer_workers=2)
+        b = export.run_flow_export(model, ds, d_gpu, cfg.data.bev_range_m, batch_size=2, device=cuda, writer_workers=2,
+                                   compress_on_gpu=True)
+        assert a["files"] == b["files"] == 9
+        for i in range(9):
+            zr, zg = np.load(os.path.join(d_ref, "%06d.npz" % i)), np.load(os.path.join(d_gpu, "%06d.npz" % i))
+            assert sorted(zr.files) == sorted(zg.files) and len(zg.files) == n_keys
+            for k in zr.files:
+                assert zr[k].dtype == zg[k].dtype and zr[k].shape == zg[k].shape, k
+                assert np.array_equal(zr[k].view(np.uint8) if zr[k].ndim else zr[k], zg[k].view(np.uint8) if zg[k].ndim else zg[k]), (i, k)
+
+
+def test_gpu_export_from_raw_scans_with_loader_threads(cuda, tmp_path):
+    """SURVEY 8f.3 + 8f.4: the export fed with RAW scans only (the device applies the ground rule, computes the pillar map and
+    compacts the decoder inputs), dataset access on loader threads, maps deflated on the device: every file equals what
+    SLIM.forward returns for the same scans prepared by preprocess_scans."""
+    from liso_b200.datasets import preprocess_scans
+    from liso_b200.slim import export
+    from liso_b200.synth import SyntheticExportDataset
+
+    cfg = make_cfg("T")
+    model, _ = _model(cfg, cuda, decode_iterations="last", static_aggregation=False)
+    ds = SyntheticExportDataset(WORKLOADS["T"], 7, frames=2, pool=2, raw=True)
+    out = export.run_flow_export(model, ds, str(tmp_path), cfg.data.bev_range_m, batch_size=3, device=cuda, writer_workers=2,
+                                 compress_on_gpu=True, loader_workers=2)
+    assert out["pairs"] == 7 and out["files"] == 7 and out["d2h_bytes"] > 0
+    assert out["d2h_bytes"] < 0.5 * 7 * 6 * WORKLOADS["T"]["img_grid_size"][0] * WORKLOADS["T"]["img_grid_size"][1] * 4
+    for i in (0, 4, 6):
+        _, s0, s1 = ds[i]
+        with torch.no_grad():
+            pf, pb = model(preprocess_scans([s0["pcl_full_w_ground_ta"].to(cuda)], cfg),
+                           preprocess_scans([s1["pcl_full_w_ground_ta"].to(cuda)], cfg), None)
+        z = np.load(os.path.join(str(tmp_path), "%06d.npz" % i))
+        assert np.array_equal(z["bev_raw_flow_t0_t1"], pf[-1].modified_network_output.static_flow[0].cpu().numpy())
+        assert np.array_equal(z["bev_dynamicness_t1_t0"], pb[-1].modified_network_output.dynamicness[0].cpu().numpy())
+        assert float(np.abs(z["bev_raw_flow_t0_t1"]).sum()) > 0
