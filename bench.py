@@ -536,6 +536,7 @@ def main():
             run_flow_export(main.model, warm, tgt + "_warm", main.W["bev_range_m"], world_size=world, worker_id=rank, batch_size=args.batch,
                             device=dev, writer_workers=writers, compress_on_gpu=True, loader_workers=loaders, unlink_after_write=True)
             barrier()
+            cap0 = getattr(main.model.raft_network, "n_graph_captures", 0)
             res = run_flow_export(main.model, ds, tgt, main.W["bev_range_m"], world_size=world, worker_id=rank, batch_size=args.batch,
                                   device=dev, writer_workers=writers, compress_on_gpu=True, loader_workers=loaders, unlink_after_write=True)
             per_sample_pairs = 1 if frames == 2 else 3
@@ -544,7 +545,8 @@ def main():
                                  "pairs_per_s": per_sample_pairs * res["pairs"] / res["elapsed_s_max"],
                                  "file_mb_per_sample": res["file_bytes"] / max(1.0, res["files"]) / 1e6,
                                  "d2h_mb_per_sample": res["d2h_bytes"] / max(1.0, res["pairs"]) / 1e6,
-                                 "arrays_per_file": 6 if frames == 2 else 14}
+                                 "arrays_per_file": 6 if frames == 2 else 14,
+                                 "graph_captures_inside_timed_run": getattr(main.model.raft_network, "n_graph_captures", 0) - cap0}
             del ds, warm
         export_line["triple_vs_three_pair_calls"] = export_line["triples"]["pairs_per_s"] / export_line["pairs"]["pairs_per_s"]
         if world == 1 and args.export_zlib_pairs > 0:  # the round-1 writer for contrast: raw fp32 maps downloaded, zlib on host threads

@@ -226,6 +226,39 @@ def current_stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _first_cuda_device(args):
+    import torch
+
+    for a in args:
+        if torch.is_tensor(a):
+            if a.is_cuda:
+                return a.device
+        elif isinstance(a, (list, tuple)):
+            for b in a:
+                if torch.is_tensor(b) and b.is_cuda:
+                    return b.device
+    return None
+
+
+def on_device_of_args(fn):
+    """Run ``fn`` with the device of its first CUDA tensor argument current: the C entry points launch on the CURRENT
+    device's stream and keep per-device launch state, so a module living on cuda:1 must not be driven while cuda:0 is
+    current (one process may drive several GPUs; bench.py uses one process per GPU + set_device)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        import torch
+
+        dev = _first_cuda_device(args) or _first_cuda_device(tuple(kwargs.values()))
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+
+    return wrapped
+
+
 def require_cuda(*tensors) -> None:
     for t in tensors:
         if t is not None and not t.is_cuda:

@@ -37,6 +37,17 @@ struct WorkspaceCarver {
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
 
+// Per-device launch state: function attributes and SM counts belong to a DEVICE, and one process may drive several GPUs.
+// slimb200_device_info (profile.cu): the current device (< SLIMB200_MAX_DEVICES) and its cached SM count.
+#define SLIMB200_MAX_DEVICES 64
+int slimb200_device_info(int* dev, int* n_sm);
+#define SLIMB200_DEVICE(dev, n_sm)                                \
+  int dev = 0, n_sm = 0;                                          \
+  do {                                                            \
+    const int e__ = slimb200_device_info(&dev, &n_sm);            \
+    if (e__ != 0) return e__;                                     \
+  } while (0)
+
 // launch accounting / optional event timing (profile.cu)
 void slimb200_prof_pre(int id, cudaStream_t s);
 void slimb200_prof_post(int id, cudaStream_t s);

@@ -26,6 +26,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -411,6 +413,14 @@ int make_map(PFN_encodeTiled enc, CUtensorMap* map, void* base, uint64_t inner, 
   return r == CUDA_SUCCESS ? SLIMB200_OK : SLIMB200_E_DRIVER;
 }
 
+struct MapSet {
+  const void *a = nullptr, *b = nullptr, *c = nullptr;
+  int nf = 0, n_cols = 0, batch = 0, n_panels = 0;
+  bool valid = false;
+  CUtensorMap ma, mb, mc;
+};
+constexpr int MAP_CACHE_ENTRIES = 16;
+
 }  // namespace
 
 extern "C" int slimb200_corr_layout_init(int32_t batch, int32_t dim, int32_t h, int32_t w, int32_t levels,
@@ -477,15 +487,36 @@ extern "C" int slimb200_corr_build(const float* fmap1, const float* fmap2, int32
 
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return SLIMB200_E_DRIVER;
-  CUtensorMap map_a, map_b, map_c;
-  int rc;
-  if ((rc = make_map(enc, &map_a, A, DIM, nf, L->batch, DIM)) != SLIMB200_OK) return rc;
-  if ((rc = make_map(enc, &map_b, Bx, DIM, L->n_cols, L->batch, DIM)) != SLIMB200_OK) return rc;
   // output: batch * n_panels * m_tiles * 2 contiguous half-tiles of 128 lines x 128 bytes (include/slimb200.h)
   const int m_tiles = (nf + BLOCK_M - 1) / BLOCK_M;
   if (L->rows_padded != m_tiles * BLOCK_M) return SLIMB200_E_INVALID;
-  if ((rc = make_map(enc, &map_c, pyramid, 64, 128, (uint64_t)L->batch * L->n_panels * m_tiles * 2, 64)) != SLIMB200_OK)
-    return rc;
+  // the three tensor maps depend on (operand addresses, pyramid address, shape) only: the workspace and the pyramid of a
+  // caller are the same buffers call after call, so the driver encodes them once (3 cuTensorMapEncodeTiled calls otherwise)
+  CUtensorMap map_a, map_b, map_c;
+  {
+    static std::mutex mu;
+    static MapSet cache[MAP_CACHE_ENTRIES];
+    static unsigned next = 0;
+    std::lock_guard<std::mutex> lock(mu);
+    MapSet* hit = nullptr;
+    for (MapSet& e : cache)
+      if (e.valid && e.a == A && e.b == Bx && e.c == pyramid && e.nf == nf && e.n_cols == L->n_cols && e.batch == L->batch &&
+          e.n_panels == L->n_panels)
+        hit = &e;
+    if (!hit) {
+      MapSet e;
+      int rc;
+      if ((rc = make_map(enc, &e.ma, A, DIM, nf, L->batch, DIM)) != SLIMB200_OK) return rc;
+      if ((rc = make_map(enc, &e.mb, Bx, DIM, L->n_cols, L->batch, DIM)) != SLIMB200_OK) return rc;
+      if ((rc = make_map(enc, &e.mc, pyramid, 64, 128, (uint64_t)L->batch * L->n_panels * m_tiles * 2, 64)) != SLIMB200_OK)
+        return rc;
+      e.a = A, e.b = Bx, e.c = pyramid, e.nf = nf, e.n_cols = L->n_cols, e.batch = L->batch, e.n_panels = L->n_panels;
+      e.valid = true;
+      hit = &cache[next++ % MAP_CACHE_ENTRIES];
+      *hit = e;
+    }
+    map_a = hit->ma, map_b = hit->mb, map_c = hit->mc;
+  }
 
   if (fmap_layout == SLIMB200_CANVAS_NCHW) {
     dim3 g((nf + 31) / 32, DIM / 32, L->batch * 2);
@@ -506,12 +537,11 @@ extern "C" int slimb200_corr_build(const float* fmap1, const float* fmap2, int32
   shape.total_items = shape.batch * shape.m_pairs * shape.n_tiles;
   shape.scale = 1.0f / sqrtf((float)L->dim);
 
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    SLIMB200_CUDA_TRY(cudaGetDevice(&dev));
-    SLIMB200_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  SLIMB200_DEVICE(dev, n_sm);
+  static bool attr_set[SLIMB200_MAX_DEVICES] = {false};
+  if (!attr_set[dev]) {
     SLIMB200_CUDA_TRY(cudaFuncSetAttribute(k_corr_gemm_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set[dev] = true;
   }
   const int grid = shape.total_items < n_sm ? shape.total_items : n_sm;
   SLIMB200_LAUNCH(SLIMB200_K_CORR_GEMM, stream,

@@ -573,11 +573,13 @@ int launch_lookup_r3(const void* pyramid, const slimb200_corr_layout* L, const f
   using V = V3<T>;
   const int nf = L->h * L->w;
   const int smem = V::smem_bytes(L->levels, NHWC);
-  static bool attr_set = false;
-  if (!attr_set) {
+  SLIMB200_DEVICE(dev, n_sm);
+  (void)n_sm;
+  static bool attr_set[SLIMB200_MAX_DEVICES] = {false};
+  if (!attr_set[dev]) {
     SLIMB200_CUDA_TRY(cudaFuncSetAttribute(k_corr_lookup_r3<T, NHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            V::smem_bytes(SLIMB200_MAX_LEVELS, NHWC)));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   dim3 grid((nf + LK_PIX - 1) / LK_PIX, L->batch);
   SLIMB200_LAUNCH(SLIMB200_K_CORR_LOOKUP, stream,
@@ -590,11 +592,13 @@ int launch_lookup(const void* pyramid, const slimb200_corr_layout* L, const floa
   using C = Cfg<T, R>;
   const int nf = L->h * L->w;
   const int smem = C::smem_bytes(L->levels);
-  static int attr_set = 0;
-  if (attr_set < smem) {
+  SLIMB200_DEVICE(dev, n_sm);
+  (void)n_sm;
+  static bool attr_set[SLIMB200_MAX_DEVICES] = {false};
+  if (!attr_set[dev]) {
     SLIMB200_CUDA_TRY(cudaFuncSetAttribute(k_corr_lookup<T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            C::smem_bytes(SLIMB200_MAX_LEVELS)));
-    attr_set = C::smem_bytes(SLIMB200_MAX_LEVELS);
+    attr_set[dev] = true;
   }
   dim3 grid((nf + LK_PIX - 1) / LK_PIX, L->batch);
   SLIMB200_LAUNCH(SLIMB200_K_CORR_LOOKUP, stream,

@@ -241,10 +241,12 @@ int slimb200_lookup_v2_launch(const void* pyramid, const slimb200_corr_layout* L
   dim3 grid((G.nf + V2_PIX - 1) / V2_PIX, L->batch);
   if (out_layout == SLIMB200_CANVAS_NHWC) {
     const int smem = V2_PIX * V2_PITCH * 4;
-    static bool attr_set = false;
-    if (!attr_set) {
+    SLIMB200_DEVICE(dev, n_sm);
+    (void)n_sm;
+    static bool attr_set[SLIMB200_MAX_DEVICES] = {false};
+    if (!attr_set[dev]) {
       SLIMB200_CUDA_TRY(cudaFuncSetAttribute(k_corr_lookup_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      attr_set = true;
+      attr_set[dev] = true;
     }
     SLIMB200_LAUNCH(SLIMB200_K_CORR_LOOKUP, stream,
                     (k_corr_lookup_v2<true><<<grid, V2_THREADS, smem, stream>>>(static_cast<const __nv_bfloat16*>(pyramid), G, coords, out)));

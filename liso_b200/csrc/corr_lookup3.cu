@@ -567,13 +567,12 @@ extern "C" int slimb200_corr_lookup_conv(const void* pyramid, int32_t pyramid_dt
                                             reinterpret_cast<const float*>(pk + 2u * packed_w_bytes(c_out)), c_out, relu, out, out_pitch,
                                             stream);
   }
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    SLIMB200_CUDA_TRY(cudaGetDevice(&dev));
-    SLIMB200_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  SLIMB200_DEVICE(dev, n_sm);
+  static bool attr_set[SLIMB200_MAX_DEVICES] = {false};
+  if (!attr_set[dev]) {
     SLIMB200_CUDA_TRY(cudaFuncSetAttribute(k_lookup_conv_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)fused_smem_bytes(F_MAX_N)));
+    attr_set[dev] = true;
   }
   const int n_tiles = L->batch * G.m_tiles;
   const int grid = n_tiles < n_sm ? n_tiles : n_sm;

@@ -437,12 +437,11 @@ int slimb200_lookup_conv_tmem_launch(const void* pyramid, const slimb200_corr_la
   int rc = make_geo(L, &G);
   if (rc != SLIMB200_OK) return rc;
   if (c_out > G_MAX_N) return SLIMB200_E_UNSUPPORTED;
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    SLIMB200_CUDA_TRY(cudaGetDevice(&dev));
-    SLIMB200_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  SLIMB200_DEVICE(dev, n_sm);
+  static bool attr_set[SLIMB200_MAX_DEVICES] = {false};
+  if (!attr_set[dev]) {
     SLIMB200_CUDA_TRY(cudaFuncSetAttribute(k_lookup_conv_tmem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_smem_bytes(G_MAX_N)));
+    attr_set[dev] = true;
   }
   const int n_tiles = L->batch * G.m_tiles;
   const int grid = n_tiles < n_sm ? n_tiles : n_sm;

@@ -4,14 +4,15 @@
 // host merely frames them as zip members (liso_b200/slim/npz_stream.py), so that np.load (torch_dataset_commons.py:
 // 614-616) reads the files unchanged.
 //
-// The maps are fp32 with exact zeros wherever the pillar is empty (head_decoder.py:567-609): runs of zero WORDS become
-// <literal 0><match distance 1, length <= 258>... and every other word four literals, all in the FIXED Huffman code
-// (RFC 1951 3.2.6), so that the bit length of every token is known without a histogram pass.
+// The maps are fp32 and constant wherever the pillar is empty (head_decoder.py:567-609: flow exactly 0, dynamicness the
+// softmax of (0, -100, -100) = one denormal): a word that equals the word before it continues a RUN, and a run becomes
+// <match distance 4, length <= 258>...; every other word is four literals (a zero word: literal 0 + <distance 1, length 3>),
+// all in the FIXED Huffman code (RFC 1951 3.2.6), so that the bit length of every token is known without a histogram pass.
 //   * a member (one array of one sample) is cut into chunks of 8 KB; one CTA encodes one chunk as ONE non-final fixed
 //     block followed by an empty stored block, which byte-aligns the stream (the zlib "sync flush" marker; the last
 //     chunk's stored block carries BFINAL).  Chunks are therefore byte strings that concatenate.
-//   * thread = 4 consecutive words.  Runs are found with a block-wide prefix max (last non-zero word before me) and
-//     suffix min (first non-zero word after me); the tokens of a run are a function of the byte offset from its start,
+//   * thread = 4 consecutive words.  Runs are found with a block-wide prefix max (last run-breaking word before me) and
+//     suffix min (first run-breaking word after me); the tokens of a run are a function of the byte offset from its start,
 //     so every thread emits exactly the tokens that START inside its 16 bytes -- no token crosses a thread boundary
 //     decision.  Pass 1 counts bits, a block scan turns them into bit positions, pass 2 ORs the codes into shared memory.
 //   * CRC-32: pure remainders are linear, R(A|B) = R(A) x^(8|B|) + R(B), and R(zero words) = 0.  A thread with non-zero
@@ -80,7 +81,7 @@ __device__ __forceinline__ Code lit_code(uint32_t v) {  // literal byte
   if (v < 144u) return {__brev(0x30u + v) >> 24, 8};
   return {__brev(0x190u + (v - 144u)) >> 23, 9};
 }
-__device__ __forceinline__ Code match_code(int len) {  // <length, distance 1>: length code + extra bits + 5 zero bits
+__device__ __forceinline__ Code match_code(int len, uint32_t dist_sym) {  // <length, distance>: length code + extra bits + distance
   uint32_t sym, extra = 0;
   int ne = 0;
   if (len == 258) {
@@ -102,9 +103,12 @@ __device__ __forceinline__ Code match_code(int len) {  // <length, distance 1>: 
     c.n = 8;
   }
   c.bits |= extra << c.n;
-  c.n += ne + 5;  // distance symbol 0 = five zero bits, no extra bits
+  c.n += ne;
+  c.bits |= (__brev(dist_sym) >> 27) << c.n;  // distance symbols 0..3 = distances 1..4, five bits, no extra bits
+  c.n += 5;
   return c;
 }
+constexpr uint32_t DIST_1 = 0, DIST_4 = 3;
 
 struct BitCounter {
   uint32_t n = 0;
@@ -129,43 +133,44 @@ struct BitWriter {  // ORs codes into the shared chunk image starting at bit `po
   }
 };
 
-// tokens of the zero run of `run_bytes` bytes that START inside [lo, hi) (byte offsets from the run's start, hi - lo <= 16):
-// offset 0: literal 0; offsets 1 + 258 k: matches of 258; then the remainder as one match (>= 3) or one / two literals
+// tokens of a run of `run_bytes` bytes (words equal to the word before the run) that START inside [lo, hi) (byte offsets from
+// the run's start, hi - lo <= 16): matches of 258 at offsets 258 k, then the remainder r as one more match; a remainder of 1
+// or 2 bytes (too short for a match) borrows 3 bytes from the last full match.  Distance 4 = one word back.
 template <class Sink>
 __device__ __forceinline__ void run_tokens(Sink& s, int run_bytes, int lo, int hi) {
-  if (lo == 0) s.put(lit_code(0));
-  const int m = run_bytes - 1, nfull = m / 258, r = m - nfull * 258;
-  const int k0 = lo <= 1 ? 0 : (lo + 256) / 258;
-  if (k0 < nfull && 1 + 258 * k0 < hi) s.put(match_code(258));
-  const int q = 1 + 258 * nfull;
-  if (r >= 3) {
-    if (q >= lo && q < hi) s.put(match_code(r));
-  } else {
-    for (int j = 0; j < r; ++j)
-      if (q + j >= lo && q + j < hi) s.put(lit_code(0));
-  }
+  const int nfull = run_bytes / 258, r = run_bytes - nfull * 258;
+  const int d = (r == 1 || r == 2) ? 3 : 0;
+  const int k0 = (lo + 257) / 258;
+  if (k0 < nfull && 258 * k0 < hi) s.put(match_code(k0 == nfull - 1 ? 258 - d : 258, DIST_4));
+  const int q = 258 * nfull - d;
+  if (r + d >= 3 && q >= lo && q < hi) s.put(match_code(r + d, DIST_4));
 }
 
-// the tokens that start inside this thread's words [i0, i0 + nv); zb / za = zero words right before / behind them
+// the tokens that start inside this thread's words [i0, i0 + nv); rep bit k: word k equals the word before it;
+// zb / za = run words right before / behind my words
 template <class Sink>
-__device__ __forceinline__ void thread_tokens(Sink& s, const uint32_t (&w)[4], int i0, int nv, int zb, int za) {
+__device__ __forceinline__ void thread_tokens(Sink& s, const uint32_t (&w)[4], uint32_t rep, int nv, int zb, int za) {
   int i = 0;
   while (i < nv) {
-    if (w[i]) {
+    if (!((rep >> i) & 1u)) {
       const uint32_t v = w[i];
-      s.put(lit_code(v & 255u));
-      s.put(lit_code((v >> 8) & 255u));
-      s.put(lit_code((v >> 16) & 255u));
-      s.put(lit_code(v >> 24));
+      if (v == 0u) {  // 00 00 00 00 as literal + <distance 1, length 3>: 20 bits instead of 32
+        s.put(lit_code(0));
+        s.put(match_code(3, DIST_1));
+      } else {
+        s.put(lit_code(v & 255u));
+        s.put(lit_code((v >> 8) & 255u));
+        s.put(lit_code((v >> 16) & 255u));
+        s.put(lit_code(v >> 24));
+      }
       ++i;
     } else {
       const int a = i;
-      while (i < nv && w[i] == 0) ++i;
+      while (i < nv && ((rep >> i) & 1u)) ++i;
       const int before = a == 0 ? zb : 0, behind = i == nv ? za : 0;
       run_tokens(s, 4 * (before + (i - a) + behind), 4 * before, 4 * (before + (i - a)));
     }
   }
-  (void)i0;
 }
 
 __global__ void __launch_bounds__(THREADS)
@@ -215,12 +220,25 @@ k_deflate_chunks(const slimb200_deflate_member* __restrict__ members, int n_memb
     }
   }
 
-  // ---- zero words right before / behind my words: prefix max of the last non-zero word, suffix min of the first one
+  // ---- which of my words repeat the word before them (the chunk's first word never does)
+  __shared__ uint32_t s_edge[WARPS];
+  if (lane == 31) s_edge[wid] = w[3];
+  uint32_t prev = __shfl_up_sync(0xffffffffu, w[3], 1);
+  __syncthreads();
+  if (lane == 0 && wid > 0) prev = s_edge[wid - 1];
+  uint32_t rep = 0;
+  bool any_nz = false;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (k < nv && (i0 + k) > 0 && w[k] == (k ? w[k - 1] : prev)) rep |= 1u << k;
+    any_nz |= (k < nv && w[k] != 0u);
+  }
+  // ---- run words right before / behind my words: prefix max of the last run-breaking word, suffix min of the first one
   int last = -1, first = nw;
   uint32_t crc = 0;
 #pragma unroll
   for (int k = 0; k < 4; ++k)
-    if (k < nv && w[k]) {
+    if (k < nv && !((rep >> k) & 1u)) {
       last = i0 + k;
       if (first == nw) first = i0 + k;
     }
@@ -243,7 +261,7 @@ k_deflate_chunks(const slimb200_deflate_member* __restrict__ members, int n_memb
 
   // ---- pass 1: bits of my tokens -> bit position
   BitCounter cnt;
-  if (nv > 0) thread_tokens(cnt, w, i0, nv, zb, za);
+  if (nv > 0) thread_tokens(cnt, w, rep, nv, zb, za);
   uint32_t inc = cnt.n;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -253,7 +271,7 @@ k_deflate_chunks(const slimb200_deflate_member* __restrict__ members, int n_memb
   if (lane == 31) s_bits[wid] = inc;
 
   // ---- CRC remainder of my words, moved to the end of the chunk
-  if (last >= 0) {
+  if (any_nz) {
 #pragma unroll
     for (int k = 0; k < 4; ++k)
       if (k < nv) {
@@ -278,7 +296,7 @@ k_deflate_chunks(const slimb200_deflate_member* __restrict__ members, int n_memb
   // ---- pass 2: write the codes
   if (cnt.n) {
     BitWriter bw(buf, pos);
-    thread_tokens(bw, w, i0, nv, zb, za);
+    thread_tokens(bw, w, rep, nv, zb, za);
     bw.flush();
   }
   // block header (BFINAL 0, BTYPE 01 -> bits 0,1,0), end-of-block (7 zero bits), stored-block header (BFINAL of the member's

@@ -1008,12 +1008,8 @@ extern "C" int slimb200_pillar_encode(const float* const* points, const int32_t*
     SLIMB200_LAUNCH(SLIMB200_K_BN_FINALIZE, stream, (k_bn_finalize<<<1, MAX_COUT, 0, stream>>>(a, n_ctas)));
   }
   {
-    static int n_sm = 0;
-    if (n_sm == 0) {
-      int dev = 0;
-      SLIMB200_CUDA_TRY(cudaGetDevice(&dev));
-      SLIMB200_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    }
+    SLIMB200_DEVICE(dev, n_sm);
+    (void)dev;
     if (p->canvas_layout == SLIMB200_CANVAS_NHWC) {
       SLIMB200_LAUNCH(SLIMB200_K_PILLAR_NHWC, stream,
                       (k_pillar_nhwc<<<n_sm * NH_CTAS_PER_SM, NH_THREADS, 0, stream>>>(a)));

@@ -16,6 +16,21 @@ long long g_count[SLIMB200_N_KERNELS] = {0};
 constexpr size_t MAX_RECS = 16384;
 }  // namespace
 
+int slimb200_device_info(int* dev, int* n_sm) {
+  static int sm_count[SLIMB200_MAX_DEVICES] = {0};
+  cudaError_t e = cudaGetDevice(dev);
+  if (e != cudaSuccess) return (int)e;
+  if (*dev < 0 || *dev >= SLIMB200_MAX_DEVICES) return SLIMB200_E_UNSUPPORTED;
+  if (sm_count[*dev] == 0) {
+    int n = 0;
+    e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, *dev);
+    if (e != cudaSuccess) return (int)e;
+    sm_count[*dev] = n;
+  }
+  *n_sm = sm_count[*dev];
+  return 0;
+}
+
 void slimb200_prof_pre(int id, cudaStream_t s) {
   g_count[id]++;
   if (!g_enabled || g_used >= MAX_RECS) return;

@@ -73,6 +73,9 @@ class _LazyLevels:
         return (self[i] for i in range(len(self)))
 
 
+@_lib.on_device_of_args
+
+
 def lookup(pyramid: torch.Tensor, L: _lib.CorrLayout, coords: torch.Tensor, radius: int,
            channels_last: bool = False) -> torch.Tensor:
     """``slimb200_corr_lookup`` on a packed pyramid (bf16 or fp32).  ``channels_last`` (radius 3 only) returns the
@@ -101,6 +104,7 @@ class PackedLookupConv:
     its shared-memory layout + biases; ``slimb200_corr_lookup_conv_pack``).  Built once per weight tensor; the owner
     re-packs when the source parameters change (:meth:`matches`)."""
 
+    @_lib.on_device_of_args
     def __init__(self, weight: torch.Tensor, bias: torch.Tensor = None, levels: int = 4, radius: int = 3):
         _lib.require_cuda(weight, bias)
         lib = _lib.load()
@@ -133,6 +137,9 @@ class PackedLookupConv:
         if bias is None or b_ref is None:
             return bias is None and b_ref is None
         return b_ref() is bias and bias._version == b_ver
+
+
+@_lib.on_device_of_args
 
 
 def lookup_conv(pyramid: torch.Tensor, L: _lib.CorrLayout, coords: torch.Tensor, radius: int, packed: PackedLookupConv,
@@ -186,6 +193,8 @@ class CorrBlock:
         self.pyramid = None
         self._ws = None
         self.rebuild(fmap1, fmap2)
+
+    @_lib.on_device_of_args
 
     def rebuild(self, fmap1: torch.Tensor, fmap2: torch.Tensor) -> "CorrBlock":
         """(Re)compute the pyramid for a new pair of feature maps INTO the buffers this block already owns (same

@@ -434,7 +434,7 @@ def _pin(sample):
 def run_flow_export(model, dataset, target_dir: str, bev_range_m, *, world_size: int = 1, worker_id: int = 0,
                     batch_size: int = 8, device=None, skip_existing: bool = False, writer_workers: Optional[int] = None,
                     pipeline_factory=None, compress_on_gpu: bool = False, loader_workers: int = 0,
-                    unlink_after_write: bool = False) -> Dict[str, float]:
+                    unlink_after_write: bool = False, pad_last_batch: bool = True) -> Dict[str, float]:
     """The flow export of ``liso/slim/experiment.py:225-361,363-471`` for the t0 -> t1 pairs of one worker: this rank's
     share of the pairs (modulo rule), batched, through the double-buffered :class:`ExportPipeline`, written by
     :class:`AsyncNpzWriter` in the reference's ``.npz`` schema under ``target_dir/<sample_id>.npz``; one collective at
@@ -445,7 +445,9 @@ def run_flow_export(model, dataset, target_dir: str, bev_range_m, *, world_size:
     t1 -> t2 are computed in one pass per batch (every frame encoded once) and the file holds all 12 maps
     (``experiment.py:404-456``).  ``compress_on_gpu``: the maps are deflated on the device and the writer threads only frame
     zip members (same files for ``np.load``).  ``loader_workers``: > 0 moves dataset access, collation and
-    pinning to a background thread (> 1: with that many threads fetching samples), like DataLoader workers.  Returns ``{"pairs", "files", "skipped", "elapsed_s_max"}`` over all ranks ("pairs"
+    pinning to a background thread (> 1: with that many threads fetching samples), like DataLoader workers.
+    ``pad_last_batch``: a ragged last batch is filled up with copies of its last sample (outputs discarded) so that no
+    tensor shape changes.  Returns ``{"pairs", "files", "skipped", "elapsed_s_max"}`` over all ranks ("pairs"
     counts samples)."""
     import time
 
@@ -472,6 +474,10 @@ def run_flow_export(model, dataset, target_dir: str, bev_range_m, *, world_size:
             if not items:
                 continue
             ids_of_batch.append([it[0] for it in items])
+            if pad_last_batch and len(items) < batch_size:
+                # a ragged last batch would change every tensor shape (new cuDNN plans, a new CUDA graph for one batch):
+                # fill it up with copies of its last sample; their outputs are never read (ids_of_batch has the real ones)
+                items = items + [items[-1]] * (batch_size - len(items))
             yield tuple(_pin(d) for d in collate_pairs([tuple(it[1:]) for it in items]))
 
     thr = float(model.moving_dynamicness_threshold.value())

@@ -50,6 +50,9 @@ def _nhwc_source(t: torch.Tensor) -> Tuple[torch.Tensor, int]:
     return t.contiguous(memory_format=torch.channels_last), Cn
 
 
+@_lib.on_device_of_args
+
+
 def nhwc_pack_into(srcs: Sequence[torch.Tensor], dsts: Sequence[Tuple[torch.Tensor, int]]) -> None:
     """Channel-concatenate ``srcs`` (<= 4; packed channels-last tensors or channel slices of such) and store the result at
     channel offset ``off`` of every ``(dst, off)`` (<= 2 destinations, packed channels-last tensors with
@@ -82,6 +85,9 @@ def nhwc_cat(srcs: Sequence[torch.Tensor]) -> torch.Tensor:
     return out
 
 
+@_lib.on_device_of_args
+
+
 def gru_gate_zr(zr_raw: torch.Tensor, bias_zr: torch.Tensor, hx: torch.Tensor, rhx: torch.Tensor, hidden: int) -> torch.Tensor:
     """``z = sigmoid(zr_raw[:, :hidden] + b)`` (returned, packed) and ``rhx[:, :hidden] = sigmoid(zr_raw[:, hidden:] + b) *
     hx[:, :hidden]`` (``update.py:33-35``); ``zr_raw`` is the stacked update|reset convolution WITHOUT its bias."""
@@ -93,6 +99,9 @@ def gru_gate_zr(zr_raw: torch.Tensor, bias_zr: torch.Tensor, hx: torch.Tensor, r
     _lib.check(_lib.load().slimb200_gru_gate_zr(zr_raw.data_ptr(), bias_zr.data_ptr(), hx.data_ptr(), hx.shape[1], z.data_ptr(),
                                                 rhx.data_ptr(), rhx.shape[1], hidden, _pixels(zr_raw), _lib.current_stream_ptr()))
     return z
+
+
+@_lib.on_device_of_args
 
 
 def gru_gate_out(q_raw: torch.Tensor, bias_q: torch.Tensor, z: torch.Tensor, hx: torch.Tensor, hidden: int) -> torch.Tensor:
@@ -121,6 +130,9 @@ def _head_strides(t: torch.Tensor) -> Tuple[torch.Tensor, int, int, int]:
     return t, t.stride(0), t.stride(1), 1
 
 
+@_lib.on_device_of_args
+
+
 def iter_update(dflow_raw: torch.Tensor, bias_flow: torch.Tensor, dlogits_raw: torch.Tensor, bias_logits: torch.Tensor,
                 coords1: torch.Tensor, flow: torch.Tensor, logits: torch.Tensor, stacked: torch.Tensor = None) -> None:
     """In place (``raft_mod.py:205-212``): ``coords1 += dflow_raw + b``; ``logits += dlogits_raw + b``;
@@ -143,6 +155,9 @@ def iter_update(dflow_raw: torch.Tensor, bias_flow: torch.Tensor, dlogits_raw: t
                                                 stacked.shape[1] if stacked is not None else 0, _lib.current_stream_ptr()))
 
 
+@_lib.on_device_of_args
+
+
 def iter_update_taps(taps: torch.Tensor, ksize: int, bias_flow: torch.Tensor, bias_logits: torch.Tensor, coords1: torch.Tensor,
                      flow: torch.Tensor, logits: torch.Tensor, stacked: torch.Tensor = None) -> None:
     """`iter_update` with the heads' k x k output convolution given as the 1x1 "tap" tensor (B, k*k*(2 + n_logits), h, w),
@@ -160,6 +175,9 @@ def iter_update_taps(taps: torch.Tensor, ksize: int, bias_flow: torch.Tensor, bi
                                                      h, w, coords1.data_ptr(), flow.data_ptr(), logits.data_ptr(),
                                                      stacked.data_ptr() if stacked is not None else None,
                                                      stacked.shape[1] if stacked is not None else 0, _lib.current_stream_ptr()))
+
+
+@_lib.on_device_of_args
 
 
 def add_relu(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:

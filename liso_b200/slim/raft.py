@@ -19,6 +19,9 @@ from ..networks.pcl_to_feature_grid import PointsPillarFeatureNetWrapper
 from .corr import CorrBlock, coords_grid, initialize_flow, uplogits_n, upflow_n
 
 
+from .. import _lib as _lib_module  # noqa: E402
+
+
 def _lib_mod():
     from .. import _lib
 
@@ -119,6 +122,9 @@ def _stacked_params(a: nn.Conv2d, b: nn.Conv2d, shared_input: bool, pad_in_to: i
         return w, torch.cat([a.bias.detach(), b.bias.detach()], dim=0)
 
     return _derived(a, ("stacked", shared_input, pad_in_to), (a.weight, a.bias, b.weight, b.bias), build)
+
+
+@_lib_module.on_device_of_args
 
 
 def instance_norm_nhwc(norm: nn.InstanceNorm2d, x: torch.Tensor, relu: bool, residual: torch.Tensor = None,
@@ -324,6 +330,9 @@ class SmallUpdateBlock(nn.Module):
         motion = self.motion_encoder(flow, corr, logits)
         net = self.gru(net, torch.cat([inp, motion], dim=1))
         return net, self.static_flow_head(net), self.classification_head(net), None
+
+
+@_lib_module.on_device_of_args
 
 
 def raft_output_fused(flow, logits, n, res_rows, res_cols):

@@ -19,6 +19,7 @@ import numpy as np
 import torch
 from torch import nn
 
+from .. import _lib as _lib_module
 from ..config import AttrDict
 from .raft import RAFT
 
@@ -111,6 +112,8 @@ class HeadDecoder(nn.Module):
         _lib.require_cuda(network_output, pc, pointwise_voxel_coordinates, pointwise_valid_mask, filled_pillar_mask)  # no CPU path
         return self._forward_fused(network_output, dynamicness_threshold, pc, pointwise_voxel_coordinates,
                                    pointwise_valid_mask, filled_pillar_mask, static_aggregation)
+
+    @_lib_module.on_device_of_args
 
     def _forward_fused(self, o, thr, pc, coors, valid, filled, static_aggregation):
         """One call into ``slimb200_head_decode``: five launches, no host sync; the tensors of the

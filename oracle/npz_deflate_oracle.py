@@ -3,8 +3,9 @@
 What is being replaced is the zlib pass of ``np.savez_compressed`` in ``liso/slim/experiment.py:459-471``; zlib itself
 (not in /root/reference: CPython's bundled zlib) is the independent checker -- ``zlib.decompress(stream, -15)`` must
 return the array's bytes and ``np.load`` must read the framed file.  This module restates the *encoder's* format
-(RFC 1951 3.2.6 fixed Huffman code; chunks of 8 KB, each a non-final fixed block + an empty stored block; zero-word
-runs as ``literal 0`` + distance-1 matches) sequentially, so that the GPU bytes can be compared exactly.
+(RFC 1951 3.2.6 fixed Huffman code; chunks of 8 KB, each a non-final fixed block + an empty stored block; a word equal to
+the word before it continues a run, runs are distance-4 matches; a zero word that starts a run is ``literal 0`` +
+``<distance 1, length 3>``) sequentially, so that the GPU bytes can be compared exactly.
 
 Pinned by ``tests/test_npz_stream.py``: every stream decodes with zlib to the input, for the edge cases of the token
 rule (runs of 1..600 words, runs across chunk borders, remainders 1 and 2, ragged last chunk, all-zero, no zero).
@@ -26,9 +27,10 @@ def lit_code(v: int):
     return (_rev(0x30 + v, 8), 8) if v < 144 else (_rev(0x190 + v - 144, 9), 9)
 
 
-def match_code(length: int):
-    """<length, distance 1>: Huffman code of the length symbol, its extra bits, five zero bits for distance symbol 0."""
-    assert 3 <= length <= 258
+def match_code(length: int, dist_sym: int = 0):
+    """<length, distance>: Huffman code of the length symbol, its extra bits, five bits of the distance symbol (0..3 =
+    distances 1..4, no extra bits)."""
+    assert 3 <= length <= 258 and 0 <= dist_sym <= 3
     extra, ne = 0, 0
     if length == 258:
         sym = 285
@@ -40,7 +42,12 @@ def match_code(length: int):
         sym = 257 + 4 * ne + (l >> ne)
         extra = l & ((1 << ne) - 1)
     bits, n = (_rev(sym - 256, 7), 7) if sym < 280 else (_rev(0xC0 + sym - 280, 8), 8)
-    return bits | (extra << n), n + ne + 5
+    bits |= extra << n
+    n += ne
+    return bits | (_rev(dist_sym, 5) << n), n + 5
+
+
+DIST_1, DIST_4 = 0, 3
 
 
 class _Bits:
@@ -53,17 +60,14 @@ class _Bits:
 
 
 def run_tokens(out: _Bits, run_bytes: int):
-    """Tokens of a run of ``run_bytes`` zero bytes: literal, matches of 258, remainder as a match (>= 3) or literals."""
-    out.put(lit_code(0))
-    m = run_bytes - 1
-    for _ in range(m // 258):
-        out.put(match_code(258))
-    r = m % 258
-    if r >= 3:
-        out.put(match_code(r))
-    else:
-        for _ in range(r):
-            out.put(lit_code(0))
+    """Tokens of a run of ``run_bytes`` bytes that repeat the word in front of the run: matches of 258 at distance 4, the
+    remainder as one more match; a remainder of 1 or 2 bytes borrows 3 bytes from the last full match."""
+    nfull, r = divmod(run_bytes, 258)
+    d = 3 if r in (1, 2) else 0
+    for k in range(nfull):
+        out.put(match_code(258 - d if k == nfull - 1 else 258, DIST_4))
+    if r + d >= 3:
+        out.put(match_code(r + d, DIST_4))
 
 
 def encode_chunk(words: np.ndarray, last: bool) -> bytes:
@@ -71,14 +75,18 @@ def encode_chunk(words: np.ndarray, last: bool) -> bytes:
     out.put((2, 3))  # BFINAL 0, BTYPE 01
     i, n = 0, len(words)
     while i < n:
-        if words[i]:
+        if i == 0 or words[i] != words[i - 1]:
             v = int(words[i])
-            for k in range(4):
-                out.put(lit_code((v >> (8 * k)) & 255))
+            if v == 0:
+                out.put(lit_code(0))
+                out.put(match_code(3, DIST_1))
+            else:
+                for k in range(4):
+                    out.put(lit_code((v >> (8 * k)) & 255))
             i += 1
         else:
             a = i
-            while i < n and words[i] == 0:
+            while i < n and words[i] == words[i - 1]:
                 i += 1
             run_tokens(out, 4 * (i - a))
     out.put((0, 7))  # end of block

@@ -507,7 +507,12 @@ def test_triple_export_writes_the_twelve_maps_of_the_reference(tmp_path):
     dataset = [("%03d" % i, sample(10 + i), sample(20 + i), sample(30 + i)) for i in range(5)]
     out = export.run_flow_export(_CpuModel(), dataset, str(tmp_path), (70.0, 70.0), batch_size=2, pipeline_factory=FakePipeline,
                                  writer_workers=2)
-    assert out["pairs"] == 5 and out["files"] == 5 and seen == [2, 2, 1]
+    assert out["pairs"] == 5 and out["files"] == 5 and seen == [2, 2, 2]  # the ragged last batch is padded, its copy not written
+    assert sorted(os.listdir(tmp_path)) == ["%03d.npz" % i for i in range(5)]
+    seen.clear()
+    out = export.run_flow_export(_CpuModel(), dataset, str(tmp_path / "ragged"), (70.0, 70.0), batch_size=2, pipeline_factory=FakePipeline,
+                                 writer_workers=2, pad_last_batch=False, loader_workers=2)
+    assert out["files"] == 5 and seen == [2, 2, 1]
     z = np.load(tmp_path / "003.npz")
     assert set(z.files) == REFERENCE_TRIPLE_KEYS
     for k, d in enumerate(export.DIRECTIONS_TRIPLE):

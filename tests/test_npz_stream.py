@@ -22,15 +22,23 @@ def _cases():
     out["one_word"] = np.array([1.5], np.float32)
     out["one_zero"] = np.zeros(1, np.float32)
     out["dense"] = rng.normal(size=5000).astype(np.float32)  # no zero at all, 9-bit literals included
-    r = []  # every run length 1 .. 140 words (remainders 0 .. 257 of the match rule), a non-zero word between
+    r = []  # every run length 1 .. 140 words (every remainder of the match rule), a different word between
     for n in range(1, 141):
         r += [0.0] * n + [float(n)]
     out["all_run_lengths"] = np.array(r, np.float32)
-    b = np.zeros(2048 * 2, np.float32)  # run bytes - 1 = 258 k + {1, 2}: the literal remainders
-    b[65] = 1.0  # run of 65 words = 260 bytes: 259 = 258 + 1
-    b[66 + 130] = 2.0  # run of 130 words = 520 bytes: 519 = 2 * 258 + 3
-    b[66 + 131 + 129] = 3.0  # run of 129 words = 516 bytes: 515 = 258 + 257
+    r = []  # the same with runs of a NON-zero word (the denormal the softmax leaves in empty pillars)
+    for n in range(1, 141):
+        r += [3.8e-44] * n + [float(n)]
+    out["all_run_lengths_denormal"] = np.array(r, np.float32)
+    b = np.zeros(2048 * 2, np.float32)  # run bytes = 258 k + 2: the remainder that borrows from the last full match
+    b[66] = 1.0  # 66 zero words: a run of 65 words = 260 bytes = 258 + 2
+    b[67 + 195] = 2.0  # a run of 194 words = 776 bytes = 3 * 258 + 2
+    b[67 + 196 + 130] = 3.0  # a run of 129 words = 516 bytes = 2 * 258 exactly
     out["remainders"] = b
+    dyn = np.full((96, 96), 3.8e-44, np.float32)  # dynamicness-like: constant denormal, 6 % occupied
+    m2 = rng.random((96, 96)) < 0.06
+    dyn[m2] = rng.random(int(m2.sum())).astype(np.float32)
+    out["bev_dynamicness"] = dyn
     bev = np.zeros((96, 96, 2), np.float32)  # BEV-like: 6 % occupied cells
     m = rng.random((96, 96)) < 0.06
     bev[m] = rng.normal(size=(int(m.sum()), 2)).astype(np.float32)
@@ -60,6 +68,7 @@ def test_fixed_code_tables():
     assert DO.match_code(3) == (0b1000000, 12) and DO.match_code(258) == (0b10100011, 13)
     assert DO.match_code(11)[1] == 13 and DO.match_code(12)[0] == DO.match_code(11)[0] | (1 << 7)
     assert DO.match_code(257)[1] == 8 + 5 + 5
+    assert DO.match_code(258, DO.DIST_4) == (0b10100011 | (0b11000 << 8), 13)  # distance symbol 3 = 00011, sent MSB first
 
 
 def test_npz_framing_reads_back_with_np_load(tmp_path):
@@ -162,8 +171,8 @@ def test_gpu_full_size_round_trip():
     g = torch.Generator(device="cpu").manual_seed(5)
     B, H, W = 8, 640, 640
     occ = torch.rand(B, H, W, generator=g) < 0.05
-    flow = torch.randn(B, H, W, 2, generator=g) * occ[..., None]
-    dyn = torch.rand(B, H, W, generator=g) * occ
+    flow = torch.where(occ[..., None], torch.randn(B, H, W, 2, generator=g), torch.zeros(()))  # (x * False would leave -0.0 words)
+    dyn = torch.where(occ, torch.rand(B, H, W, generator=g), torch.full((), 3.8e-44))  # empty pillars: the softmax denormal
     enc = npz_stream.DeflateEncoder(dev)
     enc.encode([flow.to(dev), dyn.to(dev)], slot=0)
     enc.start_download(0)
