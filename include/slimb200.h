@@ -330,6 +330,14 @@ int slimb200_iter_update_taps(const float* taps, int32_t ksize, const float* bia
                               int32_t n_logits, int32_t batch, int32_t h, int32_t w, float* coords1, float* flow,
                               float* logits, float* stacked, int32_t stacked_channels, void* stream);
 int slimb200_add_relu(const float* x, const float* y, float* out, int64_t n, void* stream);
+/* out = relu((x + bias_x[c]) + y), channels-last data with `channels` (multiple of 4) innermost: the projection shortcut
+ * of a residual block (extractor.py:44-68) convolved WITHOUT its bias, which joins here instead of in a pass of its own. */
+/* Context encoder tail (raft_mod.py:170-173): raw = cnet's last convolution WITHOUT its bias, channels-last (pixels,
+ * hidden + context); net = tanh(raw[:, :hidden] + bias), inp = relu(raw[:, hidden:] + bias), both packed channels-last. */
+int slimb200_ctx_split(const float* raw, const float* bias, int32_t hidden, int32_t context, int64_t pixels, float* net,
+                       float* inp, void* stream);
+int slimb200_add_bias_relu(const float* x, const float* bias_x, int32_t channels, const float* y, float* out, int64_t n,
+                           void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Export writer.  Replaces the zlib pass of np.savez_compressed in
@@ -418,6 +426,7 @@ enum {
   SLIMB200_K_DEFLATE_CHUNKS,
   SLIMB200_K_DEFLATE_SCAN,
   SLIMB200_K_DEFLATE_GATHER,
+  SLIMB200_K_CTX_SPLIT,
   SLIMB200_N_KERNELS
 };
 int slimb200_profile_begin(void);

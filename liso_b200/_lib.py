@@ -166,6 +166,8 @@ SYMBOLS = {
          C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p],
     ),
     "slimb200_add_relu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "slimb200_ctx_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "slimb200_add_bias_relu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "slimb200_deflate_plan": (C.c_int, [C.POINTER(DeflateMember), C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "slimb200_deflate_init": (C.c_int, [C.c_void_p, C.c_void_p]),
     "slimb200_deflate_encode": (
@@ -179,7 +181,7 @@ SYMBOLS = {
     "slimb200_launch_count": (C.c_int64, [C.c_int32]),
     "slimb200_kernel_name": (C.c_char_p, [C.c_int32]),
 }
-N_KERNELS = 38
+N_KERNELS = 39
 K_POINT_KEYS, K_SCAN_LOCAL, K_SCAN_GLOBAL, K_RANK_SCATTER = 0, 1, 2, 3
 K_TILE_ENCODE, K_PILLAR_NHWC, K_FEAT_TRANSPOSE, K_FEAT_PACK, K_CORR_GEMM, K_CORR_LOOKUP = 6, 7, 8, 9, 10, 11
 K_DECODE_BEV, K_DECODE_POINTS, K_DECODE_AGGR, K_RAFT_OUTPUT = 14, 15, 17, 18

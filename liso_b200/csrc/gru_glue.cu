@@ -204,6 +204,41 @@ __global__ void __launch_bounds__(GL_THREADS) k_add_relu(const float4* __restric
   }
 }
 
+// relu((x + bias_x[c]) + y) on channels-last data: the projection shortcut of a residual block computed without its bias
+// (ATen adds a convolution's bias in a separate pass over the tensor), rounded like conv-with-bias followed by relu(x + y)
+__global__ void __launch_bounds__(GL_THREADS) k_add_bias_relu(const float4* __restrict__ x, const float4* __restrict__ bias_x,
+                                                              int c4, const float4* __restrict__ y, float4* __restrict__ out,
+                                                              size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * GL_THREADS + threadIdx.x; i < n4; i += (size_t)gridDim.x * GL_THREADS) {
+    const float4 a = __ldg(x + i), b = __ldg(y + i), c = __ldg(bias_x + (i % (size_t)c4));
+    float4 o;
+    o.x = fmaxf(__fadd_rn(__fadd_rn(a.x, c.x), b.x), 0.f);
+    o.y = fmaxf(__fadd_rn(__fadd_rn(a.y, c.y), b.y), 0.f);
+    o.z = fmaxf(__fadd_rn(__fadd_rn(a.z, c.z), b.z), 0.f);
+    o.w = fmaxf(__fadd_rn(__fadd_rn(a.w, c.w), b.w), 0.f);
+    out[i] = o;
+  }
+}
+
+// context encoder tail (raft_mod.py:170-173): net = tanh(raw[:, :ch] + b), inp = relu(raw[:, ch:] + b) from the bias-free
+// output of cnet's last convolution -- one pass instead of ATen's bias add, split, tanh and clamp
+__global__ void __launch_bounds__(GL_THREADS) k_ctx_split(const float4* __restrict__ raw, const float4* __restrict__ bias, int ch4,
+                                                          int cx4, float4* __restrict__ net, float4* __restrict__ inp, size_t pixels) {
+  const int c4 = ch4 + cx4;
+  const size_t n4 = pixels * (size_t)c4;
+  for (size_t i = (size_t)blockIdx.x * GL_THREADS + threadIdx.x; i < n4; i += (size_t)gridDim.x * GL_THREADS) {
+    const size_t pix = i / (size_t)c4;
+    const int g = (int)(i - pix * (size_t)c4);
+    const float4 a = __ldg(raw + i), b = __ldg(bias + g);
+    float4 v = make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
+    if (g < ch4) {
+      net[pix * (size_t)ch4 + g] = make_float4(tanhf(v.x), tanhf(v.y), tanhf(v.z), tanhf(v.w));
+    } else {
+      inp[pix * (size_t)cx4 + (g - ch4)] = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+    }
+  }
+}
+
 inline bool mis16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) != 0; }
 
 }  // namespace
@@ -349,5 +384,33 @@ extern "C" int slimb200_add_relu(const float* x, const float* y, float* out, int
                   (k_add_relu<<<grid_for((size_t)n / 4, 4), GL_THREADS, 0, stream>>>(
                       reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(y), reinterpret_cast<float4*>(out),
                       (size_t)n / 4)));
+  return SLIMB200_OK;
+}
+
+extern "C" int slimb200_add_bias_relu(const float* x, const float* bias_x, int32_t channels, const float* y, float* out, int64_t n,
+                                      void* stream_) {
+  if (!x || !bias_x || !y || !out || n < 0 || channels < 4) return SLIMB200_E_INVALID;
+  if ((n & 3) || (channels & 3) || n % channels) return SLIMB200_E_UNSUPPORTED;
+  if (mis16(x) || mis16(y) || mis16(out) || mis16(bias_x)) return SLIMB200_E_ALIGNMENT;
+  if (n == 0) return SLIMB200_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SLIMB200_LAUNCH(SLIMB200_K_ADD_RELU, stream,
+                  (k_add_bias_relu<<<grid_for((size_t)n / 4, 4), GL_THREADS, 0, stream>>>(
+                      reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(bias_x), channels / 4,
+                      reinterpret_cast<const float4*>(y), reinterpret_cast<float4*>(out), (size_t)n / 4)));
+  return SLIMB200_OK;
+}
+
+extern "C" int slimb200_ctx_split(const float* raw, const float* bias, int32_t hidden, int32_t context, int64_t pixels, float* net,
+                                  float* inp, void* stream_) {
+  if (!raw || !bias || !net || !inp || pixels < 0 || hidden < 4 || context < 4) return SLIMB200_E_INVALID;
+  if ((hidden & 3) || (context & 3)) return SLIMB200_E_UNSUPPORTED;
+  if (mis16(raw) || mis16(bias) || mis16(net) || mis16(inp)) return SLIMB200_E_ALIGNMENT;
+  if (pixels == 0) return SLIMB200_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SLIMB200_LAUNCH(SLIMB200_K_CTX_SPLIT, stream,
+                  (k_ctx_split<<<grid_for((size_t)pixels * (hidden + context) / 4, 4), GL_THREADS, 0, stream>>>(
+                      reinterpret_cast<const float4*>(raw), reinterpret_cast<const float4*>(bias), hidden / 4, context / 4,
+                      reinterpret_cast<float4*>(net), reinterpret_cast<float4*>(inp), (size_t)pixels)));
   return SLIMB200_OK;
 }

@@ -37,8 +37,6 @@ def preprocess_params(cfg, c_in: int = 4, cone_angle_deg: float = 0.8) -> _lib.P
 
 
 @_lib.on_device_of_args
-
-
 def preprocess_scans(scans: Sequence[torch.Tensor], cfg, ground_labels: Optional[Sequence[Optional[torch.Tensor]]] = None,
                      cap: Optional[int] = None) -> Dict:
     """``scans``: list of ``(N_i, 3|4)`` float32 CUDA tensors (raw, with ground).  Returns the sample dictionary."""

@@ -168,7 +168,6 @@ class PointsPillarFeatureNetWrapper(nn.Module):
         return out
 
     @_lib.on_device_of_args
-
     def _encode(self, pts: Sequence[torch.Tensor], want_voxels: bool, raw_scan: bool = False, out=None):
         assert isinstance(pts, (list, tuple)), type(pts)
         lib = _lib.load()

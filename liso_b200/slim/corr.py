@@ -74,8 +74,6 @@ class _LazyLevels:
 
 
 @_lib.on_device_of_args
-
-
 def lookup(pyramid: torch.Tensor, L: _lib.CorrLayout, coords: torch.Tensor, radius: int,
            channels_last: bool = False) -> torch.Tensor:
     """``slimb200_corr_lookup`` on a packed pyramid (bf16 or fp32).  ``channels_last`` (radius 3 only) returns the
@@ -140,8 +138,6 @@ class PackedLookupConv:
 
 
 @_lib.on_device_of_args
-
-
 def lookup_conv(pyramid: torch.Tensor, L: _lib.CorrLayout, coords: torch.Tensor, radius: int, packed: PackedLookupConv,
                 relu: bool = True, out: torch.Tensor = None) -> torch.Tensor:
     """``slimb200_corr_lookup_conv``: ``act(conv1x1(lookup(coords)))`` in one kernel -- the lookup of
@@ -195,7 +191,6 @@ class CorrBlock:
         self.rebuild(fmap1, fmap2)
 
     @_lib.on_device_of_args
-
     def rebuild(self, fmap1: torch.Tensor, fmap2: torch.Tensor) -> "CorrBlock":
         """(Re)compute the pyramid for a new pair of feature maps INTO the buffers this block already owns (same
         shapes), so that a captured CUDA graph of the lookups keeps pointing at valid data."""

@@ -51,8 +51,6 @@ def _nhwc_source(t: torch.Tensor) -> Tuple[torch.Tensor, int]:
 
 
 @_lib.on_device_of_args
-
-
 def nhwc_pack_into(srcs: Sequence[torch.Tensor], dsts: Sequence[Tuple[torch.Tensor, int]]) -> None:
     """Channel-concatenate ``srcs`` (<= 4; packed channels-last tensors or channel slices of such) and store the result at
     channel offset ``off`` of every ``(dst, off)`` (<= 2 destinations, packed channels-last tensors with
@@ -86,8 +84,6 @@ def nhwc_cat(srcs: Sequence[torch.Tensor]) -> torch.Tensor:
 
 
 @_lib.on_device_of_args
-
-
 def gru_gate_zr(zr_raw: torch.Tensor, bias_zr: torch.Tensor, hx: torch.Tensor, rhx: torch.Tensor, hidden: int) -> torch.Tensor:
     """``z = sigmoid(zr_raw[:, :hidden] + b)`` (returned, packed) and ``rhx[:, :hidden] = sigmoid(zr_raw[:, hidden:] + b) *
     hx[:, :hidden]`` (``update.py:33-35``); ``zr_raw`` is the stacked update|reset convolution WITHOUT its bias."""
@@ -102,8 +98,6 @@ def gru_gate_zr(zr_raw: torch.Tensor, bias_zr: torch.Tensor, hx: torch.Tensor, r
 
 
 @_lib.on_device_of_args
-
-
 def gru_gate_out(q_raw: torch.Tensor, bias_q: torch.Tensor, z: torch.Tensor, hx: torch.Tensor, hidden: int) -> torch.Tensor:
     """``h' = (1 - z) * h + z * tanh(q_raw + b)`` (``update.py:35-38``) written into ``hx[:, :hidden]`` in place and
     returned as a packed tensor for the heads."""
@@ -131,8 +125,6 @@ def _head_strides(t: torch.Tensor) -> Tuple[torch.Tensor, int, int, int]:
 
 
 @_lib.on_device_of_args
-
-
 def iter_update(dflow_raw: torch.Tensor, bias_flow: torch.Tensor, dlogits_raw: torch.Tensor, bias_logits: torch.Tensor,
                 coords1: torch.Tensor, flow: torch.Tensor, logits: torch.Tensor, stacked: torch.Tensor = None) -> None:
     """In place (``raft_mod.py:205-212``): ``coords1 += dflow_raw + b``; ``logits += dlogits_raw + b``;
@@ -156,8 +148,6 @@ def iter_update(dflow_raw: torch.Tensor, bias_flow: torch.Tensor, dlogits_raw: t
 
 
 @_lib.on_device_of_args
-
-
 def iter_update_taps(taps: torch.Tensor, ksize: int, bias_flow: torch.Tensor, bias_logits: torch.Tensor, coords1: torch.Tensor,
                      flow: torch.Tensor, logits: torch.Tensor, stacked: torch.Tensor = None) -> None:
     """`iter_update` with the heads' k x k output convolution given as the 1x1 "tap" tensor (B, k*k*(2 + n_logits), h, w),
@@ -178,17 +168,41 @@ def iter_update_taps(taps: torch.Tensor, ksize: int, bias_flow: torch.Tensor, bi
 
 
 @_lib.on_device_of_args
-
-
-def add_relu(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
-    """``relu(x + y)`` for two fp32 CUDA tensors of the same shape and memory layout (``extractor.py:57-68``)."""
-    _lib.require_cuda(x, y)
+def add_relu(x: torch.Tensor, y: torch.Tensor, bias_x: torch.Tensor = None) -> torch.Tensor:
+    """``relu(x + y)`` for two fp32 CUDA tensors of the same shape and memory layout (``extractor.py:57-68``); with
+    ``bias_x`` (per channel, channels-last tensors) ``relu((x + bias_x) + y)``: ``x`` is then the projection shortcut
+    convolved without its bias."""
+    _lib.require_cuda(x, y, bias_x)
     if x.shape != y.shape or x.stride() != y.stride() or x.dtype != torch.float32 or y.dtype != torch.float32 \
             or not (x.is_contiguous() or x.is_contiguous(memory_format=torch.channels_last)) or x.numel() % 4:
         raise ValueError("add_relu: tensors must be dense fp32 with identical shape and strides, numel % 4 == 0")
     out = torch.empty_like(x)
+    if bias_x is not None:
+        C = int(x.shape[1])
+        if not x.is_contiguous(memory_format=torch.channels_last) or C % 4 or bias_x.numel() != C or bias_x.dtype != torch.float32:
+            raise ValueError("add_relu with bias_x: channels-last tensors with C % 4 == 0 and an fp32 bias of C elements")
+        b = bias_x.detach().contiguous()
+        _lib.check(_lib.load().slimb200_add_bias_relu(x.data_ptr(), b.data_ptr(), C, y.data_ptr(), out.data_ptr(), x.numel(),
+                                                      _lib.current_stream_ptr()))
+        return out
     _lib.check(_lib.load().slimb200_add_relu(x.data_ptr(), y.data_ptr(), out.data_ptr(), x.numel(), _lib.current_stream_ptr()))
     return out
+
+
+@_lib.on_device_of_args
+def ctx_split(raw: torch.Tensor, bias: torch.Tensor, hidden: int, context: int):
+    """Context-encoder tail (``raft_mod.py:170-173``): ``(tanh(raw[:, :hidden] + b), relu(raw[:, hidden:] + b))`` from the
+    bias-free output of cnet's last convolution (channels-last), as two packed channels-last tensors."""
+    _lib.require_cuda(raw, bias)
+    B, Cn, h, w = raw.shape
+    if Cn != hidden + context or hidden % 4 or context % 4 or raw.dtype != torch.float32 or bias.numel() != Cn \
+            or not raw.is_contiguous(memory_format=torch.channels_last):
+        raise ValueError("ctx_split: channels-last fp32 (B, hidden + context, h, w) with hidden % 4 == context % 4 == 0")
+    net = torch.empty((B, hidden, h, w), dtype=torch.float32, device=raw.device, memory_format=torch.channels_last)
+    inp = torch.empty((B, context, h, w), dtype=torch.float32, device=raw.device, memory_format=torch.channels_last)
+    _lib.check(_lib.load().slimb200_ctx_split(raw.data_ptr(), bias.detach().contiguous().data_ptr(), hidden, context, B * h * w,
+                                              net.data_ptr(), inp.data_ptr(), _lib.current_stream_ptr()))
+    return net, inp
 
 
 def add_relu_ok(x: torch.Tensor, y: torch.Tensor) -> bool:

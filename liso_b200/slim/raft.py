@@ -125,8 +125,6 @@ def _stacked_params(a: nn.Conv2d, b: nn.Conv2d, shared_input: bool, pad_in_to: i
 
 
 @_lib_module.on_device_of_args
-
-
 def instance_norm_nhwc(norm: nn.InstanceNorm2d, x: torch.Tensor, relu: bool, residual: torch.Tensor = None,
                        inplace: bool = False) -> torch.Tensor:
     """Affine InstanceNorm2d (+ ReLU) of a channels-last CUDA tensor in the library's glue kernel
@@ -222,7 +220,17 @@ class ResidualBlock(nn.Module):
         if _is_identity(self.norm1):
             y = conv_relu(self.conv2, conv_relu(self.conv1, x))
             if self.downsample is not None:
-                x = self.downsample(x)
+                d = self.downsample[0]
+                if (FAST_STOCK_OPS and d.bias is not None and d.out_channels % 4 == 0 and d.padding_mode == "zeros" and x.is_cuda
+                        and x.dtype == torch.float32 and not torch.is_grad_enabled() and not torch.is_autocast_enabled()
+                        and y.is_contiguous(memory_format=torch.channels_last) and not y.is_contiguous()):
+                    # the shortcut's bias joins in the residual kernel instead of in ATen's separate bias pass over the tensor
+                    xr = F.conv2d(x, d.weight, None, d.stride, d.padding, d.dilation, d.groups)
+                    if _glue().add_relu_ok(xr, y):
+                        return _glue().add_relu(xr, y, bias_x=d.bias)
+                    x = xr + d.bias[None, :, None, None]
+                else:
+                    x = self.downsample(x)
             return add_relu(x, y)
         y = conv_norm(self.conv1, self.norm1, x, relu=True)
         if self.downsample is not None:
@@ -251,9 +259,15 @@ class SmallEncoder(nn.Module):
             ResidualBlock(cout, cout, dummy_in_filters=cin, norm_fn=self.norm_fn, stride=1),
         )
 
-    def forward(self, x):
+    def forward(self, x, head_bias: bool = True):
+        """``head_bias=False``: the output convolution is evaluated without its bias (the caller adds it in a kernel of
+        its own, see ``RAFT._context``); not available with dropout."""
         x = conv_relu(self.conv1, x) if _is_identity(self.norm1) else conv_norm(self.conv1, self.norm1, x, relu=True)
         x = self.layer3(self.layer2(self.layer1(x)))
+        if not head_bias:
+            assert not (self.training and self.dropout is not None)
+            c = self.conv2
+            return F.conv2d(x, c.weight, None, c.stride, c.padding, c.dilation, c.groups)
         x = self.conv2(x)
         if self.training and self.dropout is not None:
             x = self.dropout(x)
@@ -333,8 +347,6 @@ class SmallUpdateBlock(nn.Module):
 
 
 @_lib_module.on_device_of_args
-
-
 def raft_output_fused(flow, logits, n, res_rows, res_cols):
     """upflow_n + uplogits_n + flip / scale + concat2network_output in one kernel (``slimb200_raft_output``,
     SURVEY 8f.2); the returned (B, H, W, 8) tensor carries the logit minimum the decoder needs."""
@@ -491,8 +503,7 @@ class RAFT(nn.Module):
         sources = sorted({f for a, b in pairs for f in (a, b)})
         ctx = {}
         for f in sources:  # context encoder of every frame a direction starts from (raft_mod.py:170-173)
-            net, inp = torch.split(self.cnet(imgs[f]), [self.hidden_dim, self.context_dim], dim=1)
-            ctx[f] = (torch.tanh(net), torch.relu(inp))
+            ctx[f] = self._context(imgs[f])
         dirs = [(a, b) for a, b in pairs for a, b in ((a, b), (b, a))]
         outs = [None] * len(dirs)
 
@@ -518,6 +529,23 @@ class RAFT(nn.Module):
         for k in range(len(dirs)):
             run(k)
         return outs
+
+    def _context(self, img):
+        """(tanh(net), relu(inp)) of the context encoder (``raft_mod.py:170-173``).  On the channels-last inference path the
+        bias of cnet's output convolution, the split, tanh and relu are ONE glue launch (``slimb200_ctx_split``) instead of
+        ATen's bias pass + tanh + clamp."""
+        cn = self.cnet
+        if (FAST_STOCK_OPS and img.is_cuda and img.dtype == torch.float32 and not torch.is_grad_enabled()
+                and not torch.is_autocast_enabled() and isinstance(cn, SmallEncoder) and cn.conv2.bias is not None
+                and not (cn.training and cn.dropout is not None) and self.hidden_dim % 4 == 0 and self.context_dim % 4 == 0):
+            raw = cn(img, head_bias=False)
+            if raw.dtype == torch.float32 and raw.is_contiguous(memory_format=torch.channels_last):
+                return _glue().ctx_split(raw, cn.conv2.bias, self.hidden_dim, self.context_dim)
+            raw = raw + cn.conv2.bias[None, :, None, None]
+        else:
+            raw = cn(img)
+        net, inp = torch.split(raw, [self.hidden_dim, self.context_dim], dim=1)
+        return torch.tanh(net), torch.relu(inp)
 
     def _branch_stream(self, device, name="bw", priority=-1):
         """Streams of the graph's branches.  The two refinement loops are captured on high-priority streams, the sink
@@ -712,6 +740,5 @@ class RAFT(nn.Module):
         b, _, H, W = img_t0.shape
         correlation = CorrBlock(fmap_t0, fmap_t1, num_levels=m.corr_cfg.num_levels, radius=m.corr_cfg.search_radius)
         if context is None:
-            net, inp = torch.split(self.cnet(img_t0), [self.hidden_dim, self.context_dim], dim=1)
-            context = (torch.tanh(net), torch.relu(inp))
+            context = self._context(img_t0)
         return self._gru_loop(correlation, context[0], context[1], (H, W), b, img_t0.device, direction)

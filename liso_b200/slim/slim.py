@@ -114,7 +114,6 @@ class HeadDecoder(nn.Module):
                                    pointwise_valid_mask, filled_pillar_mask, static_aggregation)
 
     @_lib_module.on_device_of_args
-
     def _forward_fused(self, o, thr, pc, coors, valid, filled, static_aggregation):
         """One call into ``slimb200_head_decode``: five launches, no host sync; the tensors of the
         reference's result are channel slices of two packed buffers."""
@@ -214,7 +213,7 @@ class SLIM(nn.Module):
         # until the next forward (no copy of ~0.4 GB per decoded iteration); `ExportPipeline` works this way and takes packed
         # copies of the four tensors it exports.
         self.outputs_alias_static_buffers = False
-        self._dec_static, self._dec_ctx, self._dec_n, self._sink_preds = {}, {}, {}, {}
+        self._dec_static, self._dec_ctx, self._dec_n, self._sink_preds, self._sink_filled = {}, {}, {}, {}, {}
         self._graph_preds = None  # (graph key, decoded static outputs of the captured pass)
 
     # ---- output decoding as a sink of the network (SURVEY 8f.1 + 8f.2) ------------------------------------------
@@ -228,11 +227,17 @@ class SLIM(nn.Module):
 
     def _sink_begin(self):
         self._sink_preds = {}
+        self._sink_filled = {}
 
     def _sink(self, direction, it, net_out, occupancy):
         pc, coors, valid, thr = self._dec_ctx[direction]
         dec = self.head_decoder_fw if direction % 2 == 0 else self.head_decoder_bw
-        filled = torch.squeeze(occupancy > 0.5, dim=1)
+        # one mask per direction and pass, not one per decoded iteration (per direction: the sinks of two directions are
+        # different branches of the CUDA graph, a mask shared between them would need an edge of its own)
+        fkey = (direction, occupancy.data_ptr(), tuple(occupancy.shape))
+        filled = self._sink_filled.get(fkey)
+        if filled is None:
+            filled = self._sink_filled[fkey] = torch.squeeze(occupancy > 0.5, dim=1)
         self._sink_preds[(direction, it)] = dec(net_out, thr, pc=pc, pointwise_voxel_coordinates=coors,
                                                 pointwise_valid_mask=valid, filled_pillar_mask=filled,
                                                 static_aggregation=self.static_aggregation)

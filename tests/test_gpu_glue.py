@@ -111,6 +111,11 @@ def test_residual_joins(cuda, B, C, H, W):
     x, y = _nhwc(B, C, H, W, 8, cuda), _nhwc(B, C, H, W, 9, cuda)
     assert torch.equal(R.add_relu(x, y), F.relu(x + y))
     assert torch.equal(R.add_relu(x.contiguous(), y.contiguous()), F.relu(x + y).contiguous())
+    from liso_b200.slim import glue as G
+
+    bias = torch.randn(x.shape[1], device=x.device)
+    xc, yc = x.contiguous(memory_format=torch.channels_last), y.contiguous(memory_format=torch.channels_last)
+    assert torch.equal(G.add_relu(xc, yc, bias_x=bias), F.relu((xc + bias[None, :, None, None]) + yc))
     norm = torch.nn.InstanceNorm2d(C, eps=1e-3, affine=True).to(cuda)
     with torch.no_grad():
         norm.weight.uniform_(0.5, 1.5)
@@ -163,3 +168,15 @@ def test_fused_update_block_equals_stock_loop(cuda):
         # same convolutions, same element-wise rounding: the glue kernels reproduce the stock loop
         assert float((u - b).abs().max()) <= 1e-4, float((u - b).abs().max())
         assert float((a - c).abs().max()) <= 5e-3, float((a - c).abs().max())
+
+
+def test_context_split(cuda):
+    """slimb200_ctx_split == tanh / relu of the split of (raw + bias) (raft_mod.py:170-173), to the last bit."""
+    from liso_b200.slim import glue as G
+
+    raw = _nhwc(3, 160, 20, 28, 4, cuda)
+    bias = torch.randn(160, device=cuda)
+    net, inp = G.ctx_split(raw, bias, 96, 64)
+    full = raw + bias[None, :, None, None]
+    assert torch.equal(net, torch.tanh(full[:, :96])) and torch.equal(inp, torch.relu(full[:, 96:]))
+    assert net.is_contiguous(memory_format=torch.channels_last) and inp.is_contiguous(memory_format=torch.channels_last)

@@ -334,12 +334,14 @@ def test_gpu_export_from_raw_scans_with_loader_threads(cuda, tmp_path):
                                  compress_on_gpu=True, loader_workers=2)
     assert out["pairs"] == 7 and out["files"] == 7 and out["d2h_bytes"] > 0
     assert out["d2h_bytes"] < 0.5 * 7 * 6 * WORKLOADS["T"]["img_grid_size"][0] * WORKLOADS["T"]["img_grid_size"][1] * 4
-    for i in (0, 4, 6):
-        _, s0, s1 = ds[i]
+    for chunk in ((0, 1, 2), (3, 4, 5), (6, 6, 6)):  # the export's batches (the ragged last one padded with its last sample)
+        items = [ds[i] for i in chunk]
         with torch.no_grad():
-            pf, pb = model(preprocess_scans([s0["pcl_full_w_ground_ta"].to(cuda)], cfg),
-                           preprocess_scans([s1["pcl_full_w_ground_ta"].to(cuda)], cfg), None)
-        z = np.load(os.path.join(str(tmp_path), "%06d.npz" % i))
-        assert np.array_equal(z["bev_raw_flow_t0_t1"], pf[-1].modified_network_output.static_flow[0].cpu().numpy())
-        assert np.array_equal(z["bev_dynamicness_t1_t0"], pb[-1].modified_network_output.dynamicness[0].cpu().numpy())
-        assert float(np.abs(z["bev_raw_flow_t0_t1"]).sum()) > 0
+            pf, pb = model(preprocess_scans([it[1]["pcl_full_w_ground_ta"].to(cuda) for it in items], cfg),
+                           preprocess_scans([it[2]["pcl_full_w_ground_ta"].to(cuda) for it in items], cfg), None)
+        for b, i in enumerate(chunk):
+            z = np.load(os.path.join(str(tmp_path), "%06d.npz" % i))
+            assert np.array_equal(z["bev_raw_flow_t0_t1"], pf[-1].modified_network_output.static_flow[b].cpu().numpy()), i
+            assert np.array_equal(z["bev_dynamicness_t1_t0"], pb[-1].modified_network_output.dynamicness[b].cpu().numpy()), i
+            assert float(np.abs(z["bev_raw_flow_t0_t1"]).sum()) > 0
+    assert sorted(os.listdir(str(tmp_path))) == ["%06d.npz" % i for i in range(7)]
