@@ -374,11 +374,14 @@ def main():
             n_pad = int(self.s0["pcl_ta"]["pcl"].shape[1])
             L = _lib.CorrLayout()
             lib.slimb200_corr_layout_init(B, 128, H // 8, Wd // 8, 4, C.byref(L))
-            enc_bytes = sum(n_pts) * 16 + B * 65 * H * Wd * 4
+            # frames per pillar-encoder call: both frames of the pairs go through ONE call (RAFT.batched_frame_encoding)
+            per_call = 2 if getattr(self.model.raft_network, "batched_frame_encoding", False) else 1
+            n_pts1 = [t.shape[0] for t in self.s1["pcl_full_no_ground_ta"]]
+            enc_bytes = (sum(n_pts) + (sum(n_pts1) if per_call == 2 else 0)) * 16 + per_call * B * 65 * H * Wd * 4
             look_read = B * nf * 4 * 8 * 32
             alg = {
-                _lib.K_TILE_ENCODE: dict(bytes=enc_bytes, what="points read + canvas NCHW (zeros incl.) + occupancy written, B frames per launch"),
-                _lib.K_PILLAR_NHWC: dict(bytes=enc_bytes, what="points read + canvas channels-last (zeros incl.) + occupancy written, B frames per launch"),
+                _lib.K_TILE_ENCODE: dict(bytes=enc_bytes, what="points read + canvas NCHW (zeros incl.) + occupancy written, %d x B frames per launch" % per_call),
+                _lib.K_PILLAR_NHWC: dict(bytes=enc_bytes, what="points read + canvas channels-last (zeros incl.) + occupancy written, %d x B frames per launch" % per_call),
                 _lib.K_CORR_GEMM: dict(bytes=B * nf * L.n_cols * 2 + B * (nf + L.n_cols) * 128 * 2, flops=2.0 * B * nf * L.n_cols * 128,
                                        what="bf16 pyramid written + bf16 operands read, B samples per launch"),
                 _lib.K_DECODE_BEV: dict(bytes=B * H * Wd * (8 * 4 + 1 + 16 * 4 + 3),
@@ -431,6 +434,7 @@ def main():
                 stages["pillar"] = {"bound": "hbm", "kernel": by_id[enc_id]["kernel"], "achieved": by_id[enc_id]["achieved"],
                                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": by_id[enc_id]["frac"], "avg_launch_ms": by_id[enc_id]["avg_ms"],
                                     "traffic": by_id[enc_id]["traffic"], "algorithmic_bytes_per_launch": enc_bytes,
+                                    "frames_per_launch": per_call * B,
                                     "stage_incl_prep": {"launches": len(prep) + 1, "ms": t_stage, "achieved": gbs, "frac": gbs / peaks["hbm_gbs"],
                                                         "kernels": [by_id[k]["kernel"] for k in prep + [enc_id]]}}
             if _lib.K_CORR_GEMM in prof:

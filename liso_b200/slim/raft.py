@@ -399,6 +399,7 @@ class RAFT(nn.Module):
         self.fuse_lookup_conv = False
         # forward and backward direction as two parallel branches of the CUDA graph
         self.concurrent_directions = True
+        self.batched_frame_encoding = True  # every frame of a pass through one pillar-encoder call (eval-mode BatchNorm)
         # consumer of the per-iteration network outputs, e.g. SLIM's output decoder: called as
         # output_sink(direction, iteration, net_out, occupancy) right behind the kernel that wrote `net_out`.  While the
         # CUDA graph is captured it runs on a forked stream, i.e. the decodes become side branches of the graph that
@@ -437,8 +438,18 @@ class RAFT(nn.Module):
         kw = {"raw_scan": True} if raw_scans else {}  # (the reference signature is forward(pcl, img=None))
         pairs = [(int(a), int(b)) for a, b in pairs]
         dev = pcls[0][0].device
+        B = len(pcls[0])
+        # all frames through ONE pillar-encoder call (5 launches whatever the number of frames: the key / scan / rank
+        # kernels in front of the canvas writer are latency-bound, so their cost is per call, not per frame).  Not in
+        # train-mode BatchNorm, whose batch statistics are per reference call (pcl_to_feature_grid.py:86-107).
+        one_call = (self.batched_frame_encoding and not self.pp_layer.training and all(len(p) == B for p in pcls)
+                    and B * len(pcls) <= _lib_module.MAX_BATCH and hasattr(self.pp_layer, "empty_outputs"))
         if not self.will_use_graph(*pcls):
-            enc = [self.pp_layer(p, **kw) for p in pcls]
+            if one_call and dev.type == "cuda":
+                canvas, occ = self.pp_layer([t for p in pcls for t in p], **kw)
+                enc = [(canvas[f * B:(f + 1) * B], occ[f * B:(f + 1) * B]) for f in range(len(pcls))]
+            else:
+                enc = [self.pp_layer(p, **kw) for p in pcls]
             outs = self._net_body_frames([e[0] for e in enc], [e[1] for e in enc], pairs)
             return outs, [e[1] for e in enc]
 
@@ -446,7 +457,6 @@ class RAFT(nn.Module):
         # its canvases straight into the graph's static inputs; ~800 launches per step become one graph launch.
         # The captured kernels hold raw pointers to the weights (and to cached concatenations of them): any in-place
         # update or re-allocation of a parameter invalidates the graph.
-        B = len(pcls[0])
         wsig = tuple((p.data_ptr(), p._version) for mod in (self.fnet, self.cnet, self.update_block) for p in mod.parameters())
         key = (B, self.output_iterations, self.pp_layer.canvas_memory_format, str(dev), torch.backends.cudnn.allow_tf32, self.training,
                self.fused_update_block, self.merge_parallel_convs, self.tap_heads, self.concurrent_directions, FAST_STOCK_OPS,
@@ -458,9 +468,14 @@ class RAFT(nn.Module):
         if st is not None and st["key"] != key:
             st = None  # (the old graph and its buffers are released when the slot is overwritten)
         if st is None:
-            st = {"key": key, "in": [self.pp_layer.empty_outputs(B, dev) for _ in pcls], "pairs": pairs, "slot": slot}
-        for f, p in enumerate(pcls):
-            self.pp_layer(p, out=st["in"][f], **kw)
+            big = self.pp_layer.empty_outputs(B * len(pcls), dev)  # the frames' canvases are batch slices of one buffer
+            st = {"key": key, "in_all": big, "in": [(big[0][f * B:(f + 1) * B], big[1][f * B:(f + 1) * B]) for f in range(len(pcls))],
+                  "pairs": pairs, "slot": slot}
+        if one_call:
+            self.pp_layer([t for p in pcls for t in p], out=st["in_all"], **kw)
+        else:
+            for f, p in enumerate(pcls):
+                self.pp_layer(p, out=st["in"][f], **kw)
         if "graph" not in st:
             self._capture_net_graph(st, dev)
         st["graph"].replay()
