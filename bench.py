@@ -134,6 +134,42 @@ def run_oracle_pairs(cfg, sd, s0, s1, n_runs, warmup, min_seconds=0.0, max_runs=
     return out, times
 
 
+def pin_rank_to_local_cores(local_rank: int, world: int, dist):
+    """Scaling hygiene: give every rank its own share of the host cores, taken from the cores LOCAL to its GPU (PCI topology,
+    /sys/bus/pci/devices/<gpu>/local_cpulist).  Launch thread, loader and writer threads of one rank then never migrate onto
+    another rank's cores or across a socket.  Ranks whose GPUs share a core list split it evenly.  Returns what was done."""
+    try:
+        avail = sorted(os.sched_getaffinity(0))
+        pr = torch.cuda.get_device_properties(local_rank)
+        addr = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        local = []
+        try:
+            for part in open("/sys/bus/pci/devices/%s/local_cpulist" % addr).read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                local += list(range(int(lo), int(hi or lo) + 1))
+        except (OSError, ValueError):
+            pass
+        cores = [c for c in local if c in set(avail)] or avail
+        sig = ",".join(map(str, cores))
+        sigs = [None] * world
+        if world > 1:
+            dist.all_gather_object(sigs, sig)
+        else:
+            sigs = [sig]
+        rank = dist.get_rank() if world > 1 else 0
+        peers = [r for r in range(world) if sigs[r] == sig]
+        k, n = peers.index(rank), len(peers)
+        per = max(1, len(cores) // n)
+        mine = cores[k * per:(k + 1) * per] if k < n - 1 else cores[k * per:]
+        if not mine:
+            return {"pinned": False, "why": "no cores left for this rank"}
+        os.sched_setaffinity(0, mine)
+        torch.set_num_threads(max(1, len(mine)))
+        return {"pinned": True, "gpu_pci": addr, "gpu_local_cores": len(cores), "cores": "%d-%d (%d)" % (mine[0], mine[-1], len(mine))}
+    except Exception as e:  # never fail the bench over affinity
+        return {"pinned": False, "why": repr(e)[:200]}
+
+
 class _QuietStdout:
     """Route everything written to fd 1 (NCCL banners, library chatter) to stderr; `emit` prints the ONE JSON line."""
 
@@ -248,6 +284,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
+    affinity = pin_rank_to_local_cores(local_rank, world, dist) if world > 1 else {"pinned": False, "why": "single rank"}
+    n_cpu_rank = len(os.sched_getaffinity(0))
     torch.backends.cudnn.allow_tf32 = args.conv_precision != "fp32"
     torch.backends.cuda.matmul.allow_tf32 = args.conv_precision != "fp32"
     torch.backends.cudnn.benchmark = True
@@ -523,7 +561,7 @@ def main():
         base = args.export_dir or tempfile.mkdtemp(prefix="slimb200_export_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
         main.set_decode("last")  # the export reads the last iteration only (experiment.py:391-399); identical exported tensors
         main.model.outputs_alias_static_buffers = True
-        n_cpu = os.cpu_count() or 1
+        n_cpu = n_cpu_rank * world if affinity.get("pinned") else (os.cpu_count() or 1)
         loaders = max(2, min(6, n_cpu // max(1, world) - 2))
         writers = max(2, min(8, n_cpu // max(1, world) - 1))
         export_line = {"what": "run_flow_export over distinct synthetic KITTI-sized samples (pool of ray-cast scenes, per-sample rigid motion), "
@@ -571,13 +609,16 @@ def main():
     # per-rank step times (scaling hygiene: who is the straggler)
     per_rank = None
     if world > 1:
+        aff_all = [None] * world
+        dist.all_gather_object(aff_all, affinity)
         mine_t = torch.tensor([ms_res / args.steps, ms_e2e / args.steps], dtype=torch.float64, device=dev)
         allt = [torch.zeros_like(mine_t) for _ in range(world)]
         dist.all_gather(allt, mine_t)
         res_t, e2e_t = [float(t[0]) for t in allt], [float(t[1]) for t in allt]
         per_rank = {"ms_per_step": [round(v, 4) for v in res_t], "e2e_ms_per_step": [round(v, 4) for v in e2e_t],
                     "slowest_rank": int(np.argmax(res_t)), "slowest_rank_e2e": int(np.argmax(e2e_t)),
-                    "min_ms": min(res_t), "max_ms": max(res_t), "e2e_min_ms": min(e2e_t), "e2e_max_ms": max(e2e_t)}
+                    "min_ms": min(res_t), "max_ms": max(res_t), "e2e_min_ms": min(e2e_t), "e2e_max_ms": max(e2e_t),
+                    "cpu_affinity": aff_all}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -285,6 +285,16 @@ size_t slimb200_instnorm_workspace_bytes(int32_t batch, int32_t channels, int32_
 int slimb200_instnorm_nhwc(const float* x, const float* gamma, const float* beta, float eps, int32_t batch,
                            int32_t height, int32_t width, int32_t channels, int32_t relu, const float* residual,
                            float* out, void* workspace, size_t workspace_bytes, void* stream);
+/* The same for a channel SLICE of a wider channels-last tensor: x points at the slice's first channel, x_pitch = channels
+ * per pixel of the whole tensor (x_pitch == channels: identical to slimb200_instnorm_nhwc); out is packed (channels per
+ * pixel) and must not alias x when x_pitch != channels.  Used for one half of two parallel convolutions evaluated as one. */
+int slimb200_instnorm_nhwc_slice(const float* x, int32_t x_pitch, const float* gamma, const float* beta, float eps, int32_t batch,
+                                 int32_t height, int32_t width, int32_t channels, int32_t relu, const float* residual, float* out,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+/* out (pixels, channels) packed = relu(x[:, slice] + bias): the other half (a convolution followed by ReLU, extractor.py:
+ * 262-266 with norm_fn "none"), evaluated without its bias inside the stacked convolution. */
+int slimb200_bias_relu_slice(const float* x, int32_t x_pitch, const float* bias, int32_t channels, int64_t pixels, float* out,
+                             void* stream);
 
 /* SURVEY 8(f).2 glue between the stock convolutions of the ConvGRU update block (liso/slim/model/update.py:23-38,
  * 70-93,130-150; raft_mod.py:188-212), all on channels-last fp32 tensors given as (pixels = batch*h*w, channels) rows.
@@ -427,6 +437,7 @@ enum {
   SLIMB200_K_DEFLATE_SCAN,
   SLIMB200_K_DEFLATE_GATHER,
   SLIMB200_K_CTX_SPLIT,
+  SLIMB200_K_BIAS_RELU_SLICE,
   SLIMB200_N_KERNELS
 };
 int slimb200_profile_begin(void);

@@ -239,6 +239,20 @@ __global__ void __launch_bounds__(GL_THREADS) k_ctx_split(const float4* __restri
   }
 }
 
+// relu(x[:, c0 : c0 + C] + bias) of a channels-last tensor with `pitch` channels per pixel, packed: one half of a stacked
+// convolution (two parallel convolutions evaluated as one, without bias) handed to its consumer
+__global__ void __launch_bounds__(GL_THREADS) k_bias_relu_slice(const float4* __restrict__ x, int pitch4, const float4* __restrict__ bias,
+                                                                int c4, float4* __restrict__ out, size_t pixels) {
+  const size_t n4 = pixels * (size_t)c4;
+  for (size_t i = (size_t)blockIdx.x * GL_THREADS + threadIdx.x; i < n4; i += (size_t)gridDim.x * GL_THREADS) {
+    const size_t pix = i / (size_t)c4;
+    const int g = (int)(i - pix * (size_t)c4);
+    const float4 a = __ldg(x + pix * (size_t)pitch4 + g), b = __ldg(bias + g);
+    out[i] = make_float4(fmaxf(__fadd_rn(a.x, b.x), 0.f), fmaxf(__fadd_rn(a.y, b.y), 0.f), fmaxf(__fadd_rn(a.z, b.z), 0.f),
+                         fmaxf(__fadd_rn(a.w, b.w), 0.f));
+  }
+}
+
 inline bool mis16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) != 0; }
 
 }  // namespace
@@ -412,5 +426,19 @@ extern "C" int slimb200_ctx_split(const float* raw, const float* bias, int32_t h
                   (k_ctx_split<<<grid_for((size_t)pixels * (hidden + context) / 4, 4), GL_THREADS, 0, stream>>>(
                       reinterpret_cast<const float4*>(raw), reinterpret_cast<const float4*>(bias), hidden / 4, context / 4,
                       reinterpret_cast<float4*>(net), reinterpret_cast<float4*>(inp), (size_t)pixels)));
+  return SLIMB200_OK;
+}
+
+extern "C" int slimb200_bias_relu_slice(const float* x, int32_t x_pitch, const float* bias, int32_t channels, int64_t pixels,
+                                        float* out, void* stream_) {
+  if (!x || !bias || !out || pixels < 0 || channels < 4 || x_pitch < channels) return SLIMB200_E_INVALID;
+  if ((channels & 3) || (x_pitch & 3)) return SLIMB200_E_UNSUPPORTED;
+  if (mis16(x) || mis16(bias) || mis16(out)) return SLIMB200_E_ALIGNMENT;
+  if (pixels == 0) return SLIMB200_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SLIMB200_LAUNCH(SLIMB200_K_BIAS_RELU_SLICE, stream,
+                  (k_bias_relu_slice<<<grid_for((size_t)pixels * channels / 4, 4), GL_THREADS, 0, stream>>>(
+                      reinterpret_cast<const float4*>(x), x_pitch / 4, reinterpret_cast<const float4*>(bias), channels / 4,
+                      reinterpret_cast<float4*>(out), (size_t)pixels)));
   return SLIMB200_OK;
 }

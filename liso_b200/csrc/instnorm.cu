@@ -27,6 +27,7 @@ struct InArgs {
   float* partial;   // [batch][slabs][C][3] (count, mean, M2)
   float* scale_shift;  // [batch][C][2]
   int batch, hw, C, slabs, relu;
+  int xpitch;  // floats between consecutive pixels of x (== C for a packed tensor, larger for a channel slice)
   float eps;
 };
 
@@ -76,12 +77,13 @@ __global__ void __launch_bounds__(IN_THREADS, 6) k_in_stats(const InArgs a) {
   float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
   float K[4] = {0.f, 0.f, 0.f, 0.f};
   if (lo < hi && p < P) {
-    const float4* src = reinterpret_cast<const float4*>(a.x + (size_t)b * a.hw * a.C) + g;
-    const float4 k4 = __ldg(src + (size_t)lo * G);
+    const int XG = a.xpitch >> 2;
+    const float4* src = reinterpret_cast<const float4*>(a.x + (size_t)b * a.hw * a.xpitch) + g;
+    const float4 k4 = __ldg(src + (size_t)lo * XG);
     K[0] = k4.x; K[1] = k4.y; K[2] = k4.z; K[3] = k4.w;
 #pragma unroll 8
     for (int i = lo + p; i < hi; i += P) {
-      const float4 v = __ldg(src + (size_t)i * G);
+      const float4 v = __ldg(src + (size_t)i * XG);
       const float xs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(IN_THREADS, 6) k_in_stats(const InArgs a) {
     double mean = 0.0, M2 = 0.0;
     if (n > 0) {
       // the thread that loaded channel c's shift is (p = 0, g = gg): same value in every lane of the group
-      const double Kc = (double)__ldg(a.x + ((size_t)b * a.hw + lo) * a.C + c);
+      const double Kc = (double)__ldg(a.x + ((size_t)b * a.hw + lo) * a.xpitch + c);
       mean = Kc + S1 / n;
       M2 = fmax(S2 - S1 * S1 / n, 0.0);
     }
@@ -133,13 +135,14 @@ __global__ void __launch_bounds__(IN_THREADS) k_in_apply(const InArgs a) {
   const int G = a.C >> 2;
   const size_t per_sample = (size_t)a.hw * G;
   const int b = blockIdx.y;
-  const float4* src = reinterpret_cast<const float4*>(a.x) + (size_t)b * per_sample;
+  const int XG = a.xpitch >> 2;
+  const float4* src = reinterpret_cast<const float4*>(a.x) + (size_t)b * a.hw * XG;
   float4* dst = reinterpret_cast<float4*>(a.out) + (size_t)b * per_sample;
   const float4* res = a.residual ? reinterpret_cast<const float4*>(a.residual) + (size_t)b * per_sample : nullptr;
   const float* ss = a.scale_shift + (size_t)b * a.C * 2;
   for (size_t i = (size_t)blockIdx.x * IN_THREADS + threadIdx.x; i < per_sample; i += (size_t)gridDim.x * IN_THREADS) {
     const int g = (int)(i % G);
-    const float4 v = __ldg(src + i);
+    const float4 v = __ldg(XG == G ? src + i : src + (i / G) * XG + g);
     const float4 s0 = __ldg(reinterpret_cast<const float4*>(ss + g * 8));      // scale0 shift0 scale1 shift1
     const float4 s1 = __ldg(reinterpret_cast<const float4*>(ss + g * 8 + 4));  // scale2 shift2 scale3 shift3
     float4 o;
@@ -187,11 +190,13 @@ extern "C" size_t slimb200_instnorm_workspace_bytes(int32_t batch, int32_t chann
   return w.used();
 }
 
-extern "C" int slimb200_instnorm_nhwc(const float* x, const float* gamma, const float* beta, float eps, int32_t batch,
-                                      int32_t height, int32_t width, int32_t channels, int32_t relu, const float* residual,
-                                      float* out, void* workspace, size_t workspace_bytes, void* stream_) {
+extern "C" int slimb200_instnorm_nhwc_slice(const float* x, int32_t x_pitch, const float* gamma, const float* beta, float eps,
+                                            int32_t batch, int32_t height, int32_t width, int32_t channels, int32_t relu,
+                                            const float* residual, float* out, void* workspace, size_t workspace_bytes,
+                                            void* stream_) {
   if (!x || !gamma || !beta || !out || !workspace || batch < 1 || height < 1 || width < 1) return SLIMB200_E_INVALID;
-  if (channels < 4 || (channels & 3) || channels > IN_THREADS) return SLIMB200_E_UNSUPPORTED;
+  if (channels < 4 || (channels & 3) || channels > IN_THREADS || x_pitch < channels || (x_pitch & 3)) return SLIMB200_E_UNSUPPORTED;
+  if (x_pitch != channels && out == x) return SLIMB200_E_INVALID;  // a slice cannot be normalised in place (out is packed)
   const long long hw = (long long)height * width;
   if (hw > 0x7fffffffLL) return SLIMB200_E_UNSUPPORTED;
   if (workspace_bytes < slimb200_instnorm_workspace_bytes(batch, channels, (int)hw)) return SLIMB200_E_WORKSPACE;
@@ -200,6 +205,7 @@ extern "C" int slimb200_instnorm_nhwc(const float* x, const float* gamma, const 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   InArgs a{};
   a.x = x;
+  a.xpitch = x_pitch;
   a.gamma = gamma;
   a.beta = beta;
   a.residual = residual;
@@ -220,4 +226,11 @@ extern "C" int slimb200_instnorm_nhwc(const float* x, const float* gamma, const 
   const unsigned gx = (unsigned)((per_sample + IN_THREADS * 4 - 1) / (IN_THREADS * 4) < 148 * 4 ? (per_sample + IN_THREADS * 4 - 1) / (IN_THREADS * 4) : 148 * 4);
   SLIMB200_LAUNCH(SLIMB200_K_IN_APPLY, stream, (k_in_apply<<<dim3(gx, batch), IN_THREADS, 0, stream>>>(a)));
   return SLIMB200_OK;
+}
+
+extern "C" int slimb200_instnorm_nhwc(const float* x, const float* gamma, const float* beta, float eps, int32_t batch,
+                                      int32_t height, int32_t width, int32_t channels, int32_t relu, const float* residual,
+                                      float* out, void* workspace, size_t workspace_bytes, void* stream_) {
+  return slimb200_instnorm_nhwc_slice(x, channels, gamma, beta, eps, batch, height, width, channels, relu, residual, out, workspace,
+                                      workspace_bytes, stream_);
 }

@@ -87,7 +87,7 @@ extern "C" const char* slimb200_kernel_name(int32_t kernel_id) {
       "k_point_keys", "k_scan_local", "k_scan_global", "k_rank_scatter", "k_tile_encode_stats", "k_bn_finalize",
       "k_tile_encode", "k_pillar_nhwc", "k_nchw_to_pixel_major", "k_feat_pack", "k_corr_gemm_tcgen05", "k_corr_lookup", "k_pillar_coors_f64", "k_decode_min", "k_decode_bev", "k_decode_points", "k_kabsch_finalize",
       "k_decode_aggr", "k_raft_output", "k_pre_count", "k_pre_scan", "k_pre_scatter", "k_pre_pad", "k_kabsch_moments", "k_in_stats", "k_in_finalize", "k_in_apply",
-      "k_nhwc_pack", "k_gru_gate_zr", "k_gru_gate_out", "k_iter_update", "k_add_relu", "k_lookup_conv_tf32", "k_lookup_conv_pack", "k_deflate_tables", "k_deflate_chunks", "k_deflate_scan", "k_deflate_gather", "k_ctx_split"};
+      "k_nhwc_pack", "k_gru_gate_zr", "k_gru_gate_out", "k_iter_update", "k_add_relu", "k_lookup_conv_tf32", "k_lookup_conv_pack", "k_deflate_tables", "k_deflate_chunks", "k_deflate_scan", "k_deflate_gather", "k_ctx_split", "k_bias_relu_slice"};
   return (kernel_id >= 0 && kernel_id < SLIMB200_N_KERNELS) ? names[kernel_id] : "?";
 }
 

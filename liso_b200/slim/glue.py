@@ -205,6 +205,21 @@ def ctx_split(raw: torch.Tensor, bias: torch.Tensor, hidden: int, context: int):
     return net, inp
 
 
+@_lib.on_device_of_args
+def bias_relu_slice(x: torch.Tensor, c0: int, channels: int, bias: torch.Tensor) -> torch.Tensor:
+    """``relu(x[:, c0 : c0 + channels] + bias)`` of a channels-last tensor as a packed channels-last tensor: one half of two
+    parallel convolutions evaluated as one (without bias)."""
+    _lib.require_cuda(x, bias)
+    B, Cx, h, w = x.shape
+    if c0 % 4 or channels % 4 or c0 + channels > Cx or x.dtype != torch.float32 or bias.numel() != channels \
+            or not x.is_contiguous(memory_format=torch.channels_last):
+        raise ValueError("bias_relu_slice: channels-last fp32 tensor, slice bounds multiples of 4, bias of `channels` elements")
+    out = torch.empty((B, channels, h, w), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+    _lib.check(_lib.load().slimb200_bias_relu_slice(x.data_ptr() + 4 * c0, Cx, bias.detach().contiguous().data_ptr(), channels,
+                                                    B * h * w, out.data_ptr(), _lib.current_stream_ptr()))
+    return out
+
+
 def add_relu_ok(x: torch.Tensor, y: torch.Tensor) -> bool:
     return (x.is_cuda and y.is_cuda and x.dtype == torch.float32 and y.dtype == torch.float32 and x.shape == y.shape
             and x.stride() == y.stride() and (x.is_contiguous() or x.is_contiguous(memory_format=torch.channels_last))

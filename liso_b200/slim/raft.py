@@ -126,21 +126,28 @@ def _stacked_params(a: nn.Conv2d, b: nn.Conv2d, shared_input: bool, pad_in_to: i
 
 @_lib_module.on_device_of_args
 def instance_norm_nhwc(norm: nn.InstanceNorm2d, x: torch.Tensor, relu: bool, residual: torch.Tensor = None,
-                       inplace: bool = False) -> torch.Tensor:
+                       inplace: bool = False, channel_slice=None) -> torch.Tensor:
     """Affine InstanceNorm2d (+ ReLU) of a channels-last CUDA tensor in the library's glue kernel
     (``slimb200_instnorm_nhwc``): 3 launches / 2 passes instead of copy-to-NCHW + cuDNN batch-norm + copy back + clamp.
     With ``residual`` the block's join is fused into the same pass: ``relu(residual + [relu](norm(x)))``.
-    ``inplace`` overwrites ``x`` (a convolution output nobody else reads): half the L2 footprint of the apply pass."""
+    ``inplace`` overwrites ``x`` (a convolution output nobody else reads): half the L2 footprint of the apply pass.
+    ``channel_slice=(c0, C)``: normalise channels [c0, c0 + C) of ``x`` only, into a packed C-channel tensor."""
     lib = _lib_mod().load()
     if not x.is_contiguous(memory_format=torch.channels_last):
         x = x.contiguous(memory_format=torch.channels_last)
-    B, Cn, H, W = x.shape
-    out = x if inplace else torch.empty_like(x)  # (empty_like preserves the channels-last strides)
+    B, Cx, H, W = x.shape
+    c0, Cn = (0, Cx) if channel_slice is None else channel_slice
+    if channel_slice is not None:
+        assert not inplace and c0 % 4 == 0 and Cn % 4 == 0 and c0 + Cn <= Cx
+        out = torch.empty((B, Cn, H, W), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+    else:
+        out = x if inplace else torch.empty_like(x)  # (empty_like preserves the channels-last strides)
     ws = torch.empty(max(256, lib.slimb200_instnorm_workspace_bytes(B, Cn, H * W)), dtype=torch.uint8, device=x.device)
     flags = (1 if relu else 0) | (2 if residual is not None else 0)
-    _lib_mod().check(lib.slimb200_instnorm_nhwc(x.data_ptr(), norm.weight.data_ptr(), norm.bias.data_ptr(), float(norm.eps), B, H, W,
-                                                Cn, flags, residual.data_ptr() if residual is not None else None, out.data_ptr(),
-                                                ws.data_ptr(), ws.numel(), _lib_mod().current_stream_ptr()))
+    _lib_mod().check(lib.slimb200_instnorm_nhwc_slice(
+        x.data_ptr() + 4 * c0, Cx, norm.weight.data_ptr(), norm.bias.data_ptr(), float(norm.eps), B, H, W, Cn, flags,
+        residual.data_ptr() if residual is not None else None, out.data_ptr(), ws.data_ptr(), ws.numel(),
+        _lib_mod().current_stream_ptr()))
     return out
 
 
@@ -259,10 +266,14 @@ class SmallEncoder(nn.Module):
             ResidualBlock(cout, cout, dummy_in_filters=cin, norm_fn=self.norm_fn, stride=1),
         )
 
-    def forward(self, x, head_bias: bool = True):
+    def forward(self, x, head_bias: bool = True, stem_out: torch.Tensor = None):
         """``head_bias=False``: the output convolution is evaluated without its bias (the caller adds it in a kernel of
-        its own, see ``RAFT._context``); not available with dropout."""
-        x = conv_relu(self.conv1, x) if _is_identity(self.norm1) else conv_norm(self.conv1, self.norm1, x, relu=True)
+        its own, see ``RAFT._context``); not available with dropout.  ``stem_out``: the result of the stem
+        (relu(norm1(conv1(x)))) when the caller has computed it already (``RAFT._stems``)."""
+        if stem_out is not None:
+            x = stem_out
+        else:
+            x = conv_relu(self.conv1, x) if _is_identity(self.norm1) else conv_norm(self.conv1, self.norm1, x, relu=True)
         x = self.layer3(self.layer2(self.layer1(x)))
         if not head_bias:
             assert not (self.training and self.dropout is not None)
@@ -399,6 +410,7 @@ class RAFT(nn.Module):
         self.fuse_lookup_conv = False
         # forward and backward direction as two parallel branches of the CUDA graph
         self.concurrent_directions = True
+        self.stacked_stems = True  # fnet / cnet 7x7 stems on the same canvas as one stacked convolution
         self.batched_frame_encoding = True  # every frame of a pass through one pillar-encoder call (eval-mode BatchNorm)
         # consumer of the per-iteration network outputs, e.g. SLIM's output decoder: called as
         # output_sink(direction, iteration, net_out, occupancy) right behind the kernel that wrote `net_out`.  While the
@@ -514,11 +526,13 @@ class RAFT(nn.Module):
         self._occupancies = [occupancies[f] for a, b in pairs for f in (a, b)]  # per direction: the SOURCE frame's occupancy
         if self.output_sink_begin is not None:
             self.output_sink_begin()
-        fmaps = [self.fnet(img) for img in imgs]
         sources = sorted({f for a, b in pairs for f in (a, b)})
-        ctx = {}
-        for f in sources:  # context encoder of every frame a direction starts from (raft_mod.py:170-173)
-            ctx[f] = self._context(imgs[f])
+        fmaps, ctx = [None] * len(imgs), {}
+        for f, img in enumerate(imgs):
+            stems = self._stems(img) if f in sources else None  # a frame that needs both encoders: one stacked stem convolution
+            fmaps[f] = self.fnet(img, stem_out=stems[0]) if stems is not None else self.fnet(img)
+            if f in sources:  # context encoder of every frame a direction starts from (raft_mod.py:170-173)
+                ctx[f] = self._context(img, stem_out=stems[1] if stems is not None else None)
         dirs = [(a, b) for a, b in pairs for a, b in ((a, b), (b, a))]
         outs = [None] * len(dirs)
 
@@ -545,7 +559,32 @@ class RAFT(nn.Module):
             run(k)
         return outs
 
-    def _context(self, img):
+    def _stems(self, img):
+        """The 7x7 / 2 stems of the feature and the context encoder on the same canvas (``extractor.py:262-266``, called from
+        ``raft_mod.py:140-173``) as ONE stock convolution with the output channels stacked [fnet | cnet]: both read the
+        105 MB canvas, and 32 output channels fill only half of the tensor-core tile cuDNN picks -- the stacked convolution
+        costs about what one of them does.  The feature half goes through the sliced InstanceNorm + ReLU kernel (its bias
+        is a per-channel constant the normalisation removes), the context half through bias + ReLU.  Returns (stem output
+        for fnet, stem output for cnet) or None when the layout / module types do not allow it."""
+        fn, cn = self.fnet, self.cnet
+        if not (self.stacked_stems and FAST_STOCK_OPS and img.is_cuda and img.dtype == torch.float32 and not torch.is_grad_enabled()
+                and not torch.is_autocast_enabled() and isinstance(fn, SmallEncoder) and isinstance(cn, SmallEncoder)
+                and _same_geometry(fn.conv1, cn.conv1) and fn.conv1.in_channels == cn.conv1.in_channels
+                and _is_identity(cn.norm1) and cn.conv1.bias is not None and fn.conv1.out_channels % 4 == 0
+                and cn.conv1.out_channels % 4 == 0 and img.is_contiguous(memory_format=torch.channels_last)
+                and _fused_norm_ok(fn.norm1, img, fn.conv1.out_channels)):
+            return None
+        c = fn.conv1
+        w = _cat_params(self, "stem.weight", (fn.conv1.weight, cn.conv1.weight))
+        raw = F.conv2d(img, w, None, c.stride, c.padding, c.dilation, c.groups)
+        if not raw.is_contiguous(memory_format=torch.channels_last):
+            raw = raw.contiguous(memory_format=torch.channels_last)
+        nf, nc = fn.conv1.out_channels, cn.conv1.out_channels
+        xf = instance_norm_nhwc(fn.norm1, raw, relu=True, channel_slice=(0, nf))
+        xc = _glue().bias_relu_slice(raw, nf, nc, cn.conv1.bias)
+        return xf, xc
+
+    def _context(self, img, stem_out=None):
         """(tanh(net), relu(inp)) of the context encoder (``raft_mod.py:170-173``).  On the channels-last inference path the
         bias of cnet's output convolution, the split, tanh and relu are ONE glue launch (``slimb200_ctx_split``) instead of
         ATen's bias pass + tanh + clamp."""
@@ -553,12 +592,12 @@ class RAFT(nn.Module):
         if (FAST_STOCK_OPS and img.is_cuda and img.dtype == torch.float32 and not torch.is_grad_enabled()
                 and not torch.is_autocast_enabled() and isinstance(cn, SmallEncoder) and cn.conv2.bias is not None
                 and not (cn.training and cn.dropout is not None) and self.hidden_dim % 4 == 0 and self.context_dim % 4 == 0):
-            raw = cn(img, head_bias=False)
+            raw = cn(img, head_bias=False, stem_out=stem_out)
             if raw.dtype == torch.float32 and raw.is_contiguous(memory_format=torch.channels_last):
                 return _glue().ctx_split(raw, cn.conv2.bias, self.hidden_dim, self.context_dim)
             raw = raw + cn.conv2.bias[None, :, None, None]
         else:
-            raw = cn(img)
+            raw = cn(img, stem_out=stem_out)
         net, inp = torch.split(raw, [self.hidden_dim, self.context_dim], dim=1)
         return torch.tanh(net), torch.relu(inp)
 

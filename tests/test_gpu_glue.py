@@ -180,3 +180,45 @@ def test_context_split(cuda):
     full = raw + bias[None, :, None, None]
     assert torch.equal(net, torch.tanh(full[:, :96])) and torch.equal(inp, torch.relu(full[:, 96:]))
     assert net.is_contiguous(memory_format=torch.channels_last) and inp.is_contiguous(memory_format=torch.channels_last)
+
+
+def test_sliced_instance_norm_and_bias_relu(cuda):
+    """The two halves of a stacked stem convolution: InstanceNorm + ReLU of a channel slice == the packed kernel on a copy of
+    the slice (bit for bit), bias + ReLU of the other slice == the stock expression."""
+    from liso_b200.slim import glue as G
+
+    raw = _nhwc(3, 64, 40, 56, 11, cuda)
+    norm = torch.nn.InstanceNorm2d(32, eps=1e-3, affine=True).to(cuda)
+    with torch.no_grad():
+        norm.weight.uniform_(0.5, 1.5)
+        norm.bias.uniform_(-0.5, 0.5)
+        a = R.instance_norm_nhwc(norm, raw, relu=True, channel_slice=(0, 32))
+        b = R.instance_norm_nhwc(norm, raw[:, :32].contiguous(memory_format=torch.channels_last), relu=True)
+        ref = F.relu(norm(raw[:, :32]))
+    assert torch.equal(a, b) and a.is_contiguous(memory_format=torch.channels_last)
+    assert float((a - ref).abs().max()) < 1e-5
+    bias = torch.randn(32, device=cuda)
+    c = G.bias_relu_slice(raw, 32, 32, bias)
+    assert torch.equal(c, F.relu(raw[:, 32:] + bias[None, :, None, None]))
+
+
+def test_stacked_stems_equal_separate_encoders(cuda):
+    """RAFT._stems: fnet / cnet stems as one stacked convolution -> the encoders' outputs equal the separate runs to fp32
+    round-off (the stacked convolution may pick another cuDNN algorithm; fp32 convolutions here)."""
+    from liso_b200.config import make_cfg
+    from liso_b200.slim.slim import SLIM
+    from liso_b200.weights import synth_weights_like
+
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = make_cfg("T")
+    model = SLIM(cfg).eval()
+    model.load_state_dict(synth_weights_like(model.state_dict(), 0))
+    net = model.to(cuda).to(memory_format=torch.channels_last).raft_network
+    img = torch.randn(2, 64, 256, 256, device=cuda).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        stems = net._stems(img)
+        assert stems is not None
+        f1, (n1, i1) = net.fnet(img, stem_out=stems[0]), net._context(img, stem_out=stems[1])
+        f0, (n0, i0) = net.fnet(img), net._context(img)
+    for a, b in ((f1, f0), (n1, n0), (i1, i0)):
+        assert float((a - b).abs().max()) <= 2e-5 * max(1.0, float(b.abs().max()))
