@@ -472,7 +472,7 @@ class RAFT(nn.Module):
         wsig = tuple((p.data_ptr(), p._version) for mod in (self.fnet, self.cnet, self.update_block) for p in mod.parameters())
         key = (B, self.output_iterations, self.pp_layer.canvas_memory_format, str(dev), torch.backends.cudnn.allow_tf32, self.training,
                self.fused_update_block, self.merge_parallel_convs, self.tap_heads, self.concurrent_directions, FAST_STOCK_OPS,
-               self.fuse_lookup_conv,
+               self.fuse_lookup_conv, self.stacked_stems, self.batched_frame_encoding,
                self.output_sink is not None, self.graph_extra_key, wsig)
         slot = "net" if (len(pcls), pairs) == (2, [(0, 1)]) else "net:%d:%s" % (len(pcls), pairs)
         self._last_graph_slot = slot
