@@ -326,6 +326,8 @@ int slimb200_gru_gate_zr(const float* zr_raw, const float* bias_zr, const float*
                          float* rhx, int32_t rhx_pitch, int32_t hidden, int64_t pixels, void* stream);
 int slimb200_gru_gate_out(const float* q_raw, const float* bias_q, const float* z, float* hx, int32_t hx_pitch,
                           float* h_out, int32_t hidden, int64_t pixels, void* stream);
+/* stacked (optional): copy of [flow | logits] for the stacked motion-encoder convolution, (batch, |stacked_channels|, h, w);
+ * stacked_channels > 0: planar (NCHW), < 0: channels-last with -stacked_channels channels per pixel. */
 int slimb200_iter_update(const float* dflow_raw, int64_t dflow_batch_stride, int64_t dflow_channel_stride,
                          int64_t dflow_pixel_stride, const float* bias_flow, const float* dlogits_raw,
                          int64_t dlogits_batch_stride, int64_t dlogits_channel_stride, int64_t dlogits_pixel_stride,

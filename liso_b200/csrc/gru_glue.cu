@@ -129,8 +129,8 @@ struct IterArgs {
   float* coords1;  // (batch, 2, h, w) planar
   float* flow;     // (batch, 2, h, w) planar
   float* logits;   // (batch, nl, h, w) planar
-  float* stacked;  // optional (batch, stacked_ch >= 2 + nl, h, w) planar copy [flow | logits | untouched padding channels]
-  int stacked_ch;
+  float* stacked;  // optional (batch, |stacked_ch| >= 2 + nl, h, w) copy [flow | logits | untouched padding channels]:
+  int stacked_ch;  // > 0 planar, < 0 channels-last (what the stock convolution that reads it wants)
   const float* taps;  // alternative source of the raw head outputs (see slimb200_iter_update_taps), else NULL
   int ksize;
   int batch, h, w, nl;
@@ -140,9 +140,12 @@ struct IterArgs {
 __global__ void __launch_bounds__(GL_THREADS) k_iter_update(const IterArgs a) {
   const int hw = a.h * a.w;
   const long long total = (long long)a.batch * hw;
+  const int sch = a.stacked_ch < 0 ? -a.stacked_ch : a.stacked_ch;
+  const size_t s_cs = a.stacked_ch < 0 ? 1 : (size_t)hw, s_ps = a.stacked_ch < 0 ? (size_t)sch : 1;  // channel / pixel strides
   for (long long i = (long long)blockIdx.x * GL_THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * GL_THREADS) {
     const int b = (int)(i / hw), pix = (int)(i - (long long)b * hw);
     const int row = pix / a.w, col = pix - row * a.w;
+    float* sp = a.stacked ? a.stacked + (size_t)b * sch * hw + (size_t)pix * s_ps : nullptr;
     float raw[2 + 16];
     if (a.taps) {
       // the k x k output convolution of both heads as ONE 1x1 convolution to (k*k taps) x (2 + nl) channels + this sum
@@ -177,7 +180,7 @@ __global__ void __launch_bounds__(GL_THREADS) k_iter_update(const IterArgs a) {
       *cp = nc;
       const float fl = __fsub_rn(nc, (float)(c == 0 ? col : row));  // coords0: ch0 = x, ch1 = y
       a.flow[((size_t)b * 2 + c) * hw + pix] = fl;
-      if (a.stacked) a.stacked[((size_t)b * a.stacked_ch + c) * hw + pix] = fl;
+      if (sp) sp[c * s_cs] = fl;
     }
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
@@ -186,7 +189,7 @@ __global__ void __launch_bounds__(GL_THREADS) k_iter_update(const IterArgs a) {
       float* lp = a.logits + ((size_t)b * a.nl + c) * hw + pix;
       const float nv = __fadd_rn(*lp, d);
       *lp = nv;
-      if (a.stacked) a.stacked[((size_t)b * a.stacked_ch + 2 + c) * hw + pix] = nv;
+      if (sp) sp[(2 + c) * s_cs] = nv;
     }
   }
 }
@@ -334,7 +337,7 @@ extern "C" int slimb200_iter_update(const float* dflow_raw, int64_t dflow_batch_
                                     float* coords1, float* flow, float* logits, float* stacked, int32_t stacked_channels,
                                     void* stream_) {
   if (!dflow_raw || !bias_flow || !dlogits_raw || !bias_logits || !coords1 || !flow || !logits) return SLIMB200_E_INVALID;
-  if (stacked && stacked_channels < 2 + n_logits) return SLIMB200_E_INVALID;
+  if (stacked && (stacked_channels < 0 ? -stacked_channels : stacked_channels) < 2 + n_logits) return SLIMB200_E_INVALID;
   if (batch < 1 || h < 1 || w < 1 || n_logits < 1 || n_logits > 16) return SLIMB200_E_INVALID;
   IterArgs a{};
   a.dflow = dflow_raw;
@@ -366,7 +369,7 @@ extern "C" int slimb200_iter_update_taps(const float* taps, int32_t ksize, const
                                          int32_t n_logits, int32_t batch, int32_t h, int32_t w, float* coords1, float* flow,
                                          float* logits, float* stacked, int32_t stacked_channels, void* stream_) {
   if (!taps || !bias_flow || !bias_logits || !coords1 || !flow || !logits) return SLIMB200_E_INVALID;
-  if (stacked && stacked_channels < 2 + n_logits) return SLIMB200_E_INVALID;
+  if (stacked && (stacked_channels < 0 ? -stacked_channels : stacked_channels) < 2 + n_logits) return SLIMB200_E_INVALID;
   if (batch < 1 || h < 1 || w < 1 || n_logits < 1 || n_logits > 16 || ksize < 1 || !(ksize & 1) || ksize > 7) return SLIMB200_E_INVALID;
   IterArgs a{};
   a.taps = taps;

@@ -124,6 +124,19 @@ def _head_strides(t: torch.Tensor) -> Tuple[torch.Tensor, int, int, int]:
     return t, t.stride(0), t.stride(1), 1
 
 
+def _is_nhwc(t: torch.Tensor) -> bool:
+    return t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last) and not t.is_contiguous()
+
+
+def _stacked_channels(stacked) -> int:
+    """The library's layout convention for the optional [flow | logits] copy: > 0 planar, < 0 channels-last."""
+    if stacked is None:
+        return 0
+    if stacked.dtype != torch.float32 or not stacked.is_cuda:
+        raise ValueError("stacked must be an fp32 CUDA tensor")
+    return -int(stacked.shape[1]) if _is_nhwc(stacked) else int(stacked.shape[1])
+
+
 @_lib.on_device_of_args
 def iter_update(dflow_raw: torch.Tensor, bias_flow: torch.Tensor, dlogits_raw: torch.Tensor, bias_logits: torch.Tensor,
                 coords1: torch.Tensor, flow: torch.Tensor, logits: torch.Tensor, stacked: torch.Tensor = None) -> None:
@@ -144,7 +157,7 @@ def iter_update(dflow_raw: torch.Tensor, bias_flow: torch.Tensor, dlogits_raw: t
                                                 ps_l, bias_logits.data_ptr(), logits.shape[1], B, h, w, coords1.data_ptr(),
                                                 flow.data_ptr(), logits.data_ptr(),
                                                 stacked.data_ptr() if stacked is not None else None,
-                                                stacked.shape[1] if stacked is not None else 0, _lib.current_stream_ptr()))
+                                                _stacked_channels(stacked), _lib.current_stream_ptr()))
 
 
 @_lib.on_device_of_args
@@ -164,7 +177,7 @@ def iter_update_taps(taps: torch.Tensor, ksize: int, bias_flow: torch.Tensor, bi
     _lib.check(_lib.load().slimb200_iter_update_taps(taps.data_ptr(), ksize, bias_flow.data_ptr(), bias_logits.data_ptr(), nl, B,
                                                      h, w, coords1.data_ptr(), flow.data_ptr(), logits.data_ptr(),
                                                      stacked.data_ptr() if stacked is not None else None,
-                                                     stacked.shape[1] if stacked is not None else 0, _lib.current_stream_ptr()))
+                                                     _stacked_channels(stacked), _lib.current_stream_ptr()))
 
 
 @_lib.on_device_of_args

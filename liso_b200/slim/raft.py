@@ -733,7 +733,8 @@ class RAFT(nn.Module):
             w_m2, b_m2 = _stacked_params(me.conv_flow2, me.conv_class2, shared_input=False)
             w_h1, b_h1 = _stacked_params(fh.conv1, lh.conv1, shared_input=True)
             w_h2, _ = _stacked_params(fh.conv2, lh.conv2, shared_input=False)
-            stacked = torch.zeros((batch, n_st, h, w), dtype=torch.float32, device=device)  # [flow | logits | 0]
+            # [flow | logits | 0], channels-last like the stock convolution that reads it (no layout copy per iteration)
+            stacked = torch.zeros((batch, n_st, h, w), dtype=torch.float32, device=device).contiguous(memory_format=torch.channels_last)
             n_f = me.conv_flow2.out_channels
             # the k x k output convolution of the heads (6 channels: as slow in cuDNN as one to 256) as a 1x1 convolution
             # to k*k taps x 6 channels; the window sum of the taps is part of the update kernel

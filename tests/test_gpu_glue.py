@@ -104,6 +104,11 @@ def test_iter_update_equals_stock_ops(cuda, B, h, w, fmt):
     G.iter_update_taps(taps, 3, bf, bl, coords1, flow, logits, stacked)
     assert torch.allclose(coords1, c3_ref, rtol=0, atol=2e-5) and torch.allclose(logits, l3_ref, rtol=0, atol=2e-5)
     assert torch.equal(flow, coords1 - coords0) and torch.equal(stacked[:, :6], torch.cat([flow, logits], dim=1))
+    # channels-last copy (what the stacked motion-encoder convolution reads)
+    st_cl = torch.zeros_like(stacked).contiguous(memory_format=torch.channels_last)
+    G.iter_update_taps(taps, 3, bf, bl, coords1.clone(), flow.clone(), logits.clone(), st_cl)
+    G.iter_update_taps(taps, 3, bf, bl, coords1, flow, logits, stacked)
+    assert torch.equal(st_cl[:, :6], stacked[:, :6]) and not st_cl.is_contiguous() and float(st_cl[:, 6:].abs().sum()) == 0.0
 
 
 @pytest.mark.parametrize("B,C,H,W", [(2, 32, 40, 56), (3, 96, 17, 23), (8, 32, 320, 320)])
