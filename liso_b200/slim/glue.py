@@ -144,7 +144,7 @@ def iter_update(dflow_raw: torch.Tensor, bias_flow: torch.Tensor, dlogits_raw: t
     ``flow = coords1 - coords_grid``; optionally ``stacked = cat[flow, logits]``.  The raw tensors are the head
     convolutions without bias."""
     B, _, h, w = coords1.shape
-    for t in (coords1, flow, logits) + ((stacked,) if stacked is not None else ()):
+    for t in (coords1, flow, logits) + ((stacked,) if stacked is not None and not _is_nhwc(stacked) else ()):
         if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
             raise ValueError("iter_update: coords1 / flow / logits / stacked must be contiguous fp32 CUDA tensors")
     if tuple(dflow_raw.shape) != (B, 2, h, w) or tuple(dlogits_raw.shape) != tuple(logits.shape) or tuple(flow.shape) != (B, 2, h, w):
@@ -166,7 +166,7 @@ def iter_update_taps(taps: torch.Tensor, ksize: int, bias_flow: torch.Tensor, bi
     """`iter_update` with the heads' k x k output convolution given as the 1x1 "tap" tensor (B, k*k*(2 + n_logits), h, w),
     channel = tap * (2 + n_logits) + c: the window sum of the taps is taken inside the kernel."""
     B, _, h, w = coords1.shape
-    for t in (coords1, flow, logits) + ((stacked,) if stacked is not None else ()):
+    for t in (coords1, flow, logits) + ((stacked,) if stacked is not None and not _is_nhwc(stacked) else ()):
         if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
             raise ValueError("iter_update_taps: coords1 / flow / logits / stacked must be contiguous fp32 CUDA tensors")
     nl = logits.shape[1]

@@ -280,7 +280,7 @@ def test_triple_export_pass_equals_three_forwards(cuda, tmp_path):
                    v[-1].static_flow.clone()) for k, v in tri.items()}
         enc_before = _lib.load().slimb200_launch_count(_lib.K_PILLAR_NHWC)
         model.forward_triple(*batch)
-        assert _lib.load().slimb200_launch_count(_lib.K_PILLAR_NHWC) - enc_before == 3  # three frames, three encoder passes
+        assert _lib.load().slimb200_launch_count(_lib.K_PILLAR_NHWC) - enc_before == 1  # three frames, ONE encoder pass (12 in the reference)
         for a, b in ((0, 1), (0, 2), (1, 2)):
             pf, pb = model(batch[a], batch[b], None)
             for key, p in (("t%d_t%d" % (a, b), pf), ("t%d_t%d" % (b, a), pb)):
@@ -340,6 +340,8 @@ def test_gpu_export_from_raw_scans_with_loader_threads(cuda, tmp_path):
             pf, pb = model(preprocess_scans([it[1]["pcl_full_w_ground_ta"].to(cuda) for it in items], cfg),
                            preprocess_scans([it[2]["pcl_full_w_ground_ta"].to(cuda) for it in items], cfg), None)
         for b, i in enumerate(chunk):
+            if b and i == chunk[b - 1]:
+                continue  # padding copies: the file holds slot 0 (stock convolutions differ by ~1e-6 between batch positions)
             z = np.load(os.path.join(str(tmp_path), "%06d.npz" % i))
             assert np.array_equal(z["bev_raw_flow_t0_t1"], pf[-1].modified_network_output.static_flow[b].cpu().numpy()), i
             assert np.array_equal(z["bev_dynamicness_t1_t0"], pb[-1].modified_network_output.dynamicness[b].cpu().numpy()), i
