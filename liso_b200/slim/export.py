@@ -211,6 +211,93 @@ def iterate_batches(indices: Iterable[int], batch_size: int) -> Iterable[List[in
         yield cur
 
 
+def _walk(sample, fn):
+    """The sample structure (dict / list / tensor / anything else) with ``fn`` applied to every tensor."""
+    if torch.is_tensor(sample):
+        return fn(sample)
+    if isinstance(sample, dict):
+        return {k: _walk(v, fn) for k, v in sample.items()}
+    if isinstance(sample, (list, tuple)):
+        return [_walk(v, fn) for v in sample]
+    return sample
+
+
+class PinnedArena:
+    """A few grow-only pinned host buffers that whole batches are packed into by the loader thread: the upload of a batch
+    is then ONE host-to-device copy (instead of one per tensor, each from a freshly pinned allocation), and no pinned memory
+    is allocated in steady state.  A buffer goes back to the pool together with the event of the copy that reads it."""
+
+    ALIGN = 256
+
+    def __init__(self, buffers: int = 4):
+        import queue
+
+        self.free: "queue.Queue" = queue.Queue()
+        for _ in range(buffers):
+            self.free.put({"buf": None, "evt": None})
+
+    def take(self, nbytes: int):
+        slot = self.free.get()
+        if slot["evt"] is not None:
+            slot["evt"].synchronize()  # the copy that last read this buffer
+            slot["evt"] = None
+        if slot["buf"] is None or slot["buf"].numel() < nbytes:
+            buf = torch.empty(max(nbytes + nbytes // 4, 1 << 20), dtype=torch.uint8)
+            slot["buf"] = buf.pin_memory() if torch.cuda.is_available() else buf
+        return slot
+
+    def give_back(self, slot, evt=None):
+        slot["evt"] = evt
+        self.free.put(slot)
+
+    def pack(self, frames):
+        """``frames``: tuple of (collated) sample dictionaries with host tensors -> :class:`PackedBatch`."""
+        todo, off = [], 0
+
+        def plan(t):
+            nonlocal off
+            off = (off + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+            spec = (off, tuple(t.shape), t.dtype, t.numel() * t.element_size())
+            todo.append((spec, t))
+            off += spec[3]
+            return spec
+
+        layout = tuple(_walk(f, plan) for f in frames)
+        slot = self.take(off)
+        for (o, shape, dtype, n), t in todo:
+            if n:
+                slot["buf"][o:o + n].view(dtype).view(shape).copy_(t)
+        return PackedBatch(self, slot, off, layout)
+
+
+class PackedBatch:
+    """A batch packed into one pinned buffer (:meth:`PinnedArena.pack`); ``layout`` mirrors the sample dictionaries with
+    every tensor replaced by (offset, shape, dtype, bytes)."""
+
+    def __init__(self, arena, slot, nbytes, layout):
+        self.arena, self.slot, self.nbytes, self.layout = arena, slot, nbytes, layout
+
+    def __len__(self):
+        return len(self.layout)
+
+    def views(self, base: torch.Tensor):
+        """The sample dictionaries as views of ``base`` (a uint8 buffer holding a copy of the packed bytes)."""
+        def view(spec):
+            o, shape, dtype, n = spec
+            return base[o:o + n].view(dtype).view(shape)
+
+        def walk(x):
+            if isinstance(x, tuple) and len(x) == 4 and isinstance(x[2], torch.dtype):
+                return view(x)
+            if isinstance(x, dict):
+                return {k: walk(v) for k, v in x.items()}
+            if isinstance(x, list):
+                return [walk(v) for v in x]
+            return x
+
+        return tuple(walk(f) for f in self.layout)
+
+
 class ExportPipeline:
     """Double-buffered export loop for one GPU: the host->device upload of batch i+1 and the device->host download
     of batch i-1 run on a copy stream while batch i is computed on the caller's stream.  (The reference uploads,
@@ -268,6 +355,23 @@ class ExportPipeline:
                 out[k] = v
         return out
 
+    def _upload_batch(self, batch, slot: int):
+        """Stage one batch on the device (called on the copy stream): a :class:`PackedBatch` is ONE copy into the slot's
+        grow-only device buffer, the sample dictionaries are views of it; a tuple of sample dictionaries is copied tensor
+        by tensor."""
+        if isinstance(batch, PackedBatch):
+            key = (slot, "packed")
+            buf = self._up_bufs.get(key)
+            if buf is None or buf.numel() < batch.nbytes:
+                buf = torch.empty(max(batch.nbytes + batch.nbytes // 4, 1 << 20), dtype=torch.uint8, device=self.device)
+                self._up_bufs[key] = buf
+            buf[:batch.nbytes].copy_(batch.slot["buf"][:batch.nbytes], non_blocking=True)
+            evt = torch.cuda.Event()
+            evt.record(torch.cuda.current_stream(self.device))
+            batch.arena.give_back(batch.slot, evt)  # the pinned buffer is free again once this copy has run
+            return batch.views(buf)
+        return tuple(self._upload(s, slot, "t%d" % t) for t, s in enumerate(batch))
+
     def run(self, batches, consume=None):
         import contextlib
 
@@ -281,7 +385,7 @@ class ExportPipeline:
         if nxt is not None:
             self.copy_stream.wait_stream(cur)
             with torch.cuda.stream(self.copy_stream):
-                staged = tuple(self._upload(s, 0, "t%d" % t) for t, s in enumerate(nxt))
+                staged = self._upload_batch(nxt, 0)
                 up_evt = torch.cuda.Event()
                 up_evt.record(self.copy_stream)
         idx = 0
@@ -324,7 +428,7 @@ class ExportPipeline:
                     up_slot = (idx + 1) % D
                     if done_evt[up_slot] is not None:  # the batch that last read this slot's buffers must be through
                         self.copy_stream.wait_event(done_evt[up_slot])
-                    staged = tuple(self._upload(s, up_slot, "t%d" % t) for t, s in enumerate(nxt))
+                    staged = self._upload_batch(nxt, up_slot)
                     up_evt = torch.cuda.Event()
                     up_evt.record(self.copy_stream)
                 else:
@@ -434,7 +538,7 @@ def _pin(sample):
 def run_flow_export(model, dataset, target_dir: str, bev_range_m, *, world_size: int = 1, worker_id: int = 0,
                     batch_size: int = 8, device=None, skip_existing: bool = False, writer_workers: Optional[int] = None,
                     pipeline_factory=None, compress_on_gpu: bool = False, loader_workers: int = 0,
-                    unlink_after_write: bool = False, pad_last_batch: bool = True) -> Dict[str, float]:
+                    unlink_after_write: bool = False, pad_last_batch: bool = True, pack_uploads: bool = True) -> Dict[str, float]:
     """The flow export of ``liso/slim/experiment.py:225-361,363-471`` for the t0 -> t1 pairs of one worker: this rank's
     share of the pairs (modulo rule), batched, through the double-buffered :class:`ExportPipeline`, written by
     :class:`AsyncNpzWriter` in the reference's ``.npz`` schema under ``target_dir/<sample_id>.npz``; one collective at
@@ -446,6 +550,7 @@ def run_flow_export(model, dataset, target_dir: str, bev_range_m, *, world_size:
     (``experiment.py:404-456``).  ``compress_on_gpu``: the maps are deflated on the device and the writer threads only frame
     zip members (same files for ``np.load``).  ``loader_workers``: > 0 moves dataset access, collation and
     pinning to a background thread (> 1: with that many threads fetching samples), like DataLoader workers.
+    ``pack_uploads``: every batch is packed into one recycled pinned buffer and uploaded with one copy.
     ``pad_last_batch``: a ragged last batch is filled up with copies of its last sample (outputs discarded) so that no
     tensor shape changes.  Returns ``{"pairs", "files", "skipped", "elapsed_s_max"}`` over all ranks ("pairs"
     counts samples)."""
@@ -457,6 +562,8 @@ def run_flow_export(model, dataset, target_dir: str, bev_range_m, *, world_size:
     ids_of_batch: List[List[str]] = []
     skipped = 0
 
+    # batches packed into recycled pinned buffers (one upload per batch) when the stock pipeline drives a CUDA device
+    arena = PinnedArena(4) if (pipeline_factory is None and pack_uploads and torch.cuda.is_available()) else None
     fetch_pool = None
     if loader_workers > 1:
         from concurrent.futures import ThreadPoolExecutor
@@ -478,7 +585,8 @@ def run_flow_export(model, dataset, target_dir: str, bev_range_m, *, world_size:
                 # a ragged last batch would change every tensor shape (new cuDNN plans, a new CUDA graph for one batch):
                 # fill it up with copies of its last sample; their outputs are never read (ids_of_batch has the real ones)
                 items = items + [items[-1]] * (batch_size - len(items))
-            yield tuple(_pin(d) for d in collate_pairs([tuple(it[1:]) for it in items]))
+            frames = collate_pairs([tuple(it[1:]) for it in items])
+            yield arena.pack(frames) if arena is not None else tuple(_pin(d) for d in frames)
 
     thr = float(model.moving_dynamicness_threshold.value())
     counts = {"pairs": 0, "files": 0}

@@ -265,8 +265,11 @@ class SyntheticExportDataset:
     8f.4), as ``ExportPipeline`` does for such samples -- the host then only moves bytes."""
 
     def __init__(self, workload: Dict[str, Any], n_samples: int, frames: int = 2, pool: int = 16, seed0: int = 5000,
-                 raw: bool = False):
-        assert frames in (2, 3)
+                 raw: bool = False, motion: str = "rigid"):
+        """``motion``: how a sample differs from the cast scene it is drawn from: "rigid" (yaw rotation + shift) or "shift"
+        (shift only: one pass over the points, for hosts with few cores per GPU)."""
+        assert frames in (2, 3) and motion in ("rigid", "shift")
+        self.motion = motion
         self.workload, self.n, self.frames, self.pool, self.seed0 = workload, int(n_samples), frames, max(1, int(pool)), seed0
         self.raw = bool(raw)
         self._cache: Dict[int, tuple] = {}
@@ -299,15 +302,18 @@ class SyntheticExportDataset:
         frames = self._scene_frames(i % self.pool)
         rng = np.random.default_rng(self.seed0 * 7919 + i)
         variant = i // self.pool
-        yaw = 0.0 if variant == 0 else rng.uniform(-np.pi, np.pi)
+        yaw = 0.0 if variant == 0 or self.motion == "shift" else rng.uniform(-np.pi, np.pi)
         shift = np.zeros(2) if variant == 0 else rng.uniform(-1.5, 1.5, size=2)
         c, s_ = np.float32(np.cos(yaw)), np.float32(np.sin(yaw))
         bev, grid = self.workload["bev_range_m"], self.workload["img_grid_size"]
         samples = []
         for pc in frames:
-            q = pc.copy()
-            q[:, 0] = c * pc[:, 0] - s_ * pc[:, 1] + np.float32(shift[0])
-            q[:, 1] = s_ * pc[:, 0] + c * pc[:, 1] + np.float32(shift[1])
+            if yaw == 0.0:
+                q = pc + np.array([shift[0], shift[1], 0.0, 0.0], dtype=np.float32)[:pc.shape[1]]
+            else:
+                q = pc.copy()
+                q[:, 0] = c * pc[:, 0] - s_ * pc[:, 1] + np.float32(shift[0])
+                q[:, 1] = s_ * pc[:, 0] + c * pc[:, 1] + np.float32(shift[1])
             if self.raw:
                 import torch
 
