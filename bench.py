@@ -561,9 +561,9 @@ def main():
         base = args.export_dir or tempfile.mkdtemp(prefix="slimb200_export_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
         main.set_decode("last")  # the export reads the last iteration only (experiment.py:391-399); identical exported tensors
         main.model.outputs_alias_static_buffers = True
-        n_cpu = n_cpu_rank * world if affinity.get("pinned") else (os.cpu_count() or 1)
-        loaders = max(2, min(6, n_cpu // max(1, world) - 2))
-        writers = max(2, min(8, n_cpu // max(1, world) - 1))
+        n_cpu = n_cpu_rank * world  # cores this rank may run on (its affinity mask) x ranks
+        loaders = max(2, min(6, n_cpu_rank - 2))
+        writers = max(2, min(8, n_cpu_rank - 1))
         export_line = {"what": "run_flow_export over distinct synthetic KITTI-sized samples (pool of %d ray-cast scenes, per-sample shift of the whole scene), "
                                "raw scans in (ground rule, pillar map, compaction on the device), .npz files out (maps deflated on the device, "
                                "framed + written by %d worker threads, %d loader threads); files are unlinked after the write to bound "
@@ -588,6 +588,7 @@ def main():
                                  "file_mb_per_sample": res["file_bytes"] / max(1.0, res["files"]) / 1e6,
                                  "d2h_mb_per_sample": res["d2h_bytes"] / max(1.0, res["pairs"]) / 1e6,
                                  "arrays_per_file": 6 if frames == 2 else 14,
+                                 "host_ms_per_batch_mean_over_ranks": {k[8:]: round(v / world, 3) for k, v in res.items() if k.startswith("host_ms_")},
                                  "graph_captures_inside_timed_run": getattr(main.model.raft_network, "n_graph_captures", 0) - cap0}
             del ds, warm
         export_line["triple_vs_three_pair_calls"] = export_line["triples"]["pairs_per_s"] / export_line["pairs"]["pairs_per_s"]

@@ -321,6 +321,9 @@ class ExportPipeline:
         self.compress = bool(compress)
         self.encoder = None
         self.downloaded_bytes = 0
+        # where the launch thread's time goes (seconds, summed over `run` calls): waiting for the next batch from the
+        # loader, enqueueing a batch (Python + launches), blocked on the device (member table / downloads), in `consume`
+        self.host_s = {"input_wait": 0.0, "launch": 0.0, "gpu_wait": 0.0, "consume": 0.0, "batches": 0}
         if hasattr(model, "outputs_alias_static_buffers"):
             model.outputs_alias_static_buffers = True  # this loop takes its own packed copies of what it exports (see run)
         self.copy_stream = torch.cuda.Stream(device=device)
@@ -374,7 +377,9 @@ class ExportPipeline:
 
     def run(self, batches, consume=None):
         import contextlib
+        import time
 
+        clock, hs = time.perf_counter, self.host_s
         cur = torch.cuda.current_stream(self.device)
         it = iter(batches)
         downloads = []  # (index, host tensors, event)
@@ -391,6 +396,7 @@ class ExportPipeline:
         idx = 0
         n_done = 0
         while staged is not None:
+            t_launch = clock()
             cur.wait_event(up_evt)
             ctx = self.amp_ctx() if self.amp_ctx else contextlib.nullcontext()
             with torch.no_grad(), ctx:
@@ -421,8 +427,12 @@ class ExportPipeline:
             done = torch.cuda.Event()
             done.record(cur)
             done_evt[idx % D] = done
+            t_in = clock()
+            hs["launch"] += t_in - t_launch
+            hs["batches"] += 1
             # stage the next batch and download this one on the copy stream, behind the compute of this batch
             nxt = next(it, None)
+            hs["input_wait"] += clock() - t_in
             with torch.cuda.stream(self.copy_stream):
                 if nxt is not None:
                     up_slot = (idx + 1) % D
@@ -460,19 +470,30 @@ class ExportPipeline:
         return n_done
 
     def _begin(self, d):
+        import time
+
+        t = time.perf_counter()
         self.downloaded_bytes += self.encoder.fetch_begin(d[1], self.copy_stream)
         d[2]["begun"] = True
+        self.host_s["gpu_wait"] += time.perf_counter() - t
 
     def _hand_over(self, d, consume) -> int:
+        import time
+
+        t = time.perf_counter()
         if self.compress:
             if not d[2]["begun"]:
                 self._begin(d)
+                t = time.perf_counter()
             host = self.encoder.fetch_end(d[1])
         else:
             d[2].synchronize()
             host = d[1]
+        t1 = time.perf_counter()
+        self.host_s["gpu_wait"] += t1 - t
         if consume is not None:
             consume(d[0], host)
+        self.host_s["consume"] += time.perf_counter() - t1
         return 1
 
 
@@ -570,9 +591,12 @@ def run_flow_export(model, dataset, target_dir: str, bev_range_m, *, world_size:
 
         fetch_pool = ThreadPoolExecutor(loader_workers)
 
+    loader_s = [0.0]
+
     def batches():
         nonlocal skipped
         for chunk in iterate_batches(mine, batch_size):
+            t_load = time.perf_counter()
             items = list(fetch_pool.map(dataset.__getitem__, chunk)) if fetch_pool else [dataset[i] for i in chunk]
             if skip_existing:  # (experiment.py:380-382: an existing target file skips the forward as well)
                 keep = [it for it in items if not os.path.exists(writer.target_file(it[0]))]
@@ -586,7 +610,9 @@ def run_flow_export(model, dataset, target_dir: str, bev_range_m, *, world_size:
                 # fill it up with copies of its last sample; their outputs are never read (ids_of_batch has the real ones)
                 items = items + [items[-1]] * (batch_size - len(items))
             frames = collate_pairs([tuple(it[1:]) for it in items])
-            yield arena.pack(frames) if arena is not None else tuple(_pin(d) for d in frames)
+            out = arena.pack(frames) if arena is not None else tuple(_pin(d) for d in frames)
+            loader_s[0] += time.perf_counter() - t_load
+            yield out
 
     thr = float(model.moving_dynamicness_threshold.value())
     counts = {"pairs": 0, "files": 0}
@@ -604,4 +630,10 @@ def run_flow_export(model, dataset, target_dir: str, bev_range_m, *, world_size:
     local = {"pairs": float(counts["pairs"]), "files": float(counts["files"]), "skipped": float(skipped),
              "file_bytes": float(writer.bytes_written), "d2h_bytes": float(getattr(pipeline, "downloaded_bytes", 0)),
              "elapsed_s_max": time.perf_counter() - t0}
+    hs = getattr(pipeline, "host_s", None)
+    if hs and hs.get("batches"):  # host-side time per batch (ms), summed over the ranks by reduce_counters: divide by the world size
+        nb = float(hs["batches"])
+        local.update({"host_ms_launch": 1e3 * hs["launch"] / nb, "host_ms_input_wait": 1e3 * hs["input_wait"] / nb,
+                      "host_ms_gpu_wait": 1e3 * hs["gpu_wait"] / nb, "host_ms_consume": 1e3 * hs["consume"] / nb,
+                      "host_ms_loader": 1e3 * loader_s[0] / nb})
     return reduce_counters(local, device if device is not None and torch.device(device).type == "cuda" else None)
