@@ -250,8 +250,9 @@ class PinnedArena:
         slot["evt"] = evt
         self.free.put(slot)
 
-    def pack(self, frames):
-        """``frames``: tuple of (collated) sample dictionaries with host tensors -> :class:`PackedBatch`."""
+    def pack(self, frames, executor=None):
+        """``frames``: tuple of (collated) sample dictionaries with host tensors -> :class:`PackedBatch`.  ``executor``: copy
+        the tensors on its threads (the copies release the GIL; one thread moves ~6 GB/s into pinned memory)."""
         todo, off = [], 0
 
         def plan(t):
@@ -264,9 +265,18 @@ class PinnedArena:
 
         layout = tuple(_walk(f, plan) for f in frames)
         slot = self.take(off)
-        for (o, shape, dtype, n), t in todo:
+        buf = slot["buf"]
+
+        def copy(job):
+            (o, shape, dtype, n), t = job
             if n:
-                slot["buf"][o:o + n].view(dtype).view(shape).copy_(t)
+                buf[o:o + n].view(dtype).view(shape).copy_(t)
+
+        if executor is not None and len(todo) > 1:
+            list(executor.map(copy, todo))
+        else:
+            for job in todo:
+                copy(job)
         return PackedBatch(self, slot, off, layout)
 
 
@@ -610,7 +620,7 @@ def run_flow_export(model, dataset, target_dir: str, bev_range_m, *, world_size:
                 # fill it up with copies of its last sample; their outputs are never read (ids_of_batch has the real ones)
                 items = items + [items[-1]] * (batch_size - len(items))
             frames = collate_pairs([tuple(it[1:]) for it in items])
-            out = arena.pack(frames) if arena is not None else tuple(_pin(d) for d in frames)
+            out = arena.pack(frames, fetch_pool) if arena is not None else tuple(_pin(d) for d in frames)
             loader_s[0] += time.perf_counter() - t_load
             yield out
 
