@@ -54,13 +54,15 @@ struct PillarArgs {
   int32_t* cell_prefix;     // exclusive prefix of counts inside the tile
   int32_t* cell_ord;        // pillar ordinal inside the sample (valid where count > 0)
   int32_t* tile_total;      // [n_tiles]
-  int32_t* tile_start;      // [n_tiles] exclusive prefix over the whole batch
+  int32_t* tile_start;      // [n_tiles] pt_off[sample] + exclusive prefix inside the sample: position in the sorted arrays
   int32_t* pt_key;          // [total points] cell key or -1
   int32_t* sorted_idx;      // [total points] per-sample point index, cell-contiguous
   float4* sorted_pts;       // [total points] xyzi, same order
   int32_t* blk_cnt;         // [total point blocks] first-point flags per block
   int32_t* blk_base;        // [total point blocks] exclusive prefix inside the sample
   int32_t* pillar_base;     // [batch + 1] exclusive prefix of kept pillars
+  int32_t* sample_kept;     // [batch] kept pillars per sample
+  int32_t* ticket;          // zeroed per call: how many per-sample scans have finished
   int4* pillar_info;        // [kept pillars] (cell key, first sorted point, point count, b << 24 | xi << 12 | yi), first-appearance order
   float* bn_ab;             // [2][MAX_COUT] alpha, beta' of the folded BatchNorm
   double* stat_partials;    // [STATS_MAX_CTAS][MAX_COUT][2]
@@ -132,28 +134,22 @@ __global__ void __launch_bounds__(PT_BLOCK) k_point_keys(const PillarArgs a) {
 
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_scan_local(const PillarArgs a, int n_cell_blocks) {
-  __shared__ int s_warp[8];
   const int lane = lane_id(), warp = warp_id();
   if ((int)blockIdx.x < n_cell_blocks) {
-    // 256 cells = 2 tiles; warp w covers row (w % 4) of tile (w / 4)
-    const int cell = blockIdx.x * 256 + threadIdx.x;
-    const int n_cells = a.n_tiles * TILE_CELLS;
-    const int cnt = cell < n_cells ? a.cell_count[cell] : 0;
-    int inc = cnt;
+    // one warp per tile (128 cells), four consecutive cells per lane: one 16-byte load, one warp scan, one 16-byte store
+    const int tile = blockIdx.x * 8 + warp;
+    if (tile < a.n_tiles) {
+      const int4 c = *reinterpret_cast<const int4*>(a.cell_count + (size_t)tile * TILE_CELLS + lane * 4);
+      const int sum = c.x + c.y + c.z + c.w;
+      int inc = sum;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, inc, d);
-      if (lane >= d) inc += v;
-    }
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    int before = 0;
-    const int w0 = warp & ~3;
-    for (int w = w0; w < warp; ++w) before += s_warp[w];
-    if (cell < n_cells) a.cell_prefix[cell] = before + inc - cnt;
-    if ((threadIdx.x & (TILE_CELLS - 1)) == TILE_CELLS - 1) {
-      const int tile = cell / TILE_CELLS;
-      if (tile < a.n_tiles) a.tile_total[tile] = before + inc;
+      for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += v;
+      }
+      const int ex = inc - sum;
+      *reinterpret_cast<int4*>(a.cell_prefix + (size_t)tile * TILE_CELLS + lane * 4) = make_int4(ex, ex + c.x, ex + c.x + c.y, ex + c.x + c.y + c.z);
+      if (lane == 31) a.tile_total[tile] = inc;
     }
   } else {
     const int pb = blockIdx.x - n_cell_blocks;
@@ -207,34 +203,52 @@ __device__ int block_exclusive_scan_1024(const int32_t* in, int32_t* out, int n,
   return s_tmp[32];
 }
 
+// One CTA per independent scan (round 2; a single CTA used to walk through the samples one after the other):
+//   CTA 0                  eval-mode BatchNorm fold
+//   CTA 1 + b              tile starts of sample b: exclusive prefix of its tile totals, based at pt_off[b] -- the sample's
+//                          share of the sorted arrays (host-known upper bound of its in-range points), so that no scan
+//                          crosses a sample
+//   CTA 1 + batch + b      pillar-ordinal bases of sample b's 256-point blocks; the LAST of these CTAs to finish (ticket)
+//                          turns the per-sample pillar counts (capped at max_voxels) into pillar_base
 __global__ void __launch_bounds__(1024) k_scan_global(const PillarArgs a) {
   __shared__ int s_tmp[33];
+  __shared__ int s_last;
   if (blockIdx.x == 0) {
-    block_exclusive_scan_1024(a.tile_total, a.tile_start, a.n_tiles, s_tmp);
-  } else if (blockIdx.x == 1) {
-    int base = 0;
-    for (int b = 0; b < a.batch; ++b) {
-      const int nb = a.blk_off[b + 1] - a.blk_off[b];
-      const int total = block_exclusive_scan_1024(a.blk_cnt + a.blk_off[b], a.blk_base + a.blk_off[b], nb, s_tmp);
-      if (threadIdx.x == 0) {
-        a.pillar_base[b] = base;
-        if (a.pillar_counts) a.pillar_counts[b] = base;
-      }
-      base += min(total, a.p.max_voxels);
-    }
-    if (threadIdx.x == 0) {
-      a.pillar_base[a.batch] = base;
-      if (a.pillar_counts) a.pillar_counts[a.batch] = base;
-    }
-  } else if (!a.p.bn_training) {
     // eval-mode BatchNorm folded the way ATen does: alpha = gamma / sqrt(var + eps),
     // beta' = beta - mean * alpha, y = x * alpha + beta'
     const int c = threadIdx.x;
-    if (c < a.p.c_out) {
+    if (!a.p.bn_training && c < a.p.c_out) {
       const float invstd = 1.0f / sqrtf(a.bn_var[c] + a.p.bn_eps);
       const float alpha = a.bn_weight[c] * invstd;
       a.bn_ab[c] = alpha;
       a.bn_ab[MAX_COUT + c] = a.bn_bias[c] - a.bn_mean[c] * alpha;
+    }
+  } else if ((int)blockIdx.x <= a.batch) {
+    const int b = blockIdx.x - 1, t0 = b * a.tiles_per_sample;
+    block_exclusive_scan_1024(a.tile_total + t0, a.tile_start + t0, a.tiles_per_sample, s_tmp);
+    __syncthreads();
+    const int base = a.pt_off[b];
+    for (int j = threadIdx.x; j < a.tiles_per_sample; j += 1024) a.tile_start[t0 + j] += base;
+  } else {
+    const int b = blockIdx.x - 1 - a.batch;
+    const int nb = a.blk_off[b + 1] - a.blk_off[b];
+    const int total = block_exclusive_scan_1024(a.blk_cnt + a.blk_off[b], a.blk_base + a.blk_off[b], nb, s_tmp);
+    if (threadIdx.x == 0) {
+      a.sample_kept[b] = min(total, a.p.max_voxels);
+      __threadfence();
+      s_last = atomicAdd(a.ticket, 1) == a.batch - 1;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+      __threadfence();
+      int base = 0;
+      for (int i = 0; i < a.batch; ++i) {
+        a.pillar_base[i] = base;
+        if (a.pillar_counts) a.pillar_counts[i] = base;
+        base += __ldcg(a.sample_kept + i);
+      }
+      a.pillar_base[a.batch] = base;
+      if (a.pillar_counts) a.pillar_counts[a.batch] = base;
     }
   }
 }
@@ -923,6 +937,7 @@ int make_plan(const float* const* points, const int32_t* n_points, int32_t batch
   a.cell_count = w.take<int32_t>(n_cells);
   a.cell_inv_first = w.take<int32_t>(n_cells);
   a.cell_fill = w.take<int32_t>(n_cells);
+  a.ticket = w.take<int32_t>(64);
   plan->zero_bytes = w.used();
   a.cell_prefix = w.take<int32_t>(n_cells);
   a.cell_ord = w.take<int32_t>(n_cells);
@@ -934,6 +949,7 @@ int make_plan(const float* const* points, const int32_t* n_points, int32_t batch
   a.blk_cnt = w.take<int32_t>(n_blk_cap);
   a.blk_base = w.take<int32_t>(n_blk_cap);
   a.pillar_base = w.take<int32_t>(SLIMB200_MAX_BATCH + 1);
+  a.sample_kept = w.take<int32_t>(SLIMB200_MAX_BATCH);
   {
     const size_t cap = (size_t)batch * (size_t)p->max_voxels;
     a.pillar_info = w.take<int4>((n_tot < cap ? n_tot : cap) + 1);
@@ -941,7 +957,7 @@ int make_plan(const float* const* points, const int32_t* n_points, int32_t batch
   a.bn_ab = w.take<float>(2 * MAX_COUT);
   a.stat_partials = w.take<double>((size_t)STATS_MAX_CTAS * MAX_COUT * 2);
   plan->bytes = w.used();
-  plan->n_cell_blocks = (int)((n_cells + 255) / 256);
+  plan->n_cell_blocks = (a.n_tiles + 7) / 8;  // k_scan_local: one warp per tile
   plan->n_pt_blocks = n_blk;
   plan->max_pts_per_sample = max_n;
   return SLIMB200_OK;
@@ -998,7 +1014,7 @@ extern "C" int slimb200_pillar_encode(const float* const* points, const int32_t*
   }
   SLIMB200_LAUNCH(SLIMB200_K_SCAN_LOCAL, stream,
                   (k_scan_local<<<plan.n_cell_blocks + plan.n_pt_blocks, 256, 0, stream>>>(a, plan.n_cell_blocks)));
-  SLIMB200_LAUNCH(SLIMB200_K_SCAN_GLOBAL, stream, (k_scan_global<<<3, 1024, 0, stream>>>(a)));
+  SLIMB200_LAUNCH(SLIMB200_K_SCAN_GLOBAL, stream, (k_scan_global<<<1 + 2 * batch, 1024, 0, stream>>>(a)));
   if (plan.n_pt_blocks > 0) {
     SLIMB200_LAUNCH(SLIMB200_K_RANK_SCATTER, stream, (k_rank_scatter<<<plan.n_pt_blocks, PT_BLOCK, 0, stream>>>(a)));
   }
