@@ -469,7 +469,13 @@ class RAFT(nn.Module):
         # its canvases straight into the graph's static inputs; ~800 launches per step become one graph launch.
         # The captured kernels hold raw pointers to the weights (and to cached concatenations of them): any in-place
         # update or re-allocation of a parameter invalidates the graph.
-        wsig = tuple((p.data_ptr(), p._version) for mod in (self.fnet, self.cnet, self.update_block) for p in mod.parameters())
+        # (the module tree is walked once; the modules' own parameter dictionaries are read every call, so a re-assigned
+        # or re-allocated parameter is still seen)
+        pdicts = self.__dict__.get("_graph_param_dicts")
+        if pdicts is None:
+            pdicts = self.__dict__["_graph_param_dicts"] = [m._parameters for root in (self.fnet, self.cnet, self.update_block)
+                                                            for m in root.modules() if m._parameters]
+        wsig = tuple((p.data_ptr(), p._version) for d in pdicts for p in d.values() if p is not None)
         key = (B, self.output_iterations, self.pp_layer.canvas_memory_format, str(dev), torch.backends.cudnn.allow_tf32, self.training,
                self.fused_update_block, self.merge_parallel_convs, self.tap_heads, self.concurrent_directions, FAST_STOCK_OPS,
                self.fuse_lookup_conv, self.stacked_stems, self.batched_frame_encoding,
