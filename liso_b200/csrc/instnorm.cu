@@ -2,13 +2,12 @@
 //
 // Replaces `norm_fn = "instance_affine"` + ReLU of the SLIM feature extractor (liso/slim/model/extractor.py:5-68,
 // 211-297: nn.InstanceNorm2d(C, eps=1e-3, affine=True) followed by nn.ReLU), which PyTorch runs as a copy to NCHW,
-// cuDNN's batch-norm kernel on (1, B*C, H, W), a copy back and a clamp.  Two launches, two passes over the data:
+// cuDNN's batch-norm kernel on (1, B*C, H, W), a copy back and a clamp.  Three launches, two passes over the data:
 //   k_in_stats     per (sample, slab of pixels): shifted sums (shift = the slab's first pixel) per channel, lanes = channel
 //                  groups of 4 (every load is a coalesced float4 of a pixel's channel vector), lanes added in fp64 ->
 //                  (count, mean, M2) per slab; about one wave of CTAs whatever the tensor size
-//                  the last slab of a sample to finish (ticket) pools the partials per channel exactly in fp64 (no
-//                  division per partial) -> scale = gamma / sqrt(var + eps), shift = beta - mean * scale (biased
-//                  variance, like F.instance_norm); round 1 had a launch of its own for this (k_in_finalize)
+//   k_in_finalize  per (sample, channel): exact pooling of the slab partials in fp64 (no division per partial) ->
+//                  scale = gamma / sqrt(var + eps), shift = beta - mean * scale (biased variance, like F.instance_norm)
 //   k_in_apply     out = max(x * scale + shift, 0) as float4; optionally the residual join of the block is fused in:
 //                  out = relu(residual + relu(x * scale + shift))
 // The convolutions themselves stay stock cuDNN.
@@ -27,37 +26,42 @@ struct InArgs {
   float* out;
   float* partial;   // [batch][slabs][C][3] (count, mean, M2)
   float* scale_shift;  // [batch][C][2]
-  unsigned* ticket;    // [batch], zeroed per call: slabs of the sample that have delivered their partials
   int batch, hw, C, slabs, relu;
   int xpitch;  // floats between consecutive pixels of x (== C for a packed tensor, larger for a channel slice)
   float eps;
 };
 
-// One THREAD merges the slab partials of one (sample, channel): exact pooled mean and M2 in fp64 without a division per
-// partial -- N = sum n_s, mean = sum n_s mean_s / N, M2 = sum [M2_s + n_s (mean_s - mean)^2] -- two passes over the
-// slabs in fixed order (independent loads, neighbouring threads read neighbouring channels); biased variance like
-// F.instance_norm.
-__device__ __forceinline__ void in_finalize_channel(const InArgs& a, int b, int c) {
+// One warp merges the slab partials of one (sample, channel): exact pooled mean and M2 in fp64 without a division per
+// partial -- N = sum n_s, mean = sum n_s mean_s / N, M2 = sum [M2_s + n_s (mean_s - mean)^2] -- lanes take strided
+// subsets, plain butterfly sums; biased variance like F.instance_norm.
+__device__ __forceinline__ void in_finalize_channel(const InArgs& a, int b, int c, int lane) {
   const float* base = a.partial + ((size_t)b * a.slabs * a.C + c) * 3;
   const size_t stride = (size_t)a.C * 3;
   double n = 0.0, sm = 0.0;
-#pragma unroll 4
-  for (int s = 0; s < a.slabs; ++s) {
+  for (int s = lane; s < a.slabs; s += 32) {
     const double nb = (double)__ldcg(base + s * stride), mb = (double)__ldcg(base + s * stride + 1);
     n += nb;
     sm = fma(nb, mb, sm);
   }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    n += __shfl_xor_sync(0xffffffffu, n, d);
+    sm += __shfl_xor_sync(0xffffffffu, sm, d);
+  }
   const double mu = n > 0.0 ? sm / n : 0.0;
   double M2 = 0.0;
-#pragma unroll 4
-  for (int s = 0; s < a.slabs; ++s) {
+  for (int s = lane; s < a.slabs; s += 32) {
     const double nb = (double)__ldcg(base + s * stride), dl = (double)__ldcg(base + s * stride + 1) - mu;
     M2 += (double)__ldcg(base + s * stride + 2) + nb * dl * dl;
   }
-  const double var = n > 0.0 ? M2 / n : 0.0;
-  const float scale = a.gamma[c] * (float)(1.0 / sqrt(var + (double)a.eps));
-  a.scale_shift[((size_t)b * a.C + c) * 2] = scale;
-  a.scale_shift[((size_t)b * a.C + c) * 2 + 1] = a.beta[c] - (float)mu * scale;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) M2 += __shfl_xor_sync(0xffffffffu, M2, d);
+  if (lane == 0) {
+    const double var = n > 0.0 ? M2 / n : 0.0;
+    const float scale = a.gamma[c] * (float)(1.0 / sqrt(var + (double)a.eps));
+    a.scale_shift[((size_t)b * a.C + c) * 2] = scale;
+    a.scale_shift[((size_t)b * a.C + c) * 2 + 1] = a.beta[c] - (float)mu * scale;
+  }
 }
 
 __global__ void __launch_bounds__(IN_THREADS, 6) k_in_stats(const InArgs a) {
@@ -116,16 +120,13 @@ __global__ void __launch_bounds__(IN_THREADS, 6) k_in_stats(const InArgs a) {
     o[1] = (float)mean;
     o[2] = (float)M2;
   }
-  // the LAST slab of a sample to deliver its partials pools them (one thread per channel): no separate launch
-  __shared__ bool s_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(a.ticket + b, 1u) == (unsigned)a.slabs - 1u;
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
-    if (threadIdx.x < a.C) in_finalize_channel(a, b, threadIdx.x);
-  }
+}
+
+// one warp per (sample, channel)
+__global__ void __launch_bounds__(IN_THREADS) k_in_finalize(const InArgs a) {
+  const int i = (blockIdx.x * IN_THREADS + threadIdx.x) >> 5;
+  if (i >= a.batch * a.C) return;
+  in_finalize_channel(a, i / a.C, i % a.C, threadIdx.x & 31);
 }
 
 // out = [relu_outer]([relu_inner](x * scale + shift) + residual), float4.  relu bit 0 = inner (the norm's own ReLU),
@@ -186,7 +187,6 @@ extern "C" size_t slimb200_instnorm_workspace_bytes(int32_t batch, int32_t chann
   WorkspaceCarver w(nullptr);
   w.take<float>((size_t)batch * slabs_for(batch, hw) * channels * 3);
   w.take<float>((size_t)batch * channels * 2);
-  w.take<unsigned>((size_t)batch);
   return w.used();
 }
 
@@ -219,9 +219,9 @@ extern "C" int slimb200_instnorm_nhwc_slice(const float* x, int32_t x_pitch, con
   WorkspaceCarver w(workspace);
   a.partial = w.take<float>((size_t)batch * a.slabs * channels * 3);
   a.scale_shift = w.take<float>((size_t)batch * channels * 2);
-  a.ticket = w.take<unsigned>((size_t)batch);
-  SLIMB200_CUDA_TRY(cudaMemsetAsync(a.ticket, 0, sizeof(unsigned) * batch, stream));
   SLIMB200_LAUNCH(SLIMB200_K_IN_STATS, stream, (k_in_stats<<<dim3(a.slabs, batch), IN_THREADS, 0, stream>>>(a)));
+  SLIMB200_LAUNCH(SLIMB200_K_IN_FINALIZE, stream,
+                  (k_in_finalize<<<(batch * channels * 32 + IN_THREADS - 1) / IN_THREADS, IN_THREADS, 0, stream>>>(a)));
   const size_t per_sample = (size_t)hw * (channels >> 2);
   const unsigned gx = (unsigned)((per_sample + IN_THREADS * 4 - 1) / (IN_THREADS * 4) < 148 * 4 ? (per_sample + IN_THREADS * 4 - 1) / (IN_THREADS * 4) : 148 * 4);
   SLIMB200_LAUNCH(SLIMB200_K_IN_APPLY, stream, (k_in_apply<<<dim3(gx, batch), IN_THREADS, 0, stream>>>(a)));
