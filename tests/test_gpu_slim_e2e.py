@@ -271,6 +271,9 @@ def test_triple_export_pass_equals_three_forwards(cuda, tmp_path):
 
     cfg = make_cfg("T")
     model, _ = _model(cfg, cuda, decode_iterations="last", static_aggregation=False)
+    # (encoders frame by frame: with the frames of a pass batched through the encoders a triple runs them on 3 B samples and a
+    # pair on 2 B, and cuDNN's summation order depends on the batch size -- checked at round-off level below)
+    model.raft_network.batched_encoders = False
     ds = SyntheticExportDataset(WORKLOADS["T"], 5, frames=3, pool=3)
     items = [ds[i] for i in range(2)]
     batch = export.collate_pairs([it[1:] for it in items])
@@ -287,6 +290,14 @@ def test_triple_export_pass_equals_three_forwards(cuda, tmp_path):
                 assert torch.equal(tri[key][0], p[-1].modified_network_output.static_flow), key
                 assert torch.equal(tri[key][1], p[-1].modified_network_output.dynamicness), key
                 assert torch.equal(tri[key][2], p[-1].static_flow), key
+        # default setting (all frames of the pass through the encoders at once): the same maps to fp32 round-off
+        model.raft_network.batched_encoders = True
+        tri_b = model.forward_triple(*batch)
+        for key, ref in tri.items():
+            got = tri_b[key][-1].modified_network_output.static_flow
+            assert torch.equal(got != 0, ref[0] != 0), key
+            assert float((got - ref[0]).abs().max()) <= 1e-3 * max(1.0, float(ref[0].abs().max())), key
+        model.raft_network.batched_encoders = False
     out = export.run_flow_export(model, ds, str(tmp_path), cfg.data.bev_range_m, batch_size=2, device=cuda, writer_workers=2)
     assert out["pairs"] == 5 and out["files"] == 5
     z = np.load(os.path.join(str(tmp_path), "000001.npz"))
