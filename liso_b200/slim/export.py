@@ -337,6 +337,7 @@ class ExportPipeline:
         if hasattr(model, "outputs_alias_static_buffers"):
             model.outputs_alias_static_buffers = True  # this loop takes its own packed copies of what it exports (see run)
         self.copy_stream = torch.cuda.Stream(device=device)
+        self.enc_stream = torch.cuda.Stream(device=device)  # the DEFLATE encoder of batch i runs under the front end of batch i + 1
         self.amp_ctx = amp_ctx
         self.depth = max(2, int(depth))
         self._out_bufs = [None] * self.depth
@@ -427,8 +428,23 @@ class ExportPipeline:
                     from .npz_stream import DeflateEncoder
 
                     self.encoder = DeflateEncoder(self.device, slots=D)
-                self.encoder.encode([m.static_flow for m in mods] + [m.dynamicness for m in mods], slot=idx % D)
-                self.encoder.start_download(idx % D)
+                views = [m.static_flow for m in mods] + [m.dynamicness for m in mods]
+                net = getattr(self.model, "raft_network", None)
+                if net is not None and getattr(net, "last_forward_was_graph", False) and getattr(self.model, "outputs_alias_static_buffers", False):
+                    # the maps are the graph's static outputs: encode on a side stream, under the pre-processing and the
+                    # pillar encoder of the next batch; only the next graph replay (which overwrites them) waits for it
+                    fwd_done = torch.cuda.Event()
+                    fwd_done.record(cur)
+                    self.enc_stream.wait_event(fwd_done)
+                    with torch.cuda.stream(self.enc_stream):
+                        self.encoder.encode(views, slot=idx % D)
+                        self.encoder.start_download(idx % D)
+                        enc_done = torch.cuda.Event()
+                        enc_done.record(self.enc_stream)
+                    net.pre_replay_event = enc_done
+                else:
+                    self.encoder.encode(views, slot=idx % D)
+                    self.encoder.start_download(idx % D)
                 outs = None
             else:
                 # packed copies: the predictions may be views of the CUDA graph's static outputs, which the next forward
@@ -477,6 +493,10 @@ class ExportPipeline:
             idx += 1
         for d in downloads:
             n_done += self._hand_over(d, consume)
+        cur.wait_stream(self.enc_stream)  # whoever uses the model next (on `cur`) must not overwrite maps still being encoded
+        net = getattr(self.model, "raft_network", None)
+        if net is not None and hasattr(net, "pre_replay_event"):
+            net.pre_replay_event = None
         return n_done
 
     def _begin(self, d):

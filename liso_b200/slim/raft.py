@@ -411,6 +411,8 @@ class RAFT(nn.Module):
         # forward and backward direction as two parallel branches of the CUDA graph
         self.concurrent_directions = True
         self.stacked_stems = True  # fnet / cnet 7x7 stems on the same canvas as one stacked convolution
+        self.pre_replay_event = None  # see forward_frames
+        self.last_forward_was_graph = False
         self.batched_encoders = True  # fnet / cnet over all frames of a pass at once (canvases = slices of one buffer)
         self.batched_frame_encoding = True  # every frame of a pass through one pillar-encoder call (eval-mode BatchNorm)
         # consumer of the per-iteration network outputs, e.g. SLIM's output decoder: called as
@@ -458,6 +460,8 @@ class RAFT(nn.Module):
         one_call = (self.batched_frame_encoding and not self.pp_layer.training and all(len(p) == B for p in pcls)
                     and B * len(pcls) <= _lib_module.MAX_BATCH and hasattr(self.pp_layer, "empty_outputs"))
         if not self.will_use_graph(*pcls):
+            self.last_forward_was_graph = False
+            self._wait_output_readers(dev)
             if one_call and dev.type == "cuda":
                 canvas, occ = self.pp_layer([t for p in pcls for t in p], **kw)
                 enc = [(canvas[f * B:(f + 1) * B], occ[f * B:(f + 1) * B]) for f in range(len(pcls))]
@@ -495,11 +499,22 @@ class RAFT(nn.Module):
         else:
             for f, p in enumerate(pcls):
                 self.pp_layer(p, out=st["in"][f], **kw)
+        self._wait_output_readers(dev)
         if "graph" not in st:
             self._capture_net_graph(st, dev)
+        self.last_forward_was_graph = True
         st["graph"].replay()
         _lib_mod().note_graph_replay(st["launches"])
         return st["outs"], [i[1] for i in st["in"]]
+
+    def _wait_output_readers(self, dev):
+        """A consumer on another stream may still be reading the static outputs of the previous graph replay
+        (``ExportPipeline``'s encoder sets ``pre_replay_event``): the pillar encoder in front did not have to wait for it,
+        everything that may overwrite or release those buffers does."""
+        if self.pre_replay_event is not None:
+            if dev.type == "cuda":
+                torch.cuda.current_stream(dev).wait_event(self.pre_replay_event)
+            self.pre_replay_event = None
 
     def will_use_graph(self, pcl_t0, pcl_t1, *more) -> bool:
         dev = pcl_t0[0].device
