@@ -322,6 +322,9 @@ def test_gpu_compressed_export_writes_the_same_files(cuda, tmp_path):
         b = export.run_flow_export(model, ds, d_gpu, cfg.data.bev_range_m, batch_size=2, device=cuda, writer_workers=2,
                                    compress_on_gpu=True)
         assert a["files"] == b["files"] == 9
+        again = export.run_flow_export(model, ds, d_gpu, cfg.data.bev_range_m, batch_size=2, device=cuda, writer_workers=2,
+                                       compress_on_gpu=True, skip_existing=True)
+        assert again["files"] == 0 and again["skipped"] == 9 and again["pairs"] == 0  # experiment.py:380-382: existing targets are skipped
         for i in range(9):
             zr, zg = np.load(os.path.join(d_ref, "%06d.npz" % i)), np.load(os.path.join(d_gpu, "%06d.npz" % i))
             assert sorted(zr.files) == sorted(zg.files) and len(zg.files) == n_keys

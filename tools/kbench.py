@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--skip-pillar", action="store_true")
     ap.add_argument("--skip-corr", action="store_true")
     ap.add_argument("--train-bn", action="store_true")
+    ap.add_argument("--skip-deflate", action="store_true")
     args = ap.parse_args()
     lib = _lib.load()
     dev = torch.device("cuda:0")
@@ -131,6 +132,24 @@ def main():
             runs.append(("fused gen%d x6" % cg, cgen(cg, lambda: blk_l.lookup_conv(coords, packed, relu=True))))
             runs.append(("fused gen%d int x6" % cg, cgen(cg, lambda: blk_l.lookup_conv(grid, packed, relu=True))))
             runs.append(("fused gen%d smooth x6" % cg, cgen(cg, lambda: blk_l.lookup_conv(smooth, packed, relu=True))))
+    if not args.skip_deflate:
+        # export writer: the maps of one batch (flow + dynamicness of both directions) as channel slices of two packed
+        # 16-float decoder buffers, ~5 % occupied; empty cells: flow 0, dynamicness = the softmax denormal
+        from liso_b200.slim.npz_stream import DeflateEncoder
+
+        g = torch.Generator(device="cpu").manual_seed(1)
+        bevs = []
+        for _ in range(2):
+            occ = torch.rand(B, H, Wd, generator=g) < 0.05
+            bev = torch.zeros(B, H, Wd, 16)
+            bev[..., 5] = torch.where(occ, torch.rand(B, H, Wd, generator=g), torch.full((), 3.8e-44))
+            bev[..., 7:9] = torch.where(occ[..., None], torch.randn(B, H, Wd, 2, generator=g), torch.zeros(()))
+            bevs.append(bev.to(dev))
+        enc = DeflateEncoder(dev, slots=1)
+        views = [b[..., 7:9] for b in bevs] + [b[..., 5] for b in bevs]
+        packed = [v.contiguous() for v in views]
+        runs.append(("deflate strided", lambda: enc.encode(views, 0)))
+        runs.append(("deflate packed", lambda: enc.encode(packed, 0)))
     with torch.no_grad():
         for name, fn in runs:
             for _ in range(3):
