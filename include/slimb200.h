@@ -383,6 +383,8 @@ typedef struct {
   int32_t cell_stride;    /* in words, >= words_per_cell */
   uint32_t n_words;       /* > 0 */
   uint32_t first_chunk;   /* filled by slimb200_deflate_plan */
+  uint32_t crc_geo;       /* filled by slimb200_deflate_plan: sum_{i < n_words} x^(32 i) mod P (CRC of a constant fill) */
+  uint32_t reserved;
 } slimb200_deflate_member;
 int slimb200_deflate_plan(slimb200_deflate_member* members /*host[n_members]*/, int32_t n_members, int64_t* total_chunks,
                           size_t* workspace_bytes, size_t* out_bound);

@@ -81,7 +81,7 @@ DECODE_BEV_CHANNELS, DECODE_POINT_CHANNELS = 16, 14
 
 class DeflateMember(C.Structure):
     _fields_ = [("src", C.c_void_p), ("words_per_cell", C.c_int32), ("cell_stride", C.c_int32), ("n_words", C.c_uint32),
-                ("first_chunk", C.c_uint32)]
+                ("first_chunk", C.c_uint32), ("crc_geo", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 DEFLATE_CHUNK_BYTES, DEFLATE_TABLE_BYTES = 8192, (256 + 2049 + 8192) * 4

@@ -14,11 +14,15 @@
 //   * thread = 4 consecutive words.  Runs are found with a block-wide prefix max (last run-breaking word before me) and
 //     suffix min (first run-breaking word after me); the tokens of a run are a function of the byte offset from its start,
 //     so every thread emits exactly the tokens that START inside its 16 bytes -- no token crosses a thread boundary
-//     decision.  Pass 1 counts bits, a block scan turns them into bit positions, pass 2 ORs the codes into shared memory.
-//   * CRC-32: pure remainders are linear, R(A|B) = R(A) x^(8|B|) + R(B), and R(zero words) = 0.  A thread with non-zero
-//     words folds them with the byte table, multiplies by x^(bits behind it in the chunk) (table), the CTA XORs, one
-//     thread multiplies by x^(bits behind the chunk in the member) and XORs into the member's accumulator.  The host
-//     adds the constant crc32(npy header | zeros) of the member's shape: crc(header | data) = that ^ R(data).
+//     decision.  Pass 1 counts bits (and keeps up to 128 of them in registers), a block scan turns the counts into bit
+//     positions, pass 2 ORs the codes into shared memory (only a thread with more than 128 bits generates its tokens twice).
+//   * CRC-32: pure remainders are linear, R(A|B) = R(A) x^(8|B|) + R(B), and R(zero words) = 0.  The kernel folds
+//     data ^ background (background = the member's first word repeated; zero almost everywhere, also for the dynamicness
+//     maps): a thread with foreground words folds them with the byte table, multiplies by x^(bits behind it in the chunk)
+//     (table), the CTA XORs, one thread multiplies by x^(bits behind the chunk in the member) and XORs into the member's
+//     accumulator; the member's first chunk adds R(background) = R(word) * sum_i x^(32 i) (the geometric factor comes
+//     with the member).  The host adds the constant crc32(npy header | zeros) of the member's shape:
+//     crc(header | data) = that ^ R(data).
 //   * k_deflate_scan turns chunk sizes into offsets, k_deflate_gather packs the chunks into the output stream.
 #include "common.cuh"
 
@@ -114,6 +118,19 @@ struct BitCounter {
   uint32_t n = 0;
   __device__ __forceinline__ void put(Code c) { n += c.n; }
 };
+struct BitBuffer {  // pass 1: counts the bits AND keeps the first 128 of them, so that most threads never generate tokens twice
+  uint64_t lo = 0, hi = 0;
+  uint32_t n = 0;
+  __device__ __forceinline__ void put(Code c) {
+    if (n < 64u) {
+      lo |= (uint64_t)c.bits << n;
+      if (n + c.n > 64u) hi |= (uint64_t)c.bits >> (64u - n);
+    } else if (n < 128u) {
+      hi |= (uint64_t)c.bits << (n - 64u);
+    }
+    n += c.n;
+  }
+};
 struct BitWriter {  // ORs codes into the shared chunk image starting at bit `pos`
   uint32_t* buf;
   uint64_t acc = 0;
@@ -179,7 +196,8 @@ k_deflate_chunks(const slimb200_deflate_member* __restrict__ members, int n_memb
   __shared__ uint32_t buf[SLOT_WORDS];
   __shared__ uint32_t T[256];
   __shared__ int s_last[WARPS], s_first[WARPS];
-  __shared__ uint32_t s_bits[WARPS], s_crc[WARPS];
+  __shared__ uint32_t s_bits[WARPS], s_crc[WARPS], s_edge[WARPS];
+  __shared__ uint32_t s_total;
   __shared__ int s_member;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const uint32_t chunk = blockIdx.x;
@@ -191,7 +209,6 @@ k_deflate_chunks(const slimb200_deflate_member* __restrict__ members, int n_memb
     }
     s_member = lo;
   }
-  for (int i = tid; i < SLOT_WORDS; i += THREADS) buf[i] = 0;
   if (tid < 256) T[tid] = tab[TAB_T + tid];
   __syncthreads();
   const int mi = s_member;
@@ -200,10 +217,13 @@ k_deflate_chunks(const slimb200_deflate_member* __restrict__ members, int n_memb
   const uint32_t w0 = c * CHUNK_WORDS;
   const int nw = (int)min((uint32_t)CHUNK_WORDS, m.n_words - w0);
   const int i0 = 4 * tid, nv = max(0, min(4, nw - i0));
+  const uint32_t* src = static_cast<const uint32_t*>(m.src);
+  // the member's background word (its first word): the CRC below runs over data ^ background, which is zero almost
+  // everywhere -- for the dynamicness maps, whose empty cells hold a non-zero constant, as much as for the flow maps
+  const uint32_t bg = __ldg(src);
 
   // ---- this thread's 4 words
   uint32_t w[4] = {0u, 0u, 0u, 0u};
-  const uint32_t* src = static_cast<const uint32_t*>(m.src);
   if (nv > 0) {
     const uint32_t g = w0 + i0;
     if (m.cell_stride == m.words_per_cell && nv == 4 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
@@ -221,21 +241,19 @@ k_deflate_chunks(const slimb200_deflate_member* __restrict__ members, int n_memb
   }
 
   // ---- which of my words repeat the word before them (the chunk's first word never does)
-  __shared__ uint32_t s_edge[WARPS];
   if (lane == 31) s_edge[wid] = w[3];
   uint32_t prev = __shfl_up_sync(0xffffffffu, w[3], 1);
   __syncthreads();
   if (lane == 0 && wid > 0) prev = s_edge[wid - 1];
   uint32_t rep = 0;
-  bool any_nz = false;
+  bool any_fg = false;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     if (k < nv && (i0 + k) > 0 && w[k] == (k ? w[k - 1] : prev)) rep |= 1u << k;
-    any_nz |= (k < nv && w[k] != 0u);
+    any_fg |= (k < nv && w[k] != bg);
   }
   // ---- run words right before / behind my words: prefix max of the last run-breaking word, suffix min of the first one
   int last = -1, first = nw;
-  uint32_t crc = 0;
 #pragma unroll
   for (int k = 0; k < 4; ++k)
     if (k < nv && !((rep >> k) & 1u)) {
@@ -255,14 +273,29 @@ k_deflate_chunks(const slimb200_deflate_member* __restrict__ members, int n_memb
   if (lane == 0) ex_l = -1;
   if (lane == 31) ex_f = nw;
   __syncthreads();
-  for (int k = 0; k < wid; ++k) ex_l = max(ex_l, s_last[k]);
-  for (int k = wid + 1; k < WARPS; ++k) ex_f = min(ex_f, s_first[k]);
+  if (wid == 0) {  // second level: exclusive prefix max / suffix min over the warps' aggregates, by warp 0
+    int a = lane < WARPS ? s_last[lane] : -1, b = lane < WARPS ? s_first[lane] : nw;
+#pragma unroll
+    for (int d = 1; d < WARPS; d <<= 1) {
+      const int x = __shfl_up_sync(0xffffffffu, a, d), y = __shfl_down_sync(0xffffffffu, b, d);
+      if (lane >= d) a = max(a, x);
+      if (lane + d < WARPS) b = min(b, y);
+    }
+    const int ea = __shfl_up_sync(0xffffffffu, a, 1), eb = __shfl_down_sync(0xffffffffu, b, 1);
+    if (lane < WARPS) {
+      s_last[lane] = lane == 0 ? -1 : ea;
+      s_first[lane] = lane == WARPS - 1 ? nw : eb;
+    }
+  }
+  __syncthreads();
+  ex_l = max(ex_l, s_last[wid]);
+  ex_f = min(ex_f, s_first[wid]);
   const int zb = i0 - 1 - ex_l, za = ex_f - (i0 + nv);
 
-  // ---- pass 1: bits of my tokens -> bit position
-  BitCounter cnt;
-  if (nv > 0) thread_tokens(cnt, w, rep, nv, zb, za);
-  uint32_t inc = cnt.n;
+  // ---- pass 1: my tokens -> bit count (and the bits themselves when they fit 128) -> bit position
+  BitBuffer tk;
+  if (nv > 0) thread_tokens(tk, w, rep, nv, zb, za);
+  uint32_t inc = tk.n;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     const uint32_t a = __shfl_up_sync(0xffffffffu, inc, d);
@@ -270,12 +303,13 @@ k_deflate_chunks(const slimb200_deflate_member* __restrict__ members, int n_memb
   }
   if (lane == 31) s_bits[wid] = inc;
 
-  // ---- CRC remainder of my words, moved to the end of the chunk
-  if (any_nz) {
+  // ---- CRC remainder of (my words ^ background), moved to the end of the chunk
+  uint32_t crc = 0;
+  if (any_fg) {
 #pragma unroll
     for (int k = 0; k < 4; ++k)
       if (k < nv) {
-        crc ^= w[k];
+        crc ^= w[k] ^ bg;
         crc = T[crc & 255u] ^ (crc >> 8);
         crc = T[crc & 255u] ^ (crc >> 8);
         crc = T[crc & 255u] ^ (crc >> 8);
@@ -287,42 +321,76 @@ k_deflate_chunks(const slimb200_deflate_member* __restrict__ members, int n_memb
   for (int d = 16; d > 0; d >>= 1) crc ^= __shfl_xor_sync(0xffffffffu, crc, d);
   if (lane == 0) s_crc[wid] = crc;
   __syncthreads();
-  uint32_t pos = 3 + inc - cnt.n, total = 3;
-  for (int k = 0; k < WARPS; ++k) {
-    if (k < wid) pos += s_bits[k];
-    total += s_bits[k];
+  if (wid == 0) {  // second level: exclusive prefix sum of the warps' bit counts (+ total), XOR of their CRCs
+    const uint32_t v = lane < WARPS ? s_bits[lane] : 0u;
+    uint32_t a = v, x = lane < WARPS ? s_crc[lane] : 0u;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, a, d);
+      if (lane >= d) a += y;
+      x ^= __shfl_xor_sync(0xffffffffu, x, d);
+    }
+    if (lane < WARPS) s_bits[lane] = a - v;
+    if (lane == 31) {
+      s_total = 3u + a;
+      s_crc[0] = x;
+    }
   }
-
-  // ---- pass 2: write the codes
-  if (cnt.n) {
-    BitWriter bw(buf, pos);
-    thread_tokens(bw, w, rep, nv, zb, za);
-    bw.flush();
-  }
+  __syncthreads();
+  const uint32_t pos = 3u + s_bits[wid] + inc - tk.n, total = s_total;
   // block header (BFINAL 0, BTYPE 01 -> bits 0,1,0), end-of-block (7 zero bits), stored-block header (BFINAL of the member's
   // last chunk, BTYPE 00), zero padding to the byte boundary, LEN = 0x0000, NLEN = 0xFFFF
   const uint32_t nbytes = (total + 10 + 7) >> 3;
+  const int nwords_out = min((int)((nbytes + 4 + 3) >> 2) + 1, SLOT_WORDS);  // (+1: the gather's funnel shift reads one word ahead)
+  for (int i = tid; i < nwords_out; i += THREADS) buf[i] = 0u;  // only what this chunk's stream occupies
+  __syncthreads();
+
+  // ---- pass 2: write the codes (from the buffered bits; threads with more than 128 bits generate their tokens again)
+  if (tk.n) {
+    if (tk.n <= 128u) {
+      const uint32_t sh = pos & 31u;
+      uint32_t wi = pos >> 5;
+      const uint32_t piece[4] = {(uint32_t)tk.lo, (uint32_t)(tk.lo >> 32), (uint32_t)tk.hi, (uint32_t)(tk.hi >> 32)};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (32u * k < tk.n && piece[k]) {
+          atomicOr(&buf[wi + k], piece[k] << sh);
+          if (sh && (piece[k] >> (32u - sh))) atomicOr(&buf[wi + k + 1], piece[k] >> (32u - sh));
+        }
+      }
+    } else {
+      BitWriter bw(buf, pos);
+      thread_tokens(bw, w, rep, nv, zb, za);
+      bw.flush();
+    }
+  }
   if (tid == 0) {
     atomicOr(&buf[0], 2u);
     if (c == n_chunks - 1) atomicOr(&buf[(total + 7) >> 5], 1u << ((total + 7) & 31));
     atomicOr(&buf[(nbytes + 2) >> 2], 0xFFu << (8 * ((nbytes + 2) & 3)));
     atomicOr(&buf[(nbytes + 3) >> 2], 0xFFu << (8 * ((nbytes + 3) & 3)));
     chunk_bytes[chunk] = nbytes + 4;
-    uint32_t r = 0;
-    for (int k = 0; k < WARPS; ++k) r ^= s_crc[k];
-    if (r) {
-      if (c != n_chunks - 1) {  // bits behind this chunk: (n_chunks - 2 - c) full chunks + the member's last chunk
-        const uint32_t last_words = m.n_words - (n_chunks - 1) * CHUNK_WORDS;
-        r = gf_mul(__ldg(tab + TAB_XPC + (n_chunks - 2 - c)), r);
-        r = gf_mul(__ldg(tab + TAB_XPW + last_words), r);
-      }
-      atomicXor(&member_out[4 * mi + 2], r);
+    uint32_t r = s_crc[0];
+    if (r && c != n_chunks - 1) {  // bits behind this chunk: (n_chunks - 2 - c) full chunks + the member's last chunk
+      const uint32_t last_words = m.n_words - (n_chunks - 1) * CHUNK_WORDS;
+      r = gf_mul(__ldg(tab + TAB_XPC + (n_chunks - 2 - c)), r);
+      r = gf_mul(__ldg(tab + TAB_XPW + last_words), r);
     }
+    if (c == 0 && bg) {
+      // + the remainder of the background itself: n_words copies of bg = R(bg) * sum_i x^(32 i); the geometric factor
+      // depends on the member's length only and comes with the member (slimb200_deflate_plan)
+      uint32_t rb = bg;
+      rb = T[rb & 255u] ^ (rb >> 8);
+      rb = T[rb & 255u] ^ (rb >> 8);
+      rb = T[rb & 255u] ^ (rb >> 8);
+      rb = T[rb & 255u] ^ (rb >> 8);
+      r ^= gf_mul(m.crc_geo, rb);
+    }
+    if (r) atomicXor(&member_out[4 * mi + 2], r);
   }
   __syncthreads();
   uint32_t* dst = scratch + (size_t)chunk * SLOT_WORDS;
-  const int nwords_out = (int)((nbytes + 4 + 3) >> 2) + 1;  // (+1: the gather's funnel shift reads one word ahead)
-  for (int i = tid; i < nwords_out && i < SLOT_WORDS; i += THREADS) dst[i] = buf[i];
+  for (int i = tid; i < nwords_out; i += THREADS) dst[i] = buf[i];
 }
 
 // chunk sizes -> chunk offsets, member {offset, bytes, (crc), chunks}, total; one CTA
@@ -397,6 +465,19 @@ extern "C" int slimb200_deflate_plan(slimb200_deflate_member* members, int32_t n
     if (n > SLIMB200_DEFLATE_MAX_CHUNKS) return SLIMB200_E_UNSUPPORTED;
     m.first_chunk = (uint32_t)chunks;
     chunks += n;
+    // G(n_words) = sum_{i < n_words} x^(32 i) mod P by doubling: G(2L) = G(L) (1 + x^(32 L)), G(L + 1) = G(L) x^32 + 1
+    uint32_t g = 0u, xl = 0x80000000u;
+    const uint32_t x32 = gf_xpow(32);
+    for (int bit = 31; bit >= 0; --bit) {
+      g ^= gf_mul(g, xl);
+      xl = gf_mul(xl, xl);
+      if ((m.n_words >> bit) & 1u) {
+        g = gf_mul(g, x32) ^ 0x80000000u;
+        xl = gf_mul(xl, x32);
+      }
+    }
+    m.crc_geo = g;
+    m.reserved = 0;
   }
   if (chunks * (uint64_t)SLOT_BYTES > 0xFFFFFFFFull) return SLIMB200_E_UNSUPPORTED;  // 32-bit stream offsets
   *total_chunks = (int64_t)chunks;
