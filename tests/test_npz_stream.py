@@ -100,6 +100,40 @@ def test_npz_framing_reads_back_with_np_load(tmp_path):
         np.load(io.BytesIO(bad))["a"]
 
 
+def _gf_mul(a, b):  # GF(2)[x] / P in zlib's reflected representation (bit 31 = x^0)
+    p = 0
+    for i in range(32):
+        if a & (0x80000000 >> i):
+            p ^= b
+        b = (b >> 1) ^ (0xEDB88320 if b & 1 else 0)
+    return p
+
+
+def test_plan_geometric_factor_gives_the_crc_of_a_constant_fill():
+    """Host-only part of the C ABI: slimb200_deflate_plan cuts members into chunks and fills crc_geo = sum_i x^(32 i), with
+    which the kernel turns the remainder of ONE background word into the remainder of the whole constant fill."""
+    import ctypes as C
+
+    from liso_b200 import _lib
+
+    lib = _lib.load()
+    sizes = [1, 2, 3, 2048, 2049, 5000, 640 * 640, 640 * 640 * 2, 920 * 920 * 2]
+    members = (_lib.DeflateMember * len(sizes))()
+    for m, n in zip(members, sizes):
+        m.src, m.words_per_cell, m.cell_stride, m.n_words = 4096, 1, 16, n  # (a fake, aligned device address: nothing is launched)
+    total, ws, bound = C.c_int64(), C.c_size_t(), C.c_size_t()
+    assert lib.slimb200_deflate_plan(members, len(sizes), C.byref(total), C.byref(ws), C.byref(bound)) == 0
+    assert total.value == sum((n + 2047) // 2048 for n in sizes) and [m.first_chunk for m in members][:4] == [0, 1, 2, 3]
+    assert ws.value >= total.value * 9232 and bound.value >= total.value * 9000
+    word = np.array([3.8e-44], np.float32)  # the softmax denormal of an empty pillar
+    r_word = zlib.crc32(word.tobytes()) ^ zlib.crc32(bytes(4))
+    for m, n in zip(members, sizes):
+        fill = np.full(n, word[0], np.float32).tobytes()
+        assert _gf_mul(m.crc_geo, r_word) == zlib.crc32(fill) ^ zlib.crc32(bytes(len(fill))), n
+    members[0].n_words = 0
+    assert lib.slimb200_deflate_plan(members, 1, C.byref(total), C.byref(ws), C.byref(bound)) == -1  # empty member
+
+
 def test_cell_stride_detection():
     enc = npz_stream.DeflateEncoder._cells
     bev = torch.zeros(2, 6, 5, 16)
