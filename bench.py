@@ -560,7 +560,12 @@ def main():
         from liso_b200.slim.export import run_flow_export
         from liso_b200.synth import SyntheticExportDataset
 
-        base = args.export_dir or tempfile.mkdtemp(prefix="slimb200_export_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        base = args.export_dir
+        if not base:
+            try:
+                base = tempfile.mkdtemp(prefix="slimb200_export_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+            except OSError:
+                base = tempfile.mkdtemp(prefix="slimb200_export_")
         main.set_decode("last")  # the export reads the last iteration only (experiment.py:391-399); identical exported tensors
         main.model.outputs_alias_static_buffers = True
         n_cpu = n_cpu_rank * world  # cores this rank may run on (its affinity mask) x ranks

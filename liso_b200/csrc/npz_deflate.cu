@@ -45,10 +45,10 @@ static_assert((3 + CHUNK_BYTES * 9 + 7 + 3 + 7 + 32 + 7) / 8 + 8 <= SLOT_BYTES, 
 // GF(2)[x] / P in the reflected representation zlib uses (bit 31 = x^0): a * b mod P
 __host__ __device__ __forceinline__ uint32_t gf_mul(uint32_t a, uint32_t b) {
   uint32_t p = 0;
-#pragma unroll 4
+#pragma unroll
   for (int i = 0; i < 32; ++i) {
-    if (a & (0x80000000u >> i)) p ^= b;
-    b = (b >> 1) ^ ((b & 1u) ? POLY : 0u);
+    p ^= b & (0u - ((a >> (31 - i)) & 1u));
+    b = (b >> 1) ^ (POLY & (0u - (b & 1u)));
   }
   return p;
 }
@@ -114,40 +114,26 @@ __device__ __forceinline__ Code match_code(int len, uint32_t dist_sym) {  // <le
 }
 constexpr uint32_t DIST_1 = 0, DIST_4 = 3;
 
-struct BitCounter {
+// A thread's tokens: at most 4 words x 4 literals x 9 bits = 144 bits (a run costs far less), kept in registers between the
+// pass that counts them and the pass that writes them -- tokens are generated once.
+struct BitBuffer {
+  uint64_t q0 = 0, q1 = 0, q2 = 0;
   uint32_t n = 0;
-  __device__ __forceinline__ void put(Code c) { n += c.n; }
-};
-struct BitBuffer {  // pass 1: counts the bits AND keeps the first 128 of them, so that most threads never generate tokens twice
-  uint64_t lo = 0, hi = 0;
-  uint32_t n = 0;
-  __device__ __forceinline__ void put(Code c) {
+  __device__ __forceinline__ void put(uint64_t bits, uint32_t len) {  // len <= 40
+    const uint32_t sh = n & 63u;
+    const uint64_t lo = bits << sh, hi = sh ? bits >> (64u - sh) : 0ull;
     if (n < 64u) {
-      lo |= (uint64_t)c.bits << n;
-      if (n + c.n > 64u) hi |= (uint64_t)c.bits >> (64u - n);
+      q0 |= lo;
+      q1 |= hi;
     } else if (n < 128u) {
-      hi |= (uint64_t)c.bits << (n - 64u);
+      q1 |= lo;
+      q2 |= hi;
+    } else {
+      q2 |= lo;
     }
-    n += c.n;
+    n += len;
   }
-};
-struct BitWriter {  // ORs codes into the shared chunk image starting at bit `pos`
-  uint32_t* buf;
-  uint64_t acc = 0;
-  int nb, w;
-  __device__ __forceinline__ BitWriter(uint32_t* b, uint32_t pos) : buf(b), nb(pos & 31), w(pos >> 5) {}
-  __device__ __forceinline__ void put(Code c) {
-    acc |= (uint64_t)c.bits << nb;
-    nb += c.n;
-    if (nb >= 32) {
-      atomicOr(&buf[w++], (uint32_t)acc);
-      acc >>= 32;
-      nb -= 32;
-    }
-  }
-  __device__ __forceinline__ void flush() {
-    if (nb > 0 && (uint32_t)acc) atomicOr(&buf[w], (uint32_t)acc);
-  }
+  __device__ __forceinline__ void put(Code c) { put((uint64_t)c.bits, (uint32_t)c.n); }
 };
 
 // tokens of a run of `run_bytes` bytes (words equal to the word before the run) that START inside [lo, hi) (byte offsets from
@@ -164,21 +150,22 @@ __device__ __forceinline__ void run_tokens(Sink& s, int run_bytes, int lo, int h
 }
 
 // the tokens that start inside this thread's words [i0, i0 + nv); rep bit k: word k equals the word before it;
-// zb / za = run words right before / behind my words
-template <class Sink>
-__device__ __forceinline__ void thread_tokens(Sink& s, const uint32_t (&w)[4], uint32_t rep, int nv, int zb, int za) {
+// zb / za = run words right before / behind my words; lit[v] = code | length << 16 of literal byte v (shared memory)
+__device__ __forceinline__ void thread_tokens(BitBuffer& s, const uint32_t (&w)[4], uint32_t rep, int nv, int zb, int za,
+                                              const uint32_t* __restrict__ lit) {
   int i = 0;
   while (i < nv) {
     if (!((rep >> i) & 1u)) {
       const uint32_t v = w[i];
       if (v == 0u) {  // 00 00 00 00 as literal + <distance 1, length 3>: 20 bits instead of 32
-        s.put(lit_code(0));
-        s.put(match_code(3, DIST_1));
+        const Code m3 = match_code(3, DIST_1);
+        s.put((uint64_t)(lit[0] & 0xffffu) | ((uint64_t)m3.bits << 8), 8u + (uint32_t)m3.n);
       } else {
-        s.put(lit_code(v & 255u));
-        s.put(lit_code((v >> 8) & 255u));
-        s.put(lit_code((v >> 16) & 255u));
-        s.put(lit_code(v >> 24));
+        const uint32_t c0 = lit[v & 255u], c1 = lit[(v >> 8) & 255u], c2 = lit[(v >> 16) & 255u], c3 = lit[v >> 24];
+        const uint32_t n0 = c0 >> 16, n1 = c1 >> 16, n2 = c2 >> 16, n3 = c3 >> 16;
+        const uint64_t bits = (uint64_t)(c0 & 0xffffu) | ((uint64_t)(c1 & 0xffffu) << n0) | ((uint64_t)(c2 & 0xffffu) << (n0 + n1)) |
+                              ((uint64_t)(c3 & 0xffffu) << (n0 + n1 + n2));
+        s.put(bits, n0 + n1 + n2 + n3);
       }
       ++i;
     } else {
@@ -194,22 +181,29 @@ __global__ void __launch_bounds__(THREADS)
 k_deflate_chunks(const slimb200_deflate_member* __restrict__ members, int n_members, const uint32_t* __restrict__ tab,
                  uint32_t* __restrict__ scratch, uint32_t* __restrict__ chunk_bytes, uint32_t* __restrict__ member_out) {
   __shared__ uint32_t buf[SLOT_WORDS];
-  __shared__ uint32_t T[256];
+  __shared__ uint32_t T[256], LIT[256];
   __shared__ int s_last[WARPS], s_first[WARPS];
   __shared__ uint32_t s_bits[WARPS], s_crc[WARPS], s_edge[WARPS];
   __shared__ uint32_t s_total;
   __shared__ int s_member;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const uint32_t chunk = blockIdx.x;
-  if (tid == 0) {  // the member this chunk belongs to: last one with first_chunk <= chunk
-    int lo = 0, hi = n_members - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (members[mid].first_chunk <= chunk) lo = mid; else hi = mid - 1;
+  if (wid == 0) {  // the member this chunk belongs to = the last one with first_chunk <= chunk (first_chunk ascends): the
+                   // warp looks at 32 members per round
+    int cnt = 0;
+    for (int base = 0; base < n_members; base += 32) {
+      const bool le = base + lane < n_members && members[base + lane].first_chunk <= chunk;
+      const int n = __popc(__ballot_sync(0xffffffffu, le));
+      cnt += n;
+      if (n < 32) break;
     }
-    s_member = lo;
+    if (lane == 0) s_member = cnt - 1;
   }
-  if (tid < 256) T[tid] = tab[TAB_T + tid];
+  if (tid < 256) {
+    T[tid] = tab[TAB_T + tid];
+    const Code lc = lit_code((uint32_t)tid);
+    LIT[tid] = lc.bits | ((uint32_t)lc.n << 16);
+  }
   __syncthreads();
   const int mi = s_member;
   const slimb200_deflate_member m = members[mi];
@@ -231,12 +225,15 @@ k_deflate_chunks(const slimb200_deflate_member* __restrict__ members, int n_memb
       w[0] = v.x, w[1] = v.y, w[2] = v.z, w[3] = v.w;
     } else {
       const uint32_t wpc = (uint32_t)m.words_per_cell;
+      uint32_t cell = wpc == 1u ? g : (wpc == 2u ? g >> 1 : g / wpc), within = g - cell * wpc;  // (one division at most)
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (k < nv) {
-          const uint32_t cell = (g + k) / wpc, within = (g + k) - cell * wpc;
-          w[k] = __ldg(src + (size_t)cell * (size_t)m.cell_stride + within);
+      for (int k = 0; k < 4; ++k) {
+        if (k < nv) w[k] = __ldg(src + (size_t)cell * (size_t)m.cell_stride + within);
+        if (++within == wpc) {
+          within = 0;
+          ++cell;
         }
+      }
     }
   }
 
@@ -294,7 +291,7 @@ k_deflate_chunks(const slimb200_deflate_member* __restrict__ members, int n_memb
 
   // ---- pass 1: my tokens -> bit count (and the bits themselves when they fit 128) -> bit position
   BitBuffer tk;
-  if (nv > 0) thread_tokens(tk, w, rep, nv, zb, za);
+  if (nv > 0) thread_tokens(tk, w, rep, nv, zb, za, LIT);
   uint32_t inc = tk.n;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -345,23 +342,18 @@ k_deflate_chunks(const slimb200_deflate_member* __restrict__ members, int n_memb
   for (int i = tid; i < nwords_out; i += THREADS) buf[i] = 0u;  // only what this chunk's stream occupies
   __syncthreads();
 
-  // ---- pass 2: write the codes (from the buffered bits; threads with more than 128 bits generate their tokens again)
+  // ---- pass 2: OR the buffered bits into the chunk image
   if (tk.n) {
-    if (tk.n <= 128u) {
-      const uint32_t sh = pos & 31u;
-      uint32_t wi = pos >> 5;
-      const uint32_t piece[4] = {(uint32_t)tk.lo, (uint32_t)(tk.lo >> 32), (uint32_t)tk.hi, (uint32_t)(tk.hi >> 32)};
+    const uint32_t sh = pos & 31u;
+    const uint32_t wi = pos >> 5;
+    const uint32_t piece[6] = {(uint32_t)tk.q0, (uint32_t)(tk.q0 >> 32), (uint32_t)tk.q1, (uint32_t)(tk.q1 >> 32), (uint32_t)tk.q2,
+                               (uint32_t)(tk.q2 >> 32)};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (32u * k < tk.n && piece[k]) {
-          atomicOr(&buf[wi + k], piece[k] << sh);
-          if (sh && (piece[k] >> (32u - sh))) atomicOr(&buf[wi + k + 1], piece[k] >> (32u - sh));
-        }
+    for (int k = 0; k < 6; ++k) {
+      if (32u * k < tk.n && piece[k]) {
+        atomicOr(&buf[wi + k], piece[k] << sh);
+        if (sh && (piece[k] >> (32u - sh))) atomicOr(&buf[wi + k + 1], piece[k] >> (32u - sh));
       }
-    } else {
-      BitWriter bw(buf, pos);
-      thread_tokens(bw, w, rep, nv, zb, za);
-      bw.flush();
     }
   }
   if (tid == 0) {
@@ -373,8 +365,12 @@ k_deflate_chunks(const slimb200_deflate_member* __restrict__ members, int n_memb
     uint32_t r = s_crc[0];
     if (r && c != n_chunks - 1) {  // bits behind this chunk: (n_chunks - 2 - c) full chunks + the member's last chunk
       const uint32_t last_words = m.n_words - (n_chunks - 1) * CHUNK_WORDS;
-      r = gf_mul(__ldg(tab + TAB_XPC + (n_chunks - 2 - c)), r);
-      r = gf_mul(__ldg(tab + TAB_XPW + last_words), r);
+      if (last_words == CHUNK_WORDS) {
+        r = gf_mul(__ldg(tab + TAB_XPC + (n_chunks - 1 - c)), r);
+      } else {
+        r = gf_mul(__ldg(tab + TAB_XPC + (n_chunks - 2 - c)), r);
+        r = gf_mul(__ldg(tab + TAB_XPW + last_words), r);
+      }
     }
     if (c == 0 && bg) {
       // + the remainder of the background itself: n_words copies of bg = R(bg) * sum_i x^(32 i); the geometric factor
