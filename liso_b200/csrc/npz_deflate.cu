@@ -144,7 +144,8 @@ __device__ __forceinline__ void run_tokens(Sink& s, int run_bytes, int lo, int h
   const int nfull = run_bytes / 258, r = run_bytes - nfull * 258;
   const int d = (r == 1 || r == 2) ? 3 : 0;
   const int k0 = (lo + 257) / 258;
-  if (k0 < nfull && 258 * k0 < hi) s.put(match_code(k0 == nfull - 1 ? 258 - d : 258, DIST_4));
+  // (the two codes almost every run thread emits, as constants: <258, 4> and <255, 4>; tests/test_npz_stream.py pins them)
+  if (k0 < nfull && 258 * k0 < hi) s.put((k0 == nfull - 1 && d) ? Code{0x31c23u, 18} : Code{0x18a3u, 13});
   const int q = 258 * nfull - d;
   if (r + d >= 3 && q >= lo && q < hi) s.put(match_code(r + d, DIST_4));
 }
@@ -185,7 +186,9 @@ k_deflate_chunks(const slimb200_deflate_member* __restrict__ members, int n_memb
   __shared__ int s_last[WARPS], s_first[WARPS];
   __shared__ uint32_t s_bits[WARPS], s_crc[WARPS], s_edge[WARPS];
   __shared__ uint32_t s_total;
-  __shared__ int s_member;
+  __shared__ int s_member, s_nfg;
+  __shared__ uint4 s_fg[THREADS];      // queue of foreground threads' words ^ background
+  __shared__ uint16_t s_fgpos[THREADS];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const uint32_t chunk = blockIdx.x;
   if (wid == 0) {  // the member this chunk belongs to = the last one with first_chunk <= chunk (first_chunk ascends): the
@@ -197,7 +200,10 @@ k_deflate_chunks(const slimb200_deflate_member* __restrict__ members, int n_memb
       cnt += n;
       if (n < 32) break;
     }
-    if (lane == 0) s_member = cnt - 1;
+    if (lane == 0) {
+      s_member = cnt - 1;
+      s_nfg = 0;
+    }
   }
   if (tid < 256) {
     T[tid] = tab[TAB_T + tid];
@@ -300,19 +306,31 @@ k_deflate_chunks(const slimb200_deflate_member* __restrict__ members, int n_memb
   }
   if (lane == 31) s_bits[wid] = inc;
 
-  // ---- CRC remainder of (my words ^ background), moved to the end of the chunk
-  uint32_t crc = 0;
+  // ---- CRC remainder of (my words ^ background), moved to the end of the chunk.  Threads with foreground words are few
+  // (a couple per warp): they queue their words, and the queue is worked off by the first threads of the CTA, so that
+  // whole warps run the byte-table steps and the shift by x^(bits behind the thread) instead of one or two lanes of every warp
   if (any_fg) {
+    const int slot = atomicAdd(&s_nfg, 1);
+    s_fg[slot] = make_uint4(w[0] ^ bg, w[1] ^ bg, w[2] ^ bg, w[3] ^ bg);
+    s_fgpos[slot] = (uint16_t)(((unsigned)nv << 12) | (unsigned)(nw - (i0 + nv)));  // words, words behind them in the chunk
+  }
+  __syncthreads();
+  uint32_t crc = 0;
+  for (int e = tid; e < s_nfg; e += THREADS) {
+    const uint4 f = s_fg[e];
+    const unsigned meta = s_fgpos[e], nvv = meta >> 12;
+    const uint32_t ww[4] = {f.x, f.y, f.z, f.w};
+    uint32_t x = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      if (k < nv) {
-        crc ^= w[k] ^ bg;
-        crc = T[crc & 255u] ^ (crc >> 8);
-        crc = T[crc & 255u] ^ (crc >> 8);
-        crc = T[crc & 255u] ^ (crc >> 8);
-        crc = T[crc & 255u] ^ (crc >> 8);
+      if ((unsigned)k < nvv) {
+        x ^= ww[k];
+        x = T[x & 255u] ^ (x >> 8);
+        x = T[x & 255u] ^ (x >> 8);
+        x = T[x & 255u] ^ (x >> 8);
+        x = T[x & 255u] ^ (x >> 8);
       }
-    if (crc) crc = gf_mul(__ldg(tab + TAB_XPW + (nw - (i0 + nv))), crc);
+    if (x) crc ^= gf_mul(__ldg(tab + TAB_XPW + (meta & 0xfffu)), x);
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) crc ^= __shfl_xor_sync(0xffffffffu, crc, d);

@@ -69,6 +69,8 @@ def test_fixed_code_tables():
     assert DO.match_code(11)[1] == 13 and DO.match_code(12)[0] == DO.match_code(11)[0] | (1 << 7)
     assert DO.match_code(257)[1] == 8 + 5 + 5
     assert DO.match_code(258, DO.DIST_4) == (0b10100011 | (0b11000 << 8), 13)  # distance symbol 3 = 00011, sent MSB first
+    # the two codes the kernel carries as constants (csrc/npz_deflate.cu::run_tokens)
+    assert DO.match_code(258, DO.DIST_4) == (0x18A3, 13) and DO.match_code(255, DO.DIST_4) == (0x31C23, 18)
 
 
 def test_npz_framing_reads_back_with_np_load(tmp_path):
