@@ -94,13 +94,14 @@ def build_npz(members: Sequence[tuple]) -> bytes:
 class EncodedBatch:
     """What :meth:`DeflateEncoder.fetch` hands out: the streams of all members of one encode call, on the host."""
 
-    def __init__(self, table: np.ndarray, data, shapes, batch: int):
+    def __init__(self, table: np.ndarray, data, shapes, batch: int, rank=None):
         self.table, self.data, self.shapes, self.batch = table, data, shapes, batch
+        self.rank = list(rank) if rank is not None else list(range(len(shapes)))
         self.total_bytes = int(table[-1, 0])
 
     def member(self, view: int, b: int):
         """(shape, stream bytes, crc remainder) of sample ``b`` of the ``view``-th tensor given to ``encode``."""
-        off, n, r, _ = (int(v) for v in self.table[view * self.batch + b])
+        off, n, r, _ = (int(v) for v in self.table[b * len(self.shapes) + self.rank[view]])
         return self.shapes[view], bytes(self.data[off:off + n]), r
 
 
@@ -156,7 +157,14 @@ class DeflateEncoder:
         if plan is not None:
             return plan
         B = int(views[0].shape[0])
-        members = (self._lib.DeflateMember * (len(views) * B))()
+        V = len(views)
+        # member order = sample-major, and inside a sample the views that are slices of the same buffer next to each other
+        # (flow and dynamicness of one direction live in the same packed decoder rows): the second one finds the rows in L2
+        order = sorted(range(V), key=lambda i: (views[i].untyped_storage().data_ptr(), i))
+        rank = [0] * V
+        for r, i in enumerate(order):
+            rank[i] = r
+        members = (self._lib.DeflateMember * (V * B))()
         for vi, v in enumerate(views):
             if v.dtype != torch.float32 or not v.is_cuda or int(v.shape[0]) != B:
                 raise ValueError("DeflateEncoder.encode takes fp32 CUDA tensors with a common batch size")
@@ -165,13 +173,13 @@ class DeflateEncoder:
                 raise ValueError("view with irregular strides %r: pass a contiguous tensor" % (tuple(v.stride()),))
             n_words = int(np.prod(v.shape[1:], dtype=np.int64))
             for b in range(B):
-                m = members[vi * B + b]
+                m = members[b * V + rank[vi]]
                 m.src, m.words_per_cell, m.cell_stride, m.n_words = v.data_ptr() + 4 * b * v.stride(0), cells[0], cells[1], n_words
         total, ws_bytes, bound = C.c_int64(), C.c_size_t(), C.c_size_t()
         self._lib.check(self.lib.slimb200_deflate_plan(members, len(members), C.byref(total), C.byref(ws_bytes), C.byref(bound)))
         host = torch.frombuffer(bytearray(bytes(members)), dtype=torch.uint8)
         plan = dict(n=len(members), B=B, total_chunks=int(total.value), ws_bytes=int(ws_bytes.value), bound=int(bound.value),
-                    members_dev=host.to(self.device), shapes=[tuple(v.shape[1:]) for v in views],
+                    members_dev=host.to(self.device), shapes=[tuple(v.shape[1:]) for v in views], rank=rank,
                     raw_bytes=sum(4 * int(np.prod(v.shape, dtype=np.int64)) for v in views))
         if len(self._plans) > 16:
             self._plans.clear()
@@ -236,7 +244,7 @@ class DeflateEncoder:
         s = self.slots[slot]
         s["evt2"].synchronize()
         table = s["table_host"].numpy().view(np.uint32).copy()
-        return EncodedBatch(table, memoryview(s["host"].numpy()), s["plan"]["shapes"], s["plan"]["B"])
+        return EncodedBatch(table, memoryview(s["host"].numpy()), s["plan"]["shapes"], s["plan"]["B"], s["plan"]["rank"])
 
     def fetch(self, slot: int = 0) -> EncodedBatch:
         self.fetch_begin(slot)

@@ -57,7 +57,7 @@ for rep in range(4):
         sum(m.static_flow.numel() * 4 + m.dynamicness.numel() * 4 for m in mods) / 1e6, getattr(net, "n_graph_captures", 0)))
 sizes = {}
 for v, key in enumerate(export.export_keys(len(mods) * 1 if False else len(mods))):
-    sizes[key] = int(got.table[v * 8, 1])
+    sizes[key] = len(got.member(v, 0)[1])
 print("bytes per member (sample 0):", sizes)
 import zlib
 shape, stream, r = got.member(0, 0)
