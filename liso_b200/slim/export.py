@@ -588,7 +588,7 @@ def _pin(sample):
 
 def run_flow_export(model, dataset, target_dir: str, bev_range_m, *, world_size: int = 1, worker_id: int = 0,
                     batch_size: int = 8, device=None, skip_existing: bool = False, writer_workers: Optional[int] = None,
-                    pipeline_factory=None, compress_on_gpu: bool = False, loader_workers: int = 0,
+                    pipeline_factory=None, compress_on_gpu: Optional[bool] = None, loader_workers: int = 0,
                     unlink_after_write: bool = False, pad_last_batch: bool = True, pack_uploads: bool = True) -> Dict[str, float]:
     """The flow export of ``liso/slim/experiment.py:225-361,363-471`` for the t0 -> t1 pairs of one worker: this rank's
     share of the pairs (modulo rule), batched, through the double-buffered :class:`ExportPipeline`, written by
@@ -598,8 +598,8 @@ def run_flow_export(model, dataset, target_dir: str, bev_range_m, *, world_size:
     ``dataset``: ``len()`` and ``dataset[i] -> (sample_id, sample_t0, sample_t1)`` with un-batched host tensors (see
     :func:`collate_pairs`), or ``(sample_id, t0, t1, t2)`` for the KITTI / nuScenes export: then t0 -> t1, t0 -> t2 and
     t1 -> t2 are computed in one pass per batch (every frame encoded once) and the file holds all 12 maps
-    (``experiment.py:404-456``).  ``compress_on_gpu``: the maps are deflated on the device and the writer threads only frame
-    zip members (same files for ``np.load``).  ``loader_workers``: > 0 moves dataset access, collation and
+    (``experiment.py:404-456``).  ``compress_on_gpu`` (default: on for a CUDA device): the maps are deflated on the device and
+    the writer threads only frame zip members (same files for ``np.load``); off: ``np.savez_compressed`` on host threads.  ``loader_workers``: > 0 moves dataset access, collation and
     pinning to a background thread (> 1: with that many threads fetching samples), like DataLoader workers.
     ``pack_uploads``: every batch is packed into one recycled pinned buffer and uploaded with one copy.
     ``pad_last_batch``: a ragged last batch is filled up with copies of its last sample (outputs discarded) so that no
@@ -607,6 +607,9 @@ def run_flow_export(model, dataset, target_dir: str, bev_range_m, *, world_size:
     counts samples)."""
     import time
 
+    if compress_on_gpu is None:  # default: the device-side writer whenever the stock pipeline drives a CUDA device
+        compress_on_gpu = (pipeline_factory is None and torch.cuda.is_available() and device is not None
+                           and torch.device(device).type == "cuda")
     writer = AsyncNpzWriter(target_dir, bev_range_m, workers=writer_workers, skip_existing=skip_existing,
                             unlink_after_write=unlink_after_write)
     mine = shard_indices(len(dataset), world_size, worker_id)

@@ -318,7 +318,8 @@ def test_gpu_compressed_export_writes_the_same_files(cuda, tmp_path):
     for frames, n_keys in ((2, 6), (3, 14)):
         ds = SyntheticExportDataset(WORKLOADS["T"], 9, frames=frames, pool=3)
         d_ref, d_gpu = os.path.join(str(tmp_path), "ref%d" % frames), os.path.join(str(tmp_path), "gpu%d" % frames)
-        a = export.run_flow_export(model, ds, d_ref, cfg.data.bev_range_m, batch_size=2, device=cuda, writer_workers=2)
+        a = export.run_flow_export(model, ds, d_ref, cfg.data.bev_range_m, batch_size=2, device=cuda, writer_workers=2,
+                                   compress_on_gpu=False)  # np.savez_compressed on host threads
         b = export.run_flow_export(model, ds, d_gpu, cfg.data.bev_range_m, batch_size=2, device=cuda, writer_workers=2,
                                    compress_on_gpu=True)
         assert a["files"] == b["files"] == 9
