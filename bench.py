@@ -163,8 +163,7 @@ def pin_rank_to_local_cores(local_rank: int, world: int, dist):
         mine = cores[k * per:(k + 1) * per] if k < n - 1 else cores[k * per:]
         if not mine:
             return {"pinned": False, "why": "no cores left for this rank"}
-        os.sched_setaffinity(0, mine)
-        torch.set_num_threads(max(1, len(mine)))
+        os.sched_setaffinity(0, mine)  # (torch's intra-op thread count stays what the launcher set: OMP_NUM_THREADS=1 under torchrun)
         return {"pinned": True, "gpu_pci": addr, "gpu_local_cores": len(cores), "cores": "%d-%d (%d)" % (mine[0], mine[-1], len(mine))}
     except Exception as e:  # never fail the bench over affinity
         return {"pinned": False, "why": repr(e)[:200]}

@@ -265,12 +265,12 @@ class PinnedArena:
 
         layout = tuple(_walk(f, plan) for f in frames)
         slot = self.take(off)
-        buf = slot["buf"]
+        raw = slot["buf"].numpy()  # (numpy copies: no intra-op thread team per copy, the GIL is released while bytes move)
 
         def copy(job):
             (o, shape, dtype, n), t = job
             if n:
-                buf[o:o + n].view(dtype).view(shape).copy_(t)
+                np.copyto(raw[o:o + n], t.detach().contiguous().view(torch.uint8).reshape(-1).numpy())
 
         if executor is not None and len(todo) > 1:
             list(executor.map(copy, todo))
