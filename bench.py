@@ -576,10 +576,10 @@ def main():
                                "disk use; wall clock incl. final flush, max over ranks" % (args.export_pool, writers, loaders),
                        "target": base, "decode": "last iteration only (what the export reads)"}
         for kind, frames, n_total in (("pairs", 2, args.export_pairs), ("triples", 3, max(world * args.batch, args.export_pairs // 3))):
-            ds = SyntheticExportDataset(main.W, n_total, frames=frames, pool=args.export_pool, raw=True, motion="shift").prepare(workers=min(8, max(1, n_cpu // world)))
+            ds = SyntheticExportDataset(main.W, n_total, frames=frames, pool=args.export_pool, raw=True, motion="shift", lazy=True).prepare(workers=min(8, max(1, n_cpu // world)))
             tgt = os.path.join(base, "%s_rank%d" % (kind, rank))
             # untimed: graph capture for this frame structure + cuDNN autotune, on the first batch of this rank's share
-            warm = SyntheticExportDataset(main.W, world * args.batch, frames=frames, pool=args.export_pool, raw=True, motion="shift")
+            warm = SyntheticExportDataset(main.W, world * args.batch, frames=frames, pool=args.export_pool, raw=True, motion="shift", lazy=True)
             warm._cache = ds._cache
             run_flow_export(main.model, warm, tgt + "_warm", main.W["bev_range_m"], world_size=world, worker_id=rank, batch_size=args.batch,
                             device=dev, writer_workers=writers, compress_on_gpu=True, loader_workers=loaders, unlink_after_write=True)
@@ -599,7 +599,7 @@ def main():
             del ds, warm
         export_line["triple_vs_three_pair_calls"] = export_line["triples"]["pairs_per_s"] / export_line["pairs"]["pairs_per_s"]
         if world == 1 and args.export_zlib_pairs > 0:  # the round-1 writer for contrast: raw fp32 maps downloaded, zlib on host threads
-            ds = SyntheticExportDataset(main.W, args.export_zlib_pairs, frames=2, pool=args.export_pool, raw=True, motion="shift")
+            ds = SyntheticExportDataset(main.W, args.export_zlib_pairs, frames=2, pool=args.export_pool, raw=True, motion="shift", lazy=True)
             res = run_flow_export(main.model, ds, os.path.join(base, "zlib"), main.W["bev_range_m"], batch_size=args.batch, device=dev,
                                   compress_on_gpu=False, loader_workers=loaders, unlink_after_write=True)
             export_line["pairs_host_zlib_writer"] = {"samples": int(res["pairs"]), "pairs_per_s": res["pairs"] / res["elapsed_s_max"],

@@ -211,9 +211,15 @@ def iterate_batches(indices: Iterable[int], batch_size: int) -> Iterable[List[in
         yield cur
 
 
+def _is_lazy(x) -> bool:
+    """A tensor-to-be: an object with ``shape``, ``dtype`` (torch) and ``write_into(uint8 numpy view)`` -- a sample source that
+    can produce its data straight into the pinned upload buffer (decode / transform and copy in one pass)."""
+    return hasattr(x, "write_into") and hasattr(x, "shape") and hasattr(x, "dtype")
+
+
 def _walk(sample, fn):
-    """The sample structure (dict / list / tensor / anything else) with ``fn`` applied to every tensor."""
-    if torch.is_tensor(sample):
+    """The sample structure (dict / list / tensor / anything else) with ``fn`` applied to every tensor (or lazy tensor)."""
+    if torch.is_tensor(sample) or _is_lazy(sample):
         return fn(sample)
     if isinstance(sample, dict):
         return {k: _walk(v, fn) for k, v in sample.items()}
@@ -258,7 +264,8 @@ class PinnedArena:
         def plan(t):
             nonlocal off
             off = (off + self.ALIGN - 1) // self.ALIGN * self.ALIGN
-            spec = (off, tuple(t.shape), t.dtype, t.numel() * t.element_size())
+            n_el = int(np.prod(t.shape, dtype=np.int64))
+            spec = (off, tuple(t.shape), t.dtype, n_el * torch.empty((), dtype=t.dtype).element_size())
             todo.append((spec, t))
             off += spec[3]
             return spec
@@ -269,7 +276,11 @@ class PinnedArena:
 
         def copy(job):
             (o, shape, dtype, n), t = job
-            if n:
+            if not n:
+                return
+            if _is_lazy(t):
+                t.write_into(raw[o:o + n])
+            else:
                 np.copyto(raw[o:o + n], t.detach().contiguous().view(torch.uint8).reshape(-1).numpy())
 
         if executor is not None and len(todo) > 1:
@@ -580,10 +591,12 @@ def _prefetched(it, depth: int):
 
 def _pin(sample):
     def pin(t):
+        if _is_lazy(t):
+            t = t.materialize()
         return t.pin_memory() if torch.cuda.is_available() and not t.is_pinned() else t
 
     return {k: ([pin(t) for t in v] if isinstance(v, (list, tuple)) else {kk: pin(vv) for kk, vv in v.items()}
-                if isinstance(v, dict) else (pin(v) if torch.is_tensor(v) else v)) for k, v in sample.items()}
+                if isinstance(v, dict) else (pin(v) if (torch.is_tensor(v) or _is_lazy(v)) else v)) for k, v in sample.items()}
 
 
 def run_flow_export(model, dataset, target_dir: str, bev_range_m, *, world_size: int = 1, worker_id: int = 0,

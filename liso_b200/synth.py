@@ -18,7 +18,7 @@ host-side helper kept bit-identical to ``voxelize_pcl`` (``datasets/nuscenes/ana
 """
 from __future__ import annotations
 
-from typing import Any, Dict, List, Tuple
+from typing import Any, Dict, List
 
 import numpy as np
 
@@ -252,6 +252,26 @@ def _sample_of(pc: np.ndarray, bev, grid) -> Dict[str, Any]:
             "pcl_ta": {"pcl": torch.from_numpy(pc[ok]), "pillar_coors": torch.from_numpy(coors[ok])}}
 
 
+class ShiftedCloud:
+    """A cloud that is a cast scene shifted as a whole, produced on demand: ``write_into`` adds the shift while copying into
+    the caller's (pinned) buffer -- one pass over the points instead of transform + copy (``export.PinnedArena.pack``)."""
+
+    def __init__(self, pc: np.ndarray, shift_xy):
+        import torch
+
+        self.pc = pc
+        self.vec = np.array([shift_xy[0], shift_xy[1], 0.0, 0.0], dtype=np.float32)[:pc.shape[1]]
+        self.shape, self.dtype = tuple(pc.shape), torch.float32
+
+    def write_into(self, raw_u8: np.ndarray) -> None:
+        np.add(self.pc, self.vec, out=raw_u8.view(np.float32).reshape(self.shape))
+
+    def materialize(self):
+        import torch
+
+        return torch.from_numpy(self.pc + self.vec)
+
+
 class SyntheticExportDataset:
     """Flow-export workload (BASELINE configs[4]): ``n_samples`` distinct samples of ``frames`` (2: t0, t1 | 3: t0, t1, t2)
     synthetic LiDAR frames each.  The ray caster makes a sample in ~2 s of CPU time, so the samples are drawn from a pool
@@ -265,11 +285,12 @@ class SyntheticExportDataset:
     8f.4), as ``ExportPipeline`` does for such samples -- the host then only moves bytes."""
 
     def __init__(self, workload: Dict[str, Any], n_samples: int, frames: int = 2, pool: int = 16, seed0: int = 5000,
-                 raw: bool = False, motion: str = "rigid"):
+                 raw: bool = False, motion: str = "rigid", lazy: bool = False):
         """``motion``: how a sample differs from the cast scene it is drawn from: "rigid" (yaw rotation + shift) or "shift"
         (shift only: one pass over the points, for hosts with few cores per GPU)."""
         assert frames in (2, 3) and motion in ("rigid", "shift")
         self.motion = motion
+        self.lazy = bool(lazy)  # raw + shift-only samples as `ShiftedCloud`s (written straight into the upload buffer)
         self.workload, self.n, self.frames, self.pool, self.seed0 = workload, int(n_samples), frames, max(1, int(pool)), seed0
         self.raw = bool(raw)
         self._cache: Dict[int, tuple] = {}
@@ -308,6 +329,9 @@ class SyntheticExportDataset:
         bev, grid = self.workload["bev_range_m"], self.workload["img_grid_size"]
         samples = []
         for pc in frames:
+            if yaw == 0.0 and self.raw and self.lazy:
+                samples.append({"pcl_full_w_ground_ta": ShiftedCloud(pc, shift), "raw_scan": True})
+                continue
             if yaw == 0.0:
                 q = pc + np.array([shift[0], shift[1], 0.0, 0.0], dtype=np.float32)[:pc.shape[1]]
             else:

@@ -535,3 +535,28 @@ def test_synthetic_export_dataset_is_deterministic_and_distinct():
     assert not torch.equal(b[1]["pcl_ta"]["pillar_coors"][:50], a[1]["pcl_ta"]["pillar_coors"][:50])
     d0, d1, d2 = export.collate_pairs([ds[0][1:], ds[1][1:]])
     assert d2["pcl_ta"]["pcl"].shape[0] == 2 and d2["pcl_ta"]["pcl_is_valid"].dtype == torch.bool
+
+
+def test_lazy_sample_sources_pack_like_materialised_ones():
+    """Loader protocol: a sample source with shape / dtype / write_into produces its data straight into the pinned upload
+    buffer (ShiftedCloud: shift + copy in one pass); the packed batch equals the one packed from materialised tensors."""
+    from liso_b200.synth import SyntheticExportDataset
+
+    lazy = SyntheticExportDataset(WORKLOADS["T"], 12, frames=3, pool=2, raw=True, motion="shift", lazy=True)
+    eager = SyntheticExportDataset(WORKLOADS["T"], 12, frames=3, pool=2, raw=True, motion="shift", lazy=False)
+    fl = export.collate_pairs([lazy[i][1:] for i in (3, 5)])
+    fe = export.collate_pairs([eager[i][1:] for i in (3, 5)])
+    arena = export.PinnedArena(2)
+    from concurrent.futures import ThreadPoolExecutor
+
+    with ThreadPoolExecutor(2) as ex:
+        packed = arena.pack(fl, ex)
+    views = packed.views(packed.slot["buf"].clone())
+    assert len(views) == 3 and views[0]["raw_scan"] is True
+    for t in range(3):
+        for a, b in zip(views[t]["pcl_full_w_ground_ta"], fe[t]["pcl_full_w_ground_ta"]):
+            assert torch.equal(a, b)
+    pinned = export._pin(fl[1])  # the path without an arena materialises
+    assert torch.equal(pinned["pcl_full_w_ground_ta"][0], fe[1]["pcl_full_w_ground_ta"][0])
+    arena.give_back(packed.slot)
+    assert arena.free.qsize() == 2
