@@ -148,12 +148,12 @@ struct SinkSmem {  // channels-last staging: p[k]
 
 constexpr int V2_PIX = 64;
 constexpr int V2_THREADS = V2_PIX * SLIMB200_MAX_LEVELS;  // 256
-constexpr int V2_PITCH = SLIMB200_MAX_LEVELS * WIN * WIN + 1;  // odd pitch: conflict-free scalar stores
+constexpr int V2_WPITCH = WIN * WIN;  // 49 floats per (pixel, level): odd pitch, conflict-free scalar stores
 
 template <bool NHWC>
 __global__ void __launch_bounds__(V2_THREADS, 2) k_corr_lookup_v2(const __nv_bfloat16* __restrict__ pyr, const LookupGeo G,
                                                                   const float* __restrict__ coords, float* __restrict__ out) {
-  extern __shared__ __align__(16) float s_stage[];  // NHWC only: [pixel][V2_PITCH]
+  extern __shared__ __align__(16) float s_stage[];  // NHWC only: [warp][32 units][49]
   const int lane = lane_id(), warp = warp_id();
   const int level = warp >> 1;
   const int prow = (warp & 1) * 32 + lane;
@@ -170,20 +170,24 @@ __global__ void __launch_bounds__(V2_THREADS, 2) k_corr_lookup_v2(const __nv_bfl
     const __nv_bfloat16* base = pyr + pixel_base(G, b, live ? pix : 0);
     const int panel_stride = G.m_tiles * 2 * 8192;
     if (NHWC) {
-      SinkSmem sink{s_stage + prow * V2_PITCH + level * WIN * WIN};
+      // channels-last: the 49 values of a (pixel, level) are 196 contiguous bytes of the pixel's row.  Every warp transposes
+      // its 32 units through its own shared-memory patch (odd pitch: conflict-free) and writes them out itself -- no
+      // CTA-wide barrier, so the warps of a CTA drift apart and one warp's loads overlap another's blend
+      float* patch = s_stage + warp * (32 * V2_WPITCH);
+      SinkSmem sink{patch + lane * V2_WPITCH};
       lookup_pixel_level(base, panel_stride, G.pitch, W, H, off, cx, cy, inv, live, sink);
+      __syncwarp();
+      const int p0 = i0 + (warp & 1) * 32;
+      const int n_pix = min(32, G.nf - p0);
+      float* dst = out + ((size_t)b * G.nf + p0) * n_ch + level * (WIN * WIN);
+      for (int pp = 0; pp < n_pix; ++pp) {
+        dst[(size_t)pp * n_ch + lane] = patch[pp * V2_WPITCH + lane];
+        if (lane < WIN * WIN - 32) dst[(size_t)pp * n_ch + 32 + lane] = patch[pp * V2_WPITCH + 32 + lane];
+      }
     } else {
       SinkGlobalStrided sink{out + ((size_t)b * n_ch + (size_t)level * WIN * WIN) * G.nf + pix, (size_t)G.nf, live};
       lookup_pixel_level(base, panel_stride, G.pitch, W, H, off, cx, cy, inv, live, sink);
     }
-  }
-  if (NHWC) {
-    __syncthreads();
-    // the tile is one contiguous block of the channels-last tensor: n_pix * n_ch floats
-    const int n_pix = min(V2_PIX, G.nf - i0);
-    float* blk = out + ((size_t)b * G.nf + i0) * n_ch;
-    for (int pp = warp; pp < n_pix; pp += V2_THREADS / 32)
-      for (int k = lane; k < n_ch; k += 32) blk[(size_t)pp * n_ch + k] = s_stage[pp * V2_PITCH + k];
   }
 }
 
@@ -240,7 +244,7 @@ int slimb200_lookup_v2_launch(const void* pyramid, const slimb200_corr_layout* L
   if (rc != SLIMB200_OK) return rc;
   dim3 grid((G.nf + V2_PIX - 1) / V2_PIX, L->batch);
   if (out_layout == SLIMB200_CANVAS_NHWC) {
-    const int smem = V2_PIX * V2_PITCH * 4;
+    const int smem = (V2_THREADS / 32) * 32 * V2_WPITCH * 4;
     SLIMB200_DEVICE(dev, n_sm);
     (void)n_sm;
     static bool attr_set[SLIMB200_MAX_DEVICES] = {false};
