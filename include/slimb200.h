@@ -178,6 +178,9 @@ size_t slimb200_corr_pyramid_bytes(const slimb200_corr_layout* L, int32_t store_
 /* fmap1, fmap2: device (batch, dim, h, w) f32 (dim == 128), 16-byte aligned; fmap_layout says how they are stored:
  *   SLIMB200_CANVAS_NCHW contiguous, or SLIMB200_CANVAS_NHWC = channels-last (batch, h, w, dim), which is what a
  *   channels-last fnet emits and needs no transposition.
+ * store_dtype: SLIMB200_DTYPE_BF16 only (the north star stores the volume in bf16; anything else returns
+ *   SLIMB200_E_UNSUPPORTED -- slimb200_corr_pyramid_bytes / slimb200_corr_lookup accept SLIMB200_DTYPE_F32 for pyramids the
+ *   caller packs itself in the same tiled layout, which the parity tests do).
  * pyramid: device bf16, slimb200_corr_pyramid_bytes() bytes, 128-byte aligned.
  * Computes pyramid[b][i][j] = bf16( sum_d f1[b,d,i] * pool_l(f2)[b,d,j] / sqrt(dim) ) with bf16
  * operands and fp32 accumulation on the tcgen05 tensor cores (pooling folded into the operand:
