@@ -411,6 +411,7 @@ class RAFT(nn.Module):
         # forward and backward direction as two parallel branches of the CUDA graph
         self.concurrent_directions = True
         self.stacked_stems = True  # fnet / cnet 7x7 stems on the same canvas as one stacked convolution
+        self.direction_branches = 2  # parallel branches of the CUDA graph the directions are dealt over
         self.pre_replay_event = None  # see forward_frames
         self.last_forward_was_graph = False
         self.batched_encoders = True  # fnet / cnet over all frames of a pass at once (canvases = slices of one buffer)
@@ -483,7 +484,7 @@ class RAFT(nn.Module):
         wsig = tuple((p.data_ptr(), p._version) for d in pdicts for p in d.values() if p is not None)
         key = (B, self.output_iterations, self.pp_layer.canvas_memory_format, str(dev), torch.backends.cudnn.allow_tf32, self.training,
                self.fused_update_block, self.merge_parallel_convs, self.tap_heads, self.concurrent_directions, FAST_STOCK_OPS,
-               self.fuse_lookup_conv, self.stacked_stems, self.batched_frame_encoding, self.batched_encoders,
+               self.fuse_lookup_conv, self.stacked_stems, self.batched_frame_encoding, self.batched_encoders, self.direction_branches,
                self.output_sink is not None, self.graph_extra_key, wsig)
         slot = "net" if (len(pcls), pairs) == (2, [(0, 1)]) else "net:%d:%s" % (len(pcls), pairs)
         self._last_graph_slot = slot
@@ -580,15 +581,20 @@ class RAFT(nn.Module):
             # maps, context tensors and weights: inside the CUDA graph they are two parallel branches, so the many short
             # kernels of one loop fill the gaps of the other.  Fork / join with stream waits (captured as graph
             # dependencies); every tensor a branch allocates stays on its own stream, the shared inputs outlive the join.
+            # A pair has two directions = two branches; the six directions of a triple are dealt over `direction_branches`
+            # branches (branch j runs directions j, j + n, ...; branch 0 is the capturing stream itself).
             main = torch.cuda.current_stream(imgs[0].device)
-            side = self._branch_stream(imgs[0].device)
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                for k in range(1, len(dirs), 2):
-                    run(k)
-            for k in range(0, len(dirs), 2):
+            n_br = max(1, min(len(dirs), int(self.direction_branches)))
+            sides = [self._branch_stream(imgs[0].device, "bw" if j == 1 else "br%d" % j) for j in range(1, n_br)]
+            for j, side in enumerate(sides, start=1):
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    for k in range(j, len(dirs), n_br):
+                        run(k)
+            for k in range(0, len(dirs), n_br):
                 run(k)
-            main.wait_stream(side)
+            for side in sides:
+                main.wait_stream(side)
             return outs
         for k in range(len(dirs)):
             run(k)
