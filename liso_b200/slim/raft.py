@@ -762,9 +762,9 @@ class RAFT(nn.Module):
         n_in = gru.convz.in_channels
         hx = torch.empty((batch, n_in, h, w), dtype=torch.float32, device=device, memory_format=torch.channels_last)
         rhx = torch.empty_like(hx)
-        hx[:, :Ch].copy_(net)
-        hx[:, Ch:Ch + Cx].copy_(inp)
-        rhx[:, Ch:Ch + Cx].copy_(inp)
+        # [h | inp] into both GRU input buffers with one launch (the first Ch channels of rhx are r * h, rewritten by the gate
+        # kernel before the q convolution reads them: what lands there now does not matter)
+        g.nhwc_pack_into([net, inp], [(hx, 0), (rhx, 0)])
         w_zr = _cat_params(gru, "zr.weight", (gru.convz.weight, gru.convr.weight))
         b_zr = _cat_params(gru, "zr.bias", (gru.convz.bias, gru.convr.bias))
         fh, lh = ub.static_flow_head, ub.classification_head
