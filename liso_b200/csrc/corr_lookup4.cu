@@ -438,13 +438,15 @@ k_lookup_conv_tmem(const __nv_bfloat16* __restrict__ pyr, const LookupGeo G, con
 // segments itself.  No barrier anywhere: warps drift freely.
 constexpr int V5_PIX = 64;
 constexpr int V5_THREADS = V5_PIX * G_LEVELS;  // 256
-constexpr int V5_WPITCH = WIN * WIN;           // 49: odd pitch, conflict-free scalar stores
+constexpr int V5_SPLIT = 4 * WIN;              // the 49 values of a unit leave in two parts: window columns 0..3 (28), 4..6 (21)
+constexpr int V5_WPITCH = V5_SPLIT + 1;        // 29: odd pitch, conflict-free scalar stores
 constexpr uint32_t V5_ZONE_BYTES = V5_THREADS * G_SLOT_BYTES;  // 64 KB
-constexpr uint32_t V5_SMEM_BYTES = V5_ZONE_BYTES + (V5_THREADS / 32) * 32 * V5_WPITCH * 4 + 16;
+constexpr uint32_t V5_SMEM_BYTES = V5_ZONE_BYTES + (V5_THREADS / 32) * 32 * V5_WPITCH * 4 + 16;  // 94 KB: two CTAs per SM
+static_assert(2 * (V5_SMEM_BYTES + 1024) <= 233472, "two CTAs of the fifth-generation lookup must fit one SM");
 
 struct SinkPatch {
   float* p;
-  __device__ __forceinline__ void emit(int k, float v) { p[k] = v; }
+  __device__ __forceinline__ void emit(int k, float v) { p[k < V5_SPLIT ? k : k - V5_SPLIT] = v; }
 };
 
 __device__ __forceinline__ void load_slot_row5(uint32_t my_zone, int r, uint32_t (&raw)[8]) {
@@ -515,6 +517,14 @@ k_corr_lookup_v5(const __nv_bfloat16* __restrict__ pyr, const LookupGeo G, const
     cp_async_commit();
   };
 
+  // this warp's 32 units -> channels-last: values [k0, k0 + n) of every (pixel, level), n contiguous floats per pixel
+  auto flush = [&](float* dst, int n_pix, int k0, int n) {
+    __syncwarp();
+    if (lane < n)
+      for (int pp = 0; pp < n_pix; ++pp) dst[(size_t)pp * n_ch + k0 + lane] = patch[pp * V5_WPITCH + lane];
+    __syncwarp();  // the patch is rewritten by the next part
+  };
+
   Unit cur;
   int tile = blockIdx.x;
   taps(cur, load_coord(tile));
@@ -523,6 +533,9 @@ k_corr_lookup_v5(const __nv_bfloat16* __restrict__ pyr, const LookupGeo G, const
   Coord ahead = load_coord(tile + gridDim.x);
   for (; tile < n_tiles; tile += gridDim.x) {
     const int b = tile / tiles_per_sample, mt = tile - b * tiles_per_sample;
+    const int p0 = mt * V5_PIX + half_tile * 32;
+    const int n_pix = min(32, G.nf - p0);
+    float* const dst = out + ((size_t)b * G.nf + p0) * n_ch + level * (WIN * WIN);
     const bool any_slow = __any_sync(FULL, cur.live && cur.mode == 0);
     const bool any_shift = __any_sync(FULL, cur.live && cur.mode == 2);
     Unit nxt;
@@ -558,6 +571,7 @@ k_corr_lookup_v5(const __nv_bfloat16* __restrict__ pyr, const LookupGeo G, const
 #pragma unroll
         for (int j = 0; j < WIN; ++j)
           sink.emit(i * WIN + j, fmaf(h[j + 1], tap_w1(cur.wy[j], cur.iny, j), h[j] * tap_w0(cur.wy[j], cur.iny, j)));
+        if (i == 3) flush(dst, n_pix, 0, V5_SPLIT);
       }
     } else {
       uint32_t win[9][5];
@@ -598,18 +612,10 @@ k_corr_lookup_v5(const __nv_bfloat16* __restrict__ pyr, const LookupGeo G, const
           if (lane_slow) v = sample_slow2(pyr + cur.base, panel_stride, W, H, off, ix, sample_pos2(cur.cy, inv, j - R, shm1, rh));
           sink.emit(i * WIN + j, v);
         }
+        if (i == 3) flush(dst, n_pix, 0, V5_SPLIT);
       }
     }
-    // this warp's 32 units -> channels-last: 49 contiguous floats per (pixel, level)
-    __syncwarp();
-    const int p0 = mt * V5_PIX + half_tile * 32;
-    const int n_pix = min(32, G.nf - p0);
-    float* dst = out + ((size_t)b * G.nf + p0) * n_ch + level * (WIN * WIN);
-    for (int pp = 0; pp < n_pix; ++pp) {
-      dst[(size_t)pp * n_ch + lane] = patch[pp * V5_WPITCH + lane];
-      if (lane < WIN * WIN - 32) dst[(size_t)pp * n_ch + 32 + lane] = patch[pp * V5_WPITCH + 32 + lane];
-    }
-    __syncwarp();  // the patch is rewritten by the next tile
+    flush(dst, n_pix, V5_SPLIT, WIN * WIN - V5_SPLIT);
     cur = nxt;
   }
   cp_async_wait_all();  // (the loads issued for a tile that does not exist)
