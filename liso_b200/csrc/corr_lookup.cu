@@ -633,7 +633,6 @@ int slimb200_lookup_v2_launch(const void* pyramid, const slimb200_corr_layout* L
 int slimb200_lookup_v3_launch(const void* pyramid, const slimb200_corr_layout* L, const float* coords, float* out, int out_layout,
                               cudaStream_t stream);
 int slimb200_lookup_probe_launch(const void* pyramid, const slimb200_corr_layout* L, const float* coords, float* out, cudaStream_t stream);
-int slimb200_lookup_v5_launch(const void* pyramid, const slimb200_corr_layout* L, const float* coords, float* out, cudaStream_t stream);
 
 extern "C" int slimb200_lookup_generation(int32_t generation) {
   const int prev = g_lookup_generation;
@@ -652,11 +651,9 @@ extern "C" int slimb200_corr_lookup(const void* pyramid, int32_t pyramid_dtype, 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (pyramid_dtype == SLIMB200_DTYPE_BF16 && radius == 3 && g_lookup_generation == 9)  // memory-side probe (kbench only)
     return slimb200_lookup_probe_launch(pyramid, L, coords, out, stream);
-  if (pyramid_dtype == SLIMB200_DTYPE_BF16 && radius == 3 && g_lookup_generation == 3 && out_layout == SLIMB200_CANVAS_NHWC)
-    return slimb200_lookup_v5_launch(pyramid, L, coords, out, stream);  // persistent, loads one tile ahead (channels-last only)
-  if (pyramid_dtype == SLIMB200_DTYPE_BF16 && radius == 3 && g_lookup_generation == 2)
+  if (pyramid_dtype == SLIMB200_DTYPE_BF16 && radius == 3 && g_lookup_generation >= 2)
     return slimb200_lookup_v3_launch(pyramid, L, coords, out, out_layout, stream);
-  if (pyramid_dtype == SLIMB200_DTYPE_BF16 && radius == 3 && g_lookup_generation >= 1)
+  if (pyramid_dtype == SLIMB200_DTYPE_BF16 && radius == 3 && g_lookup_generation == 1)
     return slimb200_lookup_v2_launch(pyramid, L, coords, out, out_layout, stream);
   if (pyramid_dtype == SLIMB200_DTYPE_BF16) return dispatch_radius<__nv_bfloat16>(radius, out_layout, pyramid, L, coords, out, stream);
   if (pyramid_dtype == SLIMB200_DTYPE_F32) return dispatch_radius<float>(radius, out_layout, pyramid, L, coords, out, stream);

@@ -428,199 +428,6 @@ k_lookup_conv_tmem(const __nv_bfloat16* __restrict__ pyr, const LookupGeo G, con
   }
 }
 
-
-// ------------------------------------------------------------------------------------------------------------------
-// Fifth-generation STAND-ALONE lookup (channels-last output): the gather core of the kernel above without the tensor-core
-// part.  Persistent CTAs of 256 threads = 64 pixels x 4 levels, 2 CTAs per SM; a thread owns one (pixel, level) unit per
-// tile, its 16 window-row loads are cp.async copies into a private 256-byte shared-memory slot issued ONE TILE AHEAD (in two
-// halves, as soon as the half slot has been read out), so the DRAM latency of tile t + 1 runs under the blend and the stores
-// of tile t; every warp transposes its 32 units through its own shared-memory patch and writes the 196-byte channels-last
-// segments itself.  No barrier anywhere: warps drift freely.
-constexpr int V5_PIX = 64;
-constexpr int V5_THREADS = V5_PIX * G_LEVELS;  // 256
-constexpr int V5_SPLIT = 4 * WIN;              // the 49 values of a unit leave in two parts: window columns 0..3 (28), 4..6 (21)
-constexpr int V5_WPITCH = V5_SPLIT + 1;        // 29: odd pitch, conflict-free scalar stores
-constexpr uint32_t V5_ZONE_BYTES = V5_THREADS * G_SLOT_BYTES;  // 64 KB
-constexpr uint32_t V5_SMEM_BYTES = V5_ZONE_BYTES + (V5_THREADS / 32) * 32 * V5_WPITCH * 4 + 16;  // 94 KB: two CTAs per SM
-static_assert(2 * (V5_SMEM_BYTES + 1024) <= 233472, "two CTAs of the fifth-generation lookup must fit one SM");
-
-struct SinkPatch {
-  float* p;
-  __device__ __forceinline__ void emit(int k, float v) { p[k < V5_SPLIT ? k : k - V5_SPLIT] = v; }
-};
-
-__device__ __forceinline__ void load_slot_row5(uint32_t my_zone, int r, uint32_t (&raw)[8]) {
-#pragma unroll
-  for (int c = 0; c < 2; ++c)
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(raw[c * 4 + 0]), "=r"(raw[c * 4 + 1]), "=r"(raw[c * 4 + 2]), "=r"(raw[c * 4 + 3])
-                 : "r"(my_zone + (uint32_t)((r * 2 + c) * V5_THREADS) * 16u));
-}
-
-__global__ void __launch_bounds__(V5_THREADS, 2)
-k_corr_lookup_v5(const __nv_bfloat16* __restrict__ pyr, const LookupGeo G, const float* __restrict__ coords, float* __restrict__ out,
-                 int tiles_per_sample, int n_tiles) {
-  extern __shared__ __align__(16) uint8_t smem5[];
-  const uint32_t smem_zone = (smem_u32(smem5) + 15u) & ~15u;
-  float* const patches = reinterpret_cast<float*>(smem5 + (smem_zone - smem_u32(smem5)) + V5_ZONE_BYTES);
-  const int lane = lane_id(), warp = warp_id();
-  const int level = warp >> 1;
-  if (level >= G.levels) return;  // (no barrier in this kernel)
-  const int half_tile = warp & 1;
-  const int prow = half_tile * 32 + lane;
-  const int W = pick4(G.lw, level), H = pick4(G.lh, level), off = pick4(G.lo, level);
-  const float inv = 1.0f / (float)(1 << level);
-  const int panel_stride = G.m_tiles * 2 * 8192;
-  const int n_ch = G.levels * WIN * WIN;
-  const uint32_t my_zone = smem_zone + (uint32_t)threadIdx.x * 16u;  // chunk c of row r at + (r * 2 + c) * V5_THREADS * 16
-  float* const patch = patches + warp * (32 * V5_WPITCH);
-
-  struct Coord {
-    float cx, cy;
-    uint32_t base;
-    bool live;
-  };
-  auto load_coord = [&](int tile) {
-    Coord c;
-    const bool tile_ok = tile < n_tiles;
-    const int b = tile_ok ? tile / tiles_per_sample : 0, mt = tile_ok ? tile - b * tiles_per_sample : 0;
-    const int pix = mt * V5_PIX + prow;
-    c.live = tile_ok && pix < G.nf;
-    c.cx = c.live ? __ldg(coords + ((size_t)b * 2 + 0) * G.nf + pix) : 0.f;
-    c.cy = c.live ? __ldg(coords + ((size_t)b * 2 + 1) * G.nf + pix) : 0.f;
-    c.base = (uint32_t)pixel_base(G, b, c.live ? pix : 0);
-    return c;
-  };
-  auto taps = [&](Unit& u, const Coord& c) {
-    u.live = c.live;
-    u.cx = c.cx;
-    u.cy = c.cy;
-    u.base = c.base;
-    int xb, yb;
-    bool okx, oky;
-    axis_taps_compact(u.cx, inv, W, u.wx, u.inx, xb, u.sx, okx);
-    axis_taps_compact(u.cy, inv, H, u.wy, u.iny, yb, u.sy, oky);
-    u.mode = (okx && oky) ? ((u.sx | u.sy) ? 2 : 1) : 0;
-    u.row0 = off + max(min(yb, 1 << 18), -(1 << 18)) * W + max(min(xb, 1 << 18), -(1 << 18));
-  };
-  auto issue = [&](const Unit& u, int half) {  // (all 8 addresses first, then the 8 copies back to back)
-    const __nv_bfloat16* base = pyr + u.base;
-    const __nv_bfloat16* src[8];
-#pragma unroll
-    for (int rr = 0; rr < 4; ++rr) {
-      const int ca = (u.row0 + (half * 4 + rr) * W) & ~7;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) src[rr * 2 + c] = base + col_offset(min(max(ca + 8 * c, 0), G.pitch - 8), panel_stride);
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) cp_async16(my_zone + (uint32_t)((half * 8 + k) * V5_THREADS) * 16u, src[k]);
-    cp_async_commit();
-  };
-
-  // this warp's 32 units -> channels-last: values [k0, k0 + n) of every (pixel, level), n contiguous floats per pixel
-  auto flush = [&](float* dst, int n_pix, int k0, int n) {
-    __syncwarp();
-    if (lane < n)
-      for (int pp = 0; pp < n_pix; ++pp) dst[(size_t)pp * n_ch + k0 + lane] = patch[pp * V5_WPITCH + lane];
-    __syncwarp();  // the patch is rewritten by the next part
-  };
-
-  Unit cur;
-  int tile = blockIdx.x;
-  taps(cur, load_coord(tile));
-  issue(cur, 0);
-  issue(cur, 1);
-  Coord ahead = load_coord(tile + gridDim.x);
-  for (; tile < n_tiles; tile += gridDim.x) {
-    const int b = tile / tiles_per_sample, mt = tile - b * tiles_per_sample;
-    const int p0 = mt * V5_PIX + half_tile * 32;
-    const int n_pix = min(32, G.nf - p0);
-    float* const dst = out + ((size_t)b * G.nf + p0) * n_ch + level * (WIN * WIN);
-    const bool any_slow = __any_sync(FULL, cur.live && cur.mode == 0);
-    const bool any_shift = __any_sync(FULL, cur.live && cur.mode == 2);
-    Unit nxt;
-    taps(nxt, ahead);
-    ahead = load_coord(tile + 2 * gridDim.x);
-    SinkPatch sink{patch + lane * V5_WPITCH};
-    if (!any_slow && !any_shift) {
-      uint32_t win[8][4];
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        cp_async_wait_but_one();
-#pragma unroll
-        for (int r = half * 4; r < half * 4 + 4; ++r) {
-          uint32_t raw[8];
-          load_slot_row5(my_zone, r, raw);
-          realign<4>(raw, (cur.row0 + r * W) & 7, win[r]);
-        }
-        issue(nxt, half);
-      }
-      float e0[8], e1[8];
-#pragma unroll
-      for (int r = 0; r < 8; ++r) e0[r] = wel<4>(win[r], 0);
-#pragma unroll
-      for (int i = 0; i < WIN; ++i) {
-        const float wx0 = tap_w0(cur.wx[i], cur.inx, i), wx1 = tap_w1(cur.wx[i], cur.inx, i);
-        float h[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          e1[r] = wel<4>(win[r], i + 1);
-          h[r] = fmaf(e1[r], wx1, e0[r] * wx0);
-          e0[r] = e1[r];
-        }
-#pragma unroll
-        for (int j = 0; j < WIN; ++j)
-          sink.emit(i * WIN + j, fmaf(h[j + 1], tap_w1(cur.wy[j], cur.iny, j), h[j] * tap_w0(cur.wy[j], cur.iny, j)));
-        if (i == 3) flush(dst, n_pix, 0, V5_SPLIT);
-      }
-    } else {
-      uint32_t win[9][5];
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        cp_async_wait_but_one();
-#pragma unroll
-        for (int r = half * 4; r < half * 4 + 4; ++r) {
-          uint32_t raw[8];
-          load_slot_row5(my_zone, r, raw);
-          realign<5>(raw, (cur.row0 + r * W) & 7, win[r]);
-        }
-        issue(nxt, half);
-      }
-      {
-        uint32_t raw8[8];
-        const int sft8 = fetch_row(pyr + cur.base, panel_stride, G.pitch, cur.row0 + 8 * W, raw8);
-        realign<5>(raw8, sft8, win[8]);
-      }
-      const bool lane_slow = cur.live && cur.mode == 0;
-      const float swm1 = (float)(W - 1), shm1 = (float)(H - 1);
-      const float rw = __frcp_rn(swm1), rh = __frcp_rn(shm1);
-#pragma unroll
-      for (int i = 0; i < WIN; ++i) {
-        const bool s = (cur.sx >> i) & 1u;
-        const float wx0 = tap_w0(cur.wx[i], cur.inx, i), wx1 = tap_w1(cur.wx[i], cur.inx, i);
-        const float a = s ? 0.f : wx0, bq = s ? wx0 : wx1, c = s ? wx1 : 0.f;
-        float h[9];
-#pragma unroll
-        for (int r = 0; r < 9; ++r) h[r] = fmaf(wel<5>(win[r], i + 2), c, fmaf(wel<5>(win[r], i + 1), bq, wel<5>(win[r], i) * a));
-        const float ix = lane_slow ? sample_pos2(cur.cx, inv, i - R, swm1, rw) : 0.f;
-#pragma unroll
-        for (int j = 0; j < WIN; ++j) {
-          const bool t = (cur.sy >> j) & 1u;
-          const float wy0 = tap_w0(cur.wy[j], cur.iny, j), wy1 = tap_w1(cur.wy[j], cur.iny, j);
-          const float ay = t ? 0.f : wy0, by = t ? wy0 : wy1, cyw = t ? wy1 : 0.f;
-          float v = fmaf(h[j + 2], cyw, fmaf(h[j + 1], by, h[j] * ay));
-          if (lane_slow) v = sample_slow2(pyr + cur.base, panel_stride, W, H, off, ix, sample_pos2(cur.cy, inv, j - R, shm1, rh));
-          sink.emit(i * WIN + j, v);
-        }
-        if (i == 3) flush(dst, n_pix, 0, V5_SPLIT);
-      }
-    }
-    flush(dst, n_pix, V5_SPLIT, WIN * WIN - V5_SPLIT);
-    cur = nxt;
-  }
-  cp_async_wait_all();  // (the loads issued for a tile that does not exist)
-}
-
 }  // namespace
 
 // called by slimb200_corr_lookup_conv (csrc/corr_lookup3.cu); packed_w: the B image in K-slot order level * 56 + i * 7 + j
@@ -642,25 +449,5 @@ int slimb200_lookup_conv_tmem_launch(const void* pyramid, const slimb200_corr_la
                   (k_lookup_conv_tmem<<<grid, G_THREADS, g_smem_bytes(c_out), stream>>>(
                       static_cast<const __nv_bfloat16*>(pyramid), G, coords, static_cast<const uint8_t*>(packed_w), packed_bias, out,
                       out_pitch, c_out, relu, n_tiles)));
-  return SLIMB200_OK;
-}
-
-// radius-3 lookup on a bf16 pyramid into a channels-last tensor, fifth generation (called by slimb200_corr_lookup)
-int slimb200_lookup_v5_launch(const void* pyramid, const slimb200_corr_layout* L, const float* coords, float* out, cudaStream_t stream) {
-  LookupGeo G;
-  int rc = make_geo(L, &G);
-  if (rc != SLIMB200_OK) return rc;
-  SLIMB200_DEVICE(dev, n_sm);
-  static bool attr_set[SLIMB200_MAX_DEVICES] = {false};
-  if (!attr_set[dev]) {
-    SLIMB200_CUDA_TRY(cudaFuncSetAttribute(k_corr_lookup_v5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V5_SMEM_BYTES));
-    attr_set[dev] = true;
-  }
-  const int tiles_per_sample = (G.nf + V5_PIX - 1) / V5_PIX;
-  const int n_tiles = L->batch * tiles_per_sample;
-  const int grid = n_tiles < 2 * n_sm ? n_tiles : 2 * n_sm;
-  SLIMB200_LAUNCH(SLIMB200_K_CORR_LOOKUP, stream,
-                  (k_corr_lookup_v5<<<grid, V5_THREADS, V5_SMEM_BYTES, stream>>>(static_cast<const __nv_bfloat16*>(pyramid), G, coords, out,
-                                                                                 tiles_per_sample, n_tiles)));
   return SLIMB200_OK;
 }

@@ -167,7 +167,7 @@ def test_lookup_generations_agree(cuda, B, h, w, fmt):
             lib.slimb200_lookup_generation(0)
             old = blk(coords).cpu()
             scale = float(old.abs().max())
-            for generation in (1, 2, 3):  # (3: persistent kernel with loads one tile ahead; channels-last output only)
+            for generation in (1, 2):
                 lib.slimb200_lookup_generation(generation)
                 new = blk(coords)
                 assert new.is_contiguous(memory_format=torch.channels_last if fmt == "channels_last" else torch.contiguous_format)

@@ -103,9 +103,6 @@ def main():
         runs.append(("lookup gen0 nchw x6", gen(0, lambda: blk_c(coords))))
         runs.append(("lookup gen1 nchw x6", gen(1, lambda: blk_c(coords))))
         runs.append(("lookup gen1 nchw int x6", gen(1, lambda: blk_c(grid))))
-        runs.append(("lookup gen3 nhwc x6", gen(3, lambda: blk_l(coords))))
-        runs.append(("lookup gen3 nhwc int x6", gen(3, lambda: blk_l(grid))))
-        runs.append(("lookup gen1 nhwc int x6", gen(1, lambda: blk_l(grid))))
         runs.append(("lookup gen2 nhwc x6", gen(2, lambda: blk_l(coords))))
         runs.append(("lookup gen2 nchw x6", gen(2, lambda: blk_c(coords))))
         runs.append(("lookup gen2 nchw int x6", gen(2, lambda: blk_c(grid))))
